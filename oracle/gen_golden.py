@@ -1,0 +1,160 @@
+#!/usr/bin/env python3
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE: writes tests/golden/*.json.
+
+Runs the UNMODIFIED reference (oracle/_ref/refdrv, built by `make -C oracle ref` from the sources
+under /root/reference) on a fixed list of cases and stores, per case: the flat evaluated machine,
+the token sequences, and the reference's Forward / rolling Forward / Backward / Viterbi values,
+Viterbi traceback (global transition ids) and raw posterior counts at 17 significant digits.
+Where the reference's own test-suite pins a value for the case (t/expect/*, Makefile:492-572,
+js/webgpu/test/test-cpu.mjs:129-197) that published value is stored too under "ref_expect", so
+tests can check the oracle against the reference's goldens and not only against the binary.
+
+This needs /root/reference and therefore runs only in the build container; the fixtures are
+committed so nothing on the GPU box reads the reference.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+from helpers import synth_tokens  # noqa: E402
+
+REF = os.environ.get("MB_REFERENCE", "/root/reference")
+REFDRV = os.path.join(HERE, "_ref", "refdrv")
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+def run(args):
+    r = subprocess.run([REFDRV] + args, check=True, capture_output=True, text=True)
+    return json.loads(r.stdout)
+
+
+def machine_args(specs, params):
+    a = []
+    for s in specs:
+        a += ["--machine", s]
+    if params is not None:
+        f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+        json.dump(params, f)
+        f.close()
+        a += ["--params", f.name]
+    return a
+
+
+def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backward,counts", matrices=False,
+         ref_expect=None, note=""):
+    """pairs: list of (in_symbols, out_symbols) or ("synth", N, Li, Lo, seed)."""
+    margs = machine_args(specs, params)
+    mach = run(margs + ["--emit-machine"])
+    in_alpha, out_alpha = mach["inAlphabet"], mach["outAlphabet"]
+    sym_pairs = []
+    synth = None
+    if pairs and pairs[0] == "synth":
+        _, n, li, lo, seed = pairs
+        synth = {"n": n, "li": li, "lo": lo, "seed": seed}
+        for k in range(n):
+            x = synth_tokens(seed, k, 0, li if in_alpha else 0, max(1, len(in_alpha)))
+            y = synth_tokens(seed, k, 1, lo if out_alpha else 0, max(1, len(out_alpha)))
+            sym_pairs.append(([in_alpha[t - 1] for t in x], [out_alpha[t - 1] for t in y]))
+    else:
+        sym_pairs = [(list(a), list(b)) for a, b in pairs]
+    f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": a}, "output": {"name": "y%d" % k, "sequence": b}}
+               for k, (a, b) in enumerate(sym_pairs)], f)
+    f.close()
+    if matrices:
+        do = do + ",matrices"
+    res = run(margs + ["--pairs", f.name, "--do", do])
+    os.unlink(f.name)
+    in_tok = {s: i + 1 for i, s in enumerate(in_alpha)}
+    out_tok = {s: i + 1 for i, s in enumerate(out_alpha)}
+    out_pairs = []
+    for (a, b), r in zip(sym_pairs, res["pairs"]):
+        p = {"x": [in_tok.get(s, 0) for s in a], "y": [out_tok.get(s, 0) for s in b]}
+        p.update(r)
+        out_pairs.append(p)
+    j = {"name": name, "note": note, "specs": specs, "params": params, "machine": mach, "synth": synth,
+         "pairs": out_pairs, "loglike": res.get("loglike"), "counts": res.get("counts"),
+         "ref_expect": ref_expect or {}}
+    with open(os.path.join(OUT, name + ".json"), "w") as fo:
+        json.dump(j, fo, separators=(",", ":"))
+    print("%-28s S=%-5d T=%-6d pairs=%d" % (name, mach["nStates"], len(mach["trans"]), len(out_pairs)))
+
+
+def T(rel):
+    return "file:" + os.path.join(REF, rel)
+
+
+def expect_matrix(rel):
+    """t/expect/{fwd,back}-bitnoise-params-tiny.json: cells listed as {inPos,outPos,state,logLike}."""
+    with open(os.path.join(REF, rel)) as f:
+        txt = f.read()
+    # the reference prints non-JSON "-inf" for log(0) (dpmatrix.defs.h:52)
+    j = json.loads(txt.replace("-inf", '"-Infinity"'))
+    return [[c["inPos"], c["outPos"], c["logLike"]] for c in j["cell"]]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pq99 = {"p": 0.99, "q": 0.01}
+
+    # --- the reference's own DP goldens (Makefile:492-500, 515-516, 567-572) ---
+    with open(os.path.join(REF, "t/expect/fwdback-bitnoise-params-tiny.json")) as f:
+        fb = json.load(f)
+    case("bitnoise_tiny", [T("t/machine/bitnoise.json")], [("001", "101")], params=pq99, matrices=True,
+         ref_expect={"forward_matrix_5dp": expect_matrix("t/expect/fwd-bitnoise-params-tiny.json"),
+                     "backward_matrix_5dp": expect_matrix("t/expect/back-bitnoise-params-tiny.json"),
+                     "counts": fb[0], "loglike_4sf": -4.625},
+         note="Makefile:493-500,567 test-fwd/back/fb-bitnoise-params-tiny, test-101-bitnoise-001")
+    case("bitnoise_counts", [T("t/machine/bitnoise.json")], [("101", "001")], params=pq99,
+         ref_expect={"param_counts": {"p": 2, "q": 1}}, note="Makefile:518-522 test-counts / test-counts2")
+    with open(os.path.join(REF, "t/expect/align-stutter-noise-difflen.json")) as f:
+        al = json.load(f)
+    case("stutter_noise_difflen", [T("t/machine/bitstutter.json"), T("t/machine/bitnoise.json")], [("01", "101")],
+         params=pq99, matrices=True,
+         ref_expect={"path_to": [t["to"] for t in al[0]["meta"]["path"]["trans"]],
+                     "path_in": [t.get("in", "") for t in al[0]["meta"]["path"]["trans"]],
+                     "path_out": [t.get("out", "") for t in al[0]["meta"]["path"]["trans"]]},
+         note="Makefile:515-516 test-align-stutter-noise (boss a b -P params -D difflen -A)")
+    case("bitstutternoise_0011", [T("t/machine/bitstutter-noise.json")], [("101", "0011")], params=pq99,
+         ref_expect={"forward_3sf": -9.26, "viterbi_3sf": -9.27}, note="Makefile:570-572")
+    case("counter_xxx", [T("t/machine/counter.json")], [("", "xxx")], ref_expect={"param_counts": {"p": 3}},
+         note="Makefile:524-526 test-counts3")
+    # --- known answers quoted in js/webgpu/test/test-cpu.mjs:129-197 ("boss gives ...") ---
+    case("bitnoise_p09", [T("t/machine/bitnoise.json")], [("001", "101")], params={"p": 0.9, "q": 0.1},
+         ref_expect={"forward_1e-4": -2.51331, "viterbi_1e-4": -2.51331}, note="test-cpu.mjs:125-131,178-184")
+    case("bitnoise_p001", [T("t/machine/bitnoise.json")], [("001", "101")], params={"p": 0.01, "q": 0.99},
+         ref_expect={"forward_1e-4": -9.22039}, note="test-cpu.mjs:134-140")
+    case("bitecho", [T("t/machine/bitecho.json")], [("101", "101"), ("101", "001")],
+         ref_expect={"forward_exact": [0.0, "-Infinity"]}, note="test-cpu.mjs:145-162 (second pair is impossible: -inf)")
+    case("unitindel", [T("t/machine/unitindel.json")], [("xx", "xxx"), ("", ""), ("x", ""), ("", "x"), ("xxxx", "x")],
+         params={"ins": 0.1, "no_ins": 0.9, "del": 0.1, "no_del": 0.9}, matrices=True,
+         ref_expect={"forward_1e-3": -1.6869, "viterbi_1e-3": -2.82939}, note="test-cpu.mjs:167-197; plus empty / ragged pairs")
+
+    # --- presets at the BASELINE configs' machines, pinned by running the reference itself ---
+    case("dnapsw_small", ["preset:dnapsw"], [("ACGT", "ACGT"), ("", ""), ("A", ""), ("", "G"), ("ACGTACGTAC", "AGT"),
+                                             ("AAAAAAAA", "AAAAAAAA"), ("ACGT", "TGCA")], matrices=True,
+         note="tiny dnapsw incl. empty and ragged pairs and tie-heavy homopolymers; -U default params")
+    case("dnapsw_synth64", ["preset:dnapsw"], ("synth", 4, 64, 61, 101))
+    case("dnapsw_synth300", ["preset:dnapsw"], ("synth", 2, 300, 257, 102))
+    peaked = {"gapOpen": 0.05, "gapExtend": 0.5, "eqmA": 0.25, "eqmC": 0.25, "eqmG": 0.25, "eqmT": 0.25}
+    for a in "ACGT":
+        for b in "ACGT":
+            peaked["sub%s%s" % (a, b)] = 0.91 if a == b else 0.03
+    case("dnapsw_peaked", ["preset:dnapsw"], ("synth", 3, 120, 130, 103), params=peaked,
+         note="SURVEY 8(d) parameter set B (peaked), stresses the log-sum-exp cutoff")
+    case("protpsw_synth", ["preset:protpsw"], ("synth", 3, 50, 47, 104))
+    case("protpsw_300", ["preset:protpsw"], ("synth", 1, 300, 300, 105), do="forward,rolling,viterbi,path,backward,counts")
+    case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
+         note="config-4 style composite (S=308)")
+    case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
+    case("dnapsw_1k", ["preset:dnapsw"], ("synth", 1, 1000, 1000, 12345), do="rolling,viterbi,path",
+         note="BASELINE config 1: one 1 kb x 1 kb pair")
+
+
+if __name__ == "__main__":
+    main()

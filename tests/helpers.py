@@ -1,0 +1,203 @@
+"""Shared test helpers: flat machines, the numpy synthetic generator, ctypes bindings of the C oracle.
+
+Only tests (and smoke / the CPU-baseline legs of bench.py) may touch ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+ORACLE_DIR = os.path.join(REPO, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libmb_oracle.so")
+REFDRV = os.path.join(ORACLE_DIR, "_ref", "refdrv")
+
+NEG_INF = float("-inf")
+
+
+def _num(v):
+    if isinstance(v, str):
+        return {"-Infinity": NEG_INF, "Infinity": float("inf"), "NaN": float("nan")}[v]
+    return float(v)
+
+
+@dataclass
+class FlatMachine:
+    """Flat evaluated machine in the reference's enumeration order (src/eval.cpp:49-69)."""
+
+    n_states: int
+    n_in: int
+    n_out: int
+    src: np.ndarray
+    dst: np.ndarray
+    tin: np.ndarray
+    tout: np.ndarray
+    lw: np.ndarray
+    in_alphabet: list
+    out_alphabet: list
+
+    @property
+    def n_trans(self) -> int:
+        return int(self.src.shape[0])
+
+    @staticmethod
+    def from_json(j: dict) -> "FlatMachine":
+        t = j["trans"]
+        return FlatMachine(
+            n_states=int(j["nStates"]),
+            n_in=len(j["inAlphabet"]),
+            n_out=len(j["outAlphabet"]),
+            src=np.array([r[0] for r in t], dtype=np.int32),
+            dst=np.array([r[1] for r in t], dtype=np.int32),
+            tin=np.array([r[2] for r in t], dtype=np.int32),
+            tout=np.array([r[3] for r in t], dtype=np.int32),
+            lw=np.array([_num(r[4]) for r in t], dtype=np.float64),
+            in_alphabet=list(j["inAlphabet"]),
+            out_alphabet=list(j["outAlphabet"]),
+        )
+
+    def with_weights(self, lw: np.ndarray) -> "FlatMachine":
+        return FlatMachine(self.n_states, self.n_in, self.n_out, self.src, self.dst, self.tin, self.tout,
+                           np.ascontiguousarray(lw, dtype=np.float64), self.in_alphabet, self.out_alphabet)
+
+
+def load_golden(name: str) -> dict:
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        return json.load(f)
+
+
+def golden_names() -> list:
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic tokens: numpy restatement of oracle/synth.h (kept in the tests AND in bench.py)
+# ---------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def synth_tokens(seed: int, pair_index: int, which: int, length: int, n_sym: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        base = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+                + np.uint64(2 * pair_index + which) * np.uint64(0xD1B54A32D192ED03))
+        p = np.arange(length, dtype=np.uint64) + base
+    return (1 + (_splitmix64(p) % np.uint64(n_sym))).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# C oracle (oracle/libmb_oracle.so) over ctypes
+# ---------------------------------------------------------------------------------------------
+class _MboMachine(ctypes.Structure):
+    _fields_ = [("nStates", ctypes.c_int32), ("nInTok", ctypes.c_int32), ("nOutTok", ctypes.c_int32),
+                ("nTrans", ctypes.c_int64),
+                ("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("tin", ctypes.c_void_p),
+                ("tout", ctypes.c_void_p), ("lw", ctypes.c_void_p)]
+
+
+_oracle = None
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        lib = ctypes.CDLL(ORACLE_SO)
+        P, D, I64, U8 = ctypes.c_void_p, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p
+        lib.mbo_forward.restype = D
+        lib.mbo_forward.argtypes = [P, U8, I64, U8, I64, ctypes.c_int, P]
+        lib.mbo_backward.restype = D
+        lib.mbo_backward.argtypes = [P, U8, I64, U8, I64, ctypes.c_int, P]
+        lib.mbo_viterbi.restype = D
+        lib.mbo_viterbi.argtypes = [P, U8, I64, U8, I64, P, P, I64, P]
+        lib.mbo_counts.restype = D
+        lib.mbo_counts.argtypes = [P, U8, I64, U8, I64, ctypes.c_int, P, P]
+        lib.mbo_synth.restype = None
+        lib.mbo_synth.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, I64, ctypes.c_int, P]
+        lib.mbo_log_sum_exp.restype = D
+        lib.mbo_log_sum_exp.argtypes = [D, D, ctypes.c_int]
+        _oracle = lib
+    return _oracle
+
+
+LSE_TABLE, LSE_EXACT = 0, 1
+
+
+class Oracle:
+    """The C restatement bound to one flat machine."""
+
+    def __init__(self, m: FlatMachine):
+        self.m = m
+        self.lib = oracle_lib()
+        self._keep = [np.ascontiguousarray(a) for a in (m.src, m.dst, m.tin, m.tout, m.lw)]
+        self.c = _MboMachine(m.n_states, m.n_in, m.n_out, m.n_trans, *[a.ctypes.data for a in self._keep])
+
+    @staticmethod
+    def _tok(a):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        return a, a.ctypes.data if a.size else None
+
+    def forward(self, x, y, mode=LSE_TABLE, matrix=False):
+        x, xp = self._tok(x)
+        y, yp = self._tok(y)
+        mat = np.empty((len(y) + 1, len(x) + 1, self.m.n_states)) if matrix else None
+        ll = self.lib.mbo_forward(ctypes.byref(self.c), xp, len(x), yp, len(y), mode, mat.ctypes.data if matrix else None)
+        return (ll, mat) if matrix else ll
+
+    def backward(self, x, y, mode=LSE_TABLE, matrix=False):
+        x, xp = self._tok(x)
+        y, yp = self._tok(y)
+        mat = np.empty((len(y) + 1, len(x) + 1, self.m.n_states)) if matrix else None
+        ll = self.lib.mbo_backward(ctypes.byref(self.c), xp, len(x), yp, len(y), mode, mat.ctypes.data if matrix else None)
+        return (ll, mat) if matrix else ll
+
+    def viterbi(self, x, y, path=True, matrix=False):
+        x, xp = self._tok(x)
+        y, yp = self._tok(y)
+        mat = np.empty((len(y) + 1, len(x) + 1, self.m.n_states)) if matrix else None
+        cap = (len(x) + len(y) + 1) * max(1, self.m.n_states) + 1
+        buf = np.empty(cap, dtype=np.int32) if path else None
+        n = ctypes.c_int64(0)
+        sc = self.lib.mbo_viterbi(ctypes.byref(self.c), xp, len(x), yp, len(y), mat.ctypes.data if matrix else None,
+                                  buf.ctypes.data if path else None, cap, ctypes.byref(n))
+        out = [sc]
+        if path:
+            out.append(buf[: n.value].copy())
+        if matrix:
+            out.append(mat)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def counts(self, x, y, mode=LSE_TABLE, counts=None):
+        x, xp = self._tok(x)
+        y, yp = self._tok(y)
+        if counts is None:
+            counts = np.zeros(self.m.n_trans)
+        bll = ctypes.c_double(0)
+        fll = self.lib.mbo_counts(ctypes.byref(self.c), xp, len(x), yp, len(y), mode, counts.ctypes.data, ctypes.byref(bll))
+        return fll, bll.value, counts
+
+
+def pairs_from_golden(case: dict):
+    return [(np.array(p["x"], dtype=np.uint8), np.array(p["y"], dtype=np.uint8)) for p in case["pairs"]]
+
+
+def gnum(v):
+    return _num(v)
