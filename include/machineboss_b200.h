@@ -1,0 +1,98 @@
+/* machineboss_b200.h -- C ABI of the B200-native Forward / Backward / Viterbi engine.
+ *
+ * The reference (evoldoers/machineboss) has no FFI for this path: its boundary is the C++ class
+ * surface  EvaluatedMachine / SeqPair(List) / ForwardMatrix / BackwardMatrix / ViterbiMatrix /
+ * MachineCounts  (SURVEY.md section 8b).  This header is the C-ABI layer underneath a host-side
+ * mirror of those classes (machineboss_b200/host/boss_b200.h); every entry point names the
+ * reference interface it replaces.  Plain pointers and sizes only; the caller owns every host
+ * buffer; handles own device memory.  All functions return 0 on success, non-zero on error, with
+ * the message available from mb_last_error().  There is no CPU fallback: without a CUDA device
+ * every compute call fails.
+ *
+ * Conventions shared with the reference:
+ *   - states 0..nStates-1; start state 0, end state nStates-1          (src/eval.cpp:76-84)
+ *   - token 0 is epsilon; input tokens 1..nInTok, output tokens 1..nOutTok, numbered in
+ *     alphabetical order of the alphabets                              (src/eval.h:11-25, machine.cpp:175-191)
+ *   - transitions are listed in the reference's enumeration order: source state ascending, then
+ *     position in the source's TransList, so global id = transOffset[src] + transIndex
+ *                                                                      (src/eval.cpp:49-69)
+ *   - log-weights are natural-log doubles, -inf allowed                (src/eval.cpp:58)
+ */
+#ifndef MACHINEBOSS_B200_H
+#define MACHINEBOSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_machine mb_machine;
+typedef struct mb_batch mb_batch;
+
+/* ---- library state ---- */
+const char* mb_last_error (void);                 /* message of the last failing call on this thread */
+int mb_version (void);
+int mb_device_count (int* count);                  /* cudaGetDeviceCount */
+int mb_set_device (int device);                    /* device used by handles created afterwards (default 0) */
+
+/* ---- EvaluatedMachine (src/eval.h:59-98, src/eval.cpp:42-70) ----
+ * Flattens what EvaluatedMachine::init builds: per transition its source, destination, input
+ * token, output token and log-weight, in enumeration order.  Fails, like the reference's
+ * Assert(isAdvancingMachine) (eval.cpp:44, machine.cpp:758-764), if a silent transition from a
+ * state s >= 1 goes to a state <= s. */
+int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                       const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
+                       const double* logWeight);
+/* New log-weights for the same structure: what re-running EvaluatedMachine(machine, params) does
+ * once per EM iteration (src/fitter.cpp:29). */
+int mb_machine_update_weights (mb_machine* m, const double* logWeight);
+int mb_machine_info (const mb_machine* m, int32_t* nStates, int64_t* nTrans, int32_t* engine /* MB_ENGINE_* */);
+void mb_machine_destroy (mb_machine* m);
+
+#define MB_ENGINE_GENERIC 0   /* anti-diagonal wavefront over the CSR machine, any size */
+#define MB_ENGINE_JIT     1   /* machine-specialised strip kernel compiled with NVRTC, small machines */
+/* Force an engine for machines created afterwards (-1 = choose automatically, the default). */
+int mb_set_engine (int engine);
+
+/* ---- SeqPairList (src/seqpair.h:18-73,115-121), already tokenised (DPMatrix ctor, dpmatrix.defs.h:6-7) ----
+ * Pair k has input tokens inTokens[inOff[k] .. inOff[k+1]) and output tokens
+ * outTokens[outOff[k] .. outOff[k+1]).  Tokens are 1-based (0 never appears in data).  The batch is
+ * copied to the device; full envelopes only (SeqPair without an alignment, seqpair.cpp:104-110). */
+int mb_batch_create (mb_batch** out, int64_t nPairs,
+                     const uint8_t* inTokens, const int64_t* inOff,
+                     const uint8_t* outTokens, const int64_t* outOff);
+void mb_batch_destroy (mb_batch* b);
+
+/* ---- RollingOutputForwardMatrix::logLike / ForwardMatrix::logLike (src/forward.defs.h:22-55) ----
+ * loglike[k] = log-sum over all paths of pair k, -inf if none. */
+int mb_forward (mb_machine* m, mb_batch* b, double* loglike);
+
+/* ---- BackwardMatrix::logLike (src/backward.cpp:18-50) ---- */
+int mb_backward (mb_machine* m, mb_batch* b, double* loglike);
+
+/* ---- ViterbiMatrix::logLike + ViterbiMatrix::path (src/viterbi.cpp:18-51, dpmatrix.defs.h:82-110) ----
+ * score[k] = best path log-weight.  If pathLen != NULL the traceback is run too and pathLen[k]
+ * receives the number of transitions on pair k's path (0 when score[k] is -inf, as boss.cpp:831
+ * skips those).  The tie-break is the reference's: candidates in the order match, delete, insert,
+ * silent, each by ascending source state then transition index; the first maximum wins. */
+int mb_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+/* Copies the paths of the last mb_viterbi on this batch: pair k's global transition ids, start ->
+ * end, go to pathTrans[pathOff[k] .. pathOff[k] + pathLen[k]). */
+int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff);
+
+/* ---- MachineCounts over a list (src/counts.cpp:37-64, src/backward.cpp:62-87) ----
+ * counts[t] (t < nTrans, may be NULL) receives the expected number of uses of transition t summed
+ * over all pairs; loglike[k] (may be NULL) the Forward log-likelihood of pair k.  Pairs whose
+ * log-likelihood is -inf contribute nothing. */
+int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+
+/* ---- measurement hooks (not part of the reference surface) ----
+ * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
+ * (CUDA events on the launching stream), and how many kernels that was. */
+int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACHINEBOSS_B200_H */

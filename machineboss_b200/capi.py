@@ -1,0 +1,202 @@
+"""ctypes binding of the C ABI in include/machineboss_b200.h.
+
+This is plumbing for tests, bench.py and the Python convenience layer; the product is the shared
+library.  There is no fallback: if the library is missing it is built with nvcc, and if that
+fails, or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+ENGINE_GENERIC, ENGINE_JIT = 0, 1
+
+_lib = None
+
+# every symbol include/machineboss_b200.h declares
+SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
+           "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
+           "mb_batch_create", "mb_batch_destroy", "mb_forward", "mb_backward", "mb_viterbi",
+           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms"]
+
+
+class MachineBossError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = ctypes.CDLL(path)
+        P, I32, I64, D = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+        L.mb_last_error.restype = ctypes.c_char_p
+        L.mb_last_error.argtypes = []
+        L.mb_version.restype = ctypes.c_int
+        L.mb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+        L.mb_set_device.argtypes = [ctypes.c_int]
+        L.mb_set_engine.argtypes = [ctypes.c_int]
+        L.mb_machine_create.argtypes = [ctypes.POINTER(P), I32, I32, I32, I64, P, P, P, P, P]
+        L.mb_machine_update_weights.argtypes = [P, P]
+        L.mb_machine_info.argtypes = [P, ctypes.POINTER(I32), ctypes.POINTER(I64), ctypes.POINTER(I32)]
+        L.mb_machine_destroy.argtypes = [P]
+        L.mb_machine_destroy.restype = None
+        L.mb_batch_create.argtypes = [ctypes.POINTER(P), I64, P, P, P, P]
+        L.mb_batch_destroy.argtypes = [P]
+        L.mb_batch_destroy.restype = None
+        L.mb_forward.argtypes = [P, P, P]
+        L.mb_backward.argtypes = [P, P, P]
+        L.mb_viterbi.argtypes = [P, P, P, P]
+        L.mb_viterbi_paths.argtypes = [P, P, P]
+        L.mb_counts.argtypes = [P, P, P, P]
+        L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MachineBossError(lib().mb_last_error().decode())
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    _check(lib().mb_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def set_device(d: int) -> None:
+    _check(lib().mb_set_device(d))
+
+
+def set_engine(e: int) -> None:
+    _check(lib().mb_set_engine(e))
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else None
+
+
+class Machine:
+    """Handle on a flattened EvaluatedMachine (src/eval.h:78-98) living on the device."""
+
+    def __init__(self, n_states, n_in, n_out, src, dst, tin, tout, log_weight):
+        self.n_states, self.n_in, self.n_out = int(n_states), int(n_in), int(n_out)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
+        lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+        self.n_trans = int(lw.shape[0])
+        self.h = ctypes.c_void_p()
+        _check(lib().mb_machine_create(ctypes.byref(self.h), self.n_states, self.n_in, self.n_out, self.n_trans,
+                                       *[_ptr(a) for a in arrs], _ptr(lw)))
+
+    @property
+    def engine(self) -> int:
+        e = ctypes.c_int32(0)
+        _check(lib().mb_machine_info(self.h, None, None, ctypes.byref(e)))
+        return e.value
+
+    def update_weights(self, log_weight) -> None:
+        lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+        assert lw.shape[0] == self.n_trans
+        _check(lib().mb_machine_update_weights(self.h, _ptr(lw)))
+
+    def close(self):
+        if self.h:
+            lib().mb_machine_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Handle on a tokenised SeqPairList (src/seqpair.h:115-121) living on the device."""
+
+    def __init__(self, pairs=None, *, x=None, x_off=None, y=None, y_off=None):
+        if pairs is not None:
+            xs = [np.asarray(p[0], dtype=np.uint8) for p in pairs]
+            ys = [np.asarray(p[1], dtype=np.uint8) for p in pairs]
+            x = np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+            y = np.concatenate(ys) if ys else np.zeros(0, np.uint8)
+            x_off = np.concatenate([[0], np.cumsum([len(a) for a in xs])]).astype(np.int64)
+            y_off = np.concatenate([[0], np.cumsum([len(a) for a in ys])]).astype(np.int64)
+        self.x = np.ascontiguousarray(x, dtype=np.uint8)
+        self.y = np.ascontiguousarray(y, dtype=np.uint8)
+        self.x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+        self.y_off = np.ascontiguousarray(y_off, dtype=np.int64)
+        self.n_pairs = int(self.x_off.shape[0]) - 1
+        self.h = ctypes.c_void_p()
+        _check(lib().mb_batch_create(ctypes.byref(self.h), self.n_pairs, _ptr(self.x), _ptr(self.x_off),
+                                     _ptr(self.y), _ptr(self.y_off)))
+
+    def cell_states(self, n_states: int) -> float:
+        li = np.diff(self.x_off).astype(np.float64)
+        lo = np.diff(self.y_off).astype(np.float64)
+        return float(((li + 1) * (lo + 1)).sum() * n_states)
+
+    def last_kernel_ms(self):
+        ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+        _check(lib().mb_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def close(self):
+        if self.h:
+            lib().mb_batch_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def forward(m: Machine, b: Batch) -> np.ndarray:
+    out = np.empty(b.n_pairs, dtype=np.float64)
+    _check(lib().mb_forward(m.h, b.h, _ptr(out)))
+    return out
+
+
+def backward(m: Machine, b: Batch) -> np.ndarray:
+    out = np.empty(b.n_pairs, dtype=np.float64)
+    _check(lib().mb_backward(m.h, b.h, _ptr(out)))
+    return out
+
+
+def viterbi_lengths(m: Machine, b: Batch):
+    """Viterbi scores + traceback on the device; returns (score, path lengths), paths stay on the device."""
+    score = np.empty(b.n_pairs, dtype=np.float64)
+    plen = np.zeros(b.n_pairs, dtype=np.int64)
+    _check(lib().mb_viterbi(m.h, b.h, _ptr(score), _ptr(plen)))
+    return score, plen
+
+
+def viterbi(m: Machine, b: Batch, paths: bool = True, packed: bool = False):
+    """ViterbiMatrix::logLike (+ ::path).  paths: list of int32 arrays of global transition ids,
+    or with packed=True the pair (all ids concatenated, offsets[nPairs+1])."""
+    if not paths:
+        score = np.empty(b.n_pairs, dtype=np.float64)
+        _check(lib().mb_viterbi(m.h, b.h, _ptr(score), None))
+        return score
+    score, plen = viterbi_lengths(m, b)
+    off = np.concatenate([[0], np.cumsum(plen)]).astype(np.int64)
+    trans = np.empty(int(off[-1]), dtype=np.int32)
+    if off[-1]:
+        _check(lib().mb_viterbi_paths(b.h, _ptr(trans), _ptr(off)))
+    if packed:
+        return score, (trans, off)
+    return score, [trans[off[k]:off[k + 1]] for k in range(b.n_pairs)]
+
+
+def counts(m: Machine, b: Batch):
+    c = np.zeros(m.n_trans, dtype=np.float64)
+    ll = np.empty(b.n_pairs, dtype=np.float64)
+    _check(lib().mb_counts(m.h, b.h, _ptr(c), _ptr(ll)))
+    return c, ll

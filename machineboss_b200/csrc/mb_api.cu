@@ -1,0 +1,332 @@
+// mb_api.cu -- the C ABI declared in include/machineboss_b200.h: handle management, the host-side
+// flattening of the evaluated machine (what EvaluatedMachine::init builds, src/eval.cpp:42-70) and
+// dispatch to the engines.  No compute happens on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "mb_internal.h"
+
+namespace mb {
+
+static thread_local std::string g_error;
+static int g_device = 0;
+static int g_forceEngine = -1;
+
+void set_error (const std::string& msg) { g_error = msg; }
+
+bool cuda_ok (cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error (std::string ("CUDA error: ") + cudaGetErrorString (e) + " in " + what);
+  return false;
+}
+
+int timing_begin (mb_batch* b) {
+  b->lastMs = 0;
+  b->lastLaunches = 0;
+  MB_CUDA (cudaEventRecord (b->evStart, b->stream));
+  return 0;
+}
+
+int timing_end (mb_batch* b, int64_t launches) {
+  MB_CUDA (cudaEventRecord (b->evStop, b->stream));
+  MB_CUDA (cudaEventSynchronize (b->evStop));
+  float ms = 0;
+  MB_CUDA (cudaEventElapsedTime (&ms, b->evStart, b->evStop));
+  b->lastMs = ms;
+  b->lastLaunches = launches;
+  return 0;
+}
+
+// Stable counting sort of the transitions into token-indexed lists (see DevCsr).
+static void build_csr (const mb_machine* m, bool incoming, HostCsr& c) {
+  const int64_t T = m->T;
+  const int nIn1 = m->nIn + 1, nOut1 = m->nOut + 1;
+  const int64_t nKeys = (int64_t) m->S * nIn1 * nOut1;
+  auto keyOf = [&] (int64_t t) {
+    const int st = incoming ? m->dst[t] : m->src[t];
+    return ((int64_t) st * nIn1 + m->in[t]) * nOut1 + m->out[t];
+  };
+  std::vector<int64_t> order ((size_t) T);
+  for (int64_t t = 0; t < T; ++t) order[t] = t;
+  if (!incoming)   // destination ascending, ties by id; ids already ascend with the source state
+    std::stable_sort (order.begin(), order.end(), [&] (int64_t a, int64_t b) { return m->dst[a] < m->dst[b]; });
+  c.off.assign ((size_t) nKeys + 1, 0);
+  for (int64_t t = 0; t < T; ++t) c.off[keyOf (t) + 1]++;
+  for (int64_t k = 0; k < nKeys; ++k) c.off[k + 1] += c.off[k];
+  std::vector<int64_t> pos (c.off.begin(), c.off.end() - 1);
+  c.other.resize ((size_t) T);
+  c.id.resize ((size_t) T);
+  c.lw.resize ((size_t) T);
+  for (int64_t n = 0; n < T; ++n) {
+    const int64_t t = order[n];
+    const int64_t p = pos[keyOf (t)]++;
+    c.other[p] = incoming ? m->src[t] : m->dst[t];
+    c.id[p] = (int32_t) t;
+    c.lw[p] = m->lw[t];
+  }
+}
+
+static void build_levels (const mb_machine* m, bool forward, std::vector<int32_t>& off, std::vector<int32_t>& states) {
+  const int S = m->S;
+  std::vector<int32_t> level ((size_t) S, 0);
+  // silent transitions go to strictly higher states (checked at creation), so one ordered pass suffices
+  std::vector<std::vector<int32_t>> silentTo ((size_t) S);   // forward: sources of silent edges into s; backward: destinations out of s
+  for (int64_t t = 0; t < m->T; ++t)
+    if (m->in[t] == 0 && m->out[t] == 0 && m->src[t] < m->dst[t]) {
+      if (forward) silentTo[m->dst[t]].push_back (m->src[t]);
+      else silentTo[m->src[t]].push_back (m->dst[t]);
+    }
+  int maxLevel = 0;
+  if (forward)
+    for (int s = 0; s < S; ++s) { for (int p: silentTo[s]) level[s] = std::max (level[s], level[p] + 1); maxLevel = std::max (maxLevel, level[s]); }
+  else
+    for (int s = S - 1; s >= 0; --s) { for (int p: silentTo[s]) level[s] = std::max (level[s], level[p] + 1); maxLevel = std::max (maxLevel, level[s]); }
+  off.assign ((size_t) maxLevel + 2, 0);
+  for (int s = 0; s < S; ++s) off[level[s] + 1]++;
+  for (int l = 0; l <= maxLevel; ++l) off[l + 1] += off[l];
+  states.resize ((size_t) S);
+  std::vector<int32_t> pos (off.begin(), off.end() - 1);
+  for (int s = 0; s < S; ++s) states[pos[level[s]]++] = s;
+}
+
+template<class T> static size_t blob_reserve (size_t& bytes, const std::vector<T>& v) {
+  const size_t at = (bytes + 255) & ~(size_t) 255;
+  bytes = at + std::max<size_t> (v.size(), 1) * sizeof (T);
+  return at;
+}
+
+static int upload_machine (mb_machine* m) {
+  size_t bytes = 0;
+  const size_t oIncOff = blob_reserve (bytes, m->hInc.off), oIncOther = blob_reserve (bytes, m->hInc.other),
+    oIncId = blob_reserve (bytes, m->hInc.id), oIncLw = blob_reserve (bytes, m->hInc.lw),
+    oOutOff = blob_reserve (bytes, m->hOut.off), oOutOther = blob_reserve (bytes, m->hOut.other),
+    oOutId = blob_reserve (bytes, m->hOut.id), oOutLw = blob_reserve (bytes, m->hOut.lw),
+    oFLO = blob_reserve (bytes, m->fwdLevelOff), oFLS = blob_reserve (bytes, m->fwdLevelStates),
+    oBLO = blob_reserve (bytes, m->bwdLevelOff), oBLS = blob_reserve (bytes, m->bwdLevelStates);
+  std::vector<char> host (bytes, 0);
+  auto put = [&] (size_t at, const void* p, size_t n) { if (n) memcpy (host.data() + at, p, n); };
+  put (oIncOff, m->hInc.off.data(), m->hInc.off.size() * 8); put (oIncOther, m->hInc.other.data(), m->hInc.other.size() * 4);
+  put (oIncId, m->hInc.id.data(), m->hInc.id.size() * 4); put (oIncLw, m->hInc.lw.data(), m->hInc.lw.size() * 8);
+  put (oOutOff, m->hOut.off.data(), m->hOut.off.size() * 8); put (oOutOther, m->hOut.other.data(), m->hOut.other.size() * 4);
+  put (oOutId, m->hOut.id.data(), m->hOut.id.size() * 4); put (oOutLw, m->hOut.lw.data(), m->hOut.lw.size() * 8);
+  put (oFLO, m->fwdLevelOff.data(), m->fwdLevelOff.size() * 4); put (oFLS, m->fwdLevelStates.data(), m->fwdLevelStates.size() * 4);
+  put (oBLO, m->bwdLevelOff.data(), m->bwdLevelOff.size() * 4); put (oBLS, m->bwdLevelStates.data(), m->bwdLevelStates.size() * 4);
+  MB_CUDA (cudaSetDevice (m->device));
+  MB_CUDA (cudaMalloc (&m->dBlob, bytes));
+  MB_CUDA (cudaMemcpy (m->dBlob, host.data(), bytes, cudaMemcpyHostToDevice));
+  m->blobBytes = bytes;
+  m->incLwOffset = oIncLw;
+  m->outLwOffset = oOutLw;
+  char* d = (char*) m->dBlob;
+  DevMachine& dm = m->dev;
+  dm.S = m->S; dm.nIn1 = m->nIn + 1; dm.nOut1 = m->nOut + 1;
+  dm.inc = { (const int64_t*) (d + oIncOff), (const int32_t*) (d + oIncOther), (const int32_t*) (d + oIncId), (const double*) (d + oIncLw) };
+  dm.out = { (const int64_t*) (d + oOutOff), (const int32_t*) (d + oOutOther), (const int32_t*) (d + oOutId), (const double*) (d + oOutLw) };
+  dm.nFwdLevels = (int32_t) m->fwdLevelOff.size() - 1;
+  dm.nBwdLevels = (int32_t) m->bwdLevelOff.size() - 1;
+  dm.fwdLevelOff = (const int32_t*) (d + oFLO); dm.fwdLevelStates = (const int32_t*) (d + oFLS);
+  dm.bwdLevelOff = (const int32_t*) (d + oBLO); dm.bwdLevelStates = (const int32_t*) (d + oBLS);
+  return 0;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+const char* mb_last_error (void) { return g_error.c_str(); }
+int mb_version (void) { return 100; }
+
+int mb_device_count (int* count) {
+  MB_CUDA (cudaGetDeviceCount (count));
+  return 0;
+}
+
+int mb_set_device (int device) {
+  MB_CUDA (cudaSetDevice (device));
+  g_device = device;
+  return 0;
+}
+
+int mb_set_engine (int engine) {
+  if (engine < -1 || engine > MB_ENGINE_JIT) { set_error ("mb_set_engine: unknown engine"); return 1; }
+  g_forceEngine = engine;
+  return 0;
+}
+
+int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                       const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
+                       const double* logWeight) {
+  if (!out) { set_error ("mb_machine_create: null output"); return 1; }
+  *out = nullptr;
+  if (nStates < 1) { set_error ("EvaluatedMachine has no states"); return 1; }   // eval.cpp:77
+  if (nInTok < 0 || nOutTok < 0 || nInTok > 255 || nOutTok > 255) { set_error ("mb_machine_create: alphabets must have 0..255 symbols"); return 1; }
+  if (nTrans < 0 || nTrans > 0x7fffffff) { set_error ("mb_machine_create: bad transition count"); return 1; }
+  for (int64_t t = 0; t < nTrans; ++t) {
+    if (src[t] < 0 || src[t] >= nStates || dst[t] < 0 || dst[t] >= nStates || inTok[t] < 0 || inTok[t] > nInTok || outTok[t] < 0 || outTok[t] > nOutTok) {
+      set_error ("mb_machine_create: transition " + std::to_string (t) + " is out of range"); return 1;
+    }
+    if (t && src[t] < src[t - 1]) { set_error ("mb_machine_create: transitions must be listed by ascending source state (eval.cpp:49-69)"); return 1; }
+    // machine.cpp:758-764 isAdvancingMachine, asserted at eval.cpp:44 (state 0 is not checked there)
+    if (src[t] >= 1 && inTok[t] == 0 && outTok[t] == 0 && dst[t] <= src[t]) { set_error ("Machine is not topologically sorted"); return 1; }
+  }
+  mb_machine* m = new mb_machine;
+  m->device = g_device;
+  m->S = nStates; m->nIn = nInTok; m->nOut = nOutTok; m->T = nTrans;
+  m->src.assign (src, src + nTrans); m->dst.assign (dst, dst + nTrans);
+  m->in.assign (inTok, inTok + nTrans); m->out.assign (outTok, outTok + nTrans);
+  m->lw.assign (logWeight, logWeight + nTrans);
+  build_csr (m, true, m->hInc);
+  build_csr (m, false, m->hOut);
+  build_levels (m, true, m->fwdLevelOff, m->fwdLevelStates);
+  build_levels (m, false, m->bwdLevelOff, m->bwdLevelStates);
+  if (upload_machine (m)) { mb_machine_destroy (m); return 1; }
+  std::string why;
+  const bool wantJit = g_forceEngine == MB_ENGINE_JIT || (g_forceEngine < 0 && jit_supported (m, &why));
+  if (wantJit) {
+    if (!jit_supported (m, &why)) { set_error ("mb_set_engine(JIT): " + why); mb_machine_destroy (m); return 1; }
+    if (jit_prepare (m)) { mb_machine_destroy (m); return 1; }
+    m->engine = MB_ENGINE_JIT;
+  }
+  *out = m;
+  return 0;
+}
+
+int mb_machine_update_weights (mb_machine* m, const double* logWeight) {
+  if (!m) { set_error ("null machine"); return 1; }
+  m->lw.assign (logWeight, logWeight + m->T);
+  for (int64_t p = 0; p < m->T; ++p) { m->hInc.lw[p] = m->lw[m->hInc.id[p]]; m->hOut.lw[p] = m->lw[m->hOut.id[p]]; }
+  MB_CUDA (cudaSetDevice (m->device));
+  if (m->T) {
+    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
+    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
+  }
+  if (m->engine == MB_ENGINE_JIT) return jit_update_weights (m);
+  return 0;
+}
+
+int mb_machine_info (const mb_machine* m, int32_t* nStates, int64_t* nTrans, int32_t* engine) {
+  if (!m) { set_error ("null machine"); return 1; }
+  if (nStates) *nStates = m->S;
+  if (nTrans) *nTrans = m->T;
+  if (engine) *engine = m->engine;
+  return 0;
+}
+
+void mb_machine_destroy (mb_machine* m) {
+  if (!m) return;
+  cudaSetDevice (m->device);
+  jit_destroy (m);
+  if (m->dBlob) cudaFree (m->dBlob);
+  delete m;
+}
+
+int mb_batch_create (mb_batch** out, int64_t nPairs, const uint8_t* inTokens, const int64_t* inOff,
+                     const uint8_t* outTokens, const int64_t* outOff) {
+  if (!out) { set_error ("mb_batch_create: null output"); return 1; }
+  *out = nullptr;
+  if (nPairs < 0) { set_error ("mb_batch_create: negative pair count"); return 1; }
+  for (int64_t k = 0; k < nPairs; ++k)
+    if (inOff[k + 1] < inOff[k] || outOff[k + 1] < outOff[k]) { set_error ("mb_batch_create: offsets must be non-decreasing"); return 1; }
+  mb_batch* b = new mb_batch;
+  b->device = g_device;
+  b->nPairs = nPairs;
+  b->xOff.assign (inOff, inOff + nPairs + 1);
+  b->yOff.assign (outOff, outOff + nPairs + 1);
+  const size_t nx = (size_t) (b->xOff[nPairs] - b->xOff[0]), ny = (size_t) (b->yOff[nPairs] - b->yOff[0]);
+  const int64_t x0 = b->xOff[0], y0 = b->yOff[0];
+  for (auto& v: b->xOff) v -= x0;
+  for (auto& v: b->yOff) v -= y0;
+  auto fail = [&] () { mb_batch_destroy (b); return 1; };
+  if (!cuda_ok (cudaSetDevice (b->device), "cudaSetDevice")) return fail();
+  if (!cuda_ok (cudaStreamCreateWithFlags (&b->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail();
+  if (!cuda_ok (cudaEventCreate (&b->evStart), "cudaEventCreate") || !cuda_ok (cudaEventCreate (&b->evStop), "cudaEventCreate")) return fail();
+  // 16 bytes of slack so kernels may read whole words past the last token
+  if (!cuda_ok (cudaMalloc (&b->dX, nx + 16), "cudaMalloc") || !cuda_ok (cudaMalloc (&b->dY, ny + 16), "cudaMalloc")
+      || !cuda_ok (cudaMalloc (&b->dXOff, (size_t) (nPairs + 1) * 8), "cudaMalloc") || !cuda_ok (cudaMalloc (&b->dYOff, (size_t) (nPairs + 1) * 8), "cudaMalloc"))
+    return fail();
+  if (!cuda_ok (cudaMemsetAsync (b->dX, 1, nx + 16, b->stream), "memset") || !cuda_ok (cudaMemsetAsync (b->dY, 1, ny + 16, b->stream), "memset")) return fail();
+  if (nx && !cuda_ok (cudaMemcpyAsync (b->dX, inTokens + x0, nx, cudaMemcpyHostToDevice, b->stream), "H2D tokens")) return fail();
+  if (ny && !cuda_ok (cudaMemcpyAsync (b->dY, outTokens + y0, ny, cudaMemcpyHostToDevice, b->stream), "H2D tokens")) return fail();
+  if (!cuda_ok (cudaMemcpyAsync (b->dXOff, b->xOff.data(), (size_t) (nPairs + 1) * 8, cudaMemcpyHostToDevice, b->stream), "H2D offsets")
+      || !cuda_ok (cudaMemcpyAsync (b->dYOff, b->yOff.data(), (size_t) (nPairs + 1) * 8, cudaMemcpyHostToDevice, b->stream), "H2D offsets"))
+    return fail();
+  if (!cuda_ok (cudaStreamSynchronize (b->stream), "sync")) return fail();
+  b->dev = { nPairs, b->dX, b->dXOff, b->dY, b->dYOff };
+  *out = b;
+  return 0;
+}
+
+void mb_batch_destroy (mb_batch* b) {
+  if (!b) return;
+  cudaSetDevice (b->device);
+  if (b->dX) cudaFree (b->dX);
+  if (b->dY) cudaFree (b->dY);
+  if (b->dXOff) cudaFree (b->dXOff);
+  if (b->dYOff) cudaFree (b->dYOff);
+  if (b->dPaths) cudaFree (b->dPaths);
+  if (b->evStart) cudaEventDestroy (b->evStart);
+  if (b->evStop) cudaEventDestroy (b->evStop);
+  if (b->stream) cudaStreamDestroy (b->stream);
+  delete b;
+}
+
+static int check_call (const mb_machine* m, const mb_batch* b) {
+  if (!m || !b) { set_error ("null handle"); return 1; }
+  if (m->device != b->device) { set_error ("machine and batch live on different devices"); return 1; }
+  MB_CUDA (cudaSetDevice (m->device));
+  return 0;
+}
+
+int mb_forward (mb_machine* m, mb_batch* b, double* loglike) {
+  if (check_call (m, b)) return 1;
+  return m->engine == MB_ENGINE_JIT ? jit_forward (m, b, loglike, false) : generic_forward (m, b, loglike, false);
+}
+
+int mb_backward (mb_machine* m, mb_batch* b, double* loglike) {
+  if (check_call (m, b)) return 1;
+  return m->engine == MB_ENGINE_JIT ? jit_forward (m, b, loglike, true) : generic_forward (m, b, loglike, true);
+}
+
+int mb_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
+  if (check_call (m, b)) return 1;
+  return m->engine == MB_ENGINE_JIT ? jit_viterbi (m, b, score, pathLen) : generic_viterbi (m, b, score, pathLen);
+}
+
+int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if ((int64_t) b->pathLen.size() != b->nPairs) { set_error ("mb_viterbi_paths: no traceback stored; call mb_viterbi with pathLen first"); return 1; }
+  MB_CUDA (cudaSetDevice (b->device));
+  // paths are packed on the device in pair order; one D2H copy, then scatter to the caller's offsets
+  int64_t total = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k) total += b->pathLen[k];
+  if (!total) return 0;
+  bool contiguous = true;
+  for (int64_t k = 0; k < b->nPairs && contiguous; ++k) contiguous = (pathOff[k] - pathOff[0] == b->pathStart[k]);
+  if (contiguous) {
+    MB_CUDA (cudaMemcpy (pathTrans + pathOff[0], b->dPaths, (size_t) total * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  std::vector<int32_t> tmp ((size_t) total);
+  MB_CUDA (cudaMemcpy (tmp.data(), b->dPaths, (size_t) total * 4, cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < b->nPairs; ++k)
+    memcpy (pathTrans + pathOff[k], tmp.data() + b->pathStart[k], (size_t) b->pathLen[k] * 4);
+  return 0;
+}
+
+int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
+  if (check_call (m, b)) return 1;
+  return m->engine == MB_ENGINE_JIT ? jit_counts (m, b, counts, loglike) : generic_counts (m, b, counts, loglike);
+}
+
+int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if (ms) *ms = b->lastMs;
+  if (nLaunches) *nLaunches = b->lastLaunches;
+  return 0;
+}
+
+}  // extern "C"

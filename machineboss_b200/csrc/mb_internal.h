@@ -1,0 +1,128 @@
+// mb_internal.h -- structures shared by the C-ABI layer and the engines.
+#ifndef MB_INTERNAL_H
+#define MB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/machineboss_b200.h"
+
+namespace mb {
+
+// The reference's table covers x in [0, 10) and returns 0 beyond (src/logsumexp.h:20,52-53).
+// The device log-sum-exp evaluates log(1+exp(-x)) exactly and applies the same truncation, so it
+// tracks the reference's table to the table's interpolation error (3e-10 per operation).
+#define MB_LSE_CUTOFF 10.0
+
+enum TransType { T_MATCH = 0, T_DELETE = 1, T_INSERT = 2, T_SILENT = 3 };
+
+// Token-indexed transition lists: the role of EvaluatedMachineState::incoming / outgoing
+// (src/eval.h:68-76).  key = (state * nIn1 + inTok) * nOut1 + outTok.  Within a key, entries are in
+// the reference's multimap order: other-state ascending, then transition index.
+struct DevCsr {
+  const int64_t* off;
+  const int32_t* other;
+  const int32_t* id;
+  const double* lw;
+};
+
+// Device view of an evaluated machine (passed to kernels by value).
+struct DevMachine {
+  int32_t S, nIn1, nOut1;
+  DevCsr inc, out;
+  // silent-dependency levels: states in one level have no silent transitions between them
+  int32_t nFwdLevels, nBwdLevels;
+  const int32_t* fwdLevelOff;
+  const int32_t* fwdLevelStates;
+  const int32_t* bwdLevelOff;
+  const int32_t* bwdLevelStates;
+};
+
+struct DevBatch {
+  int64_t nPairs;
+  const uint8_t* x;
+  const int64_t* xOff;
+  const uint8_t* y;
+  const int64_t* yOff;
+};
+
+struct HostCsr {
+  std::vector<int64_t> off;
+  std::vector<int32_t> other, id;
+  std::vector<double> lw;
+};
+
+void set_error (const std::string& msg);
+bool cuda_ok (cudaError_t e, const char* what);
+
+#define MB_CUDA(call) do { if (!mb::cuda_ok ((call), #call)) return 1; } while (0)
+
+}  // namespace mb
+
+// ---- handles ----
+struct mb_machine {
+  int device = 0;
+  int32_t S = 0, nIn = 0, nOut = 0;
+  int64_t T = 0;
+  std::vector<int32_t> src, dst, in, out;
+  std::vector<double> lw;
+  int engine = MB_ENGINE_GENERIC;
+
+  // generic engine
+  mb::HostCsr hInc, hOut;
+  std::vector<int32_t> fwdLevelOff, fwdLevelStates, bwdLevelOff, bwdLevelStates;
+  void* dBlob = nullptr;   // one device allocation holding everything below
+  size_t blobBytes = 0;
+  size_t incLwOffset = 0, outLwOffset = 0;   // byte offsets of the two weight arrays inside the blob
+  mb::DevMachine dev {};
+
+  // jit engine (mb_jit.cu)
+  void* jit = nullptr;
+};
+
+struct mb_batch {
+  int device = 0;
+  int64_t nPairs = 0;
+  std::vector<int64_t> xOff, yOff;    // host copies, for planning
+  uint8_t* dX = nullptr;
+  uint8_t* dY = nullptr;
+  int64_t* dXOff = nullptr;
+  int64_t* dYOff = nullptr;
+  mb::DevBatch dev {};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  double lastMs = 0;
+  int64_t lastLaunches = 0;
+  // result of the last mb_viterbi with traceback: packed paths on the device
+  int32_t* dPaths = nullptr;
+  std::vector<int64_t> pathStart, pathLen;   // per pair: offset into dPaths and length
+  int64_t pathsCapacity = 0;
+};
+
+namespace mb {
+
+// ---- generic engine (mb_generic.cu) ----
+// Each returns 0 on success.  Results are written to host arrays.
+int generic_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);
+int generic_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+int generic_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+
+// ---- jit engine (mb_jit.cu) ----
+bool jit_supported (const mb_machine* m, std::string* why);
+int jit_prepare (mb_machine* m);
+void jit_destroy (mb_machine* m);
+int jit_update_weights (mb_machine* m);
+int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);
+int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+
+// timing helpers
+int timing_begin (mb_batch* b);
+int timing_end (mb_batch* b, int64_t launches);
+
+}  // namespace mb
+
+#endif

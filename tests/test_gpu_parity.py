@@ -1,0 +1,140 @@
+"""GPU parity tests (-m gpu): the CUDA engines, called through the C ABI, against
+(a) the committed reference outputs in tests/golden and (b) the C oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): Forward / Backward log-likelihoods, Viterbi scores and
+counts within 1e-4 relative of the reference, whose log-sum-exp table itself carries up to 4.5e-5
+absolute error per operation; Viterbi scores are FP64 add/max and must be bit-identical; traceback
+paths must be identical under the reference's first-maximum tie-break.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import (LSE_EXACT, FlatMachine, Oracle, gnum, golden_names, load_golden, pairs_from_golden,
+                     synth_tokens)
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+ENGINES = [0, 1]
+
+
+def _capi():
+    from machineboss_b200 import capi
+    return capi
+
+
+def make_machine(capi, m: FlatMachine, engine: int):
+    capi.set_engine(engine)
+    try:
+        return capi.Machine(m.n_states, m.n_in, m.n_out, m.src, m.dst, m.tin, m.tout, m.lw)
+    except capi.MachineBossError as e:
+        if engine == 1 and "jit" in str(e).lower():
+            pytest.skip("JIT engine does not take this machine: %s" % e)
+        raise
+    finally:
+        capi.set_engine(-1)
+
+
+def close(a, b, rel=REL):
+    if math.isinf(a) or math.isinf(b):
+        return a == b
+    return abs(a - b) <= rel * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name, engine):
+    capi = _capi()
+    case = load_golden(name)
+    fm = FlatMachine.from_json(case["machine"])
+    pairs = pairs_from_golden(case)
+    m = make_machine(capi, fm, engine)
+    b = capi.Batch(pairs)
+    ref = case["pairs"]
+    if any("rolling" in p or "forward" in p for p in ref):
+        ll = capi.forward(m, b)
+        for k, p in enumerate(ref):
+            want = gnum(p.get("rolling", p.get("forward")))
+            assert close(ll[k], want), (name, k, ll[k], want)
+    if any("backward" in p for p in ref):
+        bl = capi.backward(m, b)
+        for k, p in enumerate(ref):
+            assert close(bl[k], gnum(p["backward"])), (name, k, bl[k], p["backward"])
+    if any("viterbi" in p for p in ref):
+        sc, paths = capi.viterbi(m, b)
+        sc2 = capi.viterbi(m, b, paths=False)
+        for k, p in enumerate(ref):
+            want = gnum(p["viterbi"])
+            assert sc[k] == want and sc2[k] == want, (name, k, sc[k], want)     # bit-exact
+            if "path" in p:
+                assert paths[k].tolist() == p["path"], (name, k)
+    if case["counts"] is not None:
+        c, ll = capi.counts(m, b)
+        want = np.array([gnum(v) for v in case["counts"]])
+        finite = [gnum(p["forward"]) for p in ref if not math.isinf(gnum(p["forward"]))]
+        if len(finite) == len(ref):      # the reference's counts are NaN-poisoned by impossible pairs
+            np.testing.assert_allclose(c, want, rtol=REL, atol=1e-7)
+            assert close(float(ll.sum()), gnum(case["loglike"]))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_against_oracle_ragged_batch(engine):
+    """A ragged batch (empty, short, long, rectangular pairs) against the oracle, table and exact."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_synth64")["machine"])
+    shapes = [(0, 0), (1, 0), (0, 1), (1, 1), (5, 40), (40, 5), (33, 33), (64, 64), (127, 129), (200, 150), (31, 32), (257, 3)]
+    pairs = [(synth_tokens(77, k, 0, li, 4), synth_tokens(77, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, engine)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    bl = capi.backward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    cnt, cll = capi.counts(m, b)
+    want_cnt = np.zeros(fm.n_trans)
+    for k, (x, y) in enumerate(pairs):
+        f_tab = orc.forward(x, y)
+        f_ex = orc.forward(x, y, mode=LSE_EXACT)
+        assert close(ll[k], f_tab) and close(cll[k], f_tab)
+        assert abs(ll[k] - f_ex) <= 1e-6 * max(1.0, abs(f_ex))     # the device softplus is exact up to the cutoff
+        assert close(bl[k], orc.backward(x, y))
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v
+        assert paths[k].tolist() == p.tolist()
+        orc.counts(x, y, counts=want_cnt)
+    np.testing.assert_allclose(cnt, want_cnt, rtol=REL, atol=1e-7)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_update_weights(engine):
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    flat = FlatMachine.from_json(load_golden("dnapsw_synth64")["machine"])
+    pairs = [(synth_tokens(5, k, 0, 50 + k, 4), synth_tokens(5, k, 1, 60 - k, 4)) for k in range(4)]
+    m = make_machine(capi, flat, engine)
+    b = capi.Batch(pairs)
+    before = capi.forward(m, b)
+    m.update_weights(fm.lw)
+    after = capi.forward(m, b)
+    orc = Oracle(fm)
+    for k, (x, y) in enumerate(pairs):
+        assert close(after[k], orc.forward(x, y))
+    assert not np.allclose(before, after)
+
+
+def test_errors():
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_small")["machine"])
+    # a silent transition going backwards: "Machine is not topologically sorted" (eval.cpp:44)
+    bad_dst = fm.dst.copy()
+    silent = np.where((fm.tin == 0) & (fm.tout == 0) & (fm.src >= 1))[0][0]
+    bad_dst[silent] = fm.src[silent]
+    with pytest.raises(capi.MachineBossError, match="topologically"):
+        capi.Machine(fm.n_states, fm.n_in, fm.n_out, fm.src, bad_dst, fm.tin, fm.tout, fm.lw)
+    with pytest.raises(capi.MachineBossError):
+        capi.Machine(0, 0, 0, [], [], [], [], [])
+    m = capi.Machine(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw)
+    b = capi.Batch([])
+    assert capi.forward(m, b).shape == (0,)
