@@ -87,6 +87,15 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff);
  * log-likelihood is -inf contribute nothing. */
 int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 
+/* ---- diagnostics (not part of the reference surface) ----
+ * Generates the machine-specialised kernels for this machine structure and compiles them with
+ * NVRTC for sm_100a WITHOUT touching a device (so it also runs where there is no GPU: the build
+ * check and the CPU tests use it).  The compiler log (register / spill report) is copied into
+ * log[0..logCap). */
+int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                          const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
+                          char* log, int64_t logCap);
+
 /* ---- measurement hooks (not part of the reference surface) ----
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
  * (CUDA events on the launching stream), and how many kernels that was. */

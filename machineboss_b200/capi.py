@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms"]
+           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_jit_compile_check"]
 
 
 class MachineBossError(RuntimeError):
@@ -53,6 +53,7 @@ def lib():
         L.mb_viterbi.argtypes = [P, P, P, P]
         L.mb_viterbi_paths.argtypes = [P, P, P]
         L.mb_counts.argtypes = [P, P, P, P]
+        L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         _lib = L
     return _lib
@@ -75,6 +76,15 @@ def set_device(d: int) -> None:
 
 def set_engine(e: int) -> None:
     _check(lib().mb_set_engine(e))
+
+
+def jit_compile_check(n_states, n_in, n_out, src, dst, tin, tout) -> str:
+    """NVRTC-compile the specialised kernels of a machine structure (no device needed); returns the log."""
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
+    buf = ctypes.create_string_buffer(1 << 16)
+    _check(lib().mb_jit_compile_check(int(n_states), int(n_in), int(n_out), int(arrs[0].shape[0]),
+                                      *[_ptr(a) for a in arrs], buf, len(buf)))
+    return buf.value.decode()
 
 
 def _ptr(a):

@@ -322,6 +322,20 @@ int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
   return m->engine == MB_ENGINE_JIT ? jit_counts (m, b, counts, loglike) : generic_counts (m, b, counts, loglike);
 }
 
+int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                          const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
+                          char* log, int64_t logCap) {
+  mb_machine m;
+  m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
+  m.src.assign (src, src + nTrans); m.dst.assign (dst, dst + nTrans);
+  m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);
+  m.lw.assign ((size_t) nTrans, 0.);
+  std::string l;
+  const int rc = jit_compile_check (&m, &l);
+  if (log && logCap > 0) { strncpy (log, l.c_str(), (size_t) logCap - 1); log[logCap - 1] = 0; }
+  return rc;
+}
+
 int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches) {
   if (!b) { set_error ("null batch"); return 1; }
   if (ms) *ms = b->lastMs;

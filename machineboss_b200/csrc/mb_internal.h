@@ -113,6 +113,7 @@ int generic_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike)
 // ---- jit engine (mb_jit.cu) ----
 bool jit_supported (const mb_machine* m, std::string* why);
 int jit_prepare (mb_machine* m);
+int jit_compile_check (const mb_machine* m, std::string* log);
 void jit_destroy (mb_machine* m);
 int jit_update_weights (mb_machine* m);
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);

@@ -1,11 +1,630 @@
-// mb_jit.cu -- placeholder until the NVRTC-specialised strip engine lands.
+// mb_jit.cu -- the specialised engine for small machines (dnapsw, protpsw and the like).
+//
+// The reference interprets the machine through nested std::map lookups per cell-state
+// (src/dpmatrix.h:101-115); its own code generator (src/compiler.cpp) shows what flattening that
+// buys on a CPU.  Here the host turns the machine into straight-line CUDA -- one expression per
+// (destination state, transition group) in the reference's candidate order -- puts it in front of
+// the strip-kernel skeleton (mb_jit_skeleton.h) and compiles it with NVRTC for sm_100a the first
+// time a machine structure is seen.  Weights are kernel arguments / shared-memory tables, so
+// mb_machine_update_weights (one per EM iteration) never recompiles.
+//
+// A "slot" is one candidate of a state: all transitions between the same (source, destination)
+// with the same kind (match / delete / insert / silent), i.e. one add + one log-sum-exp (or max)
+// per cell, with the log-weight looked up by the cell's tokens.  Slots of a state are ordered like
+// the reference's candidate list (kind, then other state, then transition index), which is what
+// makes the Viterbi back-pointer tie-break identical (src/dpmatrix.defs.h:93-99,171-174).
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+
 #include "mb_internal.h"
+#include "mb_jit_skeleton.h"
+
 namespace mb {
-bool jit_supported (const mb_machine*, std::string* why) { if (why) *why = "jit engine not built"; return false; }
-int jit_prepare (mb_machine*) { set_error ("jit engine not built"); return 1; }
-void jit_destroy (mb_machine*) { }
-int jit_update_weights (mb_machine*) { return 0; }
-int jit_forward (mb_machine*, mb_batch*, double*, bool) { set_error ("jit engine not built"); return 1; }
-int jit_viterbi (mb_machine*, mb_batch*, double*, int64_t*) { set_error ("jit engine not built"); return 1; }
-int jit_counts (mb_machine*, mb_batch*, double*, double*) { set_error ("jit engine not built"); return 1; }
+
+// ---------------------------------------------------------------------------------------------
+// driver API + NVRTC, resolved at run time so that the library loads on a machine without a GPU
+// ---------------------------------------------------------------------------------------------
+struct Driver {
+  CUresult (*ModuleLoadData) (CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload) (CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction) (CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel) (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*FuncSetAttribute) (CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute) (int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor) (int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*GetErrorString) (CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+
+struct Nvrtc {
+  void* handle = nullptr;
+  nvrtcResult (*CreateProgram) (nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram) (nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetCUBINSize) (nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN) (nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetProgramLogSize) (nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog) (nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram) (nvrtcProgram*) = nullptr;
+  const char* (*GetErrorString) (nvrtcResult) = nullptr;
+  bool ok = false;
+};
+
+static Driver g_drv;
+static Nvrtc g_nvrtc;
+
+static bool load_driver() {
+  if (g_drv.ok) return true;
+  auto get = [] (const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult st;
+    return cudaGetDriverEntryPoint (name, fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess && *fn;
+  };
+  bool ok = get ("cuModuleLoadData", (void**) &g_drv.ModuleLoadData) && get ("cuModuleUnload", (void**) &g_drv.ModuleUnload)
+    && get ("cuModuleGetFunction", (void**) &g_drv.ModuleGetFunction) && get ("cuLaunchKernel", (void**) &g_drv.LaunchKernel)
+    && get ("cuFuncSetAttribute", (void**) &g_drv.FuncSetAttribute) && get ("cuFuncGetAttribute", (void**) &g_drv.FuncGetAttribute)
+    && get ("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**) &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor)
+    && get ("cuGetErrorString", (void**) &g_drv.GetErrorString);
+  if (!ok) { set_error ("could not resolve the CUDA driver entry points (no driver?)"); return false; }
+  g_drv.ok = true;
+  return true;
 }
+
+static bool load_nvrtc() {
+  if (g_nvrtc.ok) return true;
+  std::vector<std::string> cands;
+  if (const char* e = getenv ("MB_NVRTC_LIB")) cands.push_back (e);
+  cands.push_back ("libnvrtc.so.12");
+  cands.push_back ("/usr/local/cuda/lib64/libnvrtc.so.12");
+  cands.push_back ("/usr/local/cuda/lib64/libnvrtc.so");
+  cands.push_back ("libnvrtc.so");
+  for (auto& c: cands) { g_nvrtc.handle = dlopen (c.c_str(), RTLD_NOW | RTLD_GLOBAL); if (g_nvrtc.handle) break; }
+  if (!g_nvrtc.handle) { set_error ("libnvrtc.so.12 not found (set MB_NVRTC_LIB)"); return false; }
+  auto sym = [&] (const char* n) { return dlsym (g_nvrtc.handle, n); };
+  g_nvrtc.CreateProgram = (decltype (g_nvrtc.CreateProgram)) sym ("nvrtcCreateProgram");
+  g_nvrtc.CompileProgram = (decltype (g_nvrtc.CompileProgram)) sym ("nvrtcCompileProgram");
+  g_nvrtc.GetCUBINSize = (decltype (g_nvrtc.GetCUBINSize)) sym ("nvrtcGetCUBINSize");
+  g_nvrtc.GetCUBIN = (decltype (g_nvrtc.GetCUBIN)) sym ("nvrtcGetCUBIN");
+  g_nvrtc.GetProgramLogSize = (decltype (g_nvrtc.GetProgramLogSize)) sym ("nvrtcGetProgramLogSize");
+  g_nvrtc.GetProgramLog = (decltype (g_nvrtc.GetProgramLog)) sym ("nvrtcGetProgramLog");
+  g_nvrtc.DestroyProgram = (decltype (g_nvrtc.DestroyProgram)) sym ("nvrtcDestroyProgram");
+  g_nvrtc.GetErrorString = (decltype (g_nvrtc.GetErrorString)) sym ("nvrtcGetErrorString");
+  if (!g_nvrtc.CreateProgram || !g_nvrtc.CompileProgram || !g_nvrtc.GetCUBINSize || !g_nvrtc.GetCUBIN || !g_nvrtc.GetProgramLogSize
+      || !g_nvrtc.GetProgramLog || !g_nvrtc.DestroyProgram) { set_error ("libnvrtc is missing symbols"); return false; }
+  g_nvrtc.ok = true;
+  return true;
+}
+
+static bool cu_ok (CUresult r, const char* what) {
+  if (r == CUDA_SUCCESS) return true;
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString (r, &s);
+  set_error (std::string ("CUDA driver error: ") + (s ? s : "?") + " in " + what);
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the plan: slots, tables, generated source
+// ---------------------------------------------------------------------------------------------
+struct Slot {
+  int type, self, other, rank;
+  int emitOff = -1;   // offset into the emission table (non-silent slots)
+  int silIdx = -1;    // index into the silent-weight array (silent slots)
+  int idOff = 0;      // offset into the transition-id table
+  int tableSize = 1;
+};
+
+struct Program {
+  std::vector<Slot> slots;                    // ordered by (self, type, other, rank)
+  std::vector<int> stateSlot0;                // [S+1] first slot of each state
+  std::vector<int32_t> idTab;                 // transition id per table entry, -1 = no such transition
+  std::vector<int32_t> emitId;                // transition id per emission-table entry
+  std::vector<int32_t> silId;                 // transition id per silent slot
+  int nEmit = 0, nSil = 0;
+};
+
+static int table_size (int type, int nIn, int nOut) {
+  return type == T_MATCH ? nIn * nOut : type == T_DELETE ? nIn : type == T_INSERT ? nOut : 1;
+}
+
+static int label_index (int type, int a, int b, int nOut) {   // a, b are 1-based tokens
+  return type == T_MATCH ? (a - 1) * nOut + (b - 1) : type == T_DELETE ? a - 1 : type == T_INSERT ? b - 1 : 0;
+}
+
+static int trans_type (int a, int b) { return a ? (b ? T_MATCH : T_DELETE) : (b ? T_INSERT : T_SILENT); }
+
+static void build_program (const mb_machine* m, bool forward, Program& p) {
+  struct Key { int self, type, other, rank; bool operator< (const Key& k) const { return std::tie (self, type, other, rank) < std::tie (k.self, k.type, k.other, k.rank); } };
+  std::map<Key, std::vector<std::pair<int, int>>> groups;       // -> (label index, transition id)
+  std::map<std::tuple<int, int, int, int>, int> seen;           // (self, type, other, label) -> how many so far
+  for (int64_t t = 0; t < m->T; ++t) {
+    const int type = trans_type (m->in[t], m->out[t]);
+    if (type == T_SILENT && m->dst[t] <= m->src[t]) continue;   // only possible on state 0 (machine.cpp:759); reads -inf in the reference
+    const int self = forward ? m->dst[t] : m->src[t], other = forward ? m->src[t] : m->dst[t];
+    const int li = label_index (type, m->in[t], m->out[t], m->nOut);
+    const int rank = seen[std::make_tuple (self, type, other, li)]++;
+    groups[Key { self, type, other, rank }].push_back ({ li, (int) t });
+  }
+  p.stateSlot0.assign ((size_t) m->S + 1, 0);
+  for (auto& g: groups) {
+    Slot s;
+    s.type = g.first.type; s.self = g.first.self; s.other = g.first.other; s.rank = g.first.rank;
+    s.tableSize = table_size (s.type, m->nIn, m->nOut);
+    s.idOff = (int) p.idTab.size();
+    p.idTab.resize (p.idTab.size() + s.tableSize, -1);
+    for (auto& e: g.second) p.idTab[s.idOff + e.first] = e.second;
+    if (s.type == T_SILENT) { s.silIdx = p.nSil++; p.silId.push_back (g.second[0].second); }
+    else {
+      s.emitOff = p.nEmit;
+      p.nEmit += s.tableSize;
+      p.emitId.resize ((size_t) p.nEmit, -1);
+      for (auto& e: g.second) p.emitId[s.emitOff + e.first] = e.second;
+    }
+    p.stateSlot0[s.self + 1]++;
+    p.slots.push_back (s);
+  }
+  for (int s = 0; s < m->S; ++s) p.stateSlot0[s + 1] += p.stateSlot0[s];
+}
+
+struct JitEngine {
+  Program fwd, bwd;
+  int C = 4, tbBytes = 1, threads = 128;
+  std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
+  std::string source;
+  CUmodule mod = nullptr;
+  CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr;
+  int blocksPerSM[3] = { 1, 1, 1 };
+  size_t smemBytes[3] = { 0, 0, 0 };
+  int numSMs = 148;
+  // device tables
+  double* dEmitF = nullptr;
+  double* dEmitB = nullptr;
+  int32_t* dTbPlan = nullptr;             // packed arrays for the traceback kernel
+  std::vector<char> silParam;             // MBSil { double f[max(nSilF,1)]; double b[max(nSilB,1)]; }
+  unsigned long long* dCounter = nullptr;
+};
+
+static std::string term_expr (const Slot& s, int nOut, bool forward) {
+  std::ostringstream e;
+  const char* arr = s.type == T_MATCH ? "D" : s.type == T_DELETE ? "L" : s.type == T_INSERT ? "U" : nullptr;
+  if (arr) e << arr << "[" << s.other << "]";
+  else e << "n" << s.other;
+  e << " + ";
+  if (s.type == T_MATCH) e << "E[" << s.emitOff << " + a * " << nOut << " + b]";
+  else if (s.type == T_DELETE) e << "E[" << s.emitOff << " + a]";
+  else if (s.type == T_INSERT) e << "E[" << s.emitOff << " + b]";
+  else e << "P." << (forward ? "f" : "b") << "[" << s.silIdx << "]";
+  return e.str();
+}
+
+static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program& p, bool forward, bool viterbi, const JitEngine& J) {
+  const char* name = viterbi ? "mb_cell_vit" : forward ? "mb_cell_fwd" : "mb_cell_bwd";
+  o << "__device__ __forceinline__ " << (viterbi ? "unsigned long long " : "void ") << name
+    << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P) {\n";
+  if (viterbi) o << "  unsigned long long word = 0;\n";
+  const int originState = forward ? 0 : m->S - 1;
+  for (int q = 0; q < m->S; ++q) {
+    const int d = forward ? q : m->S - 1 - q;
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    if (s0 == s1) o << "  double n" << d << " = mb_neg_inf();\n";
+    for (int k = s0; k < s1; ++k) {
+      const std::string t = term_expr (p.slots[k], m->nOut, forward);
+      if (k == s0) { o << "  double n" << d << " = " << t << ";\n"; if (viterbi && s1 - s0 > 1) o << "  unsigned p" << d << " = 0u;\n"; }
+      else if (viterbi) o << "  { const double t = " << t << "; if (n" << d << " < t) { n" << d << " = t; p" << d << " = " << (k - s0) << "u; } }\n";
+      else o << "  n" << d << " = mb_lse (n" << d << ", " << t << ");\n";
+    }
+    if (d == originState) o << "  if (origin) n" << d << " = 0.0;\n";
+    if (viterbi && s1 - s0 > 1) o << "  word |= (unsigned long long) p" << d << " << " << J.shift[d] << ";\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
+  if (viterbi) o << "  return word;\n";
+  o << "}\n\n";
+}
+
+bool jit_supported (const mb_machine* m, std::string* why) {
+  auto no = [&] (const char* w) { if (why) *why = w; return false; };
+  if (m->S > 16) return no ("more than 16 states");
+  if (m->T > 4096) return no ("more than 4096 transitions");
+  Program f, b;
+  build_program (m, true, f);
+  build_program (m, false, b);
+  if (f.slots.size() > 160 || b.slots.size() > 160) return no ("more than 160 transition groups");
+  if (f.nEmit > 3072 || b.nEmit > 3072) return no ("emission tables exceed 24 KB of shared memory");
+  if (f.nSil + b.nSil > 400) return no ("too many silent transitions for the kernel-parameter block");
+  int totalBits = 0;
+  for (int s = 0; s < m->S; ++s) { const int n = f.stateSlot0[s + 1] - f.stateSlot0[s]; int bt = 0; while ((1 << bt) < n) ++bt; totalBits += bt; }
+  if (totalBits > 64) return no ("Viterbi back-pointers need more than 64 bits per cell");
+  return true;
+}
+
+static int nvrtc_compile (JitEngine& J, std::vector<char>& cubin, std::string* logOut) {
+  if (!load_nvrtc()) return 1;
+  nvrtcProgram prog;
+  if (g_nvrtc.CreateProgram (&prog, J.source.c_str(), "mb_jit_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { set_error ("nvrtcCreateProgram failed"); return 1; }
+  const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--ptxas-options=-v" };
+  const nvrtcResult r = g_nvrtc.CompileProgram (prog, 4, opts);
+  size_t ln = 0;
+  g_nvrtc.GetProgramLogSize (prog, &ln);
+  std::string log (ln, 0);
+  if (ln) g_nvrtc.GetProgramLog (prog, &log[0]);
+  if (logOut) *logOut = log;
+  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen (d, "w"); if (f) { fputs (J.source.c_str(), f); fclose (f); } }
+  if (r != NVRTC_SUCCESS) {
+    set_error ("NVRTC compilation failed:\n" + log);
+    g_nvrtc.DestroyProgram (&prog);
+    return 1;
+  }
+  size_t n = 0;
+  g_nvrtc.GetCUBINSize (prog, &n);
+  cubin.resize (n);
+  g_nvrtc.GetCUBIN (prog, cubin.data());
+  g_nvrtc.DestroyProgram (&prog);
+  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen ((std::string (d) + ".cubin").c_str(), "wb"); if (f) { fwrite (cubin.data(), 1, n, f); fclose (f); } }
+  return 0;
+}
+
+static int compile (mb_machine* m, JitEngine& J) {
+  std::vector<char> cubin;
+  if (nvrtc_compile (J, cubin, nullptr) || !load_driver()) return 1;
+  MB_CUDA (cudaFree (0));   // make sure the primary context exists and is current
+  if (!cu_ok (g_drv.ModuleLoadData (&J.mod, cubin.data()), "cuModuleLoadData")) return 1;
+  if (!cu_ok (g_drv.ModuleGetFunction (&J.kForward, J.mod, "mb_k_forward"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackward, J.mod, "mb_k_backward"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")) return 1;
+  int dev = 0;
+  MB_CUDA (cudaGetDevice (&dev));
+  MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
+  CUfunction fn[3] = { J.kForward, J.kBackward, J.kViterbi };
+  const int ne[3] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit };
+  for (int q = 0; q < 3; ++q) {
+    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * m->S) * 8;
+    if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
+    int nb = 0;
+    if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
+    J.blocksPerSM[q] = std::max (1, nb);
+  }
+  return 0;
+}
+
+static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>& ef, std::vector<double>& eb) {
+  const double ninf = -INFINITY;
+  ef.assign ((size_t) std::max (J.fwd.nEmit, 1), ninf);
+  eb.assign ((size_t) std::max (J.bwd.nEmit, 1), ninf);
+  for (int q = 0; q < J.fwd.nEmit; ++q) if (J.fwd.emitId[q] >= 0) ef[q] = m->lw[J.fwd.emitId[q]];
+  for (int q = 0; q < J.bwd.nEmit; ++q) if (J.bwd.emitId[q] >= 0) eb[q] = m->lw[J.bwd.emitId[q]];
+  const int nf = std::max (J.fwd.nSil, 1), nb = std::max (J.bwd.nSil, 1);
+  J.silParam.assign ((size_t) (nf + nb) * 8, 0);
+  double* sp = (double*) J.silParam.data();
+  for (int q = 0; q < J.fwd.nSil; ++q) sp[q] = m->lw[J.fwd.silId[q]];
+  for (int q = 0; q < J.bwd.nSil; ++q) sp[nf + q] = m->lw[J.bwd.silId[q]];
+}
+
+int jit_update_weights (mb_machine* m) {
+  JitEngine& J = *(JitEngine*) m->jit;
+  std::vector<double> ef, eb;
+  fill_weights (m, J, ef, eb);
+  MB_CUDA (cudaMemcpy (J.dEmitF, ef.data(), ef.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (J.dEmitB, eb.data(), eb.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// layout of the traceback plan on the device (int32): [0..S] stateSlot0, then per slot type, other,
+// idOff, then per state shift, bits, then the id table
+struct TbPlan {
+  const int32_t* stateSlot0;
+  const int32_t* slotType;
+  const int32_t* slotOther;
+  const int32_t* slotIdOff;
+  const int32_t* shift;
+  const int32_t* bits;
+  const int32_t* idTab;
+  int32_t S, nOut, tbBytes, W;
+};
+
+static void generate (const mb_machine* m, JitEngine& J) {
+  build_program (m, true, J.fwd);
+  build_program (m, false, J.bwd);
+  J.shift.assign ((size_t) m->S, 0);
+  J.bits.assign ((size_t) m->S, 0);
+  int totalBits = 0;
+  for (int s = 0; s < m->S; ++s) {
+    const int n = J.fwd.stateSlot0[s + 1] - J.fwd.stateSlot0[s];
+    int bt = 0; while ((1 << bt) < n) ++bt;
+    J.shift[s] = totalBits; J.bits[s] = bt; totalBits += bt;
+  }
+  J.tbBytes = totalBits <= 8 ? 1 : totalBits <= 16 ? 2 : totalBits <= 32 ? 4 : 8;
+  J.C = m->S <= 8 ? 4 : 2;
+  if (const char* e = getenv ("MB_JIT_C")) J.C = std::max (1, std::min (8, atoi (e)));
+  while (J.C * J.tbBytes > 16) J.C /= 2;
+  if (const char* e = getenv ("MB_JIT_THREADS")) J.threads = std::max (32, std::min (1024, atoi (e) / 32 * 32));
+
+  std::ostringstream o;
+  o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
+  o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
+  o << "#define MB_S " << m->S << "\n#define MB_C " << J.C << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
+  o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
+  o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
+  o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n\n";
+  gen_cell (o, m, J.fwd, true, false, J);
+  gen_cell (o, m, J.bwd, false, false, J);
+  gen_cell (o, m, J.fwd, true, true, J);
+  o << kJitSkeleton;
+  J.source = o.str();
+}
+
+// Diagnostic used by build() and the CPU tests: generate and NVRTC-compile the kernels of a machine
+// structure without touching a device.
+int jit_compile_check (const mb_machine* m, std::string* log) {
+  std::string why;
+  if (!jit_supported (m, &why)) { set_error ("machine not eligible for the JIT engine: " + why); return 1; }
+  JitEngine J;
+  generate (m, J);
+  std::vector<char> cubin;
+  return nvrtc_compile (J, cubin, log);
+}
+
+int jit_prepare (mb_machine* m) {
+  JitEngine* Jp = new JitEngine;
+  m->jit = Jp;
+  JitEngine& J = *Jp;
+  generate (m, J);
+  if (compile (m, J)) return 1;
+
+  std::vector<double> ef, eb;
+  fill_weights (m, J, ef, eb);
+  MB_CUDA (cudaMalloc (&J.dEmitF, ef.size() * 8));
+  MB_CUDA (cudaMalloc (&J.dEmitB, eb.size() * 8));
+  MB_CUDA (cudaMalloc (&J.dCounter, 8));
+  if (jit_update_weights (m)) return 1;
+  // traceback plan
+  std::vector<int32_t> plan;
+  for (int v: J.fwd.stateSlot0) plan.push_back (v);
+  for (auto& s: J.fwd.slots) plan.push_back (s.type);
+  for (auto& s: J.fwd.slots) plan.push_back (s.other);
+  for (auto& s: J.fwd.slots) plan.push_back (s.idOff);
+  for (int v: J.shift) plan.push_back (v);
+  for (int v: J.bits) plan.push_back (v);
+  for (int v: J.fwd.idTab) plan.push_back (v);
+  MB_CUDA (cudaMalloc (&J.dTbPlan, std::max<size_t> (plan.size(), 1) * 4));
+  MB_CUDA (cudaMemcpy (J.dTbPlan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void jit_destroy (mb_machine* m) {
+  if (!m->jit) return;
+  JitEngine* J = (JitEngine*) m->jit;
+  if (J->mod && g_drv.ModuleUnload) g_drv.ModuleUnload (J->mod);
+  if (J->dEmitF) cudaFree (J->dEmitF);
+  if (J->dEmitB) cudaFree (J->dEmitB);
+  if (J->dTbPlan) cudaFree (J->dTbPlan);
+  if (J->dCounter) cudaFree (J->dCounter);
+  delete J;
+  m->jit = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+struct MBArgsHost {   // must match struct MBArgs in the skeleton
+  const uint8_t* x; const int64_t* xOff;
+  const uint8_t* y; const int64_t* yOff;
+  const int64_t* order; int64_t nWork; unsigned long long* counter;
+  double* bnd; int64_t bndStride;
+  double* result;
+  const double* emit;
+  uint8_t* tb; const int64_t* tbOff;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree (p); }
+  int alloc (size_t bytes) { MB_CUDA (cudaMalloc (&p, bytes ? bytes : 8)); return 0; }
+  template<class T> T* as() { return (T*) p; }
+};
+
+static std::vector<int64_t> cost_order (const mb_batch* b, const std::vector<int64_t>& pairs) {
+  std::vector<int64_t> o = pairs;
+  std::stable_sort (o.begin(), o.end(), [&] (int64_t p, int64_t q) {
+    const double cp = (double) (b->xOff[p + 1] - b->xOff[p] + 1) * (double) (b->yOff[p + 1] - b->yOff[p] + 1);
+    const double cq = (double) (b->xOff[q + 1] - b->xOff[q] + 1) * (double) (b->yOff[q + 1] - b->yOff[q] + 1);
+    return cp > cq;
+  });
+  return o;
+}
+
+static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff) {
+  JitEngine& J = *(JitEngine*) m->jit;
+  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : J.kViterbi;
+  int64_t maxLo = 0;
+  for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
+  const int warpsPerBlock = J.threads / 32;
+  int64_t grid = (int64_t) J.numSMs * J.blocksPerSM[which];
+  grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
+  grid = std::max<int64_t> (grid, 1);
+  const int64_t bndStride = 2 * (maxLo + 1) * m->S;
+  DevBuf dOrder, dBnd;
+  if (dOrder.alloc (order.size() * 8) || dBnd.alloc ((size_t) (grid * warpsPerBlock * bndStride) * 8)) return 1;
+  MB_CUDA (cudaMemcpyAsync (dOrder.p, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (J.dCounter, 0, 8, b->stream));
+  MBArgsHost A;
+  A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
+  A.order = dOrder.as<int64_t>(); A.nWork = (int64_t) order.size(); A.counter = J.dCounter;
+  A.bnd = dBnd.as<double>(); A.bndStride = bndStride;
+  A.result = dResult;
+  A.emit = which == 1 ? J.dEmitB : J.dEmitF;
+  A.tb = dTb; A.tbOff = dTbOff;
+  void* params[2] = { (void*) J.silParam.data(), (void*) &A };
+  if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
+  MB_CUDA (cudaStreamSynchronize (b->stream));   // the workspace buffers above are freed on return
+  return 0;
+}
+
+int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
+  if (b->nPairs == 0) return 0;
+  std::vector<int64_t> all ((size_t) b->nPairs);
+  for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
+  const std::vector<int64_t> order = cost_order (b, all);
+  DevBuf dRes;
+  if (dRes.alloc ((size_t) b->nPairs * 8)) return 1;
+  if (timing_begin (b)) return 1;
+  if (launch (m, b, backward ? 1 : 0, order, dRes.as<double>(), nullptr, nullptr)) return 1;
+  if (timing_end (b, 1)) return 1;
+  MB_CUDA (cudaMemcpy (loglike, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// DPMatrix::traceBack (dpmatrix.defs.h:82-110) over the packed back-pointers written by
+// mb_k_viterbi: one thread per pair; pass 1 (out == nullptr) measures, pass 2 writes start -> end.
+__global__ void jit_traceback_kernel (TbPlan p, DevBatch b, const int64_t* __restrict__ pairs, int64_t nPairsHere,
+                                      const uint8_t* __restrict__ tb, const int64_t* __restrict__ tbOff,
+                                      const double* __restrict__ score, int64_t* __restrict__ len,
+                                      int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+  const int64_t slot = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nPairsHere) return;
+  const int64_t k = pairs[slot];
+  const uint8_t* x = b.x + b.xOff[k];
+  const uint8_t* y = b.y + b.yOff[k];
+  const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
+  const int64_t pitch = ((Li + p.W) / p.W) * p.W;
+  const uint8_t* base = tb + tbOff[k];
+  int64_t n = 0;
+  if (score[k] > -INFINITY) {
+    const int64_t total = out ? len[slot] : 0;
+    int64_t i = Li, o = Lo;
+    int s = p.S - 1;
+    while (i > 0 || o > 0 || s != 0) {
+      const uint8_t* wp = base + (o * pitch + i) * p.tbBytes;
+      unsigned long long word = 0;
+      for (int q = 0; q < p.tbBytes; ++q) word |= (unsigned long long) wp[q] << (8 * q);
+      const int ptr = (int) ((word >> p.shift[s]) & ((1ull << p.bits[s]) - 1ull));
+      const int sl = p.stateSlot0[s] + ptr;
+      if (sl >= p.stateSlot0[s + 1]) break;    // corrupt pointer: cannot happen on a finite path
+      const int type = p.slotType[sl];
+      const int a = i ? x[i - 1] - 1 : 0, c = o ? y[o - 1] - 1 : 0;
+      const int li = type == T_MATCH ? a * p.nOut + c : type == T_DELETE ? a : type == T_INSERT ? c : 0;
+      if (out) out[outOff[slot] + total - 1 - n] = p.idTab[p.slotIdOff[sl] + li];
+      ++n;
+      if (type == T_MATCH || type == T_DELETE) --i;
+      if (type == T_MATCH || type == T_INSERT) --o;
+      s = p.slotOther[sl];
+      if (i < 0 || o < 0) break;
+    }
+  }
+  if (!out) len[slot] = n;
+}
+
+static int ensure_paths (mb_batch* b, int64_t need) {
+  if (need <= b->pathsCapacity) return 0;
+  const int64_t cap = std::max<int64_t> (need, 2 * b->pathsCapacity);
+  int32_t* p = nullptr;
+  MB_CUDA (cudaMalloc (&p, (size_t) cap * 4));
+  if (b->dPaths) {
+    MB_CUDA (cudaMemcpyAsync (p, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    cudaFree (b->dPaths);
+  }
+  b->dPaths = p;
+  b->pathsCapacity = cap;
+  return 0;
+}
+
+int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
+  JitEngine& J = *(JitEngine*) m->jit;
+  b->pathStart.clear();
+  b->pathLen.clear();
+  if (b->nPairs == 0) return 0;
+  const bool trace = pathLen != nullptr;
+  const int W = 32 * J.C;
+  // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
+  const double budget = 0.85 * (double) freeB;
+  std::vector<std::vector<int64_t>> chunks (1);
+  std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
+  std::vector<int64_t> chunkBytes (1, 0);
+  for (int64_t k = 0; k < b->nPairs; ++k) {
+    const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
+    int64_t need = (Lo + 1) * (((Li + W) / W) * W) * J.tbBytes;
+    need = (need + 255) & ~(int64_t) 255;
+    if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": Viterbi back-pointers do not fit in device memory"); return 1; }
+    if (!chunks.back().empty() && (double) (chunkBytes.back() + need) > budget) { chunks.emplace_back(); chunkBytes.push_back (0); }
+    tbOffHost[k] = chunkBytes.back();
+    chunkBytes.back() += need;
+    chunks.back().push_back (k);
+  }
+  DevBuf dRes, dTbOff;
+  if (dRes.alloc ((size_t) b->nPairs * 8) || dTbOff.alloc ((size_t) b->nPairs * 8)) return 1;
+  MB_CUDA (cudaMemcpyAsync (dTbOff.p, tbOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  if (trace) { b->pathStart.assign ((size_t) b->nPairs, 0); b->pathLen.assign ((size_t) b->nPairs, 0); }
+  char* plan = (char*) J.dTbPlan;
+  const size_t nSlots = J.fwd.slots.size();
+  TbPlan tp;
+  tp.stateSlot0 = (const int32_t*) plan;
+  tp.slotType = tp.stateSlot0 + (m->S + 1);
+  tp.slotOther = tp.slotType + nSlots;
+  tp.slotIdOff = tp.slotOther + nSlots;
+  tp.shift = tp.slotIdOff + nSlots;
+  tp.bits = tp.shift + m->S;
+  tp.idTab = tp.bits + m->S;
+  tp.S = m->S; tp.nOut = m->nOut; tp.tbBytes = J.tbBytes; tp.W = W;
+  int64_t packed = 0, launches = 0;
+  double ms = 0;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    const std::vector<int64_t> order = cost_order (b, chunks[c]);
+    DevBuf dTb;
+    if (trace && dTb.alloc ((size_t) chunkBytes[c])) return 1;
+    if (timing_begin (b)) return 1;
+    // without traceback the pointers are still written (same kernel); give it scratch of one chunk
+    if (!trace && dTb.alloc ((size_t) chunkBytes[c])) return 1;
+    if (launch (m, b, 2, order, dRes.as<double>(), dTb.as<uint8_t>(), dTbOff.as<int64_t>())) return 1;
+    ++launches;
+    if (trace) {
+      DevBuf dPairs, dLen, dOutOff;
+      const size_t n = chunks[c].size();
+      if (dPairs.alloc (n * 8) || dLen.alloc (n * 8) || dOutOff.alloc (n * 8)) return 1;
+      MB_CUDA (cudaMemcpyAsync (dPairs.p, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
+      const unsigned tg = (unsigned) ((n + 63) / 64);
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs.as<int64_t>(), (int64_t) n, dTb.as<uint8_t>(), dTbOff.as<int64_t>(), dRes.as<double>(), dLen.as<int64_t>(), nullptr, nullptr);
+      MB_CUDA (cudaGetLastError());
+      std::vector<int64_t> len (n), off (n);
+      MB_CUDA (cudaMemcpyAsync (len.data(), dLen.p, n * 8, cudaMemcpyDeviceToHost, b->stream));
+      MB_CUDA (cudaStreamSynchronize (b->stream));
+      for (size_t q = 0; q < n; ++q) {
+        off[q] = packed;
+        b->pathStart[chunks[c][q]] = packed;
+        b->pathLen[chunks[c][q]] = len[q];
+        packed += len[q];
+      }
+      if (ensure_paths (b, packed)) return 1;
+      MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs.as<int64_t>(), (int64_t) n, dTb.as<uint8_t>(), dTbOff.as<int64_t>(), dRes.as<double>(), dLen.as<int64_t>(), b->dPaths, dOutOff.as<int64_t>());
+      MB_CUDA (cudaGetLastError());
+      launches += 2;
+      MB_CUDA (cudaStreamSynchronize (b->stream));
+    }
+    if (timing_end (b, launches)) return 1;
+    ms += b->lastMs;
+  }
+  b->lastMs = ms;
+  b->lastLaunches = launches;
+  MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  if (trace) {
+    // pathStart must be ascending in pair order for mb_viterbi_paths' contiguous fast path; with one
+    // chunk and cost ordering it is in chunk order = pair order already (chunks list pairs ascending)
+    for (int64_t k = 0; k < b->nPairs; ++k) pathLen[k] = b->pathLen[k];
+  }
+  return 0;
+}
+
+int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
+  // posterior counts still run on the generic engine's kernels (full Forward and Backward matrices)
+  return generic_counts (m, b, counts, loglike);
+}
+
+}  // namespace mb

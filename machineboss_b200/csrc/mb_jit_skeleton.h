@@ -1,0 +1,180 @@
+// mb_jit_skeleton.h -- CUDA source of the machine-specialised strip kernels, compiled at run time
+// with NVRTC for sm_100a after the generated prelude (defines + the per-machine cell functions,
+// see mb_jit.cu) has been placed in front of it.
+//
+// Mapping (one warp per sequence pair; pairs are pulled from a work counter, longest first):
+//   * the DP matrix is cut into vertical strips of 32*MB_C input positions; lane j owns MB_C
+//     adjacent columns of the strip and keeps their previous-row cell values (MB_S states each)
+//     in registers;
+//   * rows are swept in a skew: at step t lane j computes output row t-j, so the cells the warp
+//     computes in one step lie on an anti-diagonal (of MB_C-wide blocks); the left neighbour's
+//     values arrive with one shuffle per state per step, the diagonal ones are last step's;
+//   * the last column of a strip is handed to the next strip through an L2-resident buffer,
+//     written by lane 31 and staged back 32 rows at a time through shared memory;
+//   * emission log-weights (token-indexed) sit in shared memory, silent log-weights arrive as a
+//     __grid_constant__ kernel parameter (constant bank), the transition structure itself is
+//     straight-line code in the generated cell function.
+// Backward runs the same sweep in reversed coordinates (i' = Li-i, o' = Lo-o) with the machine's
+// outgoing transitions.
+#ifndef MB_JIT_SKELETON_H
+#define MB_JIT_SKELETON_H
+
+static const char* const kJitSkeleton = R"MBSRC(
+#define MB_W (32 * MB_C)
+#define MB_FULL 0xffffffffu
+
+struct MBArgs {
+  const uint8_t* x; const int64_t* xOff;
+  const uint8_t* y; const int64_t* yOff;
+  const int64_t* order; int64_t nWork; unsigned long long* counter;
+  double* bnd; int64_t bndStride;
+  double* result;
+  const double* emit;
+  uint8_t* tb; const int64_t* tbOff;
+};
+
+__device__ __forceinline__ double mb_neg_inf() { return __longlong_as_double (0xfff0000000000000LL); }
+
+// log(exp(a)+exp(b)): max in FP64, softplus of |a-b| in FP32 on the MUFU pipe, truncated at the
+// range of the reference's lookup table (src/logsumexp.h:20,52): terms more than 10 nats below
+// the running value add nothing there either.
+__device__ __forceinline__ double mb_lse (double a, double b) {
+  const double t = a - b;
+  const double mx = (t < 0.0) ? b : a;
+  const float x = fabsf (__double2float_rn (t));
+  float g = __log2f (1.0f + exp2f (-1.4426950408889634f * x)) * 0.6931471805599453f;
+  g = (x < 10.0f) ? g : 0.0f;          // also discards NaN (-inf - -inf) and inf
+  return mx + (double) g;
+}
+
+template<int DIR> struct MBDir { };
+template<> struct MBDir<0> { static const int NE = MB_NEMIT_F; static const int RES = MB_S - 1; };
+template<> struct MBDir<1> { static const int NE = MB_NEMIT_B; static const int RES = 0; };
+
+// MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers
+template<int MODE, int DIR>
+__device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
+  extern __shared__ double mb_smem[];
+  double* E = mb_smem;
+  const int NE = MBDir<DIR>::NE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
+  __syncthreads();
+  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_S);
+  const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
+  double* bndA = A.bnd + wslot * A.bndStride;
+  double* bndB = bndA + (A.bndStride >> 1);
+  const double NI = mb_neg_inf();
+
+  for (;;) {
+    unsigned long long w = 0;
+    if (lane == 0) w = atomicAdd (A.counter, 1ULL);
+    w = __shfl_sync (MB_FULL, w, 0);
+    if ((int64_t) w >= A.nWork) break;
+    const int64_t k = A.order[w];
+    const int64_t x0 = A.xOff[k], y0 = A.yOff[k];
+    const int Li = (int) (A.xOff[k + 1] - x0), Lo = (int) (A.yOff[k + 1] - y0);
+    const uint8_t* x = A.x + x0;
+    const uint8_t* y = A.y + y0;
+    const int nStrips = (Li + MB_W) / MB_W;
+    const int64_t pitch = (int64_t) nStrips * MB_W;
+    uint8_t* tb = MODE == 1 ? A.tb + A.tbOff[k] : (uint8_t*) 0;
+
+    for (int strip = 0; strip < nStrips; ++strip) {
+      const int col0 = strip * MB_W + lane * MB_C;
+      int ta[MB_C];
+#pragma unroll
+      for (int c = 0; c < MB_C; ++c) {
+        const int i = col0 + c;
+        int tok = 1;
+        if (i >= 1 && i <= Li) tok = DIR ? x[Li - i] : x[i - 1];
+        ta[c] = tok - 1;
+      }
+      double U[MB_C][MB_S], Lk[MB_S];
+#pragma unroll
+      for (int s = 0; s < MB_S; ++s) {
+        Lk[s] = NI;
+#pragma unroll
+        for (int c = 0; c < MB_C; ++c) U[c][s] = NI;
+      }
+      const double* bin = (strip & 1) ? bndB : bndA;
+      double* bout = (strip & 1) ? bndA : bndB;
+      const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      int tokb = 0;
+      const int nSteps = Lo + 32;
+      for (int t = 0; t < nSteps; ++t) {
+        const int r = t - lane;
+        if (hasIn && (t & 31) == 0) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < MB_S; ++q) {
+            const int e = q * 32 + lane;
+            const int row = t + e / MB_S;
+            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * MB_S + (e % MB_S)) : NI;
+          }
+          __syncwarp();
+        }
+        const int tprev = __shfl_up_sync (MB_FULL, tokb, 1);
+        if (lane == 0) {
+          int tok = 1;
+          if (t >= 1 && t <= Lo) tok = DIR ? y[Lo - t] : y[t - 1];
+          tokb = tok - 1;
+        } else tokb = tprev;
+        double Lc[MB_S];
+#pragma unroll
+        for (int s = 0; s < MB_S; ++s) Lc[s] = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+        if (lane == 0) {
+#pragma unroll
+          for (int s = 0; s < MB_S; ++s) Lc[s] = hasIn ? sIn[(t & 31) * MB_S + s] : NI;
+        }
+        if (r >= 0 && r <= Lo) {
+          double Dc[MB_S];
+#pragma unroll
+          for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
+          unsigned long long pack0 = 0, pack1 = 0;
+#pragma unroll
+          for (int c = 0; c < MB_C; ++c) {
+            double N[MB_S];
+            const bool origin = (r == 0) && (col0 + c == 0);
+            if (MODE == 0) {
+              if (DIR == 0) mb_cell_fwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              else mb_cell_bwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+            } else {
+              const unsigned long long word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              const int sh = 8 * MB_TBBYTES * c;
+              if (sh < 64) pack0 |= word << (sh & 63);
+              else pack1 |= word << ((sh - 64) & 63);
+            }
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
+          }
+          if (MODE == 1) {
+            uint8_t* p = tb + ((int64_t) r * pitch + col0) * MB_TBBYTES;
+            if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack0;
+            else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack0;
+            else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = (unsigned int) pack0;
+            else if (MB_C * MB_TBBYTES == 8) *(unsigned long long*) p = pack0;
+            else *(ulonglong2*) p = make_ulonglong2 (pack0, pack1);
+          }
+          if (hasOut && lane == 31) {
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) bout[(int64_t) r * MB_S + s] = U[MB_C - 1][s];
+          }
+          if (r == Lo) {
+#pragma unroll
+            for (int c = 0; c < MB_C; ++c)
+              if (col0 + c == Li) A.result[k] = U[c][MBDir<DIR>::RES];
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
+)MBSRC";
+
+#endif

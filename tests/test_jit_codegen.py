@@ -1,0 +1,18 @@
+"""CPU tests: the machine-specialised kernels generate and compile (NVRTC, sm_100a, no device)
+for every small golden machine; big machines are reported as not eligible."""
+import pytest
+
+from helpers import FlatMachine, golden_names, load_golden
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_jit_kernels_compile(name):
+    from machineboss_b200 import capi
+    fm = FlatMachine.from_json(load_golden(name)["machine"])
+    try:
+        log = capi.jit_compile_check(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
+    except capi.MachineBossError as e:
+        assert fm.n_states > 16 and "not eligible" in str(e), str(e)[:2000]
+        return
+    assert "mb_k_forward" in log and "mb_k_viterbi" in log and "mb_k_backward" in log
+    assert "0 bytes spill stores" in log
