@@ -178,9 +178,12 @@ struct JitEngine {
   std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
   std::string source;
   CUmodule mod = nullptr;
-  CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr;
-  int blocksPerSM[3] = { 1, 1, 1 };
-  size_t smemBytes[3] = { 0, 0, 0 };
+  CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
+  int blocksPerSM[5] = { 1, 1, 1, 1, 1 };
+  size_t smemBytes[5] = { 0, 0, 0, 0, 0 };
+  int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
+  std::vector<int> ctxBase;              // per backward slot, -1 for silent
+  int32_t* dIdTabB = nullptr;
   int numSMs = 148;
   // device tables
   double* dEmitF = nullptr;
@@ -227,6 +230,54 @@ static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program&
   o << "}\n\n";
 }
 
+static int ctx_count (int type, int C, int nOut) { return type == T_MATCH ? C * nOut : type == T_DELETE ? C : type == T_INSERT ? nOut : 0; }
+
+// Backward cell fused with posterior counts (backward.cpp:62-87): for state s and each of its
+// outgoing transition groups, term = w + B(dest cell, dest) feeds both B(s) and
+// exp((F(s) - ll) + term), which is added to the group's accumulator.
+static void gen_cell_counts (std::ostringstream& o, const mb_machine* m, const JitEngine& J) {
+  const Program& p = J.bwd;
+  o << "__device__ __forceinline__ void mb_cell_cnt (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P, const double (&F)[MB_S], float (&cs)[MB_NSIL_B > 0 ? MB_NSIL_B : 1], float* __restrict__ acc, const int c) {\n";
+  for (int q = 0; q < m->S; ++q) {
+    const int d = m->S - 1 - q;
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    if (s0 == s1) o << "  double n" << d << " = mb_neg_inf();\n";
+    for (int k = s0; k < s1; ++k) {
+      const Slot& sl = p.slots[k];
+      o << "  const double t" << k << " = " << term_expr (sl, m->nOut, false) << ";\n";
+      if (k == s0) o << "  double n" << d << " = t" << k << ";\n";
+      else o << "  n" << d << " = mb_lse (n" << d << ", t" << k << ");\n";
+      o << "  { const float p = mb_post (F[" << d << "] + t" << k << "); ";
+      if (sl.type == T_SILENT) o << "cs[" << sl.silIdx << "] += p; }\n";
+      else {
+        o << "acc[(" << J.ctxBase[k] << " + ";
+        if (sl.type == T_MATCH) o << "c * " << m->nOut << " + b";
+        else if (sl.type == T_DELETE) o << "c";
+        else o << "b";
+        o << ") * 32] += p; }\n";
+      }
+    }
+    if (d == m->S - 1) o << "  if (origin) n" << d << " = 0.0;\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
+  o << "}\n\n";
+  // flush: per strip, accumulators -> global double counts
+  o << "__device__ __forceinline__ void mb_flush_counts (float (&cs)[MB_NSIL_B > 0 ? MB_NSIL_B : 1], float* __restrict__ acc, const int (&ta)[MB_C], double* __restrict__ counts, const int32_t* __restrict__ idTab, const int lane) {\n";
+  for (size_t k = 0; k < p.slots.size(); ++k) {
+    const Slot& sl = p.slots[k];
+    if (sl.type == T_SILENT) {
+      o << "  { const float v = mb_warp_sum (cs[" << sl.silIdx << "]); if (lane == 0 && v != 0.f) atomicAdd (counts + " << p.silId[sl.silIdx] << ", (double) v); }\n";
+    } else if (sl.type == T_MATCH) {
+      o << "  _Pragma(\"unroll\") for (int c = 0; c < MB_C; ++c) for (int b = 0; b < " << m->nOut << "; ++b) { const float v = acc[(" << J.ctxBase[k] << " + c * " << m->nOut << " + b) * 32]; if (v != 0.f) { const int id = idTab[" << sl.idOff << " + ta[c] * " << m->nOut << " + b]; if (id >= 0) atomicAdd (counts + id, (double) v); } }\n";
+    } else if (sl.type == T_DELETE) {
+      o << "  _Pragma(\"unroll\") for (int c = 0; c < MB_C; ++c) { const float v = acc[(" << J.ctxBase[k] << " + c) * 32]; if (v != 0.f) { const int id = idTab[" << sl.idOff << " + ta[c]]; if (id >= 0) atomicAdd (counts + id, (double) v); } }\n";
+    } else {
+      o << "  for (int b = 0; b < " << m->nOut << "; ++b) { const float v = acc[(" << J.ctxBase[k] << " + b) * 32]; if (v != 0.f) { const int id = idTab[" << sl.idOff << " + b]; if (id >= 0) atomicAdd (counts + id, (double) v); } }\n";
+    }
+  }
+  o << "}\n\n";
+}
+
 bool jit_supported (const mb_machine* m, std::string* why) {
   auto no = [&] (const char* w) { if (why) *why = w; return false; };
   if (m->S > 16) return no ("more than 16 states");
@@ -240,6 +291,7 @@ bool jit_supported (const mb_machine* m, std::string* why) {
   int totalBits = 0;
   for (int s = 0; s < m->S; ++s) { const int n = f.stateSlot0[s + 1] - f.stateSlot0[s]; int bt = 0; while ((1 << bt) < n) ++bt; totalBits += bt; }
   if (totalBits > 64) return no ("Viterbi back-pointers need more than 64 bits per cell");
+  { const int C = m->S <= 8 ? 4 : 2; int n = 0; for (auto& sl: b.slots) n += ctx_count (sl.type, C, m->nOut); if (n > 160) return no ("too many emitting transition groups for the per-lane count accumulators"); }
   return true;
 }
 
@@ -276,14 +328,16 @@ static int compile (mb_machine* m, JitEngine& J) {
   if (!cu_ok (g_drv.ModuleLoadData (&J.mod, cubin.data()), "cuModuleLoadData")) return 1;
   if (!cu_ok (g_drv.ModuleGetFunction (&J.kForward, J.mod, "mb_k_forward"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackward, J.mod, "mb_k_backward"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")) return 1;
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")) return 1;
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[3] = { J.kForward, J.kBackward, J.kViterbi };
-  const int ne[3] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit };
-  for (int q = 0; q < 3; ++q) {
-    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * m->S) * 8;
+  CUfunction fn[5] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts };
+  const int ne[5] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
+  for (int q = 0; q < 5; ++q) {
+    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * m->S) * 8 + (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * 4;
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
@@ -344,16 +398,26 @@ static void generate (const mb_machine* m, JitEngine& J) {
   while (J.C * J.tbBytes > 16) J.C /= 2;
   if (const char* e = getenv ("MB_JIT_THREADS")) J.threads = std::max (32, std::min (1024, atoi (e) / 32 * 32));
 
+  J.ctxBase.assign (J.bwd.slots.size(), -1);
+  J.nCtx = 0;
+  for (size_t k = 0; k < J.bwd.slots.size(); ++k) {
+    const int n = ctx_count (J.bwd.slots[k].type, J.C, m->nOut);
+    if (n) { J.ctxBase[k] = J.nCtx; J.nCtx += n; }
+  }
+
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << J.C << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
+  o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
-  o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n\n";
+  o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
+  o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n\n";
   gen_cell (o, m, J.fwd, true, false, J);
   gen_cell (o, m, J.bwd, false, false, J);
   gen_cell (o, m, J.fwd, true, true, J);
+  gen_cell_counts (o, m, J);
   o << kJitSkeleton;
   J.source = o.str();
 }
@@ -382,6 +446,8 @@ int jit_prepare (mb_machine* m) {
   MB_CUDA (cudaMalloc (&J.dEmitB, eb.size() * 8));
   MB_CUDA (cudaMalloc (&J.dCounter, 8));
   if (jit_update_weights (m)) return 1;
+  MB_CUDA (cudaMalloc (&J.dIdTabB, std::max<size_t> (J.bwd.idTab.size(), 1) * 4));
+  MB_CUDA (cudaMemcpy (J.dIdTabB, J.bwd.idTab.data(), J.bwd.idTab.size() * 4, cudaMemcpyHostToDevice));
   // traceback plan
   std::vector<int32_t> plan;
   for (int v: J.fwd.stateSlot0) plan.push_back (v);
@@ -403,6 +469,7 @@ void jit_destroy (mb_machine* m) {
   if (J->dEmitF) cudaFree (J->dEmitF);
   if (J->dEmitB) cudaFree (J->dEmitB);
   if (J->dTbPlan) cudaFree (J->dTbPlan);
+  if (J->dIdTabB) cudaFree (J->dIdTabB);
   if (J->dCounter) cudaFree (J->dCounter);
   delete J;
   m->jit = nullptr;
@@ -419,6 +486,10 @@ struct MBArgsHost {   // must match struct MBArgs in the skeleton
   double* result;
   const double* emit;
   uint8_t* tb; const int64_t* tbOff;
+  double* F; const int64_t* fOff;
+  const double* ll;
+  double* counts;
+  const int32_t* idTabB;
 };
 
 struct DevBuf {
@@ -438,9 +509,12 @@ static std::vector<int64_t> cost_order (const mb_batch* b, const std::vector<int
   return o;
 }
 
-static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff) {
+struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; };
+
+static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
+                   const CountArgs& ca = CountArgs()) {
   JitEngine& J = *(JitEngine*) m->jit;
-  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : J.kViterbi;
+  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : J.kBCounts;
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
@@ -457,8 +531,9 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.order = dOrder.as<int64_t>(); A.nWork = (int64_t) order.size(); A.counter = J.dCounter;
   A.bnd = dBnd.as<double>(); A.bndStride = bndStride;
   A.result = dResult;
-  A.emit = which == 1 ? J.dEmitB : J.dEmitF;
+  A.emit = (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
   A.tb = dTb; A.tbOff = dTbOff;
+  A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   void* params[2] = { (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   MB_CUDA (cudaStreamSynchronize (b->stream));   // the workspace buffers above are freed on return
@@ -623,8 +698,48 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
 }
 
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
-  // posterior counts still run on the generic engine's kernels (full Forward and Backward matrices)
-  return generic_counts (m, b, counts, loglike);
+  // MachineCounts over the list (counts.cpp:37-64): per pair a Forward sweep that stores its matrix,
+  // then the fused Backward + posterior-count sweep.  The batch is cut into chunks whose Forward
+  // matrices fit in free device memory.
+  if (b->nPairs == 0) { if (counts) for (int64_t t = 0; t < m->T; ++t) counts[t] = 0; return 0; }
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
+  const double budget = 0.85 * (double) freeB / 8.0;
+  std::vector<std::vector<int64_t>> chunks (1);
+  std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), chunkDoubles (1, 0);
+  for (int64_t k = 0; k < b->nPairs; ++k) {
+    const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
+    const int64_t need = (((Li + 1) * (Lo + 1) * m->S) + 31) & ~(int64_t) 31;
+    if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": the Forward matrix does not fit in device memory"); return 1; }
+    if (!chunks.back().empty() && (double) (chunkDoubles.back() + need) > budget) { chunks.emplace_back(); chunkDoubles.push_back (0); }
+    fOffHost[k] = chunkDoubles.back();
+    chunkDoubles.back() += need;
+    chunks.back().push_back (k);
+  }
+  DevBuf dLL, dBack, dFOff, dCounts;
+  if (dLL.alloc ((size_t) b->nPairs * 8) || dBack.alloc ((size_t) b->nPairs * 8) || dFOff.alloc ((size_t) b->nPairs * 8) || dCounts.alloc ((size_t) std::max<int64_t> (m->T, 1) * 8)) return 1;
+  MB_CUDA (cudaMemcpyAsync (dFOff.p, fOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounts.p, 0, (size_t) std::max<int64_t> (m->T, 1) * 8, b->stream));
+  int64_t launches = 0;
+  double ms = 0;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    const std::vector<int64_t> order = cost_order (b, chunks[c]);
+    DevBuf dF;
+    if (dF.alloc ((size_t) chunkDoubles[c] * 8)) return 1;
+    CountArgs ca;
+    ca.F = dF.as<double>(); ca.fOff = dFOff.as<int64_t>(); ca.ll = dLL.as<double>(); ca.counts = dCounts.as<double>();
+    if (timing_begin (b)) return 1;
+    if (launch (m, b, 3, order, dLL.as<double>(), nullptr, nullptr, ca)) return 1;
+    ++launches;
+    if (counts) { if (launch (m, b, 4, order, dBack.as<double>(), nullptr, nullptr, ca)) return 1; ++launches; }
+    if (timing_end (b, launches)) return 1;
+    ms += b->lastMs;
+  }
+  b->lastMs = ms;
+  b->lastLaunches = launches;
+  if (loglike) MB_CUDA (cudaMemcpy (loglike, dLL.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  if (counts) MB_CUDA (cudaMemcpy (counts, dCounts.p, (size_t) m->T * 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 }  // namespace mb

@@ -31,6 +31,10 @@ struct MBArgs {
   double* result;
   const double* emit;
   uint8_t* tb; const int64_t* tbOff;
+  double* F; const int64_t* fOff;        // full Forward matrices [outPos][inPos][state] (modes 2, 3)
+  const double* ll;                      // Forward log-likelihood per pair (mode 3)
+  double* counts;                        // [nTrans] posterior counts (mode 3)
+  const int32_t* idTabB;                 // transition id per backward-program table entry (mode 3)
 };
 
 __device__ __forceinline__ double mb_neg_inf() { return __longlong_as_double (0xfff0000000000000LL); }
@@ -47,11 +51,26 @@ __device__ __forceinline__ double mb_lse (double a, double b) {
   return mx + (double) g;
 }
 
+// exp(z) for a posterior log-odds z <= ~0, FP32 on the MUFU pipe
+__device__ __forceinline__ float mb_post (double z) {
+  return exp2f (1.4426950408889634f * __double2float_rn (z));
+}
+
+__device__ __forceinline__ float mb_warp_sum (float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (MB_FULL, v, d);
+  return v;
+}
+
 template<int DIR> struct MBDir { };
 template<> struct MBDir<0> { static const int NE = MB_NEMIT_F; static const int RES = MB_S - 1; };
 template<> struct MBDir<1> { static const int NE = MB_NEMIT_B; static const int RES = 0; };
 
-// MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers
+// MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers;
+// MODE 2: Forward that also stores every cell (the E-step's ForwardMatrix, counts.cpp:58);
+// MODE 3: Backward fused with the posterior-count accumulation of BackwardMatrix::getCounts
+//         (backward.cpp:62-87): each transition group's term w + B(dest) is formed once and used
+//         both for the Backward log-sum-exp and for exp(F(src) - ll + term).
 template<int MODE, int DIR>
 __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   extern __shared__ double mb_smem[];
@@ -61,6 +80,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
   double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_S);
+  // thread-private count accumulators of the emitting transition groups: acc[ctx * 32 + lane]
+  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_S)) + warp * (32 * MB_NCTX) + lane;
   const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -79,6 +100,9 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     const int nStrips = (Li + MB_W) / MB_W;
     const int64_t pitch = (int64_t) nStrips * MB_W;
     uint8_t* tb = MODE == 1 ? A.tb + A.tbOff[k] : (uint8_t*) 0;
+    double* Fm = (MODE == 2 || MODE == 3) ? A.F + A.fOff[k] : (double*) 0;
+    const double ll = MODE == 3 ? A.ll[k] : 0.0;
+    if (MODE == 3 && !(ll > NI)) continue;     // impossible pair: no posterior (the reference would produce NaN)
 
     for (int strip = 0; strip < nStrips; ++strip) {
       const int col0 = strip * MB_W + lane * MB_C;
@@ -96,6 +120,12 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         Lk[s] = NI;
 #pragma unroll
         for (int c = 0; c < MB_C; ++c) U[c][s] = NI;
+      }
+      float cs[MB_NSIL_B > 0 ? MB_NSIL_B : 1];
+      if (MODE == 3) {
+#pragma unroll
+        for (int q = 0; q < (MB_NSIL_B > 0 ? MB_NSIL_B : 1); ++q) cs[q] = 0.f;
+        for (int q = 0; q < MB_NCTX; ++q) acc[q * 32] = 0.f;
       }
       const double* bin = (strip & 1) ? bndB : bndA;
       double* bout = (strip & 1) ? bndA : bndB;
@@ -136,9 +166,27 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
             const bool origin = (r == 0) && (col0 + c == 0);
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 2) {
               if (DIR == 0) mb_cell_fwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               else mb_cell_bwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              if (MODE == 2 && col0 + c <= Li) {
+                double2* fp = (double2*) (Fm + ((int64_t) r * (Li + 1) + (col0 + c)) * MB_S);
+#pragma unroll
+                for (int s = 0; s + 1 < MB_S; s += 2) fp[s >> 1] = make_double2 (N[s], N[s + 1]);
+                if (MB_S & 1) Fm[((int64_t) r * (Li + 1) + (col0 + c)) * MB_S + MB_S - 1] = N[MB_S - 1];
+              }
+            } else if (MODE == 3) {
+              double Fc[MB_S];
+              const int col = col0 + c;
+              if (col <= Li) {
+                const double* fp = Fm + ((int64_t) (Lo - r) * (Li + 1) + (Li - col)) * MB_S;
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s) Fc[s] = __ldcs (fp + s) - ll;
+              } else {
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s) Fc[s] = NI;
+              }
+              mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
               const unsigned long long word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               const int sh = 8 * MB_TBBYTES * c;
@@ -167,6 +215,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           }
         }
       }
+      if (MODE == 3) mb_flush_counts (cs, acc, ta, A.counts, A.idTabB, lane);
       __syncwarp();
     }
   }
@@ -174,6 +223,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
 )MBSRC";
 
