@@ -170,10 +170,14 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               if (DIR == 0) mb_cell_fwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               else mb_cell_bwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               if (MODE == 2 && col0 + c <= Li) {
-                double2* fp = (double2*) (Fm + ((int64_t) r * (Li + 1) + (col0 + c)) * MB_S);
+                double* fq = Fm + ((int64_t) r * (Li + 1) + (col0 + c)) * MB_S;
+                if ((MB_S & 1) == 0) {      // 16-byte aligned rows of states: vector stores
 #pragma unroll
-                for (int s = 0; s + 1 < MB_S; s += 2) fp[s >> 1] = make_double2 (N[s], N[s + 1]);
-                if (MB_S & 1) Fm[((int64_t) r * (Li + 1) + (col0 + c)) * MB_S + MB_S - 1] = N[MB_S - 1];
+                  for (int s = 0; s + 1 < MB_S; s += 2) ((double2*) fq)[s >> 1] = make_double2 (N[s], N[s + 1]);
+                } else {
+#pragma unroll
+                  for (int s = 0; s < MB_S; ++s) fq[s] = N[s];
+                }
               }
             } else if (MODE == 3) {
               double Fc[MB_S];
