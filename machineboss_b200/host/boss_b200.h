@@ -1,0 +1,544 @@
+// boss_b200.h -- host-side mirror of the reference's C++ surface for the batched
+// Forward / Backward / Viterbi path, on top of the C ABI (include/machineboss_b200.h).
+//
+// Same names, argument meaning and error behaviour as the reference classes, so code written
+// against   EvaluatedMachine / SeqPair / SeqPairList / ForwardMatrix / RollingOutputForwardMatrix /
+// BackwardMatrix / ViterbiMatrix / MachineCounts   (src/eval.h:59-98, src/seqpair.h:18-121,
+// src/forward.h:8-28, src/backward.h:10-56, src/viterbi.h:8-17, src/counts.h:11-25) keeps working,
+// with every DP running on the GPU.  What is NOT mirrored is the symbolic layer (Machine,
+// WeightExpr, Params: SURVEY.md section 2 rows 13-15): an EvaluatedMachine is built here from
+// numbers -- its flat JSON form, or (states, alphabets, transitions) -- not from Machine + Params.
+// INTEGRATION.md shows the ten-line adapter that flattens the reference's own EvaluatedMachine.
+//
+// Differences a caller can observe, all deliberate:
+//   * matrices do not expose cell(i,o,s): the fills keep O(strip) state on the device;
+//   * Envelope arguments are accepted and, as in the reference (dpmatrix.defs.h:3,17 build the
+//     index mapper from the SeqPair), ignored; a SeqPair carrying an alignment would select a
+//     path envelope in the reference and is rejected here (banded DP is SURVEY 8(f) row 3);
+//   * the batched entry points (MachineCounts over a list, forwardLogLikes, viterbiPaths) send
+//     the whole SeqPairList to the device in one call instead of looping.
+#ifndef MB_HOST_BOSS_B200_H
+#define MB_HOST_BOSS_B200_H
+
+#include <cstdint>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/machineboss_b200.h"
+#include "mbjson.h"
+
+namespace MachineBoss {
+
+using std::list;
+using std::map;
+using std::ostream;
+using std::runtime_error;
+using std::string;
+using std::vector;
+
+typedef unsigned long long StateIndex;
+typedef string InputSymbol;
+typedef string OutputSymbol;
+typedef int InputToken;
+typedef int OutputToken;
+typedef double LogWeight;
+
+inline void mbCheck (int rc) { if (rc != 0) throw runtime_error (mb_last_error()); }   // Assert -> Abort -> throw (util.cpp:39-48)
+
+// infinity-safe number printing, default stream precision (src/jsonio.h:14-22)
+inline string toInfinitySafeString (double x) {
+  if (x == std::numeric_limits<double>::infinity()) return "\"Infinity\"";
+  if (x == -std::numeric_limits<double>::infinity()) return "\"-Infinity\"";
+  std::ostringstream out;
+  out << x;
+  return out.str();
+}
+
+// ---- Tokenizer (src/eval.h:11-49): token 0 is the empty string, 1..N follow the alphabet order ----
+template<typename Symbol, typename Token>
+struct Tokenizer {
+  vector<Symbol> tok2sym;
+  map<Symbol, Token> sym2tok;
+  Tokenizer() { tok2sym.push_back (Symbol()); sym2tok[Symbol()] = 0; }
+  Tokenizer (const vector<Symbol>& symbols) {
+    tok2sym.push_back (Symbol());
+    tok2sym.insert (tok2sym.end(), symbols.begin(), symbols.end());
+    for (Token tok = 0; tok < (Token) tok2sym.size(); ++tok) sym2tok[tok2sym[tok]] = tok;
+  }
+  static inline Token emptyToken() { return 0; }
+  bool canTokenize (const vector<Symbol>& symSeq) const {
+    for (const auto& sym: symSeq) if (!sym2tok.count (sym)) return false;
+    return true;
+  }
+  vector<Token> tokenize (const vector<Symbol>& symSeq) const {
+    vector<Token> tokSeq;
+    tokSeq.reserve (symSeq.size());
+    for (const auto& sym: symSeq) {
+      if (!sym2tok.count (sym)) {
+        std::ostringstream err;
+        err << "Can't tokenize symbol " << sym << " using this alphabet:";
+        for (const auto& s: tok2sym) err << ' ' << s;
+        throw runtime_error (err.str());
+      }
+      tokSeq.push_back (sym2tok.at (sym));
+    }
+    return tokSeq;
+  }
+  vector<Symbol> detokenize (const vector<Token>& tokSeq) const {
+    vector<Symbol> symSeq;
+    for (auto tok: tokSeq) symSeq.push_back (tok2sym[tok]);
+    return symSeq;
+  }
+};
+typedef Tokenizer<InputSymbol, InputToken> InputTokenizer;
+typedef Tokenizer<OutputSymbol, OutputToken> OutputTokenizer;
+
+// ---- sequences (src/seqpair.h:18-73) ----
+template<typename Symbol>
+struct NamedSeq {
+  string name;
+  vector<Symbol> seq;
+  void readJson (const Json& j) {
+    if (j.has ("name")) name = j.at ("name").asString();
+    seq.clear();
+    for (const auto& s: j.at ("sequence").arr) seq.push_back (s.asString());
+  }
+  void writeJson (ostream& out) const {
+    out << "{\"name\":\"" << name << "\",\"sequence\":[";
+    for (size_t n = 0; n < seq.size(); ++n) out << (n > 0 ? "," : "") << "\"" << seq[n] << "\"";
+    out << "]}";
+  }
+};
+typedef NamedSeq<InputSymbol> NamedInputSeq;
+typedef NamedSeq<OutputSymbol> NamedOutputSeq;
+
+// A transition on a path: what the reference's MachinePath stores per step (machine.h:207-218),
+// plus its source state and index so callers can map it back to MachineCounts::count[src][index].
+struct MachineTransition {
+  InputSymbol in;
+  OutputSymbol out;
+  StateIndex src = 0, dest = 0;
+  size_t transIndex = 0;
+  int32_t id = 0;   // global transition id = transOffset[src] + transIndex
+  LogWeight logWeight = 0;
+  bool inputEmpty() const { return in.empty(); }
+  bool outputEmpty() const { return out.empty(); }
+  bool isSilent() const { return in.empty() && out.empty(); }
+};
+typedef list<MachineTransition> TransList;
+
+struct EvaluatedMachine;
+
+struct MachinePath {
+  typedef std::pair<InputSymbol, OutputSymbol> AlignCol;
+  typedef list<AlignCol> AlignPath;
+  TransList trans;
+  AlignPath alignment() const {   // seqpair.cpp:59-65
+    AlignPath ap;
+    for (const auto& t: trans) if (!t.isSilent()) ap.push_back (AlignCol (t.in, t.out));
+    return ap;
+  }
+  void writeJson (ostream& out, const EvaluatedMachine& m) const;   // machine.cpp:1980-1998
+};
+
+struct SeqPair {
+  typedef MachinePath::AlignCol AlignCol;
+  typedef MachinePath::AlignPath AlignPath;
+  NamedInputSeq input;
+  NamedOutputSeq output;
+  AlignPath alignment;
+  Json metadata;
+  void readJson (const Json& pj) {   // seqpair.cpp:8-38
+    input.name = "input";
+    output.name = "output";
+    if (pj.has ("alignment")) {
+      vector<InputSymbol> in;
+      vector<OutputSymbol> out;
+      for (const auto& col: pj.at ("alignment").arr) {
+        const string inSym = col.at (0).asString(), outSym = col.at (1).asString();
+        if (inSym.size()) in.push_back (inSym);
+        if (outSym.size()) out.push_back (outSym);
+        alignment.push_back (AlignCol (inSym, outSym));
+      }
+      input.seq = in;
+      output.seq = out;
+      if (pj.has ("input") && pj.at ("input").has ("name")) input.name = pj.at ("input").at ("name").asString();
+      if (pj.has ("output") && pj.at ("output").has ("name")) output.name = pj.at ("output").at ("name").asString();
+      if (pj.has ("meta")) metadata = pj.at ("meta");
+    } else {
+      input.readJson (pj.at ("input"));
+      output.readJson (pj.at ("output"));
+    }
+  }
+  void writeJson (ostream& out) const {   // seqpair.cpp:40-57
+    out << "{\"input\":";
+    input.writeJson (out);
+    out << ",\"output\":";
+    output.writeJson (out);
+    if (alignment.size()) {
+      out << ",\"alignment\":[";
+      size_t n = 0;
+      for (const auto& col: alignment) out << (n++ ? "," : "") << "[\"" << Json::escape (col.first) << "\",\"" << Json::escape (col.second) << "\"]";
+      out << "]";
+    }
+    if (!metadata.isNull()) { out << ",\"meta\":"; metadata.write (out); }
+    out << "}";
+  }
+  static SeqPair seqPairFromPath (const MachinePath& mp, const EvaluatedMachine& m, const char* inputName = "input", const char* outputName = "output");
+};
+
+struct SeqPairList {
+  list<SeqPair> seqPairs;
+  void readJson (const Json& pj) { for (const auto& j: pj.arr) { SeqPair sp; sp.readJson (j); seqPairs.push_back (sp); } }
+  void writeJson (ostream& out) const {   // seqpair.cpp:251-259
+    out << "[";
+    size_t n = 0;
+    for (const auto& sp: seqPairs) { out << (n++ ? ",\n " : ""); sp.writeJson (out); }
+    out << "]";
+  }
+  static SeqPairList fromFile (const string& filename) {
+    std::ifstream in (filename);
+    if (!in) throw runtime_error ("File not found: " + filename);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    SeqPairList l;
+    l.readJson (Json::parse (ss.str()));
+    return l;
+  }
+};
+
+// Accepted for signature compatibility; the reference itself ignores a caller-supplied envelope.
+struct Envelope {
+  long inLen = 0, outLen = 0;
+  Envelope() {}
+  Envelope (const SeqPair& sp) : inLen ((long) sp.input.seq.size()), outLen ((long) sp.output.seq.size()) {}
+};
+
+// ---- EvaluatedMachine (src/eval.h:59-98) ----
+struct EvaluatedMachineState {
+  typedef size_t TransIndex;
+  Json name;
+  TransIndex nTransitions = 0, transOffset = 0;
+  vector<LogWeight> logTransWeight;   // indexed by TransIndex
+};
+
+struct EvaluatedMachine {
+  InputTokenizer inputTokenizer;
+  OutputTokenizer outputTokenizer;
+  vector<EvaluatedMachineState> state;
+  EvaluatedMachineState::TransIndex nTransitions = 0;
+  // flat form, enumeration order of eval.cpp:49-69
+  vector<int32_t> src, dst, in, out;
+  vector<double> logWeight;
+
+  EvaluatedMachine() {}
+  // transitions: (src, dest, input symbol, output symbol, log-weight), grouped by ascending src
+  EvaluatedMachine (size_t nStates, const vector<InputSymbol>& inAlphabet, const vector<OutputSymbol>& outAlphabet,
+                    const vector<MachineTransition>& transitions, const vector<Json>& stateNames = vector<Json>())
+    : inputTokenizer (inAlphabet), outputTokenizer (outAlphabet), state (nStates)
+  {
+    for (size_t s = 0; s < stateNames.size() && s < nStates; ++s) state[s].name = stateNames[s];
+    for (const auto& t: transitions) {
+      src.push_back ((int32_t) t.src); dst.push_back ((int32_t) t.dest);
+      in.push_back (inputTokenizer.sym2tok.at (t.in)); out.push_back (outputTokenizer.sym2tok.at (t.out));
+      logWeight.push_back (t.logWeight);
+    }
+    index();
+  }
+  // {"nStates":..,"inAlphabet":[..],"outAlphabet":[..],"stateNames":[..],"trans":[[src,dst,inTok,outTok,logWeight,transIndex],..]}
+  static EvaluatedMachine fromJson (const Json& j) {
+    EvaluatedMachine m;
+    vector<InputSymbol> ia;
+    vector<OutputSymbol> oa;
+    for (const auto& s: j.at ("inAlphabet").arr) ia.push_back (s.asString());
+    for (const auto& s: j.at ("outAlphabet").arr) oa.push_back (s.asString());
+    m.inputTokenizer = InputTokenizer (ia);
+    m.outputTokenizer = OutputTokenizer (oa);
+    m.state.resize ((size_t) j.at ("nStates").asInt());
+    if (j.has ("stateNames"))
+      for (size_t s = 0; s < j.at ("stateNames").size() && s < m.state.size(); ++s) m.state[s].name = j.at ("stateNames").at (s);
+    for (const auto& t: j.at ("trans").arr) {
+      m.src.push_back ((int32_t) t.at (0).asInt()); m.dst.push_back ((int32_t) t.at (1).asInt());
+      m.in.push_back ((int32_t) t.at (2).asInt()); m.out.push_back ((int32_t) t.at (3).asInt());
+      m.logWeight.push_back (t.at (4).asNumber());
+    }
+    m.index();
+    return m;
+  }
+  static EvaluatedMachine fromFile (const string& filename) {
+    std::ifstream f (filename);
+    if (!f) throw runtime_error ("File not found: " + filename);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return fromJson (Json::parse (ss.str()));
+  }
+
+  StateIndex nStates() const { return state.size(); }
+  StateIndex startState() const { if (!nStates()) throw runtime_error ("EvaluatedMachine has no states"); return 0; }
+  StateIndex endState() const { if (!nStates()) throw runtime_error ("EvaluatedMachine has no states"); return nStates() - 1; }
+  bool canTokenize (const SeqPair& sp) const { return inputTokenizer.canTokenize (sp.input.seq) && outputTokenizer.canTokenize (sp.output.seq); }
+  string stateNameJson (StateIndex s) const { return state[s].name.isNull() ? std::to_string (s) : state[s].name.dump(); }
+
+  MachineTransition transition (int32_t id) const {
+    MachineTransition t;
+    t.id = id; t.src = (StateIndex) src[id]; t.dest = (StateIndex) dst[id];
+    t.in = inputTokenizer.tok2sym[in[id]]; t.out = outputTokenizer.tok2sym[out[id]];
+    t.transIndex = (size_t) id - state[src[id]].transOffset;
+    t.logWeight = logWeight[id];
+    return t;
+  }
+
+  // new log-weights for the same structure (what EvaluatedMachine(machine, params) recomputes per EM iteration)
+  void setLogWeights (const vector<double>& lw) {
+    if (lw.size() != logWeight.size()) throw runtime_error ("setLogWeights: size mismatch");
+    logWeight = lw;
+    for (auto& st: state) for (size_t t = 0; t < st.nTransitions; ++t) st.logTransWeight[t] = lw[st.transOffset + t];
+    if (dev) mbCheck (mb_machine_update_weights (dev->h, logWeight.data()));
+  }
+
+  mb_machine* handle() const {   // device copy, created on first use
+    if (!dev) {
+      std::shared_ptr<Dev> d (new Dev);
+      mbCheck (mb_machine_create (&d->h, (int32_t) nStates(), (int32_t) inputTokenizer.tok2sym.size() - 1, (int32_t) outputTokenizer.tok2sym.size() - 1,
+                                  (int64_t) src.size(), src.data(), dst.data(), in.data(), out.data(), logWeight.data()));
+      dev = d;
+    }
+    return dev->h;
+  }
+
+private:
+  struct Dev { mb_machine* h = nullptr; ~Dev() { if (h) mb_machine_destroy (h); } };
+  mutable std::shared_ptr<Dev> dev;
+  void index() {
+    nTransitions = src.size();
+    for (size_t t = 0; t < src.size(); ++t) {
+      if (src[t] < 0 || (size_t) src[t] >= state.size()) throw runtime_error ("EvaluatedMachine: transition source out of range");
+      if (t && src[t] < src[t - 1]) throw runtime_error ("EvaluatedMachine: transitions must be grouped by ascending source state");
+      state[src[t]].logTransWeight.push_back (logWeight[t]);
+    }
+    size_t cum = 0;
+    for (auto& st: state) { st.nTransitions = st.logTransWeight.size(); st.transOffset = cum; cum += st.nTransitions; }
+  }
+};
+
+inline void MachinePath::writeJson (ostream& out, const EvaluatedMachine& m) const {
+  out << "{\"start\":" << m.startState();
+  if (!m.state[m.startState()].name.isNull()) out << ",\"id\":" << m.state[m.startState()].name.dump();
+  out << ",\"trans\":[";
+  size_t n = 0;
+  for (const auto& t: trans) {
+    out << (n++ ? "," : "") << "{\"to\":" << t.dest;
+    if (!m.state[t.dest].name.isNull()) out << ",\"id\":" << m.state[t.dest].name.dump();
+    if (!t.inputEmpty()) out << ",\"in\":\"" << Json::escape (t.in) << "\"";
+    if (!t.outputEmpty()) out << ",\"out\":\"" << Json::escape (t.out) << "\"";
+    out << "}";
+  }
+  out << "]}";
+}
+
+inline SeqPair SeqPair::seqPairFromPath (const MachinePath& mp, const EvaluatedMachine& m, const char* inputName, const char* outputName) {
+  SeqPair sp;   // seqpair.cpp:83-89
+  sp.alignment = mp.alignment();
+  sp.input.name = inputName;
+  sp.output.name = outputName;
+  for (const auto& col: sp.alignment) {
+    if (col.first.size()) sp.input.seq.push_back (col.first);
+    if (col.second.size()) sp.output.seq.push_back (col.second);
+  }
+  std::ostringstream p;
+  mp.writeJson (p, m);
+  Json meta;
+  meta.type = Json::Object;
+  meta.obj["path"] = Json::parse (p.str());   // like the reference, the path goes through a JSON object (keys sorted)
+  sp.metadata = meta;
+  return sp;
+}
+
+// ---- a tokenised SeqPairList on the device ----
+class DeviceBatch {
+public:
+  DeviceBatch (const EvaluatedMachine& m, const vector<const SeqPair*>& pairs) : n ((int64_t) pairs.size()) {
+    vector<uint8_t> x, y;
+    vector<int64_t> xo (1, 0), yo (1, 0);
+    for (const SeqPair* sp: pairs) {
+      if (sp->alignment.size()) throw runtime_error ("SeqPair carries an alignment (path envelope): banded DP is not supported by the B200 engine");
+      for (auto t: m.inputTokenizer.tokenize (sp->input.seq)) x.push_back ((uint8_t) t);     // throws on unknown symbols (eval.h:33-37)
+      for (auto t: m.outputTokenizer.tokenize (sp->output.seq)) y.push_back ((uint8_t) t);
+      xo.push_back ((int64_t) x.size());
+      yo.push_back ((int64_t) y.size());
+    }
+    mbCheck (mb_batch_create (&h, n, x.data(), xo.data(), y.data(), yo.data()));
+  }
+  ~DeviceBatch() { if (h) mb_batch_destroy (h); }
+  DeviceBatch (const DeviceBatch&) = delete;
+  DeviceBatch& operator= (const DeviceBatch&) = delete;
+  mb_batch* handle() const { return h; }
+  int64_t size() const { return n; }
+private:
+  mb_batch* h = nullptr;
+  int64_t n;
+};
+
+inline vector<const SeqPair*> pairPointers (const SeqPairList& l) {
+  vector<const SeqPair*> v;
+  for (const auto& sp: l.seqPairs) v.push_back (&sp);
+  return v;
+}
+
+// ---- Forward (src/forward.h:8-28) ----
+class ForwardMatrix {
+public:
+  const EvaluatedMachine& machine;
+  const SeqPair& seqPair;
+  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
+  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  double logLike() const { return ll; }
+private:
+  double ll = 0;
+  void fill() {
+    DeviceBatch b (machine, vector<const SeqPair*> (1, &seqPair));
+    mbCheck (mb_forward (machine.handle(), b.handle(), &ll));
+  }
+};
+typedef ForwardMatrix RollingOutputForwardMatrix;   // forward.h:28: same result, the device never stores the matrix
+
+struct MachineCounts;
+
+// ---- Backward (src/backward.h:10-56) ----
+class BackwardMatrix {
+public:
+  const EvaluatedMachine& machine;
+  const SeqPair& seqPair;
+  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
+  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  double logLike() const { return ll; }
+  void getCounts (const ForwardMatrix&, MachineCounts&) const;   // backward.cpp:58-60
+private:
+  double ll = 0;
+  void fill() {
+    DeviceBatch b (machine, vector<const SeqPair*> (1, &seqPair));
+    mbCheck (mb_backward (machine.handle(), b.handle(), &ll));
+  }
+};
+
+// ---- Viterbi (src/viterbi.h:8-17) ----
+class ViterbiMatrix {
+public:
+  const EvaluatedMachine& machine;
+  const SeqPair& seqPair;
+  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
+  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  double logLike() const { return ll; }
+  MachinePath path() const {   // viterbi.cpp:49-51 -> traceBack; asserts a finite end cell (dpmatrix.defs.h:84)
+    if (!(ll > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceback: no finite-weight paths");
+    MachinePath p;
+    for (int32_t id: ids) p.trans.push_back (machine.transition (id));
+    return p;
+  }
+  template<class AnyMachine> MachinePath path (const AnyMachine&) const { return path(); }
+private:
+  double ll = 0;
+  vector<int32_t> ids;
+  void fill() {
+    DeviceBatch b (machine, vector<const SeqPair*> (1, &seqPair));
+    int64_t len = 0, off = 0;
+    mbCheck (mb_viterbi (machine.handle(), b.handle(), &ll, &len));
+    ids.resize ((size_t) len);
+    if (len) mbCheck (mb_viterbi_paths (b.handle(), ids.data(), &off));
+  }
+};
+
+// ---- E-step accumulator (src/counts.h:11-25, counts.cpp:24-71) ----
+struct MachineCounts {
+  vector<vector<double> > count;   // indexed: count[state][nTrans]
+  double loglike = 0;
+  MachineCounts() {}
+  MachineCounts (const EvaluatedMachine& m) { init (m); }
+  MachineCounts (const EvaluatedMachine& m, const SeqPair& sp) { init (m); (void) add (m, sp); }
+  MachineCounts (const EvaluatedMachine& m, const SeqPairList& l, const list<Envelope>& = list<Envelope>()) {
+    init (m);
+    addBatch (m, pairPointers (l));   // one device call for the whole list (the reference loops, counts.cpp:41-42)
+  }
+  void init (const EvaluatedMachine& m) {
+    loglike = 0;
+    count = vector<vector<double> > (m.nStates());
+    for (StateIndex s = 0; s < m.nStates(); ++s) count[s].assign (m.state[s].nTransitions, 0.);
+  }
+  double add (const EvaluatedMachine& m, const SeqPair& sp) { return addBatch (m, vector<const SeqPair*> (1, &sp)); }
+  double add (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) { return add (m, sp); }
+  double addBatch (const EvaluatedMachine& m, const vector<const SeqPair*>& pairs) {
+    DeviceBatch b (m, pairs);
+    vector<double> c (m.nTransitions ? m.nTransitions : 1, 0.), ll (pairs.size() ? pairs.size() : 1, 0.);
+    mbCheck (mb_counts (m.handle(), b.handle(), c.data(), ll.data()));
+    double total = 0;
+    for (size_t k = 0; k < pairs.size(); ++k) total += ll[k];
+    for (StateIndex s = 0; s < m.nStates(); ++s)
+      for (size_t t = 0; t < count[s].size(); ++t) count[s][t] += c[m.state[s].transOffset + t];
+    loglike += total;
+    return total;
+  }
+  MachineCounts& operator+= (const MachineCounts& o) {
+    for (size_t s = 0; s < count.size(); ++s) for (size_t t = 0; t < count[s].size(); ++t) count[s][t] += o.count[s][t];
+    return *this;
+  }
+  void writeJson (ostream& outs) const {   // counts.cpp:73-78
+    outs << "[";
+    for (size_t s = 0; s < count.size(); ++s) {
+      outs << (s ? ",\n " : "") << "[";
+      for (size_t t = 0; t < count[s].size(); ++t) outs << (t ? "," : "") << count[s][t];
+      outs << "]";
+    }
+    outs << "]" << std::endl;
+  }
+};
+
+inline void BackwardMatrix::getCounts (const ForwardMatrix&, MachineCounts& counts) const {
+  if (counts.count.empty()) counts.init (machine);
+  const double before = counts.loglike;
+  counts.add (machine, seqPair);
+  counts.loglike = before;   // getCounts does not touch loglike (counts.cpp:61-62 adds it in add())
+}
+
+// ---- batched entry points (no reference equivalent: the reference loops over the list) ----
+inline vector<double> forwardLogLikes (const EvaluatedMachine& m, const SeqPairList& l) {
+  DeviceBatch b (m, pairPointers (l));
+  vector<double> ll (l.seqPairs.size());
+  if (ll.size()) mbCheck (mb_forward (m.handle(), b.handle(), ll.data()));
+  return ll;
+}
+
+inline vector<double> viterbiLogLikes (const EvaluatedMachine& m, const SeqPairList& l, vector<MachinePath>* paths = nullptr) {
+  DeviceBatch b (m, pairPointers (l));
+  const size_t n = l.seqPairs.size();
+  vector<double> sc (n);
+  if (!n) return sc;
+  if (!paths) { mbCheck (mb_viterbi (m.handle(), b.handle(), sc.data(), nullptr)); return sc; }
+  vector<int64_t> len (n), off (n + 1, 0);
+  mbCheck (mb_viterbi (m.handle(), b.handle(), sc.data(), len.data()));
+  for (size_t k = 0; k < n; ++k) off[k + 1] = off[k] + len[k];
+  vector<int32_t> ids ((size_t) off[n] ? (size_t) off[n] : 1);
+  if (off[n]) mbCheck (mb_viterbi_paths (b.handle(), ids.data(), off.data()));
+  paths->assign (n, MachinePath());
+  for (size_t k = 0; k < n; ++k)
+    for (int64_t q = off[k]; q < off[k + 1]; ++q) (*paths)[k].trans.push_back (m.transition (ids[q]));
+  return sc;
+}
+
+// api.h:25-31 equivalents taking an already-evaluated machine
+inline double forwardLogLike (const EvaluatedMachine& m, const SeqPair& sp) { return ForwardMatrix (m, sp).logLike(); }
+inline double viterbiLogLike (const EvaluatedMachine& m, const SeqPair& sp) { return ViterbiMatrix (m, sp).logLike(); }
+inline MachinePath viterbiAlign (const EvaluatedMachine& m, const SeqPair& sp) { return ViterbiMatrix (m, sp).path(); }
+inline MachineCounts forwardBackwardCounts (const EvaluatedMachine& m, const SeqPair& sp) { return MachineCounts (m, sp); }
+inline MachineCounts forwardBackwardCounts (const EvaluatedMachine& m, const SeqPairList& l) { return MachineCounts (m, l); }
+
+}  // namespace MachineBoss
+
+#endif

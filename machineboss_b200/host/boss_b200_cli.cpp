@@ -1,0 +1,132 @@
+// boss_b200_cli.cpp -- the `boss` verbs that reach the DP hot path (target/boss.cpp:725-848),
+// running on the B200 engine:
+//
+//   boss_b200 --evaluated-machine M.json [data options] -L | -V | -A | -C
+//
+//   -L, --loglike   Forward log-likelihoods, printed like boss.cpp:792-808:  [["in","out",ll],...]
+//   -V, --viterbi   Viterbi log-likelihoods, same layout                     (boss.cpp:819-848)
+//   -A, --align     Viterbi alignments as a SeqPairList with meta.path       (boss.cpp:833,843-846)
+//   -C, --counts    raw expected transition counts, MachineCounts::writeJson (counts.cpp:73-78)
+//                   (boss -C prints PARAMETER counts, which needs the symbolic weight derivatives
+//                   of the Machine -- outside this path)
+//   data: -D/--data pairs.json (a SeqPairList) | --input-fasta X --output-fasta Y |
+//         --input-chars S --output-chars S   (all inputs x all outputs, boss.cpp:763-765)
+//
+// The machine is given already evaluated (flat JSON: states, alphabets, numeric log-weights),
+// because building it from a symbolic Machine + Params is the reference's job.
+// Numbers are printed with the stream's default 6 significant digits, like boss (jsonio.h:19-21).
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "boss_b200.h"
+
+using namespace MachineBoss;
+using namespace std;
+
+static vector<NamedSeq<string> > readFasta (const string& filename) {
+  ifstream in (filename);
+  if (!in) throw runtime_error ("File not found: " + filename);
+  vector<NamedSeq<string> > seqs;
+  string line;
+  while (getline (in, line)) {
+    if (line.size() && line[0] == '>') {
+      NamedSeq<string> s;
+      const size_t e = line.find_first_of (" \t", 1);
+      s.name = line.substr (1, e == string::npos ? string::npos : e - 1);
+      seqs.push_back (s);
+    } else if (seqs.size())
+      for (char c: line) if (!isspace ((unsigned char) c)) seqs.back().seq.push_back (string (1, c));   // splitToChars
+  }
+  return seqs;
+}
+
+static NamedSeq<string> fromChars (const string& s) {
+  NamedSeq<string> n;
+  n.name = s;
+  for (char c: s) n.seq.push_back (string (1, c));
+  return n;
+}
+
+int main (int argc, char** argv) {
+  try {
+    string machineFile;
+    vector<string> dataFiles;
+    vector<NamedSeq<string> > inSeqs, outSeqs;
+    bool doL = false, doV = false, doA = false, doC = false;
+    for (int a = 1; a < argc; ++a) {
+      const string f = argv[a];
+      auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
+      if (f == "--evaluated-machine" || f == "-m") machineFile = next();
+      else if (f == "-D" || f == "--data") dataFiles.push_back (next());
+      else if (f == "--input-fasta") { for (auto& s: readFasta (next())) inSeqs.push_back (s); }
+      else if (f == "--output-fasta") { for (auto& s: readFasta (next())) outSeqs.push_back (s); }
+      else if (f == "--input-chars") inSeqs.push_back (fromChars (next()));
+      else if (f == "--output-chars") outSeqs.push_back (fromChars (next()));
+      else if (f == "-L" || f == "--loglike") doL = true;
+      else if (f == "-V" || f == "--viterbi") doV = true;
+      else if (f == "-A" || f == "--align") doA = true;
+      else if (f == "-C" || f == "--counts") doC = true;
+      else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
+      else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
+      else throw runtime_error ("unknown option " + f);
+    }
+    if (machineFile.empty()) throw runtime_error ("please specify --evaluated-machine");
+    const EvaluatedMachine eval = EvaluatedMachine::fromFile (machineFile);
+
+    SeqPairList data;
+    for (const auto& df: dataFiles) { SeqPairList l = SeqPairList::fromFile (df); data.seqPairs.insert (data.seqPairs.end(), l.seqPairs.begin(), l.seqPairs.end()); }
+    const bool inputEmpty = eval.inputTokenizer.tok2sym.size() == 1, outputEmpty = eval.outputTokenizer.tok2sym.size() == 1;
+    if (inSeqs.empty() && inputEmpty && !outSeqs.empty()) inSeqs.push_back (NamedSeq<string>());    // boss.cpp:757-760
+    if (outSeqs.empty() && !inSeqs.empty() && outputEmpty) outSeqs.push_back (NamedSeq<string>());
+    for (const auto& i: inSeqs) for (const auto& o: outSeqs) { SeqPair sp; sp.input = i; sp.output = o; data.seqPairs.push_back (sp); }
+    if (data.seqPairs.empty() && inputEmpty && outputEmpty) data.seqPairs.push_back (SeqPair());   // boss.cpp:769-770
+    if (data.seqPairs.empty()) throw runtime_error ("no sequence data given");
+    if (!(doL || doV || doA || doC)) throw runtime_error ("nothing to do: give -L, -V, -A or -C");
+
+    // pairs the machine cannot tokenise report -Infinity under -L/-V/-A (boss.cpp:798,826) ...
+    SeqPairList ok;
+    vector<int> okIndex;
+    int n = 0;
+    for (const auto& sp: data.seqPairs) { if (eval.canTokenize (sp)) { ok.seqPairs.push_back (sp); okIndex.push_back (n); } ++n; }
+    const double ninf = -numeric_limits<double>::infinity();
+
+    auto printScores = [&] (const vector<double>& okScores) {
+      vector<double> all (data.seqPairs.size(), ninf);
+      for (size_t k = 0; k < okScores.size(); ++k) all[okIndex[k]] = okScores[k];
+      cout << "[";
+      size_t k = 0;
+      for (const auto& sp: data.seqPairs) {
+        cout << (k ? ",\n " : "") << "[\"" << Json::escape (sp.input.name) << "\",\"" << Json::escape (sp.output.name) << "\"," << toInfinitySafeString (all[k]) << "]";
+        ++k;
+      }
+      cout << "]\n";
+    };
+
+    if (doL) printScores (forwardLogLikes (eval, ok));
+    if (doC) {
+      // ... but -C does not test canTokenize (boss.cpp:811-816): an unknown symbol throws
+      const MachineCounts counts (eval, data);
+      counts.writeJson (cout);
+    }
+    if (doA || doV) {
+      vector<MachinePath> paths;
+      const vector<double> sc = viterbiLogLikes (eval, ok, doA ? &paths : nullptr);
+      if (doV) printScores (sc);
+      if (doA) {
+        SeqPairList results;
+        size_t k = 0;
+        for (const auto& sp: ok.seqPairs) {
+          if (sc[k] > ninf) results.seqPairs.push_back (SeqPair::seqPairFromPath (paths[k], eval, sp.input.name.c_str(), sp.output.name.c_str()));
+          ++k;
+        }
+        results.writeJson (cout);
+        cout << endl;
+      }
+    }
+  } catch (const std::exception& e) {
+    cerr << e.what() << endl;
+    return EXIT_FAILURE;   // boss.cpp:923-926
+  }
+  return EXIT_SUCCESS;
+}

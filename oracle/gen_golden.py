@@ -116,7 +116,8 @@ def main():
         al = json.load(f)
     case("stutter_noise_difflen", [T("t/machine/bitstutter.json"), T("t/machine/bitnoise.json")], [("01", "101")],
          params=pq99, matrices=True,
-         ref_expect={"path_to": [t["to"] for t in al[0]["meta"]["path"]["trans"]],
+         ref_expect={"align_output": open(os.path.join(REF, "t/expect/align-stutter-noise-difflen.json")).read(),
+                     "path_to": [t["to"] for t in al[0]["meta"]["path"]["trans"]],
                      "path_in": [t.get("in", "") for t in al[0]["meta"]["path"]["trans"]],
                      "path_out": [t.get("out", "") for t in al[0]["meta"]["path"]["trans"]]},
          note="Makefile:515-516 test-align-stutter-noise (boss a b -P params -D difflen -A)")

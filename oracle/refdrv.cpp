@@ -118,7 +118,7 @@ int main (int argc, char** argv) {
       cout << "],\n \"outAlphabet\":[";
       for (size_t t = 1; t < eval.outputTokenizer.tok2sym.size(); ++t) cout << (t > 1 ? "," : "") << jstr (eval.outputTokenizer.tok2sym[t]);
       cout << "],\n \"stateNames\":[";
-      for (StateIndex s = 0; s < eval.nStates(); ++s) cout << (s ? "," : "") << jstr (eval.stateNameJson (s));
+      for (StateIndex s = 0; s < eval.nStates(); ++s) cout << (s ? "," : "") << machine.state[s].name;   // raw JSON names, null allowed
       cout << "],\n \"trans\":[";
       size_t n = 0;
       for (StateIndex s = 0; s < machine.nStates(); ++s) {

@@ -1,0 +1,90 @@
+"""The C++ host mirror (machineboss_b200/host) and its CLI: builds on CPU, fails loudly without a
+GPU, and on the GPU reproduces the reference CLI's output (`boss -A`, `-L`, `-V`, `-C` layouts)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import FlatMachine, gnum, load_golden
+
+
+def _cli():
+    from machineboss_b200 import build
+    return build.build_host()
+
+
+def _machine_file(case):
+    f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump(case["machine"], f)
+    f.close()
+    return f.name
+
+
+def _pairs_file(case):
+    m = case["machine"]
+    ia, oa = [""] + m["inAlphabet"], [""] + m["outAlphabet"]
+    f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": [ia[t] for t in p["x"]]},
+                "output": {"name": "y%d" % k, "sequence": [oa[t] for t in p["y"]]}} for k, p in enumerate(case["pairs"])], f)
+    f.close()
+    return f.name
+
+
+def test_host_cli_builds_and_fails_loudly_without_gpu():
+    import torch
+    cli = _cli()
+    assert os.path.exists(cli)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    case = load_golden("bitnoise_tiny")
+    r = subprocess.run([cli, "--evaluated-machine", _machine_file(case), "--input-chars", "001", "--output-chars", "101", "-L"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_cli_align_matches_reference_golden():
+    """Makefile:515-516: boss bitstutter bitnoise -P params -D difflen -A == t/expect/align-stutter-noise-difflen.json"""
+    case = load_golden("stutter_noise_difflen")
+    r = subprocess.run([_cli(), "--evaluated-machine", _machine_file(case), "--input-chars", "01", "--output-chars", "101", "-A"],
+                       capture_output=True, text=True, check=True)
+    assert json.loads(r.stdout) == json.loads(case["ref_expect"]["align_output"])
+    assert r.stdout.strip() == case["ref_expect"]["align_output"].strip()      # byte-for-byte, as the reference's test harness diffs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["dnapsw_small", "unitindel", "bitecho", "protpsw_synth"])
+def test_cli_loglike_viterbi_counts(name):
+    case = load_golden(name)
+    mf, pf = _machine_file(case), _pairs_file(case)
+    out = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf, "-L", "-V"], capture_output=True, text=True, check=True).stdout
+    dec = json.JSONDecoder()
+    fwd, end = dec.raw_decode(out)
+    vit, _ = dec.raw_decode(out[end:].lstrip())
+    for k, p in enumerate(case["pairs"]):
+        assert fwd[k][0] == "x%d" % k and fwd[k][1] == "y%d" % k
+        for got, key in ((fwd[k][2], "rolling"), (vit[k][2], "viterbi")):
+            want = gnum(p[key])
+            if np.isinf(want):
+                assert got == "-Infinity"
+            else:
+                assert float(got) == float("%.6g" % want) or abs(float(got) - want) <= 1e-4 * abs(want)
+    if all(not np.isinf(gnum(p["forward"])) for p in case["pairs"]):
+        out = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf, "-C"], capture_output=True, text=True, check=True).stdout
+        got = np.array([c for row in json.loads(out) for c in row])
+        want = np.array([gnum(v) for v in case["counts"]])
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-5)      # 6 printed digits
+
+
+@pytest.mark.gpu
+def test_cli_untokenisable_pair_reports_minus_infinity():
+    """boss.cpp:798,805: -L prints "-Infinity" for a pair the machine cannot tokenise; -C throws (boss.cpp:811-816)."""
+    case = load_golden("dnapsw_small")
+    mf = _machine_file(case)
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "--input-chars", "ACGN", "--output-chars", "ACGT", "-L"], capture_output=True, text=True, check=True)
+    assert json.loads(r.stdout) == [["ACGN", "ACGT", "-Infinity"]]
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "--input-chars", "ACGN", "--output-chars", "ACGT", "-C"], capture_output=True, text=True)
+    assert r.returncode != 0 and "tokenize" in r.stderr
