@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--len", type=int, default=1000)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--engine", type=int, default=-1)
+    ap.add_argument("--em-pairs", type=int, default=1024, help="pairs per GPU in the E-step (counts) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -285,10 +286,25 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(ll, ll2) and np.array_equal(sc, sc2)
 
+    # E-step of Baum-Welch on a bounded slice of the same batch: Forward (stored) + Backward fused with
+    # the posterior counts, then the path's one exchange step, the all-reduce of nTrans+1 doubles.
+    from machineboss_b200 import shard
+    n_em = min(P, args.em_pairs)
+    em_batch = capi.Batch(x=x[: n_em * args.len], x_off=x_off[: n_em + 1], y=y[: n_em * args.len], y_off=y_off[: n_em + 1])
+    capi.counts(mach, em_batch)
+    barrier()
+    t0 = time.perf_counter()
+    cnt, cll = capi.counts(mach, em_batch)
+    em_kernel_ms, em_launches = em_batch.last_kernel_ms()
+    cnt, tot_ll = shard.allreduce_counts(cnt, float(cll.sum()), device="cuda")
+    torch.cuda.synchronize()
+    em_secs = time.perf_counter() - t0
+    em_batch.close()
+
     if world > 1:
-        t = torch.tensor([total, e2e_total], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total, e2e_total, em_secs], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total, e2e_total = float(t[0]), float(t[1])
+        total, e2e_total, em_secs = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         K = args.steps
@@ -307,7 +323,11 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "engine": mach.engine,
             "check": {"forward_ll_pair0": float(ll[0]), "viterbi_pair0": float(sc[0]), "path_len_pair0": int(plen[0])},
         }
-        out["roofline"] = roofline(mach.engine, cells, fwd_ms, vit_ms)
+        em_cells = float(args.len + 1) * float(args.len + 1) * S * n_em
+        out["em"] = {"what": "E-step (MachineCounts over the list): stored Forward + fused Backward/posterior counts on %d pairs per GPU, then all-reduce of %d doubles" % (n_em, len(cnt) + 1),
+                     "pairs_per_s": n_em * world / em_secs, "gcups_2_sweeps": 2 * em_cells * world / em_secs / 1e9,
+                     "kernel_ms": em_kernel_ms, "launches": em_launches, "sum_counts": float(cnt.sum()), "loglike": tot_ll}
+        out["roofline"] = roofline(mj, cells, fwd_ms, vit_ms)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = max(8, threads)
@@ -320,20 +340,56 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline(engine: int, cells: float, fwd_ms: float, vit_ms: float) -> dict:
-    """Roofline of the dominant kernel (the Forward fill).  See DESIGN.md section 'Roofline'."""
+def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
+    """Roofline of the dominant kernel, the Forward fill (mb_k_forward).  DESIGN.md section 'Roofline'.
+
+    The fill is compute-bound: its algorithmic HBM traffic is the tokens (1 B per residue) plus 8 B
+    per pair.  The binding resource is the XU (MUFU) pipe: every transition group beyond the first
+    of a state costs one log-sum-exp = 2 MUFU (ex2, lg2), and nothing in the log semiring removes
+    them.  Peak = measured MUFU issue rate (tools/pipe_peaks.cu on this pool's B200, committed as
+    profiles/r01_pipe_peaks.json) / (2 * n_lse per cell) * states per cell.
+    """
     peaks = {}
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             peaks = json.load(f)
+    pipe = {}
+    pp = os.path.join(REPO, "profiles", "r01_pipe_peaks.json")
+    if os.path.exists(pp):
+        with open(pp) as f:
+            pipe = {r["op"]: r["gops_per_s"] for r in json.load(f)["results"]}
+    # transition groups per cell (one add + one log-sum-exp / max each) and how many need a log-sum-exp
+    groups, seen = set(), {}
+    for t in range(len(mj["src"])):
+        a, b = int(mj["tin"][t]), int(mj["tout"][t])
+        if a == 0 and b == 0 and mj["dst"][t] <= mj["src"][t]:
+            continue
+        kind = 0 if (a and b) else 1 if a else 2 if b else 3
+        lab = (a, b)
+        key = (int(mj["dst"][t]), kind, int(mj["src"][t]), lab)
+        rank = seen.get(key, 0)
+        seen[key] = rank + 1
+        groups.add((int(mj["dst"][t]), kind, int(mj["src"][t]), rank))
+    t_c = len(groups)
+    n_lse = t_c - len({g[0] for g in groups})
+    S = mj["n_states"]
+    mufu = pipe.get("mufu_ex2", 4590.0) * 1e9
+    dadd = pipe.get("dadd", 17775.0) * 1e9
+    dsel = pipe.get("dsetp_sel", 8475.0) * 1e9
+    peak_fwd = S / (2.0 * n_lse / mufu) / 1e9 if n_lse else None
+    peak_vit = S / (t_c / dadd + n_lse / dsel) / 1e9
+    ach = cells / fwd_ms / 1e6
     hbm = peaks.get("hbm_gbs", 6650.0)
-    # algorithmic HBM bytes of a score-only Forward sweep: the tokens (1 B per residue) + 8 B result
-    # per pair; nothing else needs to leave the chip.  The kernel is issue-bound, not HBM-bound.
-    return {"bound": "issue", "kernel": "forward fill", "achieved": cells / fwd_ms / 1e6, "unit": "GCUPS",
-            "peak": None, "frac": None, "traffic": None,
-            "hbm_peak_gbs": hbm, "hbm_peak_source": "measured" if peaks else "fallback",
-            "note": "issue-rate peak not measured yet in this round"}
+    return {"bound": "issue (XU/MUFU pipe; the kernel is not HBM- or tensor-bound)", "kernel": "mb_k_forward",
+            "achieved": ach, "peak": peak_fwd, "unit": "GCUPS", "frac": (ach / peak_fwd) if peak_fwd else None,
+            "traffic": None,
+            "per_cell": {"transition_groups": t_c, "log_sum_exps": n_lse, "states": S},
+            "peak_source": "measured MUFU %.0f Gop/s, DADD %.0f Gop/s (profiles/r01_pipe_peaks.json)" % (mufu / 1e9, dadd / 1e9),
+            "viterbi": {"kernel": "mb_k_viterbi", "achieved": cells / vit_ms / 1e6, "peak": peak_vit,
+                        "frac": cells / vit_ms / 1e6 / peak_vit, "bound": "issue (FP64 add + compare)"},
+            "hbm": {"peak_gbs": hbm, "peak_source": "measured" if peaks else "fallback",
+                    "algorithmic_bytes_per_launch": None}}
 
 
 if __name__ == "__main__":
