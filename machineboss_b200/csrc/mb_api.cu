@@ -39,6 +39,28 @@ int timing_end (mb_batch* b, int64_t launches) {
   return 0;
 }
 
+void ws_release (mb_batch* b, int slot) {
+  if (b->ws[slot].p) cudaFree (b->ws[slot].p);
+  b->ws[slot].p = nullptr;
+  b->ws[slot].bytes = 0;
+}
+
+void ws_release_all (mb_batch* b) { for (int s = 0; s < WS_NSLOTS; ++s) ws_release (b, s); }
+
+size_t ws_bytes (const mb_batch* b, int slot) { return b->ws[slot].bytes; }
+
+void* ws_reserve (mb_batch* b, int slot, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  if (b->ws[slot].bytes >= bytes) return b->ws[slot].p;
+  ws_release (b, slot);
+  void* p = nullptr;
+  const cudaError_t e = cudaMalloc (&p, bytes);   // never evicts other slots: callers may hold pointers into them
+  if (!cuda_ok (e, "cudaMalloc (workspace)")) { cudaGetLastError(); return nullptr; }
+  b->ws[slot].p = p;
+  b->ws[slot].bytes = bytes;
+  return p;
+}
+
 // Stable counting sort of the transitions into token-indexed lists (see DevCsr).
 static void build_csr (const mb_machine* m, bool incoming, HostCsr& c) {
   const int64_t T = m->T;
@@ -268,6 +290,7 @@ void mb_batch_destroy (mb_batch* b) {
   if (b->dXOff) cudaFree (b->dXOff);
   if (b->dYOff) cudaFree (b->dYOff);
   if (b->dPaths) cudaFree (b->dPaths);
+  ws_release_all (b);
   if (b->evStart) cudaEventDestroy (b->evStart);
   if (b->evStop) cudaEventDestroy (b->evStop);
   if (b->stream) cudaStreamDestroy (b->stream);

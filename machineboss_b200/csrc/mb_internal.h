@@ -96,6 +96,9 @@ struct mb_batch {
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   double lastMs = 0;
   int64_t lastLaunches = 0;
+  // grow-only device workspace, reused across calls on this batch so that steady-state calls do
+  // no cudaMalloc / cudaFree (slots: see enum WsSlot)
+  struct WsEntry { void* p = nullptr; size_t bytes = 0; } ws[16];
   // result of the last mb_viterbi with traceback: packed paths on the device
   int32_t* dPaths = nullptr;
   std::vector<int64_t> pathStart, pathLen;   // per pair: offset into dPaths and length
@@ -119,6 +122,13 @@ int jit_update_weights (mb_machine* m);
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);
 int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+
+// per-batch workspace (mb_api.cu)
+enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_NSLOTS };
+void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set on failure
+void ws_release (mb_batch* b, int slot);
+void ws_release_all (mb_batch* b);
+size_t ws_bytes (const mb_batch* b, int slot);
 
 // timing helpers
 int timing_begin (mb_batch* b);

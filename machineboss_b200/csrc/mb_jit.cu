@@ -522,21 +522,25 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * m->S;
-  DevBuf dOrder, dBnd;
-  if (dOrder.alloc (order.size() * 8) || dBnd.alloc ((size_t) (grid * warpsPerBlock * bndStride) * 8)) return 1;
-  MB_CUDA (cudaMemcpyAsync (dOrder.p, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
-  MB_CUDA (cudaMemsetAsync (J.dCounter, 0, 8, b->stream));
+  int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
+  double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (grid * warpsPerBlock * bndStride) * 8);
+  unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+  if (!dOrder || !dBnd || !dCounter) return 1;
+  MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
   MBArgsHost A;
   A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
-  A.order = dOrder.as<int64_t>(); A.nWork = (int64_t) order.size(); A.counter = J.dCounter;
-  A.bnd = dBnd.as<double>(); A.bndStride = bndStride;
+  A.order = dOrder; A.nWork = (int64_t) order.size(); A.counter = dCounter;
+  A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dResult;
   A.emit = (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
+  if (getenv ("MB_JIT_VERBOSE"))
+    fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
+             J.smemBytes[which], J.blocksPerSM[which], J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
-  MB_CUDA (cudaStreamSynchronize (b->stream));   // the workspace buffers above are freed on return
   return 0;
 }
 
@@ -545,12 +549,12 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
   std::vector<int64_t> all ((size_t) b->nPairs);
   for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
   const std::vector<int64_t> order = cost_order (b, all);
-  DevBuf dRes;
-  if (dRes.alloc ((size_t) b->nPairs * 8)) return 1;
+  double* dRes = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
+  if (!dRes) return 1;
   if (timing_begin (b)) return 1;
-  if (launch (m, b, backward ? 1 : 0, order, dRes.as<double>(), nullptr, nullptr)) return 1;
+  if (launch (m, b, backward ? 1 : 0, order, dRes, nullptr, nullptr)) return 1;
   if (timing_end (b, 1)) return 1;
-  MB_CUDA (cudaMemcpy (loglike, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  MB_CUDA (cudaMemcpy (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -609,6 +613,15 @@ static int ensure_paths (mb_batch* b, int64_t need) {
   return 0;
 }
 
+static double memory_budget (const mb_batch* b, int slot) {
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return 0;
+  return 0.85 * (double) (freeB + ws_bytes (b, slot));   // the slot's current buffer is released before it grows
+}
+
+// large scratch is only kept between calls when it is small enough not to starve other handles
+static const size_t kKeepScratchBytes = (size_t) 24 << 30;
+
 int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   JitEngine& J = *(JitEngine*) m->jit;
   b->pathStart.clear();
@@ -617,9 +630,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   const bool trace = pathLen != nullptr;
   const int W = 32 * J.C;
   // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
-  size_t freeB = 0, totalB = 0;
-  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
-  const double budget = 0.85 * (double) freeB;
+  const double budget = memory_budget (b, WS_TB);
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
   std::vector<int64_t> chunkBytes (1, 0);
@@ -633,9 +644,16 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     chunkBytes.back() += need;
     chunks.back().push_back (k);
   }
-  DevBuf dRes, dTbOff;
-  if (dRes.alloc ((size_t) b->nPairs * 8) || dTbOff.alloc ((size_t) b->nPairs * 8)) return 1;
-  MB_CUDA (cudaMemcpyAsync (dTbOff.p, tbOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  int64_t maxChunk = 0;
+  for (int64_t v: chunkBytes) maxChunk = std::max (maxChunk, v);
+  uint8_t* dTb = (uint8_t*) ws_reserve (b, WS_TB, (size_t) maxChunk);
+  double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
+  int64_t* dTbOff = (int64_t*) ws_reserve (b, WS_TBOFF, (size_t) b->nPairs * 8);
+  int64_t* dPairs = (int64_t*) ws_reserve (b, WS_PAIRS, (size_t) b->nPairs * 8);
+  int64_t* dLen = (int64_t*) ws_reserve (b, WS_LEN, (size_t) b->nPairs * 8);
+  int64_t* dOutOff = (int64_t*) ws_reserve (b, WS_OUTOFF, (size_t) b->nPairs * 8);
+  if (!dTb || !dRes || !dTbOff || !dPairs || !dLen || !dOutOff) return 1;
+  MB_CUDA (cudaMemcpyAsync (dTbOff, tbOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
   if (trace) { b->pathStart.assign ((size_t) b->nPairs, 0); b->pathLen.assign ((size_t) b->nPairs, 0); }
   char* plan = (char*) J.dTbPlan;
   const size_t nSlots = J.fwd.slots.size();
@@ -652,23 +670,17 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   double ms = 0;
   for (size_t c = 0; c < chunks.size(); ++c) {
     const std::vector<int64_t> order = cost_order (b, chunks[c]);
-    DevBuf dTb;
-    if (trace && dTb.alloc ((size_t) chunkBytes[c])) return 1;
     if (timing_begin (b)) return 1;
-    // without traceback the pointers are still written (same kernel); give it scratch of one chunk
-    if (!trace && dTb.alloc ((size_t) chunkBytes[c])) return 1;
-    if (launch (m, b, 2, order, dRes.as<double>(), dTb.as<uint8_t>(), dTbOff.as<int64_t>())) return 1;
+    if (launch (m, b, 2, order, dRes, dTb, dTbOff)) return 1;
     ++launches;
     if (trace) {
-      DevBuf dPairs, dLen, dOutOff;
       const size_t n = chunks[c].size();
-      if (dPairs.alloc (n * 8) || dLen.alloc (n * 8) || dOutOff.alloc (n * 8)) return 1;
-      MB_CUDA (cudaMemcpyAsync (dPairs.p, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
+      MB_CUDA (cudaMemcpyAsync (dPairs, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
       const unsigned tg = (unsigned) ((n + 63) / 64);
-      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs.as<int64_t>(), (int64_t) n, dTb.as<uint8_t>(), dTbOff.as<int64_t>(), dRes.as<double>(), dLen.as<int64_t>(), nullptr, nullptr);
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, nullptr, nullptr);
       MB_CUDA (cudaGetLastError());
       std::vector<int64_t> len (n), off (n);
-      MB_CUDA (cudaMemcpyAsync (len.data(), dLen.p, n * 8, cudaMemcpyDeviceToHost, b->stream));
+      MB_CUDA (cudaMemcpyAsync (len.data(), dLen, n * 8, cudaMemcpyDeviceToHost, b->stream));
       MB_CUDA (cudaStreamSynchronize (b->stream));
       for (size_t q = 0; q < n; ++q) {
         off[q] = packed;
@@ -677,23 +689,19 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
         packed += len[q];
       }
       if (ensure_paths (b, packed)) return 1;
-      MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
-      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs.as<int64_t>(), (int64_t) n, dTb.as<uint8_t>(), dTbOff.as<int64_t>(), dRes.as<double>(), dLen.as<int64_t>(), b->dPaths, dOutOff.as<int64_t>());
+      MB_CUDA (cudaMemcpyAsync (dOutOff, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, b->dPaths, dOutOff);
       MB_CUDA (cudaGetLastError());
       launches += 2;
-      MB_CUDA (cudaStreamSynchronize (b->stream));
     }
-    if (timing_end (b, launches)) return 1;
+    if (timing_end (b, launches)) return 1;   // synchronises the stream
     ms += b->lastMs;
   }
   b->lastMs = ms;
   b->lastLaunches = launches;
-  MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
-  if (trace) {
-    // pathStart must be ascending in pair order for mb_viterbi_paths' contiguous fast path; with one
-    // chunk and cost ordering it is in chunk order = pair order already (chunks list pairs ascending)
-    for (int64_t k = 0; k < b->nPairs; ++k) pathLen[k] = b->pathLen[k];
-  }
+  MB_CUDA (cudaMemcpy (score, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  if (trace) for (int64_t k = 0; k < b->nPairs; ++k) pathLen[k] = b->pathLen[k];
+  if (ws_bytes (b, WS_TB) > kKeepScratchBytes) ws_release (b, WS_TB);
   return 0;
 }
 
@@ -702,9 +710,7 @@ int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
   // then the fused Backward + posterior-count sweep.  The batch is cut into chunks whose Forward
   // matrices fit in free device memory.
   if (b->nPairs == 0) { if (counts) for (int64_t t = 0; t < m->T; ++t) counts[t] = 0; return 0; }
-  size_t freeB = 0, totalB = 0;
-  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
-  const double budget = 0.85 * (double) freeB / 8.0;
+  const double budget = memory_budget (b, WS_F) / 8.0;
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), chunkDoubles (1, 0);
   for (int64_t k = 0; k < b->nPairs; ++k) {
@@ -716,29 +722,34 @@ int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
     chunkDoubles.back() += need;
     chunks.back().push_back (k);
   }
-  DevBuf dLL, dBack, dFOff, dCounts;
-  if (dLL.alloc ((size_t) b->nPairs * 8) || dBack.alloc ((size_t) b->nPairs * 8) || dFOff.alloc ((size_t) b->nPairs * 8) || dCounts.alloc ((size_t) std::max<int64_t> (m->T, 1) * 8)) return 1;
-  MB_CUDA (cudaMemcpyAsync (dFOff.p, fOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
-  MB_CUDA (cudaMemsetAsync (dCounts.p, 0, (size_t) std::max<int64_t> (m->T, 1) * 8, b->stream));
+  int64_t maxChunk = 0;
+  for (int64_t v: chunkDoubles) maxChunk = std::max (maxChunk, v);
+  double* dF = (double*) ws_reserve (b, WS_F, (size_t) maxChunk * 8);
+  double* dLL = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
+  double* dBack = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
+  int64_t* dFOff = (int64_t*) ws_reserve (b, WS_FOFF, (size_t) b->nPairs * 8);
+  double* dCounts = (double*) ws_reserve (b, WS_COUNTS, (size_t) std::max<int64_t> (m->T, 1) * 8);
+  if (!dF || !dLL || !dBack || !dFOff || !dCounts) return 1;
+  MB_CUDA (cudaMemcpyAsync (dFOff, fOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounts, 0, (size_t) std::max<int64_t> (m->T, 1) * 8, b->stream));
   int64_t launches = 0;
   double ms = 0;
   for (size_t c = 0; c < chunks.size(); ++c) {
     const std::vector<int64_t> order = cost_order (b, chunks[c]);
-    DevBuf dF;
-    if (dF.alloc ((size_t) chunkDoubles[c] * 8)) return 1;
     CountArgs ca;
-    ca.F = dF.as<double>(); ca.fOff = dFOff.as<int64_t>(); ca.ll = dLL.as<double>(); ca.counts = dCounts.as<double>();
+    ca.F = dF; ca.fOff = dFOff; ca.ll = dLL; ca.counts = dCounts;
     if (timing_begin (b)) return 1;
-    if (launch (m, b, 3, order, dLL.as<double>(), nullptr, nullptr, ca)) return 1;
+    if (launch (m, b, 3, order, dLL, nullptr, nullptr, ca)) return 1;
     ++launches;
-    if (counts) { if (launch (m, b, 4, order, dBack.as<double>(), nullptr, nullptr, ca)) return 1; ++launches; }
+    if (counts) { if (launch (m, b, 4, order, dBack, nullptr, nullptr, ca)) return 1; ++launches; }
     if (timing_end (b, launches)) return 1;
     ms += b->lastMs;
   }
   b->lastMs = ms;
   b->lastLaunches = launches;
-  if (loglike) MB_CUDA (cudaMemcpy (loglike, dLL.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
-  if (counts) MB_CUDA (cudaMemcpy (counts, dCounts.p, (size_t) m->T * 8, cudaMemcpyDeviceToHost));
+  if (loglike) MB_CUDA (cudaMemcpy (loglike, dLL, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  if (counts) MB_CUDA (cudaMemcpy (counts, dCounts, (size_t) m->T * 8, cudaMemcpyDeviceToHost));
+  if (ws_bytes (b, WS_F) > kKeepScratchBytes) ws_release (b, WS_F);
   return 0;
 }
 
