@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "mb_internal.h"
 
@@ -39,8 +40,51 @@ int timing_end (mb_batch* b, int64_t launches) {
   return 0;
 }
 
+// A small caching pool of freed workspace blocks per device: a batch created for one call (the
+// host mirror's ForwardMatrix, the end-to-end bench leg) would otherwise pay cudaMalloc + cudaFree
+// of its scratch (10 GB of back-pointers for the 10 k batch) on every call.
+struct PoolBlock { void* p; size_t bytes; int device; };
+static std::vector<PoolBlock> g_pool;
+static std::mutex g_poolMutex;
+static const size_t kPoolLimitBytes = (size_t) 48 << 30;
+
+static void* pool_take (int device, size_t bytes, size_t* blockBytes) {
+  std::lock_guard<std::mutex> lock (g_poolMutex);
+  int best = -1;
+  for (size_t n = 0; n < g_pool.size(); ++n)
+    if (g_pool[n].device == device && g_pool[n].bytes >= bytes && g_pool[n].bytes <= 2 * bytes + (1 << 20)
+        && (best < 0 || g_pool[n].bytes < g_pool[best].bytes)) best = (int) n;
+  if (best < 0) return nullptr;
+  void* p = g_pool[best].p;
+  *blockBytes = g_pool[best].bytes;
+  g_pool.erase (g_pool.begin() + best);
+  return p;
+}
+
+static void pool_trim (int device, size_t keepBytes) {   // free pooled blocks until at most keepBytes remain
+  std::lock_guard<std::mutex> lock (g_poolMutex);
+  size_t total = 0;
+  for (auto& bl: g_pool) if (bl.device == device) total += bl.bytes;
+  for (size_t n = 0; n < g_pool.size() && total > keepBytes;) {
+    if (g_pool[n].device == device) { cudaFree (g_pool[n].p); total -= g_pool[n].bytes; g_pool.erase (g_pool.begin() + n); }
+    else ++n;
+  }
+}
+
+size_t ws_pool_bytes (int device) {
+  std::lock_guard<std::mutex> lock (g_poolMutex);
+  size_t total = 0;
+  for (auto& bl: g_pool) if (bl.device == device) total += bl.bytes;
+  return total;
+}
+
 void ws_release (mb_batch* b, int slot) {
-  if (b->ws[slot].p) cudaFree (b->ws[slot].p);
+  if (b->ws[slot].p) {
+    if (b->ws[slot].bytes <= kPoolLimitBytes / 2) {
+      { std::lock_guard<std::mutex> lock (g_poolMutex); g_pool.push_back (PoolBlock { b->ws[slot].p, b->ws[slot].bytes, b->device }); }
+      pool_trim (b->device, kPoolLimitBytes);
+    } else cudaFree (b->ws[slot].p);
+  }
   b->ws[slot].p = nullptr;
   b->ws[slot].bytes = 0;
 }
@@ -53,11 +97,17 @@ void* ws_reserve (mb_batch* b, int slot, size_t bytes) {
   if (bytes == 0) bytes = 8;
   if (b->ws[slot].bytes >= bytes) return b->ws[slot].p;
   ws_release (b, slot);
-  void* p = nullptr;
-  const cudaError_t e = cudaMalloc (&p, bytes);   // never evicts other slots: callers may hold pointers into them
-  if (!cuda_ok (e, "cudaMalloc (workspace)")) { cudaGetLastError(); return nullptr; }
+  bytes = (bytes + 255) & ~(size_t) 255;
+  size_t got = bytes;
+  void* p = pool_take (b->device, bytes, &got);
+  if (!p) {
+    got = bytes;
+    cudaError_t e = cudaMalloc (&p, bytes);   // never evicts other slots: callers may hold pointers into them
+    if (e != cudaSuccess) { cudaGetLastError(); pool_trim (b->device, 0); e = cudaMalloc (&p, bytes); }
+    if (!cuda_ok (e, "cudaMalloc (workspace)")) { cudaGetLastError(); return nullptr; }
+  }
   b->ws[slot].p = p;
-  b->ws[slot].bytes = bytes;
+  b->ws[slot].bytes = got;
   return p;
 }
 

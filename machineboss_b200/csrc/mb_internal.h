@@ -129,6 +129,7 @@ void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);
 size_t ws_bytes (const mb_batch* b, int slot);
+size_t ws_pool_bytes (int device);   // freed blocks kept for reuse; released when an allocation fails
 
 // timing helpers
 int timing_begin (mb_batch* b);

@@ -616,7 +616,7 @@ static int ensure_paths (mb_batch* b, int64_t need) {
 static double memory_budget (const mb_batch* b, int slot) {
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return 0;
-  return 0.85 * (double) (freeB + ws_bytes (b, slot));   // the slot's current buffer is released before it grows
+  return 0.85 * (double) (freeB + ws_bytes (b, slot) + ws_pool_bytes (b->device));   // the slot's current buffer is released before it grows
 }
 
 // large scratch is only kept between calls when it is small enough not to starve other handles
