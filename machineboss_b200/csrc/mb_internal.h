@@ -96,6 +96,7 @@ struct mb_batch {
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   double lastMs = 0;
   int64_t lastLaunches = 0;
+  int64_t lastRedo = 0;   // pairs the scaled linear sweep handed to the log-domain kernel in the last call
   // grow-only device workspace, reused across calls on this batch so that steady-state calls do
   // no cudaMalloc / cudaFree (slots: see enum WsSlot)
   struct WsEntry { void* p = nullptr; size_t bytes = 0; } ws[16];
@@ -124,7 +125,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 
 // per-batch workspace (mb_api.cu)
-enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_NSLOTS };
+enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_NSLOTS };
 void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set on failure
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);

@@ -179,11 +179,17 @@ struct JitEngine {
   std::string source;
   CUmodule mod = nullptr;
   CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
-  int blocksPerSM[5] = { 1, 1, 1, 1, 1 };
-  size_t smemBytes[5] = { 0, 0, 0, 0, 0 };
+  int blocksPerSM[7] = { 1, 1, 1, 1, 1, 1, 1 };
+  size_t smemBytes[7] = { 0, 0, 0, 0, 0, 0, 0 };
   int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
   std::vector<int> ctxBase;              // per backward slot, -1 for silent
   int32_t* dIdTabB = nullptr;
+  // scaled linear-domain sweeps
+  CUfunction kForwardLin = nullptr, kBackwardLin = nullptr;
+  bool linearOK = false;
+  double* dEmitFLin = nullptr;
+  double* dEmitBLin = nullptr;
+  std::vector<char> silParamLin;
   int numSMs = 148;
   // device tables
   double* dEmitF = nullptr;
@@ -278,6 +284,33 @@ static void gen_cell_counts (std::ostringstream& o, const mb_machine* m, const J
   o << "}\n\n";
 }
 
+// Linear-domain cell: value(state) = sum over its transition groups of value(source) * weight.
+static void gen_cell_lin (std::ostringstream& o, const mb_machine* m, const Program& p, bool forward) {
+  o << "__device__ __forceinline__ void " << (forward ? "mb_cell_fwd_lin" : "mb_cell_bwd_lin")
+    << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P) {\n";
+  const int originState = forward ? 0 : m->S - 1;
+  for (int q = 0; q < m->S; ++q) {
+    const int d = forward ? q : m->S - 1 - q;
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    if (s0 == s1) o << "  double n" << d << " = 0.0;\n";
+    for (int k = s0; k < s1; ++k) {
+      const Slot& sl = p.slots[k];
+      std::ostringstream src, w;
+      const char* arr = sl.type == T_MATCH ? "D" : sl.type == T_DELETE ? "L" : sl.type == T_INSERT ? "U" : nullptr;
+      if (arr) src << arr << "[" << sl.other << "]"; else src << "n" << sl.other;
+      if (sl.type == T_MATCH) w << "E[" << sl.emitOff << " + a * " << m->nOut << " + b]";
+      else if (sl.type == T_DELETE) w << "E[" << sl.emitOff << " + a]";
+      else if (sl.type == T_INSERT) w << "E[" << sl.emitOff << " + b]";
+      else w << "P." << (forward ? "f" : "b") << "[" << sl.silIdx << "]";
+      if (k == s0) o << "  double n" << d << " = " << src.str() << " * " << w.str() << ";\n";
+      else o << "  n" << d << " = fma (" << src.str() << ", " << w.str() << ", n" << d << ");\n";
+    }
+    if (d == originState) o << "  if (origin) n" << d << " = 1.0;\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
+  o << "}\n\n";
+}
+
 bool jit_supported (const mb_machine* m, std::string* why) {
   auto no = [&] (const char* w) { if (why) *why = w; return false; };
   if (m->S > 16) return no ("more than 16 states");
@@ -330,14 +363,16 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackward, J.mod, "mb_k_backward"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")) return 1;
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")) return 1;
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[5] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts };
-  const int ne[5] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
-  for (int q = 0; q < 5; ++q) {
-    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * m->S) * 8 + (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * 4;
+  CUfunction fn[7] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin };
+  const int ne[7] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
+  for (int q = 0; q < 7; ++q) {
+    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * (m->S + 1)) * 8 + (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * 4;
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
@@ -357,6 +392,14 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
   double* sp = (double*) J.silParam.data();
   for (int q = 0; q < J.fwd.nSil; ++q) sp[q] = m->lw[J.fwd.silId[q]];
   for (int q = 0; q < J.bwd.nSil; ++q) sp[nf + q] = m->lw[J.bwd.silId[q]];
+  J.silParamLin.assign (J.silParam.size(), 0);
+  double* sl = (double*) J.silParamLin.data();
+  for (int q = 0; q < nf + nb; ++q) sl[q] = std::exp (sp[q]);
+  // the scaled linear sweep is used only when no finite weight is extreme (see MB_RESCALE in the skeleton)
+  J.linearOK = true;
+  for (double w: m->lw) if (std::isfinite (w) && std::fabs (w) > 24.0 * 0.6931471805599453) J.linearOK = false;
+  for (double w: m->lw) if (std::isnan (w) || w == INFINITY) J.linearOK = false;
+  if (getenv ("MB_JIT_NO_LINEAR")) J.linearOK = false;
 }
 
 int jit_update_weights (mb_machine* m) {
@@ -365,6 +408,10 @@ int jit_update_weights (mb_machine* m) {
   fill_weights (m, J, ef, eb);
   MB_CUDA (cudaMemcpy (J.dEmitF, ef.data(), ef.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (J.dEmitB, eb.data(), eb.size() * 8, cudaMemcpyHostToDevice));
+  for (auto& v: ef) v = std::exp (v);
+  for (auto& v: eb) v = std::exp (v);
+  MB_CUDA (cudaMemcpy (J.dEmitFLin, ef.data(), ef.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (J.dEmitBLin, eb.data(), eb.size() * 8, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -410,6 +457,10 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << J.C << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
+  unsigned long long liveF = 0, liveB = 0;
+  for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
+  for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
+  o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
@@ -418,6 +469,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   gen_cell (o, m, J.bwd, false, false, J);
   gen_cell (o, m, J.fwd, true, true, J);
   gen_cell_counts (o, m, J);
+  gen_cell_lin (o, m, J.fwd, true);
+  gen_cell_lin (o, m, J.bwd, false);
   o << kJitSkeleton;
   J.source = o.str();
 }
@@ -444,6 +497,8 @@ int jit_prepare (mb_machine* m) {
   fill_weights (m, J, ef, eb);
   MB_CUDA (cudaMalloc (&J.dEmitF, ef.size() * 8));
   MB_CUDA (cudaMalloc (&J.dEmitB, eb.size() * 8));
+  MB_CUDA (cudaMalloc (&J.dEmitFLin, ef.size() * 8));
+  MB_CUDA (cudaMalloc (&J.dEmitBLin, eb.size() * 8));
   MB_CUDA (cudaMalloc (&J.dCounter, 8));
   if (jit_update_weights (m)) return 1;
   MB_CUDA (cudaMalloc (&J.dIdTabB, std::max<size_t> (J.bwd.idTab.size(), 1) * 4));
@@ -468,6 +523,8 @@ void jit_destroy (mb_machine* m) {
   if (J->mod && g_drv.ModuleUnload) g_drv.ModuleUnload (J->mod);
   if (J->dEmitF) cudaFree (J->dEmitF);
   if (J->dEmitB) cudaFree (J->dEmitB);
+  if (J->dEmitFLin) cudaFree (J->dEmitFLin);
+  if (J->dEmitBLin) cudaFree (J->dEmitBLin);
   if (J->dTbPlan) cudaFree (J->dTbPlan);
   if (J->dIdTabB) cudaFree (J->dIdTabB);
   if (J->dCounter) cudaFree (J->dCounter);
@@ -490,6 +547,7 @@ struct MBArgsHost {   // must match struct MBArgs in the skeleton
   const double* ll;
   double* counts;
   const int32_t* idTabB;
+  int32_t* flag;
 };
 
 struct DevBuf {
@@ -509,19 +567,20 @@ static std::vector<int64_t> cost_order (const mb_batch* b, const std::vector<int
   return o;
 }
 
-struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; };
+struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; int32_t* flag = nullptr; };
 
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
                    const CountArgs& ca = CountArgs()) {
   JitEngine& J = *(JitEngine*) m->jit;
-  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : J.kBCounts;
+  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : J.kBackwardLin;
+  const bool lin = which >= 5;
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
   int64_t grid = (int64_t) J.numSMs * J.blocksPerSM[which];
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
-  const int64_t bndStride = 2 * (maxLo + 1) * m->S;
+  const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
   double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (grid * warpsPerBlock * bndStride) * 8);
   unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
@@ -533,18 +592,20 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.order = dOrder; A.nWork = (int64_t) order.size(); A.counter = dCounter;
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dResult;
-  A.emit = (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
+  A.emit = which == 5 ? J.dEmitFLin : which == 6 ? J.dEmitBLin : (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
+  A.flag = ca.flag;
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
              J.smemBytes[which], J.blocksPerSM[which], J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
-  void* params[2] = { (void*) J.silParam.data(), (void*) &A };
+  void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
 }
 
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
+  JitEngine& J = *(JitEngine*) m->jit;
   if (b->nPairs == 0) return 0;
   std::vector<int64_t> all ((size_t) b->nPairs);
   for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
@@ -552,8 +613,28 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
   double* dRes = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
   if (!dRes) return 1;
   if (timing_begin (b)) return 1;
-  if (launch (m, b, backward ? 1 : 0, order, dRes, nullptr, nullptr)) return 1;
-  if (timing_end (b, 1)) return 1;
+  int64_t launches = 1;
+  if (J.linearOK) {
+    // scaled linear-domain sweep; pairs it flags (dangerous dynamic range) or scores -inf are
+    // re-run with the log-domain kernel, which has no range limit
+    int32_t* dFlag = (int32_t*) ws_reserve (b, WS_FLAG, (size_t) b->nPairs * 4);
+    if (!dFlag) return 1;
+    CountArgs ca;
+    ca.flag = dFlag;
+    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca)) return 1;
+    std::vector<int32_t> flag ((size_t) b->nPairs);
+    MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    std::vector<int64_t> redo;
+    for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
+    b->lastRedo = (int64_t) redo.size();
+    if (!redo.empty()) {
+      if (launch (m, b, backward ? 1 : 0, cost_order (b, redo), dRes, nullptr, nullptr)) return 1;
+      ++launches;
+    }
+  } else if (launch (m, b, backward ? 1 : 0, order, dRes, nullptr, nullptr)) return 1;
+  if (timing_end (b, launches)) return 1;
   MB_CUDA (cudaMemcpy (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -35,6 +35,7 @@ struct MBArgs {
   const double* ll;                      // Forward log-likelihood per pair (mode 3)
   double* counts;                        // [nTrans] posterior counts (mode 3)
   const int32_t* idTabB;                 // transition id per backward-program table entry (mode 3)
+  int32_t* flag;                         // per pair: 1 = the scaled linear sweep saw a dangerous dynamic range
 };
 
 __device__ __forceinline__ double mb_neg_inf() { return __longlong_as_double (0xfff0000000000000LL); }
@@ -242,6 +243,182 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward (const __
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
+
+// ---------------------------------------------------------------------------------------------
+// Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).
+//
+// Same strip / skew mapping as mb_run, but cell values are probabilities in FP64, not log-
+// probabilities: a transition group is ONE FMA (value * weight) instead of an add plus a
+// log-sum-exp, and the sum it computes is the exact log-sum-exp of the log-domain recurrence.
+// All live values of the warp share one power-of-two frame 2^ecur.  Every MB_RESCALE steps the warp
+// takes the maximum of its live values (one integer max per value on the high word, one REDUX),
+// renormalises everything to [1, 2) with an exact power-of-two multiply and adds the shift to ecur.
+// Strip-boundary rows carry their frame with them.  log-likelihood = ln(value) + ecur * ln 2.
+//
+// FP64 spans 2^-1022 .. 2^1023.  At every rescale the warp also takes the minimum non-zero value;
+// if the spread max/min exceeds 2^700 (a state that is astronomically unlikely next to its
+// neighbours but could still matter later), or a boundary row arrives more than 2^900 away from the
+// current frame, the pair is flagged and the host re-runs it with the log-domain kernel (mb_run), as
+// it does for every pair whose result is -inf.  The host only selects this kernel when every finite
+// log-weight lies in [-24 ln 2, 24 ln 2], which bounds the drift between two rescales by 2^-400.
+#define MB_RESCALE 16
+
+// states whose values are read by later cells (sources of non-silent transition groups); the
+// others are temporaries of the cell function and need neither rescaling nor a boundary slot
+template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { return ((DIR ? MB_LIVE_B : MB_LIVE_F) >> s) & 1ull; }
+
+template<int DIR>
+__device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
+  extern __shared__ double mb_smem[];
+  double* E = mb_smem;
+  const int NE = MBDir<DIR>::NE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
+  __syncthreads();
+  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * (MB_S + 1));
+  const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
+  double* bndA = A.bnd + wslot * A.bndStride;
+  double* bndB = bndA + (A.bndStride >> 1);
+
+  for (;;) {
+    unsigned long long w = 0;
+    if (lane == 0) w = atomicAdd (A.counter, 1ULL);
+    w = __shfl_sync (MB_FULL, w, 0);
+    if ((int64_t) w >= A.nWork) break;
+    const int64_t k = A.order[w];
+    const int64_t x0 = A.xOff[k], y0 = A.yOff[k];
+    const int Li = (int) (A.xOff[k + 1] - x0), Lo = (int) (A.yOff[k + 1] - y0);
+    const uint8_t* x = A.x + x0;
+    const uint8_t* y = A.y + y0;
+    const int nStrips = (Li + MB_W) / MB_W;
+    int suspect = 0;
+
+    for (int strip = 0; strip < nStrips; ++strip) {
+      const int col0 = strip * MB_W + lane * MB_C;
+      int ta[MB_C];
+#pragma unroll
+      for (int c = 0; c < MB_C; ++c) {
+        const int i = col0 + c;
+        int tok = 1;
+        if (i >= 1 && i <= Li) tok = DIR ? x[Li - i] : x[i - 1];
+        ta[c] = tok - 1;
+      }
+      double U[MB_C][MB_S], Lk[MB_S];
+#pragma unroll
+      for (int s = 0; s < MB_S; ++s) {
+        Lk[s] = 0.0;
+#pragma unroll
+        for (int c = 0; c < MB_C; ++c) U[c][s] = 0.0;
+      }
+      const double* bin = (strip & 1) ? bndB : bndA;
+      double* bout = (strip & 1) ? bndA : bndB;
+      const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      int tokb = 0;
+      // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
+      int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
+      const int nSteps = Lo + 32;
+      for (int t = 0; t < nSteps; ++t) {
+        const int r = t - lane;
+        if ((t & (MB_RESCALE - 1)) == 0 && t > 0) {
+          int mh = 0;
+          unsigned ml = 0xffffffffu;
+#pragma unroll
+          for (int s = 0; s < MB_S; ++s) {
+            if (!mb_live<DIR> (s)) continue;
+            const int h = __double2hiint (Lk[s]);
+            mh = max (mh, h); ml = min (ml, (unsigned) (h - 1));
+#pragma unroll
+            for (int c = 0; c < MB_C; ++c) { const int g = __double2hiint (U[c][s]); mh = max (mh, g); ml = min (ml, (unsigned) (g - 1)); }
+          }
+          mh = __reduce_max_sync (MB_FULL, mh);
+          ml = __reduce_min_sync (MB_FULL, ml);
+          if (mh >= 0x00100000) {
+            const int ex = mh >> 20;
+            const int shift = min (ex - 1023, 1000);
+            if (shift != 0) {
+              const double f = __hiloint2double ((1023 - shift) << 20, 0);
+#pragma unroll
+              for (int s = 0; s < MB_S; ++s) {
+                if (!mb_live<DIR> (s)) continue;
+                Lk[s] *= f;
+#pragma unroll
+                for (int c = 0; c < MB_C; ++c) U[c][s] *= f;
+              }
+              ecur += shift;
+            }
+            if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
+          }
+        }
+        if (hasIn && (t & 31) == 0) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < MB_S + 1; ++q) {
+            const int e = q * 32 + lane;
+            const int row = t + e / (MB_S + 1);
+            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * (MB_S + 1) + (e % (MB_S + 1))) : 0.0;
+          }
+          __syncwarp();
+        }
+        const int tprev = __shfl_up_sync (MB_FULL, tokb, 1);
+        if (lane == 0) {
+          int tok = 1;
+          if (t >= 1 && t <= Lo) tok = DIR ? y[Lo - t] : y[t - 1];
+          tokb = tok - 1;
+        } else tokb = tprev;
+        double Lc[MB_S];
+#pragma unroll
+        for (int s = 0; s < MB_S; ++s) Lc[s] = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+        if (lane == 0) {
+          if (hasIn && t <= Lo) {
+            const double* row = sIn + (t & 31) * (MB_S + 1);
+            int d = (int) row[MB_S] - ecur;                 // frame of the stored row relative to ours
+            if (d < -900 || d > 900) { bool any = false; for (int s = 0; s < MB_S; ++s) any |= mb_live<DIR> (s) && row[s] != 0.0; if (any) suspect = 1; }
+            d = max (min (d, 1000), -1023);
+            const double f = __hiloint2double ((1023 + d) << 20, 0);
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) Lc[s] = mb_live<DIR> (s) ? row[s] * f : 0.0;
+          } else {
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) Lc[s] = 0.0;
+          }
+        }
+        if (r >= 0 && r <= Lo) {
+          double Dc[MB_S];
+#pragma unroll
+          for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
+#pragma unroll
+          for (int c = 0; c < MB_C; ++c) {
+            double N[MB_S];
+            const bool origin = (r == 0) && (col0 + c == 0);
+            if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+            else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
+          }
+          if (hasOut && lane == 31) {
+#pragma unroll
+            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * (MB_S + 1) + s] = U[MB_C - 1][s];
+            bout[(int64_t) r * (MB_S + 1) + MB_S] = (double) ecur;
+          }
+          if (r == Lo) {
+#pragma unroll
+            for (int c = 0; c < MB_C; ++c)
+              if (col0 + c == Li) {
+                const double v = U[c][MBDir<DIR>::RES];
+                A.result[k] = v > 0.0 ? log (v) + (double) ecur * 0.6931471805599453094 : mb_neg_inf();
+              }
+          }
+        }
+      }
+      suspect = __any_sync (MB_FULL, suspect);
+      __syncwarp();
+    }
+    if (lane == 0) A.flag[k] = suspect;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<1> (P, A); }
 )MBSRC";
 
 #endif
