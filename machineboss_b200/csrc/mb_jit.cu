@@ -174,7 +174,7 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
 
 struct JitEngine {
   Program fwd, bwd;
-  int C = 4, tbBytes = 1, threads = 128;
+  int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 6;
   std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
   std::string source;
   CUmodule mod = nullptr;
@@ -443,6 +443,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   J.C = m->S <= 8 ? 4 : 2;
   if (const char* e = getenv ("MB_JIT_C")) J.C = std::max (1, std::min (8, atoi (e)));
   while (J.C * J.tbBytes > 16) J.C /= 2;
+  if (const char* e = getenv ("MB_JIT_MINBLOCKS")) J.minBlocks = std::max (1, std::min (16, atoi (e)));
+  if (const char* e = getenv ("MB_JIT_MINBLOCKS_LIN")) J.minBlocksLin = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_THREADS")) J.threads = std::max (32, std::min (1024, atoi (e) / 32 * 32));
 
   J.ctxBase.assign (J.bwd.slots.size(), -1);
@@ -461,6 +463,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
+  o << "#define MB_MINBLOCKS " << J.minBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";

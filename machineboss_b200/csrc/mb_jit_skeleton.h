@@ -79,6 +79,12 @@ template<int DIR> struct MBDir { };
 template<> struct MBDir<0> { static const int NE = MB_NEMIT_F; static const int RES = MB_S - 1; };
 template<> struct MBDir<1> { static const int NE = MB_NEMIT_B; static const int RES = 0; };
 
+// states whose values are read by later cells (sources of non-silent transition groups); the
+// others are temporaries of the cell function and need no shuffle, boundary slot or rescaling
+template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { return ((DIR ? MB_LIVE_B : MB_LIVE_F) >> s) & 1ull; }
+
+#define MB_ROW (MB_S + 1)      // doubles per strip-boundary row: the states + the frame exponent (linear sweeps)
+
 // MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers;
 // MODE 2: Forward that also stores every cell (the E-step's ForwardMatrix, counts.cpp:58);
 // MODE 3: Backward fused with the posterior-count accumulation of BackwardMatrix::getCounts
@@ -92,9 +98,9 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
-  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_S);
+  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_ROW);
   // thread-private count accumulators of the emitting transition groups: acc[ctx * 32 + lane]
-  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_S)) + warp * (32 * MB_NCTX) + lane;
+  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_ROW)) + warp * (32 * MB_NCTX) + lane;
   const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -143,17 +149,22 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       const double* bin = (strip & 1) ? bndB : bndA;
       double* bout = (strip & 1) ? bndA : bndB;
       const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      if (!hasIn) {      // the column left of the matrix: nothing comes from there
+        __syncwarp();
+        for (int q = lane; q < 32 * MB_ROW; q += 32) sIn[q] = NI;
+        __syncwarp();
+      }
       int tokb = 0;
       const int nSteps = Lo + 32;
       for (int t = 0; t < nSteps; ++t) {
         const int r = t - lane;
-        if (hasIn && (t & 31) == 0) {
+        if (hasIn && (t & 31) == 0) {       // stage the next 32 rows of the previous strip's last column
           __syncwarp();
 #pragma unroll
-          for (int q = 0; q < MB_S; ++q) {
+          for (int q = 0; q < MB_ROW; ++q) {
             const int e = q * 32 + lane;
-            const int row = t + e / MB_S;
-            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * MB_S + (e % MB_S)) : NI;
+            const int row = t + e / MB_ROW;
+            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * MB_ROW + (e % MB_ROW)) : NI;
           }
           __syncwarp();
         }
@@ -163,12 +174,15 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           if (t >= 1 && t <= Lo) tok = DIR ? y[Lo - t] : y[t - 1];
           tokb = tok - 1;
         } else tokb = tprev;
+        // left neighbour's last column at this row: a shuffle, or the staged boundary row for lane 0
         double Lc[MB_S];
 #pragma unroll
-        for (int s = 0; s < MB_S; ++s) Lc[s] = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
-        if (lane == 0) {
-#pragma unroll
-          for (int s = 0; s < MB_S; ++s) Lc[s] = hasIn ? sIn[(t & 31) * MB_S + s] : NI;
+        for (int s = 0; s < MB_S; ++s) {
+          if (mb_live<DIR> (s)) {
+            const double fromLane = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+            const double fromStrip = sIn[(t & 31) * MB_ROW + s];
+            Lc[s] = lane ? fromLane : fromStrip;
+          } else Lc[s] = NI;
         }
         if (r >= 0 && r <= Lo) {
           double Dc[MB_S];
@@ -223,7 +237,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           }
           if (hasOut && lane == 31) {
 #pragma unroll
-            for (int s = 0; s < MB_S; ++s) bout[(int64_t) r * MB_S + s] = U[MB_C - 1][s];
+            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
           }
           if (r == Lo) {
 #pragma unroll
@@ -238,11 +252,11 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
 
 // ---------------------------------------------------------------------------------------------
 // Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).
@@ -252,8 +266,9 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __g
 // log-sum-exp, and the sum it computes is the exact log-sum-exp of the log-domain recurrence.
 // All live values of the warp share one power-of-two frame 2^ecur.  Every MB_RESCALE steps the warp
 // takes the maximum of its live values (one integer max per value on the high word, one REDUX),
-// renormalises everything to [1, 2) with an exact power-of-two multiply and adds the shift to ecur.
-// Strip-boundary rows carry their frame with them.  log-likelihood = ln(value) + ecur * ln 2.
+// renormalises everything to [1, 2) with an exact power-of-two multiply and adds the shift to ecur;
+// in the same step it stages the next MB_RESCALE rows of the previous strip's boundary, each
+// carrying its own frame, already converted to the new frame.  log-likelihood = ln(value) + ecur ln 2.
 //
 // FP64 spans 2^-1022 .. 2^1023.  At every rescale the warp also takes the minimum non-zero value;
 // if the spread max/min exceeds 2^700 (a state that is astronomically unlikely next to its
@@ -263,10 +278,6 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_viterbi (const __g
 // log-weight lies in [-24 ln 2, 24 ln 2], which bounds the drift between two rescales by 2^-400.
 #define MB_RESCALE 16
 
-// states whose values are read by later cells (sources of non-silent transition groups); the
-// others are temporaries of the cell function and need neither rescaling nor a boundary slot
-template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { return ((DIR ? MB_LIVE_B : MB_LIVE_F) >> s) & 1ull; }
-
 template<int DIR>
 __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   extern __shared__ double mb_smem[];
@@ -275,7 +286,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
-  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * (MB_S + 1));
+  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_ROW);
   const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -313,51 +324,70 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       const double* bin = (strip & 1) ? bndB : bndA;
       double* bout = (strip & 1) ? bndA : bndB;
       const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      if (!hasIn) {
+        __syncwarp();
+        for (int q = lane; q < MB_RESCALE * MB_ROW; q += 32) sIn[q] = 0.0;
+        __syncwarp();
+      }
       int tokb = 0;
       // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
       const int nSteps = Lo + 32;
       for (int t = 0; t < nSteps; ++t) {
         const int r = t - lane;
-        if ((t & (MB_RESCALE - 1)) == 0 && t > 0) {
-          int mh = 0;
-          unsigned ml = 0xffffffffu;
+        if ((t & (MB_RESCALE - 1)) == 0) {
+          if (t > 0) {
+            int mh = 0;
+            unsigned ml = 0xffffffffu;
 #pragma unroll
-          for (int s = 0; s < MB_S; ++s) {
-            if (!mb_live<DIR> (s)) continue;
-            const int h = __double2hiint (Lk[s]);
-            mh = max (mh, h); ml = min (ml, (unsigned) (h - 1));
+            for (int s = 0; s < MB_S; ++s) {
+              if (!mb_live<DIR> (s)) continue;
+              const int h = __double2hiint (Lk[s]);
+              mh = max (mh, h); ml = min (ml, (unsigned) (h - 1));
 #pragma unroll
-            for (int c = 0; c < MB_C; ++c) { const int g = __double2hiint (U[c][s]); mh = max (mh, g); ml = min (ml, (unsigned) (g - 1)); }
-          }
-          mh = __reduce_max_sync (MB_FULL, mh);
-          ml = __reduce_min_sync (MB_FULL, ml);
-          if (mh >= 0x00100000) {
-            const int ex = mh >> 20;
-            const int shift = min (ex - 1023, 1000);
-            if (shift != 0) {
-              const double f = __hiloint2double ((1023 - shift) << 20, 0);
-#pragma unroll
-              for (int s = 0; s < MB_S; ++s) {
-                if (!mb_live<DIR> (s)) continue;
-                Lk[s] *= f;
-#pragma unroll
-                for (int c = 0; c < MB_C; ++c) U[c][s] *= f;
-              }
-              ecur += shift;
+              for (int c = 0; c < MB_C; ++c) { const int g = __double2hiint (U[c][s]); mh = max (mh, g); ml = min (ml, (unsigned) (g - 1)); }
             }
-            if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
-          }
-        }
-        if (hasIn && (t & 31) == 0) {
-          __syncwarp();
+            mh = __reduce_max_sync (MB_FULL, mh);
+            ml = __reduce_min_sync (MB_FULL, ml);
+            if (mh >= 0x00100000) {
+              const int ex = mh >> 20;
+              const int shift = min (ex - 1023, 1000);
+              if (shift != 0) {
+                const double f = __hiloint2double ((1023 - shift) << 20, 0);
 #pragma unroll
-          for (int q = 0; q < MB_S + 1; ++q) {
-            const int e = q * 32 + lane;
-            const int row = t + e / (MB_S + 1);
-            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * (MB_S + 1) + (e % (MB_S + 1))) : 0.0;
+                for (int s = 0; s < MB_S; ++s) {
+                  if (!mb_live<DIR> (s)) continue;
+                  Lk[s] *= f;
+#pragma unroll
+                  for (int c = 0; c < MB_C; ++c) U[c][s] *= f;
+                }
+                ecur += shift;
+              }
+              if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
+            }
           }
-          __syncwarp();
+          if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame
+            __syncwarp();
+            if (lane < MB_RESCALE) {
+              const int row = t + lane;
+              double* dst = sIn + lane * MB_ROW;
+              if (row <= Lo) {
+                const double* src = bin + (int64_t) row * MB_ROW;
+                int d = (int) __ldcg (src + MB_S) - ecur;
+                bool far = d < -900 || d > 900, any = false;
+                d = max (min (d, 1000), -1023);
+                const double f = __hiloint2double ((1023 + d) << 20, 0);
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s)
+                  if (mb_live<DIR> (s)) { const double v = __ldcg (src + s); any |= v != 0.0; dst[s] = v * f; }
+                if (far && any) suspect = 1;
+              } else {
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) dst[s] = 0.0;
+              }
+            }
+            __syncwarp();
+          }
         }
         const int tprev = __shfl_up_sync (MB_FULL, tokb, 1);
         if (lane == 0) {
@@ -367,20 +397,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         } else tokb = tprev;
         double Lc[MB_S];
 #pragma unroll
-        for (int s = 0; s < MB_S; ++s) Lc[s] = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
-        if (lane == 0) {
-          if (hasIn && t <= Lo) {
-            const double* row = sIn + (t & 31) * (MB_S + 1);
-            int d = (int) row[MB_S] - ecur;                 // frame of the stored row relative to ours
-            if (d < -900 || d > 900) { bool any = false; for (int s = 0; s < MB_S; ++s) any |= mb_live<DIR> (s) && row[s] != 0.0; if (any) suspect = 1; }
-            d = max (min (d, 1000), -1023);
-            const double f = __hiloint2double ((1023 + d) << 20, 0);
-#pragma unroll
-            for (int s = 0; s < MB_S; ++s) Lc[s] = mb_live<DIR> (s) ? row[s] * f : 0.0;
-          } else {
-#pragma unroll
-            for (int s = 0; s < MB_S; ++s) Lc[s] = 0.0;
-          }
+        for (int s = 0; s < MB_S; ++s) {
+          if (mb_live<DIR> (s)) {
+            const double fromLane = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+            const double fromStrip = sIn[(t & (MB_RESCALE - 1)) * MB_ROW + s];
+            Lc[s] = lane ? fromLane : fromStrip;
+          } else Lc[s] = 0.0;
         }
         if (r >= 0 && r <= Lo) {
           double Dc[MB_S];
@@ -397,8 +419,8 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           }
           if (hasOut && lane == 31) {
 #pragma unroll
-            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * (MB_S + 1) + s] = U[MB_C - 1][s];
-            bout[(int64_t) r * (MB_S + 1) + MB_S] = (double) ecur;
+            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
+            bout[(int64_t) r * MB_ROW + MB_S] = (double) ecur;
           }
           if (r == Lo) {
 #pragma unroll
@@ -417,8 +439,8 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<1> (P, A); }
 )MBSRC";
 
 #endif
