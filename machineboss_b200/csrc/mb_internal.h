@@ -125,7 +125,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 
 // per-batch workspace (mb_api.cu)
-enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_NSLOTS };
+enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_NSLOTS };
 void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set on failure
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);

@@ -174,18 +174,18 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
 
 struct JitEngine {
   Program fwd, bwd;
-  int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 6;
+  int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 5, minBlocksCnt = 3;
   std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
   std::string source;
   CUmodule mod = nullptr;
   CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
-  int blocksPerSM[7] = { 1, 1, 1, 1, 1, 1, 1 };
-  size_t smemBytes[7] = { 0, 0, 0, 0, 0, 0, 0 };
+  int blocksPerSM[9] = { 1, 1, 1, 1, 1, 1, 1, 1, 1 };
+  size_t smemBytes[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
   std::vector<int> ctxBase;              // per backward slot, -1 for silent
   int32_t* dIdTabB = nullptr;
   // scaled linear-domain sweeps
-  CUfunction kForwardLin = nullptr, kBackwardLin = nullptr;
+  CUfunction kForwardLin = nullptr, kBackwardLin = nullptr, kFStoreLin = nullptr, kBCountsLin = nullptr;
   bool linearOK = false;
   double* dEmitFLin = nullptr;
   double* dEmitBLin = nullptr;
@@ -311,6 +311,58 @@ static void gen_cell_lin (std::ostringstream& o, const mb_machine* m, const Prog
   o << "}\n\n";
 }
 
+// Linear-domain Backward cell fused with the posterior counts: per transition group
+//   t = B(dest) * w;  B(s) += t;  count(group) += F'(s) * t     with F' = F * 2^(eF+eB) / Z
+static void gen_cell_counts_lin (std::ostringstream& o, const mb_machine* m, const JitEngine& J) {
+  const Program& p = J.bwd;
+  o << "__device__ __forceinline__ void mb_cell_cnt_lin (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P, const double (&F)[MB_S], double (&cs)[MB_NSIL_B > 0 ? MB_NSIL_B : 1], double* __restrict__ acc, const int c) {\n";
+  for (int q = 0; q < m->S; ++q) {
+    const int d = m->S - 1 - q;
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    if (s0 == s1) o << "  double n" << d << " = 0.0;\n";
+    for (int k = s0; k < s1; ++k) {
+      const Slot& sl = p.slots[k];
+      std::ostringstream src, w;
+      const char* arr = sl.type == T_MATCH ? "D" : sl.type == T_DELETE ? "L" : sl.type == T_INSERT ? "U" : nullptr;
+      if (arr) src << arr << "[" << sl.other << "]"; else src << "n" << sl.other;
+      if (sl.type == T_MATCH) w << "E[" << sl.emitOff << " + a * " << m->nOut << " + b]";
+      else if (sl.type == T_DELETE) w << "E[" << sl.emitOff << " + a]";
+      else if (sl.type == T_INSERT) w << "E[" << sl.emitOff << " + b]";
+      else w << "P.b[" << sl.silIdx << "]";
+      o << "  const double t" << k << " = " << src.str() << " * " << w.str() << ";\n";
+      if (k == s0) o << "  double n" << d << " = t" << k << ";\n";
+      else o << "  n" << d << " += t" << k << ";\n";
+      if (sl.type == T_SILENT) o << "  cs[" << sl.silIdx << "] = fma (F[" << d << "], t" << k << ", cs[" << sl.silIdx << "]);\n";
+      else {
+        std::ostringstream ix;
+        ix << "(" << J.ctxBase[k] << " + ";
+        if (sl.type == T_MATCH) ix << "c * " << m->nOut << " + b";
+        else if (sl.type == T_DELETE) ix << "c";
+        else ix << "b";
+        ix << ") * 32";
+        o << "  acc[" << ix.str() << "] = fma (F[" << d << "], t" << k << ", acc[" << ix.str() << "]);\n";
+      }
+    }
+    if (d == m->S - 1) o << "  if (origin) n" << d << " = 1.0;\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
+  o << "}\n\n";
+  o << "__device__ __forceinline__ void mb_flush_counts_lin (double (&cs)[MB_NSIL_B > 0 ? MB_NSIL_B : 1], double* __restrict__ acc, const int (&ta)[MB_C], double* __restrict__ counts, const int32_t* __restrict__ idTab, const int lane) {\n";
+  for (size_t k = 0; k < p.slots.size(); ++k) {
+    const Slot& sl = p.slots[k];
+    if (sl.type == T_SILENT) {
+      o << "  { const double v = mb_warp_sum_d (cs[" << sl.silIdx << "]); if (lane == 0 && v != 0.0) atomicAdd (counts + " << p.silId[sl.silIdx] << ", v); }\n";
+    } else if (sl.type == T_MATCH) {
+      o << "  _Pragma(\"unroll\") for (int c = 0; c < MB_C; ++c) for (int b = 0; b < " << m->nOut << "; ++b) { const double v = acc[(" << J.ctxBase[k] << " + c * " << m->nOut << " + b) * 32]; if (v != 0.0) { const int id = idTab[" << sl.idOff << " + ta[c] * " << m->nOut << " + b]; if (id >= 0) atomicAdd (counts + id, v); } }\n";
+    } else if (sl.type == T_DELETE) {
+      o << "  _Pragma(\"unroll\") for (int c = 0; c < MB_C; ++c) { const double v = acc[(" << J.ctxBase[k] << " + c) * 32]; if (v != 0.0) { const int id = idTab[" << sl.idOff << " + ta[c]]; if (id >= 0) atomicAdd (counts + id, v); } }\n";
+    } else {
+      o << "  for (int b = 0; b < " << m->nOut << "; ++b) { const double v = acc[(" << J.ctxBase[k] << " + b) * 32]; if (v != 0.0) { const int id = idTab[" << sl.idOff << " + b]; if (id >= 0) atomicAdd (counts + id, v); } }\n";
+    }
+  }
+  o << "}\n\n";
+}
+
 bool jit_supported (const mb_machine* m, std::string* why) {
   auto no = [&] (const char* w) { if (why) *why = w; return false; };
   if (m->S > 16) return no ("more than 16 states");
@@ -365,14 +417,18 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")) return 1;
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[7] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin };
-  const int ne[7] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
-  for (int q = 0; q < 7; ++q) {
-    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * (m->S + 1)) * 8 + (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * 4;
+  CUfunction fn[9] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin };
+  const int ne[9] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
+  for (int q = 0; q < 9; ++q) {
+    const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
+    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * (m->S + 1)) * 8
+      + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0);
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
@@ -444,6 +500,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   if (const char* e = getenv ("MB_JIT_C")) J.C = std::max (1, std::min (8, atoi (e)));
   while (J.C * J.tbBytes > 16) J.C /= 2;
   if (const char* e = getenv ("MB_JIT_MINBLOCKS")) J.minBlocks = std::max (1, std::min (16, atoi (e)));
+  if (const char* e = getenv ("MB_JIT_MINBLOCKS_CNT")) J.minBlocksCnt = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_MINBLOCKS_LIN")) J.minBlocksLin = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_THREADS")) J.threads = std::max (32, std::min (1024, atoi (e) / 32 * 32));
 
@@ -463,17 +520,18 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << J.minBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n";
+  o << "#define MB_MINBLOCKS " << J.minBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
-  o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n\n";
+  o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n__device__ __forceinline__ double mb_warp_sum_d (double);\n\n";
   gen_cell (o, m, J.fwd, true, false, J);
   gen_cell (o, m, J.bwd, false, false, J);
   gen_cell (o, m, J.fwd, true, true, J);
   gen_cell_counts (o, m, J);
   gen_cell_lin (o, m, J.fwd, true);
   gen_cell_lin (o, m, J.bwd, false);
+  gen_cell_counts_lin (o, m, J);
   o << kJitSkeleton;
   J.source = o.str();
 }
@@ -551,6 +609,8 @@ struct MBArgsHost {   // must match struct MBArgs in the skeleton
   double* counts;
   const int32_t* idTabB;
   int32_t* flag;
+  unsigned* F32; const int64_t* f32Off;
+  int32_t* ef; const int64_t* efOff;
 };
 
 struct DevBuf {
@@ -570,12 +630,13 @@ static std::vector<int64_t> cost_order (const mb_batch* b, const std::vector<int
   return o;
 }
 
-struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; int32_t* flag = nullptr; };
+struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; int32_t* flag = nullptr;
+                   unsigned* F32 = nullptr; const int64_t* f32Off = nullptr; int32_t* ef = nullptr; const int64_t* efOff = nullptr; };
 
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
                    const CountArgs& ca = CountArgs()) {
   JitEngine& J = *(JitEngine*) m->jit;
-  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : J.kBackwardLin;
+  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
   const bool lin = which >= 5;
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
@@ -595,8 +656,9 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.order = dOrder; A.nWork = (int64_t) order.size(); A.counter = dCounter;
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dResult;
-  A.emit = which == 5 ? J.dEmitFLin : which == 6 ? J.dEmitBLin : (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
+  A.emit = (which == 5 || which == 7) ? J.dEmitFLin : (which == 6 || which == 8) ? J.dEmitBLin : (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
   A.flag = ca.flag;
+  A.F32 = ca.F32; A.f32Off = ca.f32Off; A.ef = ca.ef; A.efOff = ca.efOff;
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
@@ -789,15 +851,16 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   return 0;
 }
 
-int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
-  // MachineCounts over the list (counts.cpp:37-64): per pair a Forward sweep that stores its matrix,
-  // then the fused Backward + posterior-count sweep.  The batch is cut into chunks whose Forward
-  // matrices fit in free device memory.
-  if (b->nPairs == 0) { if (counts) for (int64_t t = 0; t < m->T; ++t) counts[t] = 0; return 0; }
+// MachineCounts over `pairs` (counts.cpp:37-64) with the log-domain kernels: per pair a Forward sweep
+// that stores its FP64 matrix, then the fused Backward + posterior-count sweep.  Counts are ADDED to
+// hostCounts, log-likelihoods written to loglike[k].  Chunked by free device memory.
+static int counts_log (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, bool wantCounts,
+                       std::vector<double>& hostCounts, double* loglike, int64_t& launches, double& ms) {
+  if (pairs.empty()) return 0;
   const double budget = memory_budget (b, WS_F) / 8.0;
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), chunkDoubles (1, 0);
-  for (int64_t k = 0; k < b->nPairs; ++k) {
+  for (int64_t k: pairs) {
     const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
     const int64_t need = (((Li + 1) * (Lo + 1) * m->S) + 31) & ~(int64_t) 31;
     if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": the Forward matrix does not fit in device memory"); return 1; }
@@ -808,16 +871,15 @@ int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
   }
   int64_t maxChunk = 0;
   for (int64_t v: chunkDoubles) maxChunk = std::max (maxChunk, v);
+  const size_t T = (size_t) std::max<int64_t> (m->T, 1);
   double* dF = (double*) ws_reserve (b, WS_F, (size_t) maxChunk * 8);
   double* dLL = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
   double* dBack = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
   int64_t* dFOff = (int64_t*) ws_reserve (b, WS_FOFF, (size_t) b->nPairs * 8);
-  double* dCounts = (double*) ws_reserve (b, WS_COUNTS, (size_t) std::max<int64_t> (m->T, 1) * 8);
+  double* dCounts = (double*) ws_reserve (b, WS_COUNTS, T * 8);
   if (!dF || !dLL || !dBack || !dFOff || !dCounts) return 1;
   MB_CUDA (cudaMemcpyAsync (dFOff, fOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
-  MB_CUDA (cudaMemsetAsync (dCounts, 0, (size_t) std::max<int64_t> (m->T, 1) * 8, b->stream));
-  int64_t launches = 0;
-  double ms = 0;
+  MB_CUDA (cudaMemsetAsync (dCounts, 0, T * 8, b->stream));
   for (size_t c = 0; c < chunks.size(); ++c) {
     const std::vector<int64_t> order = cost_order (b, chunks[c]);
     CountArgs ca;
@@ -825,15 +887,115 @@ int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
     if (timing_begin (b)) return 1;
     if (launch (m, b, 3, order, dLL, nullptr, nullptr, ca)) return 1;
     ++launches;
-    if (counts) { if (launch (m, b, 4, order, dBack, nullptr, nullptr, ca)) return 1; ++launches; }
+    if (wantCounts) { if (launch (m, b, 4, order, dBack, nullptr, nullptr, ca)) return 1; ++launches; }
     if (timing_end (b, launches)) return 1;
     ms += b->lastMs;
   }
+  std::vector<double> ll ((size_t) b->nPairs), cnt (T);
+  MB_CUDA (cudaMemcpy (ll.data(), dLL, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  for (int64_t k: pairs) loglike[k] = ll[k];
+  if (wantCounts) {
+    MB_CUDA (cudaMemcpy (cnt.data(), dCounts, T * 8, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < m->T; ++t) hostCounts[t] += cnt[t];
+  }
+  if (ws_bytes (b, WS_F) > kKeepScratchBytes) ws_release (b, WS_F);
+  return 0;
+}
+
+// The same E-step with the scaled linear-domain kernels: Forward stores the high words of its values
+// (4 bytes per cell-state) and the frame of every rescale block; Backward multiplies them back in.
+// Pairs the Forward sweep flags, and whole chunks in which the Backward sweep flags a pair, are
+// handed to counts_log.
+static int counts_lin (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, bool wantCounts,
+                       std::vector<double>& hostCounts, double* loglike, int64_t& launches, double& ms) {
+  JitEngine& J = *(JitEngine*) m->jit;
+  const int W = 32 * J.C;
+  const double budget = memory_budget (b, WS_F) / 4.0;     // in 32-bit words
+  std::vector<std::vector<int64_t>> chunks (1);
+  std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), efOffHost ((size_t) b->nPairs, 0), chunkWords (1, 0), chunkEf (1, 0);
+  for (int64_t k: pairs) {
+    const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
+    const int64_t need = (((Li + 1) * (Lo + 1) * m->S) + 63) & ~(int64_t) 63;
+    const int64_t needEf = ((Li + W) / W) * ((Lo + 32 + 15) / 16);
+    if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": the Forward matrix does not fit in device memory"); return 1; }
+    if (!chunks.back().empty() && (double) (chunkWords.back() + need) > budget) { chunks.emplace_back(); chunkWords.push_back (0); chunkEf.push_back (0); }
+    fOffHost[k] = chunkWords.back();
+    efOffHost[k] = chunkEf.back();
+    chunkWords.back() += need;
+    chunkEf.back() += needEf;
+    chunks.back().push_back (k);
+  }
+  int64_t maxChunk = 0, maxEf = 0;
+  for (int64_t v: chunkWords) maxChunk = std::max (maxChunk, v);
+  for (int64_t v: chunkEf) maxEf = std::max (maxEf, v);
+  const size_t T = (size_t) std::max<int64_t> (m->T, 1);
+  unsigned* dF32 = (unsigned*) ws_reserve (b, WS_F, (size_t) maxChunk * 4);
+  int32_t* dEf = (int32_t*) ws_reserve (b, WS_EF, (size_t) std::max<int64_t> (maxEf, 1) * 4);
+  double* dLL = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
+  double* dBack = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
+  int64_t* dFOff = (int64_t*) ws_reserve (b, WS_FOFF, (size_t) b->nPairs * 8);
+  int64_t* dEfOff = (int64_t*) ws_reserve (b, WS_EFOFF, (size_t) b->nPairs * 8);
+  double* dCounts = (double*) ws_reserve (b, WS_COUNTS, T * 8);
+  int32_t* dFlag = (int32_t*) ws_reserve (b, WS_FLAG, (size_t) b->nPairs * 4);
+  if (!dF32 || !dEf || !dLL || !dBack || !dFOff || !dEfOff || !dCounts || !dFlag) return 1;
+  MB_CUDA (cudaMemcpyAsync (dFOff, fOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemcpyAsync (dEfOff, efOffHost.data(), (size_t) b->nPairs * 8, cudaMemcpyHostToDevice, b->stream));
+  std::vector<int64_t> redo;
+  std::vector<double> ll ((size_t) b->nPairs), cnt (T);
+  std::vector<int32_t> flag ((size_t) b->nPairs);
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    CountArgs ca;
+    ca.F32 = dF32; ca.f32Off = dFOff; ca.ef = dEf; ca.efOff = dEfOff; ca.ll = dLL; ca.counts = dCounts; ca.flag = dFlag;
+    if (timing_begin (b)) return 1;
+    MB_CUDA (cudaMemsetAsync (dFlag, 0, (size_t) b->nPairs * 4, b->stream));
+    if (launch (m, b, 7, cost_order (b, chunks[c]), dLL, nullptr, nullptr, ca)) return 1;
+    ++launches;
+    MB_CUDA (cudaMemcpyAsync (ll.data(), dLL, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    std::vector<int64_t> good;
+    for (int64_t k: chunks[c]) {
+      if (flag[k] || !(ll[k] > -INFINITY)) redo.push_back (k);
+      else { good.push_back (k); loglike[k] = ll[k]; }
+    }
+    if (wantCounts && !good.empty()) {
+      MB_CUDA (cudaMemsetAsync (dCounts, 0, T * 8, b->stream));
+      MB_CUDA (cudaMemsetAsync (dFlag, 0, (size_t) b->nPairs * 4, b->stream));
+      if (launch (m, b, 8, cost_order (b, good), dBack, nullptr, nullptr, ca)) return 1;
+      ++launches;
+      MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
+      MB_CUDA (cudaMemcpyAsync (cnt.data(), dCounts, T * 8, cudaMemcpyDeviceToHost, b->stream));
+      MB_CUDA (cudaStreamSynchronize (b->stream));
+      bool anyFlag = false;
+      for (int64_t k: good) anyFlag |= flag[k] != 0;
+      if (anyFlag) redo.insert (redo.end(), good.begin(), good.end());     // discard this chunk's linear counts
+      else for (int64_t t = 0; t < m->T; ++t) hostCounts[t] += cnt[t];
+    }
+    if (timing_end (b, launches)) return 1;
+    ms += b->lastMs;
+  }
+  if (ws_bytes (b, WS_F) > kKeepScratchBytes) ws_release (b, WS_F);
+  b->lastRedo = (int64_t) redo.size();
+  std::sort (redo.begin(), redo.end());
+  return counts_log (m, b, redo, wantCounts, hostCounts, loglike, launches, ms);
+}
+
+int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
+  JitEngine& J = *(JitEngine*) m->jit;
+  if (counts) for (int64_t t = 0; t < m->T; ++t) counts[t] = 0;
+  if (b->nPairs == 0) return 0;
+  std::vector<int64_t> all ((size_t) b->nPairs);
+  for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
+  std::vector<double> hostCounts ((size_t) std::max<int64_t> (m->T, 1), 0.), ll ((size_t) b->nPairs, 0.);
+  int64_t launches = 0;
+  double ms = 0;
+  const int rc = J.linearOK ? counts_lin (m, b, all, counts != nullptr, hostCounts, ll.data(), launches, ms)
+                            : counts_log (m, b, all, counts != nullptr, hostCounts, ll.data(), launches, ms);
+  if (rc) return rc;
   b->lastMs = ms;
   b->lastLaunches = launches;
-  if (loglike) MB_CUDA (cudaMemcpy (loglike, dLL, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
-  if (counts) MB_CUDA (cudaMemcpy (counts, dCounts, (size_t) m->T * 8, cudaMemcpyDeviceToHost));
-  if (ws_bytes (b, WS_F) > kKeepScratchBytes) ws_release (b, WS_F);
+  if (loglike) for (int64_t k = 0; k < b->nPairs; ++k) loglike[k] = ll[k];
+  if (counts) for (int64_t t = 0; t < m->T; ++t) counts[t] = hostCounts[t];
   return 0;
 }
 

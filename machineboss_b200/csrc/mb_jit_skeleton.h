@@ -36,6 +36,8 @@ struct MBArgs {
   double* counts;                        // [nTrans] posterior counts (mode 3)
   const int32_t* idTabB;                 // transition id per backward-program table entry (mode 3)
   int32_t* flag;                         // per pair: 1 = the scaled linear sweep saw a dangerous dynamic range
+  unsigned* F32; const int64_t* f32Off;  // linear E-step: high words of the Forward values, [outPos][inPos][state]
+  int32_t* ef; const int64_t* efOff;     // linear E-step: frame exponent per (strip, block of MB_RESCALE steps)
 };
 
 __device__ __forceinline__ double mb_neg_inf() { return __longlong_as_double (0xfff0000000000000LL); }
@@ -70,6 +72,12 @@ __device__ __forceinline__ float mb_post (double z) {
 }
 
 __device__ __forceinline__ float mb_warp_sum (float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (MB_FULL, v, d);
+  return v;
+}
+
+__device__ __forceinline__ double mb_warp_sum_d (double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (MB_FULL, v, d);
   return v;
@@ -254,8 +262,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,7 +286,12 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_vite
 // log-weight lies in [-24 ln 2, 24 ln 2], which bounds the drift between two rescales by 2^-400.
 #define MB_RESCALE 16
 
-template<int DIR>
+// MODE 0: score only.  MODE 2 (DIR 0): also store the Forward values for the E-step -- the HIGH WORD
+// of each double (sign, 11-bit exponent, 20-bit mantissa, rounded: relative error 2^-21, full FP64
+// range), 4 bytes per cell-state instead of 8, plus the frame exponent of every rescale block.
+// MODE 3 (DIR 1): Backward fused with the posterior counts: for each transition group the product
+// term = B(dest) * w feeds the Backward sum and, times F(src) * 2^(eF + eB) / Z, the group's count.
+template<int MODE, int DIR>
 __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
@@ -287,6 +300,8 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
   double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_ROW);
+  // thread-private FP64 count accumulators of the emitting transition groups: accd[ctx * 32 + lane]
+  double* accd = mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
   const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -303,6 +318,20 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
     const uint8_t* y = A.y + y0;
     const int nStrips = (Li + MB_W) / MB_W;
     int suspect = 0;
+    const int nBlk = (Lo + 32 + MB_RESCALE - 1) / MB_RESCALE;
+    unsigned* F32 = (MODE == 2 || MODE == 3) ? A.F32 + A.f32Off[k] : (unsigned*) 0;
+    int32_t* ef = (MODE == 2 || MODE == 3) ? A.ef + A.efOff[k] : (int32_t*) 0;
+    // 1/Z = zf * 2^-lzi with Z = exp(ll) the pair's Forward likelihood (MODE 3)
+    int lzi = 0;
+    double zf = 1.0;
+    if (MODE == 3) {
+      const double llk = A.ll[k];
+      if (!(llk > mb_neg_inf())) continue;    // impossible pair: no posterior
+      const double lz = llk * 1.4426950408889634074;
+      const double fl = floor (lz);
+      lzi = (int) fl;
+      zf = exp2 (fl - lz);
+    }
 
     for (int strip = 0; strip < nStrips; ++strip) {
       const int col0 = strip * MB_W + lane * MB_C;
@@ -320,6 +349,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         Lk[s] = 0.0;
 #pragma unroll
         for (int c = 0; c < MB_C; ++c) U[c][s] = 0.0;
+      }
+      double csd[MB_NSIL_B > 0 ? MB_NSIL_B : 1];
+      if (MODE == 3) {
+#pragma unroll
+        for (int q = 0; q < (MB_NSIL_B > 0 ? MB_NSIL_B : 1); ++q) csd[q] = 0.0;
+        for (int q = 0; q < MB_NCTX; ++q) accd[q * 32] = 0.0;
       }
       const double* bin = (strip & 1) ? bndB : bndA;
       double* bout = (strip & 1) ? bndA : bndB;
@@ -366,6 +401,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
             }
           }
+          if (MODE == 2 && lane == 0) ef[strip * nBlk + t / MB_RESCALE] = ecur;
           if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame
             __syncwarp();
             if (lane < MB_RESCALE) {
@@ -412,8 +448,49 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
             const bool origin = (r == 0) && (col0 + c == 0);
-            if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
-            else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+            if (MODE == 3) {
+              double Fc[MB_S];
+              const int col = col0 + c;
+              if (col <= Li) {
+                const int i = Li - col, o = Lo - r;
+                const unsigned* fp = F32 + ((int64_t) o * (Li + 1) + i) * MB_S;
+                // frame of the Forward cell: forward strip i / W, lane (i % W) / C, step o + lane
+                const int eF = __ldg (ef + (i / MB_W) * nBlk + (o + (i % MB_W) / MB_C) / MB_RESCALE);
+                const int d = max (min (eF + ecur - lzi, 1000), -1023);
+                const double kap = zf * __hiloint2double ((1023 + d) << 20, 0);
+                if ((MB_S & 3) == 0) {
+#pragma unroll
+                  for (int s = 0; s < MB_S; s += 4) {
+                    const uint4 q = __ldcs ((const uint4*) (fp + s));
+                    Fc[s] = __hiloint2double ((int) q.x, 0) * kap; Fc[s + 1] = __hiloint2double ((int) q.y, 0) * kap;
+                    Fc[s + 2] = __hiloint2double ((int) q.z, 0) * kap; Fc[s + 3] = __hiloint2double ((int) q.w, 0) * kap;
+                  }
+                } else {
+#pragma unroll
+                  for (int s = 0; s < MB_S; ++s) Fc[s] = __hiloint2double ((int) __ldcs (fp + s), 0) * kap;
+                }
+              } else {
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s) Fc[s] = 0.0;
+              }
+              mb_cell_cnt_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, csd, accd, c);
+            } else {
+              if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              if (MODE == 2 && col0 + c <= Li) {
+                unsigned* fq = F32 + ((int64_t) r * (Li + 1) + (col0 + c)) * MB_S;
+                unsigned hw[MB_S];
+#pragma unroll
+                for (int s = 0; s < MB_S; ++s) hw[s] = (unsigned) __double2hiint (N[s]) + ((unsigned) __double2loint (N[s]) >> 31);
+                if ((MB_S & 3) == 0) {
+#pragma unroll
+                  for (int s = 0; s < MB_S; s += 4) *(uint4*) (fq + s) = make_uint4 (hw[s], hw[s + 1], hw[s + 2], hw[s + 3]);
+                } else {
+#pragma unroll
+                  for (int s = 0; s < MB_S; ++s) fq[s] = hw[s];
+                }
+              }
+            }
 #pragma unroll
             for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
           }
@@ -433,14 +510,17 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         }
       }
       suspect = __any_sync (MB_FULL, suspect);
+      if (MODE == 3) mb_flush_counts_lin (csd, accd, ta, A.counts, A.idTabB, lane);
       __syncwarp();
     }
     if (lane == 0) A.flag[k] = suspect;
   }
 }
 
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_fstore_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<2, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<3, 1> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
 )MBSRC";
 
 #endif
