@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--len", type=int, default=1000)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--engine", type=int, default=-1)
-    ap.add_argument("--em-pairs", type=int, default=1024, help="pairs per GPU in the E-step (counts) leg")
+    ap.add_argument("--em-pairs", type=int, default=4096, help="pairs per GPU in the E-step (counts) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

@@ -63,6 +63,9 @@ int mb_batch_create (mb_batch** out, int64_t nPairs,
                      const uint8_t* inTokens, const int64_t* inOff,
                      const uint8_t* outTokens, const int64_t* outOff);
 void mb_batch_destroy (mb_batch* b);
+/* Gives the scratch the engine keeps attached to the batch between calls (back-pointers, stored
+ * Forward values, strip boundaries) back to the device; results already fetched stay valid. */
+int mb_batch_trim (mb_batch* b);
 
 /* ---- RollingOutputForwardMatrix::logLike / ForwardMatrix::logLike (src/forward.defs.h:22-55) ----
  * loglike[k] = log-sum over all paths of pair k, -inf if none. */

@@ -20,7 +20,7 @@ _lib = None
 # every symbol include/machineboss_b200.h declares
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
-           "mb_batch_create", "mb_batch_destroy", "mb_forward", "mb_backward", "mb_viterbi",
+           "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_forward", "mb_backward", "mb_viterbi",
            "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_jit_compile_check"]
 
 
@@ -48,6 +48,7 @@ def lib():
         L.mb_batch_create.argtypes = [ctypes.POINTER(P), I64, P, P, P, P]
         L.mb_batch_destroy.argtypes = [P]
         L.mb_batch_destroy.restype = None
+        L.mb_batch_trim.argtypes = [P]
         L.mb_forward.argtypes = [P, P, P]
         L.mb_backward.argtypes = [P, P, P]
         L.mb_viterbi.argtypes = [P, P, P, P]
@@ -150,6 +151,9 @@ class Batch:
         li = np.diff(self.x_off).astype(np.float64)
         lo = np.diff(self.y_off).astype(np.float64)
         return float(((li + 1) * (lo + 1)).sum() * n_states)
+
+    def trim(self):
+        _check(lib().mb_batch_trim(self.h))
 
     def last_kernel_ms(self):
         ms, n = ctypes.c_double(0), ctypes.c_int64(0)

@@ -347,6 +347,14 @@ void mb_batch_destroy (mb_batch* b) {
   delete b;
 }
 
+int mb_batch_trim (mb_batch* b) {
+  if (!b) { set_error ("null batch"); return 1; }
+  MB_CUDA (cudaSetDevice (b->device));
+  for (int s = 0; s < WS_NSLOTS; ++s)
+    if (b->ws[s].p) { cudaFree (b->ws[s].p); b->ws[s].p = nullptr; b->ws[s].bytes = 0; }
+  return 0;
+}
+
 static int check_call (const mb_machine* m, const mb_batch* b) {
   if (!m || !b) { set_error ("null handle"); return 1; }
   if (m->device != b->device) { set_error ("machine and batch live on different devices"); return 1; }

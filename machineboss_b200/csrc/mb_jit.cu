@@ -384,8 +384,8 @@ static int nvrtc_compile (JitEngine& J, std::vector<char>& cubin, std::string* l
   if (!load_nvrtc()) return 1;
   nvrtcProgram prog;
   if (g_nvrtc.CreateProgram (&prog, J.source.c_str(), "mb_jit_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { set_error ("nvrtcCreateProgram failed"); return 1; }
-  const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--ptxas-options=-v" };
-  const nvrtcResult r = g_nvrtc.CompileProgram (prog, 4, opts);
+  const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--ptxas-options=-v", "-default-device" };
+  const nvrtcResult r = g_nvrtc.CompileProgram (prog, 5, opts);
   size_t ln = 0;
   g_nvrtc.GetProgramLogSize (prog, &ln);
   std::string log (ln, 0);
@@ -762,11 +762,20 @@ static int ensure_paths (mb_batch* b, int64_t need) {
 static double memory_budget (const mb_batch* b, int slot) {
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return 0;
-  return 0.85 * (double) (freeB + ws_bytes (b, slot) + ws_pool_bytes (b->device));   // the slot's current buffer is released before it grows
+  // the slot's current buffer is released before it grows; at most half the device per chunk, so the
+  // scratch can stay attached to the batch between calls (keep_scratch_bytes) without starving others
+  return std::min (0.85 * (double) (freeB + ws_bytes (b, slot) + ws_pool_bytes (b->device)), 0.5 * (double) totalB);
 }
 
-// large scratch is only kept between calls when it is small enough not to starve other handles
-static const size_t kKeepScratchBytes = (size_t) 24 << 30;
+// Large scratch (back-pointers, stored Forward values) stays attached to the batch between calls, so
+// that repeated calls (EM iterations) do no cudaMalloc, unless it is more than 60 % of the device;
+// mb_batch_trim or destroying the batch gives it back.
+static size_t keep_scratch_bytes() {
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return (size_t) 24 << 30;
+  return (size_t) (0.6 * (double) totalB);
+}
+#define kKeepScratchBytes keep_scratch_bytes()
 
 int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   JitEngine& J = *(JitEngine*) m->jit;
@@ -915,7 +924,8 @@ static int counts_lin (mb_machine* m, mb_batch* b, const std::vector<int64_t>& p
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), efOffHost ((size_t) b->nPairs, 0), chunkWords (1, 0), chunkEf (1, 0);
   for (int64_t k: pairs) {
     const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
-    const int64_t need = (((Li + 1) * (Lo + 1) * m->S) + 63) & ~(int64_t) 63;
+    // one block of 32 lanes x C cells x ceil(S/4) 16-byte chunks per (strip, step), in the order the sweep produces them
+    const int64_t need = ((Li + W) / W) * (Lo + 32) * (int64_t) (32 * J.C * ((m->S + 3) / 4) * 4);
     const int64_t needEf = ((Li + W) / W) * ((Lo + 32 + 15) / 16);
     if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": the Forward matrix does not fit in device memory"); return 1; }
     if (!chunks.back().empty() && (double) (chunkWords.back() + need) > budget) { chunks.emplace_back(); chunkWords.push_back (0); chunkEf.push_back (0); }

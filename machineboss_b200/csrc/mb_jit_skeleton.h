@@ -77,11 +77,15 @@ __device__ __forceinline__ float mb_warp_sum (float v) {
   return v;
 }
 
+__device__ __forceinline__ void mb_prefetch_l2 (const void* p) { asm volatile ("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ double mb_warp_sum_d (double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (MB_FULL, v, d);
   return v;
 }
+
+template<bool B> struct MBBool { static constexpr bool value = B; };
 
 template<int DIR> struct MBDir { };
 template<> struct MBDir<0> { static const int NE = MB_NEMIT_F; static const int RES = MB_S - 1; };
@@ -91,6 +95,8 @@ template<> struct MBDir<1> { static const int NE = MB_NEMIT_B; static const int 
 // others are temporaries of the cell function and need no shuffle, boundary slot or rescaling
 template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { return ((DIR ? MB_LIVE_B : MB_LIVE_F) >> s) & 1ull; }
 
+#define MB_SQ ((MB_S + 3) / 4)                 // 16-byte chunks per cell in the stored Forward blocks
+#define MB_FBLOCK (32 * MB_C * MB_SQ * 4)       // 32-bit words per warp-step block of stored Forward values
 #define MB_ROW (MB_S + 1)      // doubles per strip-boundary row: the states + the frame exponent (linear sweeps)
 
 // MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers;
@@ -164,7 +170,10 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       }
       int tokb = 0;
       const int nSteps = Lo + 32;
-      for (int t = 0; t < nSteps; ++t) {
+      // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
+      // ramp predicates (row in range, origin cell, result cell) fold away
+      auto step = [&] (const int t, auto steadyTag) {
+        constexpr bool STEADY = decltype (steadyTag)::value;
         const int r = t - lane;
         if (hasIn && (t & 31) == 0) {       // stage the next 32 rows of the previous strip's last column
           __syncwarp();
@@ -192,7 +201,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
             Lc[s] = lane ? fromLane : fromStrip;
           } else Lc[s] = NI;
         }
-        if (r >= 0 && r <= Lo) {
+        if (STEADY || (r >= 0 && r <= Lo)) {
           double Dc[MB_S];
 #pragma unroll
           for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
@@ -200,7 +209,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 #pragma unroll
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
-            const bool origin = (r == 0) && (col0 + c == 0);
+            const bool origin = !STEADY && (r == 0) && (col0 + c == 0);
             if (MODE == 0 || MODE == 2) {
               if (DIR == 0) mb_cell_fwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               else mb_cell_bwd (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
@@ -247,12 +256,19 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 #pragma unroll
             for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
           }
-          if (r == Lo) {
+          if (!STEADY && r == Lo) {
 #pragma unroll
             for (int c = 0; c < MB_C; ++c)
               if (col0 + c == Li) A.result[k] = U[c][MBDir<DIR>::RES];
           }
         }
+      };
+      {
+        int t = 0;
+        const int rampUp = min (31, nSteps);
+        for (; t < rampUp; ++t) step (t, MBBool<false>());
+        for (; t < Lo; ++t) step (t, MBBool<true>());
+        for (; t < nSteps; ++t) step (t, MBBool<false>());
       }
       if (MODE == 3) mb_flush_counts (cs, acc, ta, A.counts, A.idTabB, lane);
       __syncwarp();
@@ -334,7 +350,11 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
     }
 
     for (int strip = 0; strip < nStrips; ++strip) {
-      const int col0 = strip * MB_W + lane * MB_C;
+      // MODE 3 pads the matrix on the LEFT of the reversed sweep (columns < 0: every value there stays
+      // exactly 0, a sum of products of zeros), so that its strips and lanes mirror the Forward sweep's:
+      // step t of this strip then needs exactly the block the Forward wrote at step Lo+31-t of strip
+      // nStrips-1-strip, and both sides stream whole warp-sized blocks (see MB_FBLOCK).
+      const int col0 = strip * MB_W + lane * MB_C - (MODE == 3 ? nStrips * MB_W - (Li + 1) : 0);
       int ta[MB_C];
 #pragma unroll
       for (int c = 0; c < MB_C; ++c) {
@@ -368,7 +388,10 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
       const int nSteps = Lo + 32;
-      for (int t = 0; t < nSteps; ++t) {
+      // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
+      // ramp predicates (row in range, origin cell, result cell) fold away
+      auto step = [&] (const int t, auto steadyTag) {
+        constexpr bool STEADY = decltype (steadyTag)::value;
         const int r = t - lane;
         if ((t & (MB_RESCALE - 1)) == 0) {
           if (t > 0) {
@@ -440,34 +463,38 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             Lc[s] = lane ? fromLane : fromStrip;
           } else Lc[s] = 0.0;
         }
-        if (r >= 0 && r <= Lo) {
+        // Forward block of this step (MODE 2: written; MODE 3: read, mirrored) and L2 prefetch two steps ahead
+        unsigned* fblk = (unsigned*) 0;
+        if (MODE == 2) fblk = F32 + ((int64_t) strip * nSteps + t) * MB_FBLOCK;
+        if (MODE == 3) {
+          fblk = F32 + ((int64_t) (nStrips - 1 - strip) * nSteps + (Lo + 31 - t)) * MB_FBLOCK;
+          if (t + 2 < nSteps) mb_prefetch_l2 (fblk - 2 * MB_FBLOCK + lane * 32);
+          if (t + 2 < nSteps && MB_FBLOCK > 1024) mb_prefetch_l2 (fblk - 2 * MB_FBLOCK + 1024 + lane * 32);
+        }
+        if (STEADY || (r >= 0 && r <= Lo)) {
           double Dc[MB_S];
 #pragma unroll
           for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
 #pragma unroll
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
-            const bool origin = (r == 0) && (col0 + c == 0);
+            const bool origin = !STEADY && (r == 0) && (col0 + c == 0);
             if (MODE == 3) {
               double Fc[MB_S];
               const int col = col0 + c;
-              if (col <= Li) {
-                const int i = Li - col, o = Lo - r;
-                const unsigned* fp = F32 + ((int64_t) o * (Li + 1) + i) * MB_S;
-                // frame of the Forward cell: forward strip i / W, lane (i % W) / C, step o + lane
-                const int eF = __ldg (ef + (i / MB_W) * nBlk + (o + (i % MB_W) / MB_C) / MB_RESCALE);
+              if (col >= 0 && col <= Li) {
+                // frame of the Forward block: its strip and step
+                const int eF = __ldg (ef + (nStrips - 1 - strip) * nBlk + (Lo + 31 - t) / MB_RESCALE);
                 const int d = max (min (eF + ecur - lzi, 1000), -1023);
                 const double kap = zf * __hiloint2double ((1023 + d) << 20, 0);
-                if ((MB_S & 3) == 0) {
+                // written by Forward lane 31-lane as its cell MB_C-1-c
 #pragma unroll
-                  for (int s = 0; s < MB_S; s += 4) {
-                    const uint4 q = __ldcs ((const uint4*) (fp + s));
-                    Fc[s] = __hiloint2double ((int) q.x, 0) * kap; Fc[s + 1] = __hiloint2double ((int) q.y, 0) * kap;
-                    Fc[s + 2] = __hiloint2double ((int) q.z, 0) * kap; Fc[s + 3] = __hiloint2double ((int) q.w, 0) * kap;
-                  }
-                } else {
-#pragma unroll
-                  for (int s = 0; s < MB_S; ++s) Fc[s] = __hiloint2double ((int) __ldcs (fp + s), 0) * kap;
+                for (int g = 0; g < MB_SQ; ++g) {
+                  const uint4 q = __ldcs ((const uint4*) (fblk + (((MB_C - 1 - c) * MB_SQ + g) * 32 + (31 - lane)) * 4));
+                  if (4 * g < MB_S) Fc[4 * g] = __hiloint2double ((int) q.x, 0) * kap;
+                  if (4 * g + 1 < MB_S) Fc[4 * g + 1] = __hiloint2double ((int) q.y, 0) * kap;
+                  if (4 * g + 2 < MB_S) Fc[4 * g + 2] = __hiloint2double ((int) q.z, 0) * kap;
+                  if (4 * g + 3 < MB_S) Fc[4 * g + 3] = __hiloint2double ((int) q.w, 0) * kap;
                 }
               } else {
 #pragma unroll
@@ -477,18 +504,16 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             } else {
               if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
-              if (MODE == 2 && col0 + c <= Li) {
-                unsigned* fq = F32 + ((int64_t) r * (Li + 1) + (col0 + c)) * MB_S;
-                unsigned hw[MB_S];
+              if (MODE == 2) {
+                // high words, rounded; 16-byte chunk g of cell c goes to word ((c*MB_SQ + g)*32 + lane)*4 of
+                // the block, so every store instruction of the warp writes 512 contiguous bytes
+                unsigned hw[4 * MB_SQ];
 #pragma unroll
-                for (int s = 0; s < MB_S; ++s) hw[s] = (unsigned) __double2hiint (N[s]) + ((unsigned) __double2loint (N[s]) >> 31);
-                if ((MB_S & 3) == 0) {
+                for (int s = 0; s < 4 * MB_SQ; ++s)
+                  hw[s] = s < MB_S ? (unsigned) __double2hiint (N[s < MB_S ? s : 0]) + ((unsigned) __double2loint (N[s < MB_S ? s : 0]) >> 31) : 0u;
 #pragma unroll
-                  for (int s = 0; s < MB_S; s += 4) *(uint4*) (fq + s) = make_uint4 (hw[s], hw[s + 1], hw[s + 2], hw[s + 3]);
-                } else {
-#pragma unroll
-                  for (int s = 0; s < MB_S; ++s) fq[s] = hw[s];
-                }
+                for (int g = 0; g < MB_SQ; ++g)
+                  *(uint4*) (fblk + ((c * MB_SQ + g) * 32 + lane) * 4) = make_uint4 (hw[4 * g], hw[4 * g + 1], hw[4 * g + 2], hw[4 * g + 3]);
               }
             }
 #pragma unroll
@@ -499,7 +524,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
             bout[(int64_t) r * MB_ROW + MB_S] = (double) ecur;
           }
-          if (r == Lo) {
+          if (!STEADY && r == Lo) {
 #pragma unroll
             for (int c = 0; c < MB_C; ++c)
               if (col0 + c == Li) {
@@ -508,6 +533,13 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               }
           }
         }
+      };
+      {
+        int t = 0;
+        const int rampUp = min (31, nSteps);
+        for (; t < rampUp; ++t) step (t, MBBool<false>());
+        for (; t < Lo; ++t) step (t, MBBool<true>());
+        for (; t < nSteps; ++t) step (t, MBBool<false>());
       }
       suspect = __any_sync (MB_FULL, suspect);
       if (MODE == 3) mb_flush_counts_lin (csd, accd, ta, A.counts, A.idTabB, lane);
