@@ -341,13 +341,17 @@ def main():
 
 
 def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
-    """Roofline of the dominant kernel, the Forward fill (mb_k_forward).  DESIGN.md section 'Roofline'.
+    """Roofline of the step's kernels.  DESIGN.md section 'Roofline'.
 
-    The fill is compute-bound: its algorithmic HBM traffic is the tokens (1 B per residue) plus 8 B
-    per pair.  The binding resource is the XU (MUFU) pipe: every transition group beyond the first
-    of a state costs one log-sum-exp = 2 MUFU (ex2, lg2), and nothing in the log semiring removes
-    them.  Peak = measured MUFU issue rate (tools/pipe_peaks.cu on this pool's B200, committed as
-    profiles/r01_pipe_peaks.json) / (2 * n_lse per cell) * states per cell.
+    The fills are compute-bound (a score sweep's algorithmic HBM traffic is the tokens plus 8 B per
+    pair; the Viterbi back-pointers add 1 B per cell), so the roofline is the FP64 pipe's issue rate
+    over the per-cell transition fan-in: a dnapsw cell has T_c = 13 transition groups over 8 states,
+    5 of which are a state's second group.
+      Forward (scaled linear domain): one FP64 FMA per group  -> peak = S * DFMA / T_c
+      Viterbi (log domain, exact):    one FP64 add per group + one FP64 compare/select per second group
+                                      -> peak = S / (T_c / DADD + n_2nd / DSETP_SEL)
+    Pipe rates are measured on this pool's B200 by tools/pipe_peaks.cu (profiles/r01_pipe_peaks.json).
+    The dominant kernel of the step (longest) is reported at top level.
     """
     peaks = {}
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
@@ -359,37 +363,40 @@ def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
     if os.path.exists(pp):
         with open(pp) as f:
             pipe = {r["op"]: r["gops_per_s"] for r in json.load(f)["results"]}
-    # transition groups per cell (one add + one log-sum-exp / max each) and how many need a log-sum-exp
     groups, seen = set(), {}
     for t in range(len(mj["src"])):
         a, b = int(mj["tin"][t]), int(mj["tout"][t])
         if a == 0 and b == 0 and mj["dst"][t] <= mj["src"][t]:
             continue
         kind = 0 if (a and b) else 1 if a else 2 if b else 3
-        lab = (a, b)
-        key = (int(mj["dst"][t]), kind, int(mj["src"][t]), lab)
+        key = (int(mj["dst"][t]), kind, int(mj["src"][t]), (a, b))
         rank = seen.get(key, 0)
         seen[key] = rank + 1
         groups.add((int(mj["dst"][t]), kind, int(mj["src"][t]), rank))
     t_c = len(groups)
-    n_lse = t_c - len({g[0] for g in groups})
+    n_2nd = t_c - len({g[0] for g in groups})
     S = mj["n_states"]
-    mufu = pipe.get("mufu_ex2", 4590.0) * 1e9
+    dfma = pipe.get("dfma", 17895.0) * 1e9
     dadd = pipe.get("dadd", 17775.0) * 1e9
     dsel = pipe.get("dsetp_sel", 8475.0) * 1e9
-    peak_fwd = S / (2.0 * n_lse / mufu) / 1e9 if n_lse else None
-    peak_vit = S / (t_c / dadd + n_lse / dsel) / 1e9
-    ach = cells / fwd_ms / 1e6
+    peak_fwd = S * dfma / t_c / 1e9
+    peak_vit = S / (t_c / dadd + n_2nd / dsel) / 1e9
+    ach_fwd, ach_vit = cells / fwd_ms / 1e6, cells / vit_ms / 1e6
     hbm = peaks.get("hbm_gbs", 6650.0)
-    return {"bound": "issue (XU/MUFU pipe; the kernel is not HBM- or tensor-bound)", "kernel": "mb_k_forward",
-            "achieved": ach, "peak": peak_fwd, "unit": "GCUPS", "frac": (ach / peak_fwd) if peak_fwd else None,
-            "traffic": None,
-            "per_cell": {"transition_groups": t_c, "log_sum_exps": n_lse, "states": S},
-            "peak_source": "measured MUFU %.0f Gop/s, DADD %.0f Gop/s (profiles/r01_pipe_peaks.json)" % (mufu / 1e9, dadd / 1e9),
-            "viterbi": {"kernel": "mb_k_viterbi", "achieved": cells / vit_ms / 1e6, "peak": peak_vit,
-                        "frac": cells / vit_ms / 1e6 / peak_vit, "bound": "issue (FP64 add + compare)"},
-            "hbm": {"peak_gbs": hbm, "peak_source": "measured" if peaks else "fallback",
-                    "algorithmic_bytes_per_launch": None}}
+    fwd = {"kernel": "mb_k_forward_lin", "bound": "issue (FP64 FMA pipe)", "achieved": ach_fwd, "peak": peak_fwd,
+           "unit": "GCUPS", "frac": ach_fwd / peak_fwd, "ms_per_launch": fwd_ms}
+    vit = {"kernel": "mb_k_viterbi", "bound": "issue (FP64 add + compare/select)", "achieved": ach_vit, "peak": peak_vit,
+           "unit": "GCUPS", "frac": ach_vit / peak_vit, "ms_per_launch": vit_ms,
+           "hbm": {"algorithmic_bytes_per_launch": cells / S * 1.0, "achieved_gbs": cells / S / vit_ms / 1e6,
+                   "peak_gbs": hbm, "frac": cells / S / vit_ms / 1e6 / hbm,
+                   "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+    top = dict(vit if vit_ms >= fwd_ms else fwd)
+    top["traffic"] = None
+    top["per_cell"] = {"transition_groups": t_c, "second_groups": n_2nd, "states": S}
+    top["peak_source"] = "measured DFMA %.0f, DADD %.0f, DSETP+SEL %.0f Gop/s (profiles/r01_pipe_peaks.json)" % (dfma / 1e9, dadd / 1e9, dsel / 1e9)
+    top["forward"] = fwd
+    top["viterbi"] = vit
+    return top
 
 
 if __name__ == "__main__":

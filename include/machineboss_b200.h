@@ -103,6 +103,9 @@ int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int6
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
  * (CUDA events on the launching stream), and how many kernels that was. */
 int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches);
+/* How many pairs of the last mb_forward / mb_backward / mb_counts on this batch the scaled
+ * linear-domain sweep handed over to the log-domain kernel (dangerous dynamic range, or -inf). */
+int mb_last_redo (const mb_batch* b, int64_t* nPairs);
 
 #ifdef __cplusplus
 }

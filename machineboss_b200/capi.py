@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_jit_compile_check"]
+           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
 
 
 class MachineBossError(RuntimeError):
@@ -55,6 +55,7 @@ def lib():
         L.mb_viterbi_paths.argtypes = [P, P, P]
         L.mb_counts.argtypes = [P, P, P, P]
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
+        L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         _lib = L
     return _lib
@@ -151,6 +152,11 @@ class Batch:
         li = np.diff(self.x_off).astype(np.float64)
         lo = np.diff(self.y_off).astype(np.float64)
         return float(((li + 1) * (lo + 1)).sum() * n_states)
+
+    def last_redo(self) -> int:
+        n = ctypes.c_int64(0)
+        _check(lib().mb_last_redo(self.h, ctypes.byref(n)))
+        return n.value
 
     def trim(self):
         _check(lib().mb_batch_trim(self.h))

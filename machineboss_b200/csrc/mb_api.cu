@@ -424,4 +424,10 @@ int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches) {
   return 0;
 }
 
+int mb_last_redo (const mb_batch* b, int64_t* nPairs) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if (nPairs) *nPairs = b->lastRedo;
+  return 0;
+}
+
 }  // extern "C"

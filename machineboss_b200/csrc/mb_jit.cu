@@ -698,7 +698,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
       if (launch (m, b, backward ? 1 : 0, cost_order (b, redo), dRes, nullptr, nullptr)) return 1;
       ++launches;
     }
-  } else if (launch (m, b, backward ? 1 : 0, order, dRes, nullptr, nullptr)) return 1;
+  } else { b->lastRedo = 0; if (launch (m, b, backward ? 1 : 0, order, dRes, nullptr, nullptr)) return 1; }
   if (timing_end (b, launches)) return 1;
   MB_CUDA (cudaMemcpy (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
   return 0;

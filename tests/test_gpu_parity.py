@@ -124,6 +124,45 @@ def test_update_weights(engine):
     assert not np.allclose(before, after)
 
 
+def _trap_machine():
+    """A 'fast but doomed' branch next to a slow real one: state 1 emits a's with weight 1 and can
+    never leave; state 2 emits a or b with weight 1/8 and reaches the end.  After n a's the live
+    path is 8^-n below the trap in the same cell: the case the scaled linear sweep must hand over."""
+    w8 = math.log(0.125)
+    #          src dst in out lw
+    trans = [(0, 1, 0, 0, 0.0), (0, 2, 0, 0, 0.0), (1, 1, 0, 1, 0.0), (2, 2, 0, 1, w8), (2, 2, 0, 2, w8), (2, 3, 0, 0, 0.0)]
+    a = np.array(trans)
+    return FlatMachine(4, 0, 2, a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2].astype(np.int32),
+                       a[:, 3].astype(np.int32), a[:, 4].astype(np.float64), [], ["a", "b"])
+
+
+def test_linear_sweep_hands_dangerous_pairs_to_log_domain():
+    capi = _capi()
+    fm = _trap_machine()
+    ys = [np.array([1] * n + [2], dtype=np.uint8) for n in (10, 250, 400, 900)]
+    pairs = [(np.zeros(0, np.uint8), y) for y in ys]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    assert b.last_redo() >= 3            # 250, 400 and 900 a's exceed the 2^700 spread (or underflow outright)
+    bl = capi.backward(m, b)
+    cnt, cll = capi.counts(m, b)
+    want = np.zeros(fm.n_trans)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y)
+        assert math.isfinite(f) and close(ll[k], f) and close(cll[k], f) and close(bl[k], orc.backward(x, y))
+        orc.counts(x, y, counts=want)
+    np.testing.assert_allclose(cnt, want, rtol=REL, atol=1e-7)
+    # a machine with extreme weights never uses the linear sweep
+    fm2 = fm.with_weights(np.where(fm.lw < 0, -60.0, fm.lw))
+    m2 = make_machine(capi, fm2, 1)
+    ll2 = capi.forward(m2, b)
+    assert b.last_redo() == 0
+    for k, (x, y) in enumerate(pairs):
+        assert close(ll2[k], Oracle(fm2).forward(x, y))
+
+
 def test_errors():
     capi = _capi()
     fm = FlatMachine.from_json(load_golden("dnapsw_small")["machine"])
