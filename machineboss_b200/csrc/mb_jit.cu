@@ -214,9 +214,9 @@ static std::string term_expr (const Slot& s, int nOut, bool forward) {
 
 static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program& p, bool forward, bool viterbi, const JitEngine& J) {
   const char* name = viterbi ? "mb_cell_vit" : forward ? "mb_cell_fwd" : "mb_cell_bwd";
-  o << "__device__ __forceinline__ " << (viterbi ? "unsigned long long " : "void ") << name
+  o << "__device__ __forceinline__ " << (viterbi ? "mb_tbword " : "void ") << name
     << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P) {\n";
-  if (viterbi) o << "  unsigned long long word = 0;\n";
+  if (viterbi) o << "  mb_tbword word = 0;\n";
   const int originState = forward ? 0 : m->S - 1;
   for (int q = 0; q < m->S; ++q) {
     const int d = forward ? q : m->S - 1 - q;
@@ -224,12 +224,16 @@ static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program&
     if (s0 == s1) o << "  double n" << d << " = mb_neg_inf();\n";
     for (int k = s0; k < s1; ++k) {
       const std::string t = term_expr (p.slots[k], m->nOut, forward);
-      if (k == s0) { o << "  double n" << d << " = " << t << ";\n"; if (viterbi && s1 - s0 > 1) o << "  unsigned p" << d << " = 0u;\n"; }
-      else if (viterbi) o << "  { const double t = " << t << "; if (n" << d << " < t) { n" << d << " = t; p" << d << " = " << (k - s0) << "u; } }\n";
+      if (k == s0) o << "  double n" << d << " = " << t << ";\n";
+      else if (viterbi) {
+        // strict '<': the first maximum keeps the pointer (dpmatrix.defs.h:171-174); the pointer field
+        // of this state is overwritten in place, one logic op under the compare's predicate
+        const unsigned long long field = ((1ull << J.bits[d]) - 1ull) << J.shift[d], val = (unsigned long long) (k - s0) << J.shift[d];
+        o << "  { const double t = " << t << "; if (n" << d << " < t) { n" << d << " = t; word = (word & (mb_tbword) " << (~field) << "ull) | (mb_tbword) " << val << "ull; } }\n";
+      }
       else o << "  n" << d << " = mb_lse (n" << d << ", " << t << ");\n";
     }
     if (d == originState) o << "  if (origin) n" << d << " = 0.0;\n";
-    if (viterbi && s1 - s0 > 1) o << "  word |= (unsigned long long) p" << d << " << " << J.shift[d] << ";\n";
   }
   for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
   if (viterbi) o << "  return word;\n";
@@ -522,6 +526,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
   o << "#define MB_MINBLOCKS " << J.minBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
+  o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
   o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n__device__ __forceinline__ double mb_warp_sum_d (double);\n\n";

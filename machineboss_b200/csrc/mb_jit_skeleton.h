@@ -206,6 +206,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 #pragma unroll
           for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
           unsigned long long pack0 = 0, pack1 = 0;
+          unsigned pack32 = 0;
 #pragma unroll
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
@@ -236,19 +237,20 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               }
               mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
-              const unsigned long long word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
               const int sh = 8 * MB_TBBYTES * c;
-              if (sh < 64) pack0 |= word << (sh & 63);
-              else pack1 |= word << ((sh - 64) & 63);
+              if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
+              else if (sh < 64) pack0 |= (unsigned long long) word << (sh & 63);
+              else pack1 |= (unsigned long long) word << ((sh - 64) & 63);
             }
 #pragma unroll
             for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
           }
           if (MODE == 1) {
             uint8_t* p = tb + ((int64_t) r * pitch + col0) * MB_TBBYTES;
-            if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack0;
-            else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack0;
-            else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = (unsigned int) pack0;
+            if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack32;
+            else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack32;
+            else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = pack32;
             else if (MB_C * MB_TBBYTES == 8) *(unsigned long long*) p = pack0;
             else *(ulonglong2*) p = make_ulonglong2 (pack0, pack1);
           }
