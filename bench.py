@@ -247,12 +247,22 @@ def main():
         ms, n = batch.last_kernel_ms(); kernel_ms["viterbi"].append(ms); launches += n
         return ll, sc, plen
 
+    # end-to-end leg: host buffers in, host buffers out, through the C ABI.  Inputs are copied from
+    # pinned host memory, results land in pinned host memory the caller owns (allocated once, as a
+    # service would): per-pair log-likelihoods, Viterbi scores, path lengths and the packed paths.
+    path_cap = P * (2 * args.len + 2) * 2
+    h_ll = torch.empty(P, dtype=torch.float64).pin_memory().numpy()
+    h_sc = torch.empty(P, dtype=torch.float64).pin_memory().numpy()
+    h_len = torch.empty(P, dtype=torch.int64).pin_memory().numpy()
+    h_off = torch.empty(P + 1, dtype=torch.int64).pin_memory().numpy()
+    h_paths = torch.empty(path_cap, dtype=torch.int32).pin_memory().numpy()
+
     def step_e2e():
         b = capi.Batch(x=px.numpy(), x_off=x_off, y=py.numpy(), y_off=y_off)      # H2D from pinned memory
-        ll = capi.forward(mach, b)
-        sc, paths = capi.viterbi(mach, b, packed=True)                              # D2H of scores and packed paths
+        capi.forward_into(mach, b, h_ll)
+        total = capi.viterbi_into(mach, b, h_sc, h_len, h_off, h_paths)           # D2H of scores, lengths and packed paths
         b.close()
-        return ll, sc, paths
+        return h_ll, h_sc, (h_paths[:total], h_off)
 
     for _ in range(args.warmup):
         step_resident()

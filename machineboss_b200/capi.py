@@ -215,6 +215,27 @@ def viterbi(m: Machine, b: Batch, paths: bool = True, packed: bool = False):
     return score, [trans[off[k]:off[k + 1]] for k in range(b.n_pairs)]
 
 
+def forward_into(m: Machine, b: Batch, out: np.ndarray) -> None:
+    """mb_forward into a caller-owned float64 array (e.g. a view of pinned memory)."""
+    assert out.dtype == np.float64 and out.size >= b.n_pairs and out.flags["C_CONTIGUOUS"]
+    _check(lib().mb_forward(m.h, b.h, _ptr(out)))
+
+
+def viterbi_into(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off: np.ndarray, trans: np.ndarray) -> int:
+    """mb_viterbi + mb_viterbi_paths into caller-owned arrays; returns the total path length.
+
+    score float64[nPairs], plen int64[nPairs], off int64[nPairs+1] (filled here), trans int32[capacity]."""
+    _check(lib().mb_viterbi(m.h, b.h, _ptr(score), _ptr(plen)))
+    off[0] = 0
+    np.cumsum(plen[: b.n_pairs], out=off[1: b.n_pairs + 1])
+    total = int(off[b.n_pairs])
+    if total > trans.size:
+        raise MachineBossError("viterbi_into: path buffer too small (%d > %d)" % (total, trans.size))
+    if total:
+        _check(lib().mb_viterbi_paths(b.h, _ptr(trans), _ptr(off)))
+    return total
+
+
 def counts(m: Machine, b: Batch):
     c = np.zeros(m.n_trans, dtype=np.float64)
     ll = np.empty(b.n_pairs, dtype=np.float64)

@@ -96,7 +96,9 @@ struct mb_batch {
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   double lastMs = 0;
   int64_t lastLaunches = 0;
-  int64_t lastRedo = 0;   // pairs the scaled linear sweep handed to the log-domain kernel in the last call
+  int64_t lastRedo = 0;
+  std::vector<int64_t> fullOrder;      // all pairs, longest first (planned once)
+  bool wsOrderHoldsFull = false;       // WS_ORDER on the device currently holds fullOrder   // pairs the scaled linear sweep handed to the log-domain kernel in the last call
   // grow-only device workspace, reused across calls on this batch so that steady-state calls do
   // no cudaMalloc / cudaFree (slots: see enum WsSlot)
   struct WsEntry { void* p = nullptr; size_t bytes = 0; } ws[16];

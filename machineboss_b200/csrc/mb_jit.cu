@@ -431,7 +431,7 @@ static int compile (mb_machine* m, JitEngine& J) {
   const int ne[9] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
   for (int q = 0; q < 9; ++q) {
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
-    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * 32 * (m->S + 1)) * 8
+    J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (8 + 32 * (m->S + 1))) * 8
       + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0);
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
@@ -635,6 +635,16 @@ static std::vector<int64_t> cost_order (const mb_batch* b, const std::vector<int
   return o;
 }
 
+static const std::vector<int64_t>& full_order (mb_batch* b) {
+  if ((int64_t) b->fullOrder.size() != b->nPairs) {
+    std::vector<int64_t> all ((size_t) b->nPairs);
+    for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
+    b->fullOrder = cost_order (b, all);
+    b->wsOrderHoldsFull = false;
+  }
+  return b->fullOrder;
+}
+
 struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const double* ll = nullptr; double* counts = nullptr; int32_t* flag = nullptr;
                    unsigned* F32 = nullptr; const int64_t* f32Off = nullptr; int32_t* ef = nullptr; const int64_t* efOff = nullptr; };
 
@@ -650,11 +660,15 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
+  if (ws_bytes (b, WS_ORDER) < order.size() * 8) b->wsOrderHoldsFull = false;   // the slot is about to be re-allocated
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
   double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (grid * warpsPerBlock * bndStride) * 8);
   unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
   if (!dOrder || !dBnd || !dCounter) return 1;
-  MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  const bool isFull = &order == &b->fullOrder;
+  if (!(isFull && b->wsOrderHoldsFull))
+    MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  b->wsOrderHoldsFull = isFull;
   MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
   MBArgsHost A;
   A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
@@ -677,9 +691,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
   JitEngine& J = *(JitEngine*) m->jit;
   if (b->nPairs == 0) return 0;
-  std::vector<int64_t> all ((size_t) b->nPairs);
-  for (int64_t k = 0; k < b->nPairs; ++k) all[k] = k;
-  const std::vector<int64_t> order = cost_order (b, all);
+  const std::vector<int64_t>& order = full_order (b);
   double* dRes = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
   if (!dRes) return 1;
   if (timing_begin (b)) return 1;
@@ -829,7 +841,9 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   int64_t packed = 0, launches = 0;
   double ms = 0;
   for (size_t c = 0; c < chunks.size(); ++c) {
-    const std::vector<int64_t> order = cost_order (b, chunks[c]);
+    std::vector<int64_t> chunkOrder;
+    if (chunks.size() > 1) chunkOrder = cost_order (b, chunks[c]);
+    const std::vector<int64_t>& order = chunks.size() > 1 ? chunkOrder : full_order (b);
     if (timing_begin (b)) return 1;
     if (launch (m, b, 2, order, dRes, dTb, dTbOff)) return 1;
     ++launches;

@@ -112,10 +112,14 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
-  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_ROW);
-  // thread-private count accumulators of the emitting transition groups: acc[ctx * 32 + lane]
-  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_ROW)) + warp * (32 * MB_NCTX) + lane;
-  const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
+  // shared memory: emission table | per warp: 64-byte ring of the last 64 output-row tokens (lane j is
+  // j rows behind lane 0) | per warp: 32 staged boundary rows | per warp: thread-private count
+  // accumulators of the emitting transition groups, acc[ctx * 32 + lane] (count kernels only)
+  const int nWarps = blockDim.x >> 5;
+  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 64;
+  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 8 + warp * (32 * MB_ROW);
+  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + nWarps * (8 + 32 * MB_ROW)) + warp * (32 * MB_NCTX) + lane;
+  const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
   const double NI = mb_neg_inf();
@@ -168,7 +172,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         for (int q = lane; q < 32 * MB_ROW; q += 32) sIn[q] = NI;
         __syncwarp();
       }
-      int tokb = 0;
+      int ynext = (lane >= 1 && lane <= Lo) ? (DIR ? y[Lo - lane] : y[lane - 1]) - 1 : 0;   // token of row `lane`
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
@@ -185,12 +189,14 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           }
           __syncwarp();
         }
-        const int tprev = __shfl_up_sync (MB_FULL, tokb, 1);
-        if (lane == 0) {
-          int tok = 1;
-          if (t >= 1 && t <= Lo) tok = DIR ? y[Lo - t] : y[t - 1];
-          tokb = tok - 1;
-        } else tokb = tprev;
+        if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
+          __syncwarp();
+          ring[(t + lane) & 63] = (uint8_t) ynext;
+          const int rowN = t + 32 + lane;
+          ynext = (rowN >= 1 && rowN <= Lo) ? (DIR ? y[Lo - rowN] : y[rowN - 1]) - 1 : 0;
+          __syncwarp();
+        }
+        const int tokb = ring[(t - lane) & 63];
         // left neighbour's last column at this row: a shuffle, or the staged boundary row for lane 0
         double Lc[MB_S];
 #pragma unroll
@@ -317,10 +323,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
-  double* sIn = mb_smem + ((NE + 1) & ~1) + warp * (32 * MB_ROW);
-  // thread-private FP64 count accumulators of the emitting transition groups: accd[ctx * 32 + lane]
-  double* accd = mb_smem + ((NE + 1) & ~1) + (blockDim.x >> 5) * (32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
-  const int64_t wslot = (int64_t) blockIdx.x * (blockDim.x >> 5) + warp;
+  // shared memory layout as in mb_run; the count accumulators are FP64 here: accd[ctx * 32 + lane]
+  const int nWarps = blockDim.x >> 5;
+  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 64;
+  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 8 + warp * (32 * MB_ROW);
+  double* accd = mb_smem + ((NE + 1) & ~1) + nWarps * (8 + 32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
+  const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
 
@@ -386,7 +394,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         for (int q = lane; q < MB_RESCALE * MB_ROW; q += 32) sIn[q] = 0.0;
         __syncwarp();
       }
-      int tokb = 0;
+      int ynext = (lane >= 1 && lane <= Lo) ? (DIR ? y[Lo - lane] : y[lane - 1]) - 1 : 0;   // token of row `lane`
       // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
       const int nSteps = Lo + 32;
@@ -450,12 +458,14 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             __syncwarp();
           }
         }
-        const int tprev = __shfl_up_sync (MB_FULL, tokb, 1);
-        if (lane == 0) {
-          int tok = 1;
-          if (t >= 1 && t <= Lo) tok = DIR ? y[Lo - t] : y[t - 1];
-          tokb = tok - 1;
-        } else tokb = tprev;
+        if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
+          __syncwarp();
+          ring[(t + lane) & 63] = (uint8_t) ynext;
+          const int rowN = t + 32 + lane;
+          ynext = (rowN >= 1 && rowN <= Lo) ? (DIR ? y[Lo - rowN] : y[rowN - 1]) - 1 : 0;
+          __syncwarp();
+        }
+        const int tokb = ring[(t - lane) & 63];
         double Lc[MB_S];
 #pragma unroll
         for (int s = 0; s < MB_S; ++s) {
