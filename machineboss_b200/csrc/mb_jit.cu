@@ -776,7 +776,19 @@ static int ensure_paths (mb_batch* b, int64_t need) {
   return 0;
 }
 
-static double memory_budget (const mb_batch* b, int slot) {
+static size_t device_total_bytes (int device) {
+  static size_t cache[64] = { 0 };
+  if (device >= 0 && device < 64 && cache[device]) return cache[device];
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return (size_t) 64 << 30;
+  if (device >= 0 && device < 64) cache[device] = totalB;
+  return totalB;
+}
+
+// How much one chunk of scratch may take.  If what the slot already holds is enough for `wanted`
+// no driver query is made (cudaMemGetInfo costs milliseconds with large allocations live).
+static double memory_budget (const mb_batch* b, int slot, double wanted) {
+  if (wanted <= (double) ws_bytes (b, slot)) return (double) ws_bytes (b, slot);
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return 0;
   // the slot's current buffer is released before it grows; at most half the device per chunk, so the
@@ -787,12 +799,7 @@ static double memory_budget (const mb_batch* b, int slot) {
 // Large scratch (back-pointers, stored Forward values) stays attached to the batch between calls, so
 // that repeated calls (EM iterations) do no cudaMalloc, unless it is more than 60 % of the device;
 // mb_batch_trim or destroying the batch gives it back.
-static size_t keep_scratch_bytes() {
-  size_t freeB = 0, totalB = 0;
-  if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return (size_t) 24 << 30;
-  return (size_t) (0.6 * (double) totalB);
-}
-#define kKeepScratchBytes keep_scratch_bytes()
+#define kKeepScratchBytes ((size_t) (0.6 * (double) device_total_bytes (b->device)))
 
 int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   JitEngine& J = *(JitEngine*) m->jit;
@@ -802,7 +809,10 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   const bool trace = pathLen != nullptr;
   const int W = 32 * J.C;
   // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
-  const double budget = memory_budget (b, WS_TB);
+  double wanted = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k)
+    wanted += (double) ((((b->yOff[k + 1] - b->yOff[k]) + 1) * ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * W) * J.tbBytes + 255) & ~(int64_t) 255);
+  const double budget = memory_budget (b, WS_TB, wanted);
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
   std::vector<int64_t> chunkBytes (1, 0);
@@ -885,7 +895,9 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
 static int counts_log (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, bool wantCounts,
                        std::vector<double>& hostCounts, double* loglike, int64_t& launches, double& ms) {
   if (pairs.empty()) return 0;
-  const double budget = memory_budget (b, WS_F) / 8.0;
+  double wanted = 0;
+  for (int64_t k: pairs) wanted += 8.0 * (double) (((((b->xOff[k + 1] - b->xOff[k]) + 1) * ((b->yOff[k + 1] - b->yOff[k]) + 1) * m->S) + 31) & ~(int64_t) 31);
+  const double budget = memory_budget (b, WS_F, wanted) / 8.0;
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), chunkDoubles (1, 0);
   for (int64_t k: pairs) {
@@ -938,7 +950,10 @@ static int counts_lin (mb_machine* m, mb_batch* b, const std::vector<int64_t>& p
                        std::vector<double>& hostCounts, double* loglike, int64_t& launches, double& ms) {
   JitEngine& J = *(JitEngine*) m->jit;
   const int W = 32 * J.C;
-  const double budget = memory_budget (b, WS_F) / 4.0;     // in 32-bit words
+  double wanted = 0;
+  for (int64_t k: pairs)
+    wanted += 4.0 * (double) ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * ((b->yOff[k + 1] - b->yOff[k]) + 32) * (int64_t) (32 * J.C * ((m->S + 3) / 4) * 4));
+  const double budget = memory_budget (b, WS_F, wanted) / 4.0;     // in 32-bit words
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), efOffHost ((size_t) b->nPairs, 0), chunkWords (1, 0), chunkEf (1, 0);
   for (int64_t k: pairs) {
