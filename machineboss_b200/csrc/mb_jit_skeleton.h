@@ -112,13 +112,13 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
-  // shared memory: emission table | per warp: 64-byte ring of the last 64 output-row tokens (lane j is
-  // j rows behind lane 0) | per warp: 32 staged boundary rows | per warp: thread-private count
+  // shared memory: emission table | per warp: 128-byte ring of output-row tokens, published a block
+  // ahead so that each lane can fetch its next step's token during the current step | per warp: 32 staged boundary rows | per warp: thread-private count
   // accumulators of the emitting transition groups, acc[ctx * 32 + lane] (count kernels only)
   const int nWarps = blockDim.x >> 5;
-  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 64;
-  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 8 + warp * (32 * MB_ROW);
-  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + nWarps * (8 + 32 * MB_ROW)) + warp * (32 * MB_NCTX) + lane;
+  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 128;
+  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 16 + warp * (32 * MB_ROW);
+  float* acc = (float*) (mb_smem + ((NE + 1) & ~1) + nWarps * (16 + 32 * MB_ROW)) + warp * (32 * MB_NCTX) + lane;
   const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -172,31 +172,40 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         for (int q = lane; q < 32 * MB_ROW; q += 32) sIn[q] = NI;
         __syncwarp();
       }
-      int ynext = (lane >= 1 && lane <= Lo) ? (DIR ? y[Lo - lane] : y[lane - 1]) - 1 : 0;   // token of row `lane`
+      double stageNext[MB_S];
+#pragma unroll
+      for (int s = 0; s < MB_S; ++s)
+        stageNext[s] = (hasIn && mb_live<DIR> (s) && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_ROW + s) : NI;
+      // row tokens (0-based): rows 0..31 are published now, rows 32..63 at step 0, and so on one block ahead
+      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (DIR ? y[Lo - row] : y[row - 1]) - 1 : 0; };
+      __syncwarp();
+      ring[lane] = (uint8_t) rowTok (lane);
+      int ynext = rowTok (32 + lane);
+      __syncwarp();
+      int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
       auto step = [&] (const int t, auto steadyTag) {
         constexpr bool STEADY = decltype (steadyTag)::value;
         const int r = t - lane;
-        if (hasIn && (t & 31) == 0) {       // stage the next 32 rows of the previous strip's last column
-          __syncwarp();
+        if (hasIn && (t & 31) == 0) {       // stage 32 rows of the previous strip's last column: lane q takes row t+q;
+          __syncwarp();                     // the values were fetched a block ago, the next block's are fetched now
 #pragma unroll
-          for (int q = 0; q < MB_ROW; ++q) {
-            const int e = q * 32 + lane;
-            const int row = t + e / MB_ROW;
-            sIn[e] = row <= Lo ? __ldcg (bin + (int64_t) row * MB_ROW + (e % MB_ROW)) : NI;
-          }
+          for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) sIn[lane * MB_ROW + s] = stageNext[s];
+#pragma unroll
+          for (int s = 0; s < MB_S; ++s)
+            if (mb_live<DIR> (s)) stageNext[s] = (t + 32 + lane <= Lo) ? __ldcg (bin + (int64_t) (t + 32 + lane) * MB_ROW + s) : NI;
           __syncwarp();
         }
         if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
           __syncwarp();
-          ring[(t + lane) & 63] = (uint8_t) ynext;
-          const int rowN = t + 32 + lane;
-          ynext = (rowN >= 1 && rowN <= Lo) ? (DIR ? y[Lo - rowN] : y[rowN - 1]) - 1 : 0;
+          ring[(t + 32 + lane) & 127] = (uint8_t) ynext;
+          ynext = rowTok (t + 64 + lane);
           __syncwarp();
         }
-        const int tokb = ring[(t - lane) & 63];
+        const int tokb = tokNext;
+        tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
         // left neighbour's last column at this row: a shuffle, or the staged boundary row for lane 0
         double Lc[MB_S];
 #pragma unroll
@@ -325,9 +334,9 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   __syncthreads();
   // shared memory layout as in mb_run; the count accumulators are FP64 here: accd[ctx * 32 + lane]
   const int nWarps = blockDim.x >> 5;
-  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 64;
-  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 8 + warp * (32 * MB_ROW);
-  double* accd = mb_smem + ((NE + 1) & ~1) + nWarps * (8 + 32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
+  uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 128;
+  double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 16 + warp * (32 * MB_ROW);
+  double* accd = mb_smem + ((NE + 1) & ~1) + nWarps * (16 + 32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
   const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -394,9 +403,21 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         for (int q = lane; q < MB_RESCALE * MB_ROW; q += 32) sIn[q] = 0.0;
         __syncwarp();
       }
-      int ynext = (lane >= 1 && lane <= Lo) ? (DIR ? y[Lo - lane] : y[lane - 1]) - 1 : 0;   // token of row `lane`
+      // row tokens (0-based): rows 0..31 are published now, rows 32..63 at step 0, and so on one block ahead
+      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (DIR ? y[Lo - row] : y[row - 1]) - 1 : 0; };
+      __syncwarp();
+      ring[lane] = (uint8_t) rowTok (lane);
+      int ynext = rowTok (32 + lane);
+      __syncwarp();
+      int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
+      double stageNext[MB_S];
+      int stageNextE = ecur;
+#pragma unroll
+      for (int s = 0; s < MB_S; ++s)
+        stageNext[s] = (hasIn && mb_live<DIR> (s) && lane < MB_RESCALE && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_ROW + s) : 0.0;
+      if (hasIn && lane < MB_RESCALE && lane <= Lo) stageNextE = (int) __ldcg (bin + (int64_t) lane * MB_ROW + MB_S);
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
@@ -435,37 +456,36 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             }
           }
           if (MODE == 2 && lane == 0) ef[strip * nBlk + t / MB_RESCALE] = ecur;
-          if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame
-            __syncwarp();
+          if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame;
+            __syncwarp();  // lane q < MB_RESCALE takes row t+q: fetched a block ago, the next block's are fetched now
             if (lane < MB_RESCALE) {
-              const int row = t + lane;
               double* dst = sIn + lane * MB_ROW;
-              if (row <= Lo) {
-                const double* src = bin + (int64_t) row * MB_ROW;
-                int d = (int) __ldcg (src + MB_S) - ecur;
-                bool far = d < -900 || d > 900, any = false;
-                d = max (min (d, 1000), -1023);
-                const double f = __hiloint2double ((1023 + d) << 20, 0);
+              int d = stageNextE - ecur;
+              const bool far = d < -900 || d > 900;
+              bool any = false;
+              d = max (min (d, 1000), -1023);
+              const double f = __hiloint2double ((1023 + d) << 20, 0);
 #pragma unroll
-                for (int s = 0; s < MB_S; ++s)
-                  if (mb_live<DIR> (s)) { const double v = __ldcg (src + s); any |= v != 0.0; dst[s] = v * f; }
-                if (far && any) suspect = 1;
-              } else {
+              for (int s = 0; s < MB_S; ++s)
+                if (mb_live<DIR> (s)) { any |= stageNext[s] != 0.0; dst[s] = stageNext[s] * f; }
+              if (far && any) suspect = 1;
+              const int rowN = t + MB_RESCALE + lane;
+              const double* src = bin + (int64_t) rowN * MB_ROW;
 #pragma unroll
-                for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) dst[s] = 0.0;
-              }
+              for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) stageNext[s] = rowN <= Lo ? __ldcg (src + s) : 0.0;
+              stageNextE = rowN <= Lo ? (int) __ldcg (src + MB_S) : ecur;
             }
             __syncwarp();
           }
         }
         if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
           __syncwarp();
-          ring[(t + lane) & 63] = (uint8_t) ynext;
-          const int rowN = t + 32 + lane;
-          ynext = (rowN >= 1 && rowN <= Lo) ? (DIR ? y[Lo - rowN] : y[rowN - 1]) - 1 : 0;
+          ring[(t + 32 + lane) & 127] = (uint8_t) ynext;
+          ynext = rowTok (t + 64 + lane);
           __syncwarp();
         }
-        const int tokb = ring[(t - lane) & 63];
+        const int tokb = tokNext;
+        tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
         double Lc[MB_S];
 #pragma unroll
         for (int s = 0; s < MB_S; ++s) {
