@@ -46,7 +46,7 @@ def machine_args(specs, params):
 
 
 def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backward,counts", matrices=False,
-         ref_expect=None, note=""):
+         ref_expect=None, note="", gz=False):
     """pairs: list of (in_symbols, out_symbols) or ("synth", N, Li, Lo, seed)."""
     margs = machine_args(specs, params)
     mach = run(margs + ["--emit-machine"])
@@ -80,8 +80,13 @@ def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backw
     j = {"name": name, "note": note, "specs": specs, "params": params, "machine": mach, "synth": synth,
          "pairs": out_pairs, "loglike": res.get("loglike"), "counts": res.get("counts"),
          "ref_expect": ref_expect or {}}
-    with open(os.path.join(OUT, name + ".json"), "w") as fo:
-        json.dump(j, fo, separators=(",", ":"))
+    if gz:
+        import gzip
+        with gzip.open(os.path.join(OUT, name + ".json.gz"), "wt", compresslevel=9) as fo:
+            json.dump(j, fo, separators=(",", ":"))
+    else:
+        with open(os.path.join(OUT, name + ".json"), "w") as fo:
+            json.dump(j, fo, separators=(",", ":"))
     print("%-28s S=%-5d T=%-6d pairs=%d" % (name, mach["nStates"], len(mach["trans"]), len(out_pairs)))
 
 
@@ -153,6 +158,12 @@ def main():
     case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
          note="config-4 style composite (S=308)")
     case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
+    # --- config 5 style: an HMMER3 profile (examples/PF00516.hmm, local core machine of src/hmmer.cpp),
+    #     alone and composed with an error model; large state spaces, generator machines (no input) ---
+    hmm = "hmmer:" + os.path.join(REF, "examples/PF00516.hmm")
+    case("hmmer_pf00516", [hmm], ("synth", 3, 0, 37, 108), gz=True, note="PF00516 local core, S=2439, T=24367")
+    case("hmmer_pf00516_protpsw", [hmm, "preset:protpsw"], ("synth", 1, 0, 21, 109), gz=True,
+         note="BASELINE config 5 machine: PF00516 => protpsw, S=12176, T=74012")
     case("dnapsw_1k", ["preset:dnapsw"], ("synth", 1, 1000, 1000, 12345), do="rolling,viterbi,path",
          note="BASELINE config 1: one 1 kb x 1 kb pair")
 

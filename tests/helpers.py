@@ -68,12 +68,17 @@ class FlatMachine:
 
 
 def load_golden(name: str) -> dict:
-    with open(os.path.join(GOLDEN, name + ".json")) as f:
+    path = os.path.join(GOLDEN, name + ".json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    import gzip
+    with gzip.open(path + ".gz", "rt") as f:
         return json.load(f)
 
 
 def golden_names() -> list:
-    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+    return sorted(f[:-5] if f.endswith(".json") else f[:-8] for f in os.listdir(GOLDEN) if f.endswith((".json", ".json.gz")))
 
 
 # ---------------------------------------------------------------------------------------------
