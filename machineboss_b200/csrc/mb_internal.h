@@ -101,7 +101,7 @@ struct mb_batch {
   bool wsOrderHoldsFull = false;       // WS_ORDER on the device currently holds fullOrder   // pairs the scaled linear sweep handed to the log-domain kernel in the last call
   // grow-only device workspace, reused across calls on this batch so that steady-state calls do
   // no cudaMalloc / cudaFree (slots: see enum WsSlot)
-  struct WsEntry { void* p = nullptr; size_t bytes = 0; } ws[16];
+  struct WsEntry { void* p = nullptr; size_t bytes = 0; } ws[24];
   // result of the last mb_viterbi with traceback: packed paths on the device
   int32_t* dPaths = nullptr;
   std::vector<int64_t> pathStart, pathLen;   // per pair: offset into dPaths and length
@@ -127,7 +127,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 
 // per-batch workspace (mb_api.cu)
-enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_NSLOTS };
+enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_NSLOTS };
 void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set on failure
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);

@@ -432,7 +432,8 @@ static int compile (mb_machine* m, JitEngine& J) {
   for (int q = 0; q < 9; ++q) {
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
     J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (16 + 32 * (m->S + 1))) * 8
-      + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0);
+      + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0)
+      + (q == 8 ? (size_t) (J.threads / 32) * 2 * (32 * J.C * ((m->S + 3) / 4) * 4) * 4 : 0);     // two staged Forward blocks per warp
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
@@ -722,11 +723,15 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
 }
 
 // DPMatrix::traceBack (dpmatrix.defs.h:82-110) over the packed back-pointers written by
-// mb_k_viterbi: one thread per pair; pass 1 (out == nullptr) measures, pass 2 writes start -> end.
+// mb_k_viterbi: one thread per pair walks from (Li, Lo, end state) to (0, 0, start state) and writes
+// the transition ids end-aligned into the pair's scratch slot (capacity = the longest possible
+// path), so that they read start -> end; pack_paths_kernel then copies them into the packed result.
+// The walk is a chain of dependent loads; the pointers a few rows up the diagonal are prefetched
+// into L2 because that is where the path most likely goes.
 __global__ void jit_traceback_kernel (TbPlan p, DevBatch b, const int64_t* __restrict__ pairs, int64_t nPairsHere,
                                       const uint8_t* __restrict__ tb, const int64_t* __restrict__ tbOff,
                                       const double* __restrict__ score, int64_t* __restrict__ len,
-                                      int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+                                      int32_t* __restrict__ tmp, const int64_t* __restrict__ tmpOff) {
   const int64_t slot = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nPairsHere) return;
   const int64_t k = pairs[slot];
@@ -735,13 +740,14 @@ __global__ void jit_traceback_kernel (TbPlan p, DevBatch b, const int64_t* __res
   const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
   const int64_t pitch = ((Li + p.W) / p.W) * p.W;
   const uint8_t* base = tb + tbOff[k];
+  int32_t* out = tmp + tmpOff[slot + 1];     // one past the end of this pair's slot
   int64_t n = 0;
   if (score[k] > -INFINITY) {
-    const int64_t total = out ? len[slot] : 0;
     int64_t i = Li, o = Lo;
     int s = p.S - 1;
     while (i > 0 || o > 0 || s != 0) {
       const uint8_t* wp = base + (o * pitch + i) * p.tbBytes;
+      if (i >= 8 && o >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - (8 * pitch + 8) * p.tbBytes));
       unsigned long long word = 0;
       for (int q = 0; q < p.tbBytes; ++q) word |= (unsigned long long) wp[q] << (8 * q);
       const int ptr = (int) ((word >> p.shift[s]) & ((1ull << p.bits[s]) - 1ull));
@@ -750,15 +756,27 @@ __global__ void jit_traceback_kernel (TbPlan p, DevBatch b, const int64_t* __res
       const int type = p.slotType[sl];
       const int a = i ? x[i - 1] - 1 : 0, c = o ? y[o - 1] - 1 : 0;
       const int li = type == T_MATCH ? a * p.nOut + c : type == T_DELETE ? a : type == T_INSERT ? c : 0;
-      if (out) out[outOff[slot] + total - 1 - n] = p.idTab[p.slotIdOff[sl] + li];
       ++n;
+      out[-n] = p.idTab[p.slotIdOff[sl] + li];
       if (type == T_MATCH || type == T_DELETE) --i;
       if (type == T_MATCH || type == T_INSERT) --o;
       s = p.slotOther[sl];
       if (i < 0 || o < 0) break;
     }
   }
-  if (!out) len[slot] = n;
+  len[slot] = n;
+}
+
+// one warp per pair: copy its path from the end of its scratch slot to its place in the packed result
+__global__ void pack_paths_kernel (int64_t nPairsHere, const int64_t* __restrict__ len, const int32_t* __restrict__ tmp,
+                                   const int64_t* __restrict__ tmpOff, int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+  const int64_t slot = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= nPairsHere) return;
+  const int64_t n = len[slot];
+  const int32_t* src = tmp + tmpOff[slot + 1] - n;
+  int32_t* dst = out + outOff[slot];
+  for (int64_t q = lane; q < n; q += 32) dst[q] = src[q];
 }
 
 static int ensure_paths (mb_batch* b, int64_t need) {
@@ -859,9 +877,21 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     ++launches;
     if (trace) {
       const size_t n = chunks[c].size();
+      // scratch slots sized for the longest possible path: every loud transition consumes a symbol, and
+      // between two of them at most (silent depth) silent transitions fit
+      const int64_t depth = (int64_t) m->fwdLevelOff.size() - 1;
+      std::vector<int64_t> tmpOff (n + 1, 0);
+      for (size_t q = 0; q < n; ++q) {
+        const int64_t k = chunks[c][q];
+        tmpOff[q + 1] = tmpOff[q] + ((b->xOff[k + 1] - b->xOff[k]) + (b->yOff[k + 1] - b->yOff[k]) + 1) * depth;
+      }
+      int32_t* dTmp = (int32_t*) ws_reserve (b, WS_PATHTMP, (size_t) tmpOff[n] * 4);
+      int64_t* dTmpOff = (int64_t*) ws_reserve (b, WS_PATHTMPOFF, (n + 1) * 8);
+      if (!dTmp || !dTmpOff) return 1;
       MB_CUDA (cudaMemcpyAsync (dPairs, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
+      MB_CUDA (cudaMemcpyAsync (dTmpOff, tmpOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, b->stream));
       const unsigned tg = (unsigned) ((n + 63) / 64);
-      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, nullptr, nullptr);
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, dTmp, dTmpOff);
       MB_CUDA (cudaGetLastError());
       std::vector<int64_t> len (n), off (n);
       MB_CUDA (cudaMemcpyAsync (len.data(), dLen, n * 8, cudaMemcpyDeviceToHost, b->stream));
@@ -874,7 +904,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       }
       if (ensure_paths (b, packed)) return 1;
       MB_CUDA (cudaMemcpyAsync (dOutOff, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
-      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, b->dPaths, dOutOff);
+      pack_paths_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, b->stream>>> ((int64_t) n, dLen, dTmp, dTmpOff, b->dPaths, dOutOff);
       MB_CUDA (cudaGetLastError());
       launches += 2;
     }

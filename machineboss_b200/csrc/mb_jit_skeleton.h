@@ -77,6 +77,12 @@ __device__ __forceinline__ float mb_warp_sum (float v) {
   return v;
 }
 
+__device__ __forceinline__ void mb_cp_async16 (void* smem, const void* gmem) {
+  asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned) __cvta_generic_to_shared (smem)), "l"(gmem));
+}
+__device__ __forceinline__ void mb_cp_async_commit() { asm volatile ("cp.async.commit_group;"); }
+__device__ __forceinline__ void mb_cp_async_wait_all() { asm volatile ("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void mb_prefetch_l2 (const void* p) { asm volatile ("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 __device__ __forceinline__ double mb_warp_sum_d (double v) {
@@ -337,6 +343,8 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 128;
   double* sIn = mb_smem + ((NE + 1) & ~1) + nWarps * 16 + warp * (32 * MB_ROW);
   double* accd = mb_smem + ((NE + 1) & ~1) + nWarps * (16 + 32 * MB_ROW) + warp * (32 * MB_NCTX) + lane;
+  // MODE 3: two warp-step blocks of stored Forward words, filled by cp.async one step ahead
+  unsigned* fstage = (unsigned*) (mb_smem + ((NE + 1) & ~1) + nWarps * (16 + 32 * MB_ROW + 32 * MB_NCTX)) + warp * (2 * MB_FBLOCK);
   const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -418,6 +426,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       for (int s = 0; s < MB_S; ++s)
         stageNext[s] = (hasIn && mb_live<DIR> (s) && lane < MB_RESCALE && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_ROW + s) : 0.0;
       if (hasIn && lane < MB_RESCALE && lane <= Lo) stageNextE = (int) __ldcg (bin + (int64_t) lane * MB_ROW + MB_S);
+      if (MODE == 3) {      // the first step's Forward block
+        const unsigned* srcb = F32 + ((int64_t) (nStrips - 1 - strip) * (Lo + 32) + (Lo + 31)) * MB_FBLOCK;
+#pragma unroll
+        for (int j = 0; j < MB_C * MB_SQ; ++j) mb_cp_async16 (fstage + (j * 32 + lane) * 4, srcb + (j * 32 + (31 - lane)) * 4);
+        mb_cp_async_commit();
+      }
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
@@ -495,13 +509,28 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             Lc[s] = lane ? fromLane : fromStrip;
           } else Lc[s] = 0.0;
         }
-        // Forward block of this step (MODE 2: written; MODE 3: read, mirrored) and L2 prefetch two steps ahead
+        // Forward block of this step.  MODE 2 writes it.  MODE 3 reads the mirrored one: it was copied
+        // into shared memory by cp.async during the previous step (each lane copies exactly the 16-byte
+        // chunks it will read, so no warp barrier is needed), the next one is issued now, and the one
+        // after that is pulled into L2.
         unsigned* fblk = (unsigned*) 0;
+        const unsigned* fsm = (const unsigned*) 0;
         if (MODE == 2) fblk = F32 + ((int64_t) strip * nSteps + t) * MB_FBLOCK;
         if (MODE == 3) {
           fblk = F32 + ((int64_t) (nStrips - 1 - strip) * nSteps + (Lo + 31 - t)) * MB_FBLOCK;
-          if (t + 2 < nSteps) mb_prefetch_l2 (fblk - 2 * MB_FBLOCK + lane * 32);
-          if (t + 2 < nSteps && MB_FBLOCK > 1024) mb_prefetch_l2 (fblk - 2 * MB_FBLOCK + 1024 + lane * 32);
+          mb_cp_async_wait_all();
+          fsm = fstage + (t & 1) * MB_FBLOCK;
+          if (t + 1 < nSteps) {
+            unsigned* dstb = fstage + ((t + 1) & 1) * MB_FBLOCK;
+            const unsigned* srcb = fblk - MB_FBLOCK;
+#pragma unroll
+            for (int j = 0; j < MB_C * MB_SQ; ++j) mb_cp_async16 (dstb + (j * 32 + lane) * 4, srcb + (j * 32 + (31 - lane)) * 4);
+            mb_cp_async_commit();
+          }
+          if (t + 3 < nSteps) {
+            mb_prefetch_l2 (fblk - 3 * MB_FBLOCK + lane * 32);
+            if (MB_FBLOCK > 1024) mb_prefetch_l2 (fblk - 3 * MB_FBLOCK + 1024 + lane * 32);
+          }
         }
         if (STEADY || (r >= 0 && r <= Lo)) {
           double Dc[MB_S];
@@ -522,7 +551,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
                 // written by Forward lane 31-lane as its cell MB_C-1-c
 #pragma unroll
                 for (int g = 0; g < MB_SQ; ++g) {
-                  const uint4 q = __ldcs ((const uint4*) (fblk + (((MB_C - 1 - c) * MB_SQ + g) * 32 + (31 - lane)) * 4));
+                  const uint4 q = *(const uint4*) (fsm + (((MB_C - 1 - c) * MB_SQ + g) * 32 + lane) * 4);
                   if (4 * g < MB_S) Fc[4 * g] = __hiloint2double ((int) q.x, 0) * kap;
                   if (4 * g + 1 < MB_S) Fc[4 * g + 1] = __hiloint2double ((int) q.y, 0) * kap;
                   if (4 * g + 2 < MB_S) Fc[4 * g + 2] = __hiloint2double ((int) q.z, 0) * kap;
