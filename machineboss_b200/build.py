@@ -48,11 +48,11 @@ CLI = os.path.join(HERE, "boss_b200")
 def build_host(force: bool = False) -> str:
     """Compile the C++ host mirror's CLI (host/boss_b200_cli.cpp) against the shared library."""
     src = os.path.join(HERE, "host", "boss_b200_cli.cpp")
-    deps = [src, os.path.join(HERE, "host", "boss_b200.h"), os.path.join(HERE, "host", "mbjson.h"), LIB]
+    deps = [src, os.path.join(HERE, "host", "boss_b200.h"), os.path.join(HERE, "host", "boss_b200_fit.h"), os.path.join(HERE, "host", "mbjson.h"), LIB]
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     build()
-    cmd = ["g++", "-std=c++11", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-Wl,-rpath," + HERE]
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-Wl,-rpath," + HERE]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)

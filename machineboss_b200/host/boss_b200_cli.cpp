@@ -2,6 +2,15 @@
 // running on the B200 engine:
 //
 //   boss_b200 --evaluated-machine M.json [data options] -L | -V | -A | -C
+//   boss_b200 --machine M.json [-P params.json] [-N constraints.json] [-U] [data options] -L | -V | -A | -C | -T
+//
+//   --machine       a symbolic machine in the reference's basic JSON form (states, transitions with
+//                   weight expressions, "defs", "cons"); machine algebra ("compose", ...) is rejected
+//   -P, --params    parameter values;  -U, --use-defaults  fill missing ones from the constraints
+//                   (boss.cpp:789);  -N, --constraints  for -T
+//   -T, --train     Baum-Welch: E-step on the GPU, M-step on the host; prints the fitted parameters
+//                   like boss.cpp:776-787
+//   -C with --machine prints PARAMETER counts like `boss -C` (counts.cpp:80-106)
 //
 //   -L, --loglike   Forward log-likelihoods, printed like boss.cpp:792-808:  [["in","out",ll],...]
 //   -V, --viterbi   Viterbi log-likelihoods, same layout                     (boss.cpp:819-848)
@@ -19,7 +28,7 @@
 #include <fstream>
 #include <iostream>
 
-#include "boss_b200.h"
+#include "boss_b200_fit.h"
 
 using namespace MachineBoss;
 using namespace std;
@@ -50,14 +59,21 @@ static NamedSeq<string> fromChars (const string& s) {
 
 int main (int argc, char** argv) {
   try {
-    string machineFile;
-    vector<string> dataFiles;
+    string machineFile, symbolicFile, consFile, mstepFile;
+    vector<string> dataFiles, paramFiles;
+    bool useDefaults = false, doT = false;
     vector<NamedSeq<string> > inSeqs, outSeqs;
     bool doL = false, doV = false, doA = false, doC = false;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
       auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
       if (f == "--evaluated-machine" || f == "-m") machineFile = next();
+      else if (f == "--machine") symbolicFile = next();
+      else if (f == "-P" || f == "--params") paramFiles.push_back (next());
+      else if (f == "-N" || f == "--constraints") consFile = next();
+      else if (f == "-U" || f == "--use-defaults") useDefaults = true;
+      else if (f == "-T" || f == "--train") doT = true;
+      else if (f == "--mstep") mstepFile = next();   // one M-step from raw counts [[..],[..]] (no device needed)
       else if (f == "-D" || f == "--data") dataFiles.push_back (next());
       else if (f == "--input-fasta") { for (auto& s: readFasta (next())) inSeqs.push_back (s); }
       else if (f == "--output-fasta") { for (auto& s: readFasta (next())) outSeqs.push_back (s); }
@@ -71,8 +87,41 @@ int main (int argc, char** argv) {
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
       else throw runtime_error ("unknown option " + f);
     }
-    if (machineFile.empty()) throw runtime_error ("please specify --evaluated-machine");
-    const EvaluatedMachine eval = EvaluatedMachine::fromFile (machineFile);
+    if (machineFile.empty() && symbolicFile.empty()) throw runtime_error ("please specify --evaluated-machine or --machine");
+    Machine machine;
+    Params seed, params;
+    Constraints constraints;
+    const bool symbolic = !symbolicFile.empty();
+    if (symbolic) {
+      machine = Machine::fromFile (symbolicFile);
+      for (const auto& pf: paramFiles) seed = seed.combine (Params::fromFile (pf));
+      if (consFile.size()) constraints = Constraints::fromFile (consFile);
+      params = machine.funcs.combine (seed).combine (machine.getParamDefs (useDefaults));    // boss.cpp:789
+    } else if (doT) throw runtime_error ("-T needs a symbolic --machine");
+
+    if (mstepFile.size()) {   // MachineObjective::optimize on given counts (counts.cpp:225-295)
+      if (!symbolic) throw runtime_error ("--mstep needs a symbolic --machine");
+      std::ifstream cf (mstepFile);
+      if (!cf) throw runtime_error ("File not found: " + mstepFile);
+      std::stringstream ss; ss << cf.rdbuf();
+      const Json cj = Json::parse (ss.str());
+      MachineCounts counts;
+      for (const auto& row: cj.arr) { counts.count.push_back (vector<double>()); for (const auto& v: row.arr) counts.count.back().push_back (v.asNumber()); }
+      if (counts.count.size() != machine.nStates()) throw runtime_error ("Number of states mismatch");
+      const Params start = machine.cons.combine (constraints).defaultParams().combine (seed, true);
+      const MachineObjective objective (machine, counts, constraints, machine.funcs);
+      objective.optimize (start).writeJson (cout);
+      cout << endl;
+      return EXIT_SUCCESS;
+    }
+
+    EvaluatedMachine eval;
+    if (!symbolic) eval = EvaluatedMachine::fromFile (machineFile);
+    else if (!doT) eval = evaluate (machine, params);
+    else {   // only the alphabets are needed to assemble the data
+      Params any = machine.funcs.combine (seed).combine (machine.cons.combine (constraints).defaultParams(), false);
+      eval = evaluate (machine, any);
+    }
 
     SeqPairList data;
     for (const auto& df: dataFiles) { SeqPairList l = SeqPairList::fromFile (df); data.seqPairs.insert (data.seqPairs.end(), l.seqPairs.begin(), l.seqPairs.end()); }
@@ -82,7 +131,23 @@ int main (int argc, char** argv) {
     for (const auto& i: inSeqs) for (const auto& o: outSeqs) { SeqPair sp; sp.input = i; sp.output = o; data.seqPairs.push_back (sp); }
     if (data.seqPairs.empty() && inputEmpty && outputEmpty) data.seqPairs.push_back (SeqPair());   // boss.cpp:769-770
     if (data.seqPairs.empty()) throw runtime_error ("no sequence data given");
-    if (!(doL || doV || doA || doC)) throw runtime_error ("nothing to do: give -L, -V, -A or -C");
+    if (!(doL || doV || doA || doC || doT)) throw runtime_error ("nothing to do: give -L, -V, -A, -C or -T");
+
+    if (doT) {   // boss.cpp:776-787
+      if (constraints.empty() && machine.cons.empty()) throw runtime_error ("To fit parameters, please specify a constraints file and (for machines with input/output) a data file");
+      MachineFitter fitter;
+      fitter.machine = machine;
+      fitter.constraints = constraints;
+      fitter.constants = machine.funcs;
+      fitter.seed = fitter.allConstraints().defaultParams().combine (seed, true);
+      if (getenv ("MB_VERBOSE"))
+        fitter.onIteration = [] (int it, double ll, const Params&) { cerr << "Baum-Welch iteration #" << it << ": log-likelihood " << ll << endl; };
+      params = fitter.fit (data);
+      params.writeJson (cout);
+      cout << endl;
+      if (!(doL || doV || doA || doC)) return EXIT_SUCCESS;
+      eval = evaluate (machine, machine.funcs.combine (params));
+    }
 
     // pairs the machine cannot tokenise report -Infinity under -L/-V/-A (boss.cpp:798,826) ...
     SeqPairList ok;
@@ -107,6 +172,12 @@ int main (int argc, char** argv) {
     if (doC) {
       // ... but -C does not test canTokenize (boss.cpp:811-816): an unknown symbol throws
       const MachineCounts counts (eval, data);
+      if (symbolic) {   // MachineCounts::writeParamCountsJson (counts.cpp:80-87)
+        cout << "{";
+        size_t np = 0;
+        for (const auto& nc: paramCounts (counts, machine, params)) cout << (np++ ? "," : "") << "\"" << Json::escape (nc.first) << "\":" << nc.second;
+        cout << "}" << endl;
+      } else
       counts.writeJson (cout);
     }
     if (doA || doV) {

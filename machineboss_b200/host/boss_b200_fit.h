@@ -1,0 +1,550 @@
+// boss_b200_fit.h -- the symbolic layer the EM driver needs, and the EM driver itself
+// (`boss -T` / baumWelchFit cannot complete without an M-step, and the
+// reference's M-step is GSL's BFGS, a system package that is not in this image).
+//
+// What is mirrored, with the reference's names and JSON formats:
+//   WeightExpr / WeightAlgebra   src/weight.h:54-114      expression trees over named parameters
+//                                                         (JSON grammar of weight.cpp:547-590)
+//   Params / ParamDefs           src/params.h:14-37
+//   Constraints                  src/constraints.h:14-28  prob / rate / norm, defaultParams (constraints.cpp:65-75)
+//   Machine (basic form)         src/machine.h:93-103     states, transitions, "defs", "cons" (machine.cpp:347-...)
+//   EvaluatedMachine(Machine, Params)   src/eval.cpp:42-70
+//   MachineCounts::paramCounts   src/counts.cpp:89-106
+//   MachineObjective             src/counts.cpp:117-295   same objective and the same re-parameterisation
+//                                                         (stick-breaking z = exp(-x^2) for norm groups,
+//                                                         p = exp(-x^2) for prob, r = x^2 for rate)
+//   MachineFitter::fit           src/fitter.cpp:23-47     same loop and stopping rule
+//
+// What is NOT mirrored: machine algebra (compose, concat, union, ... machine.cpp:352-430) -- a JSON
+// machine using those operators is rejected; build the composite with the reference and pass the
+// result.  Derivatives are exact forward-mode (dual numbers) instead of symbolic; the minimiser is a
+// plain BFGS with a backtracking line search and the reference's limits (gradient norm 1e-3, 100
+// iterations).  The reference's own fit goldens pin the M-step to 4 significant digits only
+// (Makefile:502-513), so beyond that M-step parity is unpinned by construction; the E-step is not
+// affected.
+#ifndef MB_HOST_BOSS_B200_FIT_H
+#define MB_HOST_BOSS_B200_FIT_H
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <set>
+
+#include "boss_b200.h"
+
+namespace MachineBoss {
+
+// ---- weight expressions ----
+struct WeightExprNode;
+typedef std::shared_ptr<const WeightExprNode> WeightExpr;
+
+struct WeightExprNode {
+  enum Op { Const, Param, Mul, Div, Add, Sub, Log, Exp } op = Const;
+  double value = 0;
+  string name;
+  WeightExpr l, r;
+};
+
+typedef map<string, WeightExpr> ParamDefs;
+
+struct Dual {   // value + gradient with respect to the active variables
+  double v = 0;
+  vector<double> d;
+  Dual() {}
+  Dual (double v_, size_t n) : v (v_), d (n, 0.) {}
+};
+
+namespace WeightAlgebra {
+  inline WeightExpr doubleConstant (double x) { auto n = std::make_shared<WeightExprNode>(); n->op = WeightExprNode::Const; n->value = x; return n; }
+  inline WeightExpr one() { return doubleConstant (1.); }
+  inline WeightExpr zero() { return doubleConstant (0.); }
+  inline WeightExpr param (const string& p) { auto n = std::make_shared<WeightExprNode>(); n->op = WeightExprNode::Param; n->name = p; return n; }
+  inline WeightExpr binary (WeightExprNode::Op op, const WeightExpr& l, const WeightExpr& r) { auto n = std::make_shared<WeightExprNode>(); n->op = op; n->l = l; n->r = r; return n; }
+  inline WeightExpr multiply (const WeightExpr& l, const WeightExpr& r) { return binary (WeightExprNode::Mul, l, r); }
+  inline WeightExpr divide (const WeightExpr& l, const WeightExpr& r) { return binary (WeightExprNode::Div, l, r); }
+  inline WeightExpr add (const WeightExpr& l, const WeightExpr& r) { return binary (WeightExprNode::Add, l, r); }
+  inline WeightExpr subtract (const WeightExpr& l, const WeightExpr& r) { return binary (WeightExprNode::Sub, l, r); }
+  inline WeightExpr logOf (const WeightExpr& x) { return binary (WeightExprNode::Log, x, nullptr); }
+  inline WeightExpr expOf (const WeightExpr& x) { return binary (WeightExprNode::Exp, x, nullptr); }
+  inline WeightExpr negate (const WeightExpr& x) { return subtract (one(), x); }          // "not": 1 - x
+  inline WeightExpr minus (const WeightExpr& x) { return subtract (zero(), x); }
+  inline WeightExpr geometricSum (const WeightExpr& x) { return divide (one(), negate (x)); }   // 1 / (1 - x)
+
+  // JSON grammar of weight.cpp:547-590 ("expr" strings need the reference's PEG parser: rejected)
+  inline WeightExpr fromJson (const Json& w) {
+    switch (w.type) {
+      case Json::Null: return one();
+      case Json::Bool: return w.b ? one() : zero();
+      case Json::Number: return doubleConstant (w.num);
+      case Json::String: return param (w.str);
+      case Json::Array: throw runtime_error ("Unexpected type in WeightExpr: array");
+      case Json::Object: break;
+    }
+    if (w.obj.empty()) throw runtime_error ("No opcode in WeightExpr");
+    const string& opcode = w.obj.begin()->first;
+    const Json& args = w.obj.begin()->second;
+    if (opcode == "log") return logOf (fromJson (args));
+    if (opcode == "exp") return expOf (fromJson (args));
+    if (opcode == "not") return negate (fromJson (args));
+    if (opcode == "geomsum") return geometricSum (fromJson (args));
+    if (opcode == "*") return multiply (fromJson (args.at (0)), fromJson (args.at (1)));
+    if (opcode == "/") return divide (fromJson (args.at (0)), fromJson (args.at (1)));
+    if (opcode == "+") return add (fromJson (args.at (0)), fromJson (args.at (1)));
+    if (opcode == "-") return subtract (fromJson (args.at (0)), fromJson (args.at (1)));
+    throw runtime_error ("Unknown or unsupported opcode " + opcode + " in WeightExpr JSON");
+  }
+
+  inline void params (const WeightExpr& w, const ParamDefs& defs, std::set<string>& out, std::set<string>& visiting) {
+    if (!w) return;
+    if (w->op == WeightExprNode::Param) {
+      if (defs.count (w->name)) {
+        if (visiting.count (w->name)) throw runtime_error ("Cyclic parameter definition: " + w->name);
+        visiting.insert (w->name);
+        params (defs.at (w->name), defs, out, visiting);
+        visiting.erase (w->name);
+      } else out.insert (w->name);
+      return;
+    }
+    params (w->l, defs, out, visiting);
+    params (w->r, defs, out, visiting);
+  }
+  inline std::set<string> params (const WeightExpr& w, const ParamDefs& defs) { std::set<string> out, vis; params (w, defs, out, vis); return out; }
+
+  // value and exact gradient; `vars` maps the active variable names to their index and current value
+  struct Env {
+    const ParamDefs* defs;
+    const map<string, std::pair<size_t, double> >* vars;
+    size_t n;
+    map<string, Dual> memo;
+    int depth = 0;
+  };
+  inline Dual evalDual (const WeightExpr& w, Env& env) {
+    typedef WeightExprNode N;
+    if (!w) return Dual (1., env.n);
+    switch (w->op) {
+      case N::Const: return Dual (w->value, env.n);
+      case N::Param: {
+        if (env.vars && env.vars->count (w->name)) {
+          const auto& iv = env.vars->at (w->name);
+          Dual r (iv.second, env.n);
+          r.d[iv.first] = 1.;
+          return r;
+        }
+        auto m = env.memo.find (w->name);
+        if (m != env.memo.end()) return m->second;
+        if (!env.defs || !env.defs->count (w->name)) throw runtime_error ("Parameter " + w->name + " not defined");
+        if (++env.depth > 1000) throw runtime_error ("Cyclic parameter definition: " + w->name);
+        const Dual r = evalDual (env.defs->at (w->name), env);
+        --env.depth;
+        env.memo[w->name] = r;
+        return r;
+      }
+      default: break;
+    }
+    const Dual a = evalDual (w->l, env);
+    Dual r (0., env.n);
+    if (w->op == N::Log) { r.v = std::log (a.v); for (size_t k = 0; k < env.n; ++k) r.d[k] = a.d[k] / a.v; return r; }
+    if (w->op == N::Exp) { r.v = std::exp (a.v); for (size_t k = 0; k < env.n; ++k) r.d[k] = a.d[k] * r.v; return r; }
+    const Dual b = evalDual (w->r, env);
+    switch (w->op) {
+      case N::Mul: r.v = a.v * b.v; for (size_t k = 0; k < env.n; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k]; break;
+      case N::Div: r.v = a.v / b.v; for (size_t k = 0; k < env.n; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) / b.v; break;
+      case N::Add: r.v = a.v + b.v; for (size_t k = 0; k < env.n; ++k) r.d[k] = a.d[k] + b.d[k]; break;
+      case N::Sub: r.v = a.v - b.v; for (size_t k = 0; k < env.n; ++k) r.d[k] = a.d[k] - b.d[k]; break;
+      default: break;
+    }
+    return r;
+  }
+  inline double eval (const WeightExpr& w, const ParamDefs& defs) {
+    Env env { &defs, nullptr, 0 };
+    return evalDual (w, env).v;
+  }
+  inline double asDouble (const WeightExpr& w) {
+    if (!w || w->op != WeightExprNode::Const) throw runtime_error ("Parameter value is not a number");
+    return w->value;
+  }
+}  // namespace WeightAlgebra
+
+// ---- Params (src/params.h) ----
+struct Params {
+  ParamDefs defs;
+  void readJson (const Json& pj) { for (const auto& kv: pj.obj) defs[kv.first] = WeightAlgebra::fromJson (kv.second); }
+  void writeJson (ostream& out) const {   // numeric parameters, name order (params.cpp)
+    out << "{";
+    size_t n = 0;
+    for (const auto& kv: defs) {
+      out << (n++ ? "," : "") << "\"" << Json::escape (kv.first) << "\":";
+      if (kv.second && kv.second->op == WeightExprNode::Const) out << kv.second->value;
+      else out << WeightAlgebra::eval (kv.second, defs);
+    }
+    out << "}";
+  }
+  Params combine (const Params& p, bool overwriteOwnDefs = false) const {   // params.cpp: like JavaScript's extend()
+    Params q (*this);
+    for (const auto& kv: p.defs) {
+      if (q.defs.count (kv.first) && !overwriteOwnDefs) {
+        const WeightExpr &a = q.defs.at (kv.first), &b = kv.second;
+        const bool same = a && b && a->op == WeightExprNode::Const && b->op == WeightExprNode::Const && a->value == b->value;
+        if (!same) throw runtime_error ("Inconsistent parameter definitions for " + kv.first);
+      }
+      q.defs[kv.first] = kv.second;
+    }
+    return q;
+  }
+  static Params fromFile (const string& filename) {
+    std::ifstream f (filename);
+    if (!f) throw runtime_error ("File not found: " + filename);
+    std::stringstream ss; ss << f.rdbuf();
+    Params p; p.readJson (Json::parse (ss.str()));
+    return p;
+  }
+};
+typedef Params ParamAssign;
+typedef Params ParamFuncs;
+
+// ---- Constraints (src/constraints.h) ----
+struct Constraints {
+  vector<string> prob, rate;
+  vector<vector<string> > norm;
+  bool empty() const { return prob.empty() && rate.empty() && norm.empty(); }
+  void readJson (const Json& pj) {
+    if (pj.has ("norm")) for (const auto& n: pj.at ("norm").arr) { vector<string> c; for (const auto& p: n.arr) c.push_back (p.asString()); norm.push_back (c); }
+    if (pj.has ("prob")) for (const auto& p: pj.at ("prob").arr) prob.push_back (p.asString());
+    if (pj.has ("rate")) for (const auto& r: pj.at ("rate").arr) rate.push_back (r.asString());
+  }
+  Params defaultParams() const {   // constraints.cpp:65-75
+    Params params;
+    for (auto& c: norm) for (auto& cp: c) params.defs[cp] = WeightAlgebra::doubleConstant (1. / (double) c.size());
+    for (auto& pp: prob) params.defs[pp] = WeightAlgebra::doubleConstant (.5);
+    for (auto& rp: rate) params.defs[rp] = WeightAlgebra::doubleConstant (1.);
+    return params;
+  }
+  Constraints combine (const Constraints& c) const {
+    Constraints r (*this);
+    r.prob.insert (r.prob.end(), c.prob.begin(), c.prob.end());
+    r.rate.insert (r.rate.end(), c.rate.begin(), c.rate.end());
+    r.norm.insert (r.norm.end(), c.norm.begin(), c.norm.end());
+    return r;
+  }
+  static Constraints fromFile (const string& filename) {
+    std::ifstream f (filename);
+    if (!f) throw runtime_error ("File not found: " + filename);
+    std::stringstream ss; ss << f.rdbuf();
+    Constraints c; c.readJson (Json::parse (ss.str()));
+    return c;
+  }
+};
+
+// ---- Machine, basic form (src/machine.h:93-103, machine.cpp readJson's final branch) ----
+struct SymbolicTransition {
+  InputSymbol in;
+  OutputSymbol out;
+  StateIndex dest = 0;
+  WeightExpr weight;
+};
+
+struct MachineState {
+  Json name;
+  vector<SymbolicTransition> trans;
+};
+
+struct Machine {
+  ParamFuncs funcs;
+  Constraints cons;
+  vector<MachineState> state;
+  StateIndex nStates() const { return state.size(); }
+  void readJson (const Json& pj) {
+    static const char* algebra[] = { "compose", "compose-sum", "compose-unsort", "concat", "intersect", "intersect-sum", "intersect-unsort",
+                                     "union", "loop", "opt", "star", "plus", "eliminate", "merge", "reverse", "revcomp", "transpose" };
+    for (const char* op: algebra)
+      if (pj.has (op)) throw runtime_error (string ("machine JSON uses the \"") + op + "\" operator: machine algebra is not part of the B200 path; build the machine with the reference and pass the result");
+    if (pj.has ("defs")) funcs.readJson (pj.at ("defs"));
+    if (pj.has ("cons")) cons.readJson (pj.at ("cons"));
+    const Json& jstate = pj.at ("state");
+    map<string, StateIndex> id2n;
+    std::set<string> dupIds;
+    for (const Json& js: jstate.arr) {
+      MachineState ms;
+      if (js.has ("n") && (StateIndex) js.at ("n").asInt() != state.size()) throw runtime_error ("StateIndex n out of sequence");
+      if (js.has ("id")) {
+        const string idStr = js.at ("id").dump();
+        if (id2n.count (idStr)) dupIds.insert (idStr); else id2n[idStr] = state.size();
+        ms.name = js.at ("id");
+      }
+      state.push_back (ms);
+    }
+    size_t n = 0;
+    for (const Json& js: jstate.arr) {
+      MachineState& ms = state[n++];
+      if (!js.has ("trans")) continue;
+      for (const Json& jt: js.at ("trans").arr) {
+        SymbolicTransition t;
+        const Json& dest = jt.at ("to");
+        if (dest.type == Json::Number) t.dest = (StateIndex) dest.asInt();
+        else {
+          const string dstr = dest.dump();
+          if (!id2n.count (dstr)) throw runtime_error ("No such state in \"to\": " + dstr);
+          if (dupIds.count (dstr)) throw runtime_error ("Ambiguous destination state ID in \"to\": " + dstr);
+          t.dest = id2n.at (dstr);
+        }
+        if (jt.has ("in")) t.in = jt.at ("in").asString();
+        if (jt.has ("out")) t.out = jt.at ("out").asString();
+        if (jt.has ("expr")) throw runtime_error ("\"expr\" weight strings need the reference's parser; use the JSON weight form");
+        t.weight = jt.has ("weight") ? WeightAlgebra::fromJson (jt.at ("weight")) : WeightAlgebra::one();
+        if (t.dest >= state.size()) throw runtime_error ("State " + std::to_string (t.dest) + " does not exist");
+        ms.trans.push_back (t);
+      }
+    }
+  }
+  static Machine fromFile (const string& filename) {
+    std::ifstream f (filename);
+    if (!f) throw runtime_error ("File not found: " + filename);
+    std::stringstream ss; ss << f.rdbuf();
+    Machine m; m.readJson (Json::parse (ss.str()));
+    return m;
+  }
+  vector<InputSymbol> inputAlphabet() const {   // alphabetically sorted (machine.cpp:175-182)
+    std::set<string> a;
+    for (const auto& ms: state) for (const auto& t: ms.trans) if (!t.in.empty()) a.insert (t.in);
+    return vector<string> (a.begin(), a.end());
+  }
+  vector<OutputSymbol> outputAlphabet() const {
+    std::set<string> a;
+    for (const auto& ms: state) for (const auto& t: ms.trans) if (!t.out.empty()) a.insert (t.out);
+    return vector<string> (a.begin(), a.end());
+  }
+  Params getParamDefs (bool assignDefaultValuesToMissingParams = false) const {   // machine.cpp:2022-2027
+    Params p = funcs;
+    if (assignDefaultValuesToMissingParams) p = cons.defaultParams().combine (p, true);
+    return p;
+  }
+};
+
+// EvaluatedMachine (Machine, Params): log (WeightAlgebra::eval (weight)) per transition (eval.cpp:42-70)
+inline EvaluatedMachine evaluate (const Machine& machine, const Params& params) {
+  vector<MachineTransition> flat;
+  vector<Json> names;
+  for (StateIndex s = 0; s < machine.nStates(); ++s) {
+    names.push_back (machine.state[s].name);
+    for (const auto& t: machine.state[s].trans) {
+      MachineTransition f;
+      f.src = s; f.dest = t.dest; f.in = t.in; f.out = t.out;
+      f.logWeight = std::log (WeightAlgebra::eval (t.weight, params.defs));
+      flat.push_back (f);
+    }
+  }
+  return EvaluatedMachine (machine.nStates(), machine.inputAlphabet(), machine.outputAlphabet(), flat, names);
+}
+
+inline vector<double> logWeights (const Machine& machine, const Params& params) {
+  vector<double> lw;
+  for (const auto& ms: machine.state) for (const auto& t: ms.trans) lw.push_back (std::log (WeightAlgebra::eval (t.weight, params.defs)));
+  return lw;
+}
+
+// MachineCounts::paramCounts (counts.cpp:89-106): expectation of d(logLike)/d(log param)
+inline map<string, double> paramCounts (const MachineCounts& counts, const Machine& machine, const ParamAssign& prob) {
+  map<string, double> paramCount;
+  for (StateIndex s = 0; s < machine.nStates(); ++s) {
+    size_t ti = 0;
+    for (const auto& trans: machine.state[s].trans) {
+      const double c = counts.count[s][ti++];
+      const std::set<string> ps = WeightAlgebra::params (trans.weight, ParamDefs());
+      if (ps.empty()) continue;
+      map<string, std::pair<size_t, double> > vars;
+      size_t k = 0;
+      for (const auto& p: ps) { vars[p] = std::make_pair (k++, WeightAlgebra::asDouble (prob.defs.at (p))); }
+      WeightAlgebra::Env env { &prob.defs, &vars, ps.size() };
+      const Dual w = WeightAlgebra::evalDual (trans.weight, env);
+      for (const auto& p: ps) paramCount[p] += c * w.d[vars[p].first] * vars[p].second / w.v;
+    }
+  }
+  return paramCount;
+}
+
+// ---- M-step (counts.cpp:117-295) ----
+struct MachineObjective {
+  Constraints constraints;
+  vector<string> transformedParam;
+  map<string, size_t> transformedParamIndex;
+  ParamDefs constantDefs, paramTransformDefs, allDefs;
+  WeightExpr objective;
+
+  MachineObjective (const Machine& machine, const MachineCounts& counts, const Constraints& cons, const Params& constants)
+    : constraints (machine.cons.combine (cons)), constantDefs (machine.funcs.combine (constants).defs), objective (WeightAlgebra::zero())
+  {
+    using namespace WeightAlgebra;
+    for (StateIndex s = 0; s < machine.nStates(); ++s) {
+      size_t t = 0;
+      for (const auto& tr: machine.state[s].trans)
+        objective = subtract (objective, multiply (doubleConstant (counts.count[s][t++]), logOf (tr.weight)));
+    }
+    const std::set<string> p = params (objective, ParamDefs());
+    int trIdx = 0;
+    auto makeTransformedParamName = [&] (const string& prm) -> string {
+      string trParam;
+      do trParam = string ("$x") + std::to_string (++trIdx); while (p.count (trParam));
+      transformedParamIndex[prm] = transformedParam.size();
+      transformedParam.push_back (trParam);
+      return trParam;
+    };
+    auto squareFunc = [] (const string& tr) { return multiply (param (tr), param (tr)); };
+    auto expFunc = [&] (const string& tr) { return expOf (minus (squareFunc (tr))); };
+    // p_i = (1 - exp(-x_i^2)) prod_{k<i} exp(-x_k^2)
+    for (const auto& c: constraints.norm) {
+      WeightExpr notPrev = one();
+      for (size_t n = 0; n < c.size(); ++n) {
+        if (n + 1 == c.size()) paramTransformDefs[c[n]] = notPrev;
+        else {
+          const WeightExpr notThis = expFunc (makeTransformedParamName (c[n]));
+          paramTransformDefs[c[n]] = multiply (notPrev, negate (notThis));
+          notPrev = multiply (notPrev, notThis);
+        }
+      }
+    }
+    for (const auto& pp: constraints.prob) paramTransformDefs[pp] = expFunc (makeTransformedParamName (pp));
+    for (const auto& rp: constraints.rate) paramTransformDefs[rp] = squareFunc (makeTransformedParamName (rp));
+    allDefs = constantDefs;
+    for (const auto& kv: paramTransformDefs) allDefs[kv.first] = kv.second;
+  }
+
+  // objective and gradient at the transformed point x
+  double eval (const vector<double>& x, vector<double>* grad) const {
+    map<string, std::pair<size_t, double> > vars;
+    for (size_t n = 0; n < transformedParam.size(); ++n) vars[transformedParam[n]] = std::make_pair (n, x[n]);
+    WeightAlgebra::Env env { &allDefs, &vars, x.size() };
+    const Dual r = WeightAlgebra::evalDual (objective, env);
+    if (grad) *grad = r.d;
+    return r.v;
+  }
+
+  Params optimize (const Params& seed) const {
+    const size_t n = transformedParam.size();
+    vector<double> x (n, 0.);
+    // starting point from the seed (counts.cpp:233-262)
+    for (const auto& c: constraints.norm) {
+      double pSum = 0;
+      for (size_t k = 0; k + 1 < c.size(); ++k) {
+        const double p = WeightAlgebra::asDouble (seed.defs.at (c[k]));
+        const double z = 1 - p / (1 - pSum);
+        x[transformedParamIndex.at (c[k])] = std::sqrt (-std::log (z));
+        pSum += p;
+      }
+    }
+    for (const auto& pp: constraints.prob) x[transformedParamIndex.at (pp)] = std::sqrt (-std::log (WeightAlgebra::asDouble (seed.defs.at (pp))));
+    for (const auto& rp: constraints.rate) x[transformedParamIndex.at (rp)] = std::sqrt (WeightAlgebra::asDouble (seed.defs.at (rp)));
+
+    if (n) bfgs (x);
+
+    Params finalParams = seed;
+    map<string, std::pair<size_t, double> > vars;
+    for (size_t k = 0; k < n; ++k) vars[transformedParam[k]] = std::make_pair (k, x[k]);
+    for (const auto& pt: paramTransformDefs) {
+      WeightAlgebra::Env env { &allDefs, &vars, n };
+      finalParams.defs[pt.first] = WeightAlgebra::doubleConstant (WeightAlgebra::evalDual (pt.second, env).v);
+    }
+    return finalParams;
+  }
+
+private:
+  // BFGS on the inverse Hessian with an Armijo backtracking line search; the reference's limits:
+  // stop when |gradient| < 1e-3 (EpsilonAbsolute) or after 100 iterations (MaxIterations).
+  void bfgs (vector<double>& x) const {
+    const size_t n = x.size();
+    vector<double> g (n), gNew (n), d (n), xNew (n), s (n), yv (n);
+    vector<vector<double> > H (n, vector<double> (n, 0.));
+    for (size_t k = 0; k < n; ++k) H[k][k] = 1.;
+    double f = eval (x, &g);
+    auto norm = [] (const vector<double>& v) { double t = 0; for (double e: v) t += e * e; return std::sqrt (t); };
+    for (int iter = 0; iter < 100; ++iter) {
+      if (!std::isfinite (f)) break;
+      for (size_t i = 0; i < n; ++i) { d[i] = 0; for (size_t j = 0; j < n; ++j) d[i] -= H[i][j] * g[j]; }
+      double slope = 0;
+      for (size_t i = 0; i < n; ++i) slope += d[i] * g[i];
+      if (!(slope < 0)) { for (size_t i = 0; i < n; ++i) { d[i] = -g[i]; for (size_t j = 0; j < n; ++j) H[i][j] = (i == j); } slope = -norm (g) * norm (g); }
+      // first step like gsl's bfgs2 (StepSize 0.1 along the unit direction), then unit steps
+      double alpha = iter == 0 ? std::min (1., 0.1 / std::max (norm (d), 1e-300)) : 1.;
+      double fNew = f;
+      bool ok = false;
+      for (int ls = 0; ls < 60; ++ls) {
+        for (size_t i = 0; i < n; ++i) xNew[i] = x[i] + alpha * d[i];
+        fNew = eval (xNew, &gNew);
+        if (std::isfinite (fNew) && fNew <= f + 1e-4 * alpha * slope) { ok = true; break; }
+        alpha *= 0.5;
+      }
+      if (!ok) break;
+      double ys = 0;
+      for (size_t i = 0; i < n; ++i) { s[i] = xNew[i] - x[i]; yv[i] = gNew[i] - g[i]; ys += s[i] * yv[i]; }
+      if (ys > 1e-300) {   // H <- (I - s y'/ys) H (I - y s'/ys) + s s'/ys
+        vector<double> Hy (n, 0.);
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) Hy[i] += H[i][j] * yv[j];
+        double yHy = 0;
+        for (size_t i = 0; i < n; ++i) yHy += yv[i] * Hy[i];
+        for (size_t i = 0; i < n; ++i)
+          for (size_t j = 0; j < n; ++j)
+            H[i][j] += (1 + yHy / ys) * s[i] * s[j] / ys - (Hy[i] * s[j] + s[i] * Hy[j]) / ys;
+      }
+      x = xNew; g = gNew; f = fNew;
+      if (norm (g) < 1e-3) break;
+    }
+  }
+};
+
+// ---- EM driver (src/fitter.h:11-20, fitter.cpp:23-47) ----
+struct MachineFitter {
+  Machine machine;
+  Constraints constraints;
+  Params seed, constants;
+  int iterations = 0;             // EM iterations run by the last fit()
+  double logLike = 0;             // log-likelihood of the last E-step
+  std::function<void (int, double, const Params&)> onIteration;   // the reference logs these at -v2 / -v4
+
+  Constraints allConstraints() const { return machine.cons.combine (constraints); }
+
+  Params fit (const SeqPairList& trainingSet) {
+    const int MaxEMIterations = 1000;
+    const double MinEMImprovement = .001;
+    Params params = seed;
+    double prev = 0;
+    // one device copy of the machine structure and of the batch for the whole fit: only the weights change
+    EvaluatedMachine eval = evaluate (machine, machine.funcs.combine (constants).combine (params));
+    DeviceBatch batch (eval, pairPointers (trainingSet));
+    vector<double> c (eval.nTransitions ? eval.nTransitions : 1), ll (trainingSet.seqPairs.size() ? trainingSet.seqPairs.size() : 1);
+    for (int iter = 0; true; ++iter) {
+      const Params allParams = machine.funcs.combine (constants).combine (params);
+      if (iter > 0) eval.setLogWeights (logWeights (machine, allParams));
+      mbCheck (mb_counts (eval.handle(), batch.handle(), c.data(), ll.data()));
+      MachineCounts counts (eval);
+      for (StateIndex s = 0; s < eval.nStates(); ++s) for (size_t t = 0; t < counts.count[s].size(); ++t) counts.count[s][t] = c[eval.state[s].transOffset + t];
+      counts.loglike = 0;
+      for (size_t k = 0; k < trainingSet.seqPairs.size(); ++k) counts.loglike += ll[k];
+      iterations = iter + 1;
+      logLike = counts.loglike;
+      if (onIteration) onIteration (iter + 1, counts.loglike, params);
+      if (iter > 0) {
+        if (iter == MaxEMIterations) break;
+        const double improvement = (counts.loglike - prev) / std::fabs (prev);
+        if (improvement < MinEMImprovement) break;
+      }
+      const MachineObjective objective (machine, counts, constraints, constants);
+      params = objective.optimize (params);
+      prev = counts.loglike;
+    }
+    return params;
+  }
+};
+
+// api.h:33-34
+inline Params baumWelchFit (const Machine& machine, const Constraints& constraints, const SeqPairList& data,
+                            const Params& seed = Params(), const Params& constants = Params()) {
+  MachineFitter fitter;
+  fitter.machine = machine;
+  fitter.constraints = constraints;
+  fitter.constants = constants;
+  fitter.seed = fitter.allConstraints().defaultParams().combine (seed, true);
+  return fitter.fit (data);
+}
+
+}  // namespace MachineBoss
+
+#endif

@@ -158,6 +158,18 @@ def main():
     case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
          note="config-4 style composite (S=308)")
     case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
+    # --- EM / M-step inputs of the reference's own tests (Makefile:502-504) and the dnapsw preset, as text,
+    #     for the host mirror's symbolic layer; the expected fit is the reference's golden ---
+    def rd(rel):
+        return open(os.path.join(REF, rel)).read()
+    with open(os.path.join(OUT, "aux_fit_inputs.json"), "w") as fo:
+        json.dump({"note": "inputs of test-fit-bitnoise-seqpairlist (Makefile:502-504), test-counts (518-522) and the dnapsw preset",
+                   "bitnoise_machine": rd("t/machine/bitnoise.json"), "pqcons": rd("t/io/pqcons.json"),
+                   "seqpairlist": rd("t/io/seqpairlist.json"), "params": rd("t/io/params.json"),
+                   "expect_fit_bitnoise_seqpairlist": rd("t/expect/fit-bitnoise-seqpairlist.json"),
+                   "expect_counts": rd("t/expect/counts.json"),
+                   "dnapsw_machine": rd("preset/dnapsw.json")}, fo)
+
     # --- config 5 style: an HMMER3 profile (examples/PF00516.hmm, local core machine of src/hmmer.cpp),
     #     alone and composed with an error model; large state spaces, generator machines (no input) ---
     hmm = "hmmer:" + os.path.join(REF, "examples/PF00516.hmm")

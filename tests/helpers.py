@@ -78,7 +78,9 @@ def load_golden(name: str) -> dict:
 
 
 def golden_names() -> list:
-    return sorted(f[:-5] if f.endswith(".json") else f[:-8] for f in os.listdir(GOLDEN) if f.endswith((".json", ".json.gz")))
+    # aux_* files hold auxiliary inputs (not DP cases)
+    return sorted(f[:-5] if f.endswith(".json") else f[:-8] for f in os.listdir(GOLDEN)
+                  if f.endswith((".json", ".json.gz")) and not f.startswith("aux_"))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,117 @@
+"""The host mirror's symbolic layer and EM driver (machineboss_b200/host/boss_b200_fit.h).
+
+CPU: the M-step (MachineObjective::optimize, counts.cpp:117-295) reaches the closed-form optimum
+on made-up counts.  GPU: `boss_b200 -T` reproduces the reference's fit golden
+(t/expect/fit-bitnoise-seqpairlist.json, Makefile:502-504), `-C` on a symbolic machine its
+parameter-count golden (t/expect/counts.json, Makefile:518-522), and a dnapsw fit ends at an EM
+fixed point with a higher likelihood than it started from.
+"""
+import json
+import os
+import random
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import synth_tokens, load_golden
+
+
+def _cli():
+    from machineboss_b200 import build
+    return build.build_host()
+
+
+def _inputs():
+    return load_golden("aux_fit_inputs")
+
+
+def _write(text, suffix=".json"):
+    f = tempfile.NamedTemporaryFile("w", suffix=suffix, delete=False)
+    f.write(text if isinstance(text, str) else json.dumps(text))
+    f.close()
+    return f.name
+
+
+def test_mstep_reaches_closed_form_optimum():
+    """dnapsw: every parameter's optimum is a ratio of counts; BFGS on the transformed problem finds it."""
+    fi = _inputs()
+    m = json.loads(fi["dnapsw_machine"])
+    random.seed(7)
+    counts = [[random.uniform(0.5, 20) for _ in st.get("trans", [])] for st in m["state"]]
+    out = subprocess.run([_cli(), "--machine", _write(fi["dnapsw_machine"]), "--mstep", _write(counts)],
+                         capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    # expected counts per parameter: sum over transitions of count * d log w / d log p
+    num = {}
+    den = {}
+    for st, cs in zip(m["state"], counts):
+        for t, c in zip(st.get("trans", []), cs):
+            w = t.get("weight")
+            if isinstance(w, str):
+                num[w] = num.get(w, 0) + c
+            elif isinstance(w, dict) and "not" in w:
+                den[w["not"]] = den.get(w["not"], 0) + c
+    for p in ("gapOpen", "gapExtend"):
+        assert abs(got[p] - num[p] / (num[p] + den[p])) < 2e-3
+    for group in m["cons"]["norm"]:
+        tot = sum(num[p] for p in group)
+        for p in group:
+            assert abs(got[p] - num[p] / tot) < 2e-3
+        assert abs(sum(got[p] for p in group) - 1) < 1e-5      # printed with 6 significant digits
+
+
+def test_machine_algebra_is_rejected():
+    r = subprocess.run([_cli(), "--machine", _write({"compose": [{"state": [{"id": "a"}]}, {"state": [{"id": "b"}]}]}), "--mstep", _write([[]])],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "machine algebra" in r.stderr
+
+
+@pytest.mark.gpu
+def test_fit_bitnoise_seqpairlist_matches_reference_golden():
+    fi = _inputs()
+    out = subprocess.run([_cli(), "--machine", _write(fi["bitnoise_machine"]), "-N", _write(fi["pqcons"]), "-D", _write(fi["seqpairlist"]), "-T"],
+                         capture_output=True, text=True, check=True).stdout
+    got, want = json.loads(out), json.loads(fi["expect_fit_bitnoise_seqpairlist"])
+    assert set(got) == set(want)
+    for k in want:      # the reference's harness compares after rounding to 4 significant digits (t/roundfloats.py 4)
+        assert float("%.4g" % got[k]) == float("%.4g" % want[k]), (got, want)
+
+
+@pytest.mark.gpu
+def test_param_counts_match_reference_golden():
+    fi = _inputs()
+    out = subprocess.run([_cli(), "--machine", _write(fi["bitnoise_machine"]), "-P", _write(fi["params"]), "--input-chars", "101", "--output-chars", "001", "-C"],
+                         capture_output=True, text=True, check=True).stdout
+    assert out.strip() == fi["expect_counts"].strip()
+
+
+@pytest.mark.gpu
+def test_dnapsw_fit_reaches_em_fixed_point():
+    fi = _inputs()
+    rng = np.random.default_rng(3)
+    pairs = []
+    for k in range(24):
+        x = synth_tokens(11, k, 0, 90 + k, 4)
+        y = x.copy()
+        sub = rng.random(len(y)) < 0.15
+        y[sub] = rng.integers(1, 5, sub.sum())
+        y = np.delete(y, np.where(rng.random(len(y)) < 0.03)[0])
+        pairs.append({"input": {"name": "x%d" % k, "sequence": ["ACGT"[t - 1] for t in x]},
+                      "output": {"name": "y%d" % k, "sequence": ["ACGT"[t - 1] for t in y]}})
+    mf, df = _write(fi["dnapsw_machine"]), _write(pairs)
+    cli = _cli()
+    fit = json.loads(subprocess.run([cli, "--machine", mf, "-D", df, "-T"], capture_output=True, text=True, check=True).stdout)
+    assert fit["subAA"] > 0.6 and fit["subCC"] > 0.6 and fit["gapOpen"] < 0.2       # the data are 85 % identical
+    pf = _write(fit)
+    ll0 = sum(r[2] for r in json.loads(subprocess.run([cli, "--machine", mf, "-U", "-D", df, "-L"], capture_output=True, text=True, check=True).stdout))
+    ll1 = sum(r[2] for r in json.loads(subprocess.run([cli, "--machine", mf, "-P", pf, "-D", df, "-L"], capture_output=True, text=True, check=True).stdout))
+    assert ll1 > ll0 + 100
+    # fixed point: the parameter counts at the fitted parameters, normalised per constraint, give the parameters back
+    pc = json.loads(subprocess.run([cli, "--machine", mf, "-P", pf, "-D", df, "-C"], capture_output=True, text=True, check=True).stdout)
+    m = json.loads(fi["dnapsw_machine"])
+    for group in m["cons"]["norm"]:
+        tot = sum(pc[p] for p in group)
+        for p in group:
+            assert abs(pc[p] / tot - fit[p]) < 0.02, (p, pc[p] / tot, fit[p])
