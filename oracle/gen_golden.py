@@ -60,11 +60,17 @@ def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backw
             x = synth_tokens(seed, k, 0, li if in_alpha else 0, max(1, len(in_alpha)))
             y = synth_tokens(seed, k, 1, lo if out_alpha else 0, max(1, len(out_alpha)))
             sym_pairs.append(([in_alpha[t - 1] for t in x], [out_alpha[t - 1] for t in y]))
+    elif pairs and isinstance(pairs[0], dict):      # raw SeqPair JSON carrying an "alignment" (=> path envelope)
+        raw_pairs = pairs
+        sym_pairs = [([c[0] for c in p["alignment"] if c[0]], [c[1] for c in p["alignment"] if c[1]]) for p in pairs]
     else:
         sym_pairs = [(list(a), list(b)) for a, b in pairs]
     f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
-    json.dump([{"input": {"name": "x%d" % k, "sequence": a}, "output": {"name": "y%d" % k, "sequence": b}}
-               for k, (a, b) in enumerate(sym_pairs)], f)
+    if pairs and isinstance(pairs[0], dict):
+        json.dump(raw_pairs, f)
+    else:
+        json.dump([{"input": {"name": "x%d" % k, "sequence": a}, "output": {"name": "y%d" % k, "sequence": b}}
+                   for k, (a, b) in enumerate(sym_pairs)], f)
     f.close()
     if matrices:
         do = do + ",matrices"
@@ -158,6 +164,30 @@ def main():
     case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
          note="config-4 style composite (S=308)")
     case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
+    # --- path envelopes: pairs that carry an alignment get Envelope::initPath (seqpair.cpp:104-110,134-152) ---
+    import random
+    random.seed(5)
+
+    def aligned_pair(n, name):
+        cols = []
+        for _ in range(n):
+            r = random.random()
+            a, b = random.choice("ACGT"), random.choice("ACGT")
+            cols.append([a, a] if r < 0.6 else [a, b] if r < 0.8 else [a, ""] if r < 0.9 else ["", b])
+        return {"input": {"name": name + "x"}, "output": {"name": name + "y"}, "alignment": cols}
+    case("dnapsw_path_envelope", ["preset:dnapsw"], [aligned_pair(12, "a"), aligned_pair(40, "b"), aligned_pair(1, "c"),
+                                                     {"input": {"name": "dx"}, "output": {"name": "dy"}, "alignment": [["A", ""], ["", "C"], ["G", "G"]]}],
+         params=peaked, matrices=True, note="pairs with an alignment: every matrix is restricted to the path envelope")
+    env_expect = {}
+    for nm in ("tinypath_full", "tinypath_path", "smallpath_path", "smallpath_area0", "smallpath_area1", "smallpath_area2",
+               "smallpath_area3", "smallpath_area4", "asympath_area0", "asympath_area1"):
+        env_expect[nm] = json.load(open(os.path.join(REF, "t/expect/%s_env.json" % nm)))
+    with open(os.path.join(OUT, "aux_envelopes.json"), "w") as fo:
+        json.dump({"note": "Makefile:450-462 test-env: inputs t/io/{tinypath,smallpath,asympath}.json and the expected envelopes",
+                   "tinypath": json.load(open(os.path.join(REF, "t/io/tinypath.json"))),
+                   "smallpath": json.load(open(os.path.join(REF, "t/io/smallpath.json"))),
+                   "asympath": json.load(open(os.path.join(REF, "t/io/asympath.json"))), "expect": env_expect}, fo)
+
     # --- EM / M-step inputs of the reference's own tests (Makefile:502-504) and the dnapsw preset, as text,
     #     for the host mirror's symbolic layer; the expected fit is the reference's golden ---
     def rd(rel):

@@ -122,10 +122,25 @@ static void index_build (trans_index* ix, const mbo_machine* m, int incoming) {
 
 static void index_free (trans_index* ix) { free (ix->off); free (ix->other); free (ix->id); free (ix->lw); }
 
+/* ---- envelope (seqpair.h:75-113); NULL = full ---- */
+static __thread const int64_t* env_start = NULL;
+static __thread const int64_t* env_end = NULL;
+void mbo_set_envelope (const int64_t* envStart, const int64_t* envEnd) { env_start = envStart; env_end = envEnd; }
+static inline int env_contains (int64_t i, int64_t o) { return !env_start || (i >= env_start[o] && i < env_end[o]); }
+
 /* ---- storage: full [o][i][s] or two rolling output rows (dpmatrix.h:35-58) ---- */
-typedef struct { double* c; int64_t Li; int S; int rolling; } cells;
+typedef struct { double* c; int64_t Li; int S; int rolling; const double* ninf; } cells;
 static inline double* cellp (const cells* m, int64_t i, int64_t o) {
   return m->c + ((m->rolling ? (o & 1) : o) * (m->Li + 1) + i) * m->S;
+}
+/* const read access: -inf outside the envelope (dpmatrix.h:142-144) */
+static inline const double* cellr (const cells* m, int64_t i, int64_t o) {
+  return env_contains (i, o) ? cellp (m, i, o) : m->ninf;
+}
+static double* make_ninf (int S) {
+  double* v = (double*) malloc (sizeof (double) * (size_t) (S ? S : 1));
+  for (int s = 0; s < S; ++s) v[s] = -INFINITY;
+  return v;
 }
 
 /* ================= Forward (forward.defs.h:22-55) ================= */
@@ -134,13 +149,15 @@ double mbo_forward (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
   lse_init();
   trans_index ix; index_build (&ix, m, 1);
   const int S = m->nStates;
-  cells M = { matrix, Li, S, matrix == NULL };
+  double* ninf = make_ninf (S);
+  cells M = { matrix, Li, S, matrix == NULL, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * 2 * (size_t) (Li + 1) * S);
   for (int64_t o = 0; o <= Lo; ++o) {
     const int outTok = o ? y[o - 1] : 0;
     for (int64_t i = 0; i <= Li; ++i) {
       const int inTok = i ? x[i - 1] : 0;
       double* cur = cellp (&M, i, o);
+      if (!env_contains (i, o)) { for (int d = 0; d < S; ++d) cur[d] = -INFINITY; continue; }   /* storage stays -inf (dpmatrix.defs.h:36) */
       for (int d = 0; d < S; ++d) {
         double ll = (i || o || d != 0) ? -INFINITY : 0;
 #define ACC(IN, OUT, SRC)                                                           \
@@ -148,17 +165,18 @@ double mbo_forward (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
              const double* s_ = (SRC);                                              \
              for (int64_t p = ix.off[k_]; p < ix.off[k_ + 1]; ++p)                  \
                ll = lse2 (ll, s_[ix.other[p]] + ix.lw[p], mode); } while (0)
-        if (i && o) ACC (inTok, outTok, cellp (&M, i - 1, o - 1));
-        if (i) ACC (inTok, 0, cellp (&M, i - 1, o));
-        if (o) ACC (0, outTok, cellp (&M, i, o - 1));
+        if (i && o) ACC (inTok, outTok, cellr (&M, i - 1, o - 1));
+        if (i) ACC (inTok, 0, cellr (&M, i - 1, o));
+        if (o) ACC (0, outTok, cellr (&M, i, o - 1));
         ACC (0, 0, cur);
 #undef ACC
         cur[d] = ll;
       }
     }
   }
-  const double result = cellp (&M, Li, Lo)[S - 1];
+  const double result = cellr (&M, Li, Lo)[S - 1];
   if (!matrix) free (M.c);
+  free (ninf);
   index_free (&ix);
   return result;
 }
@@ -169,7 +187,8 @@ double mbo_backward (const mbo_machine* m, const uint8_t* x, int64_t Li, const u
   lse_init();
   trans_index ix; index_build (&ix, m, 0);
   const int S = m->nStates;
-  cells M = { matrix, Li, S, matrix == NULL };
+  double* ninf = make_ninf (S);
+  cells M = { matrix, Li, S, matrix == NULL, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * 2 * (size_t) (Li + 1) * S);
   for (int64_t o = Lo; o >= 0; --o) {
     const int endO = (o == Lo);
@@ -178,6 +197,7 @@ double mbo_backward (const mbo_machine* m, const uint8_t* x, int64_t Li, const u
       const int endI = (i == Li);
       const int inTok = endI ? 0 : x[i];
       double* cur = cellp (&M, i, o);
+      if (!env_contains (i, o)) { for (int s = 0; s < S; ++s) cur[s] = -INFINITY; continue; }
       for (int s = S - 1; s >= 0; --s) {
         double ll = (endI && endO && s == S - 1) ? 0 : -INFINITY;
 #define ACC(IN, OUT, DST)                                                           \
@@ -185,17 +205,18 @@ double mbo_backward (const mbo_machine* m, const uint8_t* x, int64_t Li, const u
              const double* d_ = (DST);                                              \
              for (int64_t p = ix.off[k_]; p < ix.off[k_ + 1]; ++p)                  \
                ll = lse2 (ll, d_[ix.other[p]] + ix.lw[p], mode); } while (0)
-        if (!endI && !endO) ACC (inTok, outTok, cellp (&M, i + 1, o + 1));
-        if (!endI) ACC (inTok, 0, cellp (&M, i + 1, o));
-        if (!endO) ACC (0, outTok, cellp (&M, i, o + 1));
+        if (!endI && !endO) ACC (inTok, outTok, cellr (&M, i + 1, o + 1));
+        if (!endI) ACC (inTok, 0, cellr (&M, i + 1, o));
+        if (!endO) ACC (0, outTok, cellr (&M, i, o + 1));
         ACC (0, 0, cur);
 #undef ACC
         cur[s] = ll;
       }
     }
   }
-  const double result = cellp (&M, 0, 0)[0];
+  const double result = cellr (&M, 0, 0)[0];
   if (!matrix) free (M.c);
+  free (ninf);
   index_free (&ix);
   return result;
 }
@@ -206,13 +227,15 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
   trans_index ix; index_build (&ix, m, 1);
   const int S = m->nStates;
   const int needFull = (matrix != NULL) || (path != NULL);
-  cells M = { matrix, Li, S, !needFull };
+  double* ninf = make_ninf (S);
+  cells M = { matrix, Li, S, !needFull, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * (size_t) (needFull ? Lo + 1 : 2) * (size_t) (Li + 1) * S);
   for (int64_t o = 0; o <= Lo; ++o) {
     const int outTok = o ? y[o - 1] : 0;
     for (int64_t i = 0; i <= Li; ++i) {
       const int inTok = i ? x[i - 1] : 0;
       double* cur = cellp (&M, i, o);
+      if (!env_contains (i, o)) { for (int d = 0; d < S; ++d) cur[d] = -INFINITY; continue; }
       for (int d = 0; d < S; ++d) {
         double ll = (i || o || d) ? -INFINITY : 0;
 #define ACC(IN, OUT, SRC)                                                           \
@@ -221,16 +244,16 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
              for (int64_t p = ix.off[k_]; p < ix.off[k_ + 1]; ++p) {                \
                const double t_ = s_[ix.other[p]] + ix.lw[p];                        \
                ll = ll < t_ ? t_ : ll; } } while (0)      /* std::max (dpmatrix.h:122) */
-        if (i && o) ACC (inTok, outTok, cellp (&M, i - 1, o - 1));
-        if (i) ACC (inTok, 0, cellp (&M, i - 1, o));
-        if (o) ACC (0, outTok, cellp (&M, i, o - 1));
+        if (i && o) ACC (inTok, outTok, cellr (&M, i - 1, o - 1));
+        if (i) ACC (inTok, 0, cellr (&M, i - 1, o));
+        if (o) ACC (0, outTok, cellr (&M, i, o - 1));
         ACC (0, 0, cur);
 #undef ACC
         cur[d] = ll;
       }
     }
   }
-  const double score = cellp (&M, Li, Lo)[S - 1];
+  const double score = cellr (&M, Li, Lo)[S - 1];
   double result = score;
   if (path) {
     int64_t n = 0;
@@ -248,10 +271,10 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
              for (int64_t p = ix.off[k_]; p < ix.off[k_ + 1]; ++p) {                \
                const double t_ = s_[ix.other[p]] + ix.lw[p];                        \
                if (!haveBest || best < t_) { best = t_; haveBest = 1; bestP = p; bestType = (TYPE); } } } while (0)
-        if (i && o) CAND (inTok, outTok, cellp (&M, i - 1, o - 1), 0);
-        if (i) CAND (inTok, 0, cellp (&M, i - 1, o), 1);
-        if (o) CAND (0, outTok, cellp (&M, i, o - 1), 2);
-        CAND (0, 0, cellp (&M, i, o), 3);
+        if (i && o) CAND (inTok, outTok, cellr (&M, i - 1, o - 1), 0);
+        if (i) CAND (inTok, 0, cellr (&M, i - 1, o), 1);
+        if (o) CAND (0, outTok, cellr (&M, i, o - 1), 2);
+        CAND (0, 0, cellr (&M, i, o), 3);
 #undef CAND
         if (!haveBest || n >= pathCap) { result = NAN; break; }
         path[n++] = ix.id[bestP];
@@ -265,6 +288,7 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
     if (pathLen) *pathLen = n;
   }
   if (!matrix) free (M.c);
+  free (ninf);
   index_free (&ix);
   return result;
 }
@@ -280,13 +304,15 @@ double mbo_counts (const mbo_machine* m, const uint8_t* x, int64_t Li, const uin
   const double ll = mbo_backward (m, x, Li, y, Lo, mode, B);   /* getCounts uses backward.logLike() (backward.cpp:66) */
   if (backLL) *backLL = ll;
   trans_index ix; index_build (&ix, m, 0);
-  cells MF = { F, Li, S, 0 }, MB = { B, Li, S, 0 };
+  double* ninf = make_ninf (S);
+  cells MF = { F, Li, S, 0, ninf }, MB = { B, Li, S, 0, ninf };
   for (int64_t o = Lo; o >= 0; --o) {
     const int endO = (o == Lo);
     const int outTok = endO ? 0 : y[o];
     for (int64_t i = Li; i >= 0; --i) {
       const int endI = (i == Li);
       const int inTok = endI ? 0 : x[i];
+      if (!env_contains (i, o)) continue;   /* getCounts walks the envelope's cells only (backward.cpp:70) */
       for (int s = S - 1; s >= 0; --s) {
         const double logOdds = cellp (&MF, i, o)[s] - ll;
 #define CNT(IN, OUT, DST)                                                           \
@@ -294,16 +320,16 @@ double mbo_counts (const mbo_machine* m, const uint8_t* x, int64_t Li, const uin
              const double* d_ = (DST);                                              \
              for (int64_t p = ix.off[k_]; p < ix.off[k_ + 1]; ++p)                  \
                counts[ix.id[p]] += exp (logOdds + (d_[ix.other[p]] + ix.lw[p])); } while (0)
-        if (!endI && !endO) CNT (inTok, outTok, cellp (&MB, i + 1, o + 1));
-        if (!endI) CNT (inTok, 0, cellp (&MB, i + 1, o));
-        if (!endO) CNT (0, outTok, cellp (&MB, i, o + 1));
-        CNT (0, 0, cellp (&MB, i, o));
+        if (!endI && !endO) CNT (inTok, outTok, cellr (&MB, i + 1, o + 1));
+        if (!endI) CNT (inTok, 0, cellr (&MB, i + 1, o));
+        if (!endO) CNT (0, outTok, cellr (&MB, i, o + 1));
+        CNT (0, 0, cellr (&MB, i, o));
 #undef CNT
       }
     }
   }
   index_free (&ix);
-  free (F); free (B);
+  free (F); free (B); free (ninf);
   return fll;
 }
 

@@ -57,6 +57,12 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
 double mbo_counts (const mbo_machine* m, const uint8_t* x, int64_t Li, const uint8_t* y, int64_t Lo,
                    int lse_mode, double* counts, double* backLL);
 
+/* Envelope (src/seqpair.h:75-113): cells of output row o exist only for inStart[o] <= inPos < inEnd[o];
+ * reads outside return -inf (dpmatrix.h:142-144) and the fills only visit cells inside
+ * (forward.defs.h:30, backward.cpp:26, viterbi.cpp:24).  Call with envStart == NULL for the full
+ * matrix.  Sets the envelope used by all subsequent mbo_* calls on this thread. */
+void mbo_set_envelope (const int64_t* envStart, const int64_t* envEnd);
+
 /* Synthetic tokens (oracle/synth.h). */
 void mbo_synth (uint64_t seed, uint64_t pairIndex, int which, int64_t len, int nSym, uint8_t* tokens);
 

@@ -240,6 +240,11 @@ int main (int argc, char** argv) {
           for (size_t n = 0; n < r.path.size(); ++n) cout << (n ? "," : "") << r.path[n];
           cout << "]";
         }
+        if (pairs[k].alignment.size()) {   // the path envelope every matrix of this pair was given (seqpair.cpp:104-110)
+          const Envelope env (pairs[k]);
+          cout << ",\"env\":";
+          env.writeJson (cout);
+        }
         cout << r.matrices << "}";
       }
       cout << "\n ]";

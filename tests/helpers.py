@@ -139,6 +139,8 @@ def oracle_lib():
         lib.mbo_counts.argtypes = [P, U8, I64, U8, I64, ctypes.c_int, P, P]
         lib.mbo_synth.restype = None
         lib.mbo_synth.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, I64, ctypes.c_int, P]
+        lib.mbo_set_envelope.restype = None
+        lib.mbo_set_envelope.argtypes = [P, P]
         lib.mbo_log_sum_exp.restype = D
         lib.mbo_log_sum_exp.argtypes = [D, D, ctypes.c_int]
         _oracle = lib
@@ -156,6 +158,16 @@ class Oracle:
         self.lib = oracle_lib()
         self._keep = [np.ascontiguousarray(a) for a in (m.src, m.dst, m.tin, m.tout, m.lw)]
         self.c = _MboMachine(m.n_states, m.n_in, m.n_out, m.n_trans, *[a.ctypes.data for a in self._keep])
+
+    def set_envelope(self, env=None):
+        """env: list of [inStart, inEnd) per output row (Lo+1 rows), or None for the full matrix."""
+        if env is None:
+            self._env = None
+            self.lib.mbo_set_envelope(None, None)
+        else:
+            a = np.ascontiguousarray(np.array(env, dtype=np.int64))
+            self._env = (np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]))
+            self.lib.mbo_set_envelope(self._env[0].ctypes.data, self._env[1].ctypes.data)
 
     @staticmethod
     def _tok(a):

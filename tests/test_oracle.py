@@ -27,6 +27,7 @@ def test_oracle_bit_identical_to_reference_binary(name):
     orc = Oracle(m)
     counts = np.zeros(m.n_trans)
     for (x, y), p in zip(pairs_from_golden(case), case["pairs"]):
+        orc.set_envelope(p.get("env"))
         if "rolling" in p:
             assert _same(orc.forward(x, y), gnum(p["rolling"]))
         if "forward" in p:
@@ -47,6 +48,7 @@ def test_oracle_bit_identical_to_reference_binary(name):
                 assert np.array_equal(mine, ref)
         if case["counts"] is not None:
             orc.counts(x, y, counts=counts)
+    orc.set_envelope(None)
     if case["counts"] is not None:
         ref = np.array([gnum(v) for v in case["counts"]])
         # same per-pair arithmetic; summation over pairs is in list order on both sides
