@@ -52,17 +52,27 @@ void mb_machine_destroy (mb_machine* m);
 
 #define MB_ENGINE_GENERIC 0   /* anti-diagonal wavefront over the CSR machine, any size */
 #define MB_ENGINE_JIT     1   /* machine-specialised strip kernel compiled with NVRTC, small machines */
+#define MB_ENGINE_WIDE    2   /* warp-per-column strip kernel over shared-memory transition tables: Forward and Viterbi
+                                 of mid-size and large machines (Backward and counts run on the generic engine) */
 /* Force an engine for machines created afterwards (-1 = choose automatically, the default). */
 int mb_set_engine (int engine);
 
 /* ---- SeqPairList (src/seqpair.h:18-73,115-121), already tokenised (DPMatrix ctor, dpmatrix.defs.h:6-7) ----
  * Pair k has input tokens inTokens[inOff[k] .. inOff[k+1]) and output tokens
  * outTokens[outOff[k] .. outOff[k+1]).  Tokens are 1-based (0 never appears in data).  The batch is
- * copied to the device; full envelopes only (SeqPair without an alignment, seqpair.cpp:104-110). */
+ * copied to the device with full envelopes (a SeqPair without an alignment, seqpair.cpp:104-110). */
 int mb_batch_create (mb_batch** out, int64_t nPairs,
                      const uint8_t* inTokens, const int64_t* inOff,
                      const uint8_t* outTokens, const int64_t* outOff);
 void mb_batch_destroy (mb_batch* b);
+/* ---- Envelope (src/seqpair.h:75-113, seqpair.cpp:104-152; DPMatrix cell access dpmatrix.h:128-146) ----
+ * Restricts pair k's matrices to inStart[r] <= inPos < inEnd[r] on output row o, r = rowOff[k] + o.
+ * A pair has either outLen+1 rows or none (rowOff[k+1] == rowOff[k]: the full matrix).  This is what
+ * the reference does to every matrix of a SeqPair that carries an alignment (Envelope::initPath).
+ * Fails like DPMatrix::alloc (dpmatrix.defs.h:31-32) if an envelope does not fit its pair or is
+ * not connected.  rowOff == NULL removes all envelopes.  Batches with envelopes run on the
+ * wide (Forward, Viterbi) and generic (Backward, counts) engines. */
+int mb_batch_set_envelopes (mb_batch* b, const int64_t* rowOff, const int64_t* inStart, const int64_t* inEnd);
 /* Gives the scratch the engine keeps attached to the batch between calls (back-pointers, stored
  * Forward values, strip boundaries) back to the device; results already fetched stay valid. */
 int mb_batch_trim (mb_batch* b);

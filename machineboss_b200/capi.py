@@ -13,14 +13,14 @@ import numpy as np
 
 from . import build as _build
 
-ENGINE_GENERIC, ENGINE_JIT = 0, 1
+ENGINE_GENERIC, ENGINE_JIT, ENGINE_WIDE = 0, 1, 2
 
 _lib = None
 
 # every symbol include/machineboss_b200.h declares
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
-           "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_forward", "mb_backward", "mb_viterbi",
+           "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
            "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
 
 
@@ -49,6 +49,7 @@ def lib():
         L.mb_batch_destroy.argtypes = [P]
         L.mb_batch_destroy.restype = None
         L.mb_batch_trim.argtypes = [P]
+        L.mb_batch_set_envelopes.argtypes = [P, P, P, P]
         L.mb_forward.argtypes = [P, P, P]
         L.mb_backward.argtypes = [P, P, P]
         L.mb_viterbi.argtypes = [P, P, P, P]
@@ -147,6 +148,20 @@ class Batch:
         self.h = ctypes.c_void_p()
         _check(lib().mb_batch_create(ctypes.byref(self.h), self.n_pairs, _ptr(self.x), _ptr(self.x_off),
                                      _ptr(self.y), _ptr(self.y_off)))
+
+    def set_envelopes(self, envs) -> None:
+        """envs: per pair None (full matrix) or a list of [inStart, inEnd) per output row (Lo+1 rows);
+        envs=None removes all envelopes (Envelope, src/seqpair.h:75-113)."""
+        if envs is None:
+            _check(lib().mb_batch_set_envelopes(self.h, None, None, None))
+            return
+        assert len(envs) == self.n_pairs
+        rows = [np.asarray(e, dtype=np.int64).reshape(-1, 2) if e is not None else np.zeros((0, 2), np.int64) for e in envs]
+        off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+        allr = np.concatenate(rows) if rows else np.zeros((0, 2), np.int64)
+        st = np.ascontiguousarray(allr[:, 0]) if len(allr) else np.zeros(1, np.int64)
+        en = np.ascontiguousarray(allr[:, 1]) if len(allr) else np.zeros(1, np.int64)
+        _check(lib().mb_batch_set_envelopes(self.h, off.ctypes.data, st.ctypes.data, en.ctypes.data))
 
     def cell_states(self, n_states: int) -> float:
         li = np.diff(self.x_off).astype(np.float64)

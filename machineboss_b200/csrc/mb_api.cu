@@ -224,7 +224,7 @@ int mb_set_device (int device) {
 }
 
 int mb_set_engine (int engine) {
-  if (engine < -1 || engine > MB_ENGINE_JIT) { set_error ("mb_set_engine: unknown engine"); return 1; }
+  if (engine < -1 || engine > MB_ENGINE_WIDE) { set_error ("mb_set_engine: unknown engine"); return 1; }
   g_forceEngine = engine;
   return 0;
 }
@@ -262,6 +262,10 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
     if (!jit_supported (m, &why)) { set_error ("mb_set_engine(JIT): " + why); mb_machine_destroy (m); return 1; }
     if (jit_prepare (m)) { mb_machine_destroy (m); return 1; }
     m->engine = MB_ENGINE_JIT;
+  } else if (g_forceEngine == MB_ENGINE_WIDE || (g_forceEngine < 0 && wide_supported (m, &why))) {
+    if (!wide_supported (m, &why)) { set_error ("mb_set_engine(WIDE): " + why); mb_machine_destroy (m); return 1; }
+    if (wide_prepare (m)) { mb_machine_destroy (m); return 1; }
+    m->engine = MB_ENGINE_WIDE;
   }
   *out = m;
   return 0;
@@ -276,6 +280,7 @@ int mb_machine_update_weights (mb_machine* m, const double* logWeight) {
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
   }
+  if (m->wide && wide_update_weights (m)) return 1;
   if (m->engine == MB_ENGINE_JIT) return jit_update_weights (m);
   return 0;
 }
@@ -292,6 +297,7 @@ void mb_machine_destroy (mb_machine* m) {
   if (!m) return;
   cudaSetDevice (m->device);
   jit_destroy (m);
+  wide_destroy (m);
   if (m->dBlob) cudaFree (m->dBlob);
   delete m;
 }
@@ -327,14 +333,58 @@ int mb_batch_create (mb_batch** out, int64_t nPairs, const uint8_t* inTokens, co
       || !cuda_ok (cudaMemcpyAsync (b->dYOff, b->yOff.data(), (size_t) (nPairs + 1) * 8, cudaMemcpyHostToDevice, b->stream), "H2D offsets"))
     return fail();
   if (!cuda_ok (cudaStreamSynchronize (b->stream), "sync")) return fail();
-  b->dev = { nPairs, b->dX, b->dXOff, b->dY, b->dYOff };
+  b->dev = { nPairs, b->dX, b->dXOff, b->dY, b->dYOff, nullptr, nullptr, nullptr };
   *out = b;
+  return 0;
+}
+
+int mb_batch_set_envelopes (mb_batch* b, const int64_t* rowOff, const int64_t* inStart, const int64_t* inEnd) {
+  if (!b) { set_error ("null batch"); return 1; }
+  MB_CUDA (cudaSetDevice (b->device));
+  if (b->dEnv) { cudaFree (b->dEnv); b->dEnv = nullptr; }
+  b->hasEnv = false;
+  b->envOff.clear(); b->envStart.clear(); b->envEnd.clear();
+  b->dev.envOff = b->dev.envStart = b->dev.envEnd = nullptr;
+  if (!rowOff) return 0;
+  const int64_t n = b->nPairs, r0 = rowOff[0];
+  bool any = false;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t rows = rowOff[k + 1] - rowOff[k];
+    const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
+    if (rows == 0) continue;
+    any = true;
+    // DPMatrix::alloc asserts env.fits(seqPair) and env.connected() (dpmatrix.defs.h:31-32, seqpair.cpp:170-180)
+    if (rows != Lo + 1) { set_error ("Envelope/sequence mismatch: pair " + std::to_string (k) + " has " + std::to_string (rows) + " envelope rows for output length " + std::to_string (Lo)); return 1; }
+    const int64_t* s = inStart + rowOff[k];
+    const int64_t* e = inEnd + rowOff[k];
+    auto overlapping = [] (int64_t s1, int64_t e1, int64_t s2, int64_t e2) { return !(s1 >= e2 || s2 >= e1); };   // seqpair.h:89-93
+    bool conn = overlapping (s[0], e[0], 0, 1);
+    for (int64_t y = 0; y <= Lo; ++y) {
+      if (s[y] < 0 || e[y] > Li + 1 || s[y] > e[y]) { set_error ("Envelope/sequence mismatch: pair " + std::to_string (k) + " row " + std::to_string (y) + " is outside the input"); return 1; }
+      if (y) conn = conn && overlapping (s[y - 1], e[y - 1] + 1, s[y], e[y]);
+    }
+    conn = conn && overlapping (s[Lo], e[Lo], Li, Li + 1);
+    if (!conn) { set_error ("Envelope is not connected: pair " + std::to_string (k)); return 1; }
+  }
+  if (!any) return 0;
+  const int64_t R = rowOff[n] - r0;
+  b->envOff.assign (rowOff, rowOff + n + 1);
+  for (auto& v: b->envOff) v -= r0;
+  b->envStart.assign (inStart + r0, inStart + r0 + R);
+  b->envEnd.assign (inEnd + r0, inEnd + r0 + R);
+  MB_CUDA (cudaMalloc (&b->dEnv, (size_t) (n + 1 + 2 * R) * 8));
+  MB_CUDA (cudaMemcpy (b->dEnv, b->envOff.data(), (size_t) (n + 1) * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (b->dEnv + n + 1, b->envStart.data(), (size_t) R * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (b->dEnv + n + 1 + R, b->envEnd.data(), (size_t) R * 8, cudaMemcpyHostToDevice));
+  b->dev.envOff = b->dEnv; b->dev.envStart = b->dEnv + n + 1; b->dev.envEnd = b->dEnv + n + 1 + R;
+  b->hasEnv = true;
   return 0;
 }
 
 void mb_batch_destroy (mb_batch* b) {
   if (!b) return;
   cudaSetDevice (b->device);
+  if (b->dEnv) cudaFree (b->dEnv);
   if (b->dX) cudaFree (b->dX);
   if (b->dY) cudaFree (b->dY);
   if (b->dXOff) cudaFree (b->dXOff);
@@ -362,19 +412,35 @@ static int check_call (const mb_machine* m, const mb_batch* b) {
   return 0;
 }
 
+// The strip kernels sweep full matrices; a batch carrying envelopes runs on the generic engine.
+static bool use_jit (const mb_machine* m, const mb_batch* b) { return m->engine == MB_ENGINE_JIT && !b->hasEnv; }
+// 1: the wide engine takes the call, 0: the generic engine does, -1: error
+static int use_wide (mb_machine* m, const mb_batch* b) {
+  if (m->engine == MB_ENGINE_WIDE) return 1;
+  if (m->engine == MB_ENGINE_JIT && b->hasEnv && wide_supported (m, nullptr)) {
+    if (!m->wide && wide_prepare (m)) return -1;
+    return 1;
+  }
+  return 0;
+}
+
 int mb_forward (mb_machine* m, mb_batch* b, double* loglike) {
   if (check_call (m, b)) return 1;
-  return m->engine == MB_ENGINE_JIT ? jit_forward (m, b, loglike, false) : generic_forward (m, b, loglike, false);
+  if (use_jit (m, b)) return jit_forward (m, b, loglike, false);
+  const int w = use_wide (m, b);
+  return w < 0 ? 1 : w ? wide_forward (m, b, loglike) : generic_forward (m, b, loglike, false);
 }
 
 int mb_backward (mb_machine* m, mb_batch* b, double* loglike) {
   if (check_call (m, b)) return 1;
-  return m->engine == MB_ENGINE_JIT ? jit_forward (m, b, loglike, true) : generic_forward (m, b, loglike, true);
+  return use_jit (m, b) ? jit_forward (m, b, loglike, true) : generic_forward (m, b, loglike, true);
 }
 
 int mb_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (check_call (m, b)) return 1;
-  return m->engine == MB_ENGINE_JIT ? jit_viterbi (m, b, score, pathLen) : generic_viterbi (m, b, score, pathLen);
+  if (use_jit (m, b)) return jit_viterbi (m, b, score, pathLen);
+  const int w = use_wide (m, b);
+  return w < 0 ? 1 : w ? wide_viterbi (m, b, score, pathLen) : generic_viterbi (m, b, score, pathLen);
 }
 
 int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff) {
@@ -400,7 +466,7 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff) {
 
 int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
   if (check_call (m, b)) return 1;
-  return m->engine == MB_ENGINE_JIT ? jit_counts (m, b, counts, loglike) : generic_counts (m, b, counts, loglike);
+  return use_jit (m, b) ? jit_counts (m, b, counts, loglike) : generic_counts (m, b, counts, loglike);
 }
 
 int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,

@@ -47,6 +47,17 @@ struct Cells {
   }
 };
 
+// Envelope of one pair (null rows = full matrix).
+struct Env {
+  const int64_t* start;
+  const int64_t* end;
+  __device__ __forceinline__ bool contains (int64_t i, int64_t o) const { return !start || (i >= start[o] && i < end[o]); }
+};
+__device__ __forceinline__ Env pair_env (const DevBatch& b, int64_t k) {
+  if (!b.envOff || b.envOff[k + 1] == b.envOff[k]) return Env { nullptr, nullptr };
+  return Env { b.envStart + b.envOff[k], b.envEnd + b.envOff[k] };
+}
+
 template<int OP>
 __device__ __forceinline__ double accumulate (double acc, const DevCsr& c, int64_t key, const double* cell) {
   for (int64_t p = c.off[key], e = c.off[key + 1]; p < e; ++p) {
@@ -72,6 +83,7 @@ __global__ void __launch_bounds__(256) fill_kernel (DevMachine m, DevBatch b, co
   const int32_t* levelStates = BACKWARD ? m.bwdLevelStates : m.fwdLevelStates;
   const DevCsr& csr = BACKWARD ? m.out : m.inc;
   const double ninf = neg_inf();
+  const Env env = pair_env (b, k);
 
   for (int64_t step = 0; step <= Li + Lo; ++step) {
     const int64_t d = BACKWARD ? Li + Lo - step : step;
@@ -84,6 +96,8 @@ __global__ void __launch_bounds__(256) fill_kernel (DevMachine m, DevBatch b, co
         const int s = levelStates[l0 + (int) (item % ns)];
         double* cur = C.at (i, o);
         double acc;
+        // cells outside the envelope are never filled and read as -inf (dpmatrix.h:142-144, dpmatrix.defs.h:36)
+        if (!env.contains (i, o)) { cur[s] = ninf; continue; }
         if (!BACKWARD) {
           // forward.defs.h:36-45 / viterbi.cpp:30-39
           const int a = i ? x[i - 1] : 0, c = o ? y[o - 1] : 0;
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(256) fill_kernel (DevMachine m, DevBatch b, co
     }
   }
   if (threadIdx.x == 0)
-    result[k] = BACKWARD ? C.at (0, 0)[0] : C.at (Li, Lo)[S - 1];
+    result[k] = BACKWARD ? (env.contains (0, 0) ? C.at (0, 0)[0] : ninf) : (env.contains (Li, Lo) ? C.at (Li, Lo)[S - 1] : ninf);
 }
 
 // DPMatrix::traceBack (dpmatrix.defs.h:82-110) over a stored Viterbi matrix, one thread per pair.
@@ -177,6 +191,7 @@ __global__ void __launch_bounds__(256) counts_kernel (DevMachine m, DevBatch b, 
   const int S = m.S;
   const Cells F = { const_cast<double*> (wsF) + wsOff[blockIdx.x], Li, S, 0 }, B = { const_cast<double*> (wsB) + wsOff[blockIdx.x], Li, S, 0 };
   const int64_t nKeys = (int64_t) S * m.nIn1 * m.nOut1;
+  const Env env = pair_env (b, k);
   for (int64_t key = 0; key < nKeys; ++key) {
     const int64_t p0 = m.out.off[key], p1 = m.out.off[key + 1];
     if (p0 == p1) continue;
@@ -190,6 +205,7 @@ __global__ void __launch_bounds__(256) counts_kernel (DevMachine m, DevBatch b, 
       for (int64_t cell = threadIdx.x; cell < ni * no; cell += blockDim.x) {
         const int64_t i = cell % ni, o = cell / ni;
         if ((a && x[i] != a) || (c && y[o] != c)) continue;
+        if (!env.contains (i, o)) continue;   // getCounts walks the envelope's cells (backward.cpp:70); outside reads are -inf
         sum += exp ((F.at (i, o)[s] - ll) + (B.at (i + di, o + dO)[dest] + lw));
       }
       red[threadIdx.x] = sum;

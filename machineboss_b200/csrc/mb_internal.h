@@ -47,6 +47,11 @@ struct DevBatch {
   const int64_t* xOff;
   const uint8_t* y;
   const int64_t* yOff;
+  // envelopes (src/seqpair.h:75-113): pair k's output row o keeps inPos in [envStart[r], envEnd[r]),
+  // r = envOff[k] + o; envOff[k+1] == envOff[k] means the full matrix.  All null without envelopes.
+  const int64_t* envOff;
+  const int64_t* envStart;
+  const int64_t* envEnd;
 };
 
 struct HostCsr {
@@ -81,6 +86,8 @@ struct mb_machine {
 
   // jit engine (mb_jit.cu)
   void* jit = nullptr;
+  // wide engine (mb_wide.cu)
+  void* wide = nullptr;
 };
 
 struct mb_batch {
@@ -91,6 +98,9 @@ struct mb_batch {
   uint8_t* dY = nullptr;
   int64_t* dXOff = nullptr;
   int64_t* dYOff = nullptr;
+  int64_t* dEnv = nullptr;             // envOff | envStart | envEnd in one allocation (null: full envelopes only)
+  bool hasEnv = false;
+  std::vector<int64_t> envOff, envStart, envEnd;   // host copies
   mb::DevBatch dev {};
   cudaStream_t stream = nullptr;
   cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -125,6 +135,14 @@ int jit_update_weights (mb_machine* m);
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);
 int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int jit_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+
+// ---- wide engine (mb_wide.cu): Forward log-likelihood and Viterbi for mid-size and large machines ----
+bool wide_supported (const mb_machine* m, std::string* why);
+int wide_prepare (mb_machine* m);
+void wide_destroy (mb_machine* m);
+int wide_update_weights (mb_machine* m);
+int wide_forward (mb_machine* m, mb_batch* b, double* loglike);
+int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 
 // per-batch workspace (mb_api.cu)
 enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_NSLOTS };

@@ -17,7 +17,7 @@ from helpers import (LSE_EXACT, FlatMachine, Oracle, gnum, golden_names, load_go
 pytestmark = pytest.mark.gpu
 
 REL = 1e-4
-ENGINES = [0, 1]
+ENGINES = [0, 1, 2]      # generic, jit (small machines), wide
 
 
 def _capi():
@@ -32,6 +32,8 @@ def make_machine(capi, m: FlatMachine, engine: int):
     except capi.MachineBossError as e:
         if engine == 1 and "jit" in str(e).lower():
             pytest.skip("JIT engine does not take this machine: %s" % e)
+        if engine == 2 and "wide" in str(e).lower():
+            pytest.skip("wide engine does not take this machine: %s" % e)
         raise
     finally:
         capi.set_engine(-1)
@@ -53,6 +55,8 @@ def test_golden(name, engine):
     m = make_machine(capi, fm, engine)
     b = capi.Batch(pairs)
     ref = case["pairs"]
+    if any("env" in p for p in ref):      # pairs that carried an alignment: the reference's path envelope
+        b.set_envelopes([p.get("env") for p in ref])
     if any("rolling" in p or "forward" in p for p in ref):
         ll = capi.forward(m, b)
         for k, p in enumerate(ref):
@@ -122,6 +126,47 @@ def test_update_weights(engine):
     for k, (x, y) in enumerate(pairs):
         assert close(after[k], orc.forward(x, y))
     assert not np.allclose(before, after)
+
+
+def test_wide_engine_multi_strip_composite():
+    """prot2dna => dnapsw (308 states, 12 silent levels): pairs wider than one strip of columns, against the oracle."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("prot2dna_dnapsw")["machine"])
+    shapes = [(40, 130), (17, 60), (16, 33), (0, 5), (3, 0), (35, 90)]
+    pairs = [(synth_tokens(11, k, 0, li, fm.n_in), synth_tokens(11, k, 1, lo, fm.n_out)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 2)
+    assert m.engine == 2
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    sc2 = capi.viterbi(m, b, paths=False)
+    for k, (x, y) in enumerate(pairs):
+        assert close(ll[k], orc.forward(x, y)), (k, ll[k], orc.forward(x, y))
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and sc2[k] == v, (k, sc[k], v)
+        assert paths[k].tolist() == p.tolist(), k
+
+
+def test_wide_engine_log_domain_rerun():
+    """The trap machine through the wide engine: the scaled sweep flags the long pairs and the log-domain sweep redoes them."""
+    capi = _capi()
+    fm = _trap_machine()
+    ys = [np.array([1] * n + [2], dtype=np.uint8) for n in (10, 250, 400, 900)]
+    pairs = [(np.zeros(0, np.uint8), y) for y in ys]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 2)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    assert b.last_redo() >= 2
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y)
+        assert math.isfinite(f) and close(ll[k], f), (k, ll[k], f)
+    fm2 = fm.with_weights(np.where(fm.lw < 0, -60.0, fm.lw))      # extreme weights: log domain from the start
+    m2 = make_machine(capi, fm2, 2)
+    ll2 = capi.forward(m2, b)
+    for k, (x, y) in enumerate(pairs):
+        assert close(ll2[k], Oracle(fm2).forward(x, y))
 
 
 def _trap_machine():
