@@ -1,39 +1,43 @@
 // mb_wide.cu -- the wide engine: Forward log-likelihood and Viterbi (+ traceback) for machines too
 // large for the register-resident strip kernels of mb_jit.cu (composed transducers with tens to
-// thousands of states: SURVEY.md section 8 configs 4-5).
+// thousands of states: SURVEY.md section 8 configs 4-5), and for batches that carry envelopes.
 //
 //   reference                                              here
 //   MappedForwardMatrix::fill / logLike  forward.defs.h:22-55   wide_kernel<OP_SUM>  (scaled linear domain)
+//                                                               wide_kernel<OP_LSE>  (log domain: flagged pairs, extreme weights)
 //   ViterbiMatrix::fill / logLike        viterbi.cpp:18-47      wide_kernel<OP_MAX>  (FP64 add + compare: bit-exact)
 //   DPMatrix::traceBack                  dpmatrix.defs.h:82-110 wide_traceback_kernel (stored back-pointers)
 //
-// Mapping.  One WARP owns one input position (a matrix column); the states of a cell are spread
-// over its lanes.  A CTA of W column warps (+1 loader warp) sweeps a strip of W columns down the
-// output rows in a skew (warp j works on output row t-j at step t), so the three neighbour cells a
-// cell needs -- (i,o-1) own previous step, (i-1,o) left neighbour's previous step, (i-1,o-1) left
-// neighbour's step before that -- sit in a ring of 2-3 cells per column in SHARED memory, with one
-// CTA barrier per step.  The last column of a strip hands its live states (sources of input-
-// consuming transitions) to the next strip through an L2-resident row buffer that the loader warp
-// streams back in one row ahead.
+// Mapping.  A group of G lanes (32, 16 or 8, chosen per machine) owns one input position (a matrix
+// column); the states of a cell are spread over its lanes.  A CTA of W column warps (+1 loader
+// warp) sweeps a strip of W*32/G columns down the output rows in a skew (column j works on output
+// row t-j at step t), so the three neighbour cells a cell needs -- (i,o-1) own previous step,
+// (i-1,o) left neighbour's previous step, (i-1,o-1) left neighbour's step before that -- sit in a
+// ring of 2-3 cells per column in SHARED memory, with one CTA barrier per step.  The last column
+// of a strip hands its live states (sources of input-consuming transitions) to the next strip
+// through an L2-resident row buffer that the loader warp streams back in one row ahead.
 //
 // Within a cell the work is a sparse matrix-vector product over the token-selected transition
-// lists.  Transitions that consume a token only read neighbour cells, so they run as three flat,
-// dependency-free passes (match, delete, insert: "jobs" = one destination state and its source list,
-// dealt round-robin to the lanes); silent transitions follow in dependency levels, one __syncwarp
-// apart; destinations with long source lists (a profile HMM's end state) are split over all 32
-// lanes and combined with shuffles.  The job tables live in shared memory when they fit.
+// lists.  The host lays every dependency-free set of lists (one silent level, or one token context
+// of match / delete / insert) out as ROWS of G 16-byte entries: lane l walks its column of the
+// table, one multiply-add per row, lists back to back (longest-processing-time-first over the
+// lanes), with per-entry flags saying where a list starts, where it ends (add into the destination
+// state) and where the group has to synchronise before the next dependency level.  A list much
+// longer than its level's share is cut into 2^k pieces on adjacent lanes that are combined with
+// shuffles.  The tables live in shared memory when they fit, next to the rings.
 //
 // Arithmetic.  Forward: probabilities, one FMA per transition; every cell carries a power-of-two
 // frame (F) and the exponent of its largest value (G); a cell is computed in the frame
 // max(G of its neighbours), the neighbour sums entering through one exact power-of-two factor each,
 // so nothing is ever renormalised in place.  A cell whose values span more than 2^600, or whose
-// neighbours' frames are that far apart, flags the pair; flagged pairs are re-run by the log-domain
-// generic engine (mb_last_redo counts them).  Viterbi: log-weights, FP64 add + compare in the
-// reference's candidate order with a strict '<' (first maximum wins), so scores and paths are
-// identical; a back-pointer (kind, index in the token-selected list) is stored per cell-state.
+// neighbours' frames are that far apart, flags the pair; flagged pairs are re-run in the log domain
+// (mb_last_redo counts them).  Viterbi: log-weights, FP64 add + compare in the reference's
+// candidate order with a strict '<' (first maximum wins), so scores and paths are identical; a
+// back-pointer (kind, index in the token-selected list) is stored per cell-state.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mb_internal.h"
@@ -43,20 +47,18 @@ namespace mb {
 enum { OP_SUM = 0, OP_MAX = 1, OP_LSE = 2 };      // scaled linear sum, max-plus with back-pointers, log-sum-exp
 #define W_SENT (-(1 << 29))      // G of an empty (all-zero) cell
 #define W_SPREAD 600             // exponent spread that hands a pair to the log-domain sweep
-#define W_RSYNC 1                // round flags: group barrier after the round (end of a dependency level / phase)
-#define W_RREDUCE 2              //              some list of the round is split over several lanes
+// entry word z: source state (16) | candidate index in its list (14) | first of a list | last of a list
+#define W_FIRST 0x40000000u
+#define W_LAST 0x80000000u
+// entry word w: destination state (16) | log2 pieces (3) | reduce row | sync row
+#define W_REDUCE 0x80000u
+#define W_SYNC 0x100000u
 
-// Transition tables ("rounds").  The lists of one dependency-free group (one silent level, or one
-// token context of one kind) are dealt to the G lanes of a cell group; a round is G lists side by
-// side, padded to the longest (weight 0 / -inf), so every lane runs the same number of rows; a long
-// list is cut into 2^k contiguous pieces on adjacent lanes and combined with shuffles.
-struct WEntry { double w; uint32_t srcOff; uint32_t pad; };              // srcOff = source state * 8
-struct WRound { uint32_t rowStart; uint16_t nRows; uint16_t flags; };
-struct WLane { uint32_t a; uint32_t b; };      // a: dst (16; 0xffff = nothing to write) | log2 pieces (3) | round flags (2);  b: idx0 (16) | rows of the round (16)
+struct WEntry { double w; uint32_t z; uint32_t d; };
 
 struct WideTables {       // byte offsets into one blob (entries first: the two blobs differ only in their weights)
-  uint32_t oEnt, oRound, oLane, oPhM, oPhD, oPhI, oLive, bytes;
-  uint32_t silR0, silR1;
+  uint32_t oEnt, oPhM, oPhD, oPhI, oLive, bytes;
+  uint32_t silRow0, silRow1;
   int32_t S, nIn, nOut, hasMatch, nLiveIn, bpBytes, G;
 };
 
@@ -91,105 +93,111 @@ __device__ __forceinline__ double w_lse (double a, double b) {
   return mx + (double) __logf (1.f + __expf (d));
 }
 
-struct WTab {
-  const WEntry* ent; const WRound* round; const WLane* lane; const uint32_t* phM; const uint32_t* phD; const uint32_t* phI; const uint16_t* live;
-};
+struct WTab { const WEntry* ent; const uint32_t* phM; const uint32_t* phD; const uint32_t* phI; const uint16_t* live; };
 
-// rounds [r0, r1) of one phase, reading the cell `from` (a neighbour, or the cell itself for silent lists).
-// Rows of consecutive rounds are consecutive in the entry table, so one pointer runs through the
-// phase with the next entry always in flight; the tables end with a spare row and round.
-template<int OP, int G>
-__device__ __forceinline__ void run_rounds (const WTab& T, uint32_t r0, uint32_t r1, const double* from, double* cur, uint16_t* bpS,
-                                            double f, unsigned kindBits, int gl, unsigned gmask) {
-  if (r0 == r1) return;
-  const WLane* lp = T.lane + (size_t) r0 * G + gl;
-  uint2 li = *reinterpret_cast<const uint2*> (lp);
-  const WEntry* e = T.ent + (size_t) T.round[r0].rowStart * G + gl;
-  uint4 v = *reinterpret_cast<const uint4*> (e);
-  for (uint32_t r = r0; r < r1; ++r) {
-    lp += G;
-    const uint2 nli = *reinterpret_cast<const uint2*> (lp);      // next round's lane word
-    const unsigned dst = li.x & 0xffffu, segW = 1u << ((li.x >> 16) & 7u), flags = li.x >> 19, nRows = li.y >> 16, idx0 = li.y & 0xffffu;
-    if (OP != OP_MAX) {
-      const double c0 = dst != 0xffffu ? cur[dst] : 0.;
-      double acc = OP == OP_SUM ? 0. : w_ninf();
-#pragma unroll 2
-      for (unsigned k = 0; k < nRows; ++k) {
-        const uint4 u = v;
-        e += G;
-        v = *reinterpret_cast<const uint4*> (e);
-        const double w = __hiloint2double ((int) u.y, (int) u.x);
-        const double x = *reinterpret_cast<const double*> (reinterpret_cast<const char*> (from) + u.z);
-        acc = OP == OP_SUM ? fma (w, x, acc) : w_lse (acc, x + w);
-      }
-      if (flags & W_RREDUCE)
-        for (unsigned off = G / 2; off; off >>= 1) {
-          const double o2 = __shfl_down_sync (gmask, acc, off, G);
-          if (off < segW) acc = OP == OP_SUM ? acc + o2 : w_lse (acc, o2);
-        }
-      if (dst != 0xffffu) cur[dst] = OP == OP_SUM ? fma (f, acc, c0) : w_lse (c0, acc);
-    } else {
-      const double c0 = dst != 0xffffu ? cur[dst] : 0.;
-      double best = w_ninf();
-      unsigned bp = 0xffffu;
-#pragma unroll 2
-      for (unsigned k = 0; k < nRows; ++k) {
-        const uint4 u = v;
-        e += G;
-        v = *reinterpret_cast<const uint4*> (e);
-        const double c = *reinterpret_cast<const double*> (reinterpret_cast<const char*> (from) + u.z) + __hiloint2double ((int) u.y, (int) u.x);
-        if (best < c) { best = c; bp = kindBits | (idx0 + k); }      // strict: the first maximum wins (dpmatrix.defs.h:171-174)
-      }
-      if (flags & W_RREDUCE)
-        for (unsigned off = G / 2; off; off >>= 1) {      // the tree pairs lanes out of list order: a tie goes to the earlier candidate
-          const double ob = __shfl_down_sync (gmask, best, off, G);
+// Rows [row0, row1) of one phase, reading the cell `from` (a neighbour, or the cell itself for
+// silent lists).  One table pointer runs through the phase with the next entry always in flight
+// (the table ends with a spare row).  SILENT: every group of the warp walks the same rows, so the
+// level barriers are whole-warp; the token-selected phases differ between groups and are
+// synchronised by the caller.  live == false: a group that only keeps the warp in step.
+template<int OP, int G, bool SILENT>
+__device__ __forceinline__ void run_rows (const WTab& T, uint32_t row0, uint32_t row1, const double* from, double* cur, uint16_t* bpS,
+                                          double f, unsigned kindBits, int gl, unsigned gmask, bool live) {
+  if (row0 == row1) return;
+  const WEntry* e = T.ent + (size_t) row0 * G + gl;
+  uint4 v = *reinterpret_cast<const uint4*> (e);      // this row's entry; the next row's is fetched while this one is worked on,
+  double xn = from[v.z & 0xffffu];                    // and its source value as soon as the level barrier (if any) has passed
+  double acc = OP == OP_SUM ? 0. : w_ninf();      // OP_MAX: the best candidate so far
+  unsigned bp = 0xffffu;
+  for (uint32_t row = row0; row < row1; ++row) {
+    const uint4 u = v;
+    const double x = xn;
+    e += G;
+    v = *reinterpret_cast<const uint4*> (e);
+    const double w = __hiloint2double ((int) u.y, (int) u.x);
+    if (u.z & W_FIRST) { acc = OP == OP_SUM ? 0. : w_ninf(); bp = 0xffffu; }
+    if (OP == OP_SUM) acc = fma (w, x, acc);
+    else if (OP == OP_LSE) acc = w_lse (acc, x + w);
+    else { const double c = x + w; if (acc < c) { acc = c; bp = kindBits | ((u.z >> 16) & 0x3fffu); } }      // strict: the first maximum wins (dpmatrix.defs.h:171-174)
+    if (u.w & W_REDUCE) {      // the same row in every lane of the group
+      const unsigned segW = 1u << ((u.w >> 16) & 7u);
+      for (unsigned off = G / 2; off; off >>= 1) {
+        const double o2 = __shfl_down_sync (gmask, acc, off, G);
+        if (OP == OP_MAX) {      // the tree pairs lanes out of list order: a tie goes to the earlier candidate
           const unsigned obp = __shfl_down_sync (gmask, bp, off, G);
-          if (off < segW && (best < ob || (best == ob && obp < bp))) { best = ob; bp = obp; }
-        }
-      if (dst != 0xffffu && c0 < best) { cur[dst] = best; bpS[dst] = (uint16_t) bp; }      // earlier phases keep ties
+          if (off < segW && (acc < o2 || (acc == o2 && obp < bp))) { acc = o2; bp = obp; }
+        } else if (off < segW) acc = OP == OP_SUM ? acc + o2 : w_lse (acc, o2);
+      }
     }
-    if (flags & W_RSYNC) __syncwarp (gmask);
-    li = nli;
+    if ((u.z & W_LAST) && live) {
+      const unsigned dst = u.w & 0xffffu;
+      const double c0 = cur[dst];
+      if (OP == OP_SUM) cur[dst] = fma (f, acc, c0);
+      else if (OP == OP_LSE) cur[dst] = w_lse (c0, acc);
+      else if (c0 < acc) { cur[dst] = acc; bpS[dst] = (uint16_t) bp; }      // earlier phases keep ties
+    }
+    if (SILENT && (u.w & W_SYNC)) __syncwarp();
+    xn = from[v.z & 0xffffu];      // within a level no list reads a state the level writes, so this may run ahead of the adds above
   }
 }
 
-// One cell, computed by the G lanes of a group.  up/left/diag: neighbour cells (null when outside
-// the matrix or empty).  Linear domain: fU/fL/fD scale the neighbour sums into this cell's frame.
+// One cell per lane group, all groups of the warp in step (live == false: nothing to compute, the
+// group only walks along).  up/left/diag: neighbour cells (null when outside the matrix or empty).
+// Linear domain: fU/fL/fD scale the neighbour sums into this cell's frame.
 template<int OP, int G>
 __device__ __forceinline__ void compute_cell (const WTab& T, const WideTables& t, double* cur, uint16_t* bpS,
                                               const double* up, const double* left, const double* diag,
-                                              double fU, double fL, double fD, int a, int c, bool origin, int gl, unsigned gmask) {
+                                              double fU, double fL, double fD, int a, int c, bool origin, int gl, unsigned gmask, bool live) {
   const int S = t.S;
-  for (int d = gl; d < S; d += G) { cur[d] = OP == OP_SUM ? 0. : w_ninf(); if (OP == OP_MAX) bpS[d] = 0xffff; }
-  __syncwarp (gmask);
-  if (origin && gl == 0) cur[0] = OP == OP_SUM ? 1. : 0.;
-  __syncwarp (gmask);
+  if (live) {
+    for (int d = gl; d < S; d += G) { cur[d] = OP == OP_SUM ? 0. : w_ninf(); if (OP == OP_MAX) bpS[d] = 0xffff; }
+    if (origin && gl == 0) cur[0] = OP == OP_SUM ? 1. : 0.;      // written by the lane that zeroed it
+  }
+  __syncwarp();
   const unsigned kb = t.bpBytes == 1 ? 6 : 14;
   // reference candidate order: match, delete, insert, silent (dpmatrix.defs.h:90-103)
-  if (diag) { const int k = (a - 1) * t.nOut + (c - 1); run_rounds<OP, G> (T, T.phM[k], T.phM[k + 1], diag, cur, bpS, fD, (unsigned) T_MATCH << kb, gl, gmask); }
-  if (left) run_rounds<OP, G> (T, T.phD[a - 1], T.phD[a], left, cur, bpS, fL, (unsigned) T_DELETE << kb, gl, gmask);
-  if (up) run_rounds<OP, G> (T, T.phI[c - 1], T.phI[c], up, cur, bpS, fU, (unsigned) T_INSERT << kb, gl, gmask);
-  run_rounds<OP, G> (T, t.silR0, t.silR1, cur, cur, bpS, 1., (unsigned) T_SILENT << kb, gl, gmask);
+  if (t.hasMatch) {
+    if (live && diag) { const int k = (a - 1) * t.nOut + (c - 1); run_rows<OP, G, false> (T, T.phM[k], T.phM[k + 1], diag, cur, bpS, fD, (unsigned) T_MATCH << kb, gl, gmask, true); }
+    __syncwarp();
+  }
+  if (t.nIn) {
+    if (live && left) run_rows<OP, G, false> (T, T.phD[a - 1], T.phD[a], left, cur, bpS, fL, (unsigned) T_DELETE << kb, gl, gmask, true);
+    __syncwarp();
+  }
+  if (t.nOut) {
+    if (live && up) run_rows<OP, G, false> (T, T.phI[c - 1], T.phI[c], up, cur, bpS, fU, (unsigned) T_INSERT << kb, gl, gmask, true);
+    __syncwarp();
+  }
+  run_rows<OP, G, true> (T, t.silRow0, t.silRow1, cur, cur, bpS, 1., (unsigned) T_SILENT << kb, gl, gmask, live);
+  __syncwarp();
 }
 
-// exponent bookkeeping of a finished linear-domain cell: returns G (W_SENT if empty); sets bad on
-// overflow, underflow in progress, or an exponent spread beyond W_SPREAD
+template<int G> __device__ __forceinline__ int group_max (int v) {
+#pragma unroll
+  for (int off = G / 2; off; off >>= 1) v = max (v, __shfl_xor_sync (0xffffffffu, v, off, G));
+  return v;
+}
+
+// exponent bookkeeping of a finished linear-domain cell (all groups of the warp call it together):
+// returns G (W_SENT if empty); sets bad on overflow, underflow in progress, or an exponent spread beyond W_SPREAD
 template<int G>
-__device__ __forceinline__ int cell_frame (const double* cur, int S, int F, int gl, unsigned gmask, bool& bad) {
-  int mx = 0, mn = 0x7fffffff;
-  bool dust = false;
-  for (int d = gl; d < S; d += G) {
-    const double v = cur[d];
-    const int hi = __double2hiint (v) & 0x7fffffff;
-    mx = max (mx, hi);
-    if (hi >= 0x00100000) mn = min (mn, hi);
-    else if (v != 0.) dust = true;      // a denormal: something is underflowing
-  }
-  mx = __reduce_max_sync (gmask, mx);
-  mn = __reduce_min_sync (gmask, mn);
-  if (__any_sync (gmask, dust)) bad = true;
+__device__ __forceinline__ int cell_frame (const double* cur, int S, int F, int gl, bool live, bool& bad) {
+  int mx = 0, mnNeg = -0x7fffffff, dust = 0;
+  if (live)
+    for (int d = gl; d < S; d += G) {
+      const double v = cur[d];
+      const int hi = __double2hiint (v) & 0x7fffffff;
+      mx = max (mx, hi);
+      if (hi >= 0x00100000) mnNeg = max (mnNeg, -hi);
+      else if (v != 0.) dust = 1;      // a denormal: something is underflowing
+    }
+  mx = group_max<G> (mx);
+  mnNeg = group_max<G> (mnNeg);
+  dust = group_max<G> (dust);
+  if (!live) return W_SENT;
+  if (dust) bad = true;
   if (mx < 0x00100000) return W_SENT;     // an empty cell
-  const int emx = mx >> 20, emn = mn >> 20;
+  const int emx = mx >> 20, emn = (-mnNeg) >> 20;
   if (emx == 0x7ff || emx - emn > W_SPREAD) bad = true;
   return F + emx - 1023;
 }
@@ -209,9 +217,8 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
   const int grp = lane / G, gl = lane % G;
   const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (grp * G);
   // ---- shared memory: [tables] [ring: column slots x R cells of S doubles] [FG] [bp stage] [work slot]
-  const int nSlots = nWarps * CPW;      // column slots; in the 2-D sweep slot CPW-1 of warp 0 is the virtual column left of the strip
+  const int nSlots = nWarps * CPW;      // column slots; in the 2-D sweep the last slot of warp 0 is the virtual column left of the strip
   size_t at = 0;
-  const char* tab = p.blob;
   if (TABS) {
     for (uint32_t n = threadIdx.x * 16; n < t.bytes; n += blockDim.x * 16) *reinterpret_cast<uint4*> (smem + n) = *reinterpret_cast<const uint4*> (p.blob + n);
     at = (t.bytes + 15) & ~(size_t) 15;
@@ -222,12 +229,10 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
   at = (at + 7) & ~(size_t) 7;
   volatile long long* workSlot = reinterpret_cast<volatile long long*> (smem + at);
   WTab T;
-  if (TABS) T = { reinterpret_cast<const WEntry*> (smem + t.oEnt), reinterpret_cast<const WRound*> (smem + t.oRound), reinterpret_cast<const WLane*> (smem + t.oLane),
-                  reinterpret_cast<const uint32_t*> (smem + t.oPhM), reinterpret_cast<const uint32_t*> (smem + t.oPhD), reinterpret_cast<const uint32_t*> (smem + t.oPhI),
-                  reinterpret_cast<const uint16_t*> (smem + t.oLive) };
-  else T = { reinterpret_cast<const WEntry*> (tab + t.oEnt), reinterpret_cast<const WRound*> (tab + t.oRound), reinterpret_cast<const WLane*> (tab + t.oLane),
-             reinterpret_cast<const uint32_t*> (tab + t.oPhM), reinterpret_cast<const uint32_t*> (tab + t.oPhD), reinterpret_cast<const uint32_t*> (tab + t.oPhI),
-             reinterpret_cast<const uint16_t*> (tab + t.oLive) };
+  if (TABS) T = { reinterpret_cast<const WEntry*> (smem + t.oEnt), reinterpret_cast<const uint32_t*> (smem + t.oPhM), reinterpret_cast<const uint32_t*> (smem + t.oPhD),
+                  reinterpret_cast<const uint32_t*> (smem + t.oPhI), reinterpret_cast<const uint16_t*> (smem + t.oLive) };
+  else T = { reinterpret_cast<const WEntry*> (p.blob + t.oEnt), reinterpret_cast<const uint32_t*> (p.blob + t.oPhM), reinterpret_cast<const uint32_t*> (p.blob + t.oPhD),
+             reinterpret_cast<const uint32_t*> (p.blob + t.oPhI), reinterpret_cast<const uint16_t*> (p.blob + t.oLive) };
   __syncthreads();
   const int mySlot = warp * CPW + grp;
   double* myRing = ring + (size_t) mySlot * R * S;
@@ -236,43 +241,47 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
   const double LN2 = 0.693147180559945309417232121458;
 
   if (p.oneD) {
-    // ---- batches without input sequences: every lane group sweeps its own pair, no CTA barriers
+    // ---- batches without input sequences: every lane group sweeps its own pair, the groups of a warp in step; no CTA barriers
     for (;;) {
-      long long wk = 0;
-      if (gl == 0) wk = (long long) atomicAdd (p.counter, 1ULL);
-      wk = __shfl_sync (gmask, wk, 0, G);
-      if (wk >= p.nWork) break;
-      const int64_t k = p.order[wk];
+      long long wk0 = 0;
+      if (lane == 0) wk0 = (long long) atomicAdd (p.counter, (unsigned long long) CPW);
+      wk0 = __shfl_sync (0xffffffffu, wk0, 0);
+      if (wk0 >= p.nWork) break;
+      const long long wk = wk0 + grp;
+      const bool have = wk < p.nWork;
+      const int64_t k = have ? p.order[wk] : 0;
       const uint8_t* y = p.b.y + p.b.yOff[k];
-      const int64_t Lo = p.b.yOff[k + 1] - p.b.yOff[k];
+      const int64_t Lo = have ? p.b.yOff[k + 1] - p.b.yOff[k] : -1;
+      const int64_t maxLo = (int64_t) group_max<32> ((int) Lo);
       EnvD env { nullptr, nullptr };
-      if (p.b.envOff && p.b.envOff[k + 1] != p.b.envOff[k]) env = EnvD { p.b.envStart + p.b.envOff[k], p.b.envEnd + p.b.envOff[k] };
-      unsigned char* bp = OP == OP_MAX && p.bp ? p.bp + p.bpOff[wk] : nullptr;
+      if (have && p.b.envOff && p.b.envOff[k + 1] != p.b.envOff[k]) env = EnvD { p.b.envStart + p.b.envOff[k], p.b.envEnd + p.b.envOff[k] };
+      unsigned char* bp = OP == OP_MAX && p.bp && have ? p.bp + p.bpOff[wk] : nullptr;
       bool bad = false;
       int slot = 0;
       int Fprev = 0, Gprev = W_SENT;
       double res = OP == OP_SUM ? 0. : w_ninf();
       int Fres = 0;
-      for (int64_t o = 0; o <= Lo; ++o) {
+      for (int64_t o = 0; o <= maxLo; ++o) {
+        const bool inRange = o <= Lo;
         double* cur = myRing + (size_t) slot * S;
         const double* up = o ? myRing + (size_t) (slot ^ 1) * S : nullptr;
-        const bool inside = env.contains (0, o);
+        const bool inside = inRange && env.contains (0, o);
         int F = 0;
         double fU = 1.;
         if (OP == OP_SUM && up) { if (Gprev == W_SENT) up = nullptr; else { F = Gprev; fU = w_pow2 (Fprev - F); } }
-        if (inside) compute_cell<OP, G> (T, t, cur, bpS, up, nullptr, nullptr, fU, 0., 0., 0, o ? y[o - 1] : 0, o == 0, gl, gmask);
-        else { for (int d = gl; d < S; d += G) cur[d] = OP == OP_SUM ? 0. : w_ninf(); __syncwarp (gmask); }
-        if (OP == OP_SUM) { Fprev = F; Gprev = inside ? cell_frame<G> (cur, S, F, gl, gmask, bad) : W_SENT; }
+        compute_cell<OP, G> (T, t, cur, bpS, up, nullptr, nullptr, fU, 0., 0., 0, (inRange && o) ? y[o - 1] : 1, o == 0, gl, gmask, inside);
+        if (inRange && !inside) for (int d = gl; d < S; d += G) cur[d] = OP == OP_SUM ? 0. : w_ninf();
+        if (OP == OP_SUM) { const int Gc = cell_frame<G> (cur, S, F, gl, inside, bad); if (inRange) { Fprev = F; Gprev = Gc; } }
         else if (bp && inside) {
           unsigned char* row = bp + (size_t) o * S * t.bpBytes;
           if (t.bpBytes == 1) for (int d = gl; d < S; d += G) row[d] = (unsigned char) bpS[d];
           else for (int d = gl; d < S; d += G) reinterpret_cast<uint16_t*> (row)[d] = bpS[d];
         }
+        __syncwarp();
         if (o == Lo) { res = cur[S - 1]; Fres = F; }
-        __syncwarp (gmask);
         slot ^= 1;
       }
-      if (gl == 0) {
+      if (gl == 0 && have) {
         if (OP == OP_SUM) { p.result[k] = res > 0. ? log (res) + Fres * LN2 : w_ninf(); p.flag[k] = bad || !(res > 0.) || !(res < 1e300); }
         else p.result[k] = res;
       }
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
       const int col = (warp - 1) * CPW + grp;
       const bool active = warp >= 1 && col < nCols;
       const int64_t i = i0 + col;
-      const int a = (active && i > 0) ? x[i - 1] : 0;
+      const int a = (active && i > 0) ? x[i - 1] : 1;
       const bool writesBnd = active && col == nCols - 1 && strip + 1 < nStrips;
       const double* bndIn = bndBase + (size_t) ((strip & 1) ^ 1) * p.bndRows * t.nLiveIn;
       double* bndOut = bndBase + (size_t) (strip & 1) * p.bndRows * t.nLiveIn;
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
       }
       __syncthreads();
       const int64_t nSteps = Lo + nCols;
+      const int firstCol = (warp - 1) * CPW, lastCol = min (firstCol + CPW, nCols) - 1;      // this warp's columns in the strip
       int slot = 0;      // t % R
       for (int64_t ts = 0; ts < nSteps; ++ts) {
         const int prev = slot == 0 ? R - 1 : slot - 1;            // (t-1) % R
@@ -331,43 +341,42 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
             for (int q = lane; q < t.nLiveIn; q += 32) dst[T.live[q]] = srcRow[q];
             if (lane == 0 && OP == OP_SUM) virtFG[slot] = fgIn[ts + 1];
           }
-        } else {
+        } else if (lastCol >= firstCol && ts - lastCol <= Lo && ts - firstCol >= 0) {      // some column of this warp has a row to do
           const int64_t o = ts - col;
-          if (active && o >= 0 && o <= Lo) {
-            double* cur = myRing + (size_t) slot * S;
-            const double* up = o > 0 ? myRing + (size_t) prev * S : nullptr;
-            const double* left = i > 0 ? myRing - (size_t) R * S + (size_t) prev * S : nullptr;
-            const double* diag = (i > 0 && o > 0 && t.hasMatch) ? myRing - (size_t) R * S + (size_t) prev2 * S : nullptr;
-            const bool inside = env.contains (i, o);
-            int F = 0;
-            double fU = 1., fL = 1., fD = 1.;
-            if (OP == OP_SUM) {
-              const int2 gU = up ? myFG[prev] : make_int2 (0, W_SENT);
-              const int2 gL = left ? myFG[prev - R] : make_int2 (0, W_SENT);
-              const int2 gD = diag ? myFG[prev2 - R] : make_int2 (0, W_SENT);
-              const int Gm = max (gU.y, max (gL.y, gD.y));
-              F = Gm == W_SENT ? 0 : Gm;
-              if (gU.y == W_SENT) up = nullptr; else { fU = w_pow2 (gU.x - F); if (F - gU.y > W_SPREAD) bad = true; }
-              if (gL.y == W_SENT) left = nullptr; else { fL = w_pow2 (gL.x - F); if (F - gL.y > W_SPREAD) bad = true; }
-              if (gD.y == W_SENT) diag = nullptr; else { fD = w_pow2 (gD.x - F); if (F - gD.y > W_SPREAD) bad = true; }
-            }
-            if (inside) compute_cell<OP, G> (T, t, cur, bpS, up, left, diag, fU, fL, fD, a, o ? y[o - 1] : 0, i == 0 && o == 0, gl, gmask);
-            else { for (int d = gl; d < S; d += G) cur[d] = OP == OP_SUM ? 0. : w_ninf(); __syncwarp (gmask); }
-            if (OP == OP_SUM) {
-              const int Gc = inside ? cell_frame<G> (cur, S, F, gl, gmask, bad) : W_SENT;
-              if (gl == 0) myFG[slot] = make_int2 (F, Gc);
-              if (writesBnd && gl == 0) fgOut[o] = make_int2 (F, Gc);
-            } else if (bp && inside) {
-              unsigned char* row = bp + ((size_t) o * (Li + 1) + i) * S * t.bpBytes;
-              if (t.bpBytes == 1) for (int d = gl; d < S; d += G) row[d] = (unsigned char) bpS[d];
-              else for (int d = gl; d < S; d += G) reinterpret_cast<uint16_t*> (row)[d] = bpS[d];
-            }
-            if (writesBnd) { double* dstRow = bndOut + (size_t) o * t.nLiveIn; for (int q = gl; q < t.nLiveIn; q += G) dstRow[q] = cur[T.live[q]]; }
-            if (i == Li && o == Lo && gl == 0) {
-              const double res = cur[S - 1];
-              if (OP == OP_SUM) { p.result[k] = res > 0. ? log (res) + F * LN2 : w_ninf(); if (!(res > 0.) || !(res < 1e300)) bad = true; }
-              else p.result[k] = res;
-            }
+          const bool inRange = active && o >= 0 && o <= Lo;
+          double* cur = myRing + (size_t) slot * S;
+          const double* up = (inRange && o > 0) ? myRing + (size_t) prev * S : nullptr;
+          const double* left = (inRange && i > 0) ? myRing - (size_t) R * S + (size_t) prev * S : nullptr;
+          const double* diag = (inRange && i > 0 && o > 0 && t.hasMatch) ? myRing - (size_t) R * S + (size_t) prev2 * S : nullptr;
+          const bool inside = inRange && env.contains (i, o);
+          int F = 0;
+          double fU = 1., fL = 1., fD = 1.;
+          if (OP == OP_SUM) {
+            const int2 gU = up ? myFG[prev] : make_int2 (0, W_SENT);
+            const int2 gL = left ? myFG[prev - R] : make_int2 (0, W_SENT);
+            const int2 gD = diag ? myFG[prev2 - R] : make_int2 (0, W_SENT);
+            const int Gm = max (gU.y, max (gL.y, gD.y));
+            F = Gm == W_SENT ? 0 : Gm;
+            if (gU.y == W_SENT) up = nullptr; else { fU = w_pow2 (gU.x - F); if (F - gU.y > W_SPREAD) bad = true; }
+            if (gL.y == W_SENT) left = nullptr; else { fL = w_pow2 (gL.x - F); if (F - gL.y > W_SPREAD) bad = true; }
+            if (gD.y == W_SENT) diag = nullptr; else { fD = w_pow2 (gD.x - F); if (F - gD.y > W_SPREAD) bad = true; }
+          }
+          compute_cell<OP, G> (T, t, cur, bpS, up, left, diag, fU, fL, fD, a, (inRange && o) ? y[o - 1] : 1, i == 0 && o == 0, gl, gmask, inside);
+          if (inRange && !inside) for (int d = gl; d < S; d += G) cur[d] = OP == OP_SUM ? 0. : w_ninf();
+          if (OP == OP_SUM) {
+            const int Gc = cell_frame<G> (cur, S, F, gl, inside, bad);
+            if (inRange && gl == 0) { myFG[slot] = make_int2 (F, Gc); if (writesBnd) fgOut[o] = make_int2 (F, Gc); }
+          } else if (bp && inside) {
+            unsigned char* row = bp + ((size_t) o * (Li + 1) + i) * S * t.bpBytes;
+            if (t.bpBytes == 1) for (int d = gl; d < S; d += G) row[d] = (unsigned char) bpS[d];
+            else for (int d = gl; d < S; d += G) reinterpret_cast<uint16_t*> (row)[d] = bpS[d];
+          }
+          __syncwarp();
+          if (inRange && writesBnd) { double* dstRow = bndOut + (size_t) o * t.nLiveIn; for (int q = gl; q < t.nLiveIn; q += G) dstRow[q] = cur[T.live[q]]; }
+          if (inRange && i == Li && o == Lo && gl == 0) {
+            const double res = cur[S - 1];
+            if (OP == OP_SUM) { p.result[k] = res > 0. ? log (res) + F * LN2 : w_ninf(); if (!(res > 0.) || !(res < 1e300)) bad = true; }
+            else p.result[k] = res;
           }
         }
         __syncthreads();
@@ -418,6 +427,8 @@ __global__ void wide_traceback_kernel (DevMachine m, DevBatch b, const int64_t* 
 }
 
 // ---------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct WHost {
@@ -444,8 +455,8 @@ template<class T> static uint32_t put_vec (std::vector<char>& blob, const std::v
 bool wide_supported (const mb_machine* m, std::string* why) {
   if (m->S > 16000) { if (why) *why = "wide engine: more than 16000 states"; return false; }
   if (m->T > 100000000) { if (why) *why = "wide engine: too many transitions"; return false; }
-  // one column (a ring of 3 cells + the back-pointer stage) must fit in shared memory
-  if ((size_t) m->S * (3 * 8 + 2) + 1024 > 227 * 1024) { if (why) *why = "wide engine: a cell does not fit in shared memory"; return false; }
+  // two columns (rings of 3 cells + the back-pointer stage) must fit in shared memory
+  if ((size_t) m->S * 2 * (3 * 8 + 2) + 1024 > 227 * 1024) { if (why) *why = "wide engine: a cell does not fit in shared memory"; return false; }
   return true;
 }
 
@@ -454,101 +465,82 @@ struct WList { int dst; int64_t p0, p1; };      // one destination's token-selec
 
 struct WBuilder {
   int G = 32;
-  std::vector<WEntry> ent;
+  std::vector<WEntry> ent;       // rows of G entries
   std::vector<int64_t> perm;
-  std::vector<WRound> rounds;
-  std::vector<WLane> lanes;
-  double cost = 0;      // estimated warp instructions spent in the rounds built so far
+  size_t rows() const { return ent.size() / (size_t) G; }
 };
 
 static int pow2ceil (int v) { int n = 1; while (n < v) n <<= 1; return n; }
 static int ilog2 (int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-struct WItem { int list, n, rows; };
-
-// lists of one dependency-free group -> rounds; piece cap C; returns the estimated cost, appends to B unless dry
-static double pack_group (const std::vector<WList>& lists, const mb_machine* m, int C, WBuilder& B, bool dry) {
-  const int G = B.G;
-  std::vector<WItem> items;
-  for (size_t j = 0; j < lists.size(); ++j) {
-    const int L = (int) (lists[j].p1 - lists[j].p0);
-    const int n = std::min (G, pow2ceil ((L + C - 1) / C));
-    items.push_back (WItem { (int) j, n, (L + n - 1) / n });
-  }
-  std::stable_sort (items.begin(), items.end(), [] (const WItem& a, const WItem& b) { return a.rows != b.rows ? a.rows > b.rows : a.n > b.n; });
-  double cost = 0;
-  size_t q = 0;
-  while (q < items.size()) {
-    // one round: place items at aligned lane offsets until one does not fit
-    std::vector<std::pair<int, WItem>> placed;
-    int fill = 0, rows = 0;
-    bool split = false;
-    while (q < items.size()) {
-      const int at = (fill + items[q].n - 1) / items[q].n * items[q].n;
-      if (at + items[q].n > G) break;
-      placed.push_back (std::make_pair (at, items[q]));
-      fill = at + items[q].n;
-      rows = std::max (rows, items[q].rows);
-      split = split || items[q].n > 1;
-      ++q;
-    }
-    cost += 18 + 5.5 * rows + (split ? 4.0 * ilog2 (G) : 0);
-    if (dry) continue;
-    WRound r; r.rowStart = (uint32_t) (B.ent.size() / G); r.nRows = (uint16_t) rows; r.flags = (uint16_t) ((split ? W_RREDUCE : 0) | (q == items.size() ? W_RSYNC : 0));
-    B.rounds.push_back (r);
-    const size_t l0 = B.lanes.size(), e0 = B.ent.size();
-    WLane idle; idle.a = 0xffffu | ((uint32_t) r.flags << 19); idle.b = (uint32_t) rows << 16;
-    B.lanes.resize (l0 + G, idle);
-    WEntry padE; padE.w = 0; padE.srcOff = 0; padE.pad = 0;
-    B.ent.resize (e0 + (size_t) rows * G, padE);
-    B.perm.resize (e0 + (size_t) rows * G, -1);
-    for (auto& pl: placed) {
-      const WList& ls = lists[pl.second.list];
-      const int L = (int) (ls.p1 - ls.p0);
-      for (int j = 0; j < pl.second.n; ++j) {
-        WLane& ln = B.lanes[l0 + pl.first + j];
-        ln.a = (j == 0 ? (uint32_t) ls.dst : 0xffffu) | ((uint32_t) ilog2 (pl.second.n) << 16) | ((uint32_t) r.flags << 19);
-        ln.b = (uint32_t) (j * pl.second.rows) | ((uint32_t) rows << 16);
-        for (int k = 0; k < pl.second.rows; ++k) {
-          const int n = j * pl.second.rows + k;
-          if (n >= L) break;
-          const size_t e = e0 + (size_t) k * G + pl.first + j;
-          B.ent[e].srcOff = (uint32_t) m->hInc.other[ls.p0 + n] * 8u;
-          B.perm[e] = ls.p0 + n;
-        }
-      }
-    }
-  }
-  return cost;
-}
-
-static double add_group (const std::vector<WList>& lists, const mb_machine* m, WBuilder& B) {
+// One dependency-free set of lists -> rows: long lists cut into 2^k pieces on adjacent lanes
+// (combined by shuffles on their last row), the rest dealt longest-first to the least loaded lane.
+// Returns the number of rows; the last row carries the sync flag.
+static int schedule_lists (const std::vector<WList>& lists, const mb_machine* m, WBuilder& B) {
   if (lists.empty()) return 0;
-  int maxL = 1;
-  for (auto& l: lists) maxL = std::max<int> (maxL, (int) (l.p1 - l.p0));
-  std::vector<int> caps;
-  for (int c = 1; c < maxL; c = c < 4 ? c + 1 : c + c / 2) caps.push_back (c);
-  caps.push_back (maxL);
-  int bestC = maxL;
-  double best = 1e300;
-  for (int c: caps) { const double v = pack_group (lists, m, c, B, true); if (v < best) { best = v; bestC = c; } }
-  B.cost += pack_group (lists, m, bestC, B, false);
-  return best;
+  const int G = B.G;
+  int64_t total = 0;
+  for (auto& l: lists) total += l.p1 - l.p0;
+  const int share = (int) std::max<int64_t> (3, (total + G - 1) / G);
+  struct Placed { int list, lane, row, n, rows; };
+  std::vector<Placed> placed;
+  std::vector<int> freeRow ((size_t) G, 0);
+  std::vector<int> order (lists.size());
+  for (size_t j = 0; j < lists.size(); ++j) order[j] = (int) j;
+  std::stable_sort (order.begin(), order.end(), [&] (int a, int b) { return lists[a].p1 - lists[a].p0 > lists[b].p1 - lists[b].p0; });
+  for (int j: order) {
+    const int L = (int) (lists[j].p1 - lists[j].p0);
+    int n = 1;
+    if (L >= 6 && L > share + share / 2) n = std::min (G, pow2ceil ((L + share - 1) / share));
+    const int rows = (L + n - 1) / n;
+    int bestLane = 0, bestStart = 1 << 30;
+    for (int l0 = 0; l0 + n <= G; l0 += n) {
+      int start = 0;
+      for (int l = l0; l < l0 + n; ++l) start = std::max (start, freeRow[l]);
+      if (start < bestStart) { bestStart = start; bestLane = l0; }
+    }
+    placed.push_back (Placed { j, bestLane, bestStart, n, rows });
+    for (int l = bestLane; l < bestLane + n; ++l) freeRow[l] = bestStart + rows;
+  }
+  int nRows = 0;
+  for (int l = 0; l < G; ++l) nRows = std::max (nRows, freeRow[l]);
+  const size_t e0 = B.ent.size();
+  WEntry padE; padE.w = 0; padE.z = 0; padE.d = 0;
+  B.ent.resize (e0 + (size_t) nRows * G, padE);
+  B.perm.resize (e0 + (size_t) nRows * G, -1);
+  for (auto& pl: placed) {
+    const WList& ls = lists[pl.list];
+    const int L = (int) (ls.p1 - ls.p0);
+    for (int j = 0; j < pl.n; ++j)
+      for (int k = 0; k < pl.rows; ++k) {
+        const size_t e = e0 + (size_t) (pl.row + k) * G + pl.lane + j;
+        const int n = j * pl.rows + k;
+        WEntry& en = B.ent[e];
+        if (n < L) { en.z = (uint32_t) m->hInc.other[ls.p0 + n] | ((uint32_t) n << 16); B.perm[e] = ls.p0 + n; }
+        else en.z = (uint32_t) 0 | (0x3fffu << 16);      // padding inside a piece: weight 0 / -inf
+        if (k == 0) en.z |= W_FIRST;
+        en.d = (uint32_t) ls.dst | ((uint32_t) ilog2 (pl.n) << 16);
+        if (k == pl.rows - 1 && j == 0) en.z |= W_LAST;
+      }
+  }
+  for (auto& pl: placed)      // after every entry is in place: the reduce row is flagged in all lanes of the group
+    if (pl.n > 1) for (int l = 0; l < G; ++l) B.ent[e0 + (size_t) (pl.row + pl.rows - 1) * G + l].d |= W_REDUCE;
+  for (int l = 0; l < G; ++l) B.ent[e0 + (size_t) (nRows - 1) * G + l].d |= W_SYNC;
+  return nRows;
 }
 
-// all tables for lane-group width G; the cost estimate is per cell (a warp works on 32/G cells at once)
+// all tables for lane-group width G; perCell: estimated warp instructions per cell (a warp works on 32/G cells at once)
 static void build_tables (const mb_machine* m, int G, WBuilder& B, std::vector<uint32_t>& phM, std::vector<uint32_t>& phD, std::vector<uint32_t>& phI,
-                          uint32_t& silR0, uint32_t& silR1, std::vector<uint16_t>& live, bool& hasMatch, int& maxList, double& perCell) {
+                          uint32_t& silRow0, uint32_t& silRow1, std::vector<uint16_t>& live, bool& hasMatch, int& maxList, double& perCell) {
   const int S = m->S, nIn = m->nIn, nOut = m->nOut, nIn1 = nIn + 1, nOut1 = nOut + 1;
   const HostCsr& inc = m->hInc;
   B = WBuilder();
   B.G = G;
   maxList = 0;
   std::vector<char> isLive ((size_t) S, 0);
-  auto lists_for = [&] (int a, int c, int level, bool input) {
+  auto lists_for = [&] (int a, int c, bool input) {
     std::vector<WList> ls;
     for (int d = 0; d < S; ++d) {
-      if (level >= 0 && d == 0) continue;      // state 0's only possible silent source is its own self-loop, which contributes nothing
       const int64_t key = ((int64_t) d * nIn1 + a) * nOut1 + c;
       if (inc.off[key] == inc.off[key + 1]) continue;
       ls.push_back (WList { d, inc.off[key], inc.off[key + 1] });
@@ -557,39 +549,38 @@ static void build_tables (const mb_machine* m, int G, WBuilder& B, std::vector<u
     }
     return ls;
   };
-  double cM = 0, cD = 0, cI = 0, cS = 0;
   hasMatch = false;
   phM.clear(); phD.clear(); phI.clear();
   for (int a = 1; a <= nIn; ++a) for (int c = 1; c <= nOut; ++c) {
-    phM.push_back ((uint32_t) B.rounds.size());
-    const std::vector<WList> ls = lists_for (a, c, -1, true);
-    if (!ls.empty()) hasMatch = true;
-    cM += add_group (ls, m, B);
+    phM.push_back ((uint32_t) B.rows());
+    if (schedule_lists (lists_for (a, c, true), m, B)) hasMatch = true;
   }
-  phM.push_back ((uint32_t) B.rounds.size());
-  for (int a = 1; a <= nIn; ++a) { phD.push_back ((uint32_t) B.rounds.size()); cD += add_group (lists_for (a, 0, -1, true), m, B); }
-  phD.push_back ((uint32_t) B.rounds.size());
-  for (int c = 1; c <= nOut; ++c) { phI.push_back ((uint32_t) B.rounds.size()); cI += add_group (lists_for (0, c, -1, false), m, B); }
-  phI.push_back ((uint32_t) B.rounds.size());
-  silR0 = (uint32_t) B.rounds.size();
+  phM.push_back ((uint32_t) B.rows());
+  for (int a = 1; a <= nIn; ++a) { phD.push_back ((uint32_t) B.rows()); schedule_lists (lists_for (a, 0, true), m, B); }
+  phD.push_back ((uint32_t) B.rows());
+  for (int c = 1; c <= nOut; ++c) { phI.push_back ((uint32_t) B.rows()); schedule_lists (lists_for (0, c, false), m, B); }
+  phI.push_back ((uint32_t) B.rows());
+  const double rowsM = nIn && nOut ? (double) (phM.back() - phM.front()) / ((double) nIn * nOut) : 0;
+  const double rowsD = nIn ? (double) (phD.back() - phD.front()) / nIn : 0, rowsI = nOut ? (double) (phI.back() - phI.front()) / nOut : 0;
+  silRow0 = (uint32_t) B.rows();
   const int nLevels = (int) m->fwdLevelOff.size() - 1;
   for (int l = 1; l < nLevels; ++l) {      // level 0 has no silent sources
     std::vector<WList> ls;
     for (int n = m->fwdLevelOff[l]; n < m->fwdLevelOff[l + 1]; ++n) {
       const int d = m->fwdLevelStates[n];
-      if (d == 0) continue;
+      if (d == 0) continue;      // state 0's only possible silent source is its own self-loop, which contributes nothing
       const int64_t key = (int64_t) d * nIn1 * nOut1;
       if (inc.off[key] == inc.off[key + 1]) continue;
       ls.push_back (WList { d, inc.off[key], inc.off[key + 1] });
       maxList = std::max<int> (maxList, (int) (inc.off[key + 1] - inc.off[key]));
     }
-    cS += add_group (ls, m, B);
+    schedule_lists (ls, m, B);
   }
-  silR1 = (uint32_t) B.rounds.size();
+  silRow1 = (uint32_t) B.rows();
   live.clear();
   for (int s = 0; s < S; ++s) if (isLive[s]) live.push_back ((uint16_t) s);
-  const double perWarp = cS + (nIn && nOut ? cM / ((double) nIn * nOut) : 0) + (nIn ? cD / nIn : 0) + (nOut ? cI / nOut : 0)
-    + 9.0 * ((S + G - 1) / G) + 120;      // + zero pass, frame / back-pointer pass, step overhead
+  const double perWarp = 13.0 * ((double) (silRow1 - silRow0) + rowsM + rowsD + rowsI) + 4.0 * std::max (nLevels - 1, 0)
+    + 10.0 * ((S + G - 1) / G) + 150;      // rows, level barriers, zero + frame / back-pointer passes, step overhead
   perCell = perWarp / (32 / G);
 }
 
@@ -634,9 +625,9 @@ int wide_prepare (mb_machine* m) {
   std::vector<uint32_t> phM, phD, phI, bM, bD, bI;
   std::vector<uint16_t> live, bLive;
   uint32_t s0 = 0, s1 = 0, b0 = 0, b1 = 0;
-  bool hasMatch = false;
+  bool hasMatch = false, bestMatch = false;
   int maxList = 0;
-  double bestCost = 1e300;
+  double bestCost = 1e300, bestInstr = 0;
   int forceG = 0;
   if (const char* e = getenv ("MB_WIDE_G")) forceG = atoi (e);
   for (int G: { 32, 16, 8 }) {
@@ -644,38 +635,35 @@ int wide_prepare (mb_machine* m) {
     double perCell = 0;
     build_tables (m, G, B, phM, phD, phI, s0, s1, live, hasMatch, maxList, perCell);
     // the sweep is latency-bound below ~16 warps per SM: weigh the instruction estimate by the warps that fit
-    const size_t tabBytes = B.ent.size() * sizeof (WEntry) + B.lanes.size() * sizeof (WLane) + B.rounds.size() * sizeof (WRound) + 4096;
+    const size_t tabBytes = B.ent.size() * sizeof (WEntry) + 4096;
     const size_t perWarp = (size_t) (32 / G) * ((hasMatch ? 3 : 2) * ((size_t) m->S * 8 + 8) + (size_t) m->S * 2);
     const size_t kSmem = 227 * 1024;
-    const size_t room = tabBytes + 2 * perWarp <= kSmem ? kSmem - tabBytes : kSmem;      // tables in shared memory when two warps still fit
+    const bool tabsFit = tabBytes + 2 * perWarp <= kSmem;      // tables in shared memory when two warps still fit
+    const size_t room = tabsFit ? kSmem - tabBytes : kSmem;
     const int warps = (int) std::min<size_t> (17, room / perWarp);
     if (warps < 2 && !(forceG && G == forceG)) continue;
-    perCell *= std::max (1.0, 16.0 / std::max (warps, 1)) * (room == kSmem && tabBytes + 2 * perWarp > kSmem ? 1.5 : 1.0);
-    if (perCell < bestCost) { bestCost = perCell; best = B; bM = phM; bD = phD; bI = phI; bLive = live; b0 = s0; b1 = s1; }
+    const double cost = perCell * std::max (1.0, 16.0 / std::max (warps, 1)) * (tabsFit ? 1.0 : 1.5);
+    if (cost < bestCost) { bestCost = cost; bestInstr = perCell; best = B; bM = phM; bD = phD; bI = phI; bLive = live; b0 = s0; b1 = s1; bestMatch = hasMatch; }
   }
   if (bestCost >= 1e300) { set_error ("wide engine: a cell does not fit in shared memory"); return 1; }
-  if (maxList > 16383) { set_error ("wide engine: a transition list has more than 16383 entries"); return 1; }
-  {      // spare row and round: the sweep keeps one entry and one lane word in flight
-    WEntry padE; padE.w = 0; padE.srcOff = 0; padE.pad = 0;
-    WLane padL; padL.a = 0xffffu; padL.b = 0;
+  if (maxList > 16382) { set_error ("wide engine: a transition list has more than 16382 entries"); return 1; }
+  if (best.rows() > 0xfffffff0u) { set_error ("wide engine: tables too large"); return 1; }
+  {      // spare row: the sweep keeps one entry in flight
+    WEntry padE; padE.w = 0; padE.z = 0; padE.d = 0;
     best.ent.resize (best.ent.size() + best.G, padE);
     best.perm.resize (best.perm.size() + best.G, -1);
-    best.lanes.resize (best.lanes.size() + best.G, padL);
-    WRound padR; padR.rowStart = 0; padR.nRows = 0; padR.flags = 0;
-    best.rounds.push_back (padR);
   }
-  if (best.ent.size() / best.G > 0xfffffff0u) { set_error ("wide engine: tables too large"); return 1; }
   WideTables& t = h->t;
   std::vector<char>& blob = h->blobLin;
-  t.oEnt = put_vec (blob, best.ent); t.oRound = put_vec (blob, best.rounds); t.oLane = put_vec (blob, best.lanes);
+  t.oEnt = put_vec (blob, best.ent);
   t.oPhM = put_vec (blob, bM); t.oPhD = put_vec (blob, bD); t.oPhI = put_vec (blob, bI); t.oLive = put_vec (blob, bLive);
   blob.resize ((blob.size() + 15) & ~(size_t) 15, 0);
   t.bytes = (uint32_t) blob.size();
-  t.silR0 = b0; t.silR1 = b1;
-  t.S = m->S; t.nIn = m->nIn; t.nOut = m->nOut; t.hasMatch = hasMatch ? 1 : 0;
+  t.silRow0 = b0; t.silRow1 = b1;
+  t.S = m->S; t.nIn = m->nIn; t.nOut = m->nOut; t.hasMatch = bestMatch ? 1 : 0;
   t.nLiveIn = (int32_t) bLive.size(); t.bpBytes = maxList <= 63 ? 1 : 2; t.G = best.G;
   h->maxList = maxList;
-  h->estInstrPerCell = bestCost;
+  h->estInstrPerCell = bestInstr;
   h->entPerm = best.perm;
   h->blobLog = h->blobLin;
   wide_fill_weights (m, h);
@@ -686,8 +674,8 @@ int wide_prepare (mb_machine* m) {
   MB_CUDA (cudaMemcpy (h->dLog, h->blobLog.data(), t.bytes, cudaMemcpyHostToDevice));
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   if (getenv ("MB_WIDE_VERBOSE"))
-    fprintf (stderr, "wide engine: S=%d G=%d rounds=%zu rows=%zu tables=%u bytes, est. %.0f warp-instructions per cell, live-in %d, bp %d bytes\n",
-             m->S, best.G, best.rounds.size(), best.ent.size() / best.G, t.bytes, bestCost, t.nLiveIn, t.bpBytes);
+    fprintf (stderr, "wide engine: S=%d G=%d rows=%zu (silent %u) tables=%u bytes, est. %.0f warp-instructions per cell, live-in %d, bp %d bytes\n",
+             m->S, best.G, best.rows(), b1 - b0, t.bytes, bestInstr, t.nLiveIn, t.bpBytes);
   return 0;
 }
 
