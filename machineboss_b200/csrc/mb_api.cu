@@ -262,9 +262,12 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
     if (!jit_supported (m, &why)) { set_error ("mb_set_engine(JIT): " + why); mb_machine_destroy (m); return 1; }
     if (jit_prepare (m)) { mb_machine_destroy (m); return 1; }
     m->engine = MB_ENGINE_JIT;
-  } else if (g_forceEngine == MB_ENGINE_WIDE || (g_forceEngine < 0 && wide_supported (m, &why))) {
-    if (!wide_supported (m, &why)) { set_error ("mb_set_engine(WIDE): " + why); mb_machine_destroy (m); return 1; }
-    if (wide_prepare (m)) { mb_machine_destroy (m); return 1; }
+  } else if (g_forceEngine == MB_ENGINE_WIDE || (g_forceEngine < 0 && (wide_supported (m, &why) || m->nIn == 0))) {
+    // a machine without input alphabet only ever sees batches without input sequences, which the lane
+    // engine (mb_lane.cu) sweeps whatever the number of states; the two-dimensional strip sweep needs
+    // a cell to fit in shared memory
+    if (wide_supported (m, &why)) { if (wide_prepare (m)) { mb_machine_destroy (m); return 1; } }
+    else if (m->nIn != 0) { set_error ("mb_set_engine(WIDE): " + why); mb_machine_destroy (m); return 1; }
     m->engine = MB_ENGINE_WIDE;
   }
   *out = m;
@@ -280,7 +283,7 @@ int mb_machine_update_weights (mb_machine* m, const double* logWeight) {
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
   }
-  if (m->wide && wide_update_weights (m)) return 1;
+  if ((m->wide || m->lane) && wide_update_weights (m)) return 1;
   if (m->engine == MB_ENGINE_JIT) return jit_update_weights (m);
   return 0;
 }

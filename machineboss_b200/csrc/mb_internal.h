@@ -88,6 +88,8 @@ struct mb_machine {
   void* jit = nullptr;
   // wide engine (mb_wide.cu)
   void* wide = nullptr;
+  // lane engine (mb_lane.cu): the wide engine's path for batches without input sequences
+  void* lane = nullptr;
 };
 
 struct mb_batch {
@@ -143,6 +145,14 @@ void wide_destroy (mb_machine* m);
 int wide_update_weights (mb_machine* m);
 int wide_forward (mb_machine* m, mb_batch* b, double* loglike);
 int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+
+// ---- lane engine (mb_lane.cu): a read per lane, for batches without input sequences; reached through the wide engine ----
+int lane_prepare (mb_machine* m);
+void lane_destroy (mb_machine* m);
+int lane_update_weights (mb_machine* m);
+bool lane_wanted (const mb_machine* m, const mb_batch* b);      // no input sequences, no envelopes
+int lane_forward (mb_machine* m, mb_batch* b, double* loglike);
+int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 
 // per-batch workspace (mb_api.cu)
 enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_NSLOTS };

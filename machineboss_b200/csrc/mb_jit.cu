@@ -175,6 +175,13 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
 struct JitEngine {
   Program fwd, bwd;
   int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 5, minBlocksCnt = 3;
+  // The Viterbi kernel has no shared warp frame to hold together, so it can give each lane more
+  // columns (fewer shuffles, boundary reads and loop overhead per cell): it is compiled as its own
+  // module with MB_C = CV.  The linear sweeps cannot: 32 * 8 columns under one power-of-two frame
+  // exceed the FP64 range on ordinary pairs.
+  int CV = 4, minBlocksV = 4;
+  std::string sourceV;
+  CUmodule modV = nullptr;
   std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
   std::string source;
   CUmodule mod = nullptr;
@@ -215,16 +222,24 @@ static std::string term_expr (const Slot& s, int nOut, bool forward) {
 static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program& p, bool forward, bool viterbi, const JitEngine& J) {
   const char* name = viterbi ? "mb_cell_vit" : forward ? "mb_cell_fwd" : "mb_cell_bwd";
   o << "__device__ __forceinline__ " << (viterbi ? "mb_tbword " : "void ") << name
-    << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, const double* __restrict__ E, const MBSil& P) {\n";
+    << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], const int a, const int b, const bool origin, "
+    << (viterbi ? "const bool sink, " : "") << "const double* __restrict__ E, const MBSil& P) {\n";
   if (viterbi) o << "  mb_tbword word = 0;\n";
   const int originState = forward ? 0 : m->S - 1;
+  // Viterbi: a state nothing leaves (the end state, normally) is only ever read -- as the score, and by
+  // the traceback's first step -- in the pair's last cell; everywhere else its value and pointer are
+  // dead, so they are computed under `sink` (false at compile time in the steady-state step)
+  std::vector<char> isSource ((size_t) m->S, 0);
+  for (auto& sl: p.slots) isSource[sl.other] = 1;
   for (int q = 0; q < m->S; ++q) {
     const int d = forward ? q : m->S - 1 - q;
     const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
-    if (s0 == s1) o << "  double n" << d << " = mb_neg_inf();\n";
+    const bool sinkOnly = viterbi && !isSource[d] && d != originState && s0 != s1;
+    if (s0 == s1 || sinkOnly) o << "  double n" << d << " = mb_neg_inf();\n";
+    if (sinkOnly) o << "  if (sink) {\n";
     for (int k = s0; k < s1; ++k) {
       const std::string t = term_expr (p.slots[k], m->nOut, forward);
-      if (k == s0) o << "  double n" << d << " = " << t << ";\n";
+      if (k == s0) o << (sinkOnly ? "  n" : "  double n") << d << " = " << t << ";\n";
       else if (viterbi) {
         // strict '<': the first maximum keeps the pointer (dpmatrix.defs.h:171-174); the pointer field
         // of this state is overwritten in place, one logic op under the compare's predicate
@@ -233,6 +248,7 @@ static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program&
       }
       else o << "  n" << d << " = mb_lse (n" << d << ", " << t << ");\n";
     }
+    if (sinkOnly) o << "  }\n";
     if (d == originState) o << "  if (origin) n" << d << " = 0.0;\n";
   }
   for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
@@ -384,18 +400,19 @@ bool jit_supported (const mb_machine* m, std::string* why) {
   return true;
 }
 
-static int nvrtc_compile (JitEngine& J, std::vector<char>& cubin, std::string* logOut) {
+static int nvrtc_compile (const std::string& source, const char* dumpSuffix, std::vector<char>& cubin, std::string* logOut) {
   if (!load_nvrtc()) return 1;
   nvrtcProgram prog;
-  if (g_nvrtc.CreateProgram (&prog, J.source.c_str(), "mb_jit_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { set_error ("nvrtcCreateProgram failed"); return 1; }
+  if (g_nvrtc.CreateProgram (&prog, source.c_str(), "mb_jit_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { set_error ("nvrtcCreateProgram failed"); return 1; }
   const char* opts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--ptxas-options=-v", "-default-device" };
   const nvrtcResult r = g_nvrtc.CompileProgram (prog, 5, opts);
   size_t ln = 0;
   g_nvrtc.GetProgramLogSize (prog, &ln);
   std::string log (ln, 0);
   if (ln) g_nvrtc.GetProgramLog (prog, &log[0]);
+  while (!log.empty() && log.back() == 0) log.pop_back();
   if (logOut) *logOut = log;
-  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen (d, "w"); if (f) { fputs (J.source.c_str(), f); fclose (f); } }
+  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen ((std::string (d) + dumpSuffix).c_str(), "w"); if (f) { fputs (source.c_str(), f); fclose (f); } }
   if (r != NVRTC_SUCCESS) {
     set_error ("NVRTC compilation failed:\n" + log);
     g_nvrtc.DestroyProgram (&prog);
@@ -406,18 +423,20 @@ static int nvrtc_compile (JitEngine& J, std::vector<char>& cubin, std::string* l
   cubin.resize (n);
   g_nvrtc.GetCUBIN (prog, cubin.data());
   g_nvrtc.DestroyProgram (&prog);
-  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen ((std::string (d) + ".cubin").c_str(), "wb"); if (f) { fwrite (cubin.data(), 1, n, f); fclose (f); } }
+  if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen ((std::string (d) + dumpSuffix + ".cubin").c_str(), "wb"); if (f) { fwrite (cubin.data(), 1, n, f); fclose (f); } }
   return 0;
 }
 
 static int compile (mb_machine* m, JitEngine& J) {
-  std::vector<char> cubin;
-  if (nvrtc_compile (J, cubin, nullptr) || !load_driver()) return 1;
+  std::vector<char> cubin, cubinV;
+  if (nvrtc_compile (J.source, "", cubin, nullptr) || !load_driver()) return 1;
+  if (!J.sourceV.empty() && nvrtc_compile (J.sourceV, ".viterbi.cu", cubinV, nullptr)) return 1;
   MB_CUDA (cudaFree (0));   // make sure the primary context exists and is current
   if (!cu_ok (g_drv.ModuleLoadData (&J.mod, cubin.data()), "cuModuleLoadData")) return 1;
+  if (!J.sourceV.empty() && !cu_ok (g_drv.ModuleLoadData (&J.modV, cubinV.data()), "cuModuleLoadData")) return 1;
   if (!cu_ok (g_drv.ModuleGetFunction (&J.kForward, J.mod, "mb_k_forward"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackward, J.mod, "mb_k_backward"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.modV ? J.modV : J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
@@ -504,6 +523,11 @@ static void generate (const mb_machine* m, JitEngine& J) {
   J.C = m->S <= 8 ? 4 : 2;
   if (const char* e = getenv ("MB_JIT_C")) J.C = std::max (1, std::min (8, atoi (e)));
   while (J.C * J.tbBytes > 16) J.C /= 2;
+  J.CV = J.C; J.minBlocksV = J.minBlocks;
+  if (m->S <= 8 && J.C == 4 && 8 * J.tbBytes <= 16) { J.CV = 8; J.minBlocksV = 3; }
+  if (const char* e = getenv ("MB_JIT_CV")) J.CV = std::max (1, std::min (8, atoi (e)));
+  while (J.CV * J.tbBytes > 16) J.CV /= 2;
+  if (const char* e = getenv ("MB_JIT_MINBLOCKS_V")) J.minBlocksV = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_MINBLOCKS")) J.minBlocks = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_MINBLOCKS_CNT")) J.minBlocksCnt = std::max (1, std::min (16, atoi (e)));
   if (const char* e = getenv ("MB_JIT_MINBLOCKS_LIN")) J.minBlocksLin = std::max (1, std::min (16, atoi (e)));
@@ -516,16 +540,20 @@ static void generate (const mb_machine* m, JitEngine& J) {
     if (n) { J.ctxBase[k] = J.nCtx; J.nCtx += n; }
   }
 
+  for (int pass = 0; pass < (J.CV != J.C ? 2 : 1); ++pass) {
+  const int passC = pass ? J.CV : J.C, passMinBlocks = pass ? J.minBlocksV : J.minBlocks;
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
+  if (pass) o << "#define MB_ONLY_VITERBI 1\n";
+  else if (J.CV != J.C) o << "#define MB_SKIP_VITERBI 1\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
-  o << "#define MB_S " << m->S << "\n#define MB_C " << J.C << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
+  o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
   unsigned long long liveF = 0, liveB = 0;
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << J.minBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
+  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
@@ -539,7 +567,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   gen_cell_lin (o, m, J.bwd, false);
   gen_cell_counts_lin (o, m, J);
   o << kJitSkeleton;
-  J.source = o.str();
+  (pass ? J.sourceV : J.source) = o.str();
+  }
 }
 
 // Diagnostic used by build() and the CPU tests: generate and NVRTC-compile the kernels of a machine
@@ -550,7 +579,13 @@ int jit_compile_check (const mb_machine* m, std::string* log) {
   JitEngine J;
   generate (m, J);
   std::vector<char> cubin;
-  return nvrtc_compile (J, cubin, log);
+  if (nvrtc_compile (J.source, "", cubin, log)) return 1;
+  if (!J.sourceV.empty()) {
+    std::string logV;
+    if (nvrtc_compile (J.sourceV, ".viterbi.cu", cubin, &logV)) return 1;
+    if (log) *log += "\n---- Viterbi module (MB_C = " + std::to_string (J.CV) + ") ----\n" + logV;
+  }
+  return 0;
 }
 
 int jit_prepare (mb_machine* m) {
@@ -588,6 +623,7 @@ void jit_destroy (mb_machine* m) {
   if (!m->jit) return;
   JitEngine* J = (JitEngine*) m->jit;
   if (J->mod && g_drv.ModuleUnload) g_drv.ModuleUnload (J->mod);
+  if (J->modV && g_drv.ModuleUnload) g_drv.ModuleUnload (J->modV);
   if (J->dEmitF) cudaFree (J->dEmitF);
   if (J->dEmitB) cudaFree (J->dEmitB);
   if (J->dEmitFLin) cudaFree (J->dEmitFLin);
@@ -683,7 +719,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[which], J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+             J.smemBytes[which], J.blocksPerSM[which], which == 2 ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
@@ -825,7 +861,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
-  const int W = 32 * J.C;
+  const int W = 32 * J.CV;
   // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
   double wanted = 0;
   for (int64_t k = 0; k < b->nPairs; ++k)
@@ -890,6 +926,8 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       if (!dTmp || !dTmpOff) return 1;
       MB_CUDA (cudaMemcpyAsync (dPairs, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
       MB_CUDA (cudaMemcpyAsync (dTmpOff, tmpOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+      // (a warp-per-pair walk over 32 x 32 tiles of pointers staged in shared memory was measured slower
+      // than this thread-per-pair walk with its L2 prefetch: 4.2 ms against 2.7 ms for 10 000 1 kb pairs)
       const unsigned tg = (unsigned) ((n + 63) / 64);
       jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, dTmp, dTmpOff);
       MB_CUDA (cudaGetLastError());

@@ -183,19 +183,20 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       for (int s = 0; s < MB_S; ++s)
         stageNext[s] = (hasIn && mb_live<DIR> (s) && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_ROW + s) : NI;
       // row tokens (0-based): rows 0..31 are published now, rows 32..63 at step 0, and so on one block ahead
-      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (DIR ? y[Lo - row] : y[row - 1]) - 1 : 0; };
+      // (the raw 1-based byte is kept until it is published a block later: subtracting 1 at once would make
+      // the warp wait for the global load)
+      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (int) (DIR ? y[Lo - row] : y[row - 1]) : 1; };
       __syncwarp();
-      ring[lane] = (uint8_t) rowTok (lane);
+      ring[lane] = (uint8_t) (rowTok (lane) - 1);
       int ynext = rowTok (32 + lane);
       __syncwarp();
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
-      auto step = [&] (const int t, auto steadyTag) {
-        constexpr bool STEADY = decltype (steadyTag)::value;
-        const int r = t - lane;
-        if (hasIn && (t & 31) == 0) {       // stage 32 rows of the previous strip's last column: lane q takes row t+q;
+      // every 32 steps (kept out of the step body so that the steady loop carries no block tests)
+      auto blockStart = [&] (const int t) {
+        if (hasIn) {                        // stage 32 rows of the previous strip's last column: lane q takes row t+q;
           __syncwarp();                     // the values were fetched a block ago, the next block's are fetched now
 #pragma unroll
           for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) sIn[lane * MB_ROW + s] = stageNext[s];
@@ -204,12 +205,16 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
             if (mb_live<DIR> (s)) stageNext[s] = (t + 32 + lane <= Lo) ? __ldcg (bin + (int64_t) (t + 32 + lane) * MB_ROW + s) : NI;
           __syncwarp();
         }
-        if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
+        {                                   // publish this block's row tokens, fetch the next block's
           __syncwarp();
-          ring[(t + 32 + lane) & 127] = (uint8_t) ynext;
+          ring[(t + 32 + lane) & 127] = (uint8_t) (ynext - 1);
           ynext = rowTok (t + 64 + lane);
           __syncwarp();
         }
+      };
+      auto step = [&] (const int t, auto steadyTag) {
+        constexpr bool STEADY = decltype (steadyTag)::value;
+        const int r = t - lane;
         const int tokb = tokNext;
         tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
         // left neighbour's last column at this row: a shuffle, or the staged boundary row for lane 0
@@ -258,7 +263,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               }
               mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
-              const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, !STEADY && r == Lo && col0 + c == Li, E, P);
               const int sh = 8 * MB_TBBYTES * c;
               if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
               else if (sh < 64) pack0 |= (unsigned long long) word << (sh & 63);
@@ -289,9 +294,14 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       {
         int t = 0;
         const int rampUp = min (31, nSteps);
-        for (; t < rampUp; ++t) step (t, MBBool<false>());
-        for (; t < Lo; ++t) step (t, MBBool<true>());
-        for (; t < nSteps; ++t) step (t, MBBool<false>());
+        for (; t < rampUp; ++t) { if ((t & 31) == 0) blockStart (t); step (t, MBBool<false>()); }
+        while (t < Lo) {
+          if ((t & 31) == 0) blockStart (t);
+          const int tend = min (Lo, (t | 31) + 1);
+#pragma unroll 1
+          for (; t < tend; ++t) step (t, MBBool<true>());
+        }
+        for (; t < nSteps; ++t) { if ((t & 31) == 0) blockStart (t); step (t, MBBool<false>()); }
       }
       if (MODE == 3) mb_flush_counts (cs, acc, ta, A.counts, A.idTabB, lane);
       __syncwarp();
@@ -299,11 +309,15 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   }
 }
 
+#ifndef MB_ONLY_VITERBI
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
+#endif
+#ifndef MB_SKIP_VITERBI
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).
@@ -412,20 +426,22 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         __syncwarp();
       }
       // row tokens (0-based): rows 0..31 are published now, rows 32..63 at step 0, and so on one block ahead
-      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (DIR ? y[Lo - row] : y[row - 1]) - 1 : 0; };
+      // (the raw 1-based byte is kept until it is published a block later: subtracting 1 at once would make
+      // the warp wait for the global load)
+      auto rowTok = [&] (const int row) { return (row >= 1 && row <= Lo) ? (int) (DIR ? y[Lo - row] : y[row - 1]) : 1; };
       __syncwarp();
-      ring[lane] = (uint8_t) rowTok (lane);
+      ring[lane] = (uint8_t) (rowTok (lane) - 1);
       int ynext = rowTok (32 + lane);
       __syncwarp();
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
       double stageNext[MB_S];
-      int stageNextE = ecur;
+      double stageNextE = (double) ecur;      // converted when it is used, a block after the load
 #pragma unroll
       for (int s = 0; s < MB_S; ++s)
         stageNext[s] = (hasIn && mb_live<DIR> (s) && lane < MB_RESCALE && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_ROW + s) : 0.0;
-      if (hasIn && lane < MB_RESCALE && lane <= Lo) stageNextE = (int) __ldcg (bin + (int64_t) lane * MB_ROW + MB_S);
+      if (hasIn && lane < MB_RESCALE && lane <= Lo) stageNextE = __ldcg (bin + (int64_t) lane * MB_ROW + MB_S);
       if (MODE == 3) {      // the first step's Forward block
         const unsigned* srcb = F32 + ((int64_t) (nStrips - 1 - strip) * (Lo + 32) + (Lo + 31)) * MB_FBLOCK;
 #pragma unroll
@@ -435,10 +451,9 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       const int nSteps = Lo + 32;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
-      auto step = [&] (const int t, auto steadyTag) {
-        constexpr bool STEADY = decltype (steadyTag)::value;
-        const int r = t - lane;
-        if ((t & (MB_RESCALE - 1)) == 0) {
+      // every MB_RESCALE steps (kept out of the step body so that the steady loop carries no block tests)
+      auto blockStart = [&] (const int t) {
+        {
           if (t > 0) {
             int mh = 0;
             unsigned ml = 0xffffffffu;
@@ -474,7 +489,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             __syncwarp();  // lane q < MB_RESCALE takes row t+q: fetched a block ago, the next block's are fetched now
             if (lane < MB_RESCALE) {
               double* dst = sIn + lane * MB_ROW;
-              int d = stageNextE - ecur;
+              int d = (int) stageNextE - ecur;
               const bool far = d < -900 || d > 900;
               bool any = false;
               d = max (min (d, 1000), -1023);
@@ -487,17 +502,21 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               const double* src = bin + (int64_t) rowN * MB_ROW;
 #pragma unroll
               for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) stageNext[s] = rowN <= Lo ? __ldcg (src + s) : 0.0;
-              stageNextE = rowN <= Lo ? (int) __ldcg (src + MB_S) : ecur;
+              stageNextE = rowN <= Lo ? __ldcg (src + MB_S) : (double) ecur;
             }
             __syncwarp();
           }
         }
         if ((t & 31) == 0) {                // publish this block's row tokens, fetch the next block's
           __syncwarp();
-          ring[(t + 32 + lane) & 127] = (uint8_t) ynext;
+          ring[(t + 32 + lane) & 127] = (uint8_t) (ynext - 1);
           ynext = rowTok (t + 64 + lane);
           __syncwarp();
         }
+      };
+      auto step = [&] (const int t, auto steadyTag) {
+        constexpr bool STEADY = decltype (steadyTag)::value;
+        const int r = t - lane;
         const int tokb = tokNext;
         tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
         double Lc[MB_S];
@@ -598,9 +617,14 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       {
         int t = 0;
         const int rampUp = min (31, nSteps);
-        for (; t < rampUp; ++t) step (t, MBBool<false>());
-        for (; t < Lo; ++t) step (t, MBBool<true>());
-        for (; t < nSteps; ++t) step (t, MBBool<false>());
+        for (; t < rampUp; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
+        while (t < Lo) {
+          if ((t & (MB_RESCALE - 1)) == 0) blockStart (t);
+          const int tend = min (Lo, (t | (MB_RESCALE - 1)) + 1);
+#pragma unroll 1
+          for (; t < tend; ++t) step (t, MBBool<true>());
+        }
+        for (; t < nSteps; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
       }
       suspect = __any_sync (MB_FULL, suspect);
       if (MODE == 3) mb_flush_counts_lin (csd, accd, ta, A.counts, A.idTabB, lane);
@@ -610,10 +634,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   }
 }
 
+#ifndef MB_ONLY_VITERBI
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_fstore_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<2, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<3, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
+#endif
 )MBSRC";
 
 #endif

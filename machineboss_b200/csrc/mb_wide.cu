@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(544) wide_kernel (const __grid_constant__ WPar
 // DPMatrix::traceBack (dpmatrix.defs.h:82-110) over the stored back-pointers, one thread per pair.
 // lenOut only (out == nullptr) or the path written start -> end.
 __global__ void wide_traceback_kernel (DevMachine m, DevBatch b, const int64_t* __restrict__ order, int64_t nWork,
-                                       const unsigned char* __restrict__ bp, const int64_t* __restrict__ bpOff, int bpBytes,
+                                       const unsigned char* __restrict__ bp, const int64_t* __restrict__ bpOff, int bpBytes, int laneLayout,
                                        const double* __restrict__ score, int64_t* __restrict__ lenOut, int32_t* __restrict__ out,
                                        const int64_t* __restrict__ outOff) {
   const int64_t wk = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,7 +408,8 @@ __global__ void wide_traceback_kernel (DevMachine m, DevBatch b, const int64_t* 
     int64_t i = Li, o = Lo;
     int s = S - 1;
     while (i > 0 || o > 0 || s != 0) {
-      const size_t cell = ((size_t) o * (Li + 1) + i) * S + s;
+      // wide engine: [o][i][s] per pair; lane engine (no input sequence): [o][s][read] per task of laneLayout reads
+      const size_t cell = laneLayout ? ((size_t) o * S + s) * laneLayout + (size_t) (wk % laneLayout) : ((size_t) o * (Li + 1) + i) * S + s;
       const unsigned v = bpBytes == 1 ? base[cell] : reinterpret_cast<const uint16_t*> (base)[cell];
       if (v == none) break;      // cannot happen on a finite path
       const unsigned kind = v >> kb, idx = v & ((1u << kb) - 1);
@@ -426,7 +427,13 @@ __global__ void wide_traceback_kernel (DevMachine m, DevBatch b, const int64_t* 
   if (!out) lenOut[wk] = n;
 }
 
-// ---------------------------------------------------------------------------------------------
+int wide_traceback_launch (mb_machine* m, mb_batch* b, const int64_t* dOrder, int64_t nWork, const unsigned char* dBp, const int64_t* dBpOff,
+                           int bpBytes, int laneLayout, const double* dScore, int64_t* dLen, int32_t* dOut, const int64_t* dOutOff) {
+  const unsigned tg = (unsigned) ((nWork + 31) / 32);
+  wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder, nWork, dBp, dBpOff, bpBytes, laneLayout, dScore, dLen, dOut, dOutOff);
+  MB_CUDA (cudaGetLastError());
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -600,6 +607,7 @@ static void wide_fill_weights (const mb_machine* m, WHost* h) {
 }
 
 void wide_destroy (mb_machine* m) {
+  lane_destroy (m);
   WHost* h = wh (m);
   if (!h) return;
   if (h->dLin) cudaFree (h->dLin);
@@ -609,6 +617,7 @@ void wide_destroy (mb_machine* m) {
 }
 
 int wide_update_weights (mb_machine* m) {
+  if (lane_update_weights (m)) return 1;
   WHost* h = wh (m);
   if (!h) return 0;
   wide_fill_weights (m, h);
@@ -790,6 +799,11 @@ static int wide_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& 
 int wide_forward (mb_machine* m, mb_batch* b, double* loglike) {
   b->lastRedo = 0;
   if (b->nPairs == 0) return 0;
+  if (lane_wanted (m, b)) {      // no input sequences: a read per lane (mb_lane.cu)
+    if (!m->lane && lane_prepare (m)) return 1;
+    return lane_forward (m, b, loglike);
+  }
+  if (!m->wide) return generic_forward (m, b, loglike, false);      // too large for the two-dimensional strip sweep
   WHost* h = wh (m);
   const std::vector<int64_t> order = cost_order (b, nullptr);
   WBuf dRes, dFlag;
@@ -820,6 +834,11 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathStart.clear();
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
+  if (lane_wanted (m, b)) {
+    if (!m->lane && lane_prepare (m)) return 1;
+    return lane_viterbi (m, b, score, pathLen);
+  }
+  if (!m->wide) return generic_viterbi (m, b, score, pathLen);
   WHost* h = wh (m);
   const bool trace = pathLen != nullptr;
   const std::vector<int64_t> order = cost_order (b, nullptr);
@@ -862,7 +881,7 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (wide_launch<OP_MAX> (m, b, chunk, dRes.as<double>(), nullptr, dBp.as<unsigned char>(), dBpOff.as<int64_t>())) return 1;
     const int64_t nWork = (int64_t) chunk.size();
     const unsigned tg = (unsigned) ((nWork + 31) / 32);
-    wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOff.as<int64_t>(), h->t.bpBytes,
+    wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOff.as<int64_t>(), h->t.bpBytes, 0,
                                                       dRes.as<double>(), dLen.as<int64_t>(), nullptr, nullptr);
     MB_CUDA (cudaGetLastError());
     std::vector<int64_t> len (chunk.size()), off (chunk.size());
@@ -877,7 +896,7 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (ensure_paths (b, packed)) return 1;
     if (dOutOff.alloc (off.size() * 8)) return 1;
     MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, b->stream));
-    wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOff.as<int64_t>(), h->t.bpBytes,
+    wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOff.as<int64_t>(), h->t.bpBytes, 0,
                                                       dRes.as<double>(), dLen.as<int64_t>(), b->dPaths, dOutOff.as<int64_t>());
     MB_CUDA (cudaGetLastError());
     launches += 3;

@@ -61,7 +61,18 @@ def test_golden(name, engine):
         ll = capi.forward(m, b)
         for k, p in enumerate(ref):
             want = gnum(p.get("rolling", p.get("forward")))
-            assert close(ll[k], want), (name, k, ll[k], want)
+            if close(ll[k], want):
+                continue
+            # The reference's log-sum-exp table returns 0 for x >= 10 (logsumexp.h:52): a sum over n terms can
+            # come out low by up to log1p(n e^-10) per cell (0.1 for the 2432 sources of the composed profile's
+            # end state), which exceeds 1e-4 relative on short reads.  The device sums are exact: they must
+            # agree with the exact-sum oracle, and the reference may only be lower, by at most that bound.
+            x, y = pairs[k]
+            exact = Oracle(fm).forward(x, y, mode=LSE_EXACT)
+            fan_in = int(np.bincount(fm.dst, minlength=fm.n_states).max())
+            bound = (len(x) + len(y) + 1) * math.log1p(fan_in * math.exp(-10.0))
+            assert abs(ll[k] - exact) <= 1e-6 * max(1.0, abs(exact)), (name, k, ll[k], exact)
+            assert -1e-9 <= exact - want <= bound, (name, k, exact, want, bound)
     if any("backward" in p for p in ref):
         bl = capi.backward(m, b)
         for k, p in enumerate(ref):
@@ -146,6 +157,34 @@ def test_wide_engine_multi_strip_composite():
         v, p = orc.viterbi(x, y)
         assert sc[k] == v and sc2[k] == v, (k, sc[k], v)
         assert paths[k].tolist() == p.tolist(), k
+
+
+@pytest.mark.parametrize("reads_per_lane", [1, 2, 4])
+def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
+    """Batches without input sequences go through the lane engine (a read per lane, mb_lane.cu): every
+    reads-per-lane variant, ragged read lengths filling more than one task, against the oracle."""
+    capi = _capi()
+    monkeypatch.setenv("MB_LANE_R", str(reads_per_lane))
+    for name, n_reads, max_len in (("unitindel", 150, 12), ("hmmer_pf00516", 140, 9)):
+        fm = FlatMachine.from_json(load_golden(name)["machine"])
+        lens = [(7 * k + 3) % (max_len + 1) for k in range(n_reads)]
+        pairs = [(np.zeros(0, np.uint8), synth_tokens(21, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
+        orc = Oracle(fm)
+        m = make_machine(capi, fm, 2)
+        b = capi.Batch(pairs)
+        ll = capi.forward(m, b)
+        sc, paths = capi.viterbi(m, b)
+        sc2 = capi.viterbi(m, b, paths=False)
+        for k in list(range(0, n_reads, 13)) + [n_reads - 1]:
+            x, y = pairs[k]
+            f = orc.forward(x, y)
+            assert close(ll[k], f), (name, k, ll[k], f)
+            v, p = orc.viterbi(x, y)
+            assert sc[k] == v and sc2[k] == v, (name, k, sc[k], v)
+            if math.isfinite(v):
+                assert paths[k].tolist() == p.tolist(), (name, k)
+            else:
+                assert len(paths[k]) == 0
 
 
 def test_wide_engine_log_domain_rerun():
