@@ -175,10 +175,11 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
 struct JitEngine {
   Program fwd, bwd;
   int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 5, minBlocksCnt = 3;
-  // The Viterbi kernel has no shared warp frame to hold together, so it can give each lane more
-  // columns (fewer shuffles, boundary reads and loop overhead per cell): it is compiled as its own
-  // module with MB_C = CV.  The linear sweeps cannot: 32 * 8 columns under one power-of-two frame
-  // exceed the FP64 range on ordinary pairs.
+  // The score-only kernels (Viterbi, linear Forward / Backward) are compiled as a second module with
+  // MB_C = CV columns per lane: fewer shuffles, boundary reads and loop overhead per cell (Viterbi fill
+  // 26.5 -> 15.8 ms for 10 000 1 kb pairs).  256 columns under ONE power-of-two frame would exceed the
+  // FP64 range on ordinary pairs, so in that module the linear sweeps keep a frame per lane
+  // (MB_LANE_FRAMES); the E-step kernels, whose stored Forward blocks share a frame per warp, stay at C.
   int CV = 4, minBlocksV = 4;
   std::string sourceV;
   CUmodule modV = nullptr;
@@ -439,8 +440,8 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.modV ? J.modV : J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
-      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.modV ? J.modV : J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.modV ? J.modV : J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
   int dev = 0;
@@ -544,7 +545,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   const int passC = pass ? J.CV : J.C, passMinBlocks = pass ? J.minBlocksV : J.minBlocks;
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
-  if (pass) o << "#define MB_ONLY_VITERBI 1\n";
+  if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n";
   else if (J.CV != J.C) o << "#define MB_SKIP_VITERBI 1\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
@@ -553,7 +554,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << J.minBlocksLin << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
+  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << (pass ? J.minBlocksV : J.minBlocksLin) << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
@@ -719,7 +720,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[which], which == 2 ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+             J.smemBytes[which], J.blocksPerSM[which], (which == 2 || which == 5 || which == 6) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
@@ -759,60 +760,106 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
 }
 
 // DPMatrix::traceBack (dpmatrix.defs.h:82-110) over the packed back-pointers written by
-// mb_k_viterbi: one thread per pair walks from (Li, Lo, end state) to (0, 0, start state) and writes
-// the transition ids end-aligned into the pair's scratch slot (capacity = the longest possible
-// path), so that they read start -> end; pack_paths_kernel then copies them into the packed result.
-// The walk is a chain of dependent loads; the pointers a few rows up the diagonal are prefetched
-// into L2 because that is where the path most likely goes.
-__global__ void jit_traceback_kernel (TbPlan p, DevBatch b, const int64_t* __restrict__ pairs, int64_t nPairsHere,
+// mb_k_viterbi, in two passes.
+//   1. jit_traceback_kernel: one thread per pair walks from (Li, Lo, end state) to (0, 0, start
+//      state).  The walk is a chain of dependent loads, so it does as little as possible per step:
+//      the pointer word of the cell is fetched only when the path moves to another cell (the silent
+//      steps of a cell reuse it), the tables it decodes with sit in shared memory, and all it
+//      records is the transition GROUP it took, one byte, end-aligned in the pair's scratch slot so
+//      that the record reads start -> end.  The pointers a few rows up the diagonal are prefetched
+//      into L2 because that is where the path most likely goes.
+//   2. jit_path_ids_kernel: one warp per pair turns the groups into transition ids, all steps in
+//      parallel: a warp scan of the groups' (input, output) moves gives the cell of every step, the
+//      cell gives the tokens, group + tokens give the id (the group's token-indexed id table).
+#define TB_MAXS 64
+#define TB_MAXSLOTS 256
+__global__ void __launch_bounds__(64) jit_traceback_kernel (TbPlan p, int nSlots, DevBatch b, const int64_t* __restrict__ pairs, int64_t nPairsHere,
                                       const uint8_t* __restrict__ tb, const int64_t* __restrict__ tbOff,
                                       const double* __restrict__ score, int64_t* __restrict__ len,
-                                      int32_t* __restrict__ tmp, const int64_t* __restrict__ tmpOff) {
+                                      uint8_t* __restrict__ tmp, const int64_t* __restrict__ tmpOff) {
+  __shared__ unsigned perState[TB_MAXS + 1];      // shift | bits << 8 | first slot << 16
+  __shared__ unsigned char slotMove[TB_MAXSLOTS], slotOther[TB_MAXSLOTS];      // moves: bit 0 input, bit 1 output
+  for (int q = threadIdx.x; q <= p.S; q += blockDim.x)
+    perState[q] = (q < p.S ? (unsigned) p.shift[q] | ((unsigned) p.bits[q] << 8) : 0u) | ((unsigned) p.stateSlot0[q] << 16);
+  for (int q = threadIdx.x; q < nSlots; q += blockDim.x) {
+    const int type = p.slotType[q];
+    slotMove[q] = (unsigned char) (((type == T_MATCH || type == T_DELETE) ? 1 : 0) | ((type == T_MATCH || type == T_INSERT) ? 2 : 0));
+    slotOther[q] = (unsigned char) p.slotOther[q];
+  }
+  __syncthreads();
   const int64_t slot = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nPairsHere) return;
   const int64_t k = pairs[slot];
-  const uint8_t* x = b.x + b.xOff[k];
-  const uint8_t* y = b.y + b.yOff[k];
   const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
   const int64_t pitch = ((Li + p.W) / p.W) * p.W;
   const uint8_t* base = tb + tbOff[k];
-  int32_t* out = tmp + tmpOff[slot + 1];     // one past the end of this pair's slot
+  uint8_t* out = tmp + tmpOff[slot + 1];     // one past the end of this pair's slot
   int64_t n = 0;
   if (score[k] > -INFINITY) {
     int64_t i = Li, o = Lo;
     int s = p.S - 1;
+    auto fetch = [&] (int64_t ii, int64_t oo) {
+      const uint8_t* wp = base + (oo * pitch + ii) * p.tbBytes;
+      if (ii >= 8 && oo >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - (8 * pitch + 8) * p.tbBytes));
+      unsigned long long w = 0;
+      for (int q = 0; q < p.tbBytes; ++q) w |= (unsigned long long) wp[q] << (8 * q);
+      return w;
+    };
+    unsigned long long word = fetch (i, o);
     while (i > 0 || o > 0 || s != 0) {
-      const uint8_t* wp = base + (o * pitch + i) * p.tbBytes;
-      if (i >= 8 && o >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - (8 * pitch + 8) * p.tbBytes));
-      unsigned long long word = 0;
-      for (int q = 0; q < p.tbBytes; ++q) word |= (unsigned long long) wp[q] << (8 * q);
-      const int ptr = (int) ((word >> p.shift[s]) & ((1ull << p.bits[s]) - 1ull));
-      const int sl = p.stateSlot0[s] + ptr;
-      if (sl >= p.stateSlot0[s + 1]) break;    // corrupt pointer: cannot happen on a finite path
-      const int type = p.slotType[sl];
-      const int a = i ? x[i - 1] - 1 : 0, c = o ? y[o - 1] - 1 : 0;
-      const int li = type == T_MATCH ? a * p.nOut + c : type == T_DELETE ? a : type == T_INSERT ? c : 0;
+      const unsigned ps = perState[s];
+      const int ptr = (int) ((word >> (ps & 0xffu)) & ((1ull << ((ps >> 8) & 0xffu)) - 1ull));
+      const unsigned sl = (ps >> 16) + (unsigned) ptr;
+      if (sl >= (perState[s + 1] >> 16)) break;    // corrupt pointer: cannot happen on a finite path
       ++n;
-      out[-n] = p.idTab[p.slotIdOff[sl] + li];
-      if (type == T_MATCH || type == T_DELETE) --i;
-      if (type == T_MATCH || type == T_INSERT) --o;
-      s = p.slotOther[sl];
-      if (i < 0 || o < 0) break;
+      out[-n] = (uint8_t) sl;
+      const unsigned mv = slotMove[sl];
+      s = slotOther[sl];
+      if (mv) {
+        i -= mv & 1u; o -= mv >> 1;
+        if (i < 0 || o < 0) break;
+        word = fetch (i, o);
+      }
     }
   }
   len[slot] = n;
 }
 
-// one warp per pair: copy its path from the end of its scratch slot to its place in the packed result
-__global__ void pack_paths_kernel (int64_t nPairsHere, const int64_t* __restrict__ len, const int32_t* __restrict__ tmp,
-                                   const int64_t* __restrict__ tmpOff, int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+// pass 2: one warp per pair; step q of the path (start -> end) took group g[q]; the cell it arrives in is
+// the inclusive prefix sum of the groups' moves; its id is idTab[idOff[g] + label (tokens of that cell)]
+__global__ void __launch_bounds__(256) jit_path_ids_kernel (TbPlan p, int nSlots, DevBatch b, const int64_t* __restrict__ pairs, int64_t nPairsHere,
+                                     const int64_t* __restrict__ len, const uint8_t* __restrict__ tmp, const int64_t* __restrict__ tmpOff,
+                                     int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+  __shared__ int slotIdOff[TB_MAXSLOTS];
+  __shared__ unsigned char slotType[TB_MAXSLOTS];
+  for (int q = threadIdx.x; q < nSlots; q += blockDim.x) { slotIdOff[q] = p.slotIdOff[q]; slotType[q] = (unsigned char) p.slotType[q]; }
+  __syncthreads();
   const int64_t slot = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slot >= nPairsHere) return;
+  const int64_t k = pairs[slot];
+  const uint8_t* x = b.x + b.xOff[k];
+  const uint8_t* y = b.y + b.yOff[k];
   const int64_t n = len[slot];
-  const int32_t* src = tmp + tmpOff[slot + 1] - n;
+  const uint8_t* src = tmp + tmpOff[slot + 1] - n;
   int32_t* dst = out + outOff[slot];
-  for (int64_t q = lane; q < n; q += 32) dst[q] = src[q];
+  int ci = 0, co = 0;      // cell reached before this chunk of 32 steps
+  for (int64_t q0 = 0; q0 < n; q0 += 32) {
+    const int64_t q = q0 + lane;
+    const int g = q < n ? src[q] : 0;
+    const int type = q < n ? slotType[g] : T_SILENT;
+    int mv = ((type == T_MATCH || type == T_DELETE) ? 1 : 0) | ((type == T_MATCH || type == T_INSERT) ? 0x10000 : 0);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync (0xffffffffu, mv, d); if (lane >= d) mv += up; }
+    const int i = ci + (mv & 0xffff), o = co + (mv >> 16);
+    if (q < n) {
+      const int a = i ? x[i - 1] - 1 : 0, c = o ? y[o - 1] - 1 : 0;
+      const int li = type == T_MATCH ? a * p.nOut + c : type == T_DELETE ? a : type == T_INSERT ? c : 0;
+      dst[q] = p.idTab[slotIdOff[g] + li];
+    }
+    const int tot = __shfl_sync (0xffffffffu, mv, 31);
+    ci += tot & 0xffff; co += tot >> 16;
+  }
 }
 
 static int ensure_paths (mb_batch* b, int64_t need) {
@@ -921,15 +968,13 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
         const int64_t k = chunks[c][q];
         tmpOff[q + 1] = tmpOff[q] + ((b->xOff[k + 1] - b->xOff[k]) + (b->yOff[k + 1] - b->yOff[k]) + 1) * depth;
       }
-      int32_t* dTmp = (int32_t*) ws_reserve (b, WS_PATHTMP, (size_t) tmpOff[n] * 4);
+      uint8_t* dTmp = (uint8_t*) ws_reserve (b, WS_PATHTMP, (size_t) tmpOff[n]);
       int64_t* dTmpOff = (int64_t*) ws_reserve (b, WS_PATHTMPOFF, (n + 1) * 8);
       if (!dTmp || !dTmpOff) return 1;
       MB_CUDA (cudaMemcpyAsync (dPairs, chunks[c].data(), n * 8, cudaMemcpyHostToDevice, b->stream));
       MB_CUDA (cudaMemcpyAsync (dTmpOff, tmpOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, b->stream));
-      // (a warp-per-pair walk over 32 x 32 tiles of pointers staged in shared memory was measured slower
-      // than this thread-per-pair walk with its L2 prefetch: 4.2 ms against 2.7 ms for 10 000 1 kb pairs)
       const unsigned tg = (unsigned) ((n + 63) / 64);
-      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, dTmp, dTmpOff);
+      jit_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, (int) nSlots, b->dev, dPairs, (int64_t) n, dTb, dTbOff, dRes, dLen, dTmp, dTmpOff);
       MB_CUDA (cudaGetLastError());
       std::vector<int64_t> len (n), off (n);
       MB_CUDA (cudaMemcpyAsync (len.data(), dLen, n * 8, cudaMemcpyDeviceToHost, b->stream));
@@ -942,7 +987,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       }
       if (ensure_paths (b, packed)) return 1;
       MB_CUDA (cudaMemcpyAsync (dOutOff, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
-      pack_paths_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, b->stream>>> ((int64_t) n, dLen, dTmp, dTmpOff, b->dPaths, dOutOff);
+      jit_path_ids_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, b->stream>>> (tp, (int) nSlots, b->dev, dPairs, (int64_t) n, dLen, dTmp, dTmpOff, b->dPaths, dOutOff);
       MB_CUDA (cudaGetLastError());
       launches += 2;
     }

@@ -309,7 +309,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   }
 }
 
-#ifndef MB_ONLY_VITERBI
+#ifndef MB_SCORE_MODULE
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_forward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_backward (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<0, 1> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_fstore (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<2, 0> (P, A); }
@@ -346,6 +346,11 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_vite
 // term = B(dest) * w feeds the Backward sum and, times F(src) * 2^(eF + eB) / Z, the group's count.
 template<int MODE, int DIR>
 __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
+#ifdef MB_LANE_FRAMES
+  constexpr bool LF = MODE == 0;
+#else
+  constexpr bool LF = false;
+#endif
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
   const int NE = MBDir<DIR>::NE;
@@ -434,8 +439,13 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       int ynext = rowTok (32 + lane);
       __syncwarp();
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
-      // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row
+      // frame: true value = stored value * 2^ecur; a strip starts in the frame of its first boundary row.
+      // LF (score-only sweeps of the wide-lane module): every lane keeps its OWN frame, so that the spread
+      // check spans only the lane's columns and the strip can be 256 columns wide; the left neighbour's
+      // values then arrive through the exact power-of-two factor gl = 2^(its frame - mine), refreshed
+      // whenever the lanes renormalise.
       int ecur = hasIn ? (int) __ldcg (bin + MB_S) : 0;
+      double gl = 1.0;
       double stageNext[MB_S];
       double stageNextE = (double) ecur;      // converted when it is used, a block after the load
 #pragma unroll
@@ -465,8 +475,10 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
 #pragma unroll
               for (int c = 0; c < MB_C; ++c) { const int g = __double2hiint (U[c][s]); mh = max (mh, g); ml = min (ml, (unsigned) (g - 1)); }
             }
-            mh = __reduce_max_sync (MB_FULL, mh);
-            ml = __reduce_min_sync (MB_FULL, ml);
+            if (!LF) {
+              mh = __reduce_max_sync (MB_FULL, mh);
+              ml = __reduce_min_sync (MB_FULL, ml);
+            }
             if (mh >= 0x00100000) {
               const int ex = mh >> 20;
               const int shift = min (ex - 1023, 1000);
@@ -483,13 +495,28 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               }
               if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
             }
+            if (LF) {
+              // a lane with nothing of its own yet adopts the frame of what is about to reach it (lane 0: the
+              // staged boundary row of this step); then every lane learns its left neighbour's frame
+              const bool nz = mh >= 0x00100000;
+              int eL = __shfl_up_sync (MB_FULL, ecur, 1);
+              if (lane == 0) eL = hasIn ? (int) stageNextE : ecur;
+              if (!nz) ecur = eL;
+              eL = __shfl_up_sync (MB_FULL, ecur, 1);
+              const bool leftNz = __shfl_up_sync (MB_FULL, (int) nz, 1) != 0;
+              int d = lane ? eL - ecur : 0;
+              if (leftNz && (d < -900 || d > 900)) suspect = 1;
+              d = max (min (d, 1000), -1022);
+              gl = __hiloint2double ((1023 + d) << 20, 0);
+            }
           }
           if (MODE == 2 && lane == 0) ef[strip * nBlk + t / MB_RESCALE] = ecur;
           if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame;
+            const int e0 = LF ? __shfl_sync (MB_FULL, ecur, 0) : ecur;      // (lane 0's frame: it is the one that reads them)
             __syncwarp();  // lane q < MB_RESCALE takes row t+q: fetched a block ago, the next block's are fetched now
             if (lane < MB_RESCALE) {
               double* dst = sIn + lane * MB_ROW;
-              int d = (int) stageNextE - ecur;
+              int d = (int) stageNextE - e0;
               const bool far = d < -900 || d > 900;
               bool any = false;
               d = max (min (d, 1000), -1023);
@@ -502,7 +529,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               const double* src = bin + (int64_t) rowN * MB_ROW;
 #pragma unroll
               for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) stageNext[s] = rowN <= Lo ? __ldcg (src + s) : 0.0;
-              stageNextE = rowN <= Lo ? __ldcg (src + MB_S) : (double) ecur;
+              stageNextE = rowN <= Lo ? __ldcg (src + MB_S) : (double) e0;
             }
             __syncwarp();
           }
@@ -525,7 +552,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           if (mb_live<DIR> (s)) {
             const double fromLane = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
             const double fromStrip = sIn[(t & (MB_RESCALE - 1)) * MB_ROW + s];
-            Lc[s] = lane ? fromLane : fromStrip;
+            Lc[s] = lane ? (LF ? fromLane * gl : fromLane) : fromStrip;
           } else Lc[s] = 0.0;
         }
         // Forward block of this step.  MODE 2 writes it.  MODE 3 reads the mirrored one: it was copied
@@ -634,11 +661,13 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   }
 }
 
-#ifndef MB_ONLY_VITERBI
+#ifndef MB_SKIP_VITERBI
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
+#endif
+#ifndef MB_SCORE_MODULE
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_fstore_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<2, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<3, 1> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
 #endif
 )MBSRC";
 

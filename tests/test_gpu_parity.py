@@ -45,6 +45,20 @@ def close(a, b, rel=REL):
     return abs(a - b) <= rel * max(1.0, abs(b))
 
 
+def forward_agrees(fm, x, y, got, want):
+    """got (device) against want (the reference's table-based value).  Within 1e-4 relative, or, on machines
+    with a large fan-in: the reference's log-sum-exp table returns 0 for x >= 10 (logsumexp.h:52), so a sum
+    over n terms can come out low by up to log1p(n e^-10) per cell (0.1 for the 2432 sources of the composed
+    profile's end state), which exceeds 1e-4 relative on short reads.  The device sums are exact: they must
+    then agree with the exact-sum oracle to 1e-6, and the reference may only be lower, by at most that bound."""
+    if close(got, want):
+        return True
+    exact = Oracle(fm).forward(x, y, mode=LSE_EXACT)
+    fan_in = int(np.bincount(fm.dst, minlength=fm.n_states).max())
+    bound = (len(x) + len(y) + 1) * math.log1p(fan_in * math.exp(-10.0))
+    return abs(got - exact) <= 1e-6 * max(1.0, abs(exact)) and -1e-6 <= exact - want <= bound
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", golden_names())
 def test_golden(name, engine):
@@ -61,18 +75,7 @@ def test_golden(name, engine):
         ll = capi.forward(m, b)
         for k, p in enumerate(ref):
             want = gnum(p.get("rolling", p.get("forward")))
-            if close(ll[k], want):
-                continue
-            # The reference's log-sum-exp table returns 0 for x >= 10 (logsumexp.h:52): a sum over n terms can
-            # come out low by up to log1p(n e^-10) per cell (0.1 for the 2432 sources of the composed profile's
-            # end state), which exceeds 1e-4 relative on short reads.  The device sums are exact: they must
-            # agree with the exact-sum oracle, and the reference may only be lower, by at most that bound.
-            x, y = pairs[k]
-            exact = Oracle(fm).forward(x, y, mode=LSE_EXACT)
-            fan_in = int(np.bincount(fm.dst, minlength=fm.n_states).max())
-            bound = (len(x) + len(y) + 1) * math.log1p(fan_in * math.exp(-10.0))
-            assert abs(ll[k] - exact) <= 1e-6 * max(1.0, abs(exact)), (name, k, ll[k], exact)
-            assert -1e-9 <= exact - want <= bound, (name, k, exact, want, bound)
+            assert forward_agrees(fm, pairs[k][0], pairs[k][1], ll[k], want), (name, k, ll[k], want)
     if any("backward" in p for p in ref):
         bl = capi.backward(m, b)
         for k, p in enumerate(ref):
@@ -178,7 +181,7 @@ def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
         for k in list(range(0, n_reads, 13)) + [n_reads - 1]:
             x, y = pairs[k]
             f = orc.forward(x, y)
-            assert close(ll[k], f), (name, k, ll[k], f)
+            assert forward_agrees(fm, x, y, ll[k], f), (name, k, ll[k], f)
             v, p = orc.viterbi(x, y)
             assert sc[k] == v and sc2[k] == v, (name, k, sc[k], v)
             if math.isfinite(v):

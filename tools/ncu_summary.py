@@ -48,10 +48,10 @@ def num(uv):
 
 
 summary = {"round": rnd, "kernels": {}}
-for rep in sorted(glob.glob(os.path.join(OUT, "prof_mb_k_*.ncu-rep"))):
+for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
     m = raw(rep)
     name = os.path.basename(rep)[5:-8]
-    k = {}
+    k = {"kernel_name": m.get("Kernel Name", ("", ""))[1] if "Kernel Name" in m else name}
     for key, metric in KEYS.items():
         if metric in m:
             k[key] = num(m[metric])
@@ -90,7 +90,7 @@ with open(os.path.join(REPO, "profiles", rnd + "_ncu_summary.md"), "w") as f:
             k["dram_traffic_bytes"] / 1e9, k.get("threads_per_inst", 0),
             ", ".join("%s %.2f" % kv for kv in k["top_stalls_per_issue"].items())))
     if "launch_list" in summary:
-        f.write("\nLaunch list of `bench.py --pairs 4736 --steps 2 --warmup 1` (cold-cache, serialised: compare shares):\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        f.write("\nLaunch list of `bench.py --steps 2 --warmup 1 --em-pairs 2048` (10 000 pairs per step; cold-cache, serialised: compare shares):\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for nm, v in summary["launch_list"].items():
             f.write("| %s | %d | %.2f | %.3f |\n" % (nm, v["launches"], v["total_ms"], v["share"]))
 print(json.dumps(summary)[:1500])

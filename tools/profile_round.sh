@@ -3,14 +3,27 @@
 # command, and one `ncu --set full` capture per hot kernel.  Outputs go to gpurun_out/ (scratch);
 # tools/ncu_summary.py turns the reports into the summaries committed under profiles/.
 set -u
+cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
+rm -f gpurun_out/prof_*.ncu-rep
 export MB_JIT_DUMP=gpurun_out/mb_jit_kernels.cu
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 400 gpurun_out/bench.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --pairs 4736 --steps 2 --warmup 1 --no-cpu-baseline --em-pairs 2368 > gpurun_out/ncu_launches_run.log 2>&1
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+unset MB_JIT_DUMP
+# the launch list of the default command (10 000 pairs per step; the E-step leg on 2048)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --em-pairs 2048 > gpurun_out/ncu_launches_run.log 2>&1
+# full captures at the bench's own size, so that dram bytes per launch are the bench's
 for k in mb_k_forward_lin mb_k_viterbi mb_k_fstore_lin mb_k_bcounts_lin; do
-  ncu --set full --clock-control none --import-source on -k regex:^${k}\$ -c 1 -o gpurun_out/prof_${k} \
-      python bench.py --pairs 4736 --steps 1 --warmup 0 --no-cpu-baseline --em-pairs 2368 > gpurun_out/ncu_${k}_run.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^${k}\$ -c 1 -o gpurun_out/prof_${k} \
+      python bench.py --steps 1 --warmup 0 --no-cpu-baseline --em-pairs 2048 > gpurun_out/ncu_${k}_run.log 2>&1
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:jit_traceback_kernel -c 1 -o gpurun_out/prof_jit_traceback_kernel \
+    python bench.py --steps 1 --warmup 0 --no-cpu-baseline --em-pairs 256 > gpurun_out/ncu_tb_run.log 2>&1
+# the engines of the other configs: the wide strip sweep (config 4 machine) and the lane sweep (config 5 machine)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wide_kernel -c 1 -o gpurun_out/prof_wide_kernel_forward \
+    python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 148 --li 300 --lo 1000 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_wide_run.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lane_kernel -c 1 -o gpurun_out/prof_lane_kernel_forward \
+    python tools/bench_wide.py --machine hmmer_pf00516 --pairs 65536 --li 0 --lo 100 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_lane_run.log 2>&1
 ls -la gpurun_out/*.ncu-rep
