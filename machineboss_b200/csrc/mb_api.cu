@@ -111,6 +111,44 @@ void* ws_reserve (mb_batch* b, int slot, size_t bytes) {
   return p;
 }
 
+// pooled allocation for a batch's own buffers (tokens, packed paths): same pool as the workspace
+static void* pooled_alloc (int device, size_t bytes, size_t* got) {
+  bytes = (std::max<size_t> (bytes, 8) + 255) & ~(size_t) 255;
+  void* p = pool_take (device, bytes, got);
+  if (p) return p;
+  *got = bytes;
+  cudaError_t e = cudaMalloc (&p, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); pool_trim (device, 0); e = cudaMalloc (&p, bytes); }
+  if (!cuda_ok (e, "cudaMalloc")) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+static void pooled_free (int device, void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes <= kPoolLimitBytes / 2) {
+    { std::lock_guard<std::mutex> lock (g_poolMutex); g_pool.push_back (PoolBlock { p, bytes, device }); }
+    pool_trim (device, kPoolLimitBytes);
+  } else cudaFree (p);
+}
+
+// room for `need` packed path entries in b->dPaths, keeping what is already there (chunked tracebacks append)
+int paths_reserve (mb_batch* b, int64_t need) {
+  if (need <= b->pathsCapacity) return 0;
+  const int64_t want = std::max<int64_t> (need, 2 * b->pathsCapacity);
+  size_t got = 0;
+  int32_t* p = (int32_t*) pooled_alloc (b->device, (size_t) want * 4, &got);
+  if (!p) return 1;
+  if (b->dPaths) {
+    MB_CUDA (cudaMemcpyAsync (p, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    pooled_free (b->device, b->dPaths, b->pathsBytes);
+  }
+  b->dPaths = p;
+  b->pathsBytes = got;
+  b->pathsCapacity = (int64_t) (got / 4);
+  return 0;
+}
+
 // Stable counting sort of the transitions into token-indexed lists (see DevCsr).
 static void build_csr (const mb_machine* m, bool incoming, HostCsr& c) {
   const int64_t T = m->T;
@@ -325,10 +363,15 @@ int mb_batch_create (mb_batch** out, int64_t nPairs, const uint8_t* inTokens, co
   if (!cuda_ok (cudaSetDevice (b->device), "cudaSetDevice")) return fail();
   if (!cuda_ok (cudaStreamCreateWithFlags (&b->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail();
   if (!cuda_ok (cudaEventCreate (&b->evStart), "cudaEventCreate") || !cuda_ok (cudaEventCreate (&b->evStop), "cudaEventCreate")) return fail();
-  // 16 bytes of slack so kernels may read whole words past the last token
-  if (!cuda_ok (cudaMalloc (&b->dX, nx + 16), "cudaMalloc") || !cuda_ok (cudaMalloc (&b->dY, ny + 16), "cudaMalloc")
-      || !cuda_ok (cudaMalloc (&b->dXOff, (size_t) (nPairs + 1) * 8), "cudaMalloc") || !cuda_ok (cudaMalloc (&b->dYOff, (size_t) (nPairs + 1) * 8), "cudaMalloc"))
-    return fail();
+  // one pooled block: offsets, then the tokens with 16 bytes of slack each so kernels may read whole words past the last token
+  {
+    const size_t offB = ((size_t) (nPairs + 1) * 8 + 255) & ~(size_t) 255, xB = (nx + 16 + 255) & ~(size_t) 255, yB = (ny + 16 + 255) & ~(size_t) 255;
+    char* blk = (char*) pooled_alloc (b->device, 2 * offB + xB + yB, &b->tokBytes);
+    if (!blk) return fail();
+    b->dTokBlock = blk;
+    b->dXOff = (int64_t*) blk; b->dYOff = (int64_t*) (blk + offB);
+    b->dX = (uint8_t*) (blk + 2 * offB); b->dY = (uint8_t*) (blk + 2 * offB + xB);
+  }
   if (!cuda_ok (cudaMemsetAsync (b->dX, 1, nx + 16, b->stream), "memset") || !cuda_ok (cudaMemsetAsync (b->dY, 1, ny + 16, b->stream), "memset")) return fail();
   if (nx && !cuda_ok (cudaMemcpyAsync (b->dX, inTokens + x0, nx, cudaMemcpyHostToDevice, b->stream), "H2D tokens")) return fail();
   if (ny && !cuda_ok (cudaMemcpyAsync (b->dY, outTokens + y0, ny, cudaMemcpyHostToDevice, b->stream), "H2D tokens")) return fail();
@@ -388,11 +431,8 @@ void mb_batch_destroy (mb_batch* b) {
   if (!b) return;
   cudaSetDevice (b->device);
   if (b->dEnv) cudaFree (b->dEnv);
-  if (b->dX) cudaFree (b->dX);
-  if (b->dY) cudaFree (b->dY);
-  if (b->dXOff) cudaFree (b->dXOff);
-  if (b->dYOff) cudaFree (b->dYOff);
-  if (b->dPaths) cudaFree (b->dPaths);
+  pooled_free (b->device, b->dTokBlock, b->tokBytes);
+  pooled_free (b->device, b->dPaths, b->pathsBytes);
   ws_release_all (b);
   if (b->evStart) cudaEventDestroy (b->evStart);
   if (b->evStop) cudaEventDestroy (b->evStop);

@@ -282,20 +282,6 @@ int generic_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward)
   return 0;
 }
 
-static int ensure_paths (mb_batch* b, int64_t need) {
-  if (need <= b->pathsCapacity) return 0;
-  const int64_t cap = std::max<int64_t> (need, 2 * b->pathsCapacity);
-  int32_t* p = nullptr;
-  MB_CUDA (cudaMalloc (&p, (size_t) cap * 4));
-  if (b->dPaths) {
-    MB_CUDA (cudaMemcpyAsync (p, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
-    MB_CUDA (cudaStreamSynchronize (b->stream));
-    cudaFree (b->dPaths);
-  }
-  b->dPaths = p;
-  b->pathsCapacity = cap;
-  return 0;
-}
 
 int generic_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathStart.clear();
@@ -333,7 +319,7 @@ int generic_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen
         b->pathLen[ch.pairs[n]] = len[n];
         packed += len[n];
       }
-      if (ensure_paths (b, packed)) return 1;
+      if (paths_reserve (b, packed)) return 1;
       if (upload (dOutOff, off, b->stream)) return 1;
       traceback_kernel<<<tg, 64, 0, b->stream>>> (m->dev, cb, dPairs.as<int64_t>(), dOff.as<int64_t>(), dWs.as<double>(), dRes.as<double>(), dLen.as<int64_t>(), b->dPaths, dOutOff.as<int64_t>());
       MB_CUDA (cudaGetLastError());

@@ -100,6 +100,8 @@ struct mb_batch {
   uint8_t* dY = nullptr;
   int64_t* dXOff = nullptr;
   int64_t* dYOff = nullptr;
+  void* dTokBlock = nullptr;           // the pooled allocation the four pointers above point into
+  size_t tokBytes = 0;
   int64_t* dEnv = nullptr;             // envOff | envStart | envEnd in one allocation (null: full envelopes only)
   bool hasEnv = false;
   std::vector<int64_t> envOff, envStart, envEnd;   // host copies
@@ -118,6 +120,7 @@ struct mb_batch {
   int32_t* dPaths = nullptr;
   std::vector<int64_t> pathStart, pathLen;   // per pair: offset into dPaths and length
   int64_t pathsCapacity = 0;
+  size_t pathsBytes = 0;               // size of the pooled block behind dPaths
 };
 
 namespace mb {
@@ -161,6 +164,7 @@ void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);
 size_t ws_bytes (const mb_batch* b, int slot);
 size_t ws_pool_bytes (int device);   // freed blocks kept for reuse; released when an allocation fails
+int paths_reserve (mb_batch* b, int64_t need);   // room for `need` packed path entries in b->dPaths (pooled; keeps the content)
 
 // timing helpers
 int timing_begin (mb_batch* b);

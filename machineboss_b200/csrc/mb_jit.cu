@@ -182,6 +182,10 @@ struct JitEngine {
   // (MB_LANE_FRAMES); the E-step kernels, whose stored Forward blocks share a frame per warp, stay at C.
   int CV = 4, minBlocksV = 4;
   std::string sourceV;
+  // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
+  // start state); the others follow from them inside the cell through the silent groups
+  std::vector<int> stored;
+  int storeQ = 1;      // 16-byte chunks per cell
   CUmodule modV = nullptr;
   std::vector<int> shift, bits;          // Viterbi back-pointer packing per state
   std::string source;
@@ -332,6 +336,45 @@ static void gen_cell_lin (std::ostringstream& o, const mb_machine* m, const Prog
   o << "}\n\n";
 }
 
+// The E-step's stored Forward cell (linear domain).  A state all of whose incoming transition groups
+// are silent is a linear function of lower-numbered states of the SAME cell, so only the states that
+// something emitting enters (and the start state, which carries the origin) need to be kept: 3 of
+// dnapsw's 8.  mb_fpack_lin rounds those to their high words; mb_fexpand_lin rebuilds the whole cell,
+// scaled by kap, for the posterior products.
+static void gen_fstore_lin (std::ostringstream& o, const mb_machine* m, JitEngine& J) {
+  const Program& p = J.fwd;
+  std::vector<char> keep ((size_t) m->S, 0);
+  keep[0] = 1;
+  for (auto& sl: p.slots) if (sl.type != T_SILENT) keep[sl.self] = 1;
+  J.stored.clear();
+  for (int d = 0; d < m->S; ++d) if (keep[d]) J.stored.push_back (d);
+  J.storeQ = ((int) J.stored.size() + 3) / 4;
+  o << "#define MB_SQ " << J.storeQ << "      // 16-byte chunks per cell in the stored Forward blocks (" << J.stored.size() << " of " << m->S << " states kept)\n";
+  o << "__device__ __forceinline__ void mb_fpack_lin (const double (&N)[MB_S], unsigned (&hw)[4 * MB_SQ]) {\n";
+  for (int j = 0; j < 4 * J.storeQ; ++j) {
+    if (j < (int) J.stored.size()) o << "  hw[" << j << "] = (unsigned) __double2hiint (N[" << J.stored[j] << "]) + ((unsigned) __double2loint (N[" << J.stored[j] << "]) >> 31);\n";
+    else o << "  hw[" << j << "] = 0u;\n";
+  }
+  o << "}\n\n";
+  o << "__device__ __forceinline__ void mb_fexpand_lin (const unsigned (&hw)[4 * MB_SQ], const double kap, double (&F)[MB_S], const MBSil& P) {\n";
+  for (int d = 0; d < m->S; ++d) {
+    if (keep[d]) {
+      const int j = (int) (std::find (J.stored.begin(), J.stored.end(), d) - J.stored.begin());
+      o << "  const double f" << d << " = __hiloint2double ((int) hw[" << j << "], 0) * kap;\n";
+      continue;
+    }
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    if (s0 == s1) { o << "  const double f" << d << " = 0.0;\n"; continue; }
+    for (int k = s0; k < s1; ++k) {
+      const Slot& sl = p.slots[k];
+      if (k == s0) o << "  double f" << d << " = f" << sl.other << " * P.f[" << sl.silIdx << "];\n";
+      else o << "  f" << d << " = fma (f" << sl.other << ", P.f[" << sl.silIdx << "], f" << d << ");\n";
+    }
+  }
+  for (int d = 0; d < m->S; ++d) o << "  F[" << d << "] = f" << d << ";\n";
+  o << "}\n\n";
+}
+
 // Linear-domain Backward cell fused with the posterior counts: per transition group
 //   t = B(dest) * w;  B(s) += t;  count(group) += F'(s) * t     with F' = F * 2^(eF+eB) / Z
 static void gen_cell_counts_lin (std::ostringstream& o, const mb_machine* m, const JitEngine& J) {
@@ -453,7 +496,7 @@ static int compile (mb_machine* m, JitEngine& J) {
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
     J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (16 + 32 * (m->S + 1))) * 8
       + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0)
-      + (q == 8 ? (size_t) (J.threads / 32) * 2 * (32 * J.C * ((m->S + 3) / 4) * 4) * 4 : 0);     // two staged Forward blocks per warp
+      + (q == 8 ? (size_t) (J.threads / 32) * 2 * (32 * J.C * J.storeQ * 4) * 4 : 0);     // two staged Forward blocks per warp
     if (!cu_ok (g_drv.FuncSetAttribute (fn[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[q]), "cuFuncSetAttribute")) return 1;
     int nb = 0;
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
@@ -567,6 +610,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   gen_cell_lin (o, m, J.fwd, true);
   gen_cell_lin (o, m, J.bwd, false);
   gen_cell_counts_lin (o, m, J);
+  gen_fstore_lin (o, m, J);
   o << kJitSkeleton;
   (pass ? J.sourceV : J.source) = o.str();
   }
@@ -862,20 +906,6 @@ __global__ void __launch_bounds__(256) jit_path_ids_kernel (TbPlan p, int nSlots
   }
 }
 
-static int ensure_paths (mb_batch* b, int64_t need) {
-  if (need <= b->pathsCapacity) return 0;
-  const int64_t cap = std::max<int64_t> (need, 2 * b->pathsCapacity);
-  int32_t* p = nullptr;
-  MB_CUDA (cudaMalloc (&p, (size_t) cap * 4));
-  if (b->dPaths) {
-    MB_CUDA (cudaMemcpyAsync (p, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
-    MB_CUDA (cudaStreamSynchronize (b->stream));
-    cudaFree (b->dPaths);
-  }
-  b->dPaths = p;
-  b->pathsCapacity = cap;
-  return 0;
-}
 
 static size_t device_total_bytes (int device) {
   static size_t cache[64] = { 0 };
@@ -985,7 +1015,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
         b->pathLen[chunks[c][q]] = len[q];
         packed += len[q];
       }
-      if (ensure_paths (b, packed)) return 1;
+      if (paths_reserve (b, packed)) return 1;
       MB_CUDA (cudaMemcpyAsync (dOutOff, off.data(), n * 8, cudaMemcpyHostToDevice, b->stream));
       jit_path_ids_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, b->stream>>> (tp, (int) nSlots, b->dev, dPairs, (int64_t) n, dLen, dTmp, dTmpOff, b->dPaths, dOutOff);
       MB_CUDA (cudaGetLastError());
@@ -1065,14 +1095,14 @@ static int counts_lin (mb_machine* m, mb_batch* b, const std::vector<int64_t>& p
   const int W = 32 * J.C;
   double wanted = 0;
   for (int64_t k: pairs)
-    wanted += 4.0 * (double) ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * ((b->yOff[k + 1] - b->yOff[k]) + 32) * (int64_t) (32 * J.C * ((m->S + 3) / 4) * 4));
+    wanted += 4.0 * (double) ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * ((b->yOff[k + 1] - b->yOff[k]) + 32) * (int64_t) (32 * J.C * J.storeQ * 4));
   const double budget = memory_budget (b, WS_F, wanted) / 4.0;     // in 32-bit words
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), efOffHost ((size_t) b->nPairs, 0), chunkWords (1, 0), chunkEf (1, 0);
   for (int64_t k: pairs) {
     const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
     // one block of 32 lanes x C cells x ceil(S/4) 16-byte chunks per (strip, step), in the order the sweep produces them
-    const int64_t need = ((Li + W) / W) * (Lo + 32) * (int64_t) (32 * J.C * ((m->S + 3) / 4) * 4);
+    const int64_t need = ((Li + W) / W) * (Lo + 32) * (int64_t) (32 * J.C * J.storeQ * 4);
     const int64_t needEf = ((Li + W) / W) * ((Lo + 32 + 15) / 16);
     if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": the Forward matrix does not fit in device memory"); return 1; }
     if (!chunks.back().empty() && (double) (chunkWords.back() + need) > budget) { chunks.emplace_back(); chunkWords.push_back (0); chunkEf.push_back (0); }

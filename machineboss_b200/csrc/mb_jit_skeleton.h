@@ -101,7 +101,6 @@ template<> struct MBDir<1> { static const int NE = MB_NEMIT_B; static const int 
 // others are temporaries of the cell function and need no shuffle, boundary slot or rescaling
 template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { return ((DIR ? MB_LIVE_B : MB_LIVE_F) >> s) & 1ull; }
 
-#define MB_SQ ((MB_S + 3) / 4)                 // 16-byte chunks per cell in the stored Forward blocks
 #define MB_FBLOCK (32 * MB_C * MB_SQ * 4)       // 32-bit words per warp-step block of stored Forward values
 #define MB_ROW (MB_S + 1)      // doubles per strip-boundary row: the states + the frame exponent (linear sweeps)
 
@@ -341,7 +340,9 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_vite
 
 // MODE 0: score only.  MODE 2 (DIR 0): also store the Forward values for the E-step -- the HIGH WORD
 // of each double (sign, 11-bit exponent, 20-bit mantissa, rounded: relative error 2^-21, full FP64
-// range), 4 bytes per cell-state instead of 8, plus the frame exponent of every rescale block.
+// range), 4 bytes instead of 8, and only for the states an emitting transition enters (the rest of a
+// cell follows from those through its silent transitions, mb_fexpand_lin), plus the frame exponent of
+// every rescale block.
 // MODE 3 (DIR 1): Backward fused with the posterior counts: for each transition group the product
 // term = B(dest) * w feeds the Backward sum and, times F(src) * 2^(eF + eB) / Z, the group's count.
 template<int MODE, int DIR>
@@ -595,14 +596,13 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
                 const int d = max (min (eF + ecur - lzi, 1000), -1023);
                 const double kap = zf * __hiloint2double ((1023 + d) << 20, 0);
                 // written by Forward lane 31-lane as its cell MB_C-1-c
+                unsigned hw[4 * MB_SQ];
 #pragma unroll
                 for (int g = 0; g < MB_SQ; ++g) {
                   const uint4 q = *(const uint4*) (fsm + (((MB_C - 1 - c) * MB_SQ + g) * 32 + lane) * 4);
-                  if (4 * g < MB_S) Fc[4 * g] = __hiloint2double ((int) q.x, 0) * kap;
-                  if (4 * g + 1 < MB_S) Fc[4 * g + 1] = __hiloint2double ((int) q.y, 0) * kap;
-                  if (4 * g + 2 < MB_S) Fc[4 * g + 2] = __hiloint2double ((int) q.z, 0) * kap;
-                  if (4 * g + 3 < MB_S) Fc[4 * g + 3] = __hiloint2double ((int) q.w, 0) * kap;
+                  hw[4 * g] = q.x; hw[4 * g + 1] = q.y; hw[4 * g + 2] = q.z; hw[4 * g + 3] = q.w;
                 }
+                mb_fexpand_lin (hw, kap, Fc, P);      // the kept states, and through the silent groups the others
               } else {
 #pragma unroll
                 for (int s = 0; s < MB_S; ++s) Fc[s] = 0.0;
@@ -615,9 +615,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
                 // high words, rounded; 16-byte chunk g of cell c goes to word ((c*MB_SQ + g)*32 + lane)*4 of
                 // the block, so every store instruction of the warp writes 512 contiguous bytes
                 unsigned hw[4 * MB_SQ];
-#pragma unroll
-                for (int s = 0; s < 4 * MB_SQ; ++s)
-                  hw[s] = s < MB_S ? (unsigned) __double2hiint (N[s < MB_S ? s : 0]) + ((unsigned) __double2loint (N[s < MB_S ? s : 0]) >> 31) : 0u;
+                mb_fpack_lin (N, hw);
 #pragma unroll
                 for (int g = 0; g < MB_SQ; ++g)
                   *(uint4*) (fblk + ((c * MB_SQ + g) * 32 + lane) * 4) = make_uint4 (hw[4 * g], hw[4 * g + 1], hw[4 * g + 2], hw[4 * g + 3]);

@@ -523,18 +523,7 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       b->pathLen[chunk[n]] = len[n];
       packed += len[n];
     }
-    if (packed > b->pathsCapacity) {
-      const int64_t cap = std::max<int64_t> (packed, 2 * b->pathsCapacity);
-      int32_t* np = nullptr;
-      MB_CUDA (cudaMalloc (&np, (size_t) cap * 4));
-      if (b->dPaths) {
-        MB_CUDA (cudaMemcpyAsync (np, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
-        MB_CUDA (cudaStreamSynchronize (b->stream));
-        cudaFree (b->dPaths);
-      }
-      b->dPaths = np;
-      b->pathsCapacity = cap;
-    }
+    if (paths_reserve (b, packed)) return 1;
     if (dOutOff.alloc (off.size() * 8)) return 1;
     MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, b->stream));
     if (wide_traceback_launch (m, b, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOffRead.as<int64_t>(), h->bpBytes, LPT,

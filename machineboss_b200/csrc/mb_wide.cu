@@ -727,20 +727,6 @@ static int choose_shape (const WHost* h, bool oneD, WShape& best) {
   return 0;
 }
 
-static int ensure_paths (mb_batch* b, int64_t need) {
-  if (need <= b->pathsCapacity) return 0;
-  const int64_t cap = std::max<int64_t> (need, 2 * b->pathsCapacity);
-  int32_t* p = nullptr;
-  MB_CUDA (cudaMalloc (&p, (size_t) cap * 4));
-  if (b->dPaths) {
-    MB_CUDA (cudaMemcpyAsync (p, b->dPaths, (size_t) b->pathsCapacity * 4, cudaMemcpyDeviceToDevice, b->stream));
-    MB_CUDA (cudaStreamSynchronize (b->stream));
-    cudaFree (b->dPaths);
-  }
-  b->dPaths = p;
-  b->pathsCapacity = cap;
-  return 0;
-}
 
 struct WBuf {
   void* p = nullptr;
@@ -893,7 +879,7 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       b->pathLen[chunk[n]] = len[n];
       packed += len[n];
     }
-    if (ensure_paths (b, packed)) return 1;
+    if (paths_reserve (b, packed)) return 1;
     if (dOutOff.alloc (off.size() * 8)) return 1;
     MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, b->stream));
     wide_traceback_kernel<<<tg, 32, 0, b->stream>>> (m->dev, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned char>(), dBpOff.as<int64_t>(), h->t.bpBytes, 0,
