@@ -181,6 +181,10 @@ struct JitEngine {
   // FP64 range on ordinary pairs, so in that module the linear sweeps keep a frame per lane
   // (MB_LANE_FRAMES); the E-step kernels, whose stored Forward blocks share a frame per warp, stay at C.
   int CV = 4, minBlocksV = 4;
+  // the same three kernels at C columns per lane (first module): chosen per call for batches whose pairs
+  // would leave most of a 32 * CV column strip empty (300 aa proteins: 2 strips of 256 against 3 of 128)
+  CUfunction kViterbiN = nullptr, kForwardLinN = nullptr, kBackwardLinN = nullptr;
+  int blocksPerSMN[3] = { 1, 1, 1 };
   std::string sourceV;
   // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
   // start state); the others follow from them inside the cell through the silent groups
@@ -487,6 +491,9 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.modV ? J.modV : J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
+  if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiN, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLinN, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLinN, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction"))) return 1;
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
@@ -502,7 +509,32 @@ static int compile (mb_machine* m, JitEngine& J) {
     if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fn[q], J.threads, J.smemBytes[q]), "occupancy")) return 1;
     J.blocksPerSM[q] = std::max (1, nb);
   }
+  if (J.modV) {
+    CUfunction fnN[3] = { J.kViterbiN, J.kForwardLinN, J.kBackwardLinN };
+    const int qOf[3] = { 2, 5, 6 };
+    for (int q = 0; q < 3; ++q) {
+      if (!cu_ok (g_drv.FuncSetAttribute (fnN[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[qOf[q]]), "cuFuncSetAttribute")) return 1;
+      int nb = 0;
+      if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fnN[q], J.threads, J.smemBytes[qOf[q]]), "occupancy")) return 1;
+      J.blocksPerSMN[q] = std::max (1, nb);
+    }
+  }
   return 0;
+}
+
+// Columns per lane for a score-only call over `pairs`: CV unless the narrower strips of C waste so much
+// less padding that they win.  Cost per cell relative to C (measured, 10 000 dnapsw pairs of 1 kb):
+// Viterbi 0.60, linear sweeps 0.87.
+static bool use_narrow (const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, bool viterbi) {
+  if (!J.modV) return false;
+  if (const char* e = getenv ("MB_JIT_NARROW")) return atoi (e) != 0;
+  double cellsN = 0, cellsW = 0;
+  for (int64_t k: pairs) {
+    const double Li = (double) (b->xOff[k + 1] - b->xOff[k]), rows = (double) (b->yOff[k + 1] - b->yOff[k]) + 32;
+    cellsN += std::ceil ((Li + 1) / (32.0 * J.C)) * 32.0 * J.C * rows;
+    cellsW += std::ceil ((Li + 1) / (32.0 * J.CV)) * 32.0 * J.CV * rows;
+  }
+  return cellsN < (viterbi ? 0.60 : 0.87) * cellsW;
 }
 
 static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>& ef, std::vector<double>& eb) {
@@ -589,7 +621,6 @@ static void generate (const mb_machine* m, JitEngine& J) {
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
   if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n";
-  else if (J.CV != J.C) o << "#define MB_SKIP_VITERBI 1\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
@@ -731,14 +762,15 @@ struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const dou
                    unsigned* F32 = nullptr; const int64_t* f32Off = nullptr; int32_t* ef = nullptr; const int64_t* efOff = nullptr; };
 
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
-                   const CountArgs& ca = CountArgs()) {
+                   const CountArgs& ca = CountArgs(), bool narrow = false) {
   JitEngine& J = *(JitEngine*) m->jit;
-  CUfunction fn = which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
+  narrow = narrow && J.modV && (which == 2 || which == 5 || which == 6);
+  CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : J.kBackwardLinN) : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
   const bool lin = which >= 5;
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
-  int64_t grid = (int64_t) J.numSMs * J.blocksPerSM[which];
+  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : 2] : J.blocksPerSM[which]);
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
@@ -764,7 +796,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[which], (which == 2 || which == 5 || which == 6) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+             J.smemBytes[which], J.blocksPerSM[which], ((which == 2 || which == 5 || which == 6) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
@@ -785,7 +817,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     if (!dFlag) return 1;
     CountArgs ca;
     ca.flag = dFlag;
-    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca)) return 1;
+    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (J, b, order, false))) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
     MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
     MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -938,7 +970,8 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
-  const int W = 32 * J.CV;
+  const bool narrow = use_narrow (J, b, full_order (b), true);
+  const int W = 32 * (narrow ? J.C : J.CV);
   // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
   double wanted = 0;
   for (int64_t k = 0; k < b->nPairs; ++k)
@@ -986,7 +1019,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (chunks.size() > 1) chunkOrder = cost_order (b, chunks[c]);
     const std::vector<int64_t>& order = chunks.size() > 1 ? chunkOrder : full_order (b);
     if (timing_begin (b)) return 1;
-    if (launch (m, b, 2, order, dRes, dTb, dTbOff)) return 1;
+    if (launch (m, b, 2, order, dRes, dTb, dTbOff, CountArgs(), narrow)) return 1;
     ++launches;
     if (trace) {
       const size_t n = chunks[c].size();

@@ -162,6 +162,30 @@ def test_wide_engine_multi_strip_composite():
         assert paths[k].tolist() == p.tolist(), k
 
 
+@pytest.mark.parametrize("narrow", [0, 1])
+def test_jit_strip_widths(narrow, monkeypatch):
+    """The score-only kernels exist at 4 and at 8 columns per lane (the wider ones with a frame per lane in the
+    linear sweeps); the engine picks per call.  Both, forced, on pairs that span several strips of either width."""
+    capi = _capi()
+    monkeypatch.setenv("MB_JIT_NARROW", str(narrow))
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    shapes = [(300, 280), (0, 7), (129, 40), (257, 300), (520, 64), (31, 530)]
+    pairs = [(synth_tokens(91, k, 0, li, 4), synth_tokens(91, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    bl = capi.backward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(ll[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, ll[k], f)
+        assert abs(bl[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, bl[k], f)
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v, (k, sc[k], v)
+        assert paths[k].tolist() == p.tolist(), k
+
+
 @pytest.mark.parametrize("reads_per_lane", [1, 2, 4])
 def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
     """Batches without input sequences go through the lane engine (a read per lane, mb_lane.cu): every
