@@ -100,6 +100,18 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff);
  * log-likelihood is -inf contribute nothing. */
 int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 
+/* ---- DPMatrix::cell of a ForwardMatrix / BackwardMatrix / ViterbiMatrix (src/dpmatrix.h:128-146) ----
+ * The whole log-domain matrix of ONE pair of the batch, as the reference stores it (dpmatrix.h:86-95):
+ * cells[((o * (inLen + 1)) + i) * nStates + s], state fastest; -inf outside the pair's envelope.  It is what
+ * the reference's consumers of a stored matrix read: ForwardMatrix::samplePath (forward.cpp:17-23,
+ * dpmatrix.defs.h:176-186), postTransQueue / traceFrom (backward.cpp:52-56,89-108).  The caller provides
+ * (inLen + 1) * (outLen + 1) * nStates doubles.  Sums use the reference's log-sum-exp cut-off
+ * (logsumexp.h:52), so cells track the reference's to its table's interpolation error. */
+#define MB_MATRIX_FORWARD  0
+#define MB_MATRIX_BACKWARD 1
+#define MB_MATRIX_VITERBI  2
+int mb_matrix (mb_machine* m, mb_batch* b, int64_t pair, int32_t kind, double* cells);
+
 /* ---- diagnostics (not part of the reference surface) ----
  * Generates the machine-specialised kernels for this machine structure and compiles them with
  * NVRTC for sm_100a WITHOUT touching a device (so it also runs where there is no GPU: the build

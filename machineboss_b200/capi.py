@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_counts", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
+           "mb_viterbi_paths", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
 
 
 class MachineBossError(RuntimeError):
@@ -55,6 +55,7 @@ def lib():
         L.mb_viterbi.argtypes = [P, P, P, P]
         L.mb_viterbi_paths.argtypes = [P, P, P]
         L.mb_counts.argtypes = [P, P, P, P]
+        L.mb_matrix.argtypes = [P, P, I64, I32, P]
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
         L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
@@ -249,6 +250,15 @@ def viterbi_into(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off:
     if total:
         _check(lib().mb_viterbi_paths(b.h, _ptr(trans), _ptr(off)))
     return total
+
+
+def matrix(m: Machine, b: Batch, pair: int, kind: int = 0) -> np.ndarray:
+    """DPMatrix cells of one pair, shape (outLen+1, inLen+1, nStates); kind 0 Forward, 1 Backward, 2 Viterbi."""
+    li = int(b.x_off[pair + 1] - b.x_off[pair])
+    lo = int(b.y_off[pair + 1] - b.y_off[pair])
+    out = np.empty((lo + 1, li + 1, m.n_states), dtype=np.float64)
+    _check(lib().mb_matrix(m.h, b.h, int(pair), int(kind), _ptr(out)))
+    return out
 
 
 def counts(m: Machine, b: Batch):

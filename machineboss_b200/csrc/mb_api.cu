@@ -512,6 +512,12 @@ int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike) {
   return use_jit (m, b) ? jit_counts (m, b, counts, loglike) : generic_counts (m, b, counts, loglike);
 }
 
+int mb_matrix (mb_machine* m, mb_batch* b, int64_t pair, int32_t kind, double* cells) {
+  if (check_call (m, b)) return 1;
+  if (!cells) { set_error ("mb_matrix: null output"); return 1; }
+  return generic_matrix (m, b, pair, kind, cells);
+}
+
 int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
                           const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
                           char* log, int64_t logCap) {

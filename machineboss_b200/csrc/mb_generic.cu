@@ -283,6 +283,26 @@ int generic_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward)
 }
 
 
+// DPMatrix::cell (dpmatrix.h:128-146): the whole matrix of one pair, [o][i][s] as the reference stores it
+// (state fastest, then input position, then output position), -inf outside the envelope.
+int generic_matrix (mb_machine* m, mb_batch* b, int64_t pair, int kind, double* cells) {
+  if (pair < 0 || pair >= b->nPairs) { set_error ("mb_matrix: no such pair"); return 1; }
+  if (kind < 0 || kind > 2) { set_error ("mb_matrix: kind must be 0 (Forward), 1 (Backward) or 2 (Viterbi)"); return 1; }
+  const int64_t Li = b->xOff[pair + 1] - b->xOff[pair], Lo = b->yOff[pair + 1] - b->yOff[pair];
+  const size_t n = (size_t) (Li + 1) * (size_t) (Lo + 1) * m->S;
+  std::vector<int64_t> one (1, pair), zero (1, 0);
+  DevBuf dPairs, dOff, dWs, dRes;
+  if (upload (dPairs, one, b->stream) || upload (dOff, zero, b->stream) || dWs.alloc (n * 8) || dRes.alloc ((size_t) b->nPairs * 8)) return 1;
+  if (timing_begin (b)) return 1;
+  if (kind == 0) fill_kernel<OP_SUM, false><<<1, 256, 0, b->stream>>> (m->dev, b->dev, dPairs.as<int64_t>(), dOff.as<int64_t>(), dWs.as<double>(), 0, dRes.as<double>());
+  else if (kind == 1) fill_kernel<OP_SUM, true><<<1, 256, 0, b->stream>>> (m->dev, b->dev, dPairs.as<int64_t>(), dOff.as<int64_t>(), dWs.as<double>(), 0, dRes.as<double>());
+  else fill_kernel<OP_MAX, false><<<1, 256, 0, b->stream>>> (m->dev, b->dev, dPairs.as<int64_t>(), dOff.as<int64_t>(), dWs.as<double>(), 0, dRes.as<double>());
+  MB_CUDA (cudaGetLastError());
+  if (timing_end (b, 1)) return 1;
+  MB_CUDA (cudaMemcpy (cells, dWs.p, n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int generic_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathStart.clear();
   b->pathLen.clear();

@@ -130,6 +130,7 @@ namespace mb {
 int generic_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);
 int generic_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int generic_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
+int generic_matrix (mb_machine* m, mb_batch* b, int64_t pair, int kind, double* cells);
 
 // ---- jit engine (mb_jit.cu) ----
 bool jit_supported (const mb_machine* m, std::string* why);

@@ -27,6 +27,8 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <random>
+#include <cmath>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -296,6 +298,16 @@ struct EvaluatedMachine {
     return t;
   }
 
+  // the role of EvaluatedMachineState::incoming (eval.h:68-76): ids of the transitions into `s` labelled
+  // (inTok, outTok), by source state then transition index (= ascending id)
+  vector<int32_t> incomingIds (StateIndex s, int inTok, int outTok) const {
+    vector<int32_t> ids;
+    for (size_t t = 0; t < dst.size(); ++t) if ((StateIndex) dst[t] == s && in[t] == inTok && out[t] == outTok) ids.push_back ((int32_t) t);
+    return ids;
+  }
+  StateIndex transSource (int32_t id) const { return (StateIndex) src[id]; }
+  double transLogWeight (int32_t id) const { return logWeight[id]; }
+
   // new log-weights for the same structure (what EvaluatedMachine(machine, params) recomputes per EM iteration)
   void setLogWeights (const vector<double>& lw) {
     if (lw.size() != logWeight.size()) throw runtime_error ("setLogWeights: size mismatch");
@@ -393,14 +405,87 @@ inline vector<const SeqPair*> pairPointers (const SeqPairList& l) {
   return v;
 }
 
-// ---- Forward (src/forward.h:8-28) ----
-class ForwardMatrix {
+// ---- stored matrices: DPMatrix::cell (src/dpmatrix.h:128-146) and the stochastic traceback built on it ----
+// The device keeps no matrix for a score; the first cell() fetches the pair's whole matrix (mb_matrix).
+class StoredMatrix {
 public:
   const EvaluatedMachine& machine;
   const SeqPair& seqPair;
-  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
-  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  StoredMatrix (const EvaluatedMachine& m, const SeqPair& sp, int kind) : machine (m), seqPair (sp), kind (kind) {}
+  // dpmatrix.h:136-146: -inf outside the matrix
+  double cell (long inPos, long outPos, int state) const {
+    const long Li = (long) seqPair.input.seq.size(), Lo = (long) seqPair.output.seq.size();
+    if (inPos < 0 || inPos > Li || outPos < 0 || outPos > Lo || state < 0 || state >= (int) machine.nStates()) return -std::numeric_limits<double>::infinity();
+    fetch();
+    return cells[((size_t) outPos * (size_t) (Li + 1) + (size_t) inPos) * (size_t) machine.nStates() + (size_t) state];
+  }
+protected:
+  int kind;
+  mutable vector<double> cells;
+  void fetch() const {
+    if (!cells.empty()) return;
+    const size_t Li = seqPair.input.seq.size(), Lo = seqPair.output.seq.size();
+    cells.resize ((Li + 1) * (Lo + 1) * (size_t) machine.nStates());
+    DeviceBatch b (machine, vector<const SeqPair*> (1, &seqPair));
+    mbCheck (mb_matrix (machine.handle(), b.handle(), 0, kind, cells.data()));
+  }
+  // DPMatrix::traceBack with a TransSelector (dpmatrix.defs.h:82-110): candidates in the reference's order
+  // (match, delete, insert, silent sources; each list by source state, then transition index)
+  template<class Selector>
+  MachinePath traceBackWith (Selector select, int s) const {
+    long i = (long) seqPair.input.seq.size(), o = (long) seqPair.output.seq.size();
+    if (!(cell (i, o, s) > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceback: no finite-weight paths");
+    const vector<InputToken> inTok = machine.inputTokenizer.tokenize (seqPair.input.seq);
+    const vector<OutputToken> outTok = machine.outputTokenizer.tokenize (seqPair.output.seq);
+    list<MachineTransition> rev;
+    while (i > 0 || o > 0 || s != 0) {
+      vector<double> ll;
+      vector<int32_t> ids;
+      const int a = i ? inTok[i - 1] : 0, c = o ? outTok[o - 1] : 0;
+      auto visit = [&] (int wantIn, int wantOut, long pi, long po) {
+        for (int32_t id: machine.incomingIds (s, wantIn, wantOut)) { ids.push_back (id); ll.push_back (cell (pi, po, machine.transSource (id)) + machine.transLogWeight (id)); }
+      };
+      if (i && o) visit (a, c, i - 1, o - 1);
+      if (i) visit (a, 0, i - 1, o);
+      if (o) visit (0, c, i, o - 1);
+      visit (0, 0, i, o);
+      if (ids.empty()) throw runtime_error ("traceback: dead end");
+      const size_t best = select (ll);
+      const int32_t id = ids[best < ids.size() ? best : ids.size() - 1];
+      const MachineTransition& t = machine.transition (id);
+      rev.push_front (t);
+      if (!t.inputEmpty()) --i;
+      if (!t.outputEmpty()) --o;
+      s = (int) machine.transSource (id);
+    }
+    MachinePath p;
+    p.trans.assign (rev.begin(), rev.end());
+    return p;
+  }
+};
+
+// ---- Forward (src/forward.h:8-28) ----
+class ForwardMatrix : public StoredMatrix {
+public:
+  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : StoredMatrix (m, sp, MB_MATRIX_FORWARD) { fill(); }
+  ForwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : StoredMatrix (m, sp, MB_MATRIX_FORWARD) { fill(); }
   double logLike() const { return ll; }
+  // ForwardMatrix::samplePath (forward.cpp:17-23): stochastic traceback, candidate weights exp(cell + logWeight),
+  // random_index over them with the caller's mt19937 (dpmatrix.defs.h:176-186, util.h:151-165)
+  template<class AnyMachine> MachinePath samplePath (const AnyMachine&, std::mt19937& rng) const { return samplePath (rng); }
+  MachinePath samplePath (std::mt19937& rng) const {
+    auto select = [&] (const vector<double>& logWeights) -> size_t {
+      vector<double> w;
+      double norm = 0;
+      for (double lw: logWeights) { w.push_back (exp (lw)); norm += w.back(); }
+      if (!(norm > 0)) throw runtime_error ("Zero weights in random_index");
+      // random_double (util.h:102-106): generator() / (max + 1)
+      double variate = (double) rng() / ((double) std::numeric_limits<std::mt19937::result_type>::max() + 1) * norm;
+      for (size_t n = 0; n < w.size(); ++n) if ((variate -= w[n]) <= 0) return n;
+      return w.size();
+    };
+    return traceBackWith (select, (int) machine.nStates() - 1);
+  }
 private:
   double ll = 0;
   void fill() {
@@ -413,12 +498,10 @@ typedef ForwardMatrix RollingOutputForwardMatrix;   // forward.h:28: same result
 struct MachineCounts;
 
 // ---- Backward (src/backward.h:10-56) ----
-class BackwardMatrix {
+class BackwardMatrix : public StoredMatrix {
 public:
-  const EvaluatedMachine& machine;
-  const SeqPair& seqPair;
-  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
-  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp) : StoredMatrix (m, sp, MB_MATRIX_BACKWARD) { fill(); }
+  BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : StoredMatrix (m, sp, MB_MATRIX_BACKWARD) { fill(); }
   double logLike() const { return ll; }
   void getCounts (const ForwardMatrix&, MachineCounts&) const;   // backward.cpp:58-60
 private:
@@ -430,12 +513,10 @@ private:
 };
 
 // ---- Viterbi (src/viterbi.h:8-17) ----
-class ViterbiMatrix {
+class ViterbiMatrix : public StoredMatrix {
 public:
-  const EvaluatedMachine& machine;
-  const SeqPair& seqPair;
-  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp) : machine (m), seqPair (sp) { fill(); }
-  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : machine (m), seqPair (sp) { fill(); }
+  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp) : StoredMatrix (m, sp, MB_MATRIX_VITERBI) { fill(); }
+  ViterbiMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : StoredMatrix (m, sp, MB_MATRIX_VITERBI) { fill(); }
   double logLike() const { return ll; }
   MachinePath path() const {   // viterbi.cpp:49-51 -> traceBack; asserts a finite end cell (dpmatrix.defs.h:84)
     if (!(ll > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceback: no finite-weight paths");

@@ -16,6 +16,7 @@
 //   -V, --viterbi   Viterbi log-likelihoods, same layout                     (boss.cpp:819-848)
 //   -A, --align     Viterbi alignments as a SeqPairList with meta.path       (boss.cpp:833,843-846)
 //   -C, --counts    raw expected transition counts, MachineCounts::writeJson (counts.cpp:73-78)
+//   --sample-paths SEED   one path per pair drawn from the posterior, ForwardMatrix::samplePath (forward.cpp:17-23)
 //                   (boss -C prints PARAMETER counts, which needs the symbolic weight derivatives
 //                   of the Machine -- outside this path)
 //   data: -D/--data pairs.json (a SeqPairList) | --input-fasta X --output-fasta Y |
@@ -63,7 +64,8 @@ int main (int argc, char** argv) {
     vector<string> dataFiles, paramFiles;
     bool useDefaults = false, doT = false;
     vector<NamedSeq<string> > inSeqs, outSeqs;
-    bool doL = false, doV = false, doA = false, doC = false;
+    bool doL = false, doV = false, doA = false, doC = false, doSample = false;
+    long long sampleSeed = 1;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
       auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
@@ -83,6 +85,7 @@ int main (int argc, char** argv) {
       else if (f == "-V" || f == "--viterbi") doV = true;
       else if (f == "-A" || f == "--align") doA = true;
       else if (f == "-C" || f == "--counts") doC = true;
+      else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
       else throw runtime_error ("unknown option " + f);
@@ -131,7 +134,7 @@ int main (int argc, char** argv) {
     for (const auto& i: inSeqs) for (const auto& o: outSeqs) { SeqPair sp; sp.input = i; sp.output = o; data.seqPairs.push_back (sp); }
     if (data.seqPairs.empty() && inputEmpty && outputEmpty) data.seqPairs.push_back (SeqPair());   // boss.cpp:769-770
     if (data.seqPairs.empty()) throw runtime_error ("no sequence data given");
-    if (!(doL || doV || doA || doC || doT)) throw runtime_error ("nothing to do: give -L, -V, -A, -C or -T");
+    if (!(doL || doV || doA || doC || doT || doSample)) throw runtime_error ("nothing to do: give -L, -V, -A, -C or -T");
 
     if (doT) {   // boss.cpp:776-787
       if (constraints.empty() && machine.cons.empty()) throw runtime_error ("To fit parameters, please specify a constraints file and (for machines with input/output) a data file");
@@ -179,6 +182,24 @@ int main (int argc, char** argv) {
         cout << "}" << endl;
       } else
       counts.writeJson (cout);
+    }
+    if (doSample) {   // ForwardMatrix::samplePath (forward.cpp:17-19), pair k drawn with mt19937 (seed + k): [[transition ids], ...]
+      cout << "[";
+      size_t k = 0;
+      for (const auto& sp: data.seqPairs) {
+        cout << (k ? ",\n " : "") << "[";
+        if (eval.canTokenize (sp)) {
+          const ForwardMatrix f (eval, sp);
+          if (f.logLike() > ninf) {
+            std::mt19937 rng ((unsigned) (sampleSeed + (long long) k));
+            size_t n = 0;
+            for (const auto& t: f.samplePath (rng).trans) cout << (n++ ? "," : "") << t.id;
+          }
+        }
+        cout << "]";
+        ++k;
+      }
+      cout << "]\n";
     }
     if (doA || doV) {
       vector<MachinePath> paths;

@@ -210,5 +210,35 @@ def main():
          note="BASELINE config 1: one 1 kb x 1 kb pair")
 
 
+def sample_case():
+    """ForwardMatrix::samplePath (forward.cpp:17-19): paths drawn by the reference with mt19937 (seed + pair index)."""
+    peaked = {"gapOpen": 0.05, "gapExtend": 0.5, "eqmA": 0.25, "eqmC": 0.25, "eqmG": 0.25, "eqmT": 0.25}
+    for a in "ACGT":
+        for b in "ACGT":
+            peaked["sub%s%s" % (a, b)] = 0.91 if a == b else 0.03
+    margs = machine_args(["preset:dnapsw"], peaked)
+    mach = run(margs + ["--emit-machine"])
+    alpha = mach["inAlphabet"]
+    shapes = [(12, 14), (30, 26), (0, 3), (5, 0), (40, 41)]
+    sym_pairs = [([alpha[t - 1] for t in synth_tokens(110, k, 0, li, 4)], [alpha[t - 1] for t in synth_tokens(110, k, 1, lo, 4)])
+                 for k, (li, lo) in enumerate(shapes)]
+    f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": a}, "output": {"name": "y%d" % k, "sequence": b}} for k, (a, b) in enumerate(sym_pairs)], f)
+    f.close()
+    seed = 20261017
+    res = run(margs + ["--pairs", f.name, "--do", "sample", "--sample-seed", str(seed)])
+    os.unlink(f.name)
+    with open(os.path.join(OUT, "aux_sample_paths.json"), "w") as fo:
+        json.dump({"note": "ForwardMatrix::samplePath of the reference: pair k drawn with mt19937(seed + k); global transition ids start -> end",
+                   "machine": mach, "seed": seed,
+                   "pairs": [{"input": a, "output": b, "forward": r["forward"], "sample": r["sample"]} for (a, b), r in zip(sym_pairs, res["pairs"])]},
+                  fo, separators=(",", ":"))
+    print("aux_sample_paths             pairs=%d" % len(sym_pairs))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sample":
+        sample_case()
+    else:
+        main()
+        sample_case()

@@ -73,6 +73,7 @@ struct PairResult {
   bool tokenizable = true;
   double forward = 0, rolling = 0, viterbi = 0, backward = 0;
   vector<long long> path;  // global transition ids, start -> end
+  vector<long long> sample;  // a path drawn by ForwardMatrix::samplePath
   string matrices;
 };
 
@@ -82,6 +83,7 @@ int main (int argc, char** argv) {
   bool useDefaults = true, emitMachine = false, quiet = false;
   long long synthN = 0, synthLi = 0, synthLo = 0, synthSeed = 0;
   int nThreads = 1;
+  long long sampleSeed = 1;
   for (int a = 1; a < argc; ++a) {
     const string f = argv[a];
     auto next = [&] () -> string { if (a + 1 >= argc) { cerr << "missing value for " << f << endl; exit (1); } return argv[++a]; };
@@ -93,6 +95,7 @@ int main (int argc, char** argv) {
     else if (f == "--synth") { if (sscanf (next().c_str(), "%lld,%lld,%lld,%lld", &synthN, &synthLi, &synthLo, &synthSeed) != 4) { cerr << "bad --synth" << endl; exit (1); } }
     else if (f == "--do") doList = next();
     else if (f == "--threads") nThreads = atoi (next().c_str());
+    else if (f == "--sample-seed") sampleSeed = atoll (next().c_str());
     else if (f == "--quiet-results") quiet = true;
     else { cerr << "unknown flag " << f << endl; exit (1); }
   }
@@ -152,7 +155,7 @@ int main (int argc, char** argv) {
 
     auto wants = [&] (const char* w) { return (("," + doList + ",").find (string (",") + w + ",")) != string::npos; };
     const bool doForward = wants ("forward"), doRolling = wants ("rolling"), doViterbi = wants ("viterbi"), doPath = wants ("path"),
-      doBackward = wants ("backward"), doCounts = wants ("counts"), doMatrices = wants ("matrices");
+      doBackward = wants ("backward"), doCounts = wants ("counts"), doMatrices = wants ("matrices"), doSample = wants ("sample");
 
     vector<PairResult> res (pairs.size());
     vector<MachineCounts> threadCounts ((size_t) nThreads, MachineCounts (eval));
@@ -177,6 +180,20 @@ int main (int argc, char** argv) {
             };
             v.traceBack (machine, v.inLen, v.outLen, v.nStates - 1, collect);
             std::reverse (r.path.begin(), r.path.end());
+          }
+        }
+        if (doSample) {
+          // ForwardMatrix::samplePath (forward.cpp:17-19) = traceBack with randomTransSelector; pair k draws from mt19937 (sampleSeed + k)
+          const ForwardMatrix f (eval, sp);
+          r.forward = f.logLike();
+          if (r.forward > -numeric_limits<double>::infinity()) {
+            mt19937 rng ((unsigned) (sampleSeed + (long long) k));
+            ForwardMatrix::TraceTerminator collect = [&] (Envelope::InputIndex, Envelope::OutputIndex, StateIndex src, EvaluatedMachineState::TransIndex ti) {
+              r.sample.push_back ((long long) (eval.state[src].transOffset + ti));
+              return false;
+            };
+            f.traceBack (machine, f.inLen, f.outLen, f.nStates - 1, collect, ForwardMatrix::randomTransSelector (rng));
+            std::reverse (r.sample.begin(), r.sample.end());
           }
         }
         if (doCounts) {
@@ -232,12 +249,17 @@ int main (int argc, char** argv) {
         cout << (k ? ",\n  " : "\n  ") << "{\"tokenizable\":" << (r.tokenizable ? "true" : "false");
         const double ninf = -numeric_limits<double>::infinity();
         if (doRolling) cout << ",\"rolling\":" << dstr (r.tokenizable ? r.rolling : ninf);
-        if (doForward || doCounts || doMatrices) cout << ",\"forward\":" << dstr (r.tokenizable ? r.forward : ninf);
+        if (doForward || doCounts || doMatrices || doSample) cout << ",\"forward\":" << dstr (r.tokenizable ? r.forward : ninf);
         if (doBackward || doCounts || doMatrices) cout << ",\"backward\":" << dstr (r.tokenizable ? r.backward : ninf);
         if (doViterbi || doPath || doMatrices) cout << ",\"viterbi\":" << dstr (r.tokenizable ? r.viterbi : ninf);
         if (doPath) {
           cout << ",\"path\":[";
           for (size_t n = 0; n < r.path.size(); ++n) cout << (n ? "," : "") << r.path[n];
+          cout << "]";
+        }
+        if (doSample) {
+          cout << ",\"sample\":[";
+          for (size_t n = 0; n < r.sample.size(); ++n) cout << (n ? "," : "") << r.sample[n];
           cout << "]";
         }
         if (pairs[k].alignment.size()) {   // the path envelope every matrix of this pair was given (seqpair.cpp:104-110)

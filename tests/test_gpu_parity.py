@@ -162,6 +162,33 @@ def test_wide_engine_multi_strip_composite():
         assert paths[k].tolist() == p.tolist(), k
 
 
+@pytest.mark.parametrize("name", ["bitnoise_tiny", "unitindel", "dnapsw_small", "stutter_noise_difflen", "dnapsw_path_envelope"])
+def test_stored_matrices(name):
+    """mb_matrix (DPMatrix::cell, dpmatrix.h:128-146): whole Forward / Backward / Viterbi matrices against the
+    reference's, cell by cell, including the -inf cells outside a path envelope."""
+    capi = _capi()
+    case = load_golden(name)
+    fm = FlatMachine.from_json(case["machine"])
+    pairs = pairs_from_golden(case)
+    m = make_machine(capi, fm, -1)
+    b = capi.Batch(pairs)
+    if any("env" in p for p in case["pairs"]):
+        b.set_envelopes([p.get("env") for p in case["pairs"]])
+    for k, p in enumerate(case["pairs"]):
+        if "F" not in p:
+            continue
+        for kind, key in ((0, "F"), (1, "B"), (2, "V")):
+            want = np.array([gnum(v) for v in p[key]])
+            got = capi.matrix(m, b, k, kind).reshape(-1)
+            assert got.shape == want.shape, (name, k, key)
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isfinite(got), fin), (name, k, key)
+            if kind == 2:
+                assert np.array_equal(got[fin], want[fin]), (name, k, key)      # add + max only: bit-exact
+            else:
+                np.testing.assert_allclose(got[fin], want[fin], rtol=1e-7, atol=1e-7)      # the table interpolates, the device evaluates log1p(exp())
+
+
 @pytest.mark.parametrize("narrow", [0, 1])
 def test_jit_strip_widths(narrow, monkeypatch):
     """The score-only kernels exist at 4 and at 8 columns per lane (the wider ones with a frame per lane in the

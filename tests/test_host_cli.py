@@ -88,3 +88,19 @@ def test_cli_untokenisable_pair_reports_minus_infinity():
     assert json.loads(r.stdout) == [["ACGN", "ACGT", "-Infinity"]]
     r = subprocess.run([_cli(), "--evaluated-machine", mf, "--input-chars", "ACGN", "--output-chars", "ACGT", "-C"], capture_output=True, text=True)
     assert r.returncode != 0 and "tokenize" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_sample_paths_match_the_reference():
+    """ForwardMatrix::samplePath (forward.cpp:17-23) over the device's stored Forward matrix (mb_matrix): with the
+    reference's generator (mt19937, seed + pair index) and its random_index, the drawn paths are the reference's."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_sample_paths.json")) as f:
+        g = json.load(f)
+    mf = _machine_file(g)
+    pf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": p["input"]}, "output": {"name": "y%d" % k, "sequence": p["output"]}}
+               for k, p in enumerate(g["pairs"])], pf)
+    pf.close()
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "--sample-paths", str(g["seed"])], capture_output=True, text=True, check=True)
+    got = json.loads(r.stdout)
+    assert got == [p["sample"] for p in g["pairs"]]
