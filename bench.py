@@ -249,13 +249,16 @@ def main():
 
     # end-to-end leg: host buffers in, host buffers out, through the C ABI.  Inputs are copied from
     # pinned host memory, results land in pinned host memory the caller owns (allocated once, as a
-    # service would): per-pair log-likelihoods, Viterbi scores, path lengths and the packed paths.
+    # service would): per-pair log-likelihoods, Viterbi scores, path lengths and the packed paths
+    # (global transition ids, one byte each for a machine this small).
     path_cap = P * (2 * args.len + 2) * 2
     h_ll = torch.empty(P, dtype=torch.float64).pin_memory().numpy()
     h_sc = torch.empty(P, dtype=torch.float64).pin_memory().numpy()
     h_len = torch.empty(P, dtype=torch.int64).pin_memory().numpy()
     h_off = torch.empty(P + 1, dtype=torch.int64).pin_memory().numpy()
-    h_paths = torch.empty(path_cap, dtype=torch.int32).pin_memory().numpy()
+    # transition ids as bytes when the machine has at most 256 transitions (dnapsw: 34), mb_viterbi_paths_narrow
+    id_dtype = torch.uint8 if len(mj["lw"]) <= 256 else torch.int32
+    h_paths = torch.empty(path_cap, dtype=id_dtype).pin_memory().numpy()
 
     def step_e2e():
         b = capi.Batch(x=px.numpy(), x_off=x_off, y=py.numpy(), y_off=y_off)      # H2D from pinned memory

@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
+           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
 
 
 class MachineBossError(RuntimeError):
@@ -54,6 +54,7 @@ def lib():
         L.mb_backward.argtypes = [P, P, P]
         L.mb_viterbi.argtypes = [P, P, P, P]
         L.mb_viterbi_paths.argtypes = [P, P, P]
+        L.mb_viterbi_paths_narrow.argtypes = [P, P, I32, P]
         L.mb_counts.argtypes = [P, P, P, P]
         L.mb_matrix.argtypes = [P, P, I64, I32, P]
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
@@ -240,7 +241,7 @@ def forward_into(m: Machine, b: Batch, out: np.ndarray) -> None:
 def viterbi_into(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off: np.ndarray, trans: np.ndarray) -> int:
     """mb_viterbi + mb_viterbi_paths into caller-owned arrays; returns the total path length.
 
-    score float64[nPairs], plen int64[nPairs], off int64[nPairs+1] (filled here), trans int32[capacity]."""
+    score float64[nPairs], plen int64[nPairs], off int64[nPairs+1] (filled here), trans int32 / uint16 / uint8 [capacity]."""
     _check(lib().mb_viterbi(m.h, b.h, _ptr(score), _ptr(plen)))
     off[0] = 0
     np.cumsum(plen[: b.n_pairs], out=off[1: b.n_pairs + 1])
@@ -248,7 +249,11 @@ def viterbi_into(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off:
     if total > trans.size:
         raise MachineBossError("viterbi_into: path buffer too small (%d > %d)" % (total, trans.size))
     if total:
-        _check(lib().mb_viterbi_paths(b.h, _ptr(trans), _ptr(off)))
+        if trans.dtype == np.int32:
+            _check(lib().mb_viterbi_paths(b.h, _ptr(trans), _ptr(off)))
+        else:      # uint8 / uint16 ids (machines with at most 256 / 65 536 transitions)
+            assert trans.dtype in (np.uint8, np.uint16)
+            _check(lib().mb_viterbi_paths_narrow(b.h, _ptr(trans), trans.dtype.itemsize, _ptr(off)))
     return total
 
 

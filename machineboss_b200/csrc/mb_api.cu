@@ -245,6 +245,11 @@ static int upload_machine (mb_machine* m) {
 
 using namespace mb;
 
+template<class T>
+__global__ void narrow_ids_kernel (const int32_t* __restrict__ in, T* __restrict__ out, int64_t n) {
+  for (int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t) gridDim.x * blockDim.x) out[q] = (T) in[q];
+}
+
 extern "C" {
 
 const char* mb_last_error (void) { return g_error.c_str(); }
@@ -481,6 +486,7 @@ int mb_backward (mb_machine* m, mb_batch* b, double* loglike) {
 
 int mb_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (check_call (m, b)) return 1;
+  b->pathIdLimit = m->T;
   if (use_jit (m, b)) return jit_viterbi (m, b, score, pathLen);
   const int w = use_wide (m, b);
   return w < 0 ? 1 : w ? wide_viterbi (m, b, score, pathLen) : generic_viterbi (m, b, score, pathLen);
@@ -504,6 +510,29 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff) {
   MB_CUDA (cudaMemcpy (tmp.data(), b->dPaths, (size_t) total * 4, cudaMemcpyDeviceToHost));
   for (int64_t k = 0; k < b->nPairs; ++k)
     memcpy (pathTrans + pathOff[k], tmp.data() + b->pathStart[k], (size_t) b->pathLen[k] * 4);
+  return 0;
+}
+
+int mb_viterbi_paths_narrow (mb_batch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if ((int64_t) b->pathLen.size() != b->nPairs) { set_error ("mb_viterbi_paths_narrow: no traceback stored; call mb_viterbi with pathLen first"); return 1; }
+  if (bytesPerId == 4) return mb_viterbi_paths (b, (int32_t*) pathTrans, pathOff);
+  if (bytesPerId != 1 && bytesPerId != 2) { set_error ("mb_viterbi_paths_narrow: bytesPerId must be 1, 2 or 4"); return 1; }
+  if (b->pathIdLimit > (bytesPerId == 1 ? 256 : 65536)) { set_error ("mb_viterbi_paths_narrow: the machine's transition ids do not fit in " + std::to_string (bytesPerId) + " byte(s)"); return 1; }
+  MB_CUDA (cudaSetDevice (b->device));
+  int64_t total = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k) total += b->pathLen[k];
+  if (!total) return 0;
+  for (int64_t k = 0; k < b->nPairs; ++k)
+    if (pathOff[k] - pathOff[0] != b->pathStart[k]) { set_error ("mb_viterbi_paths_narrow: paths must be requested packed, in the order mb_viterbi stored them"); return 1; }
+  void* tmp = ws_reserve (b, WS_PATHNARROW, (size_t) total * bytesPerId);
+  if (!tmp) return 1;
+  const unsigned grid = (unsigned) std::min<int64_t> ((total + 255) / 256, 148 * 16);
+  if (bytesPerId == 1) narrow_ids_kernel<uint8_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint8_t*) tmp, total);
+  else narrow_ids_kernel<uint16_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint16_t*) tmp, total);
+  MB_CUDA (cudaGetLastError());
+  MB_CUDA (cudaMemcpyAsync ((char*) pathTrans + pathOff[0] * bytesPerId, tmp, (size_t) total * bytesPerId, cudaMemcpyDeviceToHost, b->stream));
+  MB_CUDA (cudaStreamSynchronize (b->stream));
   return 0;
 }
 

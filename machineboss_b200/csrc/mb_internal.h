@@ -121,6 +121,7 @@ struct mb_batch {
   std::vector<int64_t> pathStart, pathLen;   // per pair: offset into dPaths and length
   int64_t pathsCapacity = 0;
   size_t pathsBytes = 0;               // size of the pooled block behind dPaths
+  int64_t pathIdLimit = 0;             // transition ids of the stored paths are below this (the machine's nTrans)
 };
 
 namespace mb {
@@ -159,7 +160,7 @@ int lane_forward (mb_machine* m, mb_batch* b, double* loglike);
 int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 
 // per-batch workspace (mb_api.cu)
-enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_NSLOTS };
+enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_PATHNARROW, WS_NSLOTS };
 void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set on failure
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);

@@ -174,7 +174,7 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
 
 struct JitEngine {
   Program fwd, bwd;
-  int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 5, minBlocksCnt = 3;
+  int C = 4, tbBytes = 1, threads = 128, minBlocks = 4, minBlocksLin = 5, minBlocksCnt = 4;
   // The score-only kernels (Viterbi, linear Forward / Backward) are compiled as a second module with
   // MB_C = CV columns per lane: fewer shuffles, boundary reads and loop overhead per cell (Viterbi fill
   // 26.5 -> 15.8 ms for 10 000 1 kb pairs).  256 columns under ONE power-of-two frame would exceed the

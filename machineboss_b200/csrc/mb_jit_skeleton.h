@@ -581,6 +581,12 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           double Dc[MB_S];
 #pragma unroll
           for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
+          double kapStep = 0.0;      // MODE 3: stored Forward word -> F * 2^(eF + eB) / Z, one factor for the whole step
+          if (MODE == 3) {
+            const int eF = __ldg (ef + (nStrips - 1 - strip) * nBlk + (Lo + 31 - t) / MB_RESCALE);      // frame of the Forward block: its strip and step
+            const int d = max (min (eF + ecur - lzi, 1000), -1023);
+            kapStep = zf * __hiloint2double ((1023 + d) << 20, 0);
+          }
 #pragma unroll
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
@@ -588,23 +594,16 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
             if (MODE == 3) {
               double Fc[MB_S];
               const int col = col0 + c;
-              if (col >= 0 && col <= Li) {
-                // frame of the Forward block: its strip and step
-                const int eF = __ldg (ef + (nStrips - 1 - strip) * nBlk + (Lo + 31 - t) / MB_RESCALE);
-                const int d = max (min (eF + ecur - lzi, 1000), -1023);
-                const double kap = zf * __hiloint2double ((1023 + d) << 20, 0);
-                // written by Forward lane 31-lane as its cell MB_C-1-c
-                unsigned hw[4 * MB_SQ];
+              // written by Forward lane 31-lane as its cell MB_C-1-c; the padding columns hold finite values
+              // too, so a zero factor replaces a branch around the loads
+              const double kap = (col >= 0 && col <= Li) ? kapStep : 0.0;
+              unsigned hw[4 * MB_SQ];
 #pragma unroll
-                for (int g = 0; g < MB_SQ; ++g) {
-                  const uint4 q = *(const uint4*) (fsm + (((MB_C - 1 - c) * MB_SQ + g) * 32 + lane) * 4);
-                  hw[4 * g] = q.x; hw[4 * g + 1] = q.y; hw[4 * g + 2] = q.z; hw[4 * g + 3] = q.w;
-                }
-                mb_fexpand_lin (hw, kap, Fc, P);      // the kept states, and through the silent groups the others
-              } else {
-#pragma unroll
-                for (int s = 0; s < MB_S; ++s) Fc[s] = 0.0;
+              for (int g = 0; g < MB_SQ; ++g) {
+                const uint4 q = *(const uint4*) (fsm + (((MB_C - 1 - c) * MB_SQ + g) * 32 + lane) * 4);
+                hw[4 * g] = q.x; hw[4 * g + 1] = q.y; hw[4 * g + 2] = q.z; hw[4 * g + 3] = q.w;
               }
+              mb_fexpand_lin (hw, kap, Fc, P);      // the kept states, and through the silent groups the others
               mb_cell_cnt_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, csd, accd, c);
             } else {
               if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);

@@ -365,12 +365,13 @@ struct LBuf {
   template<class T> T* as() { return (T*) p; }
 };
 
-// reads per lane.  Measured on B200 (PF00516, 65 536 reads of 275): the sums gain from a second
-// independent chain per thread (40 -> 89 GCUPS) and nothing from four; the max-plus sweep, which
-// carries a pointer per chain, is fastest with one (71 GCUPS against 67 and 45).
+// reads per lane.  Measured on B200 (PF00516, reads of 275): with enough reads to give every SM some 40
+// warps, one read per lane is fastest (262 144 reads: 175 GCUPS Forward, 132 Viterbi); with fewer, a second
+// independent chain per thread makes up for the missing warps in the sums (65 536 reads: 40 -> 89 GCUPS),
+// while the max-plus sweep, which carries a pointer per chain, stays at one.
 static int lane_reads_per_lane (const LHost* h, int64_t nWork, int op) {
   if (const char* e = getenv ("MB_LANE_R")) { const int r = atoi (e); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
-  if (op == L_MAX) return 1;
+  if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
 
@@ -382,28 +383,31 @@ static int lane_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>
   const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + LPT - 1) / LPT;
   int ctas = 0;
   MB_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&ctas, lane_kernel<OP, R>, 128, 0));
-  int warpsPerSM = 32;
+  int warpsPerSM = 48;      // the sweep is bound by the latency of its state-vector loads: as many warps as the registers allow
   if (const char* e = getenv ("MB_LANE_WARPS")) warpsPerSM = std::max (4, atoi (e));
   ctas = std::max (1, std::min (ctas, warpsPerSM / 4));
   // few tasks: one warp per CTA spreads them over the SMs
   const int threads = nTasks >= (int64_t) ctas * h->numSMs * 4 ? 128 : nTasks >= (int64_t) h->numSMs * 2 ? 64 : 32;
   const int wpc = threads / 32;
   const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + wpc - 1) / wpc, (int64_t) ctas * h->numSMs));
-  LBuf dOrder, dCounter, dVec;
-  if (dOrder.alloc (order.size() * 8) || dCounter.alloc (8) || dVec.alloc ((size_t) grid * wpc * 2 * h->S * LPT * 8)) return 1;
-  MB_CUDA (cudaMemcpyAsync (dOrder.p, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
-  MB_CUDA (cudaMemsetAsync (dCounter.p, 0, 8, b->stream));
+  // scratch from the batch's grow-only workspace: a repeated call allocates nothing
+  b->wsOrderHoldsFull = false;
+  int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
+  unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * wpc * 2 * h->S * LPT * 8);
+  if (!dOrder || !dCounter || !dVec) return 1;
+  MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
   LParams p {};
   p.rec = OP == L_SUM ? h->dRecLin : h->dRecLog; p.nRec = h->nRec;
   p.em = OP == L_SUM ? h->dEmLin : h->dEmLog; p.emIdx = h->dEmIdx;
   p.S = h->S; p.nOut = h->nOut; p.bpBytes = h->bpBytes;
   p.b = b->dev;
-  p.order = dOrder.as<int64_t>(); p.nWork = nWork; p.counter = dCounter.as<unsigned long long>();
-  p.result = dResult; p.flag = dFlag; p.vec = dVec.as<double>();
+  p.order = dOrder; p.nWork = nWork; p.counter = dCounter;
+  p.result = dResult; p.flag = dFlag; p.vec = dVec;
   p.bp = dBp; p.bpOff = dBpOff;
   lane_kernel<OP, R><<<grid, threads, 0, b->stream>>> (p);
   MB_CUDA (cudaGetLastError());
-  MB_CUDA (cudaStreamSynchronize (b->stream));      // the scratch buffers above die with this scope
   return 0;
 }
 
@@ -443,7 +447,8 @@ int lane_forward (mb_machine* m, mb_batch* b, double* loglike) {
   if (h->linearOk) {
     if (lane_launch<L_SUM> (m, b, R, order, dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
-    MB_CUDA (cudaMemcpy (flag.data(), dFlag.p, flag.size() * 4, cudaMemcpyDeviceToHost));
+    MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag.p, flag.size() * 4, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
     std::vector<int64_t> redo;
     for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k]) redo.push_back (k);
     if (!redo.empty()) {
@@ -481,7 +486,7 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   const int R = lane_reads_per_lane (h, b->nPairs, L_MAX), LPT = 32 * R;
   size_t freeB = 0, totalB = 0;
   MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
-  const double vecBytes = (double) h->numSMs * 32 * 2 * h->S * LPT * 8;
+  const double vecBytes = (double) h->numSMs * 48 * 2 * h->S * LPT * 8;
   const double budget = 0.75 * ((double) freeB - vecBytes);
   b->pathStart.assign ((size_t) b->nPairs, 0);
   b->pathLen.assign ((size_t) b->nPairs, 0);

@@ -50,9 +50,13 @@ enum { OP_SUM = 0, OP_MAX = 1, OP_LSE = 2 };      // scaled linear sum, max-plus
 // entry word z: source state (16) | candidate index in its list (14) | first of a list | last of a list
 #define W_FIRST 0x40000000u
 #define W_LAST 0x80000000u
-// entry word w: destination state (16) | log2 pieces (3) | reduce row | sync row
+// entry word w: destination state (16) | log2 pieces (3) | reduce row | sync row | store | end of a list piece.
+// One test of the last four bits separates the plain rows (load, multiply-add) from the rest.
 #define W_REDUCE 0x80000u
 #define W_SYNC 0x100000u
+#define W_STORE 0x200000u
+#define W_PEND 0x400000u
+#define W_SPECIAL (W_REDUCE | W_SYNC | W_STORE | W_PEND)
 
 struct WEntry { double w; uint32_t z; uint32_t d; };
 
@@ -115,28 +119,44 @@ __device__ __forceinline__ void run_rows (const WTab& T, uint32_t row0, uint32_t
     e += G;
     v = *reinterpret_cast<const uint4*> (e);
     const double w = __hiloint2double ((int) u.y, (int) u.x);
-    if (u.z & W_FIRST) { acc = OP == OP_SUM ? 0. : w_ninf(); bp = 0xffffu; }
-    if (OP == OP_SUM) acc = fma (w, x, acc);
-    else if (OP == OP_LSE) acc = w_lse (acc, x + w);
-    else { const double c = x + w; if (acc < c) { acc = c; bp = kindBits | ((u.z >> 16) & 0x3fffu); } }      // strict: the first maximum wins (dpmatrix.defs.h:171-174)
-    if (u.w & W_REDUCE) {      // the same row in every lane of the group
-      const unsigned segW = 1u << ((u.w >> 16) & 7u);
-      for (unsigned off = G / 2; off; off >>= 1) {
-        const double o2 = __shfl_down_sync (gmask, acc, off, G);
-        if (OP == OP_MAX) {      // the tree pairs lanes out of list order: a tie goes to the earlier candidate
+    if (OP == OP_MAX) {
+      // (the max-plus sweep keeps one test per flag: measured 138 GCUPS on prot2dna => dnapsw against 90 with
+      // the combined test below, whose special path most rows take when lists average 1.6 entries)
+      if (u.z & W_FIRST) { acc = w_ninf(); bp = 0xffffu; }
+      const double c = x + w;
+      if (acc < c) { acc = c; bp = kindBits | ((u.z >> 16) & 0x3fffu); }      // strict: the first maximum wins (dpmatrix.defs.h:171-174)
+      if (u.w & W_REDUCE) {      // the same row in every lane of the group
+        const unsigned segW = 1u << ((u.w >> 16) & 7u);
+        for (unsigned off = G / 2; off; off >>= 1) {      // the tree pairs lanes out of list order: a tie goes to the earlier candidate
+          const double o2 = __shfl_down_sync (gmask, acc, off, G);
           const unsigned obp = __shfl_down_sync (gmask, bp, off, G);
           if (off < segW && (acc < o2 || (acc == o2 && obp < bp))) { acc = o2; bp = obp; }
-        } else if (off < segW) acc = OP == OP_SUM ? acc + o2 : w_lse (acc, o2);
+        }
+      }
+      if ((u.z & W_LAST) && live) {
+        const unsigned dst = u.w & 0xffffu;
+        if (cur[dst] < acc) { cur[dst] = acc; bpS[dst] = (uint16_t) bp; }      // earlier phases keep ties
+      }
+      if (SILENT && (u.w & W_SYNC)) __syncwarp();
+    } else {
+      acc = OP == OP_SUM ? fma (w, x, acc) : w_lse (acc, x + w);
+      if (u.w & W_SPECIAL) {      // one test separates the plain rows (load, multiply-add) from the rest
+        if (u.w & W_REDUCE) {      // the same row in every lane of the group
+          const unsigned segW = 1u << ((u.w >> 16) & 7u);
+          for (unsigned off = G / 2; off; off >>= 1) {
+            const double o2 = __shfl_down_sync (gmask, acc, off, G);
+            if (off < segW) acc = OP == OP_SUM ? acc + o2 : w_lse (acc, o2);
+          }
+        }
+        if ((u.w & W_STORE) && live) {
+          const unsigned dst = u.w & 0xffffu;
+          const double c0 = cur[dst];
+          cur[dst] = OP == OP_SUM ? fma (f, acc, c0) : w_lse (c0, acc);
+        }
+        if (u.w & W_PEND) acc = OP == OP_SUM ? 0. : w_ninf();      // the lane's next list starts on the next row
+        if (SILENT && (u.w & W_SYNC)) __syncwarp();
       }
     }
-    if ((u.z & W_LAST) && live) {
-      const unsigned dst = u.w & 0xffffu;
-      const double c0 = cur[dst];
-      if (OP == OP_SUM) cur[dst] = fma (f, acc, c0);
-      else if (OP == OP_LSE) cur[dst] = w_lse (c0, acc);
-      else if (c0 < acc) { cur[dst] = acc; bpS[dst] = (uint16_t) bp; }      // earlier phases keep ties
-    }
-    if (SILENT && (u.w & W_SYNC)) __syncwarp();
     xn = from[v.z & 0xffffu];      // within a level no list reads a state the level writes, so this may run ahead of the adds above
   }
 }
@@ -527,7 +547,8 @@ static int schedule_lists (const std::vector<WList>& lists, const mb_machine* m,
         else en.z = (uint32_t) 0 | (0x3fffu << 16);      // padding inside a piece: weight 0 / -inf
         if (k == 0) en.z |= W_FIRST;
         en.d = (uint32_t) ls.dst | ((uint32_t) ilog2 (pl.n) << 16);
-        if (k == pl.rows - 1 && j == 0) en.z |= W_LAST;
+        if (k == pl.rows - 1) en.d |= W_PEND;
+        if (k == pl.rows - 1 && j == 0) { en.z |= W_LAST; en.d |= W_STORE; }
       }
   }
   for (auto& pl: placed)      // after every entry is in place: the reduce row is flagged in all lanes of the group

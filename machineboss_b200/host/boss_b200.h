@@ -11,10 +11,10 @@
 // INTEGRATION.md shows the ten-line adapter that flattens the reference's own EvaluatedMachine.
 //
 // Differences a caller can observe, all deliberate:
-//   * matrices do not expose cell(i,o,s): the fills keep O(strip) state on the device;
-//   * Envelope arguments are accepted and, as in the reference (dpmatrix.defs.h:3,17 build the
-//     index mapper from the SeqPair), ignored; a SeqPair carrying an alignment would select a
-//     path envelope in the reference and is rejected here (banded DP is SURVEY 8(f) row 3);
+//   * the fills keep O(strip) state on the device: the first cell(i,o,s) of a matrix fetches it (mb_matrix);
+//   * Envelope ARGUMENTS are accepted and, as in the reference (dpmatrix.defs.h:1-27 builds the index
+//     mapper from the SeqPair alone), ignored; what restricts a matrix is the SeqPair itself: one
+//     that carries an alignment gets the path envelope (Envelope::initPath), as in the reference;
 //   * the batched entry points (MachineCounts over a list, forwardLogLikes, viterbiPaths) send
 //     the whole SeqPairList to the device in one call instead of looping.
 #ifndef MB_HOST_BOSS_B200_H
@@ -217,12 +217,79 @@ struct SeqPairList {
   }
 };
 
-// Accepted for signature compatibility; the reference itself ignores a caller-supplied envelope.
+// ---- Envelope (src/seqpair.h:75-113, seqpair.cpp:100-229) ----
+// Output row j keeps input positions inStart[j] <= i < inEnd[j].
 struct Envelope {
-  long inLen = 0, outLen = 0;
-  Envelope() {}
-  Envelope (const SeqPair& sp) : inLen ((long) sp.input.seq.size()), outLen ((long) sp.output.seq.size()) {}
+  typedef long InputIndex;
+  typedef long OutputIndex;
+  InputIndex inLen = 0;
+  OutputIndex outLen = 0;
+  vector<InputIndex> inStart, inEnd;
+  Envelope() { clear(); }
+  Envelope (const SeqPair& sp) {                       // seqpair.cpp:104-110
+    if (sp.alignment.size()) initPath (sp.alignment); else initFull (sp);
+    if (!fits (sp)) throw runtime_error ("Envelope/sequence mismatch");
+  }
+  Envelope (const SeqPair& sp, size_t width) {         // seqpair.cpp:112-118
+    if (sp.alignment.size()) initPathArea (sp.alignment, width); else initFull (sp);
+    if (!fits (sp)) throw runtime_error ("Envelope/sequence mismatch");
+  }
+  void clear() { inLen = outLen = 0; inStart.assign (1, 0); inEnd.assign (1, 1); }
+  void initFull (const SeqPair& sp) {
+    clear();
+    inLen = (InputIndex) sp.input.seq.size();
+    outLen = (OutputIndex) sp.output.seq.size();
+    inStart.assign ((size_t) outLen + 1, 0);
+    inEnd.assign ((size_t) outLen + 1, inLen + 1);
+  }
+  void initPath (const SeqPair::AlignPath& cols) {     // seqpair.cpp:134-152
+    clear();
+    for (const auto& t: cols) {
+      const bool gotInput = t.first.size(), gotOutput = t.second.size();
+      if (!gotInput && gotOutput) { inStart.push_back (inEnd.back() - 1); inEnd.push_back (inEnd.back()); ++outLen; }
+      else if (gotInput && !gotOutput) { ++inEnd.back(); ++inLen; }
+      else if (gotInput && gotOutput) { inStart.push_back (inEnd.back()); inEnd.push_back (inEnd.back() + 1); ++inLen; ++outLen; }
+    }
+  }
+  void initPathArea (const SeqPair::AlignPath& cols, size_t width) {   // seqpair.cpp:154-182
+    clear();
+    vector<InputIndex> match;
+    vector<size_t> nBefore (1, 0);
+    for (const auto& t: cols) {
+      const bool gotInput = t.first.size(), gotOutput = t.second.size();
+      if (gotInput && gotOutput) match.push_back (inLen);
+      if (gotInput) ++inLen;
+      if (gotOutput) { ++outLen; nBefore.push_back (match.size()); }
+    }
+    inStart.clear();
+    inEnd.clear();
+    for (OutputIndex j = 0; j <= outLen; ++j) {
+      InputIndex iStart = 0, iEnd = inLen + 1;
+      if (nBefore[j] > width) iStart = match[nBefore[j] - width - 1] + 1;
+      const size_t nAfter = match.size() - nBefore[j];
+      if (nAfter > width) iEnd = match[nBefore[j] + width] + 1;
+      inStart.push_back (iStart);
+      inEnd.push_back (iEnd);
+    }
+  }
+  bool fits (const SeqPair& sp) const { return inLen == (InputIndex) sp.input.seq.size() && outLen == (OutputIndex) sp.output.seq.size(); }
+  static bool overlapping (InputIndex s1, InputIndex e1, InputIndex s2, InputIndex e2) { return !(s1 >= e2 || s2 >= e1); }   // seqpair.h:89-93
+  bool connected() const {                              // seqpair.cpp:188-194
+    bool conn = overlapping (inStart[0], inEnd[0], 0, 1);
+    for (OutputIndex y = 1; conn && y <= outLen; ++y) conn = conn && overlapping (inStart[y - 1], inEnd[y - 1] + 1, inStart[y], inEnd[y]);
+    return conn && overlapping (inStart[outLen], inEnd[outLen], inLen, inLen + 1);
+  }
+  bool isFull() const { for (OutputIndex j = 0; j <= outLen; ++j) if (inStart[j] != 0 || inEnd[j] != inLen + 1) return false; return true; }
+  static Envelope fullEnvelope (const SeqPair& sp) { Envelope e; e.initFull (sp); return e; }
+  void writeJson (ostream& out) const {                 // seqpair.cpp:224-229
+    out << "[";
+    for (OutputIndex j = 0; j <= outLen; ++j) out << (j ? "," : "") << "[" << inStart[j] << "," << inEnd[j] << "]";
+    out << "]";
+  }
 };
+
+inline list<Envelope> envelopes (const SeqPairList& l) { list<Envelope> e; for (const auto& sp: l.seqPairs) e.push_back (Envelope (sp)); return e; }                 // seqpair.cpp:231-236
+inline list<Envelope> envelopes (const SeqPairList& l, size_t width) { list<Envelope> e; for (const auto& sp: l.seqPairs) e.push_back (Envelope (sp, width)); return e; }   // seqpair.cpp:238-243
 
 // ---- EvaluatedMachine (src/eval.h:59-98) ----
 struct EvaluatedMachineState {
@@ -381,13 +448,28 @@ public:
     vector<uint8_t> x, y;
     vector<int64_t> xo (1, 0), yo (1, 0);
     for (const SeqPair* sp: pairs) {
-      if (sp->alignment.size()) throw runtime_error ("SeqPair carries an alignment (path envelope): banded DP is not supported by the B200 engine");
       for (auto t: m.inputTokenizer.tokenize (sp->input.seq)) x.push_back ((uint8_t) t);     // throws on unknown symbols (eval.h:33-37)
       for (auto t: m.outputTokenizer.tokenize (sp->output.seq)) y.push_back ((uint8_t) t);
       xo.push_back ((int64_t) x.size());
       yo.push_back ((int64_t) y.size());
     }
     mbCheck (mb_batch_create (&h, n, x.data(), xo.data(), y.data(), yo.data()));
+    // every matrix of a SeqPair that carries an alignment is restricted to the path envelope: the DPMatrix
+    // constructors build their index mapper from Envelope(seqPair) (dpmatrix.defs.h:3,17, seqpair.cpp:104-110)
+    bool any = false;
+    for (const SeqPair* sp: pairs) any = any || sp->alignment.size();
+    if (any) {
+      vector<int64_t> rowOff (1, 0), st, en;
+      for (const SeqPair* sp: pairs) {
+        if (sp->alignment.size()) {
+          const Envelope env (*sp);
+          st.insert (st.end(), env.inStart.begin(), env.inStart.end());
+          en.insert (en.end(), env.inEnd.begin(), env.inEnd.end());
+        }
+        rowOff.push_back ((int64_t) st.size());
+      }
+      mbCheck (mb_batch_set_envelopes (h, rowOff.data(), st.data(), en.data()));
+    }
   }
   ~DeviceBatch() { if (h) mb_batch_destroy (h); }
   DeviceBatch (const DeviceBatch&) = delete;
@@ -605,9 +687,16 @@ inline vector<double> viterbiLogLikes (const EvaluatedMachine& m, const SeqPairL
   vector<int64_t> len (n), off (n + 1, 0);
   mbCheck (mb_viterbi (m.handle(), b.handle(), sc.data(), len.data()));
   for (size_t k = 0; k < n; ++k) off[k + 1] = off[k] + len[k];
+  paths->assign (n, MachinePath());
+  if (m.nTransitions <= 256) {      // byte ids: a quarter of the device-to-host copy
+    vector<uint8_t> ids ((size_t) off[n] ? (size_t) off[n] : 1);
+    if (off[n]) mbCheck (mb_viterbi_paths_narrow (b.handle(), ids.data(), 1, off.data()));
+    for (size_t k = 0; k < n; ++k)
+      for (int64_t q = off[k]; q < off[k + 1]; ++q) (*paths)[k].trans.push_back (m.transition ((int32_t) ids[q]));
+    return sc;
+  }
   vector<int32_t> ids ((size_t) off[n] ? (size_t) off[n] : 1);
   if (off[n]) mbCheck (mb_viterbi_paths (b.handle(), ids.data(), off.data()));
-  paths->assign (n, MachinePath());
   for (size_t k = 0; k < n; ++k)
     for (int64_t q = off[k]; q < off[k + 1]; ++q) (*paths)[k].trans.push_back (m.transition (ids[q]));
   return sc;

@@ -65,6 +65,7 @@ int main (int argc, char** argv) {
     bool useDefaults = false, doT = false;
     vector<NamedSeq<string> > inSeqs, outSeqs;
     bool doL = false, doV = false, doA = false, doC = false, doSample = false;
+    string envMode;
     long long sampleSeed = 1;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
@@ -85,10 +86,24 @@ int main (int argc, char** argv) {
       else if (f == "-V" || f == "--viterbi") doV = true;
       else if (f == "-A" || f == "--align") doA = true;
       else if (f == "-C" || f == "--counts") doC = true;
+      else if (f == "--envelope") envMode = next();      // full | path | <width>: print each pair's Envelope (t/src/testenv.cpp; no device needed)
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
       else throw runtime_error ("unknown option " + f);
+    }
+    if (envMode.size()) {
+      SeqPairList data;
+      for (const auto& df: dataFiles) { SeqPairList l = SeqPairList::fromFile (df); data.seqPairs.insert (data.seqPairs.end(), l.seqPairs.begin(), l.seqPairs.end()); }
+      size_t k = 0;
+      for (const auto& sp: data.seqPairs) {
+        const Envelope env = envMode == "full" ? Envelope::fullEnvelope (sp) : envMode == "path" ? Envelope (sp) : Envelope (sp, (size_t) atoi (envMode.c_str()));
+        if (!env.connected()) throw runtime_error ("Envelope is not connected");
+        cout << (k++ ? "\n" : "");
+        env.writeJson (cout);
+      }
+      cout << endl;
+      return EXIT_SUCCESS;
     }
     if (machineFile.empty() && symbolicFile.empty()) throw runtime_error ("please specify --evaluated-machine or --machine");
     Machine machine;

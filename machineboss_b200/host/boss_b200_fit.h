@@ -501,6 +501,14 @@ struct MachineFitter {
 
   Constraints allConstraints() const { return machine.cons.combine (constraints); }
 
+  // fitter.h:18-20.  As in the reference, the envelopes handed in reach MachineCounts::add (counts.cpp:57-64) and
+  // stop there: the matrices build their own from each SeqPair (dpmatrix.defs.h:15-27), i.e. the path envelope
+  // for a pair that carries an alignment and the full matrix otherwise -- which is what DeviceBatch sets up.
+  Params fit (const SeqPairList& trainingSet, size_t width) { return fit (trainingSet, envelopes (trainingSet, width)); }
+  Params fit (const SeqPairList& trainingSet, const list<Envelope>& envs) {
+    if (envs.size() != trainingSet.seqPairs.size()) throw runtime_error ("Envelope/training set mismatch");      // fitter.cpp:24
+    return fit (trainingSet);
+  }
   Params fit (const SeqPairList& trainingSet) {
     const int MaxEMIterations = 1000;
     const double MinEMImprovement = .001;

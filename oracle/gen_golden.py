@@ -79,9 +79,11 @@ def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backw
     in_tok = {s: i + 1 for i, s in enumerate(in_alpha)}
     out_tok = {s: i + 1 for i, s in enumerate(out_alpha)}
     out_pairs = []
-    for (a, b), r in zip(sym_pairs, res["pairs"]):
+    for k, ((a, b), r) in enumerate(zip(sym_pairs, res["pairs"])):
         p = {"x": [in_tok.get(s, 0) for s in a], "y": [out_tok.get(s, 0) for s in b]}
         p.update(r)
+        if pairs and isinstance(pairs[0], dict):
+            p["alignment"] = pairs[k]["alignment"]
         out_pairs.append(p)
     j = {"name": name, "note": note, "specs": specs, "params": params, "machine": mach, "synth": synth,
          "pairs": out_pairs, "loglike": res.get("loglike"), "counts": res.get("counts"),
@@ -164,20 +166,7 @@ def main():
     case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
          note="config-4 style composite (S=308)")
     case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
-    # --- path envelopes: pairs that carry an alignment get Envelope::initPath (seqpair.cpp:104-110,134-152) ---
-    import random
-    random.seed(5)
-
-    def aligned_pair(n, name):
-        cols = []
-        for _ in range(n):
-            r = random.random()
-            a, b = random.choice("ACGT"), random.choice("ACGT")
-            cols.append([a, a] if r < 0.6 else [a, b] if r < 0.8 else [a, ""] if r < 0.9 else ["", b])
-        return {"input": {"name": name + "x"}, "output": {"name": name + "y"}, "alignment": cols}
-    case("dnapsw_path_envelope", ["preset:dnapsw"], [aligned_pair(12, "a"), aligned_pair(40, "b"), aligned_pair(1, "c"),
-                                                     {"input": {"name": "dx"}, "output": {"name": "dy"}, "alignment": [["A", ""], ["", "C"], ["G", "G"]]}],
-         params=peaked, matrices=True, note="pairs with an alignment: every matrix is restricted to the path envelope")
+    envelope_case()
     env_expect = {}
     for nm in ("tinypath_full", "tinypath_path", "smallpath_path", "smallpath_area0", "smallpath_area1", "smallpath_area2",
                "smallpath_area3", "smallpath_area4", "asympath_area0", "asympath_area1"):
@@ -210,6 +199,27 @@ def main():
          note="BASELINE config 1: one 1 kb x 1 kb pair")
 
 
+def envelope_case():
+    peaked = {"gapOpen": 0.05, "gapExtend": 0.5, "eqmA": 0.25, "eqmC": 0.25, "eqmG": 0.25, "eqmT": 0.25}
+    for a in "ACGT":
+        for b in "ACGT":
+            peaked["sub%s%s" % (a, b)] = 0.91 if a == b else 0.03
+    # --- path envelopes: pairs that carry an alignment get Envelope::initPath (seqpair.cpp:104-110,134-152) ---
+    import random
+    random.seed(5)
+
+    def aligned_pair(n, name):
+        cols = []
+        for _ in range(n):
+            r = random.random()
+            a, b = random.choice("ACGT"), random.choice("ACGT")
+            cols.append([a, a] if r < 0.6 else [a, b] if r < 0.8 else [a, ""] if r < 0.9 else ["", b])
+        return {"input": {"name": name + "x"}, "output": {"name": name + "y"}, "alignment": cols}
+    case("dnapsw_path_envelope", ["preset:dnapsw"], [aligned_pair(12, "a"), aligned_pair(40, "b"), aligned_pair(1, "c"),
+                                                     {"input": {"name": "dx"}, "output": {"name": "dy"}, "alignment": [["A", ""], ["", "C"], ["G", "G"]]}],
+         params=peaked, matrices=True, note="pairs with an alignment: every matrix is restricted to the path envelope")
+
+
 def sample_case():
     """ForwardMatrix::samplePath (forward.cpp:17-19): paths drawn by the reference with mt19937 (seed + pair index)."""
     peaked = {"gapOpen": 0.05, "gapExtend": 0.5, "eqmA": 0.25, "eqmC": 0.25, "eqmG": 0.25, "eqmT": 0.25}
@@ -239,6 +249,8 @@ def sample_case():
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sample":
         sample_case()
+    elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "envelope":
+        envelope_case()
     else:
         main()
         sample_case()

@@ -123,6 +123,14 @@ def test_against_oracle_ragged_batch(engine):
         assert paths[k].tolist() == p.tolist()
         orc.counts(x, y, counts=want_cnt)
     np.testing.assert_allclose(cnt, want_cnt, rtol=REL, atol=1e-7)
+    # the same paths through the caller-owned-buffer entry points, ids as int32, uint16 and bytes (mb_viterbi_paths_narrow)
+    for dt in (np.int32, np.uint16, np.uint8):
+        score, plen, off = np.empty(len(pairs)), np.zeros(len(pairs), np.int64), np.zeros(len(pairs) + 1, np.int64)
+        trans = np.zeros(sum(len(p) for p in paths) + 3, dtype=dt)
+        total = capi.viterbi_into(m, b, score, plen, off, trans)
+        assert total == sum(len(p) for p in paths) and np.array_equal(score, sc)
+        for k, p in enumerate(paths):
+            assert trans[off[k]:off[k + 1]].tolist() == p.tolist(), (dt, k)
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -104,3 +104,41 @@ def test_cli_sample_paths_match_the_reference():
     r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "--sample-paths", str(g["seed"])], capture_output=True, text=True, check=True)
     got = json.loads(r.stdout)
     assert got == [p["sample"] for p in g["pairs"]]
+
+
+def test_cli_envelopes_match_the_reference_goldens():
+    """Makefile:450-462 test-env: Envelope::initFull / initPath / initPathArea of the host mirror against
+    t/expect/*_env.json (CPU only: no device involved)."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_envelopes.json")) as f:
+        g = json.load(f)
+    cases = [("tinypath", "full", "tinypath_full"), ("tinypath", "path", "tinypath_path"), ("smallpath", "path", "smallpath_path"),
+             ("smallpath", "0", "smallpath_area0"), ("smallpath", "1", "smallpath_area1"), ("smallpath", "2", "smallpath_area2"),
+             ("smallpath", "3", "smallpath_area3"), ("smallpath", "4", "smallpath_area4"), ("smallpath", "5", "smallpath_area4"),
+             ("asympath", "0", "asympath_area0"), ("asympath", "1", "asympath_area1")]
+    for inp, mode, want in cases:
+        pf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+        json.dump([g[inp]], pf)
+        pf.close()
+        r = subprocess.run([_cli(), "-D", pf.name, "--envelope", mode], capture_output=True, text=True, check=True)
+        assert json.loads(r.stdout) == g["expect"][want], (inp, mode)
+
+
+@pytest.mark.gpu
+def test_cli_pairs_with_alignments_get_the_path_envelope():
+    """A SeqPair that carries an alignment restricts every matrix to the path envelope (seqpair.cpp:104-110,
+    dpmatrix.defs.h:3): -L, -V and -C through the host mirror against the reference's values for such pairs."""
+    case = load_golden("dnapsw_path_envelope")
+    pf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k}, "output": {"name": "y%d" % k}, "alignment": p["alignment"]} for k, p in enumerate(case["pairs"])], pf)
+    pf.close()
+    mf = _machine_file(case)
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "-L"], capture_output=True, text=True, check=True)
+    for row, p in zip(json.loads(r.stdout.replace("-Infinity", '"-Infinity"')), case["pairs"]):
+        assert abs(gnum(row[2]) - gnum(p["forward"])) <= 1e-5 * max(1.0, abs(gnum(p["forward"]))), (row, p["forward"])      # 6 significant digits printed
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "-V"], capture_output=True, text=True, check=True)
+    for row, p in zip(json.loads(r.stdout.replace("-Infinity", '"-Infinity"')), case["pairs"]):
+        assert abs(gnum(row[2]) - gnum(p["viterbi"])) <= 1e-5 * max(1.0, abs(gnum(p["viterbi"]))), (row, p["viterbi"])
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "-C"], capture_output=True, text=True, check=True)
+    got = np.array([v for row in json.loads(r.stdout) for v in row], dtype=np.float64)
+    want = np.array([gnum(v) for v in case["counts"]])
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
