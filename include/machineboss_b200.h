@@ -96,8 +96,8 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff);
 
 /* The same paths with ids narrowed to bytesPerId = 1 or 2 bytes (4: as mb_viterbi_paths), for machines with at
  * most 256 / 65 536 transitions: the paths of 10 000 dnapsw pairs of 1 kb are 150 MB as int32 and 37 MB as
- * bytes, and the copy to the host is what an end-to-end call waits for last.  pathOff must be the packed
- * layout (pathOff[k+1] = pathOff[k] + pathLen[k]); pair k's ids go to element pathOff[k] onwards. */
+ * bytes, and the copy to the host is what an end-to-end call waits for last.  Pair k's ids go to elements
+ * pathOff[k] .. pathOff[k] + pathLen[k]. */
 int mb_viterbi_paths_narrow (mb_batch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff);
 
 /* ---- MachineCounts over a list (src/counts.cpp:37-64, src/backward.cpp:62-87) ----

@@ -523,16 +523,24 @@ int mb_viterbi_paths_narrow (mb_batch* b, void* pathTrans, int32_t bytesPerId, c
   int64_t total = 0;
   for (int64_t k = 0; k < b->nPairs; ++k) total += b->pathLen[k];
   if (!total) return 0;
-  for (int64_t k = 0; k < b->nPairs; ++k)
-    if (pathOff[k] - pathOff[0] != b->pathStart[k]) { set_error ("mb_viterbi_paths_narrow: paths must be requested packed, in the order mb_viterbi stored them"); return 1; }
+  bool contiguous = true;      // the engines pack in their own order (JIT: pair order; wide, lane: longest first)
+  for (int64_t k = 0; k < b->nPairs && contiguous; ++k) contiguous = (pathOff[k] - pathOff[0] == b->pathStart[k]);
   void* tmp = ws_reserve (b, WS_PATHNARROW, (size_t) total * bytesPerId);
   if (!tmp) return 1;
   const unsigned grid = (unsigned) std::min<int64_t> ((total + 255) / 256, 148 * 16);
   if (bytesPerId == 1) narrow_ids_kernel<uint8_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint8_t*) tmp, total);
   else narrow_ids_kernel<uint16_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint16_t*) tmp, total);
   MB_CUDA (cudaGetLastError());
-  MB_CUDA (cudaMemcpyAsync ((char*) pathTrans + pathOff[0] * bytesPerId, tmp, (size_t) total * bytesPerId, cudaMemcpyDeviceToHost, b->stream));
+  if (contiguous) {
+    MB_CUDA (cudaMemcpyAsync ((char*) pathTrans + pathOff[0] * bytesPerId, tmp, (size_t) total * bytesPerId, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    return 0;
+  }
+  std::vector<char> host ((size_t) total * bytesPerId);
+  MB_CUDA (cudaMemcpyAsync (host.data(), tmp, host.size(), cudaMemcpyDeviceToHost, b->stream));
   MB_CUDA (cudaStreamSynchronize (b->stream));
+  for (int64_t k = 0; k < b->nPairs; ++k)
+    memcpy ((char*) pathTrans + pathOff[k] * bytesPerId, host.data() + b->pathStart[k] * bytesPerId, (size_t) b->pathLen[k] * bytesPerId);
   return 0;
 }
 
