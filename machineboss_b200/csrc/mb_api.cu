@@ -326,7 +326,7 @@ int mb_machine_update_weights (mb_machine* m, const double* logWeight) {
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
     MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
   }
-  if ((m->wide || m->lane) && wide_update_weights (m)) return 1;
+  if ((m->wide || m->lane || m->big) && wide_update_weights (m)) return 1;
   if (m->engine == MB_ENGINE_JIT) return jit_update_weights (m);
   return 0;
 }
@@ -564,7 +564,7 @@ int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int6
   m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);
   m.lw.assign ((size_t) nTrans, 0.);
   std::string l;
-  const int rc = jit_compile_check (&m, &l);
+  const int rc = m.S > 16 ? big_compile_check (&m, &l) : jit_compile_check (&m, &l);      // mid-size machines: the big engine's generated sweep
   if (log && logCap > 0) { strncpy (log, l.c_str(), (size_t) logCap - 1); log[logCap - 1] = 0; }
   return rc;
 }

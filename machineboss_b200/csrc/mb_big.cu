@@ -1,0 +1,262 @@
+// mb_big.cu -- the big engine: machine-specialised Forward sweep (scaled linear domain) for MID-SIZE machines,
+// tens to hundreds of states -- composed transducers such as prot2dna => dnapsw (308 states, 716 transition
+// groups), SURVEY.md section 8 config 4 -- over full two-dimensional matrices.
+//
+//   reference                                              here
+//   MappedForwardMatrix::fill / logLike  forward.defs.h:22-55   mb_k_big_forward (generated, NVRTC, sm_100a)
+//
+// The wide engine (mb_wide.cu) interprets such a machine from tables with a group of lanes per cell and
+// spends ~75 thread-instructions per transition on decode, flags, gathers and level barriers (150 GCUPS on
+// prot2dna => dnapsw, FP64 pipe 6 % busy).  Here the machine is written out the way mb_jit.cu does for small
+// machines -- one multiply-add per transition group, straight-line, in state order -- but with a THREAD PER
+// CELL (lane = matrix column, mb_big_skeleton.h) and the cell's long-lived states in shared memory instead
+// of registers: the states insert groups read from the cell above sit in the lane's column of a
+// shared-memory array, the few that delete / match groups read from the cell to the left arrive by shuffle,
+// silent weights are constant-memory operands, emission weights token-indexed shared-memory tables.
+// Transition groups = all transitions between one (source, destination) of one kind, weight looked up by
+// token (0 where no transition carries that label), as in mb_jit.cu.
+//
+// Reached through the wide engine (wide_forward) for batches of full matrices; envelopes, Viterbi, and pairs
+// the scaled sweep flags stay with the wide engine.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <tuple>
+
+#include "mb_internal.h"
+#include "mb_big_skeleton.h"
+
+namespace mb {
+
+struct BigGroup { int self, type, other, rank; int emitOff = -1, silIdx = -1, tableSize = 1; std::vector<std::pair<int, int64_t>> entries; };      // (label, transition)
+
+struct BigEngine {
+  std::vector<BigGroup> groups;      // by (destination, kind, source, rank): the reference's candidate order
+  std::vector<int> liveU, liveL;     // sources of insert groups; sources of delete / match groups
+  int nEmit = 0, nSil = 0, threads = 128;
+  std::string source;
+  void* mod = nullptr;
+  void* kForward = nullptr;
+  void* dSil = nullptr;              // __constant__ mb_big_sil in the module
+  double* dEmit = nullptr;
+  size_t smemBytes = 0;
+  int blocksPerSM = 1, numSMs = 148;
+  bool linearOK = false;
+};
+
+static BigEngine* be (const mb_machine* m) { return static_cast<BigEngine*> (m->big); }
+
+static int big_type (int a, int b) { return a ? (b ? T_MATCH : T_DELETE) : (b ? T_INSERT : T_SILENT); }
+
+static void big_plan (const mb_machine* m, BigEngine& B) {
+  std::map<std::tuple<int, int, int, int>, BigGroup> g;
+  std::map<std::tuple<int, int, int, int>, int> seen;
+  for (int64_t t = 0; t < m->T; ++t) {
+    const int type = big_type (m->in[t], m->out[t]);
+    if (type == T_SILENT && m->dst[t] <= m->src[t]) continue;      // only possible on state 0 (machine.cpp:759); contributes nothing
+    const int li = type == T_MATCH ? (m->in[t] - 1) * m->nOut + (m->out[t] - 1) : type == T_DELETE ? m->in[t] - 1 : type == T_INSERT ? m->out[t] - 1 : 0;
+    const int rank = seen[std::make_tuple ((int) m->dst[t], type, (int) m->src[t], li)]++;
+    BigGroup& gr = g[std::make_tuple ((int) m->dst[t], type, (int) m->src[t], rank)];
+    gr.self = m->dst[t]; gr.type = type; gr.other = m->src[t]; gr.rank = rank;
+    gr.entries.push_back ({ li, t });
+  }
+  B.groups.clear();
+  B.nEmit = B.nSil = 0;
+  std::vector<char> isU ((size_t) m->S, 0), isL ((size_t) m->S, 0);
+  for (auto& kv: g) {
+    BigGroup gr = kv.second;
+    gr.tableSize = gr.type == T_MATCH ? m->nIn * m->nOut : gr.type == T_DELETE ? m->nIn : gr.type == T_INSERT ? m->nOut : 1;
+    if (gr.type == T_SILENT) gr.silIdx = B.nSil++;
+    else { gr.emitOff = B.nEmit; B.nEmit += gr.tableSize; }
+    if (gr.type == T_INSERT) isU[gr.other] = 1;
+    if (gr.type == T_DELETE || gr.type == T_MATCH) isL[gr.other] = 1;
+    B.groups.push_back (gr);
+  }
+  B.liveU.clear(); B.liveL.clear();
+  for (int s = 0; s < m->S; ++s) { if (isU[s]) B.liveU.push_back (s); if (isL[s]) B.liveL.push_back (s); }
+}
+
+bool big_supported (const mb_machine* m, std::string* why) {
+  auto no = [&] (const char* w) { if (why) *why = w; return false; };
+  if (getenv ("MB_NO_BIG")) return no ("big engine: disabled (MB_NO_BIG)");
+  if (m->S <= 16) return no ("big engine: small machines belong to the JIT engine");
+  if (m->S > 1024 || m->T > 65536) return no ("big engine: more than 1024 states or 65536 transitions");
+  if (m->nIn == 0 || m->nOut == 0) return no ("big engine: no two-dimensional matrices without both alphabets");
+  BigEngine B;
+  big_plan (m, B);
+  if (B.groups.size() > 6000) return no ("big engine: more than 6000 transition groups");
+  if (B.nSil > 7000) return no ("big engine: silent weights exceed constant memory");
+  if (B.liveL.size() > 24) return no ("big engine: more than 24 states cross a column boundary");
+  const size_t smem = (size_t) (((B.nEmit + 1) & ~1) + 4 * (B.liveU.size() * 32 + 16 * std::max<size_t> (B.liveL.size(), 1))) * 8;
+  if (smem > 220 * 1024) return no ("big engine: emission tables and live states do not fit in shared memory");
+  return true;
+}
+
+static void big_generate (const mb_machine* m, BigEngine& B) {
+  big_plan (m, B);
+  const int S = m->S, nLL = std::max<int> ((int) B.liveL.size(), 1);
+  std::vector<int> uIdx ((size_t) S, -1), lIdx ((size_t) S, -1);
+  for (size_t q = 0; q < B.liveU.size(); ++q) uIdx[B.liveU[q]] = (int) q;
+  for (size_t q = 0; q < B.liveL.size(); ++q) lIdx[B.liveL[q]] = (int) q;
+  std::ostringstream o;
+  o << "// generated by machineboss_b200 (mb_big.cu) for a machine with " << S << " states, " << m->T << " transitions, " << B.groups.size() << " transition groups\n";
+  o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
+  o << "#define MB_S " << S << "\n#define MB_NLU " << B.liveU.size() << "\n#define MB_NLL " << nLL << "\n#define MB_NEMIT " << std::max (B.nEmit, 1)
+    << "\n#define MB_BIG_THREADS " << B.threads << "\n";
+  o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n\n";
+  // the cell: live-up states read from (and written back to) the lane's column of `up`, left / diagonal cells' states in L / D
+  o << "__device__ __forceinline__ void mb_big_cell (double* __restrict__ up, const double (&L)[MB_NLL], const double (&D)[MB_NLL], double (&Lo)[MB_NLL], "
+       "const int a, const int b, const bool origin, const double* __restrict__ E, double& res) {\n";
+  std::vector<char> loaded ((size_t) S, 0);
+  size_t gi = 0;
+  for (int d = 0; d < S; ++d) {
+    bool first = true;
+    for (; gi < B.groups.size() && B.groups[gi].self == d; ++gi) {
+      const BigGroup& gr = B.groups[gi];
+      std::ostringstream src, w;
+      if (gr.type == T_INSERT) {
+        if (!loaded[gr.other]) { o << "  const double u" << gr.other << " = up[" << uIdx[gr.other] << " * 32];\n"; loaded[gr.other] = 1; }
+        src << "u" << gr.other; w << "E[" << gr.emitOff << " + b]";
+      } else if (gr.type == T_DELETE) { src << "L[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a]"; }
+      else if (gr.type == T_MATCH) { src << "D[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a * " << m->nOut << " + b]"; }
+      else { src << "n" << gr.other; w << "mb_big_sil[" << gr.silIdx << "]"; }
+      if (first) { o << "  double n" << d << " = " << src.str() << " * " << w.str() << ";\n"; first = false; }
+      else o << "  n" << d << " = fma (" << src.str() << ", " << w.str() << ", n" << d << ");\n";
+    }
+    if (first) o << "  double n" << d << " = 0.0;\n";
+    if (d == 0) o << "  if (origin) n0 = 1.0;\n";
+  }
+  for (size_t q = 0; q < B.liveU.size(); ++q) o << "  up[" << q << " * 32] = n" << B.liveU[q] << ";\n";
+  for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
+  if (B.liveL.empty()) o << "  Lo[0] = 0.0;\n";
+  o << "  res = n" << S - 1 << ";\n}\n";
+  o << kBigSkeleton;
+  B.source = o.str();
+}
+
+int big_compile_check (const mb_machine* m, std::string* log) {
+  std::string why;
+  if (!big_supported (m, &why)) { set_error ("machine not eligible for the big engine: " + why); return 1; }
+  BigEngine B;
+  big_generate (m, B);
+  std::vector<char> cubin;
+  return rt_compile (B.source, ".big.cu", cubin, log);
+}
+
+void big_destroy (mb_machine* m) {
+  BigEngine* B = be (m);
+  if (!B) return;
+  if (B->mod) rt_unload (B->mod);
+  if (B->dEmit) cudaFree (B->dEmit);
+  delete B;
+  m->big = nullptr;
+}
+
+int big_update_weights (mb_machine* m) {
+  BigEngine* B = be (m);
+  if (!B) return 0;
+  std::vector<double> emit ((size_t) std::max (B->nEmit, 1), 0.), sil ((size_t) std::max (B->nSil, 1), 0.);
+  bool ok = true;
+  const double lim = 24.0 * 0.6931471805599453;
+  for (auto& gr: B->groups)
+    for (auto& e: gr.entries) {
+      const double lw = m->lw[e.second];
+      if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
+      if (gr.type == T_SILENT) sil[gr.silIdx] = std::exp (lw); else emit[(size_t) gr.emitOff + e.first] = std::exp (lw);
+    }
+  B->linearOK = ok;
+  MB_CUDA (cudaSetDevice (m->device));
+  MB_CUDA (cudaMemcpy (B->dEmit, emit.data(), emit.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (B->dSil, sil.data(), sil.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int big_prepare (mb_machine* m) {
+  BigEngine* B = new BigEngine;
+  m->big = B;
+  big_generate (m, *B);
+  std::vector<char> cubin;
+  if (rt_compile (B->source, ".big.cu", cubin, nullptr)) return 1;
+  MB_CUDA (cudaSetDevice (m->device));
+  if (rt_load (cubin, &B->mod) || rt_function (B->mod, "mb_k_big_forward", &B->kForward)) return 1;
+  size_t bytes = 0;
+  if (rt_global (B->mod, "mb_big_sil", &B->dSil, &bytes)) return 1;
+  MB_CUDA (cudaMalloc (&B->dEmit, (size_t) std::max (B->nEmit, 1) * 8));
+  MB_CUDA (cudaDeviceGetAttribute (&B->numSMs, cudaDevAttrMultiProcessorCount, m->device));
+  const int warps = B->threads / 32, nLL = std::max<int> ((int) B->liveL.size(), 1);
+  B->smemBytes = (size_t) (((std::max (B->nEmit, 1) + 1) & ~1) + warps * ((int) B->liveU.size() * 32 + 16 * nLL)) * 8;
+  if (rt_prepare (B->kForward, B->threads, B->smemBytes, &B->blocksPerSM)) return 1;
+  if (B->blocksPerSM < 1) { set_error ("big engine: the kernel does not fit on an SM"); return 1; }
+  if (getenv ("MB_WIDE_VERBOSE"))
+    fprintf (stderr, "big engine: S=%d groups=%zu (silent %d), live-up %zu, left-going %zu, emission table %d doubles, %zu B smem, %d CTA(s)/SM\n",
+             m->S, B->groups.size(), B->nSil, B->liveU.size(), B->liveL.size(), B->nEmit, B->smemBytes, B->blocksPerSM);
+  return big_update_weights (m);
+}
+
+bool big_wanted (const mb_machine* m, const mb_batch* b) {
+  if (!m->big || !be (m)->linearOK || b->hasEnv) return false;
+  return true;
+}
+
+struct MBBigArgsHost {      // must match struct MBBigArgs in the skeleton
+  const uint8_t* x; const int64_t* xOff;
+  const uint8_t* y; const int64_t* yOff;
+  const int64_t* order; int64_t nWork; unsigned long long* counter;
+  double* bnd; int64_t bndStride;
+  double* result; int32_t* flag;
+  const double* emit;
+};
+
+int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
+  BigEngine& B = *be (m);
+  b->lastRedo = 0;
+  if (b->nPairs == 0) return 0;
+  std::vector<int64_t> order ((size_t) b->nPairs);
+  for (int64_t k = 0; k < b->nPairs; ++k) order[k] = k;
+  auto cost = [&] (int64_t k) { return (double) (b->xOff[k + 1] - b->xOff[k] + 1) * (double) (b->yOff[k + 1] - b->yOff[k] + 1); };
+  std::stable_sort (order.begin(), order.end(), [&] (int64_t p, int64_t q) { return cost (p) > cost (q); });
+  int64_t maxLo = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
+  const int warps = B.threads / 32, nLL = std::max<int> ((int) B.liveL.size(), 1);
+  const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) B.numSMs * B.blocksPerSM, (b->nPairs + warps - 1) / warps));
+  const int64_t bndStride = 2 * (maxLo + 1) * (nLL + 1);
+  b->wsOrderHoldsFull = false;
+  int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
+  unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+  double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (grid * warps * bndStride) * 8);
+  double* dRes = (double*) ws_reserve (b, WS_RESULT, (size_t) b->nPairs * 8);
+  int32_t* dFlag = (int32_t*) ws_reserve (b, WS_FLAG, (size_t) b->nPairs * 4);
+  if (!dOrder || !dCounter || !dBnd || !dRes || !dFlag) return 1;
+  MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
+  MB_CUDA (cudaMemsetAsync (dFlag, 0, (size_t) b->nPairs * 4, b->stream));
+  MBBigArgsHost A;
+  A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
+  A.order = dOrder; A.nWork = b->nPairs; A.counter = dCounter;
+  A.bnd = dBnd; A.bndStride = bndStride;
+  A.result = dRes; A.flag = dFlag; A.emit = B.dEmit;
+  void* params[1] = { &A };
+  if (timing_begin (b)) return 1;
+  if (rt_launch (B.kForward, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params)) return 1;
+  std::vector<int32_t> flag ((size_t) b->nPairs);
+  MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
+  MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, flag.size() * 4, cudaMemcpyDeviceToHost, b->stream));
+  MB_CUDA (cudaStreamSynchronize (b->stream));
+  std::vector<int64_t> redo;
+  for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
+  int64_t launches = 1;
+  if (!redo.empty()) {      // dangerous dynamic range, or no path at all: the wide engine's log-domain sweep decides
+    if (wide_forward_log_subset (m, b, redo, dRes)) return 1;
+    ++launches;
+  }
+  b->lastRedo = (int64_t) redo.size();
+  if (timing_end (b, launches)) return 1;
+  if (!redo.empty()) MB_CUDA (cudaMemcpy (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace mb

@@ -90,6 +90,9 @@ struct mb_machine {
   void* wide = nullptr;
   // lane engine (mb_lane.cu): the wide engine's path for batches without input sequences
   void* lane = nullptr;
+  // big engine (mb_big.cu): generated straight-line Forward sweep for mid-size machines, reached through the wide engine
+  void* big = nullptr;
+  bool bigTried = false;
 };
 
 struct mb_batch {
@@ -158,6 +161,26 @@ int lane_update_weights (mb_machine* m);
 bool lane_wanted (const mb_machine* m, const mb_batch* b);      // no input sequences, no envelopes
 int lane_forward (mb_machine* m, mb_batch* b, double* loglike);
 int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+
+// ---- big engine (mb_big.cu): machine-specialised Forward sweep for mid-size machines (a thread per cell, the cell as
+// straight-line code); full two-dimensional matrices only; flagged pairs go back to the wide engine's log-domain sweep ----
+bool big_supported (const mb_machine* m, std::string* why);
+int big_compile_check (const mb_machine* m, std::string* log);      // generate + NVRTC-compile without a device
+int big_prepare (mb_machine* m);
+void big_destroy (mb_machine* m);
+int big_update_weights (mb_machine* m);
+bool big_wanted (const mb_machine* m, const mb_batch* b);
+int big_forward (mb_machine* m, mb_batch* b, double* loglike);
+int wide_forward_log_subset (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, double* dResult);      // mb_wide.cu
+
+// run-time compilation plumbing shared by the generated engines (mb_jit.cu)
+int rt_compile (const std::string& source, const char* dumpSuffix, std::vector<char>& cubin, std::string* log);
+int rt_load (const std::vector<char>& cubin, void** module);
+void rt_unload (void* module);
+int rt_function (void* module, const char* name, void** fn);
+int rt_global (void* module, const char* name, void** devPtr, size_t* bytes);
+int rt_prepare (void* fn, int threads, size_t smemBytes, int* blocksPerSM);
+int rt_launch (void* fn, unsigned grid, unsigned threads, size_t smemBytes, cudaStream_t stream, void** params);
 
 // per-batch workspace (mb_api.cu)
 enum WsSlot { WS_ORDER = 0, WS_BND, WS_RESULT, WS_RESULT2, WS_TB, WS_TBOFF, WS_F, WS_FOFF, WS_COUNTS, WS_PAIRS, WS_LEN, WS_OUTOFF, WS_COUNTER, WS_FLAG, WS_EF, WS_EFOFF, WS_PATHTMP, WS_PATHTMPOFF, WS_PATHNARROW, WS_NSLOTS };

@@ -36,6 +36,7 @@ struct Driver {
   CUresult (*ModuleLoadData) (CUmodule*, const void*) = nullptr;
   CUresult (*ModuleUnload) (CUmodule) = nullptr;
   CUresult (*ModuleGetFunction) (CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal) (CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel) (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*FuncSetAttribute) (CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*FuncGetAttribute) (int*, CUfunction_attribute, CUfunction) = nullptr;
@@ -68,6 +69,7 @@ static bool load_driver() {
   };
   bool ok = get ("cuModuleLoadData", (void**) &g_drv.ModuleLoadData) && get ("cuModuleUnload", (void**) &g_drv.ModuleUnload)
     && get ("cuModuleGetFunction", (void**) &g_drv.ModuleGetFunction) && get ("cuLaunchKernel", (void**) &g_drv.LaunchKernel)
+    && get ("cuModuleGetGlobal", (void**) &g_drv.ModuleGetGlobal)
     && get ("cuFuncSetAttribute", (void**) &g_drv.FuncSetAttribute) && get ("cuFuncGetAttribute", (void**) &g_drv.FuncGetAttribute)
     && get ("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**) &g_drv.OccupancyMaxActiveBlocksPerMultiprocessor)
     && get ("cuGetErrorString", (void**) &g_drv.GetErrorString);
@@ -183,8 +185,9 @@ struct JitEngine {
   int CV = 4, minBlocksV = 4;
   // the same three kernels at C columns per lane (first module): chosen per call for batches whose pairs
   // would leave most of a 32 * CV column strip empty (300 aa proteins: 2 strips of 256 against 3 of 128)
-  CUfunction kViterbiN = nullptr, kForwardLinN = nullptr, kBackwardLinN = nullptr;
-  int blocksPerSMN[3] = { 1, 1, 1 };
+  CUfunction kViterbiN = nullptr, kForwardLinN = nullptr, kBackwardLinN = nullptr, kViterbiScoreN = nullptr;
+  int blocksPerSMN[4] = { 1, 1, 1, 1 };
+  CUfunction kViterbiScore = nullptr;      // Viterbi without back-pointers (mb_viterbi with pathLen == NULL, boss -V)
   std::string sourceV;
   // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
   // start state); the others follow from them inside the cell through the silent groups
@@ -195,8 +198,8 @@ struct JitEngine {
   std::string source;
   CUmodule mod = nullptr;
   CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
-  int blocksPerSM[9] = { 1, 1, 1, 1, 1, 1, 1, 1, 1 };
-  size_t smemBytes[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  int blocksPerSM[10] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };      // index 9: mb_k_viterbi_score
+  size_t smemBytes[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
   std::vector<int> ctxBase;              // per backward slot, -1 for silent
   int32_t* dIdTabB = nullptr;
@@ -485,6 +488,7 @@ static int compile (mb_machine* m, JitEngine& J) {
   if (!cu_ok (g_drv.ModuleGetFunction (&J.kForward, J.mod, "mb_k_forward"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackward, J.mod, "mb_k_backward"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbi, J.modV ? J.modV : J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
+      || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScore, J.modV ? J.modV : J.mod, "mb_k_viterbi_score"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStore, J.mod, "mb_k_fstore"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCounts, J.mod, "mb_k_bcounts"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLin, J.modV ? J.modV : J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
@@ -492,14 +496,15 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
   if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiN, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreN, J.mod, "mb_k_viterbi_score"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLinN, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLinN, J.mod, "mb_k_backward_lin"), "cuModuleGetFunction"))) return 1;
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[9] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin };
-  const int ne[9] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit };
-  for (int q = 0; q < 9; ++q) {
+  CUfunction fn[10] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin, J.kViterbiScore };
+  const int ne[10] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit };
+  for (int q = 0; q < 10; ++q) {
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
     J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (16 + 32 * (m->S + 1))) * 8
       + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0)
@@ -510,9 +515,9 @@ static int compile (mb_machine* m, JitEngine& J) {
     J.blocksPerSM[q] = std::max (1, nb);
   }
   if (J.modV) {
-    CUfunction fnN[3] = { J.kViterbiN, J.kForwardLinN, J.kBackwardLinN };
-    const int qOf[3] = { 2, 5, 6 };
-    for (int q = 0; q < 3; ++q) {
+    CUfunction fnN[4] = { J.kViterbiN, J.kForwardLinN, J.kBackwardLinN, J.kViterbiScoreN };
+    const int qOf[4] = { 2, 5, 6, 9 };
+    for (int q = 0; q < 4; ++q) {
       if (!cu_ok (g_drv.FuncSetAttribute (fnN[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[qOf[q]]), "cuFuncSetAttribute")) return 1;
       int nb = 0;
       if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, fnN[q], J.threads, J.smemBytes[qOf[q]]), "occupancy")) return 1;
@@ -535,6 +540,40 @@ static bool use_narrow (const JitEngine& J, const mb_batch* b, const std::vector
     cellsW += std::ceil ((Li + 1) / (32.0 * J.CV)) * 32.0 * J.CV * rows;
   }
   return cellsN < (viterbi ? 0.60 : 0.87) * cellsW;
+}
+
+// ---- the same run-time compilation plumbing for the other generated engine (mb_big.cu) ----
+int rt_compile (const std::string& source, const char* dumpSuffix, std::vector<char>& cubin, std::string* log) { return nvrtc_compile (source, dumpSuffix, cubin, log); }
+int rt_load (const std::vector<char>& cubin, void** module) {
+  if (!load_driver()) return 1;
+  MB_CUDA (cudaFree (0));
+  CUmodule mod = nullptr;
+  if (!cu_ok (g_drv.ModuleLoadData (&mod, cubin.data()), "cuModuleLoadData")) return 1;
+  *module = mod;
+  return 0;
+}
+void rt_unload (void* module) { if (module && g_drv.ModuleUnload) g_drv.ModuleUnload ((CUmodule) module); }
+int rt_function (void* module, const char* name, void** fn) {
+  CUfunction f = nullptr;
+  if (!cu_ok (g_drv.ModuleGetFunction (&f, (CUmodule) module, name), "cuModuleGetFunction")) return 1;
+  *fn = f;
+  return 0;
+}
+int rt_global (void* module, const char* name, void** devPtr, size_t* bytes) {
+  CUdeviceptr p = 0;
+  if (!cu_ok (g_drv.ModuleGetGlobal (&p, bytes, (CUmodule) module, name), "cuModuleGetGlobal")) return 1;
+  *devPtr = (void*) p;
+  return 0;
+}
+int rt_prepare (void* fn, int threads, size_t smemBytes, int* blocksPerSM) {
+  if (!cu_ok (g_drv.FuncSetAttribute ((CUfunction) fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) smemBytes), "cuFuncSetAttribute")) return 1;
+  int nb = 0;
+  if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, (CUfunction) fn, threads, smemBytes), "occupancy")) return 1;
+  *blocksPerSM = nb;
+  return 0;
+}
+int rt_launch (void* fn, unsigned grid, unsigned threads, size_t smemBytes, cudaStream_t stream, void** params) {
+  return cu_ok (g_drv.LaunchKernel ((CUfunction) fn, grid, 1, 1, threads, 1, 1, (unsigned) smemBytes, (CUstream) stream, params, nullptr), "cuLaunchKernel") ? 0 : 1;
 }
 
 static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>& ef, std::vector<double>& eb) {
@@ -764,13 +803,13 @@ struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const dou
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
                    const CountArgs& ca = CountArgs(), bool narrow = false) {
   JitEngine& J = *(JitEngine*) m->jit;
-  narrow = narrow && J.modV && (which == 2 || which == 5 || which == 6);
-  CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : J.kBackwardLinN) : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
-  const bool lin = which >= 5;
+  narrow = narrow && J.modV && (which == 2 || which == 5 || which == 6 || which == 9);
+  CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : which == 6 ? J.kBackwardLinN : J.kViterbiScoreN) : which == 9 ? J.kViterbiScore : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
+  const bool lin = which >= 5 && which <= 8;      // 9: the score-only Viterbi, log domain
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
-  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : 2] : J.blocksPerSM[which]);
+  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[which]);
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
@@ -796,7 +835,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (getenv ("MB_JIT_VERBOSE"))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[which], ((which == 2 || which == 5 || which == 6) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+             J.smemBytes[which], J.blocksPerSM[which], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
@@ -971,6 +1010,15 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
   const bool narrow = use_narrow (J, b, full_order (b), true);
+  if (!trace) {      // scores only (boss -V): no back-pointers, no scratch beyond the strip boundaries
+    double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
+    if (!dRes) return 1;
+    if (timing_begin (b)) return 1;
+    if (launch (m, b, 9, full_order (b), dRes, nullptr, nullptr, CountArgs(), narrow)) return 1;
+    if (timing_end (b, 1)) return 1;
+    MB_CUDA (cudaMemcpy (score, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  }
   const int W = 32 * (narrow ? J.C : J.CV);
   // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
   double wanted = 0;

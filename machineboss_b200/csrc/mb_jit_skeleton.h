@@ -105,6 +105,7 @@ template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { re
 #define MB_ROW (MB_S + 1)      // doubles per strip-boundary row: the states + the frame exponent (linear sweeps)
 
 // MODE 0: log-sum-exp score (Forward for DIR 0, Backward for DIR 1); MODE 1: Viterbi + back-pointers;
+// MODE 4: Viterbi score only (boss -V without -A: no pointer is formed, packed or stored);
 // MODE 2: Forward that also stores every cell (the E-step's ForwardMatrix, counts.cpp:58);
 // MODE 3: Backward fused with the posterior-count accumulation of BackwardMatrix::getCounts
 //         (backward.cpp:62-87): each transition group's term w + B(dest) is formed once and used
@@ -263,10 +264,12 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
               const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, !STEADY && r == Lo && col0 + c == Li, E, P);
-              const int sh = 8 * MB_TBBYTES * c;
-              if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
-              else if (sh < 64) pack0 |= (unsigned long long) word << (sh & 63);
-              else pack1 |= (unsigned long long) word << ((sh - 64) & 63);
+              if (MODE == 1) {
+                const int sh = 8 * MB_TBBYTES * c;
+                if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
+                else if (sh < 64) pack0 |= (unsigned long long) word << (sh & 63);
+                else pack1 |= (unsigned long long) word << ((sh - 64) & 63);
+              }
             }
 #pragma unroll
             for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
@@ -315,6 +318,7 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<3, 1> (P, A); }
 #endif
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0> (P, A); }
 
 // ---------------------------------------------------------------------------------------------
 // Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).

@@ -629,6 +629,7 @@ static void wide_fill_weights (const mb_machine* m, WHost* h) {
 
 void wide_destroy (mb_machine* m) {
   lane_destroy (m);
+  big_destroy (m);
   WHost* h = wh (m);
   if (!h) return;
   if (h->dLin) cudaFree (h->dLin);
@@ -639,6 +640,7 @@ void wide_destroy (mb_machine* m) {
 
 int wide_update_weights (mb_machine* m) {
   if (lane_update_weights (m)) return 1;
+  if (big_update_weights (m)) return 1;
   WHost* h = wh (m);
   if (!h) return 0;
   wide_fill_weights (m, h);
@@ -803,12 +805,24 @@ static int wide_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& 
   return 0;
 }
 
+// the log-domain sweep over a subset of the batch, results into dResult[pair] (device): where the big engine sends the pairs it flags
+int wide_forward_log_subset (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, double* dResult) {
+  if (!m->wide) { set_error ("wide engine not prepared for this machine"); return 1; }
+  WBuf dFlag;
+  if (dFlag.alloc ((size_t) b->nPairs * 4)) return 1;
+  return wide_launch<OP_LSE> (m, b, cost_order (b, &pairs), dResult, dFlag.as<int32_t>(), nullptr, nullptr);
+}
+
 int wide_forward (mb_machine* m, mb_batch* b, double* loglike) {
   b->lastRedo = 0;
   if (b->nPairs == 0) return 0;
   if (lane_wanted (m, b)) {      // no input sequences: a read per lane (mb_lane.cu)
     if (!m->lane && lane_prepare (m)) return 1;
     return lane_forward (m, b, loglike);
+  }
+  if (m->wide && !b->hasEnv) {      // full matrices of a mid-size machine: the generated thread-per-cell sweep (mb_big.cu)
+    if (!m->bigTried) { m->bigTried = true; if (big_supported (m, nullptr) && big_prepare (m)) return 1; }
+    if (big_wanted (m, b)) return big_forward (m, b, loglike);
   }
   if (!m->wide) return generic_forward (m, b, loglike, false);      // too large for the two-dimensional strip sweep
   WHost* h = wh (m);

@@ -10,10 +10,9 @@ from helpers import FlatMachine, golden_names, load_golden
 def test_jit_kernels_compile(name):
     from machineboss_b200 import capi
     fm = FlatMachine.from_json(load_golden(name)["machine"])
-    try:
-        log = capi.jit_compile_check(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
-    except capi.MachineBossError as e:
-        assert fm.n_states > 16 and "not eligible" in str(e), str(e)[:2000]
+    log = capi.jit_compile_check(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
+    if fm.n_states > 16:      # mid-size machines: the big engine's generated thread-per-cell Forward sweep (mb_big.cu)
+        assert "mb_k_big_forward" in log
         return
     assert "mb_k_forward" in log and "mb_k_viterbi" in log and "mb_k_backward" in log
     assert "0 bytes spill stores" in log
