@@ -248,6 +248,13 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   MB_CUDA (cudaStreamSynchronize (b->stream));
   std::vector<int64_t> redo;
   for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
+  if (getenv ("MB_BIG_DEBUG")) {
+    int64_t nf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ninf = 0;
+    for (int64_t k = 0; k < b->nPairs; ++k) { ++nf[flag[k] & 7]; if (!(loglike[k] > -INFINITY)) ++ninf; }
+    fprintf (stderr, "big engine: %lld pairs, flags by reason mask 0..7: %lld %lld %lld %lld %lld %lld %lld %lld, -inf or nan results %lld, first results %.10g %.10g\n",
+             (long long) b->nPairs, (long long) nf[0], (long long) nf[1], (long long) nf[2], (long long) nf[3], (long long) nf[4], (long long) nf[5], (long long) nf[6], (long long) nf[7],
+             (long long) ninf, loglike[0], loglike[b->nPairs > 1 ? 1 : 0]);
+  }
   int64_t launches = 1;
   if (!redo.empty()) {      // dangerous dynamic range, or no path at all: the wide engine's log-domain sweep decides
     if (wide_forward_log_subset (m, b, redo, dRes)) return 1;

@@ -92,6 +92,7 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
 
       for (int t = 0; t < nSteps; ++t) {
         if ((t & (MB_BIG_RESCALE - 1)) == 0) {
+          bool nz = false;
           if (t > 0) {      // renormalise my values to [1, 2)
             int mh = 0;
             unsigned ml = 0xffffffffu;
@@ -101,7 +102,7 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
               const int h = __double2hiint (Lown[j]), g = __double2hiint (Lprev[j]);
               mh = max (mh, max (h, g)); ml = min (ml, min ((unsigned) (h - 1), (unsigned) (g - 1)));
             }
-            const bool nz = mh >= 0x00100000;
+            nz = mh >= 0x00100000;
             if (nz) {
               const int ex = mh >> 20;
               const int shift = min (ex - 1023, 1000);
@@ -112,16 +113,29 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
                 for (int j = 0; j < MB_NLL; ++j) { Lown[j] *= f; Lprev[j] *= f; }
                 ecur += shift;
               }
-              if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
+              if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect |= 1;
             }
-            // a lane with nothing of its own yet adopts the frame of what is about to reach it; then every lane learns its left neighbour's
-            int eL = __shfl_up_sync (MB_FULL, ecur, 1);
-            if (lane == 0) eL = hasIn ? (int) stageNextE : ecur;
-            if (!nz) ecur = eL;
-            eL = __shfl_up_sync (MB_FULL, ecur, 1);
+          }
+          // A lane that holds nothing yet takes the frame of what is about to reach it: the nearest lane to its
+          // left that holds something, or -- for the lanes left of all of those -- the first staged boundary row
+          // that is not all zero (a strip starts with every lane empty, and its first rows are often empty too:
+          // cells no path reaches).  Then every lane learns its left neighbour's frame.
+          {
+            bool rowNz = false;
+            if (hasIn && lane < MB_BIG_RESCALE) {
+#pragma unroll
+              for (int j = 0; j < MB_NLL; ++j) rowNz |= stageNext[j] != 0.0;
+            }
+            const unsigned rowMask = __ballot_sync (MB_FULL, rowNz), nzMask = __ballot_sync (MB_FULL, nz);
+            const double eRow = __shfl_sync (MB_FULL, stageNextE, rowMask ? __ffs (rowMask) - 1 : 0);
+            if (lane == 0 && !nz && hasIn) ecur = (int) eRow;
+            const unsigned below = nzMask & ((1u << lane) - 1u);
+            const int eFrom = __shfl_sync (MB_FULL, ecur, below ? 31 - __clz (below) : 0);
+            if (!nz && lane > 0) ecur = eFrom;
+            const int eL = __shfl_up_sync (MB_FULL, ecur, 1);
             const bool leftNz = __shfl_up_sync (MB_FULL, (int) nz, 1) != 0;
             int d = lane ? eL - ecur : 0;
-            if (leftNz && (d < -900 || d > 900)) suspect = 1;
+            if (leftNz && (d < -900 || d > 900)) suspect |= 2;
             d = max (min (d, 1000), -1022);
             gl = mb_pow2 (d);
           }
@@ -136,7 +150,7 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
               const double f = mb_pow2 (d);
 #pragma unroll
               for (int j = 0; j < MB_NLL; ++j) { any |= stageNext[j] != 0.0; sIn[lane * MB_NLL + j] = stageNext[j] * f; }
-              if (far && any) suspect = 1;
+              if (far && any) suspect |= 4;
               const int rowN = t + MB_BIG_RESCALE + lane;
               const double* src = bin + (int64_t) rowN * MB_BROW;
 #pragma unroll
@@ -167,7 +181,7 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
 #pragma unroll
         for (int j = 0; j < MB_NLL; ++j) Lprev[j] = Lin[j];
       }
-      suspect = __any_sync (MB_FULL, suspect);
+      suspect = __reduce_or_sync (MB_FULL, (unsigned) suspect);      // why: 1 spread, 2 neighbour frame, 4 boundary frame
       __syncwarp();
     }
     if (lane == 0) A.flag[k] = suspect;
