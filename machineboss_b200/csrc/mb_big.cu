@@ -41,8 +41,18 @@ struct BigEngine {
   std::string source;
   void* mod = nullptr;
   void* kForward = nullptr;
-  void* dSil = nullptr;              // __constant__ mb_big_sil in the module
+  void* kViterbi = nullptr;
+  void* kViterbiScore = nullptr;
+  void* dSil = nullptr;              // __constant__ mb_big_sil in the module (linear weights)
+  void* dSilLog = nullptr;           // __constant__ mb_big_sil_log
   double* dEmit = nullptr;
+  double* dEmitLog = nullptr;
+  // Viterbi back-pointers: state d's field is bits[d] wide at (word[d], shift[d]); it holds the index of the winning
+  // group among the state's groups [groupStart[d], groupStart[d+1])
+  std::vector<int> ptrWord, ptrShift, ptrBits, groupStart;
+  int nPtrWords = 1;
+  int32_t* dPlan = nullptr;          // traceback tables: see BigTbPlan
+  int blocksPerSMV = 1, blocksPerSMVS = 1;
   size_t smemBytes = 0;
   int blocksPerSM = 1, numSMs = 148;
   bool linearOK = false;
@@ -78,6 +88,21 @@ static void big_plan (const mb_machine* m, BigEngine& B) {
   }
   B.liveU.clear(); B.liveL.clear();
   for (int s = 0; s < m->S; ++s) { if (isU[s]) B.liveU.push_back (s); if (isL[s]) B.liveL.push_back (s); }
+  // pointer fields, packed greedily into 32-bit words (no field straddles a word)
+  B.groupStart.assign ((size_t) m->S + 1, 0);
+  for (auto& gr: B.groups) B.groupStart[gr.self + 1]++;
+  for (int s = 0; s < m->S; ++s) B.groupStart[s + 1] += B.groupStart[s];
+  B.ptrWord.assign ((size_t) m->S, 0); B.ptrShift.assign ((size_t) m->S, 0); B.ptrBits.assign ((size_t) m->S, 0);
+  int word = 0, used = 0;
+  for (int s = 0; s < m->S; ++s) {
+    const int n = B.groupStart[s + 1] - B.groupStart[s];
+    int bt = 0; while ((1 << bt) < n) ++bt;
+    if (bt == 0) continue;
+    if (used + bt > 32) { ++word; used = 0; }
+    B.ptrWord[s] = word; B.ptrShift[s] = used; B.ptrBits[s] = bt;
+    used += bt;
+  }
+  B.nPtrWords = word + 1;
 }
 
 bool big_supported (const mb_machine* m, std::string* why) {
@@ -107,7 +132,8 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
   o << "#define MB_S " << S << "\n#define MB_NLU " << B.liveU.size() << "\n#define MB_NLL " << nLL << "\n#define MB_NEMIT " << std::max (B.nEmit, 1)
     << "\n#define MB_BIG_THREADS " << B.threads << "\n";
-  o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n\n";
+  o << "#define MB_NPW " << B.nPtrWords << "\n";
+  o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n__constant__ double mb_big_sil_log[" << std::max (B.nSil, 1) << "];\n\n";
   // the cell: live-up states read from (and written back to) the lane's column of `up`, left / diagonal cells' states in L / D
   o << "__device__ __forceinline__ void mb_big_cell (double* __restrict__ up, const double (&L)[MB_NLL], const double (&D)[MB_NLL], double (&Lo)[MB_NLL], "
        "const int a, const int b, const bool origin, const double* __restrict__ E, double& res) {\n";
@@ -133,6 +159,40 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   for (size_t q = 0; q < B.liveU.size(); ++q) o << "  up[" << q << " * 32] = n" << B.liveU[q] << ";\n";
   for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
   if (B.liveL.empty()) o << "  Lo[0] = 0.0;\n";
+  o << "  res = n" << S - 1 << ";\n}\n\n";
+  // the same cell in the max-plus semiring (viterbi.cpp:30-39): candidates of a state in the reference's order (match,
+  // delete, insert, silent sources; each by source state, then transition index), strict '<' keeps the first maximum
+  // (dpmatrix.defs.h:171-174); pw receives the packed pointers
+  o << "__device__ __forceinline__ void mb_big_cell_vit (double* __restrict__ up, const double (&L)[MB_NLL], const double (&D)[MB_NLL], double (&Lo)[MB_NLL], "
+       "const int a, const int b, const bool origin, const double* __restrict__ E, double& res, unsigned (&pw)[MB_NPW]) {\n";
+  o << "  const double NI = __longlong_as_double (0xfff0000000000000LL);\n";
+  std::fill (loaded.begin(), loaded.end(), 0);
+  gi = 0;
+  for (int d = 0; d < S; ++d) {
+    int k = 0;
+    for (; gi < B.groups.size() && B.groups[gi].self == d; ++gi, ++k) {
+      const BigGroup& gr = B.groups[gi];
+      std::ostringstream src, w;
+      if (gr.type == T_INSERT) {
+        if (!loaded[gr.other]) { o << "  const double u" << gr.other << " = up[" << uIdx[gr.other] << " * 32];\n"; loaded[gr.other] = 1; }
+        src << "u" << gr.other; w << "E[" << gr.emitOff << " + b]";
+      } else if (gr.type == T_DELETE) { src << "L[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a]"; }
+      else if (gr.type == T_MATCH) { src << "D[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a * " << m->nOut << " + b]"; }
+      else { src << "n" << gr.other; w << "mb_big_sil_log[" << gr.silIdx << "]"; }
+      if (k == 0) { o << "  double n" << d << " = " << src.str() << " + " << w.str() << ";\n"; if (B.ptrBits[d]) o << "  unsigned p" << d << " = 0u;\n"; }
+      else o << "  { const double t = " << src.str() << " + " << w.str() << "; if (n" << d << " < t) { n" << d << " = t; p" << d << " = " << k << "u; } }\n";
+    }
+    if (k == 0) o << "  double n" << d << " = NI;\n";
+    if (d == 0) o << "  if (origin) n0 = 0.0;\n";
+  }
+  for (size_t q = 0; q < B.liveU.size(); ++q) o << "  up[" << q << " * 32] = n" << B.liveU[q] << ";\n";
+  for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
+  if (B.liveL.empty()) o << "  Lo[0] = NI;\n";
+  for (int wd = 0; wd < B.nPtrWords; ++wd) {
+    o << "  pw[" << wd << "] = 0u";
+    for (int d = 0; d < S; ++d) if (B.ptrBits[d] && B.ptrWord[d] == wd) o << " | (p" << d << " << " << B.ptrShift[d] << ")";
+    o << ";\n";
+  }
   o << "  res = n" << S - 1 << ";\n}\n";
   o << kBigSkeleton;
   B.source = o.str();
@@ -152,6 +212,8 @@ void big_destroy (mb_machine* m) {
   if (!B) return;
   if (B->mod) rt_unload (B->mod);
   if (B->dEmit) cudaFree (B->dEmit);
+  if (B->dEmitLog) cudaFree (B->dEmitLog);
+  if (B->dPlan) cudaFree (B->dPlan);
   delete B;
   m->big = nullptr;
 }
@@ -160,18 +222,22 @@ int big_update_weights (mb_machine* m) {
   BigEngine* B = be (m);
   if (!B) return 0;
   std::vector<double> emit ((size_t) std::max (B->nEmit, 1), 0.), sil ((size_t) std::max (B->nSil, 1), 0.);
+  std::vector<double> emitLog (emit.size(), -INFINITY), silLog (sil.size(), -INFINITY);
   bool ok = true;
   const double lim = 24.0 * 0.6931471805599453;
   for (auto& gr: B->groups)
     for (auto& e: gr.entries) {
       const double lw = m->lw[e.second];
       if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
-      if (gr.type == T_SILENT) sil[gr.silIdx] = std::exp (lw); else emit[(size_t) gr.emitOff + e.first] = std::exp (lw);
+      if (gr.type == T_SILENT) { sil[gr.silIdx] = std::exp (lw); silLog[gr.silIdx] = lw; }
+      else { emit[(size_t) gr.emitOff + e.first] = std::exp (lw); emitLog[(size_t) gr.emitOff + e.first] = lw; }
     }
   B->linearOK = ok;
   MB_CUDA (cudaSetDevice (m->device));
   MB_CUDA (cudaMemcpy (B->dEmit, emit.data(), emit.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (B->dSil, sil.data(), sil.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (B->dEmitLog, emitLog.data(), emitLog.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (B->dSilLog, silLog.data(), silLog.size() * 8, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -182,15 +248,32 @@ int big_prepare (mb_machine* m) {
   std::vector<char> cubin;
   if (rt_compile (B->source, ".big.cu", cubin, nullptr)) return 1;
   MB_CUDA (cudaSetDevice (m->device));
-  if (rt_load (cubin, &B->mod) || rt_function (B->mod, "mb_k_big_forward", &B->kForward)) return 1;
+  if (rt_load (cubin, &B->mod) || rt_function (B->mod, "mb_k_big_forward", &B->kForward)
+      || rt_function (B->mod, "mb_k_big_viterbi", &B->kViterbi) || rt_function (B->mod, "mb_k_big_viterbi_score", &B->kViterbiScore)) return 1;
   size_t bytes = 0;
-  if (rt_global (B->mod, "mb_big_sil", &B->dSil, &bytes)) return 1;
+  if (rt_global (B->mod, "mb_big_sil", &B->dSil, &bytes) || rt_global (B->mod, "mb_big_sil_log", &B->dSilLog, &bytes)) return 1;
   MB_CUDA (cudaMalloc (&B->dEmit, (size_t) std::max (B->nEmit, 1) * 8));
+  MB_CUDA (cudaMalloc (&B->dEmitLog, (size_t) std::max (B->nEmit, 1) * 8));
+  {      // traceback tables, one int32 array: [S+1] groupStart | [S] word | [S] shift | [S] bits | [G] type | [G] source | [G] idOff | ids
+    std::vector<int32_t> plan;
+    for (int v: B->groupStart) plan.push_back (v);
+    for (int v: B->ptrWord) plan.push_back (v);
+    for (int v: B->ptrShift) plan.push_back (v);
+    for (int v: B->ptrBits) plan.push_back (v);
+    for (auto& gr: B->groups) plan.push_back (gr.type);
+    for (auto& gr: B->groups) plan.push_back (gr.other);
+    std::vector<int32_t> ids;
+    for (auto& gr: B->groups) { plan.push_back ((int32_t) ids.size()); ids.resize (ids.size() + gr.tableSize, -1); for (auto& e: gr.entries) ids[ids.size() - gr.tableSize + e.first] = (int32_t) e.second; }
+    plan.insert (plan.end(), ids.begin(), ids.end());
+    MB_CUDA (cudaMalloc (&B->dPlan, plan.size() * 4));
+    MB_CUDA (cudaMemcpy (B->dPlan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice));
+  }
   MB_CUDA (cudaDeviceGetAttribute (&B->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   const int warps = B->threads / 32, nLL = std::max<int> ((int) B->liveL.size(), 1);
   B->smemBytes = (size_t) (((std::max (B->nEmit, 1) + 1) & ~1) + warps * ((int) B->liveU.size() * 32 + 16 * nLL)) * 8;
-  if (rt_prepare (B->kForward, B->threads, B->smemBytes, &B->blocksPerSM)) return 1;
-  if (B->blocksPerSM < 1) { set_error ("big engine: the kernel does not fit on an SM"); return 1; }
+  if (rt_prepare (B->kForward, B->threads, B->smemBytes, &B->blocksPerSM) || rt_prepare (B->kViterbi, B->threads, B->smemBytes, &B->blocksPerSMV)
+      || rt_prepare (B->kViterbiScore, B->threads, B->smemBytes, &B->blocksPerSMVS)) return 1;
+  if (B->blocksPerSM < 1 || B->blocksPerSMV < 1 || B->blocksPerSMVS < 1) { set_error ("big engine: a kernel does not fit on an SM"); return 1; }
   if (getenv ("MB_WIDE_VERBOSE"))
     fprintf (stderr, "big engine: S=%d groups=%zu (silent %d), live-up %zu, left-going %zu, emission table %d doubles, %zu B smem, %d CTA(s)/SM\n",
              m->S, B->groups.size(), B->nSil, B->liveU.size(), B->liveL.size(), B->nEmit, B->smemBytes, B->blocksPerSM);
@@ -209,6 +292,7 @@ struct MBBigArgsHost {      // must match struct MBBigArgs in the skeleton
   double* bnd; int64_t bndStride;
   double* result; int32_t* flag;
   const double* emit;
+  unsigned* bp; const int64_t* bpOff;
 };
 
 int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
@@ -239,6 +323,7 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   A.order = dOrder; A.nWork = b->nPairs; A.counter = dCounter;
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dRes; A.flag = dFlag; A.emit = B.dEmit;
+  A.bp = nullptr; A.bpOff = nullptr;
   void* params[1] = { &A };
   if (timing_begin (b)) return 1;
   if (rt_launch (B.kForward, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params)) return 1;
@@ -263,6 +348,166 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   b->lastRedo = (int64_t) redo.size();
   if (timing_end (b, launches)) return 1;
   if (!redo.empty()) MB_CUDA (cudaMemcpy (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+bool big_wanted_viterbi (const mb_machine* m, const mb_batch* b) { return m->big && !b->hasEnv; }
+
+struct BigTbPlan {
+  const int32_t* groupStart; const int32_t* word; const int32_t* shift; const int32_t* bits;
+  const int32_t* type; const int32_t* source; const int32_t* idOff; const int32_t* ids;
+  int32_t S, nOut, nWords;
+};
+
+// DPMatrix::traceBack (dpmatrix.defs.h:82-110) over the packed pointers of mb_k_big_viterbi, one thread per pair.
+// out == nullptr: lengths only; otherwise the path is written start -> end at out[outOff[n] ..).
+__global__ void big_traceback_kernel (BigTbPlan p, DevBatch b, const int64_t* __restrict__ order, int64_t nWork,
+                                      const unsigned* __restrict__ bp, const int64_t* __restrict__ bpOff,
+                                      const double* __restrict__ score, int64_t* __restrict__ lenOut, int32_t* __restrict__ out,
+                                      const int64_t* __restrict__ outOff) {
+  const int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nWork) return;
+  const int64_t k = order[n];
+  const uint8_t* x = b.x + b.xOff[k];
+  const uint8_t* y = b.y + b.yOff[k];
+  const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
+  const int64_t nStrips = (Li + 32) / 32;
+  const unsigned* base = bp + bpOff[n];
+  int64_t len = 0;
+  if (score[k] > -INFINITY) {      // boss.cpp:831
+    const int64_t total = out ? lenOut[n] : 0;
+    int64_t i = Li, o = Lo;
+    int s = p.S - 1;
+    while (i > 0 || o > 0 || s != 0) {
+      const int g0 = p.groupStart[s], ng = p.groupStart[s + 1] - g0;
+      if (ng == 0) break;      // cannot happen on a finite path
+      int ptr = 0;
+      if (p.bits[s]) {
+        const unsigned w = base[((o * nStrips + (i >> 5)) * p.nWords + p.word[s]) * 32 + (i & 31)];
+        ptr = (int) ((w >> p.shift[s]) & ((1u << p.bits[s]) - 1u));
+      }
+      if (ptr >= ng) break;
+      const int g = g0 + ptr, type = p.type[g];
+      const int a = i ? x[i - 1] - 1 : 0, c = o ? y[o - 1] - 1 : 0;
+      const int li = type == T_MATCH ? a * p.nOut + c : type == T_DELETE ? a : type == T_INSERT ? c : 0;
+      if (out) out[outOff[n] + total - 1 - len] = p.ids[p.idOff[g] + li];
+      ++len;
+      if (type == T_MATCH || type == T_DELETE) --i;
+      if (type == T_MATCH || type == T_INSERT) --o;
+      s = p.source[g];
+      if (i < 0 || o < 0) break;
+    }
+  }
+  if (!out) lenOut[n] = len;
+}
+
+struct BigBuf {
+  void* p = nullptr;
+  ~BigBuf() { if (p) cudaFree (p); }
+  int alloc (size_t bytes) { MB_CUDA (cudaMalloc (&p, bytes ? bytes : 8)); return 0; }
+  template<class T> T* as() { return (T*) p; }
+};
+
+int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
+  BigEngine& B = *be (m);
+  b->pathStart.clear();
+  b->pathLen.clear();
+  if (b->nPairs == 0) return 0;
+  const bool trace = pathLen != nullptr;
+  std::vector<int64_t> order ((size_t) b->nPairs);
+  for (int64_t k = 0; k < b->nPairs; ++k) order[k] = k;
+  auto cost = [&] (int64_t k) { return (double) (b->xOff[k + 1] - b->xOff[k] + 1) * (double) (b->yOff[k + 1] - b->yOff[k] + 1); };
+  std::stable_sort (order.begin(), order.end(), [&] (int64_t p, int64_t q) { return cost (p) > cost (q); });
+  int64_t maxLo = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
+  const int warps = B.threads / 32, nLL = std::max<int> ((int) B.liveL.size(), 1);
+  const int perSM = trace ? B.blocksPerSMV : B.blocksPerSMVS;
+  const int64_t maxGrid = (int64_t) B.numSMs * perSM;
+  const int64_t bndStride = 2 * (maxLo + 1) * (nLL + 1);
+  b->wsOrderHoldsFull = false;
+  unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+  double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (maxGrid * warps * bndStride) * 8);
+  double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
+  if (!dCounter || !dBnd || !dRes) return 1;
+  MBBigArgsHost A;
+  A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
+  A.counter = dCounter; A.bnd = dBnd; A.bndStride = bndStride;
+  A.result = dRes; A.flag = nullptr; A.emit = B.dEmitLog;
+  A.bp = nullptr; A.bpOff = nullptr;
+  void* params[1] = { &A };
+  auto launch = [&] (const std::vector<int64_t>& work, const int64_t* dOrder) {
+    const int64_t grid = std::max<int64_t> (1, std::min<int64_t> (maxGrid, ((int64_t) work.size() + warps - 1) / warps));
+    A.order = dOrder; A.nWork = (int64_t) work.size();
+    MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
+    return rt_launch (trace ? B.kViterbi : B.kViterbiScore, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params);
+  };
+  if (!trace) {
+    int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
+    if (!dOrder) return 1;
+    MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    if (timing_begin (b)) return 1;
+    if (launch (order, dOrder)) return 1;
+    if (timing_end (b, 1)) return 1;
+    MB_CUDA (cudaMemcpy (score, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  // chunks of pairs whose pointers ((Lo+1) rows x strips x MB_NPW words x 32 lanes) fit in free memory
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
+  const double budget = 0.75 * (double) freeB;
+  BigTbPlan tp;
+  {
+    const int S = m->S, G = (int) B.groups.size();
+    const int32_t* q = B.dPlan;
+    tp.groupStart = q; q += S + 1; tp.word = q; q += S; tp.shift = q; q += S; tp.bits = q; q += S;
+    tp.type = q; q += G; tp.source = q; q += G; tp.idOff = q; q += G; tp.ids = q;
+    tp.S = S; tp.nOut = m->nOut; tp.nWords = B.nPtrWords;
+  }
+  b->pathStart.assign ((size_t) b->nPairs, 0);
+  b->pathLen.assign ((size_t) b->nPairs, 0);
+  int64_t packed = 0, launches = 0;
+  double ms = 0;
+  for (size_t c0 = 0; c0 < order.size();) {
+    std::vector<int64_t> chunk, bpOff;
+    double words = 0;
+    size_t c1 = c0;
+    for (; c1 < order.size(); ++c1) {
+      const int64_t k = order[c1];
+      const double need = (double) (b->yOff[k + 1] - b->yOff[k] + 1) * (double) ((b->xOff[k + 1] - b->xOff[k] + 32) / 32) * B.nPtrWords * 32;
+      if (need * 4 > budget) { set_error ("pair " + std::to_string (k) + " needs more device memory for its back-pointers than is free (" + std::to_string (need * 4) + " bytes)"); return 1; }
+      if (!chunk.empty() && (words + need) * 4 > budget) break;
+      chunk.push_back (k);
+      bpOff.push_back ((int64_t) words);
+      words += need;
+    }
+    c0 = c1;
+    BigBuf dBp, dBpOff, dOrder, dLen, dOutOff;
+    if (dBp.alloc ((size_t) words * 4) || dBpOff.alloc (bpOff.size() * 8) || dOrder.alloc (chunk.size() * 8) || dLen.alloc (chunk.size() * 8) || dOutOff.alloc (chunk.size() * 8)) return 1;
+    MB_CUDA (cudaMemcpyAsync (dBpOff.p, bpOff.data(), bpOff.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOrder.p, chunk.data(), chunk.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    A.bp = dBp.as<unsigned>(); A.bpOff = dBpOff.as<int64_t>();
+    if (timing_begin (b)) return 1;
+    if (launch (chunk, dOrder.as<int64_t>())) return 1;
+    const int64_t nWork = (int64_t) chunk.size();
+    const unsigned tg = (unsigned) ((nWork + 63) / 64);
+    big_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned>(), dBpOff.as<int64_t>(), dRes, dLen.as<int64_t>(), nullptr, nullptr);
+    MB_CUDA (cudaGetLastError());
+    std::vector<int64_t> len (chunk.size()), off (chunk.size());
+    MB_CUDA (cudaMemcpyAsync (len.data(), dLen.p, len.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    for (size_t n = 0; n < len.size(); ++n) { off[n] = packed; b->pathStart[chunk[n]] = packed; b->pathLen[chunk[n]] = len[n]; packed += len[n]; }
+    if (paths_reserve (b, packed)) return 1;
+    MB_CUDA (cudaMemcpyAsync (dOutOff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    big_traceback_kernel<<<tg, 64, 0, b->stream>>> (tp, b->dev, dOrder.as<int64_t>(), nWork, dBp.as<unsigned>(), dBpOff.as<int64_t>(), dRes, dLen.as<int64_t>(), b->dPaths, dOutOff.as<int64_t>());
+    MB_CUDA (cudaGetLastError());
+    launches += 3;
+    if (timing_end (b, launches)) return 1;
+    ms += b->lastMs;
+  }
+  b->lastMs = ms;
+  b->lastLaunches = launches;
+  MB_CUDA (cudaMemcpy (score, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < b->nPairs; ++k) pathLen[k] = b->pathLen[k];
   return 0;
 }
 

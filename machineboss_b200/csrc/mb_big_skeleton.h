@@ -18,6 +18,12 @@
 // enter through 2^(its frame - mine); strip-boundary rows carry their frame; a spread above 2^700, a
 // neighbour or boundary frame more than 2^900 away or a zero result flags the pair for the log-domain
 // sweep (wide engine).
+//
+// MODE 0: that Forward sweep.  MODE 1 / 2: Viterbi (viterbi.cpp:18-47) with / without back-pointers: the same
+// sweep in the log domain, FP64 add + strict '<' over each state's groups in the reference's candidate order
+// (bit-exact scores, first maximum wins); no frames.  A cell's pointers (ceil(log2(#groups)) bits per state,
+// MB_NPW 32-bit words) are stored as bp[((row * nStrips + strip) * MB_NPW + word) * 32 + lane]: every store of the
+// warp is one 128-byte line.
 #ifndef MB_BIG_SKELETON_H
 #define MB_BIG_SKELETON_H
 
@@ -33,11 +39,15 @@ struct MBBigArgs {
   double* bnd; int64_t bndStride;      // per warp: two buffers of (maxLo + 1) boundary rows
   double* result; int32_t* flag;
   const double* emit;
+  unsigned* bp; const int64_t* bpOff;      // MODE 1: back-pointer words of work item n at bp + bpOff[n]
 };
 
 __device__ __forceinline__ double mb_pow2 (int d) { return __hiloint2double ((1023 + d) << 20, 0); }
 
-extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward (const __grid_constant__ MBBigArgs A) {
+template<int MODE>
+__device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
+  constexpr bool LIN = MODE == 0;
+  const double ZERO = LIN ? 0.0 : __longlong_as_double (0xfff0000000000000LL);
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
   for (int q = threadIdx.x; q < MB_NEMIT; q += blockDim.x) E[q] = A.emit[q];
@@ -62,38 +72,39 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
     const uint8_t* y = A.y + y0;
     const int nStrips = (Li + 32) / 32;
     int suspect = 0;
+    unsigned* bp = MODE == 1 ? A.bp + A.bpOff[w] + lane : (unsigned*) 0;
 
     for (int strip = 0; strip < nStrips; ++strip) {
       const int col = strip * 32 + lane;
       const bool inCol = col <= Li;
       const int a = (col >= 1 && inCol) ? x[col - 1] - 1 : 0;
-      for (int q = 0; q < MB_NLU; ++q) up[q * 32] = 0.0;
+      for (int q = 0; q < MB_NLU; ++q) up[q * 32] = ZERO;
       double Lown[MB_NLL], Lprev[MB_NLL];      // my last cell's left-going states; what I received a step ago (the diagonal cell)
 #pragma unroll
-      for (int j = 0; j < MB_NLL; ++j) { Lown[j] = 0.0; Lprev[j] = 0.0; }
+      for (int j = 0; j < MB_NLL; ++j) { Lown[j] = ZERO; Lprev[j] = ZERO; }
       const double* bin = (strip & 1) ? bndB : bndA;
       double* bout = (strip & 1) ? bndA : bndB;
       const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
-      int ecur = hasIn ? (int) __ldcg (bin + MB_NLL) : 0;      // frame: true value = stored value * 2^ecur
+      int ecur = (LIN && hasIn) ? (int) __ldcg (bin + MB_NLL) : 0;      // frame: true value = stored value * 2^ecur
       double gl = 1.0;                                         // 2^(left neighbour's frame - mine)
       if (!hasIn) {
         __syncwarp();
-        for (int q = lane; q < MB_BIG_RESCALE * MB_NLL; q += 32) sIn[q] = 0.0;
+        for (int q = lane; q < MB_BIG_RESCALE * MB_NLL; q += 32) sIn[q] = ZERO;
         __syncwarp();
       }
       double stageNext[MB_NLL], stageNextE = (double) ecur;      // boundary row t + lane of the next block (lanes < MB_BIG_RESCALE)
 #pragma unroll
       for (int j = 0; j < MB_NLL; ++j)
-        stageNext[j] = (hasIn && lane < MB_BIG_RESCALE && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_BROW + j) : 0.0;
-      if (hasIn && lane < MB_BIG_RESCALE && lane <= Lo) stageNextE = __ldcg (bin + (int64_t) lane * MB_BROW + MB_NLL);
+        stageNext[j] = (hasIn && lane < MB_BIG_RESCALE && lane <= Lo) ? __ldcg (bin + (int64_t) lane * MB_BROW + j) : ZERO;
+      if (LIN && hasIn && lane < MB_BIG_RESCALE && lane <= Lo) stageNextE = __ldcg (bin + (int64_t) lane * MB_BROW + MB_NLL);
       int tokNext = 0;      // output token of my row at the next step (row 0 has none)
       const int nSteps = Lo + 32;
-      double res = 0.0;
+      double res = ZERO;
 
       for (int t = 0; t < nSteps; ++t) {
         if ((t & (MB_BIG_RESCALE - 1)) == 0) {
           bool nz = false;
-          if (t > 0) {      // renormalise my values to [1, 2)
+          if (LIN && t > 0) {      // renormalise my values to [1, 2)
             int mh = 0;
             unsigned ml = 0xffffffffu;
             for (int q = 0; q < MB_NLU; ++q) { const int h = __double2hiint (up[q * 32]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
@@ -120,7 +131,7 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
           // left that holds something, or -- for the lanes left of all of those -- the first staged boundary row
           // that is not all zero (a strip starts with every lane empty, and its first rows are often empty too:
           // cells no path reaches).  Then every lane learns its left neighbour's frame.
-          {
+          if (LIN) {
             bool rowNz = false;
             if (hasIn && lane < MB_BIG_RESCALE) {
 #pragma unroll
@@ -149,13 +160,13 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
               d = max (min (d, 1000), -1023);
               const double f = mb_pow2 (d);
 #pragma unroll
-              for (int j = 0; j < MB_NLL; ++j) { any |= stageNext[j] != 0.0; sIn[lane * MB_NLL + j] = stageNext[j] * f; }
-              if (far && any) suspect |= 4;
+              for (int j = 0; j < MB_NLL; ++j) { any |= stageNext[j] != 0.0; sIn[lane * MB_NLL + j] = LIN ? stageNext[j] * f : stageNext[j]; }
+              if (LIN && far && any) suspect |= 4;
               const int rowN = t + MB_BIG_RESCALE + lane;
               const double* src = bin + (int64_t) rowN * MB_BROW;
 #pragma unroll
-              for (int j = 0; j < MB_NLL; ++j) stageNext[j] = rowN <= Lo ? __ldcg (src + j) : 0.0;
-              stageNextE = rowN <= Lo ? __ldcg (src + MB_NLL) : (double) e0;
+              for (int j = 0; j < MB_NLL; ++j) stageNext[j] = rowN <= Lo ? __ldcg (src + j) : ZERO;
+              if (LIN) stageNextE = rowN <= Lo ? __ldcg (src + MB_NLL) : (double) e0;
             }
             __syncwarp();
           }
@@ -166,17 +177,30 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
         double Lin[MB_NLL];
 #pragma unroll
         for (int j = 0; j < MB_NLL; ++j) {
-          const double fromLane = __shfl_up_sync (MB_FULL, Lown[j], 1) * gl;
+          const double fromUp = __shfl_up_sync (MB_FULL, Lown[j], 1);
+          const double fromLane = LIN ? fromUp * gl : fromUp;
           Lin[j] = lane ? fromLane : sIn[(t & (MB_BIG_RESCALE - 1)) * MB_NLL + j];
         }
         if (r >= 0 && r <= Lo && inCol) {
-          mb_big_cell (up, Lin, Lprev, Lown, a, tokb, r == 0 && col == 0, E, res);
+          if (LIN) mb_big_cell (up, Lin, Lprev, Lown, a, tokb, r == 0 && col == 0, E, res);
+          else {
+            unsigned pw[MB_NPW];
+            mb_big_cell_vit (up, Lin, Lprev, Lown, a, tokb, r == 0 && col == 0, E, res, pw);
+            if (MODE == 1) {
+              unsigned* dst = bp + ((int64_t) r * nStrips + strip) * (MB_NPW * 32);
+#pragma unroll
+              for (int q = 0; q < MB_NPW; ++q) dst[q * 32] = pw[q];
+            }
+          }
           if (hasOut && lane == 31) {
 #pragma unroll
             for (int j = 0; j < MB_NLL; ++j) bout[(int64_t) r * MB_BROW + j] = Lown[j];
-            bout[(int64_t) r * MB_BROW + MB_NLL] = (double) ecur;
+            if (LIN) bout[(int64_t) r * MB_BROW + MB_NLL] = (double) ecur;
           }
-          if (r == Lo && col == Li) A.result[k] = res > 0.0 ? log (res) + (double) ecur * 0.6931471805599453094 : __longlong_as_double (0xfff0000000000000LL);
+          if (r == Lo && col == Li) {
+            if (LIN) A.result[k] = res > 0.0 ? log (res) + (double) ecur * 0.6931471805599453094 : __longlong_as_double (0xfff0000000000000LL);
+            else A.result[k] = res;
+          }
         }
 #pragma unroll
         for (int j = 0; j < MB_NLL; ++j) Lprev[j] = Lin[j];
@@ -184,9 +208,13 @@ extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward
       suspect = __reduce_or_sync (MB_FULL, (unsigned) suspect);      // why: 1 spread, 2 neighbour frame, 4 boundary frame
       __syncwarp();
     }
-    if (lane == 0) A.flag[k] = suspect;
+    if (LIN && lane == 0) A.flag[k] = suspect;
   }
 }
+
+extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward (const __grid_constant__ MBBigArgs A) { mb_big_run<0> (A); }
+extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_viterbi (const __grid_constant__ MBBigArgs A) { mb_big_run<1> (A); }
+extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_viterbi_score (const __grid_constant__ MBBigArgs A) { mb_big_run<2> (A); }
 )MBSRC";
 
 #endif

@@ -171,6 +171,8 @@ void big_destroy (mb_machine* m);
 int big_update_weights (mb_machine* m);
 bool big_wanted (const mb_machine* m, const mb_batch* b);
 int big_forward (mb_machine* m, mb_batch* b, double* loglike);
+bool big_wanted_viterbi (const mb_machine* m, const mb_batch* b);
+int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int wide_forward_log_subset (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, double* dResult);      // mb_wide.cu
 
 // run-time compilation plumbing shared by the generated engines (mb_jit.cu)

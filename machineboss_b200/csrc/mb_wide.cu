@@ -859,6 +859,10 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (!m->lane && lane_prepare (m)) return 1;
     return lane_viterbi (m, b, score, pathLen);
   }
+  if (m->wide && !b->hasEnv) {      // full matrices of a mid-size machine: the generated thread-per-cell sweep (mb_big.cu)
+    if (!m->bigTried) { m->bigTried = true; if (big_supported (m, nullptr) && big_prepare (m)) return 1; }
+    if (big_wanted_viterbi (m, b)) return big_viterbi (m, b, score, pathLen);
+  }
   if (!m->wide) return generic_viterbi (m, b, score, pathLen);
   WHost* h = wh (m);
   const bool trace = pathLen != nullptr;

@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 tail -c 300 gpurun_out/bench_reference.json
 timeout 300 python tools/other_configs.py > gpurun_out/other_configs.json 2> gpurun_out/other_configs.err
 cat gpurun_out/other_configs.json
-MB_WIDE_VERBOSE=1 timeout 300 python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 148 --li 300 --lo 10000 --engines 2 > gpurun_out/wide_cfg4.json 2> gpurun_out/wide_cfg4.err
+MB_WIDE_VERBOSE=1 timeout 300 python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 592 --li 300 --lo 2000 --engines 2 > gpurun_out/wide_cfg4.json 2> gpurun_out/wide_cfg4.err
 tail -c 900 gpurun_out/wide_cfg4.json; tail -2 gpurun_out/wide_cfg4.err
 MB_WIDE_VERBOSE=1 timeout 300 python tools/bench_wide.py --machine hmmer_pf00516 --pairs 262144 --li 0 --lo 275 --engines 2 --no-trace > gpurun_out/lane_cfg5.json 2> gpurun_out/lane_cfg5.err
 tail -c 600 gpurun_out/lane_cfg5.json; tail -2 gpurun_out/lane_cfg5.err

@@ -21,9 +21,12 @@ for k in mb_k_forward_lin mb_k_viterbi mb_k_fstore_lin mb_k_bcounts_lin; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jit_traceback_kernel -c 1 -o gpurun_out/prof_jit_traceback_kernel \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --em-pairs 256 > gpurun_out/ncu_tb_run.log 2>&1
-# the engines of the other configs: the wide strip sweep (config 4 machine) and the lane sweep (config 5 machine)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wide_kernel -c 1 -o gpurun_out/prof_wide_kernel_forward \
+# the engines of the other configs: the generated thread-per-cell sweep and the table-driven strip sweep (config 4 machine) ...
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mb_k_big_forward -c 1 -o gpurun_out/prof_mb_k_big_forward \
+    python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 592 --li 300 --lo 1000 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_big_run.log 2>&1
+MB_NO_BIG=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:wide_kernel -c 1 -o gpurun_out/prof_wide_kernel_forward \
     python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 148 --li 300 --lo 1000 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_wide_run.log 2>&1
+# ... and the lane sweep (config 5 machine)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lane_kernel -c 1 -o gpurun_out/prof_lane_kernel_forward \
     python tools/bench_wide.py --machine hmmer_pf00516 --pairs 65536 --li 0 --lo 100 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_lane_run.log 2>&1
 ls -la gpurun_out/*.ncu-rep
