@@ -124,6 +124,13 @@ bool big_supported (const mb_machine* m, std::string* why) {
 static void big_generate (const mb_machine* m, BigEngine& B) {
   big_plan (m, B);
   const int S = m->S, nLL = std::max<int> ((int) B.liveL.size(), 1);
+  // as many warps per CTA (one CTA per SM) as shared memory holds: the emission tables once, the live-up states per warp
+  {
+    int warps = 8;      // 255 registers per thread: at most 8 warps per SM
+    if (const char* e = getenv ("MB_BIG_WARPS")) warps = std::max (1, std::min (8, atoi (e)));
+    while (warps > 1 && (size_t) (((std::max (B.nEmit, 1) + 1) & ~1) + warps * ((int) B.liveU.size() * 32 + 16 * nLL)) * 8 > 226 * 1024) --warps;
+    B.threads = 32 * warps;
+  }
   std::vector<int> uIdx ((size_t) S, -1), lIdx ((size_t) S, -1);
   for (size_t q = 0; q < B.liveU.size(); ++q) uIdx[B.liveU[q]] = (int) q;
   for (size_t q = 0; q < B.liveL.size(); ++q) lIdx[B.liveL[q]] = (int) q;
