@@ -249,6 +249,37 @@ def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
                 assert len(paths[k]) == 0
 
 
+def test_big_engine_against_wide_engine(monkeypatch):
+    """Mid-size machines with full matrices run on the generated thread-per-cell sweep (mb_big.cu); the same pairs
+    through the table-driven wide engine (MB_NO_BIG) must give the same Forward values to rounding, bit-identical
+    Viterbi scores and identical paths.  Pairs long enough for several strips whose first rows no path reaches
+    (the case that needs an empty lane to adopt its frame from the boundary), none of them flagged."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("prot2dna_dnapsw")["machine"])
+    shapes = [(120, 700), (70, 150), (33, 400), (3, 10), (0, 4), (64, 64)]
+    pairs = [(synth_tokens(31, k, 0, li, fm.n_in), synth_tokens(31, k, 1, lo, fm.n_out)) for k, (li, lo) in enumerate(shapes)]
+    b = capi.Batch(pairs)
+    m_big = make_machine(capi, fm, 2)
+    ll = capi.forward(m_big, b)
+    redo = b.last_redo()
+    sc, paths = capi.viterbi(m_big, b)
+    sc_only = capi.viterbi(m_big, b, paths=False)
+    monkeypatch.setenv("MB_NO_BIG", "1")
+    m_wide = make_machine(capi, fm, 2)
+    ll_w = capi.forward(m_wide, b)
+    sc_w, paths_w = capi.viterbi(m_wide, b)
+    assert redo == 0
+    for k in range(len(pairs)):
+        assert close(ll[k], ll_w[k], rel=1e-11), (k, ll[k], ll_w[k])
+        assert sc[k] == sc_w[k] and sc_only[k] == sc_w[k], (k, sc[k], sc_w[k])
+        assert paths[k].tolist() == paths_w[k].tolist(), k
+    orc = Oracle(fm)
+    x, y = pairs[1]
+    assert forward_agrees(fm, x, y, ll[1], orc.forward(x, y))
+    v, p = orc.viterbi(x, y)
+    assert sc[1] == v and paths[1].tolist() == p.tolist()
+
+
 def test_wide_engine_log_domain_rerun():
     """The trap machine through the wide engine: the scaled sweep flags the long pairs and the log-domain sweep redoes them."""
     capi = _capi()
