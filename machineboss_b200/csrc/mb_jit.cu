@@ -864,6 +864,12 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     std::vector<int64_t> redo;
     for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
     b->lastRedo = (int64_t) redo.size();
+    if (getenv ("MB_JIT_VERBOSE") && !redo.empty()) {
+      int64_t nf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+      for (int64_t k = 0; k < b->nPairs; ++k) ++nf[flag[k] & 7];
+      fprintf (stderr, "[mb_jit] linear sweep flagged %lld of %lld pairs; by reason mask (1 spread, 2 neighbour frame, 4 boundary frame) 0..7: %lld %lld %lld %lld %lld %lld %lld %lld\n",
+               (long long) redo.size(), (long long) b->nPairs, (long long) nf[0], (long long) nf[1], (long long) nf[2], (long long) nf[3], (long long) nf[4], (long long) nf[5], (long long) nf[6], (long long) nf[7]);
+    }
     if (!redo.empty()) {
       if (launch (m, b, backward ? 1 : 0, cost_order (b, redo), dRes, nullptr, nullptr)) return 1;
       ++launches;

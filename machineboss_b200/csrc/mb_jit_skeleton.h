@@ -467,6 +467,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       // every MB_RESCALE steps (kept out of the step body so that the steady loop carries no block tests)
       auto blockStart = [&] (const int t) {
         {
+          bool nz = false;      // LF: this lane holds something
           if (t > 0) {
             int mh = 0;
             unsigned ml = 0xffffffffu;
@@ -482,7 +483,8 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               mh = __reduce_max_sync (MB_FULL, mh);
               ml = __reduce_min_sync (MB_FULL, ml);
             }
-            if (mh >= 0x00100000) {
+            nz = mh >= 0x00100000;
+            if (nz) {
               const int ex = mh >> 20;
               const int shift = min (ex - 1023, 1000);
               if (shift != 0) {
@@ -496,22 +498,31 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
                 }
                 ecur += shift;
               }
-              if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect = 1;
+              if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect |= 1;
             }
-            if (LF) {
-              // a lane with nothing of its own yet adopts the frame of what is about to reach it (lane 0: the
-              // staged boundary row of this step); then every lane learns its left neighbour's frame
-              const bool nz = mh >= 0x00100000;
-              int eL = __shfl_up_sync (MB_FULL, ecur, 1);
-              if (lane == 0) eL = hasIn ? (int) stageNextE : ecur;
-              if (!nz) ecur = eL;
-              eL = __shfl_up_sync (MB_FULL, ecur, 1);
-              const bool leftNz = __shfl_up_sync (MB_FULL, (int) nz, 1) != 0;
-              int d = lane ? eL - ecur : 0;
-              if (leftNz && (d < -900 || d > 900)) suspect = 1;
-              d = max (min (d, 1000), -1022);
-              gl = __hiloint2double ((1023 + d) << 20, 0);
+          }
+          if (LF) {
+            // A lane that holds nothing yet takes the frame of what is about to reach it: the nearest lane to its left
+            // that holds something, or -- for the lanes left of all of those -- the first staged boundary row that is
+            // not all zero (a strip starts with every lane empty, and far from the diagonal its first rows have
+            // underflowed to zero and carry a meaningless frame).  Then every lane learns its left neighbour's frame.
+            bool rowNz = false;
+            if (hasIn && lane < MB_RESCALE) {
+#pragma unroll
+              for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) rowNz |= stageNext[s] != 0.0;
             }
+            const unsigned rowMask = __ballot_sync (MB_FULL, rowNz), nzMask = __ballot_sync (MB_FULL, nz);
+            const double eRow = __shfl_sync (MB_FULL, stageNextE, rowMask ? __ffs (rowMask) - 1 : 0);
+            if (lane == 0 && !nz && hasIn) ecur = (int) eRow;
+            const unsigned below = nzMask & ((1u << lane) - 1u);
+            const int eFrom = __shfl_sync (MB_FULL, ecur, below ? 31 - __clz (below) : 0);
+            if (!nz && lane > 0) ecur = eFrom;
+            const int eL = __shfl_up_sync (MB_FULL, ecur, 1);
+            const bool leftNz = __shfl_up_sync (MB_FULL, (int) nz, 1) != 0;
+            int d = lane ? eL - ecur : 0;
+            if (leftNz && (d < -900 || d > 900)) suspect |= 2;
+            d = max (min (d, 1000), -1022);
+            gl = __hiloint2double ((1023 + d) << 20, 0);
           }
           if (MODE == 2 && lane == 0) ef[strip * nBlk + t / MB_RESCALE] = ecur;
           if (hasIn) {     // stage rows t .. t+MB_RESCALE-1 of the previous strip's last column, in the current frame;
@@ -527,7 +538,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
 #pragma unroll
               for (int s = 0; s < MB_S; ++s)
                 if (mb_live<DIR> (s)) { any |= stageNext[s] != 0.0; dst[s] = stageNext[s] * f; }
-              if (far && any) suspect = 1;
+              if (far && any) suspect |= 4;
               const int rowN = t + MB_RESCALE + lane;
               const double* src = bin + (int64_t) rowN * MB_ROW;
 #pragma unroll
@@ -652,7 +663,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         }
         for (; t < nSteps; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
       }
-      suspect = __any_sync (MB_FULL, suspect);
+      suspect = (int) __reduce_or_sync (MB_FULL, (unsigned) suspect);      // why: 1 spread, 2 neighbour frame, 4 boundary frame
       if (MODE == 3) mb_flush_counts_lin (csd, accd, ta, A.counts, A.idTabB, lane);
       __syncwarp();
     }

@@ -249,6 +249,27 @@ def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
                 assert len(paths[k]) == 0
 
 
+def test_linear_sweep_long_pairs_stay_in_the_linear_domain():
+    """Pairs long enough for a dozen 256-column strips: far from the diagonal the first rows of a strip have underflowed
+    to zero, and an empty lane must take its frame from the first boundary row that holds something; nothing may be
+    handed to the log-domain kernel, and the values are the exact sums."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_synth64")["machine"])
+    shapes = [(3000, 2800), (2100, 2600)]
+    pairs = [(synth_tokens(57, k, 0, li, 4), synth_tokens(57, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    assert b.last_redo() == 0
+    bl = capi.backward(m, b)
+    assert b.last_redo() == 0
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(ll[k] - f) <= 1e-9 * abs(f), (k, ll[k], f)
+        assert abs(bl[k] - f) <= 1e-9 * abs(f), (k, bl[k], f)
+
+
 def test_big_engine_against_wide_engine(monkeypatch):
     """Mid-size machines with full matrices run on the generated thread-per-cell sweep (mb_big.cu); the same pairs
     through the table-driven wide engine (MB_NO_BIG) must give the same Forward values to rounding, bit-identical
