@@ -166,6 +166,8 @@ def main():
     case("prot2dna_dnapsw", ["preset:prot2dna", "preset:dnapsw"], ("synth", 2, 7, 24, 106),
          note="config-4 style composite (S=308)")
     case("translate", ["preset:translate"], ("synth", 2, 9, 27, 107))
+    case("dnapsw_dnapsw", ["preset:dnapsw", "preset:dnapsw"], ("synth", 4, 40, 37, 111),
+         note="dnapsw => dnapsw: a mid-size composite WITH match transitions (the big engine's diagonal path)")
     envelope_case()
     env_expect = {}
     for nm in ("tinypath_full", "tinypath_path", "smallpath_path", "smallpath_area0", "smallpath_area1", "smallpath_area2",

@@ -6,7 +6,7 @@ from helpers import FlatMachine, golden_names, load_golden
 
 
 # one fixture per distinct machine structure (each check compiles nine kernels)
-@pytest.mark.parametrize("name", ["bitnoise_tiny", "unitindel", "stutter_noise_difflen", "counter_xxx", "dnapsw_small", "protpsw_synth", "translate", "prot2dna_dnapsw"])
+@pytest.mark.parametrize("name", ["bitnoise_tiny", "unitindel", "stutter_noise_difflen", "counter_xxx", "dnapsw_small", "protpsw_synth", "translate", "prot2dna_dnapsw", "dnapsw_dnapsw"])
 def test_jit_kernels_compile(name):
     from machineboss_b200 import capi
     fm = FlatMachine.from_json(load_golden(name)["machine"])
