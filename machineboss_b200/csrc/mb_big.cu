@@ -140,6 +140,11 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
   o << "#define MB_S " << S << "\n#define MB_NLU " << B.liveU.size() << "\n#define MB_NLL " << nLL << "\n#define MB_NEMIT " << std::max (B.nEmit, 1)
     << "\n#define MB_BIG_THREADS " << B.threads << "\n";
+  {      // which emission-table entries carry a transition (the others stay 0 / -inf): lets a host-side harness fill the tables
+    std::string present ((size_t) std::max (B.nEmit, 1), '0');
+    for (auto& gr: B.groups) if (gr.type != T_SILENT) for (auto& e: gr.entries) present[(size_t) gr.emitOff + e.first] = '1';
+    o << "// MB_EMIT_PRESENT " << present << "\n// MB_NSIL " << B.nSil << "\n";
+  }
   o << "#define MB_NPW " << B.nPtrWords << "\n";
   o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n__constant__ double mb_big_sil_log[" << std::max (B.nSil, 1) << "];\n\n";
   // the cell: live-up states read from (and written back to) the lane's column of `up`, left / diagonal cells' states in L / D
