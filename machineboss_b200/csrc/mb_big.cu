@@ -114,7 +114,7 @@ bool big_supported (const mb_machine* m, std::string* why) {
   BigEngine B;
   big_plan (m, B);
   if (B.groups.size() > 6000) return no ("big engine: more than 6000 transition groups");
-  if (B.nSil > 7000) return no ("big engine: silent weights exceed constant memory");
+  if (B.nSil > 3900) return no ("big engine: silent weights (linear and log copies) exceed the 64 KB of constant memory");
   if (B.liveL.size() > 24) return no ("big engine: more than 24 states cross a column boundary");
   const size_t smem = (size_t) (((B.nEmit + 1) & ~1) + 4 * (B.liveU.size() * 32 + 16 * std::max<size_t> (B.liveL.size(), 1))) * 8;
   if (smem > 220 * 1024) return no ("big engine: emission tables and live states do not fit in shared memory");
