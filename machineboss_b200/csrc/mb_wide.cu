@@ -821,7 +821,13 @@ int wide_forward (mb_machine* m, mb_batch* b, double* loglike) {
     return lane_forward (m, b, loglike);
   }
   if (m->wide && !b->hasEnv) {      // full matrices of a mid-size machine: the generated thread-per-cell sweep (mb_big.cu)
-    if (!m->bigTried) { m->bigTried = true; if (big_supported (m, nullptr) && big_prepare (m)) return 1; }
+    if (!m->bigTried) {      // a machine the generator cannot handle after all (NVRTC out of resources, ...) stays with the table-driven sweep
+      m->bigTried = true;
+      if (big_supported (m, nullptr) && big_prepare (m)) {
+        if (getenv ("MB_WIDE_VERBOSE")) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
+        big_destroy (m);
+      }
+    }
     if (big_wanted (m, b)) return big_forward (m, b, loglike);
   }
   if (!m->wide) return generic_forward (m, b, loglike, false);      // too large for the two-dimensional strip sweep
@@ -860,7 +866,13 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     return lane_viterbi (m, b, score, pathLen);
   }
   if (m->wide && !b->hasEnv) {      // full matrices of a mid-size machine: the generated thread-per-cell sweep (mb_big.cu)
-    if (!m->bigTried) { m->bigTried = true; if (big_supported (m, nullptr) && big_prepare (m)) return 1; }
+    if (!m->bigTried) {      // a machine the generator cannot handle after all (NVRTC out of resources, ...) stays with the table-driven sweep
+      m->bigTried = true;
+      if (big_supported (m, nullptr) && big_prepare (m)) {
+        if (getenv ("MB_WIDE_VERBOSE")) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
+        big_destroy (m);
+      }
+    }
     if (big_wanted_viterbi (m, b)) return big_viterbi (m, b, score, pathLen);
   }
   if (!m->wide) return generic_viterbi (m, b, score, pathLen);
