@@ -52,8 +52,11 @@ void mb_machine_destroy (mb_machine* m);
 
 #define MB_ENGINE_GENERIC 0   /* anti-diagonal wavefront over the CSR machine, any size */
 #define MB_ENGINE_JIT     1   /* machine-specialised strip kernel compiled with NVRTC, small machines */
-#define MB_ENGINE_WIDE    2   /* warp-per-column strip kernel over shared-memory transition tables: Forward and Viterbi
-                                 of mid-size and large machines (Backward and counts run on the generic engine) */
+#define MB_ENGINE_WIDE    2   /* Forward and Viterbi of mid-size and large machines (their Backward and counts run on the generic
+                                 engine), by whichever sweep fits the call: a generated thread-per-cell kernel for full matrices
+                                 of machines of up to ~1000 states, a read per lane for batches without input sequences (profile
+                                 HMMs of any size), a table-driven strip kernel over shared-memory transition tables otherwise
+                                 (envelopes, log-domain re-runs) */
 /* Force an engine for machines created afterwards (-1 = choose automatically, the default). */
 int mb_set_engine (int engine);
 
@@ -71,7 +74,7 @@ void mb_batch_destroy (mb_batch* b);
  * the reference does to every matrix of a SeqPair that carries an alignment (Envelope::initPath).
  * Fails like DPMatrix::alloc (dpmatrix.defs.h:31-32) if an envelope does not fit its pair or is
  * not connected.  rowOff == NULL removes all envelopes.  Batches with envelopes run on the
- * wide (Forward, Viterbi) and generic (Backward, counts) engines. */
+ * wide engine's table-driven sweep (Forward, Viterbi) and on the generic engine (Backward, counts). */
 int mb_batch_set_envelopes (mb_batch* b, const int64_t* rowOff, const int64_t* inStart, const int64_t* inEnd);
 /* Gives the scratch the engine keeps attached to the batch between calls (back-pointers, stored
  * Forward values, strip boundaries) back to the device; results already fetched stay valid. */
