@@ -30,11 +30,18 @@ extern "C" {
 typedef struct mb_machine mb_machine;
 typedef struct mb_batch mb_batch;
 
-/* ---- library state ---- */
+/* ---- library state: everything here is PER HOST THREAD, so that a host thread per GPU can drive its own
+ * device without locking (the reference has no threads; its only global state is its logger and caches) ---- */
 const char* mb_last_error (void);                 /* message of the last failing call on this thread */
 int mb_version (void);
 int mb_device_count (int* count);                  /* cudaGetDeviceCount */
-int mb_set_device (int device);                    /* device used by handles created afterwards (default 0) */
+int mb_set_device (int device);                    /* device used by handles this thread creates afterwards (default 0) */
+/* Tuning / diagnostic knobs (integers; MB_OPTION_UNSET restores the built-in choice).  mb_set_option sets the
+ * calling thread's defaults, copied into every machine it creates afterwards; mb_machine_set_option changes one
+ * machine.  Names: see kOptionNames in csrc/mb_api.cu ("verbose", "jit_narrow", "lane_r", "no_big", ...).
+ * The compute path never reads the environment. */
+#define MB_OPTION_UNSET (-2147483647 - 1)
+int mb_set_option (const char* name, int32_t value);
 
 /* ---- EvaluatedMachine (src/eval.h:59-98, src/eval.cpp:42-70) ----
  * Flattens what EvaluatedMachine::init builds: per transition its source, destination, input
@@ -48,6 +55,7 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
  * once per EM iteration (src/fitter.cpp:29). */
 int mb_machine_update_weights (mb_machine* m, const double* logWeight);
 int mb_machine_info (const mb_machine* m, int32_t* nStates, int64_t* nTrans, int32_t* engine /* MB_ENGINE_* */);
+int mb_machine_set_option (mb_machine* m, const char* name, int32_t value);
 void mb_machine_destroy (mb_machine* m);
 
 #define MB_ENGINE_GENERIC 0   /* anti-diagonal wavefront over the CSR machine, any size */
@@ -57,7 +65,7 @@ void mb_machine_destroy (mb_machine* m);
                                  of machines of up to ~1000 states, a read per lane for batches without input sequences (profile
                                  HMMs of any size), a table-driven strip kernel over shared-memory transition tables otherwise
                                  (envelopes, log-domain re-runs) */
-/* Force an engine for machines created afterwards (-1 = choose automatically, the default). */
+/* Force an engine for machines this thread creates afterwards (-1 = choose automatically, the default). */
 int mb_set_engine (int engine);
 
 /* ---- SeqPairList (src/seqpair.h:18-73,115-121), already tokenised (DPMatrix ctor, dpmatrix.defs.h:6-7) ----

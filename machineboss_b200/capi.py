@@ -18,7 +18,7 @@ ENGINE_GENERIC, ENGINE_JIT, ENGINE_WIDE = 0, 1, 2
 _lib = None
 
 # every symbol include/machineboss_b200.h declares
-SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine",
+SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
            "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
@@ -40,6 +40,8 @@ def lib():
         L.mb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
         L.mb_set_device.argtypes = [ctypes.c_int]
         L.mb_set_engine.argtypes = [ctypes.c_int]
+        L.mb_set_option.argtypes = [ctypes.c_char_p, I32]
+        L.mb_machine_set_option.argtypes = [P, ctypes.c_char_p, I32]
         L.mb_machine_create.argtypes = [ctypes.POINTER(P), I32, I32, I32, I64, P, P, P, P, P]
         L.mb_machine_update_weights.argtypes = [P, P]
         L.mb_machine_info.argtypes = [P, ctypes.POINTER(I32), ctypes.POINTER(I64), ctypes.POINTER(I32)]
@@ -83,6 +85,14 @@ def set_engine(e: int) -> None:
     _check(lib().mb_set_engine(e))
 
 
+OPTION_UNSET = -2147483648
+
+
+def set_option(name: str, value) -> None:
+    """Default of a tuning knob for machines this thread creates afterwards (None: the built-in choice)."""
+    _check(lib().mb_set_option(name.encode(), OPTION_UNSET if value is None else int(value)))
+
+
 def jit_compile_check(n_states, n_in, n_out, src, dst, tin, tout) -> str:
     """NVRTC-compile the specialised kernels of a machine structure (no device needed); returns the log."""
     arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
@@ -113,6 +123,9 @@ class Machine:
         e = ctypes.c_int32(0)
         _check(lib().mb_machine_info(self.h, None, None, ctypes.byref(e)))
         return e.value
+
+    def set_option(self, name: str, value) -> None:
+        _check(lib().mb_machine_set_option(self.h, name.encode(), OPTION_UNSET if value is None else int(value)))
 
     def update_weights(self, log_weight) -> None:
         lw = np.ascontiguousarray(log_weight, dtype=np.float64)

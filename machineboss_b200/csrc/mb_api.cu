@@ -11,9 +11,26 @@
 
 namespace mb {
 
+// per-thread library state: a host thread per GPU sets its own device, engine and options without
+// touching another thread's
 static thread_local std::string g_error;
-static int g_device = 0;
-static int g_forceEngine = -1;
+static thread_local int g_device = 0;
+static thread_local int g_forceEngine = -1;
+static thread_local Options g_options;
+
+static const char* const kOptionNames[] = {
+  "verbose",                                                  // 1: engines report their launch geometry and flags on stderr
+  "jit_narrow", "jit_no_linear", "jit_c", "jit_cv", "jit_minblocks", "jit_minblocks_v", "jit_minblocks_lin", "jit_minblocks_cnt", "jit_threads",
+  "jit_tb_budget_mb", "jit_f_budget_mb",                      // cap on one chunk of back-pointer / stored-Forward scratch (tests force several chunks)
+  "jit_chunks",                                               // pairs of a Viterbi call are traced back and copied out in this many pipeline stages
+  "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
+  "lane_r", "lane_warps", "no_lane", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
+};
+
+bool option_known (const char* name) {
+  for (const char* n: kOptionNames) if (!strcmp (n, name)) return true;
+  return false;
+}
 
 void set_error (const std::string& msg) { g_error = msg; }
 
@@ -158,18 +175,24 @@ static void build_csr (const mb_machine* m, bool incoming, HostCsr& c) {
     const int st = incoming ? m->dst[t] : m->src[t];
     return ((int64_t) st * nIn1 + m->in[t]) * nOut1 + m->out[t];
   };
-  std::vector<int64_t> order ((size_t) T);
-  for (int64_t t = 0; t < T; ++t) order[t] = t;
+  // A silent transition that does not advance can only sit on state 0 (machine.cpp:759 exempts it from
+  // isAdvancingMachine).  In the reference's fill it reads the cell being computed, which still holds the
+  // -inf it was initialised with (dpmatrix.defs.h:36), so it never contributes: it is left out of the lists.
+  std::vector<int64_t> order;
+  order.reserve ((size_t) T);
+  for (int64_t t = 0; t < T; ++t)
+    if (!(m->in[t] == 0 && m->out[t] == 0 && m->dst[t] <= m->src[t])) order.push_back (t);
+  const int64_t nKept = (int64_t) order.size();
   if (!incoming)   // destination ascending, ties by id; ids already ascend with the source state
     std::stable_sort (order.begin(), order.end(), [&] (int64_t a, int64_t b) { return m->dst[a] < m->dst[b]; });
   c.off.assign ((size_t) nKeys + 1, 0);
-  for (int64_t t = 0; t < T; ++t) c.off[keyOf (t) + 1]++;
+  for (int64_t t: order) c.off[keyOf (t) + 1]++;
   for (int64_t k = 0; k < nKeys; ++k) c.off[k + 1] += c.off[k];
   std::vector<int64_t> pos (c.off.begin(), c.off.end() - 1);
-  c.other.resize ((size_t) T);
-  c.id.resize ((size_t) T);
-  c.lw.resize ((size_t) T);
-  for (int64_t n = 0; n < T; ++n) {
+  c.other.resize ((size_t) nKept);
+  c.id.resize ((size_t) nKept);
+  c.lw.resize ((size_t) nKept);
+  for (int64_t n = 0; n < nKept; ++n) {
     const int64_t t = order[n];
     const int64_t p = pos[keyOf (t)]++;
     c.other[p] = incoming ? m->src[t] : m->dst[t];
@@ -245,6 +268,27 @@ static int upload_machine (mb_machine* m) {
 
 using namespace mb;
 
+// smallest and largest token of each sequence set, r = { minX, maxX, minY, maxY } (preset to 255, 0, 255, 0):
+// checked against the machine's alphabets by every compute call (a token beyond them would index past the
+// emission tables; 0 is epsilon and never appears in data)
+__global__ void token_range_kernel (const uint8_t* __restrict__ x, int64_t nx, const uint8_t* __restrict__ y, int64_t ny, int* __restrict__ r) {
+  int lo[2] = { 255, 255 }, hi[2] = { 0, 0 };
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x, t0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t q = t0; q < nx; q += stride) { const int v = x[q]; lo[0] = min (lo[0], v); hi[0] = max (hi[0], v); }
+  for (int64_t q = t0; q < ny; q += stride) { const int v = y[q]; lo[1] = min (lo[1], v); hi[1] = max (hi[1], v); }
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    lo[w] = __reduce_min_sync (0xffffffffu, lo[w]);
+    hi[w] = __reduce_max_sync (0xffffffffu, hi[w]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (lo[0] < 255) atomicMin (r + 0, lo[0]);
+    if (hi[0] > 0) atomicMax (r + 1, hi[0]);
+    if (lo[1] < 255) atomicMin (r + 2, lo[1]);
+    if (hi[1] > 0) atomicMax (r + 3, hi[1]);
+  }
+}
+
 template<class T>
 __global__ void narrow_ids_kernel (const int32_t* __restrict__ in, T* __restrict__ out, int64_t n) {
   for (int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t) gridDim.x * blockDim.x) out[q] = (T) in[q];
@@ -272,6 +316,19 @@ int mb_set_engine (int engine) {
   return 0;
 }
 
+int mb_set_option (const char* name, int32_t value) {
+  if (!name || !option_known (name)) { set_error (std::string ("mb_set_option: unknown option '") + (name ? name : "") + "'"); return 1; }
+  if (value == MB_OPTION_UNSET) g_options.unset (name); else g_options.set (name, value);
+  return 0;
+}
+
+int mb_machine_set_option (mb_machine* m, const char* name, int32_t value) {
+  if (!m) { set_error ("null machine"); return 1; }
+  if (!name || !option_known (name)) { set_error (std::string ("mb_machine_set_option: unknown option '") + (name ? name : "") + "'"); return 1; }
+  if (value == MB_OPTION_UNSET) m->opt.unset (name); else m->opt.set (name, value);
+  return 0;
+}
+
 int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
                        const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
                        const double* logWeight) {
@@ -290,6 +347,7 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
   }
   mb_machine* m = new mb_machine;
   m->device = g_device;
+  m->opt = g_options;
   m->S = nStates; m->nIn = nInTok; m->nOut = nOutTok; m->T = nTrans;
   m->src.assign (src, src + nTrans); m->dst.assign (dst, dst + nTrans);
   m->in.assign (inTok, inTok + nTrans); m->out.assign (outTok, outTok + nTrans);
@@ -299,19 +357,28 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
   build_levels (m, true, m->fwdLevelOff, m->fwdLevelStates);
   build_levels (m, false, m->bwdLevelOff, m->bwdLevelStates);
   if (upload_machine (m)) { mb_machine_destroy (m); return 1; }
+  // Engine choice.  A forced engine that cannot take the machine is an error; in automatic mode a
+  // failing preparation (NVRTC unavailable, tables too large, ...) falls through to the next engine --
+  // the generic engine, already uploaded, runs any machine.
   std::string why;
-  const bool wantJit = g_forceEngine == MB_ENGINE_JIT || (g_forceEngine < 0 && jit_supported (m, &why));
-  if (wantJit) {
+  const bool automatic = g_forceEngine < 0;
+  bool chosen = g_forceEngine == MB_ENGINE_GENERIC;
+  if (!chosen && (g_forceEngine == MB_ENGINE_JIT || (automatic && jit_supported (m, &why)))) {
     if (!jit_supported (m, &why)) { set_error ("mb_set_engine(JIT): " + why); mb_machine_destroy (m); return 1; }
-    if (jit_prepare (m)) { mb_machine_destroy (m); return 1; }
-    m->engine = MB_ENGINE_JIT;
-  } else if (g_forceEngine == MB_ENGINE_WIDE || (g_forceEngine < 0 && (wide_supported (m, &why) || m->nIn == 0))) {
+    if (jit_prepare (m) == 0) { m->engine = MB_ENGINE_JIT; chosen = true; }
+    else if (!automatic) { mb_machine_destroy (m); return 1; }
+    else jit_destroy (m);
+  }
+  if (!chosen && (g_forceEngine == MB_ENGINE_WIDE || (automatic && (wide_supported (m, &why) || m->nIn == 0)))) {
     // a machine without input alphabet only ever sees batches without input sequences, which the lane
     // engine (mb_lane.cu) sweeps whatever the number of states; the two-dimensional strip sweep needs
     // a cell to fit in shared memory
-    if (wide_supported (m, &why)) { if (wide_prepare (m)) { mb_machine_destroy (m); return 1; } }
+    bool ok = true;
+    if (wide_supported (m, &why)) ok = wide_prepare (m) == 0;      // (wide_prepare cleans up after itself on failure)
     else if (m->nIn != 0) { set_error ("mb_set_engine(WIDE): " + why); mb_machine_destroy (m); return 1; }
-    m->engine = MB_ENGINE_WIDE;
+    if (ok) { m->engine = MB_ENGINE_WIDE; chosen = true; }
+    else if (!automatic && m->nIn != 0) { mb_machine_destroy (m); return 1; }
+    else if (m->nIn == 0) { m->engine = MB_ENGINE_WIDE; chosen = true; }      // the lane sweep needs no wide tables
   }
   *out = m;
   return 0;
@@ -320,11 +387,11 @@ int mb_machine_create (mb_machine** out, int32_t nStates, int32_t nInTok, int32_
 int mb_machine_update_weights (mb_machine* m, const double* logWeight) {
   if (!m) { set_error ("null machine"); return 1; }
   m->lw.assign (logWeight, logWeight + m->T);
-  for (int64_t p = 0; p < m->T; ++p) { m->hInc.lw[p] = m->lw[m->hInc.id[p]]; m->hOut.lw[p] = m->lw[m->hOut.id[p]]; }
+  for (size_t p = 0; p < m->hInc.id.size(); ++p) { m->hInc.lw[p] = m->lw[m->hInc.id[p]]; m->hOut.lw[p] = m->lw[m->hOut.id[p]]; }
   MB_CUDA (cudaSetDevice (m->device));
-  if (m->T) {
-    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
-    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), (size_t) m->T * 8, cudaMemcpyHostToDevice));
+  if (!m->hInc.lw.empty()) {
+    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->incLwOffset, m->hInc.lw.data(), m->hInc.lw.size() * 8, cudaMemcpyHostToDevice));
+    MB_CUDA (cudaMemcpy ((char*) m->dBlob + m->outLwOffset, m->hOut.lw.data(), m->hOut.lw.size() * 8, cudaMemcpyHostToDevice));
   }
   if ((m->wide || m->lane || m->big) && wide_update_weights (m)) return 1;
   if (m->engine == MB_ENGINE_JIT) return jit_update_weights (m);
@@ -371,11 +438,12 @@ int mb_batch_create (mb_batch** out, int64_t nPairs, const uint8_t* inTokens, co
   // one pooled block: offsets, then the tokens with 16 bytes of slack each so kernels may read whole words past the last token
   {
     const size_t offB = ((size_t) (nPairs + 1) * 8 + 255) & ~(size_t) 255, xB = (nx + 16 + 255) & ~(size_t) 255, yB = (ny + 16 + 255) & ~(size_t) 255;
-    char* blk = (char*) pooled_alloc (b->device, 2 * offB + xB + yB, &b->tokBytes);
+    char* blk = (char*) pooled_alloc (b->device, 2 * offB + xB + yB + 256, &b->tokBytes);
     if (!blk) return fail();
     b->dTokBlock = blk;
     b->dXOff = (int64_t*) blk; b->dYOff = (int64_t*) (blk + offB);
     b->dX = (uint8_t*) (blk + 2 * offB); b->dY = (uint8_t*) (blk + 2 * offB + xB);
+    b->dTokRange = (int*) (blk + 2 * offB + xB + yB);
   }
   if (!cuda_ok (cudaMemsetAsync (b->dX, 1, nx + 16, b->stream), "memset") || !cuda_ok (cudaMemsetAsync (b->dY, 1, ny + 16, b->stream), "memset")) return fail();
   if (nx && !cuda_ok (cudaMemcpyAsync (b->dX, inTokens + x0, nx, cudaMemcpyHostToDevice, b->stream), "H2D tokens")) return fail();
@@ -383,6 +451,16 @@ int mb_batch_create (mb_batch** out, int64_t nPairs, const uint8_t* inTokens, co
   if (!cuda_ok (cudaMemcpyAsync (b->dXOff, b->xOff.data(), (size_t) (nPairs + 1) * 8, cudaMemcpyHostToDevice, b->stream), "H2D offsets")
       || !cuda_ok (cudaMemcpyAsync (b->dYOff, b->yOff.data(), (size_t) (nPairs + 1) * 8, cudaMemcpyHostToDevice, b->stream), "H2D offsets"))
     return fail();
+  {   // token range, on the device (the host never walks the sequences)
+    const int init[4] = { 255, 0, 255, 0 };
+    if (!cuda_ok (cudaMemcpyAsync (b->dTokRange, init, sizeof init, cudaMemcpyHostToDevice, b->stream), "H2D")) return fail();
+    if (nx + ny) {
+      const unsigned grid = (unsigned) std::min<size_t> ((std::max (nx, ny) + 255) / 256, 148 * 8);
+      token_range_kernel<<<grid, 256, 0, b->stream>>> (b->dX, (int64_t) nx, b->dY, (int64_t) ny, b->dTokRange);
+      if (!cuda_ok (cudaGetLastError(), "token_range_kernel")) return fail();
+    }
+    if (!cuda_ok (cudaMemcpyAsync (b->tokRange, b->dTokRange, sizeof init, cudaMemcpyDeviceToHost, b->stream), "D2H")) return fail();
+  }
   if (!cuda_ok (cudaStreamSynchronize (b->stream), "sync")) return fail();
   b->dev = { nPairs, b->dX, b->dXOff, b->dY, b->dYOff, nullptr, nullptr, nullptr };
   *out = b;
@@ -456,6 +534,13 @@ int mb_batch_trim (mb_batch* b) {
 static int check_call (const mb_machine* m, const mb_batch* b) {
   if (!m || !b) { set_error ("null handle"); return 1; }
   if (m->device != b->device) { set_error ("machine and batch live on different devices"); return 1; }
+  // Tokenizer::tokenize throws on a symbol outside the alphabet (eval.h:33-37); a pre-tokenised batch is held to the same rule
+  if (b->tokRange[1] > m->nIn || b->tokRange[3] > m->nOut || (b->tokRange[1] && b->tokRange[0] == 0) || (b->tokRange[3] && b->tokRange[2] == 0)) {
+    set_error ("batch tokens are outside the machine's alphabets: input tokens " + std::to_string (b->tokRange[0]) + ".." + std::to_string (b->tokRange[1])
+               + " (machine: 1.." + std::to_string (m->nIn) + "), output tokens " + std::to_string (b->tokRange[2]) + ".." + std::to_string (b->tokRange[3])
+               + " (machine: 1.." + std::to_string (m->nOut) + "); 0 is epsilon and never appears in data");
+    return 1;
+  }
   MB_CUDA (cudaSetDevice (m->device));
   return 0;
 }
@@ -466,7 +551,7 @@ static bool use_jit (const mb_machine* m, const mb_batch* b) { return m->engine 
 static int use_wide (mb_machine* m, const mb_batch* b) {
   if (m->engine == MB_ENGINE_WIDE) return 1;
   if (m->engine == MB_ENGINE_JIT && b->hasEnv && wide_supported (m, nullptr)) {
-    if (!m->wide && wide_prepare (m)) return -1;
+    if (!m->wide && wide_prepare (m)) return -1;      // (a failed preparation leaves m->wide null)
     return 1;
   }
   return 0;
@@ -559,6 +644,7 @@ int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int6
                           const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
                           char* log, int64_t logCap) {
   mb_machine m;
+  m.opt = g_options;
   m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
   m.src.assign (src, src + nTrans); m.dst.assign (dst, dst + nTrans);
   m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);

@@ -107,7 +107,7 @@ static void big_plan (const mb_machine* m, BigEngine& B) {
 
 bool big_supported (const mb_machine* m, std::string* why) {
   auto no = [&] (const char* w) { if (why) *why = w; return false; };
-  if (getenv ("MB_NO_BIG")) return no ("big engine: disabled (MB_NO_BIG)");
+  if (m->opt.get ("no_big", 0)) return no ("big engine: disabled (option no_big)");
   if (m->S <= 16) return no ("big engine: small machines belong to the JIT engine");
   if (m->S > 1024 || m->T > 65536) return no ("big engine: more than 1024 states or 65536 transitions");
   if (m->nIn == 0 || m->nOut == 0) return no ("big engine: no two-dimensional matrices without both alphabets");
@@ -127,7 +127,7 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   // as many warps per CTA (one CTA per SM) as shared memory holds: the emission tables once, the live-up states per warp
   {
     int warps = 8;      // 255 registers per thread: at most 8 warps per SM
-    if (const char* e = getenv ("MB_BIG_WARPS")) warps = std::max (1, std::min (8, atoi (e)));
+    if (m->opt.has ("big_warps")) warps = std::max (1, std::min (8, m->opt.get ("big_warps", 8)));
     // (192 KB, not all 227: what is left is the L1 that holds the spilled registers -- prot2dna => dnapsw ran 3 % faster with 4 warps than with 5)
     while (warps > 1 && (size_t) (((std::max (B.nEmit, 1) + 1) & ~1) + warps * ((int) B.liveU.size() * 32 + 16 * nLL)) * 8 > 192 * 1024) --warps;
     B.threads = 32 * warps;
@@ -287,7 +287,7 @@ int big_prepare (mb_machine* m) {
   if (rt_prepare (B->kForward, B->threads, B->smemBytes, &B->blocksPerSM) || rt_prepare (B->kViterbi, B->threads, B->smemBytes, &B->blocksPerSMV)
       || rt_prepare (B->kViterbiScore, B->threads, B->smemBytes, &B->blocksPerSMVS)) return 1;
   if (B->blocksPerSM < 1 || B->blocksPerSMV < 1 || B->blocksPerSMVS < 1) { set_error ("big engine: a kernel does not fit on an SM"); return 1; }
-  if (getenv ("MB_WIDE_VERBOSE"))
+  if (m->opt.get ("verbose", 0))
     fprintf (stderr, "big engine: S=%d groups=%zu (silent %d), live-up %zu, left-going %zu, emission table %d doubles, %zu B smem, %d CTA(s)/SM\n",
              m->S, B->groups.size(), B->nSil, B->liveU.size(), B->liveL.size(), B->nEmit, B->smemBytes, B->blocksPerSM);
   return big_update_weights (m);
@@ -346,7 +346,7 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   MB_CUDA (cudaStreamSynchronize (b->stream));
   std::vector<int64_t> redo;
   for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
-  if (getenv ("MB_BIG_DEBUG")) {
+  if (m->opt.get ("big_debug", 0)) {
     int64_t nf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ninf = 0;
     for (int64_t k = 0; k < b->nPairs; ++k) { ++nf[flag[k] & 7]; if (!(loglike[k] > -INFINITY)) ++ninf; }
     fprintf (stderr, "big engine: %lld pairs, flags by reason mask 0..7: %lld %lld %lld %lld %lld %lld %lld %lld, -inf or nan results %lld, first results %.10g %.10g\n",

@@ -60,6 +60,17 @@ struct HostCsr {
   std::vector<double> lw;
 };
 
+// Tuning and diagnostic knobs.  mb_set_option sets the calling thread's defaults, which a machine copies when
+// it is created; mb_machine_set_option changes one machine.  Nothing on the compute path reads the environment.
+struct Options {
+  std::vector<std::pair<std::string, int>> kv;
+  bool has (const char* name) const { for (auto& e: kv) if (e.first == name) return true; return false; }
+  int get (const char* name, int dflt) const { for (auto& e: kv) if (e.first == name) return e.second; return dflt; }
+  void set (const char* name, int value) { for (auto& e: kv) if (e.first == name) { e.second = value; return; } kv.emplace_back (name, value); }
+  void unset (const char* name) { for (size_t n = 0; n < kv.size(); ++n) if (kv[n].first == name) { kv.erase (kv.begin() + n); return; } }
+};
+bool option_known (const char* name);
+
 void set_error (const std::string& msg);
 bool cuda_ok (cudaError_t e, const char* what);
 
@@ -75,6 +86,7 @@ struct mb_machine {
   std::vector<int32_t> src, dst, in, out;
   std::vector<double> lw;
   int engine = MB_ENGINE_GENERIC;
+  mb::Options opt;         // copied from the creating thread's defaults (mb_set_option)
 
   // generic engine
   mb::HostCsr hInc, hOut;
@@ -105,6 +117,8 @@ struct mb_batch {
   int64_t* dYOff = nullptr;
   void* dTokBlock = nullptr;           // the pooled allocation the four pointers above point into
   size_t tokBytes = 0;
+  int* dTokRange = nullptr;            // { min, max input token, min, max output token }, computed on the device at creation
+  int tokRange[4] = { 255, 0, 255, 0 };
   int64_t* dEnv = nullptr;             // envOff | envStart | envEnd in one allocation (null: full envelopes only)
   bool hasEnv = false;
   std::vector<int64_t> envOff, envStart, envEnd;   // host copies

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <sstream>
 
 #include "mb_internal.h"
@@ -60,8 +61,10 @@ struct Nvrtc {
 
 static Driver g_drv;
 static Nvrtc g_nvrtc;
+static std::mutex g_loadMutex;      // several host threads (one per GPU) may create machines at once
 
 static bool load_driver() {
+  std::lock_guard<std::mutex> lock (g_loadMutex);
   if (g_drv.ok) return true;
   auto get = [] (const char* name, void** fn) {
     cudaDriverEntryPointQueryResult st;
@@ -79,6 +82,7 @@ static bool load_driver() {
 }
 
 static bool load_nvrtc() {
+  std::lock_guard<std::mutex> lock (g_loadMutex);
   if (g_nvrtc.ok) return true;
   std::vector<std::string> cands;
   if (const char* e = getenv ("MB_NVRTC_LIB")) cands.push_back (e);
@@ -530,9 +534,9 @@ static int compile (mb_machine* m, JitEngine& J) {
 // Columns per lane for a score-only call over `pairs`: CV unless the narrower strips of C waste so much
 // less padding that they win.  Cost per cell relative to C (measured, 10 000 dnapsw pairs of 1 kb):
 // Viterbi 0.60, linear sweeps 0.87.
-static bool use_narrow (const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, bool viterbi) {
+static bool use_narrow (const mb_machine* m, const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, bool viterbi) {
   if (!J.modV) return false;
-  if (const char* e = getenv ("MB_JIT_NARROW")) return atoi (e) != 0;
+  if (m->opt.has ("jit_narrow")) return m->opt.get ("jit_narrow", 0) != 0;
   double cellsN = 0, cellsW = 0;
   for (int64_t k: pairs) {
     const double Li = (double) (b->xOff[k + 1] - b->xOff[k]), rows = (double) (b->yOff[k + 1] - b->yOff[k]) + 32;
@@ -594,7 +598,7 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
   J.linearOK = true;
   for (double w: m->lw) if (std::isfinite (w) && std::fabs (w) > 24.0 * 0.6931471805599453) J.linearOK = false;
   for (double w: m->lw) if (std::isnan (w) || w == INFINITY) J.linearOK = false;
-  if (getenv ("MB_JIT_NO_LINEAR")) J.linearOK = false;
+  if (m->opt.get ("jit_no_linear", 0)) J.linearOK = false;
 }
 
 int jit_update_weights (mb_machine* m) {
@@ -636,17 +640,17 @@ static void generate (const mb_machine* m, JitEngine& J) {
   }
   J.tbBytes = totalBits <= 8 ? 1 : totalBits <= 16 ? 2 : totalBits <= 32 ? 4 : 8;
   J.C = m->S <= 8 ? 4 : 2;
-  if (const char* e = getenv ("MB_JIT_C")) J.C = std::max (1, std::min (8, atoi (e)));
+  if (m->opt.has ("jit_c")) J.C = std::max (1, std::min (8, m->opt.get ("jit_c", 4)));
   while (J.C * J.tbBytes > 16) J.C /= 2;
   J.CV = J.C; J.minBlocksV = J.minBlocks;
   if (m->S <= 8 && J.C == 4 && 8 * J.tbBytes <= 16) { J.CV = 8; J.minBlocksV = 3; }
-  if (const char* e = getenv ("MB_JIT_CV")) J.CV = std::max (1, std::min (8, atoi (e)));
+  if (m->opt.has ("jit_cv")) J.CV = std::max (1, std::min (8, m->opt.get ("jit_cv", 8)));
   while (J.CV * J.tbBytes > 16) J.CV /= 2;
-  if (const char* e = getenv ("MB_JIT_MINBLOCKS_V")) J.minBlocksV = std::max (1, std::min (16, atoi (e)));
-  if (const char* e = getenv ("MB_JIT_MINBLOCKS")) J.minBlocks = std::max (1, std::min (16, atoi (e)));
-  if (const char* e = getenv ("MB_JIT_MINBLOCKS_CNT")) J.minBlocksCnt = std::max (1, std::min (16, atoi (e)));
-  if (const char* e = getenv ("MB_JIT_MINBLOCKS_LIN")) J.minBlocksLin = std::max (1, std::min (16, atoi (e)));
-  if (const char* e = getenv ("MB_JIT_THREADS")) J.threads = std::max (32, std::min (1024, atoi (e) / 32 * 32));
+  if (m->opt.has ("jit_minblocks_v")) J.minBlocksV = std::max (1, std::min (16, m->opt.get ("jit_minblocks_v", 3)));
+  if (m->opt.has ("jit_minblocks")) J.minBlocks = std::max (1, std::min (16, m->opt.get ("jit_minblocks", 4)));
+  if (m->opt.has ("jit_minblocks_cnt")) J.minBlocksCnt = std::max (1, std::min (16, m->opt.get ("jit_minblocks_cnt", 4)));
+  if (m->opt.has ("jit_minblocks_lin")) J.minBlocksLin = std::max (1, std::min (16, m->opt.get ("jit_minblocks_lin", 5)));
+  if (m->opt.has ("jit_threads")) J.threads = std::max (32, std::min (1024, m->opt.get ("jit_threads", 128) / 32 * 32));
 
   J.ctxBase.assign (J.bwd.slots.size(), -1);
   J.nCtx = 0;
@@ -833,7 +837,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F32 = ca.F32; A.f32Off = ca.f32Off; A.ef = ca.ef; A.efOff = ca.efOff;
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
-  if (getenv ("MB_JIT_VERBOSE"))
+  if (m->opt.get ("verbose", 0))
     fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
              J.smemBytes[which], J.blocksPerSM[which], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
@@ -856,7 +860,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     if (!dFlag) return 1;
     CountArgs ca;
     ca.flag = dFlag;
-    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (J, b, order, false))) return 1;
+    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (m, J, b, order, false))) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
     MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
     MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -864,7 +868,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     std::vector<int64_t> redo;
     for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(loglike[k] > -INFINITY)) redo.push_back (k);
     b->lastRedo = (int64_t) redo.size();
-    if (getenv ("MB_JIT_VERBOSE") && !redo.empty()) {
+    if (m->opt.get ("verbose", 0) && !redo.empty()) {
       int64_t nf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
       for (int64_t k = 0; k < b->nPairs; ++k) ++nf[flag[k] & 7];
       fprintf (stderr, "[mb_jit] linear sweep flagged %lld of %lld pairs; by reason mask (1 spread, 2 neighbour frame, 4 boundary frame) 0..7: %lld %lld %lld %lld %lld %lld %lld %lld\n",
@@ -1015,7 +1019,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
-  const bool narrow = use_narrow (J, b, full_order (b), true);
+  const bool narrow = use_narrow (m, J, b, full_order (b), true);
   if (!trace) {      // scores only (boss -V): no back-pointers, no scratch beyond the strip boundaries
     double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
     if (!dRes) return 1;

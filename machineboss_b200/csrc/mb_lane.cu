@@ -353,7 +353,7 @@ int lane_prepare (mb_machine* m) {
   lane_fill_weights (m, h);
   if (lane_upload (m, h, true)) return 1;
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
-  if (getenv ("MB_WIDE_VERBOSE"))
+  if (m->opt.get ("verbose", 0))
     fprintf (stderr, "lane engine: S=%d records=%lld (emitting rows %zu x %d tokens), bp %d bytes\n", S, (long long) h->nRec, h->emPerm.size() / std::max (nOut, 1), nOut, h->bpBytes);
   return 0;
 }
@@ -369,8 +369,8 @@ struct LBuf {
 // warps, one read per lane is fastest (262 144 reads: 175 GCUPS Forward, 132 Viterbi); with fewer, a second
 // independent chain per thread makes up for the missing warps in the sums (65 536 reads: 40 -> 89 GCUPS),
 // while the max-plus sweep, which carries a pointer per chain, stays at one.
-static int lane_reads_per_lane (const LHost* h, int64_t nWork, int op) {
-  if (const char* e = getenv ("MB_LANE_R")) { const int r = atoi (e); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
+static int lane_reads_per_lane (const mb_machine* m, const LHost* h, int64_t nWork, int op) {
+  if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
   if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
@@ -384,7 +384,7 @@ static int lane_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>
   int ctas = 0;
   MB_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&ctas, lane_kernel<OP, R>, 128, 0));
   int warpsPerSM = 48;      // the sweep is bound by the latency of its state-vector loads: as many warps as the registers allow
-  if (const char* e = getenv ("MB_LANE_WARPS")) warpsPerSM = std::max (4, atoi (e));
+  if (m->opt.has ("lane_warps")) warpsPerSM = std::max (4, m->opt.get ("lane_warps", 48));
   ctas = std::max (1, std::min (ctas, warpsPerSM / 4));
   // few tasks: one warp per CTA spreads them over the SMs
   const int threads = nTasks >= (int64_t) ctas * h->numSMs * 4 ? 128 : nTasks >= (int64_t) h->numSMs * 2 ? 64 : 32;
@@ -428,7 +428,7 @@ static std::vector<int64_t> lane_order (const mb_batch* b, const std::vector<int
 }
 
 bool lane_wanted (const mb_machine* m, const mb_batch* b) {
-  if (b->hasEnv || getenv ("MB_NO_LANE")) return false;
+  if (b->hasEnv || m->opt.get ("no_lane", 0)) return false;
   for (int64_t k = 0; k < b->nPairs; ++k) if (b->xOff[k + 1] != b->xOff[k]) return false;
   return true;
 }
@@ -443,7 +443,7 @@ int lane_forward (mb_machine* m, mb_batch* b, double* loglike) {
   MB_CUDA (cudaMemsetAsync (dFlag.p, 0, (size_t) b->nPairs * 4, b->stream));
   if (timing_begin (b)) return 1;
   int64_t launches = 1;
-  const int R = lane_reads_per_lane (h, b->nPairs, L_SUM);
+  const int R = lane_reads_per_lane (m, h, b->nPairs, L_SUM);
   if (h->linearOk) {
     if (lane_launch<L_SUM> (m, b, R, order, dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
@@ -452,7 +452,7 @@ int lane_forward (mb_machine* m, mb_batch* b, double* loglike) {
     std::vector<int64_t> redo;
     for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k]) redo.push_back (k);
     if (!redo.empty()) {
-      if (lane_launch<L_LSE> (m, b, lane_reads_per_lane (h, (int64_t) redo.size(), L_LSE), lane_order (b, &redo), dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
+      if (lane_launch<L_LSE> (m, b, lane_reads_per_lane (m, h, (int64_t) redo.size(), L_LSE), lane_order (b, &redo), dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
       ++launches;
     }
     b->lastRedo = (int64_t) redo.size();
@@ -477,13 +477,13 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (dRes.alloc ((size_t) b->nPairs * 8)) return 1;
   if (!trace) {
     if (timing_begin (b)) return 1;
-    if (lane_launch<L_MAX> (m, b, lane_reads_per_lane (h, b->nPairs, L_MAX), order, dRes.as<double>(), nullptr, nullptr, nullptr)) return 1;
+    if (lane_launch<L_MAX> (m, b, lane_reads_per_lane (m, h, b->nPairs, L_MAX), order, dRes.as<double>(), nullptr, nullptr, nullptr)) return 1;
     if (timing_end (b, 1)) return 1;
     MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
     return 0;
   }
   // chunks of whole tasks (LPT reads) whose back-pointers, (maxLo+1) * S * LPT bytes or half-words per task, fit in free memory
-  const int R = lane_reads_per_lane (h, b->nPairs, L_MAX), LPT = 32 * R;
+  const int R = lane_reads_per_lane (m, h, b->nPairs, L_MAX), LPT = 32 * R;
   size_t freeB = 0, totalB = 0;
   MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
   const double vecBytes = (double) h->numSMs * 48 * 2 * h->S * LPT * 8;

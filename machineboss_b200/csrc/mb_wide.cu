@@ -650,7 +650,7 @@ int wide_update_weights (mb_machine* m) {
   return 0;
 }
 
-int wide_prepare (mb_machine* m) {
+static int wide_prepare_tables (mb_machine* m) {
   WHost* h = new WHost;
   m->wide = h;
   WBuilder B, best;
@@ -661,7 +661,7 @@ int wide_prepare (mb_machine* m) {
   int maxList = 0;
   double bestCost = 1e300, bestInstr = 0;
   int forceG = 0;
-  if (const char* e = getenv ("MB_WIDE_G")) forceG = atoi (e);
+  forceG = m->opt.get ("wide_g", 0);
   for (int G: { 32, 16, 8 }) {
     if (forceG && G != forceG) continue;
     double perCell = 0;
@@ -705,10 +705,22 @@ int wide_prepare (mb_machine* m) {
   MB_CUDA (cudaMemcpy (h->dLin, h->blobLin.data(), t.bytes, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (h->dLog, h->blobLog.data(), t.bytes, cudaMemcpyHostToDevice));
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
-  if (getenv ("MB_WIDE_VERBOSE"))
+  if (m->opt.get ("verbose", 0))
     fprintf (stderr, "wide engine: S=%d G=%d rows=%zu (silent %u) tables=%u bytes, est. %.0f warp-instructions per cell, live-in %d, bp %d bytes\n",
              m->S, best.G, best.rows(), b1 - b0, t.bytes, bestInstr, t.nLiveIn, t.bpBytes);
   return 0;
+}
+
+// A failed preparation leaves no half-built tables behind: m->wide is either complete or null.
+int wide_prepare (mb_machine* m) {
+  if (wide_prepare_tables (m) == 0) return 0;
+  if (WHost* h = wh (m)) {
+    if (h->dLin) cudaFree (h->dLin);
+    if (h->dLog) cudaFree (h->dLog);
+    delete h;
+    m->wide = nullptr;
+  }
+  return 1;
 }
 
 // launch shape: column warps per CTA (W), ring depth, where the tables live, CTAs per SM
@@ -721,14 +733,12 @@ template<int OP> static const void* kernel_for (int G, bool tabs) {
 }
 
 template<int OP>
-static int choose_shape (const WHost* h, bool oneD, WShape& best) {
+static int choose_shape (const WHost* h, bool oneD, int forceW, WShape& best) {
   const WideTables& t = h->t;
   const int R = t.hasMatch ? 3 : 2, CPW = 32 / t.G;
   const size_t kMaxSmem = 227 * 1024;
   double bestScore = -1;
   static const int cand[] = { 16, 12, 8, 6, 4, 3, 2, 1, 0 };
-  int forceW = 0;
-  if (const char* e = getenv ("MB_WIDE_W")) forceW = atoi (e);
   for (int tabIn = 1; tabIn >= 0; --tabIn) {
     const void* fn = kernel_for<OP> (t.G, tabIn != 0);
     MB_CUDA (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxSmem));
@@ -776,7 +786,7 @@ static int wide_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& 
   int64_t maxLo = 0;
   for (int64_t k: order) { if (b->xOff[k + 1] != b->xOff[k]) oneD = false; maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]); }
   WShape sh;
-  if (choose_shape<OP> (h, oneD, sh)) return 1;
+  if (choose_shape<OP> (h, oneD, m->opt.get ("wide_w", 0), sh)) return 1;
   const int nWarps = sh.W + 1, CPW = 32 / h->t.G;
   const int64_t nWork = (int64_t) order.size();
   const int64_t wantCtas = oneD ? (nWork + nWarps * CPW - 1) / (nWarps * CPW) : nWork;
@@ -824,7 +834,7 @@ int wide_forward (mb_machine* m, mb_batch* b, double* loglike) {
     if (!m->bigTried) {      // a machine the generator cannot handle after all (NVRTC out of resources, ...) stays with the table-driven sweep
       m->bigTried = true;
       if (big_supported (m, nullptr) && big_prepare (m)) {
-        if (getenv ("MB_WIDE_VERBOSE")) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
+        if (m->opt.get ("verbose", 0)) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
         big_destroy (m);
       }
     }
@@ -869,7 +879,7 @@ int wide_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (!m->bigTried) {      // a machine the generator cannot handle after all (NVRTC out of resources, ...) stays with the table-driven sweep
       m->bigTried = true;
       if (big_supported (m, nullptr) && big_prepare (m)) {
-        if (getenv ("MB_WIDE_VERBOSE")) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
+        if (m->opt.get ("verbose", 0)) fprintf (stderr, "big engine: not available for this machine (%s); using the wide engine\n", mb_last_error());
         big_destroy (m);
       }
     }

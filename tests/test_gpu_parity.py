@@ -25,8 +25,10 @@ def _capi():
     return capi
 
 
-def make_machine(capi, m: FlatMachine, engine: int):
+def make_machine(capi, m: FlatMachine, engine: int, **options):
     capi.set_engine(engine)
+    for k, v in options.items():
+        capi.set_option(k, v)
     try:
         return capi.Machine(m.n_states, m.n_in, m.n_out, m.src, m.dst, m.tin, m.tout, m.lw)
     except capi.MachineBossError as e:
@@ -37,6 +39,8 @@ def make_machine(capi, m: FlatMachine, engine: int):
         raise
     finally:
         capi.set_engine(-1)
+        for k in options:
+            capi.set_option(k, None)
 
 
 def close(a, b, rel=REL):
@@ -198,16 +202,15 @@ def test_stored_matrices(name):
 
 
 @pytest.mark.parametrize("narrow", [0, 1])
-def test_jit_strip_widths(narrow, monkeypatch):
+def test_jit_strip_widths(narrow):
     """The score-only kernels exist at 4 and at 8 columns per lane (the wider ones with a frame per lane in the
     linear sweeps); the engine picks per call.  Both, forced, on pairs that span several strips of either width."""
     capi = _capi()
-    monkeypatch.setenv("MB_JIT_NARROW", str(narrow))
     fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
     shapes = [(300, 280), (0, 7), (129, 40), (257, 300), (520, 64), (31, 530)]
     pairs = [(synth_tokens(91, k, 0, li, 4), synth_tokens(91, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
     orc = Oracle(fm)
-    m = make_machine(capi, fm, 1)
+    m = make_machine(capi, fm, 1, jit_narrow=narrow)
     b = capi.Batch(pairs)
     ll = capi.forward(m, b)
     bl = capi.backward(m, b)
@@ -222,17 +225,16 @@ def test_jit_strip_widths(narrow, monkeypatch):
 
 
 @pytest.mark.parametrize("reads_per_lane", [1, 2, 4])
-def test_lane_engine_reads_per_lane(reads_per_lane, monkeypatch):
+def test_lane_engine_reads_per_lane(reads_per_lane):
     """Batches without input sequences go through the lane engine (a read per lane, mb_lane.cu): every
     reads-per-lane variant, ragged read lengths filling more than one task, against the oracle."""
     capi = _capi()
-    monkeypatch.setenv("MB_LANE_R", str(reads_per_lane))
     for name, n_reads, max_len in (("unitindel", 150, 12), ("hmmer_pf00516", 140, 9)):
         fm = FlatMachine.from_json(load_golden(name)["machine"])
         lens = [(7 * k + 3) % (max_len + 1) for k in range(n_reads)]
         pairs = [(np.zeros(0, np.uint8), synth_tokens(21, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
         orc = Oracle(fm)
-        m = make_machine(capi, fm, 2)
+        m = make_machine(capi, fm, 2, lane_r=reads_per_lane)
         b = capi.Batch(pairs)
         ll = capi.forward(m, b)
         sc, paths = capi.viterbi(m, b)
@@ -270,9 +272,9 @@ def test_linear_sweep_long_pairs_stay_in_the_linear_domain():
         assert abs(bl[k] - f) <= 1e-9 * abs(f), (k, bl[k], f)
 
 
-def test_big_engine_against_wide_engine(monkeypatch):
+def test_big_engine_against_wide_engine():
     """Mid-size machines with full matrices run on the generated thread-per-cell sweep (mb_big.cu); the same pairs
-    through the table-driven wide engine (MB_NO_BIG) must give the same Forward values to rounding, bit-identical
+    through the table-driven wide engine (option no_big) must give the same Forward values to rounding, bit-identical
     Viterbi scores and identical paths.  Pairs long enough for several strips whose first rows no path reaches
     (the case that needs an empty lane to adopt its frame from the boundary), none of them flagged."""
     capi = _capi()
@@ -285,8 +287,7 @@ def test_big_engine_against_wide_engine(monkeypatch):
     redo = b.last_redo()
     sc, paths = capi.viterbi(m_big, b)
     sc_only = capi.viterbi(m_big, b, paths=False)
-    monkeypatch.setenv("MB_NO_BIG", "1")
-    m_wide = make_machine(capi, fm, 2)
+    m_wide = make_machine(capi, fm, 2, no_big=1)
     ll_w = capi.forward(m_wide, b)
     sc_w, paths_w = capi.viterbi(m_wide, b)
     assert redo == 0
