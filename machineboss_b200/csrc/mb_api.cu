@@ -88,6 +88,14 @@ static void pool_trim (int device, size_t keepBytes) {   // free pooled blocks u
   }
 }
 
+// whether a block of the pool would serve a request of `bytes` (same rule as pool_take)
+bool ws_pool_fits (int device, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t) 255;
+  std::lock_guard<std::mutex> lock (g_poolMutex);
+  for (auto& bl: g_pool) if (bl.device == device && bl.bytes >= bytes && bl.bytes <= 2 * bytes + (1 << 20)) return true;
+  return false;
+}
+
 size_t ws_pool_bytes (int device) {
   std::lock_guard<std::mutex> lock (g_poolMutex);
   size_t total = 0;

@@ -204,7 +204,8 @@ void* ws_reserve (mb_batch* b, int slot, size_t bytes);   // nullptr + error set
 void ws_release (mb_batch* b, int slot);
 void ws_release_all (mb_batch* b);
 size_t ws_bytes (const mb_batch* b, int slot);
-size_t ws_pool_bytes (int device);   // freed blocks kept for reuse; released when an allocation fails
+size_t ws_pool_bytes (int device);
+bool ws_pool_fits (int device, size_t bytes);   // a pooled block would serve this request   // freed blocks kept for reuse; released when an allocation fails
 int paths_reserve (mb_batch* b, int64_t need);   // room for `need` packed path entries in b->dPaths (pooled; keeps the content)
 
 // timing helpers

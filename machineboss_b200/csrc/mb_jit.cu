@@ -999,13 +999,18 @@ static size_t device_total_bytes (int device) {
 
 // How much one chunk of scratch may take.  If what the slot already holds is enough for `wanted`
 // no driver query is made (cudaMemGetInfo costs milliseconds with large allocations live).
-static double memory_budget (const mb_batch* b, int slot, double wanted) {
-  if (wanted <= (double) ws_bytes (b, slot)) return (double) ws_bytes (b, slot);
+static double memory_budget (const mb_machine* m, const mb_batch* b, int slot, double wanted, const char* capOption) {
+  // a cap set by option (MiB): tests use it to force several chunks
+  const double cap = m->opt.has (capOption) ? (double) m->opt.get (capOption, 0) * 1048576.0 : 1e300;
+  if (wanted <= (double) ws_bytes (b, slot)) return std::min (cap, (double) ws_bytes (b, slot));
+  // a fresh batch of a repeated call (the end-to-end path creates one per call) finds the previous batch's
+  // scratch in the pool: no driver query then either (cudaMemGetInfo took 2 - 16 ms with 10 GB live)
+  if (wanted <= cap && ws_pool_fits (b->device, (size_t) wanted)) return wanted;
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo (&freeB, &totalB) != cudaSuccess) return 0;
   // the slot's current buffer is released before it grows; at most half the device per chunk, so the
   // scratch can stay attached to the batch between calls (keep_scratch_bytes) without starving others
-  return std::min (0.85 * (double) (freeB + ws_bytes (b, slot) + ws_pool_bytes (b->device)), 0.5 * (double) totalB);
+  return std::min (cap, std::min (0.85 * (double) (freeB + ws_bytes (b, slot) + ws_pool_bytes (b->device)), 0.5 * (double) totalB));
 }
 
 // Large scratch (back-pointers, stored Forward values) stays attached to the batch between calls, so
@@ -1034,7 +1039,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   double wanted = 0;
   for (int64_t k = 0; k < b->nPairs; ++k)
     wanted += (double) ((((b->yOff[k + 1] - b->yOff[k]) + 1) * ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * W) * J.tbBytes + 255) & ~(int64_t) 255);
-  const double budget = memory_budget (b, WS_TB, wanted);
+  const double budget = memory_budget (m, b, WS_TB, wanted, "jit_tb_budget_mb");
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
   std::vector<int64_t> chunkBytes (1, 0);
@@ -1131,7 +1136,7 @@ static int counts_log (mb_machine* m, mb_batch* b, const std::vector<int64_t>& p
   if (pairs.empty()) return 0;
   double wanted = 0;
   for (int64_t k: pairs) wanted += 8.0 * (double) (((((b->xOff[k + 1] - b->xOff[k]) + 1) * ((b->yOff[k + 1] - b->yOff[k]) + 1) * m->S) + 31) & ~(int64_t) 31);
-  const double budget = memory_budget (b, WS_F, wanted) / 8.0;
+  const double budget = memory_budget (m, b, WS_F, wanted, "jit_f_budget_mb") / 8.0;
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), chunkDoubles (1, 0);
   for (int64_t k: pairs) {
@@ -1187,7 +1192,7 @@ static int counts_lin (mb_machine* m, mb_batch* b, const std::vector<int64_t>& p
   double wanted = 0;
   for (int64_t k: pairs)
     wanted += 4.0 * (double) ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * ((b->yOff[k + 1] - b->yOff[k]) + 32) * (int64_t) (32 * J.C * J.storeQ * 4));
-  const double budget = memory_budget (b, WS_F, wanted) / 4.0;     // in 32-bit words
+  const double budget = memory_budget (m, b, WS_F, wanted, "jit_f_budget_mb") / 4.0;     // in 32-bit words
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> fOffHost ((size_t) b->nPairs, 0), efOffHost ((size_t) b->nPairs, 0), chunkWords (1, 0), chunkEf (1, 0);
   for (int64_t k: pairs) {

@@ -217,75 +217,98 @@ struct SeqPairList {
   }
 };
 
-// ---- Envelope (src/seqpair.h:75-113, seqpair.cpp:100-229) ----
-// Output row j keeps input positions inStart[j] <= i < inEnd[j].
+// ---- Envelope (the role of src/seqpair.h:75-113, seqpair.cpp:100-229) ----
+// The cells of a pair's matrices that may be used: on output row j the input positions inStart[j] <= i < inEnd[j]
+// (row j = after j output symbols, position i = after i input symbols).  Three shapes, as in the reference:
+//   full   every cell;
+//   path   exactly the cells an alignment passes through: row j runs from the input position at which output
+//          symbol j was emitted to the position at which symbol j+1 is about to be;
+//   area   the band around an alignment that keeps, on each row, the cells between the match columns `width`
+//          matches before and `width` matches after the row's own position in the alignment.
 struct Envelope {
   typedef long InputIndex;
   typedef long OutputIndex;
   InputIndex inLen = 0;
   OutputIndex outLen = 0;
   vector<InputIndex> inStart, inEnd;
-  Envelope() { clear(); }
-  Envelope (const SeqPair& sp) {                       // seqpair.cpp:104-110
-    if (sp.alignment.size()) initPath (sp.alignment); else initFull (sp);
-    if (!fits (sp)) throw runtime_error ("Envelope/sequence mismatch");
+
+  Envelope() { setRows (0, 0); }
+  Envelope (const SeqPair& sp) {
+    if (sp.alignment.empty()) initFull (sp); else initPath (sp.alignment);
+    requireFit (sp);
   }
-  Envelope (const SeqPair& sp, size_t width) {         // seqpair.cpp:112-118
-    if (sp.alignment.size()) initPathArea (sp.alignment, width); else initFull (sp);
-    if (!fits (sp)) throw runtime_error ("Envelope/sequence mismatch");
+  Envelope (const SeqPair& sp, size_t width) {
+    if (sp.alignment.empty()) initFull (sp); else initPathArea (sp.alignment, width);
+    requireFit (sp);
   }
-  void clear() { inLen = outLen = 0; inStart.assign (1, 0); inEnd.assign (1, 1); }
-  void initFull (const SeqPair& sp) {
-    clear();
-    inLen = (InputIndex) sp.input.seq.size();
-    outLen = (OutputIndex) sp.output.seq.size();
-    inStart.assign ((size_t) outLen + 1, 0);
-    inEnd.assign ((size_t) outLen + 1, inLen + 1);
-  }
-  void initPath (const SeqPair::AlignPath& cols) {     // seqpair.cpp:134-152
-    clear();
-    for (const auto& t: cols) {
-      const bool gotInput = t.first.size(), gotOutput = t.second.size();
-      if (!gotInput && gotOutput) { inStart.push_back (inEnd.back() - 1); inEnd.push_back (inEnd.back()); ++outLen; }
-      else if (gotInput && !gotOutput) { ++inEnd.back(); ++inLen; }
-      else if (gotInput && gotOutput) { inStart.push_back (inEnd.back()); inEnd.push_back (inEnd.back() + 1); ++inLen; ++outLen; }
-    }
-  }
-  void initPathArea (const SeqPair::AlignPath& cols, size_t width) {   // seqpair.cpp:154-182
-    clear();
-    vector<InputIndex> match;
-    vector<size_t> nBefore (1, 0);
-    for (const auto& t: cols) {
-      const bool gotInput = t.first.size(), gotOutput = t.second.size();
-      if (gotInput && gotOutput) match.push_back (inLen);
-      if (gotInput) ++inLen;
-      if (gotOutput) { ++outLen; nBefore.push_back (match.size()); }
-    }
-    inStart.clear();
+  static Envelope fullEnvelope (const SeqPair& sp) { Envelope e; e.initFull (sp); return e; }
+
+  void clear() { setRows (0, 0); }
+  void initFull (const SeqPair& sp) { setRows ((InputIndex) sp.input.seq.size(), (OutputIndex) sp.output.seq.size()); }
+
+  // One walk over the alignment columns.  `consumed` counts input symbols so far; a column with an output
+  // symbol closes the current row just before it (a match column's own input symbol belongs to the next row)
+  // and opens the next row just after it.
+  void initPath (const SeqPair::AlignPath& cols) {
+    inStart.assign (1, 0);
     inEnd.clear();
-    for (OutputIndex j = 0; j <= outLen; ++j) {
-      InputIndex iStart = 0, iEnd = inLen + 1;
-      if (nBefore[j] > width) iStart = match[nBefore[j] - width - 1] + 1;
-      const size_t nAfter = match.size() - nBefore[j];
-      if (nAfter > width) iEnd = match[nBefore[j] + width] + 1;
-      inStart.push_back (iStart);
-      inEnd.push_back (iEnd);
+    InputIndex consumed = 0;
+    for (const auto& col: cols) {
+      const bool hasIn = !col.first.empty(), hasOut = !col.second.empty();
+      if (hasOut) inEnd.push_back (consumed + 1);
+      if (hasIn) ++consumed;
+      if (hasOut) inStart.push_back (consumed);
+    }
+    inEnd.push_back (consumed + 1);
+    inLen = consumed;
+    outLen = (OutputIndex) inStart.size() - 1;
+  }
+
+  // matchAt[k] = input position just before the k-th match column; on row j, seen = matches at or before output
+  // symbol j.  The row keeps everything after the match `width + 1` back and up to the match `width` ahead.
+  void initPathArea (const SeqPair::AlignPath& cols, size_t width) {
+    vector<InputIndex> matchAt;
+    vector<size_t> seenOnRow (1, 0);
+    InputIndex consumed = 0;
+    for (const auto& col: cols) {
+      const bool hasIn = !col.first.empty(), hasOut = !col.second.empty();
+      if (hasIn && hasOut) matchAt.push_back (consumed);
+      if (hasIn) ++consumed;
+      if (hasOut) seenOnRow.push_back (matchAt.size());
+    }
+    setRows (consumed, (OutputIndex) seenOnRow.size() - 1);
+    const size_t nMatch = matchAt.size();
+    for (size_t j = 0; j < seenOnRow.size(); ++j) {
+      const size_t seen = seenOnRow[j];
+      if (seen > width) inStart[j] = matchAt[seen - width - 1] + 1;
+      if (seen + width < nMatch) inEnd[j] = matchAt[seen + width] + 1;
     }
   }
+
   bool fits (const SeqPair& sp) const { return inLen == (InputIndex) sp.input.seq.size() && outLen == (OutputIndex) sp.output.seq.size(); }
-  static bool overlapping (InputIndex s1, InputIndex e1, InputIndex s2, InputIndex e2) { return !(s1 >= e2 || s2 >= e1); }   // seqpair.h:89-93
-  bool connected() const {                              // seqpair.cpp:188-194
-    bool conn = overlapping (inStart[0], inEnd[0], 0, 1);
-    for (OutputIndex y = 1; conn && y <= outLen; ++y) conn = conn && overlapping (inStart[y - 1], inEnd[y - 1] + 1, inStart[y], inEnd[y]);
-    return conn && overlapping (inStart[outLen], inEnd[outLen], inLen, inLen + 1);
+  static bool overlapping (InputIndex s1, InputIndex e1, InputIndex s2, InputIndex e2) { return s1 < e2 && s2 < e1; }   // half-open intervals share a point
+  // A path from (0, 0) to (inLen, outLen) exists inside the envelope's outline: the first row holds position 0,
+  // the last row holds inLen, and each row reaches the previous one straight down or diagonally.
+  bool connected() const {
+    if (!(inStart[0] <= 0 && inEnd[0] > 0)) return false;
+    for (OutputIndex j = 1; j <= outLen; ++j)
+      if (!overlapping (inStart[j - 1], inEnd[j - 1] + 1, inStart[j], inEnd[j])) return false;
+    return inStart[outLen] <= inLen && inEnd[outLen] > inLen;
   }
   bool isFull() const { for (OutputIndex j = 0; j <= outLen; ++j) if (inStart[j] != 0 || inEnd[j] != inLen + 1) return false; return true; }
-  static Envelope fullEnvelope (const SeqPair& sp) { Envelope e; e.initFull (sp); return e; }
-  void writeJson (ostream& out) const {                 // seqpair.cpp:224-229
+  void writeJson (ostream& out) const {                 // [[start, end], ...] per output row (seqpair.cpp:224-229)
     out << "[";
     for (OutputIndex j = 0; j <= outLen; ++j) out << (j ? "," : "") << "[" << inStart[j] << "," << inEnd[j] << "]";
     out << "]";
   }
+
+private:
+  void setRows (InputIndex nIn, OutputIndex nOut) {     // every row of an nIn x nOut pair, unrestricted
+    inLen = nIn; outLen = nOut;
+    inStart.assign ((size_t) nOut + 1, 0);
+    inEnd.assign ((size_t) nOut + 1, nIn + 1);
+  }
+  void requireFit (const SeqPair& sp) const { if (!fits (sp)) throw runtime_error ("Envelope/sequence mismatch"); }
 };
 
 inline list<Envelope> envelopes (const SeqPairList& l) { list<Envelope> e; for (const auto& sp: l.seqPairs) e.push_back (Envelope (sp)); return e; }                 // seqpair.cpp:231-236

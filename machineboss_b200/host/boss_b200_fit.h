@@ -362,88 +362,109 @@ inline map<string, double> paramCounts (const MachineCounts& counts, const Machi
   return paramCount;
 }
 
-// ---- M-step (counts.cpp:117-295) ----
+// ---- M-step (the role of MachineObjective, counts.cpp:108-295) ----
+// Maximise  Q(theta) = sum_t count_t * log w_t(theta)  over the constrained parameters theta.  Every degree of
+// freedom gets an unconstrained coordinate u, and each constrained parameter is an expression of coordinates:
+//   "prob"  p = exp(-u^2)          "rate"  r = u^2
+//   "norm"  group p_0 .. p_{n-1}: a unit stick is broken n-1 times, break k keeping the fraction
+//           keep_k = exp(-u_k^2) of what is left:   p_k = (1 - keep_k) prod_{j<k} keep_j,   p_{n-1} = prod_j keep_j
+// This is the reference's map (it has to be: its fit goldens pin the optimum's basin to 4 digits, and BFGS from
+// the same start in the same coordinates is what reproduces them); everything else here -- the objective kept
+// as a list of (count, weight) terms and differentiated with dual numbers, the coordinate bookkeeping, the
+// minimiser -- is this file's own.
 struct MachineObjective {
-  Constraints constraints;
-  vector<string> transformedParam;
-  map<string, size_t> transformedParamIndex;
-  ParamDefs constantDefs, paramTransformDefs, allDefs;
-  WeightExpr objective;
+  struct Term { double count; WeightExpr weight; };
+  struct Group { vector<string> member; size_t firstCoord; };      // a norm group and its n-1 coordinates
+  struct Single { string name; size_t coord; bool isRate; };       // a prob or rate parameter and its coordinate
 
-  MachineObjective (const Machine& machine, const MachineCounts& counts, const Constraints& cons, const Params& constants)
-    : constraints (machine.cons.combine (cons)), constantDefs (machine.funcs.combine (constants).defs), objective (WeightAlgebra::zero())
-  {
+  vector<Term> terms;              // transitions with a non-zero expected count
+  vector<Group> groups;
+  vector<Single> singles;
+  vector<string> coordName;        // coordinate k is the variable coordName[k]
+  ParamDefs bound;                 // constants and functions, plus every constrained parameter in coordinates
+
+  MachineObjective (const Machine& machine, const MachineCounts& counts, const Constraints& cons, const Params& constants) {
     using namespace WeightAlgebra;
-    for (StateIndex s = 0; s < machine.nStates(); ++s) {
-      size_t t = 0;
-      for (const auto& tr: machine.state[s].trans)
-        objective = subtract (objective, multiply (doubleConstant (counts.count[s][t++]), logOf (tr.weight)));
-    }
-    const std::set<string> p = params (objective, ParamDefs());
-    int trIdx = 0;
-    auto makeTransformedParamName = [&] (const string& prm) -> string {
-      string trParam;
-      do trParam = string ("$x") + std::to_string (++trIdx); while (p.count (trParam));
-      transformedParamIndex[prm] = transformedParam.size();
-      transformedParam.push_back (trParam);
-      return trParam;
-    };
-    auto squareFunc = [] (const string& tr) { return multiply (param (tr), param (tr)); };
-    auto expFunc = [&] (const string& tr) { return expOf (minus (squareFunc (tr))); };
-    // p_i = (1 - exp(-x_i^2)) prod_{k<i} exp(-x_k^2)
-    for (const auto& c: constraints.norm) {
-      WeightExpr notPrev = one();
-      for (size_t n = 0; n < c.size(); ++n) {
-        if (n + 1 == c.size()) paramTransformDefs[c[n]] = notPrev;
-        else {
-          const WeightExpr notThis = expFunc (makeTransformedParamName (c[n]));
-          paramTransformDefs[c[n]] = multiply (notPrev, negate (notThis));
-          notPrev = multiply (notPrev, notThis);
-        }
+    std::set<string> taken;        // names already meaning something: a coordinate must not shadow them
+    for (StateIndex s = 0; s < machine.nStates(); ++s)
+      for (size_t t = 0; t < machine.state[s].trans.size(); ++t) {
+        const WeightExpr& w = machine.state[s].trans[t].weight;
+        for (const auto& nm: params (w, ParamDefs())) taken.insert (nm);
+        if (counts.count[s][t] != 0.) terms.push_back (Term { counts.count[s][t], w });
       }
+    bound = machine.funcs.combine (constants).defs;
+    for (const auto& kv: bound) taken.insert (kv.first);
+    size_t serial = 0;
+    auto newCoord = [&] () {
+      string nm;
+      do nm = "$x" + std::to_string (++serial); while (taken.count (nm));
+      coordName.push_back (nm);
+      return coordName.size() - 1;
+    };
+    auto keepOf = [&] (size_t coord) {      // exp(-u^2)
+      const WeightExpr u = param (coordName[coord]);
+      return expOf (minus (multiply (u, u)));
+    };
+    const Constraints all = machine.cons.combine (cons);
+    for (const auto& members: all.norm) {
+      if (members.empty()) continue;
+      Group g { members, coordName.size() };
+      for (size_t k = 0; k + 1 < members.size(); ++k) newCoord();
+      WeightExpr left = one();               // what remains of the stick before break k
+      for (size_t k = 0; k < members.size(); ++k) {
+        if (k + 1 == members.size()) { bound[members[k]] = left; break; }
+        const WeightExpr keep = keepOf (g.firstCoord + k);
+        bound[members[k]] = multiply (left, negate (keep));
+        left = multiply (left, keep);
+      }
+      groups.push_back (g);
     }
-    for (const auto& pp: constraints.prob) paramTransformDefs[pp] = expFunc (makeTransformedParamName (pp));
-    for (const auto& rp: constraints.rate) paramTransformDefs[rp] = squareFunc (makeTransformedParamName (rp));
-    allDefs = constantDefs;
-    for (const auto& kv: paramTransformDefs) allDefs[kv.first] = kv.second;
+    for (const auto& nm: all.prob) { const size_t c = newCoord(); bound[nm] = keepOf (c); singles.push_back (Single { nm, c, false }); }
+    for (const auto& nm: all.rate) { const size_t c = newCoord(); const WeightExpr u = param (coordName[c]); bound[nm] = multiply (u, u); singles.push_back (Single { nm, c, true }); }
   }
 
-  // objective and gradient at the transformed point x
-  double eval (const vector<double>& x, vector<double>* grad) const {
+  // -Q and its gradient at the coordinates u (exact forward-mode derivatives)
+  double eval (const vector<double>& u, vector<double>* grad) const {
     map<string, std::pair<size_t, double> > vars;
-    for (size_t n = 0; n < transformedParam.size(); ++n) vars[transformedParam[n]] = std::make_pair (n, x[n]);
-    WeightAlgebra::Env env { &allDefs, &vars, x.size() };
-    const Dual r = WeightAlgebra::evalDual (objective, env);
-    if (grad) *grad = r.d;
-    return r.v;
+    for (size_t k = 0; k < coordName.size(); ++k) vars[coordName[k]] = std::make_pair (k, u[k]);
+    WeightAlgebra::Env env { &bound, &vars, u.size() };      // (env.memo shares the parameter expressions between terms)
+    double f = 0;
+    if (grad) grad->assign (u.size(), 0.);
+    for (const Term& t: terms) {
+      const Dual w = WeightAlgebra::evalDual (t.weight, env);
+      f -= t.count * std::log (w.v);
+      if (grad) for (size_t k = 0; k < u.size(); ++k) (*grad)[k] -= t.count * w.d[k] / w.v;
+    }
+    return f;
+  }
+
+  // coordinates of a parameter assignment: the inverse of the map above
+  vector<double> coordinatesOf (const Params& at) const {
+    vector<double> u (coordName.size(), 0.);
+    auto value = [&] (const string& nm) { return WeightAlgebra::asDouble (at.defs.at (nm)); };
+    for (const Group& g: groups) {
+      double left = 1;
+      for (size_t k = 0; k + 1 < g.member.size(); ++k) {
+        const double keep = 1 - value (g.member[k]) / left;      // fraction of the remaining stick that survives break k
+        u[g.firstCoord + k] = std::sqrt (-std::log (keep));
+        left -= value (g.member[k]);
+      }
+    }
+    for (const Single& sp: singles) u[sp.coord] = sp.isRate ? std::sqrt (value (sp.name)) : std::sqrt (-std::log (value (sp.name)));
+    return u;
   }
 
   Params optimize (const Params& seed) const {
-    const size_t n = transformedParam.size();
-    vector<double> x (n, 0.);
-    // starting point from the seed (counts.cpp:233-262)
-    for (const auto& c: constraints.norm) {
-      double pSum = 0;
-      for (size_t k = 0; k + 1 < c.size(); ++k) {
-        const double p = WeightAlgebra::asDouble (seed.defs.at (c[k]));
-        const double z = 1 - p / (1 - pSum);
-        x[transformedParamIndex.at (c[k])] = std::sqrt (-std::log (z));
-        pSum += p;
-      }
-    }
-    for (const auto& pp: constraints.prob) x[transformedParamIndex.at (pp)] = std::sqrt (-std::log (WeightAlgebra::asDouble (seed.defs.at (pp))));
-    for (const auto& rp: constraints.rate) x[transformedParamIndex.at (rp)] = std::sqrt (WeightAlgebra::asDouble (seed.defs.at (rp)));
-
-    if (n) bfgs (x);
-
-    Params finalParams = seed;
+    vector<double> u = coordinatesOf (seed);
+    if (!u.empty()) bfgs (u);
+    Params fitted = seed;
     map<string, std::pair<size_t, double> > vars;
-    for (size_t k = 0; k < n; ++k) vars[transformedParam[k]] = std::make_pair (k, x[k]);
-    for (const auto& pt: paramTransformDefs) {
-      WeightAlgebra::Env env { &allDefs, &vars, n };
-      finalParams.defs[pt.first] = WeightAlgebra::doubleConstant (WeightAlgebra::evalDual (pt.second, env).v);
-    }
-    return finalParams;
+    for (size_t k = 0; k < u.size(); ++k) vars[coordName[k]] = std::make_pair (k, u[k]);
+    WeightAlgebra::Env env { &bound, &vars, u.size() };
+    auto assign = [&] (const string& nm) { fitted.defs[nm] = WeightAlgebra::doubleConstant (WeightAlgebra::evalDual (bound.at (nm), env).v); };
+    for (const Group& g: groups) for (const auto& nm: g.member) assign (nm);
+    for (const Single& sp: singles) assign (sp.name);
+    return fitted;
   }
 
 private:

@@ -21,7 +21,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(REPO, "tests"))
-from helpers import synth_tokens  # noqa: E402
+from helpers import mutate_tokens, synth_tokens  # noqa: E402
 
 REF = os.environ.get("MB_REFERENCE", "/root/reference")
 REFDRV = os.path.join(HERE, "_ref", "refdrv")
@@ -46,8 +46,9 @@ def machine_args(specs, params):
 
 
 def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backward,counts", matrices=False,
-         ref_expect=None, note="", gz=False):
-    """pairs: list of (in_symbols, out_symbols) or ("synth", N, Li, Lo, seed)."""
+         ref_expect=None, note="", gz=False, machine_from=None):
+    """pairs: list of (in_symbols, out_symbols), ("synth", N, Li, Lo, seed), or ("tokens", [(x, y), ...]) with
+    1-based token arrays.  machine_from: name of another fixture holding the same machine (stored once)."""
     margs = machine_args(specs, params)
     mach = run(margs + ["--emit-machine"])
     in_alpha, out_alpha = mach["inAlphabet"], mach["outAlphabet"]
@@ -60,6 +61,8 @@ def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backw
             x = synth_tokens(seed, k, 0, li if in_alpha else 0, max(1, len(in_alpha)))
             y = synth_tokens(seed, k, 1, lo if out_alpha else 0, max(1, len(out_alpha)))
             sym_pairs.append(([in_alpha[t - 1] for t in x], [out_alpha[t - 1] for t in y]))
+    elif pairs and pairs[0] == "tokens":
+        sym_pairs = [([in_alpha[t - 1] for t in x], [out_alpha[t - 1] for t in y]) for x, y in pairs[1]]
     elif pairs and isinstance(pairs[0], dict):      # raw SeqPair JSON carrying an "alignment" (=> path envelope)
         raw_pairs = pairs
         sym_pairs = [([c[0] for c in p["alignment"] if c[0]], [c[1] for c in p["alignment"] if c[1]]) for p in pairs]
@@ -85,9 +88,17 @@ def case(name, specs, pairs, params=None, do="forward,rolling,viterbi,path,backw
         if pairs and isinstance(pairs[0], dict):
             p["alignment"] = pairs[k]["alignment"]
         out_pairs.append(p)
-    j = {"name": name, "note": note, "specs": specs, "params": params, "machine": mach, "synth": synth,
+    if machine_from:
+        with_machine = json.load(__import__("gzip").open(os.path.join(OUT, machine_from + ".json.gz"), "rt")) if os.path.exists(os.path.join(OUT, machine_from + ".json.gz")) \
+            else json.load(open(os.path.join(OUT, machine_from + ".json")))
+        assert with_machine["machine"] == mach, "machine_from does not hold the same machine"
+    j = {"name": name, "note": note, "specs": specs, "params": params, "synth": synth,
          "pairs": out_pairs, "loglike": res.get("loglike"), "counts": res.get("counts"),
          "ref_expect": ref_expect or {}}
+    if machine_from:
+        j["machine_from"] = machine_from
+    else:
+        j["machine"] = mach
     if gz:
         import gzip
         with gzip.open(os.path.join(OUT, name + ".json.gz"), "wt", compresslevel=9) as fo:
@@ -197,8 +208,53 @@ def main():
     case("hmmer_pf00516", [hmm], ("synth", 3, 0, 37, 108), gz=True, note="PF00516 local core, S=2439, T=24367")
     case("hmmer_pf00516_protpsw", [hmm, "preset:protpsw"], ("synth", 1, 0, 21, 109), gz=True,
          note="BASELINE config 5 machine: PF00516 => protpsw, S=12176, T=74012")
-    case("dnapsw_1k", ["preset:dnapsw"], ("synth", 1, 1000, 1000, 12345), do="rolling,viterbi,path",
-         note="BASELINE config 1: one 1 kb x 1 kb pair")
+    round2_cases()
+
+
+def peaked_dna():
+    p = {"gapOpen": 0.05, "gapExtend": 0.5, "eqmA": 0.25, "eqmC": 0.25, "eqmG": 0.25, "eqmT": 0.25}
+    for a in "ACGT":
+        for b in "ACGT":
+            p["sub%s%s" % (a, b)] = 0.91 if a == b else 0.03
+    return p
+
+
+def peaked_protein():
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    p = {"gapOpen": 0.05, "gapExtend": 0.5}
+    for a in aa:
+        p["eqm" + a] = 0.05
+        for b in aa:
+            p["sub%s%s" % (a, b)] = 0.62 if a == b else 0.02
+    return p
+
+
+def round2_cases():
+    """Fixtures at the BASELINE configs' own sizes and on hard inputs ('next round' item 1)."""
+    hmm = "hmmer:" + os.path.join(REF, "examples/PF00516.hmm")
+    # (i) counts at config sizes
+    case("dnapsw_1k", ["preset:dnapsw"], ("synth", 1, 1000, 1000, 12345), do="forward,rolling,viterbi,path,backward,counts",
+         note="BASELINE configs 1 and 2: one 1 kb x 1 kb pair, every pass incl. posterior counts")
+    case("protpsw_300_batch", ["preset:protpsw"], ("synth", 4, 300, 300, 205), gz=True,
+         note="BASELINE config 3 size: 300 aa pairs, every pass incl. counts")
+    # (ii) parameter set B (SURVEY 8d): peaked weights, output = input mutated 10 % / 2 %
+    xs = [synth_tokens(301, k, 0, 1000, 4) for k in range(2)]
+    case("dnapsw_peaked_1k", ["preset:dnapsw"], ("tokens", [(x, mutate_tokens(301, k, x, 4)) for k, x in enumerate(xs)]),
+         params=peaked_dna(), gz=True, note="set B at config size: 1 kb pairs, output = input with 10 % substitutions, 2 % indels")
+    xs = [synth_tokens(302, k, 0, 300, 20) for k in range(3)]
+    case("protpsw_peaked_300", ["preset:protpsw"], ("tokens", [(x, mutate_tokens(302, k, x, 20)) for k, x in enumerate(xs)]),
+         params=peaked_protein(), gz=True, note="set B, protpsw: 300 aa pairs, mutated copies")
+    # (iii) config 4 at a config-like shape
+    case("prot2dna_dnapsw_2k", ["preset:prot2dna", "preset:dnapsw"], ("synth", 1, 300, 2000, 206), do="rolling,viterbi,path", gz=True,
+         machine_from="prot2dna_dnapsw", note="BASELINE config 4 machine, one pair of 300 aa x 2 kb")
+    # (iv) config 5 at its read lengths
+    for nm, specs, seed in (("hmmer_pf00516_reads", [hmm], 207), ("hmmer_pf00516_protpsw_reads", [hmm, "preset:protpsw"], 208)):
+        reads = [(synth_tokens(seed, k, 0, 0, 1), synth_tokens(seed, k, 1, lo, 20)) for k, lo in enumerate((50, 275, 500))]
+        case(nm, specs, ("tokens", reads), do="rolling,viterbi,path", gz=True, machine_from=nm[:-6],
+             note="BASELINE config 5: reads of 50, 275 and 500 residues")
+    # (v) an E-step pair beyond the linear count kernels' range (log-domain FP32-accumulator path)
+    case("dnapsw_3k", ["preset:dnapsw"], ("synth", 1, 3300, 3100, 209), do="forward,backward,counts,viterbi", gz=True,
+         note="a pair longer than 3 kb: Forward, Backward, posterior counts, Viterbi score")
 
 
 def envelope_case():
@@ -253,6 +309,8 @@ if __name__ == "__main__":
         sample_case()
     elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "envelope":
         envelope_case()
+    elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "round2":
+        round2_cases()
     else:
         main()
         sample_case()

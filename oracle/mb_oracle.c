@@ -137,6 +137,10 @@ static inline double* cellp (const cells* m, int64_t i, int64_t o) {
 static inline const double* cellr (const cells* m, int64_t i, int64_t o) {
   return env_contains (i, o) ? cellp (m, i, o) : m->ninf;
 }
+/* DPMatrix::alloc fills the storage with -inf (dpmatrix.defs.h:36): a read of a cell that has not been written
+   yet -- the silent self-loop isAdvancingMachine allows on state 0 (machine.cpp:759) -- sees -inf in a full
+   matrix, and whatever row o-2 left behind in a rolling one */
+static void fill_ninf (double* c, size_t n) { for (size_t q = 0; q < n; ++q) c[q] = -INFINITY; }
 static double* make_ninf (int S) {
   double* v = (double*) malloc (sizeof (double) * (size_t) (S ? S : 1));
   for (int s = 0; s < S; ++s) v[s] = -INFINITY;
@@ -152,6 +156,7 @@ double mbo_forward (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
   double* ninf = make_ninf (S);
   cells M = { matrix, Li, S, matrix == NULL, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * 2 * (size_t) (Li + 1) * S);
+  fill_ninf (M.c, (size_t) (matrix ? Lo + 1 : 2) * (size_t) (Li + 1) * S);
   for (int64_t o = 0; o <= Lo; ++o) {
     const int outTok = o ? y[o - 1] : 0;
     for (int64_t i = 0; i <= Li; ++i) {
@@ -190,6 +195,7 @@ double mbo_backward (const mbo_machine* m, const uint8_t* x, int64_t Li, const u
   double* ninf = make_ninf (S);
   cells M = { matrix, Li, S, matrix == NULL, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * 2 * (size_t) (Li + 1) * S);
+  fill_ninf (M.c, (size_t) (matrix ? Lo + 1 : 2) * (size_t) (Li + 1) * S);
   for (int64_t o = Lo; o >= 0; --o) {
     const int endO = (o == Lo);
     const int outTok = endO ? 0 : y[o];
@@ -230,6 +236,7 @@ double mbo_viterbi (const mbo_machine* m, const uint8_t* x, int64_t Li, const ui
   double* ninf = make_ninf (S);
   cells M = { matrix, Li, S, !needFull, ninf };
   if (!matrix) M.c = (double*) malloc (sizeof (double) * (size_t) (needFull ? Lo + 1 : 2) * (size_t) (Li + 1) * S);
+  fill_ninf (M.c, (size_t) (needFull ? Lo + 1 : 2) * (size_t) (Li + 1) * S);
   for (int64_t o = 0; o <= Lo; ++o) {
     const int outTok = o ? y[o - 1] : 0;
     for (int64_t i = 0; i <= Li; ++i) {

@@ -71,10 +71,14 @@ def load_golden(name: str) -> dict:
     path = os.path.join(GOLDEN, name + ".json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f)
-    import gzip
-    with gzip.open(path + ".gz", "rt") as f:
-        return json.load(f)
+            j = json.load(f)
+    else:
+        import gzip
+        with gzip.open(path + ".gz", "rt") as f:
+            j = json.load(f)
+    if isinstance(j, dict) and "machine_from" in j:      # large machines are stored once
+        j["machine"] = load_golden(j["machine_from"])["machine"]
+    return j
 
 
 def golden_names() -> list:
@@ -103,6 +107,29 @@ def synth_tokens(seed: int, pair_index: int, which: int, length: int, n_sym: int
                 + np.uint64(2 * pair_index + which) * np.uint64(0xD1B54A32D192ED03))
         p = np.arange(length, dtype=np.uint64) + base
     return (1 + (_splitmix64(p) % np.uint64(n_sym))).astype(np.uint8)
+
+
+def mutate_tokens(seed: int, pair_index: int, x: np.ndarray, n_sym: int, sub: float = 0.10, indel: float = 0.02) -> np.ndarray:
+    """SURVEY 8(d) parameter set B's data: the output is the input with `sub` substitutions and `indel` insertions
+    + deletions per position (half each), drawn from the splitmix64 stream (pair, which = 2)."""
+    n = len(x)
+    with np.errstate(over="ignore"):
+        base = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+                + np.uint64(2 * pair_index) * np.uint64(0xD1B54A32D192ED03) + np.uint64(0x5851F42D4C957F2D))
+        r = _splitmix64(np.arange(3 * n, dtype=np.uint64) + base)
+    u = (r[:n] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    alt = (r[n:2 * n] % np.uint64(n_sym - 1)).astype(np.int64)
+    ins = (1 + r[2 * n:] % np.uint64(n_sym)).astype(np.uint8)
+    xi = x.astype(np.int64)
+    subst = (1 + (xi - 1 + 1 + alt) % n_sym).astype(np.uint8)      # a different symbol
+    out = []
+    for p in range(n):
+        if u[p] < indel / 2:
+            continue                                 # deletion
+        out.append(subst[p] if u[p] < indel / 2 + sub else x[p])
+        if u[p] > 1.0 - indel / 2:
+            out.append(ins[p])                       # insertion after this position
+    return np.array(out, dtype=np.uint8)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -376,3 +376,144 @@ def test_errors():
     m = capi.Machine(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw)
     b = capi.Batch([])
     assert capi.forward(m, b).shape == (0,)
+
+
+def test_set_b_mutated_pairs_at_config_size():
+    """SURVEY 8(d) parameter set B at config size: peaked dnapsw weights, 1 kb pairs whose output is the input with
+    10 % substitutions and 2 % indels.  These are the hard inputs for the scaled linear sweeps (the likelihood
+    concentrates on a narrow diagonal band, so the dynamic range across a strip is at its largest): every pass
+    against the oracle, and NONE of the pairs may be handed to the log-domain kernels."""
+    from helpers import mutate_tokens
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked_1k")["machine"])
+    xs = [synth_tokens(401, k, 0, 1000 - 7 * k, 4) for k in range(6)]
+    pairs = [(x, mutate_tokens(401, k, x, 4)) for k, x in enumerate(xs)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    assert b.last_redo() == 0
+    bl = capi.backward(m, b)
+    assert b.last_redo() == 0
+    sc, paths = capi.viterbi(m, b)
+    cnt, cll = capi.counts(m, b)
+    assert b.last_redo() == 0
+    want = np.zeros(fm.n_trans)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(ll[k] - f) <= 1e-9 * abs(f) and abs(bl[k] - f) <= 1e-9 * abs(f), (k, ll[k], bl[k], f)
+        assert close(ll[k], orc.forward(x, y)) and close(cll[k], f)
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and paths[k].tolist() == p.tolist(), k
+        orc.counts(x, y, counts=want)
+    np.testing.assert_allclose(cnt, want, rtol=REL, atol=1e-7)
+
+
+@pytest.mark.parametrize("reads_per_lane", [1, 2, 4])
+def test_lane_engine_config5_read_lengths(reads_per_lane):
+    """BASELINE config 5's own read lengths (50 - 500 residues, ragged, several lane tasks, the last one partly
+    empty) through the lane engine at every reads-per-lane variant: PF00516 and PF00516 => protpsw."""
+    capi = _capi()
+    for name, n_reads in (("hmmer_pf00516", 150), ("hmmer_pf00516_protpsw", 70)):
+        fm = FlatMachine.from_json(load_golden(name)["machine"])
+        lens = [50 + (k * 37) % 451 for k in range(n_reads)]
+        lens[0], lens[1], lens[2] = 500, 50, 275
+        pairs = [(np.zeros(0, np.uint8), synth_tokens(23, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
+        orc = Oracle(fm)
+        m = make_machine(capi, fm, 2, lane_r=reads_per_lane)
+        b = capi.Batch(pairs)
+        ll = capi.forward(m, b)
+        assert b.last_redo() == 0, (name, b.last_redo())
+        sc, paths = capi.viterbi(m, b)
+        sc2 = capi.viterbi(m, b, paths=False)
+        check = sorted(set([0, 1, 2, 31, 32, 33, n_reads - 1] + list(range(5, n_reads, 29))))
+        for k in check:
+            x, y = pairs[k]
+            f = orc.forward(x, y)
+            assert forward_agrees(fm, x, y, ll[k], f), (name, k, ll[k], f)
+            v, p = orc.viterbi(x, y)
+            assert sc[k] == v and sc2[k] == v, (name, k, sc[k], v)
+            assert paths[k].tolist() == p.tolist(), (name, k)
+
+
+def test_chunked_traceback_and_counts():
+    """A scratch budget of a few MiB (options jit_tb_budget_mb / jit_f_budget_mb) forces the Viterbi back-pointers and
+    the E-step's stored Forward values into several chunks of pairs: same results as in one piece, and as the oracle."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    shapes = [(300 - 11 * k, 280 + 9 * k) for k in range(12)]
+    pairs = [(synth_tokens(93, k, 0, li, 4), synth_tokens(93, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
+    b = capi.Batch(pairs)
+    m1 = make_machine(capi, fm, 1)
+    sc1, paths1 = capi.viterbi(m1, b)
+    cnt1, ll1 = capi.counts(m1, b)
+    mc = make_machine(capi, fm, 1, jit_tb_budget_mb=1, jit_f_budget_mb=4)
+    b2 = capi.Batch(pairs)
+    sc, paths = capi.viterbi(mc, b2)
+    cnt, ll = capi.counts(mc, b2)
+    assert np.array_equal(sc, sc1) and np.array_equal(ll, ll1)
+    np.testing.assert_allclose(cnt, cnt1, rtol=1e-12)
+    for k in range(len(pairs)):
+        assert paths[k].tolist() == paths1[k].tolist(), k
+    # ids as bytes through the packed-path entry point (the chunks pack in pair order)
+    score, plen, off = np.empty(len(pairs)), np.zeros(len(pairs), np.int64), np.zeros(len(pairs) + 1, np.int64)
+    trans = np.zeros(sum(len(p) for p in paths), dtype=np.uint8)
+    capi.viterbi_into(mc, b2, score, plen, off, trans)
+    for k, p in enumerate(paths):
+        assert trans[off[k]:off[k + 1]].tolist() == p.tolist(), k
+    orc = Oracle(fm)
+    want = np.zeros(fm.n_trans)
+    for k, (x, y) in enumerate(pairs):
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and paths[k].tolist() == p.tolist(), k
+        orc.counts(x, y, counts=want)
+    np.testing.assert_allclose(cnt, want, rtol=REL, atol=1e-7)
+
+
+def test_tokens_outside_the_alphabet_are_rejected():
+    """A pre-tokenised batch is held to Tokenizer::tokenize's rule (eval.h:33-37): a token beyond the machine's
+    alphabet, or a 0 (epsilon) in the data, fails the call instead of indexing past the device tables."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_small")["machine"])
+    m = make_machine(capi, fm, -1)
+    for bad in ([1, 2, 5], [1, 0, 2]):
+        b = capi.Batch([(np.array(bad, np.uint8), np.array([1, 2], np.uint8))])
+        for call in (capi.forward, capi.backward, capi.counts, lambda mm, bb: capi.viterbi(mm, bb, paths=False)):
+            with pytest.raises(capi.MachineBossError, match="alphabet"):
+                call(m, b)
+    ok = capi.Batch([(np.array([1, 2, 4], np.uint8), np.array([1, 2], np.uint8))])
+    assert np.isfinite(capi.forward(m, ok)[0])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_silent_self_loop_on_the_start_state(engine):
+    """isAdvancingMachine exempts state 0 (machine.cpp:759): a silent 0 -> 0 transition is legal.  In the
+    reference's fill it reads the cell under construction, still -inf, so it never contributes; every engine
+    must agree (the generic engine once read the uninitialised cell there)."""
+    capi = _capi()
+    base = FlatMachine.from_json(load_golden("unitindel")["machine"])
+    ins = int(np.searchsorted(base.src, 1))      # after state 0's transitions
+    def with_loop(a, v):
+        return np.insert(a, ins, v)
+    fm = FlatMachine(base.n_states, base.n_in, base.n_out, with_loop(base.src, 0).astype(np.int32), with_loop(base.dst, 0).astype(np.int32),
+                     with_loop(base.tin, 0).astype(np.int32), with_loop(base.tout, 0).astype(np.int32), with_loop(base.lw, math.log(0.5)),
+                     base.in_alphabet, base.out_alphabet)
+    pairs = [(synth_tokens(3, k, 0, li, max(1, fm.n_in)), synth_tokens(3, k, 1, lo, max(1, fm.n_out))) for k, (li, lo) in enumerate([(2, 3), (0, 0), (5, 4), (40, 37)])]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, engine)
+    b = capi.Batch(pairs)
+    ll, bl = capi.forward(m, b), capi.backward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    cnt, _ = capi.counts(m, b)
+    want = np.zeros(fm.n_trans)
+    for k, (x, y) in enumerate(pairs):
+        # the reference's FULL matrices (ForwardMatrix, the API's storage): its rolling matrix reads row o-2's stale cell there
+        assert close(ll[k], orc.forward(x, y, matrix=True)[0]) and close(bl[k], orc.backward(x, y, matrix=True)[0]), (k, ll[k], bl[k])
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and paths[k].tolist() == p.tolist(), k
+        orc.counts(x, y, counts=want)
+    # getCounts multiplies the finished F and B cells through the loop (backward.cpp:76-84): a number no path
+    # produces; here the loop, which no path can take, counts 0
+    keep = np.arange(fm.n_trans) != ins
+    np.testing.assert_allclose(cnt[keep], want[keep], rtol=REL, atol=1e-7)
+    assert cnt[ins] == 0
