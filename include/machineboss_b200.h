@@ -129,6 +129,42 @@ int mb_counts (mb_machine* m, mb_batch* b, double* counts, double* loglike);
 #define MB_MATRIX_VITERBI  2
 int mb_matrix (mb_machine* m, mb_batch* b, int64_t pair, int32_t kind, double* cells);
 
+/* ---- one list of pairs over several GPUs of a box ----
+ * Replaces the reference's single-core loops over a SeqPairList: MachineCounts (counts.cpp:37-43) inside
+ * MachineFitter::fit (fitter.cpp:23-47), and the -L / -A loops of the CLI (boss.cpp:796,826).  The pairs are
+ * dealt to the devices longest-processing-time first by cell count (Li+1)(Lo+1); the machine is replicated; one
+ * host thread per device drives that device's share.  Forward / Viterbi: no communication, results gathered by
+ * pair index.  Counts: ncclAllReduce (sum, ncclDouble) of nTrans + 1 values over NVLink (libnccl.so.2, resolved
+ * at run time; one device, or no NCCL: added on the host -- mb_group_info says which).  Results are those of
+ * the single-device calls: identical for Forward and Viterbi, equal up to the order of summation for counts. */
+typedef struct mb_group mb_group;
+typedef struct mb_gmachine mb_gmachine;
+typedef struct mb_gbatch mb_gbatch;
+/* shardOfPair[k] = shard (0 .. nShards-1) of pair k under that deal; deterministic; pure host code */
+int mb_shard_pairs (int64_t nPairs, const int64_t* inOff, const int64_t* outOff, int32_t nShards, int32_t* shardOfPair);
+int mb_group_create (mb_group** out, const int32_t* devices, int32_t nDevices);      /* nDevices <= 0: every visible device */
+int mb_group_info (const mb_group* g, int32_t* nDevices, int32_t* devices, int32_t* usesNccl);
+void mb_group_destroy (mb_group* g);
+int mb_group_machine_create (mb_group* g, mb_gmachine** out, int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                             const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight);
+int mb_group_machine_update_weights (mb_gmachine* m, const double* logWeight);
+int mb_group_machine_set_option (mb_gmachine* m, const char* name, int32_t value);
+int mb_group_machine_info (const mb_gmachine* m, int32_t* nStates, int64_t* nTrans, int32_t* engine);
+void mb_group_machine_destroy (mb_gmachine* m);
+int mb_group_batch_create (mb_group* g, mb_gbatch** out, int64_t nPairs, const uint8_t* inTokens, const int64_t* inOff,
+                           const uint8_t* outTokens, const int64_t* outOff);
+int mb_group_batch_set_envelopes (mb_gbatch* b, const int64_t* rowOff, const int64_t* inStart, const int64_t* inEnd);
+int mb_group_batch_shard (const mb_gbatch* b, int32_t* deviceOfPair /* [nPairs], may be NULL */, double* cellsPerDevice /* [nDevices], may be NULL */);
+void mb_group_batch_destroy (mb_gbatch* b);
+int mb_group_forward (mb_gmachine* m, mb_gbatch* b, double* loglike);
+int mb_group_backward (mb_gmachine* m, mb_gbatch* b, double* loglike);
+int mb_group_viterbi (mb_gmachine* m, mb_gbatch* b, double* score, int64_t* pathLen);
+int mb_group_viterbi_paths (mb_gbatch* b, int32_t* pathTrans, const int64_t* pathOff);
+int mb_group_viterbi_paths_narrow (mb_gbatch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff);
+int mb_group_counts (mb_gmachine* m, mb_gbatch* b, double* counts, double* loglike);
+int mb_group_last_loglike (const mb_gmachine* m, double* total);      /* summed over all pairs by the last mb_group_counts' all-reduce */
+int mb_group_last_kernel_ms (const mb_gbatch* b, double* maxMs, int64_t* nLaunches);      /* slowest device, launches of all */
+
 /* ---- diagnostics (not part of the reference surface) ----
  * Generates the machine-specialised kernels for this machine structure and compiles them with
  * NVRTC for sm_100a WITHOUT touching a device (so it also runs where there is no GPU: the build

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmachineboss_b200.so")
-SOURCES = ["mb_api.cu", "mb_generic.cu", "mb_jit.cu", "mb_wide.cu", "mb_lane.cu", "mb_big.cu"]
+SOURCES = ["mb_api.cu", "mb_generic.cu", "mb_jit.cu", "mb_wide.cu", "mb_lane.cu", "mb_big.cu", "mb_group.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -52,7 +52,7 @@ def build_host(force: bool = False) -> str:
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     build()
-    cmd = ["g++", "-std=c++14", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-Wl,-rpath," + HERE]
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-lz", "-Wl,-rpath," + HERE]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)

@@ -21,7 +21,11 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check"]
+           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check",
+           "mb_shard_pairs", "mb_group_create", "mb_group_info", "mb_group_destroy", "mb_group_machine_create", "mb_group_machine_update_weights",
+           "mb_group_machine_set_option", "mb_group_machine_info", "mb_group_machine_destroy", "mb_group_batch_create", "mb_group_batch_set_envelopes",
+           "mb_group_batch_shard", "mb_group_batch_destroy", "mb_group_forward", "mb_group_backward", "mb_group_viterbi", "mb_group_viterbi_paths",
+           "mb_group_viterbi_paths_narrow", "mb_group_counts", "mb_group_last_loglike", "mb_group_last_kernel_ms"]
 
 
 class MachineBossError(RuntimeError):
@@ -62,6 +66,30 @@ def lib():
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
         L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
+        L.mb_shard_pairs.argtypes = [I64, P, P, I32, P]
+        L.mb_group_create.argtypes = [ctypes.POINTER(P), P, I32]
+        L.mb_group_info.argtypes = [P, ctypes.POINTER(I32), P, ctypes.POINTER(I32)]
+        L.mb_group_destroy.argtypes = [P]
+        L.mb_group_destroy.restype = None
+        L.mb_group_machine_create.argtypes = [P, ctypes.POINTER(P), I32, I32, I32, I64, P, P, P, P, P]
+        L.mb_group_machine_update_weights.argtypes = [P, P]
+        L.mb_group_machine_set_option.argtypes = [P, ctypes.c_char_p, I32]
+        L.mb_group_machine_info.argtypes = [P, ctypes.POINTER(I32), ctypes.POINTER(I64), ctypes.POINTER(I32)]
+        L.mb_group_machine_destroy.argtypes = [P]
+        L.mb_group_machine_destroy.restype = None
+        L.mb_group_batch_create.argtypes = [P, ctypes.POINTER(P), I64, P, P, P, P]
+        L.mb_group_batch_set_envelopes.argtypes = [P, P, P, P]
+        L.mb_group_batch_shard.argtypes = [P, P, P]
+        L.mb_group_batch_destroy.argtypes = [P]
+        L.mb_group_batch_destroy.restype = None
+        L.mb_group_forward.argtypes = [P, P, P]
+        L.mb_group_backward.argtypes = [P, P, P]
+        L.mb_group_viterbi.argtypes = [P, P, P, P]
+        L.mb_group_viterbi_paths.argtypes = [P, P, P]
+        L.mb_group_viterbi_paths_narrow.argtypes = [P, P, I32, P]
+        L.mb_group_counts.argtypes = [P, P, P, P]
+        L.mb_group_last_loglike.argtypes = [P, ctypes.POINTER(D)]
+        L.mb_group_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         _lib = L
     return _lib
 
@@ -284,3 +312,137 @@ def counts(m: Machine, b: Batch):
     ll = np.empty(b.n_pairs, dtype=np.float64)
     _check(lib().mb_counts(m.h, b.h, _ptr(c), _ptr(ll)))
     return c, ll
+
+
+# ---------------------------------------------------------------------------------------------
+# several GPUs of one box (mb_group_*): the list dealt to the devices, one host thread per device
+# ---------------------------------------------------------------------------------------------
+def shard_pairs(x_off, y_off, n_shards: int) -> np.ndarray:
+    """Shard (0 .. n_shards-1) of every pair under the library's longest-processing-time-first deal by cell count."""
+    x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.int64)
+    n = int(x_off.shape[0]) - 1
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    _check(lib().mb_shard_pairs(n, _ptr(x_off), _ptr(y_off), int(n_shards), out.ctypes.data))
+    return out[:n]
+
+
+class Group:
+    def __init__(self, devices=None):
+        self.h = ctypes.c_void_p()
+        if devices is None:
+            _check(lib().mb_group_create(ctypes.byref(self.h), None, 0))
+        else:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            _check(lib().mb_group_create(ctypes.byref(self.h), d.ctypes.data, int(d.shape[0])))
+        n, nccl = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(lib().mb_group_info(self.h, ctypes.byref(n), None, ctypes.byref(nccl)))
+        self.n_devices, self.uses_nccl = n.value, bool(nccl.value)
+
+    def close(self):
+        if self.h:
+            lib().mb_group_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupMachine:
+    def __init__(self, group: Group, n_states, n_in, n_out, src, dst, tin, tout, log_weight):
+        self.group = group
+        self.n_states, self.n_in, self.n_out = int(n_states), int(n_in), int(n_out)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
+        lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+        self.n_trans = int(lw.shape[0])
+        self.h = ctypes.c_void_p()
+        _check(lib().mb_group_machine_create(group.h, ctypes.byref(self.h), self.n_states, self.n_in, self.n_out, self.n_trans,
+                                             *[_ptr(a) for a in arrs], _ptr(lw)))
+
+    def update_weights(self, log_weight) -> None:
+        lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+        _check(lib().mb_group_machine_update_weights(self.h, _ptr(lw)))
+
+    def last_loglike(self) -> float:
+        v = ctypes.c_double(0)
+        _check(lib().mb_group_last_loglike(self.h, ctypes.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            lib().mb_group_machine_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupBatch:
+    def __init__(self, group: Group, pairs=None, *, x=None, x_off=None, y=None, y_off=None):
+        self.group = group
+        if pairs is not None:
+            xs = [np.asarray(p[0], dtype=np.uint8) for p in pairs]
+            ys = [np.asarray(p[1], dtype=np.uint8) for p in pairs]
+            x = np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+            y = np.concatenate(ys) if ys else np.zeros(0, np.uint8)
+            x_off = np.concatenate([[0], np.cumsum([len(a) for a in xs])]).astype(np.int64)
+            y_off = np.concatenate([[0], np.cumsum([len(a) for a in ys])]).astype(np.int64)
+        self.x = np.ascontiguousarray(x, dtype=np.uint8)
+        self.y = np.ascontiguousarray(y, dtype=np.uint8)
+        self.x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+        self.y_off = np.ascontiguousarray(y_off, dtype=np.int64)
+        self.n_pairs = int(self.x_off.shape[0]) - 1
+        self.h = ctypes.c_void_p()
+        _check(lib().mb_group_batch_create(group.h, ctypes.byref(self.h), self.n_pairs, _ptr(self.x), _ptr(self.x_off), _ptr(self.y), _ptr(self.y_off)))
+
+    def shard(self):
+        dev = np.zeros(max(self.n_pairs, 1), dtype=np.int32)
+        cells = np.zeros(self.group.n_devices, dtype=np.float64)
+        _check(lib().mb_group_batch_shard(self.h, dev.ctypes.data, cells.ctypes.data))
+        return dev[: self.n_pairs], cells
+
+    def last_kernel_ms(self):
+        ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+        _check(lib().mb_group_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def close(self):
+        if self.h:
+            lib().mb_group_batch_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def group_forward(m: GroupMachine, b: GroupBatch) -> np.ndarray:
+    out = np.empty(max(b.n_pairs, 1), dtype=np.float64)
+    _check(lib().mb_group_forward(m.h, b.h, out.ctypes.data))
+    return out[: b.n_pairs]
+
+
+def group_viterbi(m: GroupMachine, b: GroupBatch):
+    score = np.empty(max(b.n_pairs, 1), dtype=np.float64)
+    plen = np.zeros(max(b.n_pairs, 1), dtype=np.int64)
+    _check(lib().mb_group_viterbi(m.h, b.h, score.ctypes.data, plen.ctypes.data))
+    off = np.concatenate([[0], np.cumsum(plen[: b.n_pairs])]).astype(np.int64)
+    trans = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+    if off[-1]:
+        _check(lib().mb_group_viterbi_paths(b.h, trans.ctypes.data, off.ctypes.data))
+    return score[: b.n_pairs], [trans[off[k]:off[k + 1]] for k in range(b.n_pairs)]
+
+
+def group_counts(m: GroupMachine, b: GroupBatch):
+    c = np.zeros(max(m.n_trans, 1), dtype=np.float64)
+    ll = np.empty(max(b.n_pairs, 1), dtype=np.float64)
+    _check(lib().mb_group_counts(m.h, b.h, c.ctypes.data, ll.ctypes.data))
+    return c[: m.n_trans], ll[: b.n_pairs]

@@ -27,6 +27,10 @@ static const char* const kOptionNames[] = {
   "lane_r", "lane_warps", "no_lane", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
 };
 
+Options thread_options() { return g_options; }
+void set_thread_options (const Options& o) { g_options = o; }
+int thread_engine() { return g_forceEngine; }
+
 bool option_known (const char* name) {
   for (const char* n: kOptionNames) if (!strcmp (n, name)) return true;
   return false;

@@ -70,6 +70,10 @@ struct Options {
   void unset (const char* name) { for (size_t n = 0; n < kv.size(); ++n) if (kv[n].first == name) { kv.erase (kv.begin() + n); return; } }
 };
 bool option_known (const char* name);
+// the calling thread's defaults (mb_set_option, mb_set_engine), for handing them to another thread
+Options thread_options();
+void set_thread_options (const Options& o);
+int thread_engine();
 
 void set_error (const std::string& msg);
 bool cuda_ok (cudaError_t e, const char* what);

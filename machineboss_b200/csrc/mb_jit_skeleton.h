@@ -653,7 +653,9 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       };
       {
         int t = 0;
-        const int rampUp = min (31, nSteps);
+        // MODE 3 pads its matrix on the left, so column 0 -- the origin cell, at row 0 -- can sit on any lane, lane 31
+        // included, whose row 0 is step 31: the steady loop (which folds the origin test away) starts a step later there
+        const int rampUp = min (MODE == 3 ? 32 : 31, nSteps);
         for (; t < rampUp; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
         while (t < Lo) {
           if ((t & (MB_RESCALE - 1)) == 0) blockStart (t);

@@ -34,6 +34,8 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/machineboss_b200.h"
 #include "mbjson.h"
 
@@ -52,6 +54,24 @@ typedef string OutputSymbol;
 typedef int InputToken;
 typedef int OutputToken;
 typedef double LogWeight;
+
+// whole file as text; a name ending in .gz is inflated on the way (the larger preset machines ship compressed)
+inline string readTextFile (const string& filename) {
+  if (filename.size() > 3 && filename.compare (filename.size() - 3, 3, ".gz") == 0) {
+    gzFile f = gzopen (filename.c_str(), "rb");
+    if (!f) throw std::runtime_error ("File not found: " + filename);
+    string text;
+    char buf[1 << 16];
+    for (int n; (n = gzread (f, buf, sizeof buf)) > 0;) text.append (buf, (size_t) n);
+    gzclose (f);
+    return text;
+  }
+  std::ifstream in (filename);
+  if (!in) throw std::runtime_error ("File not found: " + filename);
+  std::stringstream ss;
+  ss << in.rdbuf();
+  return ss.str();
+}
 
 inline void mbCheck (int rc) { if (rc != 0) throw runtime_error (mb_last_error()); }   // Assert -> Abort -> throw (util.cpp:39-48)
 
@@ -207,12 +227,8 @@ struct SeqPairList {
     out << "]";
   }
   static SeqPairList fromFile (const string& filename) {
-    std::ifstream in (filename);
-    if (!in) throw runtime_error ("File not found: " + filename);
-    std::stringstream ss;
-    ss << in.rdbuf();
     SeqPairList l;
-    l.readJson (Json::parse (ss.str()));
+    l.readJson (Json::parse (readTextFile (filename)));
     return l;
   }
 };
@@ -365,13 +381,7 @@ struct EvaluatedMachine {
     m.index();
     return m;
   }
-  static EvaluatedMachine fromFile (const string& filename) {
-    std::ifstream f (filename);
-    if (!f) throw runtime_error ("File not found: " + filename);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    return fromJson (Json::parse (ss.str()));
-  }
+  static EvaluatedMachine fromFile (const string& filename) { return fromJson (Json::parse (readTextFile (filename))); }
 
   StateIndex nStates() const { return state.size(); }
   StateIndex startState() const { if (!nStates()) throw runtime_error ("EvaluatedMachine has no states"); return 0; }
@@ -404,6 +414,7 @@ struct EvaluatedMachine {
     logWeight = lw;
     for (auto& st: state) for (size_t t = 0; t < st.nTransitions; ++t) st.logTransWeight[t] = lw[st.transOffset + t];
     if (dev) mbCheck (mb_machine_update_weights (dev->h, logWeight.data()));
+    if (gdev) mbCheck (mb_group_machine_update_weights (gdev->h, logWeight.data()));
   }
 
   mb_machine* handle() const {   // device copy, created on first use
@@ -416,9 +427,21 @@ struct EvaluatedMachine {
     return dev->h;
   }
 
+  mb_gmachine* groupHandle (mb_group* g) const {   // one replica per device of the group, created on first use
+    if (!gdev) {
+      std::shared_ptr<GDev> d (new GDev);
+      mbCheck (mb_group_machine_create (g, &d->h, (int32_t) nStates(), (int32_t) inputTokenizer.tok2sym.size() - 1, (int32_t) outputTokenizer.tok2sym.size() - 1,
+                                        (int64_t) src.size(), src.data(), dst.data(), in.data(), out.data(), logWeight.data()));
+      gdev = d;
+    }
+    return gdev->h;
+  }
+
 private:
   struct Dev { mb_machine* h = nullptr; ~Dev() { if (h) mb_machine_destroy (h); } };
+  struct GDev { mb_gmachine* h = nullptr; ~GDev() { if (h) mb_group_machine_destroy (h); } };
   mutable std::shared_ptr<Dev> dev;
+  mutable std::shared_ptr<GDev> gdev;
   void index() {
     nTransitions = src.size();
     for (size_t t = 0; t < src.size(); ++t) {
@@ -509,6 +532,75 @@ inline vector<const SeqPair*> pairPointers (const SeqPairList& l) {
   for (const auto& sp: l.seqPairs) v.push_back (&sp);
   return v;
 }
+
+// ---- a SeqPairList over every GPU of the box ----
+// The reference walks a list in one loop (counts.cpp:37-43, fitter.cpp:23-47, boss.cpp:796,826).  Here the list goes
+// to the devices in one piece: with one visible GPU as a DeviceBatch, with several through the C ABI's group entry
+// points (pairs dealt longest-first to the least loaded device, a host thread per device, the E-step's counts summed
+// with an NCCL all-reduce).  hostGpuLimit() caps the devices used (0 = all visible; the CLI's --gpus).
+inline int& hostGpuLimit() { static int limit = 0; return limit; }
+
+inline mb_group* hostGroup() {      // null with a single device
+  struct Holder { mb_group* g = nullptr; bool tried = false; ~Holder() { if (g) mb_group_destroy (g); } };
+  static Holder h;
+  if (!h.tried) {
+    h.tried = true;
+    int n = 0;
+    mbCheck (mb_device_count (&n));
+    if (hostGpuLimit() > 0 && hostGpuLimit() < n) n = hostGpuLimit();
+    if (n > 1) {
+      vector<int32_t> devs;
+      for (int d = 0; d < n; ++d) devs.push_back (d);
+      mbCheck (mb_group_create (&h.g, devs.data(), (int32_t) devs.size()));
+    }
+  }
+  return h.g;
+}
+
+class ListBatch {
+public:
+  ListBatch (const EvaluatedMachine& m, const vector<const SeqPair*>& pairs) : machine (m), n ((int64_t) pairs.size()) {
+    mb_group* g = pairs.size() > 1 ? hostGroup() : nullptr;
+    if (!g) { single.reset (new DeviceBatch (m, pairs)); return; }
+    vector<uint8_t> x, y;
+    vector<int64_t> xo (1, 0), yo (1, 0), rowOff (1, 0), st, en;
+    bool anyEnvelope = false;
+    for (const SeqPair* sp: pairs) {
+      for (auto t: m.inputTokenizer.tokenize (sp->input.seq)) x.push_back ((uint8_t) t);
+      for (auto t: m.outputTokenizer.tokenize (sp->output.seq)) y.push_back ((uint8_t) t);
+      xo.push_back ((int64_t) x.size());
+      yo.push_back ((int64_t) y.size());
+      if (sp->alignment.size()) {      // a pair that carries an alignment gets its path envelope, as in DeviceBatch
+        const Envelope env (*sp);
+        st.insert (st.end(), env.inStart.begin(), env.inStart.end());
+        en.insert (en.end(), env.inEnd.begin(), env.inEnd.end());
+        anyEnvelope = true;
+      }
+      rowOff.push_back ((int64_t) st.size());
+    }
+    x.push_back (0); y.push_back (0);
+    mbCheck (mb_group_batch_create (g, &gb, n, x.data(), xo.data(), y.data(), yo.data()));
+    if (anyEnvelope) mbCheck (mb_group_batch_set_envelopes (gb, rowOff.data(), st.data(), en.data()));
+    gm = m.groupHandle (g);
+  }
+  ~ListBatch() { if (gb) mb_group_batch_destroy (gb); }
+  ListBatch (const ListBatch&) = delete;
+  ListBatch& operator= (const ListBatch&) = delete;
+  int64_t size() const { return n; }
+  bool sharded() const { return gb != nullptr; }
+  void forward (double* ll) { if (gb) mbCheck (mb_group_forward (gm, gb, ll)); else mbCheck (mb_forward (machine.handle(), single->handle(), ll)); }
+  void viterbi (double* score, int64_t* len) { if (gb) mbCheck (mb_group_viterbi (gm, gb, score, len)); else mbCheck (mb_viterbi (machine.handle(), single->handle(), score, len)); }
+  void paths (void* ids, int bytesPerId, const int64_t* off) {
+    if (gb) mbCheck (mb_group_viterbi_paths_narrow (gb, ids, bytesPerId, off)); else mbCheck (mb_viterbi_paths_narrow (single->handle(), ids, bytesPerId, off));
+  }
+  void counts (double* c, double* ll) { if (gb) mbCheck (mb_group_counts (gm, gb, c, ll)); else mbCheck (mb_counts (machine.handle(), single->handle(), c, ll)); }
+private:
+  const EvaluatedMachine& machine;
+  int64_t n;
+  std::unique_ptr<DeviceBatch> single;
+  mb_gbatch* gb = nullptr;
+  mb_gmachine* gm = nullptr;
+};
 
 // ---- stored matrices: DPMatrix::cell (src/dpmatrix.h:128-146) and the stochastic traceback built on it ----
 // The device keeps no matrix for a score; the first cell() fetches the pair's whole matrix (mb_matrix).
@@ -661,9 +753,9 @@ struct MachineCounts {
   double add (const EvaluatedMachine& m, const SeqPair& sp) { return addBatch (m, vector<const SeqPair*> (1, &sp)); }
   double add (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) { return add (m, sp); }
   double addBatch (const EvaluatedMachine& m, const vector<const SeqPair*>& pairs) {
-    DeviceBatch b (m, pairs);
+    ListBatch b (m, pairs);
     vector<double> c (m.nTransitions ? m.nTransitions : 1, 0.), ll (pairs.size() ? pairs.size() : 1, 0.);
-    mbCheck (mb_counts (m.handle(), b.handle(), c.data(), ll.data()));
+    b.counts (c.data(), ll.data());
     double total = 0;
     for (size_t k = 0; k < pairs.size(); ++k) total += ll[k];
     for (StateIndex s = 0; s < m.nStates(); ++s)
@@ -695,31 +787,31 @@ inline void BackwardMatrix::getCounts (const ForwardMatrix&, MachineCounts& coun
 
 // ---- batched entry points (no reference equivalent: the reference loops over the list) ----
 inline vector<double> forwardLogLikes (const EvaluatedMachine& m, const SeqPairList& l) {
-  DeviceBatch b (m, pairPointers (l));
+  ListBatch b (m, pairPointers (l));
   vector<double> ll (l.seqPairs.size());
-  if (ll.size()) mbCheck (mb_forward (m.handle(), b.handle(), ll.data()));
+  if (ll.size()) b.forward (ll.data());
   return ll;
 }
 
 inline vector<double> viterbiLogLikes (const EvaluatedMachine& m, const SeqPairList& l, vector<MachinePath>* paths = nullptr) {
-  DeviceBatch b (m, pairPointers (l));
+  ListBatch b (m, pairPointers (l));
   const size_t n = l.seqPairs.size();
   vector<double> sc (n);
   if (!n) return sc;
-  if (!paths) { mbCheck (mb_viterbi (m.handle(), b.handle(), sc.data(), nullptr)); return sc; }
+  if (!paths) { b.viterbi (sc.data(), nullptr); return sc; }
   vector<int64_t> len (n), off (n + 1, 0);
-  mbCheck (mb_viterbi (m.handle(), b.handle(), sc.data(), len.data()));
+  b.viterbi (sc.data(), len.data());
   for (size_t k = 0; k < n; ++k) off[k + 1] = off[k] + len[k];
   paths->assign (n, MachinePath());
   if (m.nTransitions <= 256) {      // byte ids: a quarter of the device-to-host copy
     vector<uint8_t> ids ((size_t) off[n] ? (size_t) off[n] : 1);
-    if (off[n]) mbCheck (mb_viterbi_paths_narrow (b.handle(), ids.data(), 1, off.data()));
+    if (off[n]) b.paths (ids.data(), 1, off.data());
     for (size_t k = 0; k < n; ++k)
       for (int64_t q = off[k]; q < off[k + 1]; ++q) (*paths)[k].trans.push_back (m.transition ((int32_t) ids[q]));
     return sc;
   }
   vector<int32_t> ids ((size_t) off[n] ? (size_t) off[n] : 1);
-  if (off[n]) mbCheck (mb_viterbi_paths (b.handle(), ids.data(), off.data()));
+  if (off[n]) b.paths (ids.data(), 4, off.data());
   for (size_t k = 0; k < n; ++k)
     for (int64_t q = off[k]; q < off[k + 1]; ++q) (*paths)[k].trans.push_back (m.transition (ids[q]));
   return sc;

@@ -25,6 +25,8 @@
 // The machine is given already evaluated (flat JSON: states, alphabets, numeric log-weights),
 // because building it from a symbolic Machine + Params is the reference's job.
 // Numbers are printed with the stream's default 6 significant digits, like boss (jsonio.h:19-21).
+#include <unistd.h>
+
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -58,19 +60,35 @@ static NamedSeq<string> fromChars (const string& s) {
   return n;
 }
 
+// The machines of the BASELINE configs ship next to the executable, evaluated by the reference with `boss -U`
+// default parameters (machineboss_b200/presets/NAME.eval.json[.gz], written by tools/make_presets.py): the symbolic
+// preset library itself (src/preset.cpp) is outside the accelerated path.
+static string presetFile (const string& name) {
+  char exe[4096];
+  const ssize_t n = readlink ("/proc/self/exe", exe, sizeof exe - 1);
+  string dir = n > 0 ? string (exe, (size_t) n) : string (".");
+  dir = dir.substr (0, dir.find_last_of ('/'));
+  for (const char* ext: { ".eval.json", ".eval.json.gz" }) {
+    const string path = dir + "/presets/" + name + ext;
+    if (std::ifstream (path)) return path;
+  }
+  throw runtime_error ("no evaluated preset '" + name + "' under " + dir + "/presets (shipped: dnapsw, protpsw, prot2dna_dnapsw, PF00516, PF00516_protpsw)");
+}
+
 int main (int argc, char** argv) {
   try {
     string machineFile, symbolicFile, consFile, mstepFile;
     vector<string> dataFiles, paramFiles;
     bool useDefaults = false, doT = false;
     vector<NamedSeq<string> > inSeqs, outSeqs;
-    bool doL = false, doV = false, doA = false, doC = false, doSample = false;
+    bool doL = false, doV = false, doA = false, doC = false, doSample = false, useApi = false;
     string envMode;
     long long sampleSeed = 1;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
       auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
       if (f == "--evaluated-machine" || f == "-m") machineFile = next();
+      else if (f == "--preset") machineFile = presetFile (next());      // boss --preset NAME (boss.cpp:247-249), already evaluated with -U defaults
       else if (f == "--machine") symbolicFile = next();
       else if (f == "-P" || f == "--params") paramFiles.push_back (next());
       else if (f == "-N" || f == "--constraints") consFile = next();
@@ -89,6 +107,8 @@ int main (int argc, char** argv) {
       else if (f == "--envelope") envMode = next();      // full | path | <width>: print each pair's Envelope (t/src/testenv.cpp; no device needed)
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
+      else if (f == "--api") useApi = true;      // route the verbs through the api.h free functions (Machine, Params, SeqPair), pair by pair
+      else if (f == "--gpus") hostGpuLimit() = atoi (next().c_str());      // lists of pairs use this many GPUs (default: every visible one)
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
       else throw runtime_error ("unknown option " + f);
     }
@@ -186,6 +206,27 @@ int main (int argc, char** argv) {
       cout << "]\n";
     };
 
+    if (useApi) {      // src/api.h:21-30, called the way a program written against the reference calls them
+      if (!symbolic) throw runtime_error ("--api needs a symbolic --machine");
+      const Params all = machine.funcs.combine (params);
+      if (doL) { vector<double> v; for (const auto& sp: ok.seqPairs) v.push_back (forwardLogLike (machine, all, sp)); printScores (v); }
+      if (doV) { vector<double> v; for (const auto& sp: ok.seqPairs) v.push_back (viterbiLogLike (machine, all, sp)); printScores (v); }
+      if (doC) {
+        const MachineCounts counts = forwardBackwardCounts (machine, all, data);
+        cout << "{";
+        size_t np = 0;
+        for (const auto& nc: paramCounts (counts, machine, params)) cout << (np++ ? "," : "") << "\"" << Json::escape (nc.first) << "\":" << nc.second;
+        cout << "}" << endl;
+      }
+      if (doA) {
+        SeqPairList results;
+        for (const auto& sp: ok.seqPairs)
+          if (viterbiLogLike (machine, all, sp) > ninf) results.seqPairs.push_back (SeqPair::seqPairFromPath (viterbiAlign (machine, all, sp), eval, sp.input.name.c_str(), sp.output.name.c_str()));
+        results.writeJson (cout);
+        cout << endl;
+      }
+      return EXIT_SUCCESS;
+    }
     if (doL) printScores (forwardLogLikes (eval, ok));
     if (doC) {
       // ... but -C does not test canTokenize (boss.cpp:811-816): an unknown symbol throws

@@ -537,12 +537,12 @@ struct MachineFitter {
     double prev = 0;
     // one device copy of the machine structure and of the batch for the whole fit: only the weights change
     EvaluatedMachine eval = evaluate (machine, machine.funcs.combine (constants).combine (params));
-    DeviceBatch batch (eval, pairPointers (trainingSet));
+    ListBatch batch (eval, pairPointers (trainingSet));      // every visible GPU: pairs dealt to the devices, counts all-reduced
     vector<double> c (eval.nTransitions ? eval.nTransitions : 1), ll (trainingSet.seqPairs.size() ? trainingSet.seqPairs.size() : 1);
     for (int iter = 0; true; ++iter) {
       const Params allParams = machine.funcs.combine (constants).combine (params);
       if (iter > 0) eval.setLogWeights (logWeights (machine, allParams));
-      mbCheck (mb_counts (eval.handle(), batch.handle(), c.data(), ll.data()));
+      batch.counts (c.data(), ll.data());
       MachineCounts counts (eval);
       for (StateIndex s = 0; s < eval.nStates(); ++s) for (size_t t = 0; t < counts.count[s].size(); ++t) counts.count[s][t] = c[eval.state[s].transOffset + t];
       counts.loglike = 0;
@@ -562,6 +562,37 @@ struct MachineFitter {
     return params;
   }
 };
+
+// ---- the free functions of src/api.h:14-34, with the reference's signatures: (Machine, Params, data) ----
+// Like api.cpp:31-75 each call evaluates the machine anew; the forms taking an EvaluatedMachine (boss_b200.h) skip
+// that.  A call on ONE pair pays a device round trip for a single matrix: lists belong in forwardBackwardCounts
+// (Machine, Params, SeqPairList), forwardLogLikes / viterbiLogLikes, or MachineFitter.
+inline Machine loadMachine (const string& filename) { return Machine::fromFile (filename); }                              // api.h:15
+inline Machine loadMachineJson (const string& jsonString) { Machine m; m.readJson (Json::parse (jsonString)); return m; }  // api.h:16
+inline double forwardLogLike (const Machine& machine, const Params& params, const SeqPair& seqPair) {                      // api.h:21
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return ForwardMatrix (eval, seqPair).logLike();
+}
+inline double forwardLogLike (const Machine& machine, const Params& params, const SeqPair& seqPair, const Envelope& env) { // api.h:22
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return ForwardMatrix (eval, seqPair, env).logLike();
+}
+inline double viterbiLogLike (const Machine& machine, const Params& params, const SeqPair& seqPair) {                      // api.h:25
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return ViterbiMatrix (eval, seqPair).logLike();
+}
+inline MachinePath viterbiAlign (const Machine& machine, const Params& params, const SeqPair& seqPair) {                   // api.h:26
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return ViterbiMatrix (eval, seqPair).path (machine);
+}
+inline MachineCounts forwardBackwardCounts (const Machine& machine, const Params& params, const SeqPair& seqPair) {        // api.h:29
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return MachineCounts (eval, seqPair);
+}
+inline MachineCounts forwardBackwardCounts (const Machine& machine, const Params& params, const SeqPairList& seqPairList) { // api.h:30
+  const EvaluatedMachine eval = evaluate (machine, params);
+  return MachineCounts (eval, seqPairList);
+}
 
 // api.h:33-34
 inline Params baumWelchFit (const Machine& machine, const Constraints& constraints, const SeqPairList& data,

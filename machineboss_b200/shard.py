@@ -5,26 +5,25 @@ need no communication.  The E-step of Baum-Welch (MachineCounts over the list, s
 sums per-pair counts, so after each rank has processed its shard the count vector and the total
 log-likelihood are combined with ONE all-reduce of nTransitions + 1 doubles -- NCCL over NVLink on
 the GPUs, gloo in the CPU tests.
+
+Two launch models share the deal of pairs to devices (mb_shard_pairs in the library):
+  * one process, several GPUs: the C ABI's mb_group_* entry points (a host thread per device, ncclAllReduce of
+    the counts) -- what the host mirror's MachineCounts / MachineFitter and the boss_b200 CLI use;
+  * one process per GPU under torchrun (bench.py --gpus N): this module, the exchange step through torch.distributed.
 """
 from __future__ import annotations
 
 import numpy as np
 
 
-def lpt_assign(costs, world: int):
-    """Longest-processing-time-first assignment of pairs to ranks; returns a list of index arrays.
-
-    costs[k] ~ (Li+1)*(Lo+1).  Ties and order are deterministic so every rank computes the same plan.
-    """
-    costs = np.asarray(costs, dtype=np.float64)
-    order = np.argsort(-costs, kind="stable")
-    load = np.zeros(world)
-    bins = [[] for _ in range(world)]
-    for k in order:
-        r = int(np.argmin(load))
-        bins[r].append(int(k))
-        load[r] += costs[k]
-    return [np.array(sorted(b), dtype=np.int64) for b in bins]
+def lpt_assign(x_off, y_off, world: int):
+    """The library's deal of pairs to `world` shards (mb_shard_pairs: longest-processing-time first by cell count
+    (Li+1)(Lo+1), each pair to the least loaded shard, deterministic so every rank computes the same plan);
+    returns the list of index arrays, one per rank.  Ranks of a torchrun job use it to pick their pairs; inside one
+    process the same deal is what mb_group_batch_create applies to the devices of a group."""
+    from . import capi
+    shard_of = capi.shard_pairs(x_off, y_off, world)
+    return [np.flatnonzero(shard_of == r).astype(np.int64) for r in range(world)]
 
 
 def allreduce_counts(counts: np.ndarray, loglike: float, device=None):

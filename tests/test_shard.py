@@ -15,21 +15,27 @@ def test_lpt_assign_balances_and_partitions():
     rng = np.random.default_rng(1)
     li, lo = rng.integers(50, 500, 1000), rng.integers(50, 500, 1000)
     costs = (li + 1.0) * (lo + 1.0)
+    x_off, y_off = np.concatenate([[0], np.cumsum(li)]), np.concatenate([[0], np.cumsum(lo)])
     for world in (1, 2, 4, 8):
-        bins = shard.lpt_assign(costs, world)
+        bins = shard.lpt_assign(x_off, y_off, world)
         allk = np.sort(np.concatenate(bins))
         assert np.array_equal(allk, np.arange(1000))
         loads = np.array([costs[b].sum() for b in bins])
         assert loads.max() / loads.mean() < 1.01
-    assert all(np.array_equal(a, b) for a, b in zip(shard.lpt_assign(costs, 4), shard.lpt_assign(costs, 4)))
+    assert all(np.array_equal(a, b) for a, b in zip(shard.lpt_assign(x_off, y_off, 4), shard.lpt_assign(x_off, y_off, 4)))
+    # the longest pair opens shard 0, the next ones shards 1, 2, 3: longest-processing-time first
+    order = np.argsort(-costs, kind="stable")
+    first = [int(np.flatnonzero([k in b for b in shard.lpt_assign(x_off, y_off, 4)])[0]) for k in order[:4]]
+    assert first == [0, 1, 2, 3]
 
 
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    costs = np.arange(1, 11, dtype=np.float64)
-    mine = shard.lpt_assign(costs, world)[rank]
+    lens = np.arange(0, 10, dtype=np.int64)      # pair k costs (k + 1) * 1 cells
+    x_off, y_off = np.concatenate([[0], np.cumsum(lens)]), np.zeros(11, dtype=np.int64)
+    mine = shard.lpt_assign(x_off, y_off, world)[rank]
     # stand-in for per-shard E-step results: counts proportional to the pair index, ll = -index
     counts = np.zeros(5)
     for k in mine:
