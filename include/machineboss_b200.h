@@ -174,6 +174,15 @@ int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int6
                           const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok,
                           char* log, int64_t logCap);
 
+/* The tables the generated score kernels of a small machine read, as the host prepares them for these weights
+ * (no device needed; the CPU tests drive the generated cell functions with them).  which: 0 forward log weights
+ * in row layout, 1 / 2 forward / backward normalised linear weights in row layout, 3 the silent log-weights,
+ * 4 the normalised silent weights followed by { originF, originB, resLogF, resLogB }, 5 { normalisation usable,
+ * no positive log-weight }.  *n receives the number of doubles; at most cap are copied to out. */
+int mb_jit_host_tables (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                        const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                        int32_t which, double* out, int64_t cap, int64_t* n);
+
 /* ---- measurement hooks (not part of the reference surface) ----
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
  * (CUDA events on the launching stream), and how many kernels that was. */

@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check",
+           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables",
            "mb_shard_pairs", "mb_group_create", "mb_group_info", "mb_group_destroy", "mb_group_machine_create", "mb_group_machine_update_weights",
            "mb_group_machine_set_option", "mb_group_machine_info", "mb_group_machine_destroy", "mb_group_batch_create", "mb_group_batch_set_envelopes",
            "mb_group_batch_shard", "mb_group_batch_destroy", "mb_group_forward", "mb_group_backward", "mb_group_viterbi", "mb_group_viterbi_paths",
@@ -64,6 +64,7 @@ def lib():
         L.mb_counts.argtypes = [P, P, P, P]
         L.mb_matrix.argtypes = [P, P, I64, I32, P]
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
+        L.mb_jit_host_tables.argtypes = [I32, I32, I32, I64, P, P, P, P, P, I32, P, I64, ctypes.POINTER(I64)]
         L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         L.mb_shard_pairs.argtypes = [I64, P, P, I32, P]
@@ -128,6 +129,17 @@ def jit_compile_check(n_states, n_in, n_out, src, dst, tin, tout) -> str:
     _check(lib().mb_jit_compile_check(int(n_states), int(n_in), int(n_out), int(arrs[0].shape[0]),
                                       *[_ptr(a) for a in arrs], buf, len(buf)))
     return buf.value.decode()
+
+
+def jit_host_tables(n_states, n_in, n_out, src, dst, tin, tout, log_weight, which: int) -> np.ndarray:
+    """The tables the generated score kernels read for these weights (no device needed); see mb_jit_host_tables."""
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
+    lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+    n = ctypes.c_int64(0)
+    _check(lib().mb_jit_host_tables(int(n_states), int(n_in), int(n_out), int(lw.shape[0]), *[_ptr(a) for a in arrs], _ptr(lw), int(which), None, 0, ctypes.byref(n)))
+    out = np.zeros(max(n.value, 1), dtype=np.float64)
+    _check(lib().mb_jit_host_tables(int(n_states), int(n_in), int(n_out), int(lw.shape[0]), *[_ptr(a) for a in arrs], _ptr(lw), int(which), out.ctypes.data, n.value, ctypes.byref(n)))
+    return out[: n.value]
 
 
 def _ptr(a):

@@ -23,6 +23,9 @@ static const char* const kOptionNames[] = {
   "jit_narrow", "jit_no_linear", "jit_c", "jit_cv", "jit_minblocks", "jit_minblocks_v", "jit_minblocks_lin", "jit_minblocks_cnt", "jit_threads",
   "jit_tb_budget_mb", "jit_f_budget_mb",                      // cap on one chunk of back-pointer / stored-Forward scratch (tests force several chunks)
   "jit_chunks",                                               // pairs of a Viterbi call are traced back and copied out in this many pipeline stages
+  "jit_no_norm",                                              // 1: never use the normalised linear kernels (score module)
+  "jit_vit_intcmp",                                           // 0: Viterbi always compares in FP64
+  "jit_unroll",                                               // unroll factor of the steady-state step loop (1 - 4)
   "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
   "lane_r", "lane_warps", "no_lane", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
 };
@@ -665,6 +668,22 @@ int mb_jit_compile_check (int32_t nStates, int32_t nInTok, int32_t nOutTok, int6
   const int rc = m.S > 16 ? big_compile_check (&m, &l) : jit_compile_check (&m, &l);      // mid-size machines: the big engine's generated sweep
   if (log && logCap > 0) { strncpy (log, l.c_str(), (size_t) logCap - 1); log[logCap - 1] = 0; }
   return rc;
+}
+
+int mb_jit_host_tables (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                        const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                        int32_t which, double* out, int64_t cap, int64_t* n) {
+  mb_machine m;
+  m.opt = g_options;
+  m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
+  m.src.assign (src, src + nTrans); m.dst.assign (dst, dst + nTrans);
+  m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);
+  m.lw.assign (logWeight, logWeight + nTrans);
+  std::vector<double> v;
+  if (jit_host_tables (&m, which, v)) return 1;
+  if (n) *n = (int64_t) v.size();
+  if (out) for (int64_t q = 0; q < (int64_t) v.size() && q < cap; ++q) out[q] = v[q];
+  return 0;
 }
 
 int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches) {

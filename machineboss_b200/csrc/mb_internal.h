@@ -158,6 +158,7 @@ int generic_matrix (mb_machine* m, mb_batch* b, int64_t pair, int kind, double* 
 bool jit_supported (const mb_machine* m, std::string* why);
 int jit_prepare (mb_machine* m);
 int jit_compile_check (const mb_machine* m, std::string* log);
+int jit_host_tables (const mb_machine* m, int which, std::vector<double>& out);
 void jit_destroy (mb_machine* m);
 int jit_update_weights (mb_machine* m);
 int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward);

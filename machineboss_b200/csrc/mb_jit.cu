@@ -133,6 +133,21 @@ struct Program {
   std::vector<int32_t> emitId;                // transition id per emission-table entry
   std::vector<int32_t> silId;                 // transition id per silent slot
   int nEmit = 0, nSil = 0;
+  // The same emission weights in ROW layout (score module): one row per input token holding, for every match
+  // group, its nOut weights and, for every delete group, its weight; then one row per output token holding every
+  // insert group's weight.  A cell's column keeps the shared-memory address of its input token's row in a
+  // register, so a match weight is at (row + 8 * outTok) + constant, a delete weight at row + constant and an
+  // insert weight at (the step's output-token row) + constant: one add per cell instead of an index computation
+  // per weight.  rowOff[slot] = offset of the group inside its row; rowId[entry] = transition id (-1: none).
+  int WA = 0, WB = 0;
+  std::vector<int> rowOff;
+  std::vector<int32_t> rowId;
+  std::vector<int> rowSlot;                   // the group every row-layout entry belongs to
+  // Linear-domain normalisation (score module).  State values are only defined up to a constant factor per
+  // state: with value'(d) = value(d) / sigma_d every group's weight becomes w * sigma_src / sigma_d, and
+  // choosing sigma_d = w_u * sigma_src(u) for ONE silent group u of d makes that group's weight exactly 1 --
+  // its multiply disappears from the cell (dnapsw: 11 multiply-adds per cell become 7).  unitSlot[d] = u, or -1.
+  std::vector<int> unitSlot;
 };
 
 static int table_size (int type, int nIn, int nOut) {
@@ -176,6 +191,28 @@ static void build_program (const mb_machine* m, bool forward, Program& p) {
     p.slots.push_back (s);
   }
   for (int s = 0; s < m->S; ++s) p.stateSlot0[s + 1] += p.stateSlot0[s];
+  // row layout
+  p.rowOff.assign (p.slots.size(), -1);
+  for (size_t k = 0; k < p.slots.size(); ++k) {
+    const Slot& sl = p.slots[k];
+    if (sl.type == T_MATCH) { p.rowOff[k] = p.WA; p.WA += m->nOut; }
+    else if (sl.type == T_DELETE) { p.rowOff[k] = p.WA; p.WA += 1; }
+    else if (sl.type == T_INSERT) { p.rowOff[k] = p.WB; p.WB += 1; }
+  }
+  p.rowId.assign ((size_t) std::max (m->nIn * p.WA + m->nOut * p.WB, 1), -1);
+  p.rowSlot.assign (p.rowId.size(), -1);
+  for (size_t k = 0; k < p.slots.size(); ++k) {
+    const Slot& sl = p.slots[k];
+    auto put = [&] (int entry, int label) { p.rowId[entry] = p.idTab[sl.idOff + label]; p.rowSlot[entry] = (int) k; };
+    if (sl.type == T_MATCH) { for (int a = 0; a < m->nIn; ++a) for (int b = 0; b < m->nOut; ++b) put (a * p.WA + p.rowOff[k] + b, a * m->nOut + b); }
+    else if (sl.type == T_DELETE) { for (int a = 0; a < m->nIn; ++a) put (a * p.WA + p.rowOff[k], a); }
+    else if (sl.type == T_INSERT) { for (int b = 0; b < m->nOut; ++b) put (m->nIn * p.WA + b * p.WB + p.rowOff[k], b); }
+  }
+  // the unit group of a state: its first silent group
+  p.unitSlot.assign ((size_t) m->S, -1);
+  for (int d = 0; d < m->S; ++d)
+    for (int k = p.stateSlot0[d]; k < p.stateSlot0[d + 1]; ++k)
+      if (p.slots[k].type == T_SILENT) { p.unitSlot[d] = k; break; }
 }
 
 struct JitEngine {
@@ -192,6 +229,16 @@ struct JitEngine {
   CUfunction kViterbiN = nullptr, kForwardLinN = nullptr, kBackwardLinN = nullptr, kViterbiScoreN = nullptr;
   int blocksPerSMN[4] = { 1, 1, 1, 1 };
   CUfunction kViterbiScore = nullptr;      // Viterbi without back-pointers (mb_viterbi with pathLen == NULL, boss -V)
+  CUfunction kViterbiI = nullptr, kViterbiScoreI = nullptr;      // score module: the same two with integer compares (no weight above 1)
+  CUfunction kViterbiI2 = nullptr, kViterbiScoreI2 = nullptr;    // ... and with every other compare an integer one (both pipes share the work)
+  int vitIcmp = 4;                        // which of the three the machine's calls use when eligible: 0, 2 or 4
+  // score module: row-layout tables (Program::WA) -- log weights for Viterbi, normalised linear weights for the sums
+  double* dRowVit = nullptr;
+  double* dRowFLinN = nullptr;
+  double* dRowBLinN = nullptr;
+  std::vector<char> silParamLinN;         // MBSilN { f[], b[], originF, originB, resLogF, resLogB }
+  bool normOK = false;                    // every unit group's weight is usable: the normalised linear kernels may run
+  bool nonPositive = false;               // no finite log-weight above 0: Viterbi may compare bit patterns
   std::string sourceV;
   // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
   // start state); the others follow from them inside the cell through the silent groups
@@ -202,8 +249,8 @@ struct JitEngine {
   std::string source;
   CUmodule mod = nullptr;
   CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
-  int blocksPerSM[10] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };      // index 9: mb_k_viterbi_score
-  size_t smemBytes[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  int blocksPerSM[14] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };      // index 9: mb_k_viterbi_score, 10 / 11: mb_k_viterbi_i / _score_i, 12 / 13: _i2 / _score_i2
+  size_t smemBytes[14] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
   std::vector<int> ctxBase;              // per backward slot, -1 for silent
   int32_t* dIdTabB = nullptr;
@@ -269,6 +316,84 @@ static void gen_cell (std::ostringstream& o, const mb_machine* m, const Program&
   }
   for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
   if (viterbi) o << "  return word;\n";
+  o << "}\n\n";
+}
+
+// ---- score module: cell functions over the row-layout tables (see Program::WA) ----
+// ea = shared-memory byte address of the input token's row, em = ea + 8 * output token, ebr = address of the
+// output token's row.  MB_LDS (address, byte offset) reads one weight.
+static std::string row_weight (const Slot& s, int rowOff) {
+  std::ostringstream e;
+  e << "MB_LDS (" << (s.type == T_MATCH ? "em" : s.type == T_DELETE ? "ea" : "ebr") << ", " << rowOff * 8 << ")";
+  return e.str();
+}
+
+static std::string source_expr (const Slot& s) {
+  std::ostringstream e;
+  const char* arr = s.type == T_MATCH ? "D" : s.type == T_DELETE ? "L" : s.type == T_INSERT ? "U" : nullptr;
+  if (arr) e << arr << "[" << s.other << "]"; else e << "n" << s.other;
+  return e.str();
+}
+
+// Viterbi: FP64 add + compare in the reference's candidate order.  ICMP of every four compares (0, 2 or 4) are
+// done on the bit patterns as unsigned integers instead, i.e. on the integer pipe -- valid when no value can be
+// positive: a < b <=> bits (a) > bits (b) for a, b in [-inf, +0] -- which takes them off the FP64 pipe, where a
+// compare costs two adds' worth of cycles
+static void gen_cell_row_vit (std::ostringstream& o, const mb_machine* m, const Program& p, const JitEngine& J) {
+  int compareNo = 0;
+  o << "template<int ICMP> __device__ __forceinline__ mb_tbword mb_cell_vitr (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], "
+       "const unsigned ea, const unsigned em, const unsigned ebr, const bool origin, const bool sink, const MBSil& P) {\n";
+  o << "  mb_tbword word = 0;\n";
+  std::vector<char> isSource ((size_t) m->S, 0);
+  for (auto& sl: p.slots) isSource[sl.other] = 1;
+  for (int d = 0; d < m->S; ++d) {
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1];
+    const bool sinkOnly = !isSource[d] && d != 0 && s0 != s1;
+    if (s0 == s1 || sinkOnly) o << "  double n" << d << " = mb_neg_inf();\n";
+    if (sinkOnly) o << "  if (sink) {\n";
+    for (int k = s0; k < s1; ++k) {
+      const Slot& sl = p.slots[k];
+      std::ostringstream t;
+      t << source_expr (sl) << " + ";
+      if (sl.type == T_SILENT) t << "P.f[" << sl.silIdx << "]"; else t << row_weight (sl, p.rowOff[k]);
+      if (k == s0) o << (sinkOnly ? "  n" : "  double n") << d << " = " << t.str() << ";\n";
+      else {
+        const unsigned long long field = ((1ull << J.bits[d]) - 1ull) << J.shift[d], val = (unsigned long long) (k - s0) << J.shift[d];
+        o << "  { const double t = " << t.str() << "; if (mb_lt<((" << (compareNo++ & 3) << ") < ICMP)> (n" << d << ", t)) { n" << d << " = t; word = (word & (mb_tbword) " << (~field) << "ull) | (mb_tbword) " << val << "ull; } }\n";
+      }
+    }
+    if (sinkOnly) o << "  }\n";
+    if (d == 0) o << "  if (origin) n" << d << " = 0.0;\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
+  o << "  return word;\n}\n\n";
+}
+
+// Linear domain, normalised: the unit group of a state is a plain copy, every other group one multiply-add
+// with its scaled weight
+static void gen_cell_row_lin (std::ostringstream& o, const mb_machine* m, const Program& p, bool forward) {
+  o << "__device__ __forceinline__ void " << (forward ? "mb_cell_fwd_linr" : "mb_cell_bwd_linr")
+    << " (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], "
+       "const unsigned ea, const unsigned em, const unsigned ebr, const bool origin, const MBSilN& P) {\n";
+  const int originState = forward ? 0 : m->S - 1;
+  for (int q = 0; q < m->S; ++q) {
+    const int d = forward ? q : m->S - 1 - q;
+    const int s0 = p.stateSlot0[d], s1 = p.stateSlot0[d + 1], unit = p.unitSlot[d];
+    if (s0 == s1) o << "  double n" << d << " = 0.0;\n";
+    if (unit >= 0) o << "  double n" << d << " = " << source_expr (p.slots[unit]) << ";\n";
+    bool first = unit < 0;
+    for (int k = s0; k < s1; ++k) {
+      if (k == unit) continue;
+      const Slot& sl = p.slots[k];
+      std::ostringstream w;
+      if (sl.type == T_SILENT) w << "P." << (forward ? "f" : "b") << "[" << sl.silIdx << "]"; else w << row_weight (sl, p.rowOff[k]);
+      if (first) o << "  double n" << d << " = " << source_expr (sl) << " * " << w.str() << ";\n";
+      else o << "  n" << d << " = fma (" << source_expr (sl) << ", " << w.str() << ", n" << d << ");\n";
+      first = false;
+    }
+    if (d == originState) o << "  if (origin) n" << d << " = P." << (forward ? "originF" : "originB") << ";\n";
+  }
+  for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
   o << "}\n\n";
 }
 
@@ -499,6 +624,10 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.modV ? J.modV : J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
+  if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiI, J.modV, "mb_k_viterbi_i"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreI, J.modV, "mb_k_viterbi_score_i"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiI2, J.modV, "mb_k_viterbi_i2"), "cuModuleGetFunction")
+                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreI2, J.modV, "mb_k_viterbi_score_i2"), "cuModuleGetFunction"))) return 1;
   if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiN, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreN, J.mod, "mb_k_viterbi_score"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLinN, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
@@ -506,9 +635,12 @@ static int compile (mb_machine* m, JitEngine& J) {
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[10] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin, J.kViterbiScore };
-  const int ne[10] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit };
-  for (int q = 0; q < 10; ++q) {
+  CUfunction fn[14] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin, J.kViterbiScore,
+                        J.kViterbiI, J.kViterbiScoreI, J.kViterbiI2, J.kViterbiScoreI2 };
+  const int ne[14] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.fwd.nEmit,
+                       J.fwd.nEmit, J.fwd.nEmit };
+  for (int q = 0; q < 14; ++q) {
+    if (!fn[q]) continue;      // (the integer-compare kernels exist in the score module only)
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
     J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (16 + 32 * (m->S + 1))) * 8
       + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0)
@@ -580,6 +712,47 @@ int rt_launch (void* fn, unsigned grid, unsigned threads, size_t smemBytes, cuda
   return cu_ok (g_drv.LaunchKernel ((CUfunction) fn, grid, 1, 1, threads, 1, 1, (unsigned) smemBytes, (CUstream) stream, params, nullptr), "cuLaunchKernel") ? 0 : 1;
 }
 
+// Row-layout tables of one program (Program::WA): the log weights as they are (Viterbi), and the normalised
+// linear weights w * sigma_src / sigma_self with sigma from the unit groups (Program::unitSlot).  ok = false when
+// a unit group's weight is zero or not finite, or a scale leaves 2^+-100: the normalised kernels must not run then.
+struct RowTables { std::vector<double> rowLog, rowLinN, silN; double originInv = 1, resLog = 0; bool ok = true; };
+
+static void row_tables (const mb_machine* m, const Program& p, bool forward, RowTables& r) {
+  const int S = m->S;
+  const double kLn2 = 0.6931471805599453;
+  std::vector<double> ls ((size_t) S, 0.);      // log sigma
+  r.ok = true;
+  for (int q = 0; q < S; ++q) {
+    const int d = forward ? q : S - 1 - q;      // a silent group's source comes earlier in this order
+    const int u = p.unitSlot[d];
+    if (u < 0) continue;
+    const double w = m->lw[p.silId[p.slots[u].silIdx]];
+    if (!std::isfinite (w)) { r.ok = false; continue; }
+    ls[d] = w + ls[p.slots[u].other];
+    if (std::fabs (ls[d]) > 100. * kLn2) r.ok = false;
+  }
+  auto scaled = [&] (int slot, double w) {      // linear weight of a group's transition in normalised units
+    if (!(w > -INFINITY)) return 0.;
+    const double lw = w + ls[p.slots[slot].other] - ls[p.slots[slot].self];
+    if (!std::isfinite (lw) || std::fabs (lw) > 48. * kLn2) r.ok = false;
+    return std::exp (lw);
+  };
+  r.rowLog.assign (p.rowId.size(), -INFINITY);
+  r.rowLinN.assign (p.rowId.size(), 0.);
+  for (size_t e = 0; e < p.rowId.size(); ++e) {
+    if (p.rowId[e] < 0) continue;
+    const double w = m->lw[p.rowId[e]];
+    r.rowLog[e] = w + 0.0;      // (-0.0 becomes +0.0: the integer compare of bit patterns needs one zero)
+    r.rowLinN[e] = scaled (p.rowSlot[e], w);
+  }
+  r.silN.assign ((size_t) std::max (p.nSil, 1), 1.);
+  for (size_t k = 0; k < p.slots.size(); ++k)
+    if (p.slots[k].type == T_SILENT && (int) k != p.unitSlot[p.slots[k].self]) r.silN[p.slots[k].silIdx] = scaled ((int) k, m->lw[p.silId[p.slots[k].silIdx]]);
+  const int originState = forward ? 0 : S - 1, resState = forward ? S - 1 : 0;
+  r.originInv = std::exp (-ls[originState]);
+  r.resLog = ls[resState];
+}
+
 static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>& ef, std::vector<double>& eb) {
   const double ninf = -INFINITY;
   ef.assign ((size_t) std::max (J.fwd.nEmit, 1), ninf);
@@ -589,8 +762,8 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
   const int nf = std::max (J.fwd.nSil, 1), nb = std::max (J.bwd.nSil, 1);
   J.silParam.assign ((size_t) (nf + nb) * 8, 0);
   double* sp = (double*) J.silParam.data();
-  for (int q = 0; q < J.fwd.nSil; ++q) sp[q] = m->lw[J.fwd.silId[q]];
-  for (int q = 0; q < J.bwd.nSil; ++q) sp[nf + q] = m->lw[J.bwd.silId[q]];
+  for (int q = 0; q < J.fwd.nSil; ++q) sp[q] = m->lw[J.fwd.silId[q]] + 0.0;      // (+ 0.0: no negative zero, see row_tables)
+  for (int q = 0; q < J.bwd.nSil; ++q) sp[nf + q] = m->lw[J.bwd.silId[q]] + 0.0;
   J.silParamLin.assign (J.silParam.size(), 0);
   double* sl = (double*) J.silParamLin.data();
   for (int q = 0; q < nf + nb; ++q) sl[q] = std::exp (sp[q]);
@@ -599,6 +772,34 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
   for (double w: m->lw) if (std::isfinite (w) && std::fabs (w) > 24.0 * 0.6931471805599453) J.linearOK = false;
   for (double w: m->lw) if (std::isnan (w) || w == INFINITY) J.linearOK = false;
   if (m->opt.get ("jit_no_linear", 0)) J.linearOK = false;
+  // Viterbi may compare bit patterns as integers when no path score can be positive
+  J.nonPositive = true;
+  for (double w: m->lw) if (!(w <= 0.)) J.nonPositive = false;      // (NaN fails too)
+  if (m->opt.has ("jit_vit_intcmp")) { const int v = m->opt.get ("jit_vit_intcmp", 4); J.vitIcmp = v >= 4 ? 4 : v >= 2 ? 2 : 0; }
+}
+
+// score module: row-layout tables and the parameter block of the normalised linear kernels
+static int upload_row_tables (const mb_machine* m, JitEngine& J) {
+  if (!J.modV) return 0;
+  RowTables f, b;
+  row_tables (m, J.fwd, true, f);
+  row_tables (m, J.bwd, false, b);
+  J.normOK = f.ok && b.ok && J.linearOK && !m->opt.get ("jit_no_norm", 0);
+  const int nf = std::max (J.fwd.nSil, 1), nb = std::max (J.bwd.nSil, 1);
+  J.silParamLinN.assign ((size_t) (nf + nb + 4) * 8, 0);
+  double* sn = (double*) J.silParamLinN.data();
+  for (int q = 0; q < nf; ++q) sn[q] = f.silN[q];
+  for (int q = 0; q < nb; ++q) sn[nf + q] = b.silN[q];
+  sn[nf + nb] = f.originInv; sn[nf + nb + 1] = b.originInv; sn[nf + nb + 2] = f.resLog; sn[nf + nb + 3] = b.resLog;
+  if (!J.dRowVit) {
+    MB_CUDA (cudaMalloc (&J.dRowVit, f.rowLog.size() * 8));
+    MB_CUDA (cudaMalloc (&J.dRowFLinN, f.rowLinN.size() * 8));
+    MB_CUDA (cudaMalloc (&J.dRowBLinN, b.rowLinN.size() * 8));
+  }
+  MB_CUDA (cudaMemcpy (J.dRowVit, f.rowLog.data(), f.rowLog.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (J.dRowFLinN, f.rowLinN.data(), f.rowLinN.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (J.dRowBLinN, b.rowLinN.data(), b.rowLinN.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
 }
 
 int jit_update_weights (mb_machine* m) {
@@ -611,7 +812,7 @@ int jit_update_weights (mb_machine* m) {
   for (auto& v: eb) v = std::exp (v);
   MB_CUDA (cudaMemcpy (J.dEmitFLin, ef.data(), ef.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (J.dEmitBLin, eb.data(), eb.size() * 8, cudaMemcpyHostToDevice));
-  return 0;
+  return upload_row_tables (m, J);
 }
 
 // layout of the traceback plan on the device (int32): [0..S] stateSlot0, then per slot type, other,
@@ -663,7 +864,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   const int passC = pass ? J.CV : J.C, passMinBlocks = pass ? J.minBlocksV : J.minBlocks;
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
-  if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n";
+  if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n#define MB_ROWTAB 1\n";
+  o << "#define MB_STEADY_UNROLL " << std::max (1, std::min (4, m->opt.get ("jit_unroll", 1))) << "\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
@@ -677,6 +879,23 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
   o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n__device__ __forceinline__ double mb_warp_sum_d (double);\n\n";
+  if (pass) {
+    // row-layout emission tables and the normalised linear parameter block (see Program::WA, Program::unitSlot)
+    o << "// MB_ROWCELLS_BEGIN (the host harness of tests/test_jit_rowcells_host.py compiles from here to MB_ROWCELLS_END)\n";
+    o << "#define MB_WA_F " << J.fwd.WA << "\n#define MB_WB_F " << J.fwd.WB << "\n#define MB_WA_B " << J.bwd.WA << "\n#define MB_WB_B " << J.bwd.WB << "\n";
+    o << "struct MBSilN { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; double originF, originB, resLogF, resLogB; };\n";
+    o << "#ifndef MB_LDS\n"
+         "template<int OFF> __device__ __forceinline__ double mb_lds (const unsigned addr) { double v; asm (\"ld.shared.f64 %0, [%1+%2];\" : \"=d\"(v) : \"r\"(addr), \"n\"(OFF)); return v; }\n"
+         "#define MB_LDS(addr, off) mb_lds<off> (addr)\n#endif\n";
+    o << "#ifndef MB_HOST_HARNESS\n"
+         "template<bool ICMP> __device__ __forceinline__ bool mb_lt (const double a, const double b) {      // a < b\n"
+         "  if (ICMP) return (unsigned long long) __double_as_longlong (a) > (unsigned long long) __double_as_longlong (b);      // a, b in [-inf, +0]: the order of the bit patterns, reversed\n"
+         "  return a < b;\n}\n#endif\n\n";
+    gen_cell_row_vit (o, m, J.fwd, J);
+    gen_cell_row_lin (o, m, J.fwd, true);
+    gen_cell_row_lin (o, m, J.bwd, false);
+    o << "// MB_ROWCELLS_END\n";
+  }
   gen_cell (o, m, J.fwd, true, false, J);
   gen_cell (o, m, J.bwd, false, false, J);
   gen_cell (o, m, J.fwd, true, true, J);
@@ -688,6 +907,35 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << kJitSkeleton;
   (pass ? J.sourceV : J.source) = o.str();
   }
+}
+
+// Diagnostic used by the CPU tests: the tables the score module's kernels read, as the host prepares them for
+// these weights (no device).  which: 0 forward row-layout log weights (Viterbi), 1 forward / 2 backward row-layout
+// normalised linear weights, 3 the log parameter block (f | b), 4 the normalised block (f | b | originF, originB,
+// resLogF, resLogB), 5 { normalisation usable, no positive log-weight }.
+int jit_host_tables (const mb_machine* m, int which, std::vector<double>& out) {
+  std::string why;
+  if (!jit_supported (m, &why)) { set_error ("machine not eligible for the JIT engine: " + why); return 1; }
+  JitEngine J;
+  generate (m, J);
+  std::vector<double> ef, eb;
+  fill_weights (m, J, ef, eb);
+  RowTables f, b;
+  row_tables (m, J.fwd, true, f);
+  row_tables (m, J.bwd, false, b);
+  const int nf = std::max (J.fwd.nSil, 1), nb = std::max (J.bwd.nSil, 1);
+  out.clear();
+  if (which == 0) out = f.rowLog;
+  else if (which == 1) out = f.rowLinN;
+  else if (which == 2) out = b.rowLinN;
+  else if (which == 3) { const double* sp = (const double*) J.silParam.data(); out.assign (sp, sp + nf + nb); }
+  else if (which == 4) {
+    out.insert (out.end(), f.silN.begin(), f.silN.begin() + nf);
+    out.insert (out.end(), b.silN.begin(), b.silN.begin() + nb);
+    out.push_back (f.originInv); out.push_back (b.originInv); out.push_back (f.resLog); out.push_back (b.resLog);
+  } else if (which == 5) { out.push_back (f.ok && b.ok && J.linearOK ? 1. : 0.); out.push_back (J.nonPositive ? 1. : 0.); }
+  else { set_error ("mb_jit_host_tables: which must be 0..5"); return 1; }
+  return 0;
 }
 
 // Diagnostic used by build() and the CPU tests: generate and NVRTC-compile the kernels of a machine
@@ -750,6 +998,9 @@ void jit_destroy (mb_machine* m) {
   if (J->dTbPlan) cudaFree (J->dTbPlan);
   if (J->dIdTabB) cudaFree (J->dIdTabB);
   if (J->dCounter) cudaFree (J->dCounter);
+  if (J->dRowVit) cudaFree (J->dRowVit);
+  if (J->dRowFLinN) cudaFree (J->dRowFLinN);
+  if (J->dRowBLinN) cudaFree (J->dRowBLinN);
   delete J;
   m->jit = nullptr;
 }
@@ -807,13 +1058,21 @@ struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const dou
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
                    const CountArgs& ca = CountArgs(), bool narrow = false) {
   JitEngine& J = *(JitEngine*) m->jit;
-  narrow = narrow && J.modV && (which == 2 || which == 5 || which == 6 || which == 9);
-  CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : which == 6 ? J.kBackwardLinN : J.kViterbiScoreN) : which == 9 ? J.kViterbiScore : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
+  const bool scoreKernel = which == 2 || which == 5 || which == 6 || which == 9;
+  // the score module's linear sweeps are the normalised ones: without usable unit weights the first module's take over
+  if (J.modV && (which == 5 || which == 6) && !J.normOK) narrow = true;
+  narrow = narrow && J.modV && scoreKernel;
+  const bool rowTab = J.modV && scoreKernel && !narrow;      // score module: row-layout tables
+  const int icmp = (rowTab && (which == 2 || which == 9) && J.nonPositive) ? J.vitIcmp : 0;      // how many of four Viterbi compares go to the integer pipe
+  const int slot = icmp ? (which == 2 ? 10 : 11) + (icmp == 2 ? 2 : 0) : which;      // index into blocksPerSM / smemBytes
+  CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : which == 6 ? J.kBackwardLinN : J.kViterbiScoreN)
+    : icmp == 4 ? (which == 2 ? J.kViterbiI : J.kViterbiScoreI) : icmp == 2 ? (which == 2 ? J.kViterbiI2 : J.kViterbiScoreI2)
+    : which == 9 ? J.kViterbiScore : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
   const bool lin = which >= 5 && which <= 8;      // 9: the score-only Viterbi, log domain
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
-  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[which]);
+  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[slot]);
   grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
@@ -833,14 +1092,15 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dResult;
   A.emit = (which == 5 || which == 7) ? J.dEmitFLin : (which == 6 || which == 8) ? J.dEmitBLin : (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
+  if (rowTab) A.emit = which == 5 ? J.dRowFLinN : which == 6 ? J.dRowBLinN : J.dRowVit;
   A.flag = ca.flag;
   A.F32 = ca.F32; A.f32Off = ca.f32Off; A.ef = ca.ef; A.efOff = ca.efOff;
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "[mb_jit] kernel %d grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[which], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
-  void* params[2] = { lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
+    fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, icmp ? " (integer compares)" : rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
+             J.smemBytes[which], J.blocksPerSM[slot], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+  void* params[2] = { (rowTab && lin) ? (void*) J.silParamLinN.data() : lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
 }

@@ -91,6 +91,18 @@ __device__ __forceinline__ double mb_warp_sum_d (double v) {
   return v;
 }
 
+// lane 0 replaces v by the double at a shared-memory address (the staged boundary row); the other lanes keep theirs:
+// one predicated load instead of an unconditional load and two selects
+__device__ __forceinline__ void mb_lds_lane0 (double& v, const int lane, const unsigned addr) {
+  asm volatile ("{ .reg .pred p; setp.eq.s32 p, %1, 0; @p ld.shared.f64 %0, [%2]; }" : "+d"(v) : "r"(lane), "r"(addr));
+}
+
+// log of the scale the result state carries in the normalised linear kernels (0 elsewhere)
+template<int DIR> __device__ __forceinline__ double mb_res_log (const MBSil&) { return 0.0; }
+#ifdef MB_ROWTAB
+template<int DIR> __device__ __forceinline__ double mb_res_log (const MBSilN& P) { return DIR ? P.resLogB : P.resLogF; }
+#endif
+
 template<bool B> struct MBBool { static constexpr bool value = B; };
 
 template<int DIR> struct MBDir { };
@@ -110,7 +122,7 @@ template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { re
 // MODE 3: Backward fused with the posterior-count accumulation of BackwardMatrix::getCounts
 //         (backward.cpp:62-87): each transition group's term w + B(dest) is formed once and used
 //         both for the Backward log-sum-exp and for exp(F(src) - ll + term).
-template<int MODE, int DIR>
+template<int MODE, int DIR, int ICMP = 0>
 __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
@@ -118,6 +130,9 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
+#ifdef MB_ROWTAB
+  const unsigned eBase = (unsigned) __cvta_generic_to_shared (E);      // the emission weights in row layout (see the generated prelude)
+#endif
   // shared memory: emission table | per warp: 128-byte ring of output-row tokens, published a block
   // ahead so that each lane can fetch its next step's token during the current step | per warp: 32 staged boundary rows | per warp: thread-private count
   // accumulators of the emitting transition groups, acc[ctx * 32 + lane] (count kernels only)
@@ -129,6 +144,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
   const double NI = mb_neg_inf();
+  const unsigned sInAddr = (unsigned) __cvta_generic_to_shared (sIn);
 
   for (;;) {
     unsigned long long w = 0;
@@ -150,12 +166,18 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     for (int strip = 0; strip < nStrips; ++strip) {
       const int col0 = strip * MB_W + lane * MB_C;
       int ta[MB_C];
+#ifdef MB_ROWTAB
+      unsigned ea[MB_C];      // shared-memory address of each column's input-token row
+#endif
 #pragma unroll
       for (int c = 0; c < MB_C; ++c) {
         const int i = col0 + c;
         int tok = 1;
         if (i >= 1 && i <= Li) tok = DIR ? x[Li - i] : x[i - 1];
         ta[c] = tok - 1;
+#ifdef MB_ROWTAB
+        ea[c] = eBase + (unsigned) (tok - 1) * (unsigned) (MB_WA_F * 8);
+#endif
       }
       double U[MB_C][MB_S], Lk[MB_S];
 #pragma unroll
@@ -192,6 +214,10 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       __syncwarp();
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       const int nSteps = Lo + 32;
+      // where this lane's row r = t - lane goes: pointers advanced by one row per step instead of recomputed
+      uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) (0 - lane) * pitch + col0) * MB_TBBYTES : (uint8_t*) 0;
+      const int64_t tbStep = pitch * MB_TBBYTES;
+      double* boutRow = bout + (int64_t) (0 - lane) * MB_ROW;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
       // every 32 steps (kept out of the step body so that the steady loop carries no block tests)
@@ -217,14 +243,22 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         const int r = t - lane;
         const int tokb = tokNext;
         tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
+#ifdef MB_ROWTAB
+        const unsigned eb8 = (unsigned) tokb * 8u, ebr = eBase + (unsigned) (MB_NIN * MB_WA_F * 8) + (unsigned) tokb * (unsigned) (MB_WB_F * 8);
+#endif
         // left neighbour's last column at this row: a shuffle, or the staged boundary row for lane 0
         double Lc[MB_S];
 #pragma unroll
         for (int s = 0; s < MB_S; ++s) {
           if (mb_live<DIR> (s)) {
+#ifdef MB_ROWTAB
+            Lc[s] = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+            mb_lds_lane0 (Lc[s], lane, sInAddr + (unsigned) (((t & 31) * MB_ROW + s) * 8));      // a predicated load: no select
+#else
             const double fromLane = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
             const double fromStrip = sIn[(t & 31) * MB_ROW + s];
             Lc[s] = lane ? fromLane : fromStrip;
+#endif
           } else Lc[s] = NI;
         }
         if (STEADY || (r >= 0 && r <= Lo)) {
@@ -263,7 +297,11 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               }
               mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
+#ifdef MB_ROWTAB
+              const mb_tbword word = mb_cell_vitr<ICMP> (Dc, Lc, U[c], N, ea[c], ea[c] + eb8, ebr, origin, !STEADY && r == Lo && col0 + c == Li, P);
+#else
               const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, !STEADY && r == Lo && col0 + c == Li, E, P);
+#endif
               if (MODE == 1) {
                 const int sh = 8 * MB_TBBYTES * c;
                 if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
@@ -275,7 +313,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
             for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
           }
           if (MODE == 1) {
-            uint8_t* p = tb + ((int64_t) r * pitch + col0) * MB_TBBYTES;
+            uint8_t* p = tbRow;
             if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack32;
             else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack32;
             else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = pack32;
@@ -284,7 +322,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           }
           if (hasOut && lane == 31) {
 #pragma unroll
-            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
+            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) boutRow[s] = U[MB_C - 1][s];
           }
           if (!STEADY && r == Lo) {
 #pragma unroll
@@ -292,6 +330,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               if (col0 + c == Li) A.result[k] = U[c][MBDir<DIR>::RES];
           }
         }
+        tbRow += tbStep;
+        boutRow += MB_ROW;
       };
       {
         int t = 0;
@@ -300,7 +340,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         while (t < Lo) {
           if ((t & 31) == 0) blockStart (t);
           const int tend = min (Lo, (t | 31) + 1);
-#pragma unroll 1
+#pragma unroll MB_STEADY_UNROLL
           for (; t < tend; ++t) step (t, MBBool<true>());
         }
         for (; t < nSteps; ++t) { if ((t & 31) == 0) blockStart (t); step (t, MBBool<false>()); }
@@ -319,6 +359,14 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_
 #endif
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0> (P, A); }
+#ifdef MB_ROWTAB
+// the same two with the compares done on the bit patterns (integer pipe): only launched when no log-weight is positive
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_i (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0, 4> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score_i (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0, 4> (P, A); }
+// ... and with two of every four compares there, the other two on the FP64 pipe
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_i2 (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0, 2> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score_i2 (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0, 2> (P, A); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).
@@ -347,8 +395,8 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_vite
 // every rescale block.
 // MODE 3 (DIR 1): Backward fused with the posterior counts: for each transition group the product
 // term = B(dest) * w feeds the Backward sum and, times F(src) * 2^(eF + eB) / Z, the group's count.
-template<int MODE, int DIR>
-__device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
+template<int MODE, int DIR, class SIL>
+__device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
 #ifdef MB_LANE_FRAMES
   constexpr bool LF = MODE == 0;
 #else
@@ -360,6 +408,14 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < NE; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
+#ifdef MB_ROWTAB
+  // score module: the normalised linear weights in row layout (see the generated prelude)
+  constexpr bool ROW = MODE == 0;
+  const unsigned eBase = (unsigned) __cvta_generic_to_shared (E);
+  constexpr unsigned WA8 = (DIR ? MB_WA_B : MB_WA_F) * 8, WB8 = (DIR ? MB_WB_B : MB_WB_F) * 8;
+#else
+  constexpr bool ROW = false;
+#endif
   // shared memory layout as in mb_run; the count accumulators are FP64 here: accd[ctx * 32 + lane]
   const int nWarps = blockDim.x >> 5;
   uint8_t* ring = (uint8_t*) (mb_smem + ((NE + 1) & ~1)) + warp * 128;
@@ -370,6 +426,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
+  const unsigned sInAddr = (unsigned) __cvta_generic_to_shared (sIn);
 
   for (;;) {
     unsigned long long w = 0;
@@ -405,12 +462,18 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
       // nStrips-1-strip, and both sides stream whole warp-sized blocks (see MB_FBLOCK).
       const int col0 = strip * MB_W + lane * MB_C - (MODE == 3 ? nStrips * MB_W - (Li + 1) : 0);
       int ta[MB_C];
+#ifdef MB_ROWTAB
+      unsigned ea[MB_C];      // shared-memory address of each column's input-token row
+#endif
 #pragma unroll
       for (int c = 0; c < MB_C; ++c) {
         const int i = col0 + c;
         int tok = 1;
         if (i >= 1 && i <= Li) tok = DIR ? x[Li - i] : x[i - 1];
         ta[c] = tok - 1;
+#ifdef MB_ROWTAB
+        ea[c] = eBase + (unsigned) (tok - 1) * WA8;
+#endif
       }
       double U[MB_C][MB_S], Lk[MB_S];
 #pragma unroll
@@ -462,6 +525,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         mb_cp_async_commit();
       }
       const int nSteps = Lo + 32;
+      double* boutRow = bout + (int64_t) (0 - lane) * MB_ROW;      // this lane's row r = t - lane of the outgoing boundary, advanced per step
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
       // every MB_RESCALE steps (kept out of the step body so that the steady loop carries no block tests)
@@ -560,13 +624,23 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         const int r = t - lane;
         const int tokb = tokNext;
         tokNext = ring[(t + 1 - lane) & 127];         // next step's token, off the critical path
+#ifdef MB_ROWTAB
+        const unsigned eb8 = (unsigned) tokb * 8u, ebr = eBase + (unsigned) MB_NIN * WA8 + (unsigned) tokb * WB8;
+#endif
         double Lc[MB_S];
 #pragma unroll
         for (int s = 0; s < MB_S; ++s) {
           if (mb_live<DIR> (s)) {
+#ifdef MB_ROWTAB
+            double v = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
+            if (LF) v *= gl;
+            mb_lds_lane0 (v, lane, sInAddr + (unsigned) (((t & (MB_RESCALE - 1)) * MB_ROW + s) * 8));      // a predicated load: no select
+            Lc[s] = v;
+#else
             const double fromLane = __shfl_up_sync (MB_FULL, U[MB_C - 1][s], 1);
             const double fromStrip = sIn[(t & (MB_RESCALE - 1)) * MB_ROW + s];
             Lc[s] = lane ? (LF ? fromLane * gl : fromLane) : fromStrip;
+#endif
           } else Lc[s] = 0.0;
         }
         // Forward block of this step.  MODE 2 writes it.  MODE 3 reads the mirrored one: it was copied
@@ -606,7 +680,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
             const bool origin = !STEADY && (r == 0) && (col0 + c == 0);
-            if (MODE == 3) {
+            if constexpr (MODE == 3) {
               double Fc[MB_S];
               const int col = col0 + c;
               // written by Forward lane 31-lane as its cell MB_C-1-c; the padding columns hold finite values
@@ -621,8 +695,16 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
               mb_fexpand_lin (hw, kap, Fc, P);      // the kept states, and through the silent groups the others
               mb_cell_cnt_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, csd, accd, c);
             } else {
-              if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
-              else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+#ifdef MB_ROWTAB
+              if constexpr (ROW) {
+                if (DIR == 0) mb_cell_fwd_linr (Dc, Lc, U[c], N, ea[c], ea[c] + eb8, ebr, origin, P);
+                else mb_cell_bwd_linr (Dc, Lc, U[c], N, ea[c], ea[c] + eb8, ebr, origin, P);
+              } else
+#endif
+              {
+                if (DIR == 0) mb_cell_fwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+                else mb_cell_bwd_lin (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P);
+              }
               if (MODE == 2) {
                 // high words, rounded; 16-byte chunk g of cell c goes to word ((c*MB_SQ + g)*32 + lane)*4 of
                 // the block, so every store instruction of the warp writes 512 contiguous bytes
@@ -638,18 +720,19 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
           }
           if (hasOut && lane == 31) {
 #pragma unroll
-            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) bout[(int64_t) r * MB_ROW + s] = U[MB_C - 1][s];
-            bout[(int64_t) r * MB_ROW + MB_S] = (double) ecur;
+            for (int s = 0; s < MB_S; ++s) if (mb_live<DIR> (s)) boutRow[s] = U[MB_C - 1][s];
+            boutRow[MB_S] = (double) ecur;
           }
           if (!STEADY && r == Lo) {
 #pragma unroll
             for (int c = 0; c < MB_C; ++c)
               if (col0 + c == Li) {
                 const double v = U[c][MBDir<DIR>::RES];
-                A.result[k] = v > 0.0 ? log (v) + (double) ecur * 0.6931471805599453094 : mb_neg_inf();
+                A.result[k] = v > 0.0 ? log (v) + (double) ecur * 0.6931471805599453094 + mb_res_log<DIR> (P) : mb_neg_inf();
               }
           }
         }
+        boutRow += MB_ROW;
       };
       {
         int t = 0;
@@ -660,7 +743,7 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
         while (t < Lo) {
           if ((t & (MB_RESCALE - 1)) == 0) blockStart (t);
           const int tend = min (Lo, (t | (MB_RESCALE - 1)) + 1);
-#pragma unroll 1
+#pragma unroll MB_STEADY_UNROLL
           for (; t < tend; ++t) step (t, MBBool<true>());
         }
         for (; t < nSteps; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
@@ -673,8 +756,13 @@ __device__ __forceinline__ void mb_run_lin (const MBSil& P, const MBArgs& A) {
   }
 }
 
+#ifdef MB_ROWTAB
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSilN P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 0> (P, A); }
+extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSilN P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
+#else
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_forward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_backward_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<0, 1> (P, A); }
+#endif
 #ifndef MB_SCORE_MODULE
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_LIN) mb_k_fstore_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<2, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_bcounts_lin (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run_lin<3, 1> (P, A); }
