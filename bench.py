@@ -5,12 +5,19 @@ One "step" = one pass of the hot path over one batch: Forward log-likelihood (bo
 score + traceback (boss -V/-A) for every pair of the batch.  Metric (BASELINE.json): DP cell-state
 updates per second, in GCUPS, summed over both sweeps and over all ranks; pairs/s beside it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--len L] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--len L] [--impl reference] [--no-configs]
 
 N > 1: launched by torchrun, one rank per GPU; every rank processes its own P pairs (weak scaling,
 no data-path collective; the E-step's count all-reduce is timed separately as "em").  Times are
 taken per step between device synchronisations, L2 is flushed between steps, the maximum over
 ranks is used, and SM clocks / throttle reasons are sampled with nvidia-smi during the timed region.
+
+Beside the headline line's own keys the JSON carries
+  "set_b"    the same step on HARD data: peaked parameters (SURVEY 8d set B), every output the input with 10 %
+             substitutions and 2 % indels, with the number of pairs the linear sweeps handed to the log domain;
+  "strong"   strong scaling: 10 000 pairs IN TOTAL dealt over the ranks by the library's sharder (mb_shard_pairs);
+  "configs"  (one GPU only) BASELINE configs 2 - 5 at their stated sizes or a stated sub-sample, each with GCUPS,
+             pairs/s, the pairs re-run in the log domain, and its own roofline fraction.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/refdrv, the unmodified
 reference sources; falls back to the C restatement if that binary is absent) on the host cores.
@@ -54,6 +61,47 @@ def dnapsw_machine():
                 lw=np.array([num(r[4]) for r in t], np.float64))
 
 
+def eval_machine(preset: str):
+    """A shipped pre-evaluated machine (machineboss_b200/presets/NAME.eval.json[.gz], boss -U default parameters)."""
+    import gzip
+    base = os.path.join(REPO, "machineboss_b200", "presets", preset + ".eval.json")
+    if os.path.exists(base):
+        with open(base) as f:
+            j = json.load(f)
+    else:
+        with gzip.open(base + ".gz", "rt") as f:
+            j = json.load(f)
+    return _flat(j)
+
+
+def fixture_machine(name: str):
+    """The evaluated machine of a committed fixture (tests/golden), e.g. dnapsw with the peaked parameter set B."""
+    import gzip
+    base = os.path.join(REPO, "tests", "golden", name + ".json")
+    if os.path.exists(base):
+        with open(base) as f:
+            j = json.load(f)
+    else:
+        with gzip.open(base + ".gz", "rt") as f:
+            j = json.load(f)
+    return _flat(j["machine"])
+
+
+def _flat(j):
+    t = j["trans"]
+
+    def num(v):
+        return float("-inf") if v == "-Infinity" else float(v)
+    return dict(n_states=j["nStates"], n_in=len(j["inAlphabet"]), n_out=len(j["outAlphabet"]),
+                src=np.array([r[0] for r in t], np.int32), dst=np.array([r[1] for r in t], np.int32),
+                tin=np.array([r[2] for r in t], np.int32), tout=np.array([r[3] for r in t], np.int32),
+                lw=np.array([num(r[4]) for r in t], np.float64))
+
+
+def make_machine(capi, mj):
+    return capi.Machine(mj["n_states"], mj["n_in"], mj["n_out"], mj["src"], mj["dst"], mj["tin"], mj["tout"], mj["lw"])
+
+
 def _splitmix64(x):
     with np.errstate(over="ignore"):
         x = x + np.uint64(0x9E3779B97F4A7C15)
@@ -74,6 +122,40 @@ def synth_batch(seed: int, first_pair: int, n_pairs: int, li: int, lo: int, n_sy
     x_off = np.arange(n_pairs + 1, dtype=np.int64) * li
     y_off = np.arange(n_pairs + 1, dtype=np.int64) * lo
     return out[0], x_off, out[1], y_off
+
+
+def synth_ragged(seed: int, lengths, n_sym: int, which: int = 1):
+    """iid uniform tokens for sequences of the given lengths (the stream of synth_batch, pair k = index k)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    total = int(off[-1])
+    pair = np.repeat(np.arange(len(lengths), dtype=np.uint64), lengths)
+    pos = (np.arange(total, dtype=np.int64) - np.repeat(off[:-1], lengths)).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        base = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + (pair * np.uint64(2) + np.uint64(which)) * np.uint64(0xD1B54A32D192ED03)
+        tok = (1 + (_splitmix64(base + pos) % np.uint64(n_sym))).astype(np.uint8)
+    return tok, off
+
+
+def mutate_batch(seed: int, x: np.ndarray, x_off: np.ndarray, n_sym: int, sub: float = 0.10, indel: float = 0.02):
+    """SURVEY 8(d) set B data: every output = its input with `sub` substitutions and `indel` indels per position
+    (half deletions, half insertions), vectorised over the whole batch."""
+    n = int(x.shape[0])
+    with np.errstate(over="ignore"):
+        r = _splitmix64(np.arange(3 * n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x5851F42D4C957F2D))
+    u = (r[:n] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    alt = (r[n:2 * n] % np.uint64(n_sym - 1)).astype(np.int64)
+    ins = (1 + r[2 * n:] % np.uint64(n_sym)).astype(np.uint8)
+    base = np.where(u < indel / 2 + sub, (1 + (x.astype(np.int64) + alt) % n_sym).astype(np.uint8), x)
+    count = np.where(u < indel / 2, 0, np.where(u > 1.0 - indel / 2, 2, 1)).astype(np.int64)      # deleted / kept / kept + insertion
+    start = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
+    y = np.empty(int(start[-1]), dtype=np.uint8)
+    kept = count >= 1
+    y[start[:-1][kept]] = base[kept]
+    two = count == 2
+    y[start[:-1][two] + 1] = ins[two]
+    y_off = start[x_off]
+    return y, y_off.astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,7 +249,7 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n),
+        "config": dict(workload_config(args, n), pairs_per_gpu=None, pairs_total=n, parallelism="host threads on rank 0 only (%d); the other ranks exit" % threads),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "pairs_per_s": n / statistics.mean(secs)}))
@@ -195,6 +277,11 @@ def main():
     ap.add_argument("--engine", type=int, default=-1)
     ap.add_argument("--em-pairs", type=int, default=4096, help="pairs per GPU in the E-step (counts) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the set-B, strong-scaling and configs 2-5 legs")
+    ap.add_argument("--strong-pairs", type=int, default=10000, help="pairs IN TOTAL of the strong-scaling leg")
+    ap.add_argument("--cfg3-pairs", type=int, default=100000)
+    ap.add_argument("--cfg4-pairs", type=int, default=148)
+    ap.add_argument("--cfg5-reads", type=int, default=65536)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -262,8 +349,9 @@ def main():
 
     def step_e2e():
         b = capi.Batch(x=px.numpy(), x_off=x_off, y=py.numpy(), y_off=y_off)      # H2D from pinned memory
-        capi.forward_into(mach, b, h_ll)
-        total = capi.viterbi_into(mach, b, h_sc, h_len, h_off, h_paths)           # D2H of scores, lengths and packed paths
+        total = capi.viterbi_start(mach, b, h_sc, h_len, h_off, h_paths)          # D2H of scores and lengths; the packed paths leave through the copy engine ...
+        capi.forward_into(mach, b, h_ll)                                          # ... while the Forward sweep of the same pairs runs
+        b.wait()                                                                  # paths have arrived
         b.close()
         return h_ll, h_sc, (h_paths[:total], h_off)
 
@@ -314,10 +402,30 @@ def main():
     em_secs = time.perf_counter() - t0
     em_batch.close()
 
+    # strong scaling: a fixed list of pairs dealt over the ranks by the library's sharder (longest-processing-time first by
+    # cell count; mb_shard_pairs is also what mb_group_batch_create applies inside one process), resident, same step
+    sp = args.strong_pairs
+    sx, sx_off, sy, sy_off = synth_batch(SEED + 2, 0, sp, args.len, args.len, 4)
+    mine = np.flatnonzero(capi.shard_pairs(sx_off, sy_off, world) == rank)
+    sel = (mine[:, None] * args.len + np.arange(args.len)[None, :]).reshape(-1)
+    s_off = np.arange(len(mine) + 1, dtype=np.int64) * args.len
+    s_batch = capi.Batch(x=sx[sel], x_off=s_off, y=sy[sel], y_off=s_off)
+    for _ in range(2):
+        capi.forward(mach, s_batch); capi.viterbi_lengths(mach, s_batch)
+    strong_times = []
+    for _ in range(max(3, args.steps)):
+        barrier()
+        t0 = time.perf_counter()
+        capi.forward(mach, s_batch); capi.viterbi_lengths(mach, s_batch)
+        torch.cuda.synchronize()
+        strong_times.append(time.perf_counter() - t0)
+    strong_secs = sum(strong_times) / len(strong_times)
+    s_batch.close()
+
     if world > 1:
-        t = torch.tensor([total, e2e_total, em_secs], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total, e2e_total, em_secs, strong_secs], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total, e2e_total, em_secs = float(t[0]), float(t[1]), float(t[2])
+        total, e2e_total, em_secs, strong_secs = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         K = args.steps
@@ -341,6 +449,13 @@ def main():
                      "pairs_per_s": n_em * world / em_secs, "gcups_2_sweeps": 2 * em_cells * world / em_secs / 1e9,
                      "kernel_ms": em_kernel_ms, "launches": em_launches, "sum_counts": float(cnt.sum()), "loglike": tot_ll}
         out["roofline"] = roofline(mj, cells, fwd_ms, vit_ms)
+        out["strong"] = {"what": "strong scaling: %d pairs of %d x %d IN TOTAL, dealt over %d rank(s) by mb_shard_pairs; Forward + Viterbi with traceback, resident" % (sp, args.len, args.len, world),
+                         "value": 2 * float(args.len + 1) ** 2 * S * sp / strong_secs / 1e9, "unit": UNIT, "ms_per_step": 1e3 * strong_secs,
+                         "pairs_total": sp, "pairs_this_rank": int(len(mine)), "scaling": "strong"}
+        if not args.no_configs:
+            out["set_b"] = run_set_b(capi, P, args.len)
+            if world == 1:
+                out["configs"] = run_configs(capi, args)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = max(8, threads)
@@ -353,29 +468,9 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
-    """Roofline of the step's kernels.  DESIGN.md section 'Roofline'.
-
-    The fills are compute-bound (a score sweep's algorithmic HBM traffic is the tokens plus 8 B per
-    pair; the Viterbi back-pointers add 1 B per cell), so the roofline is the FP64 pipe's issue rate
-    over the per-cell transition fan-in: a dnapsw cell has T_c = 13 transition groups over 8 states,
-    5 of which are a state's second group.
-      Forward (scaled linear domain): one FP64 FMA per group  -> peak = S * DFMA / T_c
-      Viterbi (log domain, exact):    one FP64 add per group + one FP64 compare/select per second group
-                                      -> peak = S / (T_c / DADD + n_2nd / DSETP_SEL)
-    Pipe rates are measured on this pool's B200 by tools/pipe_peaks.cu (profiles/r01_pipe_peaks.json).
-    The dominant kernel of the step (longest) is reported at top level.
-    """
-    peaks = {}
-    p = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            peaks = json.load(f)
-    pipe = {}
-    pp = os.path.join(REPO, "profiles", "r01_pipe_peaks.json")
-    if os.path.exists(pp):
-        with open(pp) as f:
-            pipe = {r["op"]: r["gops_per_s"] for r in json.load(f)["results"]}
+def machine_groups(mj: dict):
+    """Transition groups of a machine: (groups per cell = T_c of SURVEY 8, second-and-later groups of a state,
+    states whose first silent group the normalised linear sweep turns into a plain copy)."""
     groups, seen = set(), {}
     for t in range(len(mj["src"])):
         a, b = int(mj["tin"][t]), int(mj["tout"][t])
@@ -388,37 +483,199 @@ def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
         groups.add((int(mj["dst"][t]), kind, int(mj["src"][t]), rank))
     t_c = len(groups)
     n_2nd = t_c - len({g[0] for g in groups})
+    n_unit = len({g[0] for g in groups if g[1] == 3})
+    return t_c, n_2nd, n_unit
+
+
+def pipe_peaks():
+    """FP64 pipe rates measured on this pool's B200 by tools/pipe_peaks.cu (Gop/s, chip-wide, from CUDA events)."""
+    pipe, src = {}, None
+    for name in ("r02_pipe_peaks.json", "r01_pipe_peaks.json"):
+        pp = os.path.join(REPO, "profiles", name)
+        if os.path.exists(pp):
+            with open(pp) as f:
+                pipe = {r["op"]: r["gops_per_s"] for r in json.load(f)["results"]}
+            src = "profiles/" + name
+            break
+    return {"dfma": pipe.get("dfma", 17895.0), "dadd": pipe.get("dadd", 17775.0), "dsetp_sel": pipe.get("dsetp_sel", 8475.0), "source": src or "fallback constants"}
+
+
+def hbm_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def issue_roofline(mj: dict, what: str, cells: float, ms: float, groups_per_cell=None) -> dict:
+    """Issue roofline of one sweep over the per-cell transition fan-in (BASELINE.json).
+
+      sums (scaled linear domain): one FP64 multiply-add per transition group      peak = S * DFMA / T_c
+      Viterbi (exact FP64 add + compare): one add per group, one compare + select
+        per second-and-later group of a state                                      peak = S / (T_c / DADD + n_2nd / DSETP_SEL)
+    T_c counts EVERY group of a cell (dnapsw: 13, 5 of them second groups).  What the kernels execute is less: the
+    end state is only formed in a pair's last cell (Viterbi: 11 adds + 4 compares), and the normalised sums turn each
+    state's first silent group into a copy (7 multiply-adds) -- `executed` gives the fraction against that count too."""
     S = mj["n_states"]
-    dfma = pipe.get("dfma", 17895.0) * 1e9
-    dadd = pipe.get("dadd", 17775.0) * 1e9
-    dsel = pipe.get("dsetp_sel", 8475.0) * 1e9
-    peak_fwd = S * dfma / t_c / 1e9
-    peak_vit = S / (t_c / dadd + n_2nd / dsel) / 1e9
-    ach_fwd, ach_vit = cells / fwd_ms / 1e6, cells / vit_ms / 1e6
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    fwd = {"kernel": "mb_k_forward_lin", "bound": "issue (FP64 FMA pipe)", "achieved": ach_fwd, "peak": peak_fwd,
-           "unit": "GCUPS", "frac": ach_fwd / peak_fwd, "ms_per_launch": fwd_ms}
-    vit = {"kernel": "mb_k_viterbi", "bound": "issue (FP64 add + compare/select)", "achieved": ach_vit, "peak": peak_vit,
-           "unit": "GCUPS", "frac": ach_vit / peak_vit, "ms_per_launch": vit_ms,
-           "hbm": {"algorithmic_bytes_per_launch": cells / S * 1.0, "achieved_gbs": cells / S / vit_ms / 1e6,
-                   "peak_gbs": hbm, "frac": cells / S / vit_ms / 1e6 / hbm,
-                   "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+    t_c, n_2nd, n_unit = machine_groups(mj)
+    if groups_per_cell:
+        t_c = groups_per_cell
+    pk = pipe_peaks()
+    ach = cells / ms / 1e6
+    if what == "viterbi":
+        peak = S / (t_c / pk["dadd"] + n_2nd / pk["dsetp_sel"])
+        bound = "issue (FP64 add + compare/select)"
+        ex_adds, ex_cmp = t_c - 2, n_2nd - 1      # the end state's two groups are only formed in the last cell
+        executed = {"adds": ex_adds, "compares": ex_cmp, "peak": S / (ex_adds / pk["dadd"] + ex_cmp / pk["dsetp_sel"])}
+    else:
+        peak = S * pk["dfma"] / t_c
+        bound = "issue (FP64 FMA pipe)"
+        ex = max(t_c - n_unit - 2, 1)               # (the end state's groups likewise)
+        executed = {"multiply_adds": ex, "peak": S * pk["dfma"] / ex}
+    executed["frac"] = ach / executed["peak"]
+    return {"bound": bound, "achieved": ach, "peak": peak, "unit": "GCUPS", "frac": ach / peak, "ms_per_launch": ms,
+            "per_cell": {"transition_groups": t_c, "second_groups": n_2nd, "states": S}, "executed": executed}
+
+
+def roofline(mj: dict, cells: float, fwd_ms: float, vit_ms: float) -> dict:
+    """Roofline block of the headline step: the dominant kernel (longest) at top level, both sweeps inside."""
+    pk = pipe_peaks()
+    hbm, hbm_src = hbm_peak()
+    S = mj["n_states"]
+    fwd = dict(issue_roofline(mj, "forward", cells, fwd_ms), kernel="mb_k_forward_lin")
+    vit = dict(issue_roofline(mj, "viterbi", cells, vit_ms), kernel="mb_k_viterbi (+ traceback kernels: the whole mb_viterbi call)")
+    vit["hbm"] = {"algorithmic_bytes_per_launch": cells / S * 1.0, "achieved_gbs": cells / S / vit_ms / 1e6, "peak_gbs": hbm,
+                  "frac": cells / S / vit_ms / 1e6 / hbm, "peak_source": hbm_src}
     top = dict(vit if vit_ms >= fwd_ms else fwd)
-    # DRAM bytes (read + write) of one launch of that kernel from the committed `ncu --set full` capture,
-    # which profile_round.sh takes at this bench's default size (10 000 pairs of 1000 x 1000)
+    # DRAM bytes (read + write) of one launch of that kernel from the committed `ncu --set full` capture, taken at
+    # this bench's default size (10 000 pairs of 1000 x 1000)
     top["traffic"] = None
-    sp = os.path.join(REPO, "profiles", "r01_ncu_summary.json")
-    if os.path.exists(sp) and abs(cells - 1001.0 * 1001.0 * 8 * 10000) < 1:
-        with open(sp) as f:
-            k = json.load(f).get("kernels", {}).get(top["kernel"], {})
-        if k.get("dram_traffic_bytes") and k.get("pairs", 10000) == 10000:
-            top["traffic"] = k["dram_traffic_bytes"]
-            top["traffic_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_summary.json)"
-    top["per_cell"] = {"transition_groups": t_c, "second_groups": n_2nd, "states": S}
-    top["peak_source"] = "measured DFMA %.0f, DADD %.0f, DSETP+SEL %.0f Gop/s (profiles/r01_pipe_peaks.json)" % (dfma / 1e9, dadd / 1e9, dsel / 1e9)
+    for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+        sp = os.path.join(REPO, "profiles", name)
+        if os.path.exists(sp) and abs(cells - 1001.0 * 1001.0 * 8 * 10000) < 1:
+            with open(sp) as f:
+                kk = json.load(f).get("kernels", {})
+            k = kk.get("mb_k_viterbi_i") or kk.get("mb_k_viterbi_i2") or kk.get("mb_k_viterbi") or {}
+            if vit_ms < fwd_ms:
+                k = kk.get("mb_k_forward_lin", {})
+            if k.get("dram_traffic_bytes") and k.get("pairs", 10000) == 10000:
+                top["traffic"] = k["dram_traffic_bytes"]
+                top["traffic_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/%s)" % name
+                break
+    top["peak_source"] = "measured DFMA %.0f, DADD %.0f, DSETP+SEL %.0f Gop/s (%s)" % (pk["dfma"], pk["dadd"], pk["dsetp_sel"], pk["source"])
     top["forward"] = fwd
     top["viterbi"] = vit
     return top
+
+
+# ---------------------------------------------------------------------------------------------
+# the other legs: hard data, strong scaling, BASELINE configs 2 - 5
+# ---------------------------------------------------------------------------------------------
+def timed_passes(capi, mach, batch, passes, reps=2):
+    """Kernel milliseconds (device events inside the library) and wall seconds per pass, best of `reps` after a warm-up."""
+    out = {}
+    for name in passes:
+        fn = {"forward": lambda: capi.forward(mach, batch), "viterbi": lambda: capi.viterbi_lengths(mach, batch),
+              "viterbi_score": lambda: capi.viterbi(mach, batch, paths=False), "counts": lambda: capi.counts(mach, batch)}[name]
+        fn()
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = fn()
+            wall = time.perf_counter() - t0
+            ms, nl = batch.last_kernel_ms()
+            if best is None or ms < best["kernel_ms"]:
+                best = {"kernel_ms": ms, "wall_ms": 1e3 * wall, "launches": nl}
+        best["redo"] = batch.last_redo() if name in ("forward", "counts") else 0
+        out[name] = (best, res)
+    return out
+
+
+def run_set_b(capi, P, L):
+    """The headline step on hard data: peaked dnapsw parameters, mutated copies (SURVEY 8d set B)."""
+    mj = fixture_machine("dnapsw_peaked")
+    mach = make_machine(capi, mj)
+    x, x_off, _, _ = synth_batch(SEED + 1, 0, P, L, L, 4)
+    y, y_off = mutate_batch(SEED + 1, x, x_off, 4)
+    batch = capi.Batch(x=x, x_off=x_off, y=y, y_off=y_off)
+    cells = batch.cell_states(mj["n_states"])
+    r = timed_passes(capi, mach, batch, ["forward", "viterbi"])
+    f, v = r["forward"][0], r["viterbi"][0]
+    ms = f["kernel_ms"] + v["kernel_ms"]
+    out = {"what": "set B: peaked dnapsw parameters (sub 0.91 / 0.03, gapOpen 0.05, gapExtend 0.5), %d pairs, input %d nt iid, output = input with 10 %% substitutions + 2 %% indels" % (P, L),
+           "value": 2 * cells / ms / 1e6, "unit": UNIT, "forward_gcups": cells / f["kernel_ms"] / 1e6, "viterbi_gcups": cells / v["kernel_ms"] / 1e6,
+           "pairs_per_s": P / (ms / 1e3), "redo_pairs": f["redo"], "redo_frac": f["redo"] / P,
+           "loglike_pair0": float(r["forward"][1][0]), "viterbi_pair0": float(r["viterbi"][1][0][0])}
+    batch.close(); mach.close()
+    return out
+
+
+def run_configs(capi, args):
+    """BASELINE configs 2 - 5 on one GPU, each at its stated size or a stated sub-sample of it."""
+    out = []
+    hbm, _ = hbm_peak()
+
+    def entry(name, workload, sample, mj, batch, n_pairs, r, extra=None, groups=None):
+        cells = batch.cell_states(mj["n_states"])
+        e = {"config": name, "workload": workload, "sample": sample, "pairs": n_pairs, "cell_states_per_pass": cells, "states": mj["n_states"], "transitions": int(len(mj["lw"]))}
+        for k, (t, _) in r.items():
+            e[k] = {"gcups": cells / t["kernel_ms"] / 1e6, "pairs_per_s": n_pairs / (t["wall_ms"] / 1e3), "kernel_ms": t["kernel_ms"], "launches": t["launches"], "redo_pairs": t["redo"]}
+            if k in ("forward", "viterbi", "viterbi_score"):
+                rf = issue_roofline(mj, "viterbi" if k.startswith("viterbi") else "forward", cells, t["kernel_ms"], groups)
+                e[k]["roofline"] = {kk: rf[kk] for kk in ("bound", "peak", "frac", "unit")}
+        if extra:
+            e.update(extra)
+        out.append(e)
+
+    # config 2: E-step (stored Forward + fused Backward / posterior counts) on dnapsw 1 kb pairs, one GPU's share
+    mj = eval_machine("dnapsw")
+    mach = make_machine(capi, mj)
+    n = args.em_pairs
+    x, x_off, y, y_off = synth_batch(SEED, 0, n, 1000, 1000, 4)
+    b = capi.Batch(x=x, x_off=x_off, y=y, y_off=y_off)
+    r = timed_passes(capi, mach, b, ["counts"])
+    t = r["counts"][0]
+    algo_bytes = 2.0 * 16.0 * 1001 * 1001 * n * 1.03      # 16-byte stored Forward cells written once and read once (+3 % ramps)
+    entry("cfg2", "preset dnapsw Baum-Welch E-step (Forward stored + Backward fused with posterior counts), 10 000 pairs of 1 kb over 8 GPUs",
+          "%d pairs of 1000 x 1000 on one GPU (the config's share per GPU is 1250)" % n, mj, b, n, r,
+          {"counts_sum_per_pair": float(r["counts"][1][0].sum()) / n,
+           "roofline": {"bound": "hbm", "achieved": algo_bytes / t["kernel_ms"] / 1e6, "peak": hbm, "unit": "GB/s", "frac": algo_bytes / t["kernel_ms"] / 1e6 / hbm}})
+    b.close(); mach.close()
+
+    # config 3: protpsw Viterbi alignment, 300 aa pairs
+    mj = eval_machine("protpsw")
+    mach = make_machine(capi, mj)
+    n = args.cfg3_pairs
+    x, x_off, y, y_off = synth_batch(SEED + 3, 0, n, 300, 300, 20)
+    b = capi.Batch(x=x, x_off=x_off, y=y, y_off=y_off)
+    entry("cfg3", "preset protpsw Viterbi alignment (score + traceback), 100 000 pairs of 300 aa", "%d pairs of 300 x 300" % n, mj, b, n,
+          timed_passes(capi, mach, b, ["viterbi", "forward"]))
+    b.close(); mach.close()
+
+    # config 4: the GeneWise-style composite, protein against 10 kb of DNA
+    mj = eval_machine("prot2dna_dnapsw")
+    mach = make_machine(capi, mj)
+    n = args.cfg4_pairs
+    x, x_off, _, _ = synth_batch(SEED + 4, 0, n, 300, 300, mj["n_in"])
+    _, _, y, y_off = synth_batch(SEED + 4, 0, n, 10000, 10000, mj["n_out"])
+    b = capi.Batch(x=x, x_off=x_off, y=y, y_off=y_off)
+    entry("cfg4", "prot2dna => dnapsw (308 states), Forward + Viterbi, 1000 pairs of 300 aa x 10 kb", "%d pairs of 300 aa x 10 000 nt" % n, mj, b, n,
+          timed_passes(capi, mach, b, ["forward", "viterbi_score", "viterbi"], reps=1))
+    b.close(); mach.close()
+
+    # config 5: a profile HMM composed with an error model scoring reads of 50 - 500 residues (length-bucketed inside the engine)
+    for preset, n in (("PF00516", args.cfg5_reads), ("PF00516_protpsw", args.cfg5_reads // 4)):
+        mj = eval_machine(preset)
+        mach = make_machine(capi, mj)
+        lens = 50 + (np.arange(n, dtype=np.int64) * 7919) % 451
+        y, y_off = synth_ragged(SEED + 5, lens, mj["n_out"])
+        b = capi.Batch(x=np.zeros(0, np.uint8), x_off=np.zeros(n + 1, np.int64), y=y, y_off=y_off)
+        entry("cfg5" if preset == "PF00516_protpsw" else "cfg5-core",
+              "HMMER profile %s (%d states), Forward + Viterbi on 1 000 000 reads of 50 - 500 residues" % (preset.replace("_", " => "), mj["n_states"]),
+              "%d reads, lengths 50 - 500 (uniform, ragged)" % n, mj, b, n, timed_passes(capi, mach, b, ["forward", "viterbi_score"], reps=1))
+        b.close(); mach.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -111,6 +111,14 @@ int mb_viterbi_paths (mb_batch* b, int32_t* pathTrans, const int64_t* pathOff);
  * pathOff[k] .. pathOff[k] + pathLen[k]. */
 int mb_viterbi_paths_narrow (mb_batch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff);
 
+/* The same copy without waiting for it: the ids are narrowed on the batch's stream and handed to the copy engine;
+ * the call returns at once, later calls on the batch (an mb_forward of the same pairs, say) run while the paths
+ * travel, and mb_batch_wait returns when they have arrived.  pathTrans should be page-locked host memory (with
+ * pageable memory the call simply blocks); it must not be read before mb_batch_wait.  Offsets that are not the
+ * packed order of the batch (pathOff[k+1] - pathOff[k] == pathLen[k]) take the blocking path. */
+int mb_viterbi_paths_start (mb_batch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff);
+int mb_batch_wait (mb_batch* b);
+
 /* ---- MachineCounts over a list (src/counts.cpp:37-64, src/backward.cpp:62-87) ----
  * counts[t] (t < nTrans, may be NULL) receives the expected number of uses of transition t summed
  * over all pairs; loglike[k] (may be NULL) the Forward log-likelihood of pair k.  Pairs whose

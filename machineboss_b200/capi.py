@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables",
+           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_viterbi_paths_start", "mb_batch_wait", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables",
            "mb_shard_pairs", "mb_group_create", "mb_group_info", "mb_group_destroy", "mb_group_machine_create", "mb_group_machine_update_weights",
            "mb_group_machine_set_option", "mb_group_machine_info", "mb_group_machine_destroy", "mb_group_batch_create", "mb_group_batch_set_envelopes",
            "mb_group_batch_shard", "mb_group_batch_destroy", "mb_group_forward", "mb_group_backward", "mb_group_viterbi", "mb_group_viterbi_paths",
@@ -61,6 +61,8 @@ def lib():
         L.mb_viterbi.argtypes = [P, P, P, P]
         L.mb_viterbi_paths.argtypes = [P, P, P]
         L.mb_viterbi_paths_narrow.argtypes = [P, P, I32, P]
+        L.mb_viterbi_paths_start.argtypes = [P, P, I32, P]
+        L.mb_batch_wait.argtypes = [P]
         L.mb_counts.argtypes = [P, P, P, P]
         L.mb_matrix.argtypes = [P, P, I64, I32, P]
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
@@ -231,6 +233,9 @@ class Batch:
     def trim(self):
         _check(lib().mb_batch_trim(self.h))
 
+    def wait(self):
+        _check(lib().mb_batch_wait(self.h))
+
     def last_kernel_ms(self):
         ms, n = ctypes.c_double(0), ctypes.c_int64(0)
         _check(lib().mb_last_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(n)))
@@ -307,6 +312,20 @@ def viterbi_into(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off:
         else:      # uint8 / uint16 ids (machines with at most 256 / 65 536 transitions)
             assert trans.dtype in (np.uint8, np.uint16)
             _check(lib().mb_viterbi_paths_narrow(b.h, _ptr(trans), trans.dtype.itemsize, _ptr(off)))
+    return total
+
+
+def viterbi_start(m: Machine, b: Batch, score: np.ndarray, plen: np.ndarray, off: np.ndarray, trans: np.ndarray) -> int:
+    """viterbi_into without waiting for the paths: they are on their way into `trans` (page-locked memory) when this
+    returns, other calls on the batch may follow, and b.wait() returns once they have arrived."""
+    _check(lib().mb_viterbi(m.h, b.h, _ptr(score), _ptr(plen)))
+    off[0] = 0
+    np.cumsum(plen[: b.n_pairs], out=off[1: b.n_pairs + 1])
+    total = int(off[b.n_pairs])
+    if total > trans.size:
+        raise MachineBossError("viterbi_start: path buffer too small (%d > %d)" % (total, trans.size))
+    if total:
+        _check(lib().mb_viterbi_paths_start(b.h, _ptr(trans), trans.dtype.itemsize, _ptr(off)))
     return total
 
 

@@ -20,11 +20,10 @@ static thread_local Options g_options;
 
 static const char* const kOptionNames[] = {
   "verbose",                                                  // 1: engines report their launch geometry and flags on stderr
-  "jit_narrow", "jit_no_linear", "jit_c", "jit_cv", "jit_minblocks", "jit_minblocks_v", "jit_minblocks_lin", "jit_minblocks_cnt", "jit_threads",
+  "jit_narrow", "jit_no_linear", "jit_c", "jit_cv", "jit_minblocks", "jit_minblocks_v", "jit_minblocks_linv", "jit_minblocks_lin", "jit_minblocks_cnt", "jit_threads",
   "jit_tb_budget_mb", "jit_f_budget_mb",                      // cap on one chunk of back-pointer / stored-Forward scratch (tests force several chunks)
   "jit_chunks",                                               // pairs of a Viterbi call are traced back and copied out in this many pipeline stages
   "jit_no_norm",                                              // 1: never use the normalised linear kernels (score module)
-  "jit_vit_intcmp",                                           // 0: Viterbi always compares in FP64
   "jit_unroll",                                               // unroll factor of the steady-state step loop (1 - 4)
   "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
   "lane_r", "lane_warps", "no_lane", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
@@ -532,6 +531,8 @@ void mb_batch_destroy (mb_batch* b) {
   pooled_free (b->device, b->dTokBlock, b->tokBytes);
   pooled_free (b->device, b->dPaths, b->pathsBytes);
   ws_release_all (b);
+  if (b->copyStream) { cudaStreamSynchronize (b->copyStream); cudaStreamDestroy (b->copyStream); }
+  if (b->evCopy) cudaEventDestroy (b->evCopy);
   if (b->evStart) cudaEventDestroy (b->evStart);
   if (b->evStop) cudaEventDestroy (b->evStop);
   if (b->stream) cudaStreamDestroy (b->stream);
@@ -586,6 +587,7 @@ int mb_backward (mb_machine* m, mb_batch* b, double* loglike) {
 
 int mb_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (check_call (m, b)) return 1;
+  if (b->copyStream) MB_CUDA (cudaStreamSynchronize (b->copyStream));      // paths of the previous call still on their way out
   b->pathIdLimit = m->T;
   if (use_jit (m, b)) return jit_viterbi (m, b, score, pathLen);
   const int w = use_wide (m, b);
@@ -641,6 +643,45 @@ int mb_viterbi_paths_narrow (mb_batch* b, void* pathTrans, int32_t bytesPerId, c
   MB_CUDA (cudaStreamSynchronize (b->stream));
   for (int64_t k = 0; k < b->nPairs; ++k)
     memcpy ((char*) pathTrans + pathOff[k] * bytesPerId, host.data() + b->pathStart[k] * bytesPerId, (size_t) b->pathLen[k] * bytesPerId);
+  return 0;
+}
+
+int mb_viterbi_paths_start (mb_batch* b, void* pathTrans, int32_t bytesPerId, const int64_t* pathOff) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if ((int64_t) b->pathLen.size() != b->nPairs) { set_error ("mb_viterbi_paths_start: no traceback stored; call mb_viterbi with pathLen first"); return 1; }
+  if (bytesPerId != 1 && bytesPerId != 2 && bytesPerId != 4) { set_error ("mb_viterbi_paths_start: bytesPerId must be 1, 2 or 4"); return 1; }
+  if (bytesPerId < 4 && b->pathIdLimit > (bytesPerId == 1 ? 256 : 65536)) { set_error ("mb_viterbi_paths_start: the machine's transition ids do not fit in " + std::to_string (bytesPerId) + " byte(s)"); return 1; }
+  int64_t total = 0;
+  for (int64_t k = 0; k < b->nPairs; ++k) total += b->pathLen[k];
+  bool contiguous = true;
+  for (int64_t k = 0; k < b->nPairs && contiguous; ++k) contiguous = (pathOff[k] - pathOff[0] == b->pathStart[k]);
+  if (!contiguous) return mb_viterbi_paths_narrow (b, pathTrans, bytesPerId, pathOff);      // scattered offsets: the blocking path
+  if (!total) return 0;
+  MB_CUDA (cudaSetDevice (b->device));
+  if (!b->copyStream) {
+    MB_CUDA (cudaStreamCreateWithFlags (&b->copyStream, cudaStreamNonBlocking));
+    MB_CUDA (cudaEventCreateWithFlags (&b->evCopy, cudaEventDisableTiming));
+  }
+  const void* src = b->dPaths;
+  if (bytesPerId < 4) {
+    void* tmp = ws_reserve (b, WS_PATHNARROW, (size_t) total * bytesPerId);
+    if (!tmp) return 1;
+    const unsigned grid = (unsigned) std::min<int64_t> ((total + 255) / 256, 148 * 16);
+    if (bytesPerId == 1) narrow_ids_kernel<uint8_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint8_t*) tmp, total);
+    else narrow_ids_kernel<uint16_t><<<grid, 256, 0, b->stream>>> (b->dPaths, (uint16_t*) tmp, total);
+    MB_CUDA (cudaGetLastError());
+    src = tmp;
+  }
+  // the copy engine takes it from here; later kernels on the batch's stream do not wait for it (they never write the paths)
+  MB_CUDA (cudaEventRecord (b->evCopy, b->stream));
+  MB_CUDA (cudaStreamWaitEvent (b->copyStream, b->evCopy, 0));
+  MB_CUDA (cudaMemcpyAsync ((char*) pathTrans + pathOff[0] * bytesPerId, src, (size_t) total * bytesPerId, cudaMemcpyDeviceToHost, b->copyStream));
+  return 0;
+}
+
+int mb_batch_wait (mb_batch* b) {
+  if (!b) { set_error ("null batch"); return 1; }
+  if (b->copyStream) MB_CUDA (cudaStreamSynchronize (b->copyStream));
   return 0;
 }
 

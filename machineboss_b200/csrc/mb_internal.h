@@ -128,6 +128,8 @@ struct mb_batch {
   std::vector<int64_t> envOff, envStart, envEnd;   // host copies
   mb::DevBatch dev {};
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;   // results on their way to the host while the next call's kernels run (mb_viterbi_paths_start)
+  cudaEvent_t evCopy = nullptr;
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   double lastMs = 0;
   int64_t lastLaunches = 0;

@@ -224,21 +224,18 @@ struct JitEngine {
   // FP64 range on ordinary pairs, so in that module the linear sweeps keep a frame per lane
   // (MB_LANE_FRAMES); the E-step kernels, whose stored Forward blocks share a frame per warp, stay at C.
   int CV = 4, minBlocksV = 4;
+  int minBlocksLinV = 4;      // the score module's normalised sums: 4 CTAs per SM at 128 registers beat 3 at 168 (8.33 against 8.80 ms)
   // the same three kernels at C columns per lane (first module): chosen per call for batches whose pairs
   // would leave most of a 32 * CV column strip empty (300 aa proteins: 2 strips of 256 against 3 of 128)
   CUfunction kViterbiN = nullptr, kForwardLinN = nullptr, kBackwardLinN = nullptr, kViterbiScoreN = nullptr;
   int blocksPerSMN[4] = { 1, 1, 1, 1 };
   CUfunction kViterbiScore = nullptr;      // Viterbi without back-pointers (mb_viterbi with pathLen == NULL, boss -V)
-  CUfunction kViterbiI = nullptr, kViterbiScoreI = nullptr;      // score module: the same two with integer compares (no weight above 1)
-  CUfunction kViterbiI2 = nullptr, kViterbiScoreI2 = nullptr;    // ... and with every other compare an integer one (both pipes share the work)
-  int vitIcmp = 4;                        // which of the three the machine's calls use when eligible: 0, 2 or 4
   // score module: row-layout tables (Program::WA) -- log weights for Viterbi, normalised linear weights for the sums
   double* dRowVit = nullptr;
   double* dRowFLinN = nullptr;
   double* dRowBLinN = nullptr;
   std::vector<char> silParamLinN;         // MBSilN { f[], b[], originF, originB, resLogF, resLogB }
   bool normOK = false;                    // every unit group's weight is usable: the normalised linear kernels may run
-  bool nonPositive = false;               // no finite log-weight above 0: Viterbi may compare bit patterns
   std::string sourceV;
   // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
   // start state); the others follow from them inside the cell through the silent groups
@@ -249,8 +246,8 @@ struct JitEngine {
   std::string source;
   CUmodule mod = nullptr;
   CUfunction kForward = nullptr, kBackward = nullptr, kViterbi = nullptr, kFStore = nullptr, kBCounts = nullptr;
-  int blocksPerSM[14] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };      // index 9: mb_k_viterbi_score, 10 / 11: mb_k_viterbi_i / _score_i, 12 / 13: _i2 / _score_i2
-  size_t smemBytes[14] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  int blocksPerSM[10] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };      // index 9: mb_k_viterbi_score
+  size_t smemBytes[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   int nCtx = 0;                          // thread-private count accumulators per lane (backward program's emitting slots)
   std::vector<int> ctxBase;              // per backward slot, -1 for silent
   int32_t* dIdTabB = nullptr;
@@ -335,15 +332,16 @@ static std::string source_expr (const Slot& s) {
   return e.str();
 }
 
-// Viterbi: FP64 add + compare in the reference's candidate order.  ICMP of every four compares (0, 2 or 4) are
-// done on the bit patterns as unsigned integers instead, i.e. on the integer pipe -- valid when no value can be
-// positive: a < b <=> bits (a) > bits (b) for a, b in [-inf, +0] -- which takes them off the FP64 pipe, where a
-// compare costs two adds' worth of cycles
+// Viterbi: FP64 add + compare in the reference's candidate order.  PTR = also record which candidate won: the
+// pointer field of the state goes straight into the step's packed words (pk, the cell's word starting at bit sh:
+// a constant once the column loop is unrolled) under the compare's own predicate -- mb_vmax is one compare, the
+// select of the value and ONE predicated logic instruction, with no per-cell word to build, shift and merge.
+// (Comparing the bit patterns on the integer pipe instead -- valid when no log-weight is positive -- was measured
+// slower: 17.2 against 15.9 ms for 10 000 dnapsw pairs of 1 kb; an integer compare of two doubles is two
+// instructions and the sweep is short of issue slots, not of FP64 cycles.)
 static void gen_cell_row_vit (std::ostringstream& o, const mb_machine* m, const Program& p, const JitEngine& J) {
-  int compareNo = 0;
-  o << "template<int ICMP> __device__ __forceinline__ mb_tbword mb_cell_vitr (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], "
-       "const unsigned ea, const unsigned em, const unsigned ebr, const bool origin, const bool sink, const MBSil& P) {\n";
-  o << "  mb_tbword word = 0;\n";
+  o << "template<bool PTR> __device__ __forceinline__ void mb_cell_vitr (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], "
+       "const unsigned ea, const unsigned em, const unsigned ebr, const bool origin, const bool sink, const MBSil& P, unsigned (&pk)[MB_PKW], const int sh) {\n";
   std::vector<char> isSource ((size_t) m->S, 0);
   for (auto& sl: p.slots) isSource[sl.other] = 1;
   for (int d = 0; d < m->S; ++d) {
@@ -358,15 +356,17 @@ static void gen_cell_row_vit (std::ostringstream& o, const mb_machine* m, const 
       if (sl.type == T_SILENT) t << "P.f[" << sl.silIdx << "]"; else t << row_weight (sl, p.rowOff[k]);
       if (k == s0) o << (sinkOnly ? "  n" : "  double n") << d << " = " << t.str() << ";\n";
       else {
-        const unsigned long long field = ((1ull << J.bits[d]) - 1ull) << J.shift[d], val = (unsigned long long) (k - s0) << J.shift[d];
-        o << "  { const double t = " << t.str() << "; if (mb_lt<((" << (compareNo++ & 3) << ") < ICMP)> (n" << d << ", t)) { n" << d << " = t; word = (word & (mb_tbword) " << (~field) << "ull) | (mb_tbword) " << val << "ull; } }\n";
+        // the field never straddles a 32-bit word (see generate()): word index and shift inside it
+        const unsigned field = (unsigned) ((1ull << J.bits[d]) - 1ull), val = (unsigned) (k - s0);
+        o << "  mb_vmax<PTR> (n" << d << ", " << t.str() << ", pk[(sh + " << J.shift[d] << ") >> 5], " << field << "u << ((sh + " << J.shift[d] << ") & 31), "
+          << val << "u << ((sh + " << J.shift[d] << ") & 31));\n";
       }
     }
     if (sinkOnly) o << "  }\n";
     if (d == 0) o << "  if (origin) n" << d << " = 0.0;\n";
   }
   for (int d = 0; d < m->S; ++d) o << "  N[" << d << "] = n" << d << ";\n";
-  o << "  return word;\n}\n\n";
+  o << "}\n\n";
 }
 
 // Linear domain, normalised: the unit group of a state is a plain copy, every other group one multiply-add
@@ -574,7 +574,12 @@ bool jit_supported (const mb_machine* m, std::string* why) {
   if (f.nEmit > 3072 || b.nEmit > 3072) return no ("emission tables exceed 24 KB of shared memory");
   if (f.nSil + b.nSil > 400) return no ("too many silent transitions for the kernel-parameter block");
   int totalBits = 0;
-  for (int s = 0; s < m->S; ++s) { const int n = f.stateSlot0[s + 1] - f.stateSlot0[s]; int bt = 0; while ((1 << bt) < n) ++bt; totalBits += bt; }
+  for (int s = 0; s < m->S; ++s) {
+    const int n = f.stateSlot0[s + 1] - f.stateSlot0[s];
+    int bt = 0; while ((1 << bt) < n) ++bt;
+    if (bt && (totalBits >> 5) != ((totalBits + bt - 1) >> 5)) totalBits = (totalBits + 31) & ~31;      // as in generate()
+    totalBits += bt;
+  }
   if (totalBits > 64) return no ("Viterbi back-pointers need more than 64 bits per cell");
   { const int C = m->S <= 8 ? 4 : 2; int n = 0; for (auto& sl: b.slots) n += ctx_count (sl.type, C, m->nOut); if (n > 160) return no ("too many emitting transition groups for the per-lane count accumulators"); }
   return true;
@@ -624,10 +629,6 @@ static int compile (mb_machine* m, JitEngine& J) {
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBackwardLin, J.modV ? J.modV : J.mod, "mb_k_backward_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kFStoreLin, J.mod, "mb_k_fstore_lin"), "cuModuleGetFunction")
       || !cu_ok (g_drv.ModuleGetFunction (&J.kBCountsLin, J.mod, "mb_k_bcounts_lin"), "cuModuleGetFunction")) return 1;
-  if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiI, J.modV, "mb_k_viterbi_i"), "cuModuleGetFunction")
-                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreI, J.modV, "mb_k_viterbi_score_i"), "cuModuleGetFunction")
-                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiI2, J.modV, "mb_k_viterbi_i2"), "cuModuleGetFunction")
-                 || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreI2, J.modV, "mb_k_viterbi_score_i2"), "cuModuleGetFunction"))) return 1;
   if (J.modV && (!cu_ok (g_drv.ModuleGetFunction (&J.kViterbiN, J.mod, "mb_k_viterbi"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kViterbiScoreN, J.mod, "mb_k_viterbi_score"), "cuModuleGetFunction")
                  || !cu_ok (g_drv.ModuleGetFunction (&J.kForwardLinN, J.mod, "mb_k_forward_lin"), "cuModuleGetFunction")
@@ -635,12 +636,9 @@ static int compile (mb_machine* m, JitEngine& J) {
   int dev = 0;
   MB_CUDA (cudaGetDevice (&dev));
   MB_CUDA (cudaDeviceGetAttribute (&J.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  CUfunction fn[14] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin, J.kViterbiScore,
-                        J.kViterbiI, J.kViterbiScoreI, J.kViterbiI2, J.kViterbiScoreI2 };
-  const int ne[14] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.fwd.nEmit,
-                       J.fwd.nEmit, J.fwd.nEmit };
-  for (int q = 0; q < 14; ++q) {
-    if (!fn[q]) continue;      // (the integer-compare kernels exist in the score module only)
+  CUfunction fn[10] = { J.kForward, J.kBackward, J.kViterbi, J.kFStore, J.kBCounts, J.kForwardLin, J.kBackwardLin, J.kFStoreLin, J.kBCountsLin, J.kViterbiScore };
+  const int ne[10] = { J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit, J.bwd.nEmit, J.fwd.nEmit };
+  for (int q = 0; q < 10; ++q) {
     const bool needAcc = q == 4 || q == 8;      // only the count kernels use the per-lane accumulators (FP32 / FP64)
     J.smemBytes[q] = (size_t) (((ne[q] + 1) & ~1) + (J.threads / 32) * (16 + 32 * (m->S + 1))) * 8
       + (needAcc ? (size_t) (J.threads / 32) * 32 * std::max (J.nCtx, 1) * (q == 8 ? 8 : 4) : 0)
@@ -772,10 +770,6 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
   for (double w: m->lw) if (std::isfinite (w) && std::fabs (w) > 24.0 * 0.6931471805599453) J.linearOK = false;
   for (double w: m->lw) if (std::isnan (w) || w == INFINITY) J.linearOK = false;
   if (m->opt.get ("jit_no_linear", 0)) J.linearOK = false;
-  // Viterbi may compare bit patterns as integers when no path score can be positive
-  J.nonPositive = true;
-  for (double w: m->lw) if (!(w <= 0.)) J.nonPositive = false;      // (NaN fails too)
-  if (m->opt.has ("jit_vit_intcmp")) { const int v = m->opt.get ("jit_vit_intcmp", 4); J.vitIcmp = v >= 4 ? 4 : v >= 2 ? 2 : 0; }
 }
 
 // score module: row-layout tables and the parameter block of the normalised linear kernels
@@ -837,6 +831,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (int s = 0; s < m->S; ++s) {
     const int n = J.fwd.stateSlot0[s + 1] - J.fwd.stateSlot0[s];
     int bt = 0; while ((1 << bt) < n) ++bt;
+    if (bt && (totalBits >> 5) != ((totalBits + bt - 1) >> 5)) totalBits = (totalBits + 31) & ~31;      // a field stays inside one 32-bit word
     J.shift[s] = totalBits; J.bits[s] = bt; totalBits += bt;
   }
   J.tbBytes = totalBits <= 8 ? 1 : totalBits <= 16 ? 2 : totalBits <= 32 ? 4 : 8;
@@ -848,6 +843,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   if (m->opt.has ("jit_cv")) J.CV = std::max (1, std::min (8, m->opt.get ("jit_cv", 8)));
   while (J.CV * J.tbBytes > 16) J.CV /= 2;
   if (m->opt.has ("jit_minblocks_v")) J.minBlocksV = std::max (1, std::min (16, m->opt.get ("jit_minblocks_v", 3)));
+  J.minBlocksLinV = std::max (J.minBlocksV, 4);
+  if (m->opt.has ("jit_minblocks_linv")) J.minBlocksLinV = std::max (1, std::min (16, m->opt.get ("jit_minblocks_linv", 4)));
   if (m->opt.has ("jit_minblocks")) J.minBlocks = std::max (1, std::min (16, m->opt.get ("jit_minblocks", 4)));
   if (m->opt.has ("jit_minblocks_cnt")) J.minBlocksCnt = std::max (1, std::min (16, m->opt.get ("jit_minblocks_cnt", 4)));
   if (m->opt.has ("jit_minblocks_lin")) J.minBlocksLin = std::max (1, std::min (16, m->opt.get ("jit_minblocks_lin", 5)));
@@ -865,7 +862,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
   if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n#define MB_ROWTAB 1\n";
-  o << "#define MB_STEADY_UNROLL " << std::max (1, std::min (4, m->opt.get ("jit_unroll", 1))) << "\n";
+  o << "#define MB_STEADY_UNROLL " << std::max (1, std::min (4, m->opt.get ("jit_unroll", pass ? 2 : 1))) << "\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
   o << "#define MB_NEMIT_F " << J.fwd.nEmit << "\n#define MB_NEMIT_B " << J.bwd.nEmit << "\n#define MB_TBBYTES " << J.tbBytes << "\n#define MB_THREADS " << J.threads << "\n";
@@ -873,7 +870,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << (pass ? J.minBlocksV : J.minBlocksLin) << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
+  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << (pass ? J.minBlocksLinV : J.minBlocksLin) << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
@@ -887,10 +884,15 @@ static void generate (const mb_machine* m, JitEngine& J) {
     o << "#ifndef MB_LDS\n"
          "template<int OFF> __device__ __forceinline__ double mb_lds (const unsigned addr) { double v; asm (\"ld.shared.f64 %0, [%1+%2];\" : \"=d\"(v) : \"r\"(addr), \"n\"(OFF)); return v; }\n"
          "#define MB_LDS(addr, off) mb_lds<off> (addr)\n#endif\n";
+    o << "#define MB_PKW " << (J.CV * J.tbBytes + 3) / 4 << "      // 32-bit words of packed back-pointers per lane and step\n";
     o << "#ifndef MB_HOST_HARNESS\n"
-         "template<bool ICMP> __device__ __forceinline__ bool mb_lt (const double a, const double b) {      // a < b\n"
-         "  if (ICMP) return (unsigned long long) __double_as_longlong (a) > (unsigned long long) __double_as_longlong (b);      // a, b in [-inf, +0]: the order of the bit patterns, reversed\n"
-         "  return a < b;\n}\n#endif\n\n";
+         "// n = max (n, t) with the reference's tie-break (a later candidate wins only if strictly greater); with PTR the\n"
+         "// winner's field value replaces the field in `word`: (word & ~field) | val, or a plain OR for a one-bit field\n"
+         "template<bool PTR> __device__ __forceinline__ void mb_vmax (double& n, const double t, unsigned& word, const unsigned field, const unsigned val) {\n"
+         "  if (!PTR) { if (n < t) n = t; return; }\n"
+         "  if (field == val) asm (\"{ .reg .pred p; setp.lt.f64 p, %0, %2; selp.f64 %0, %2, %0, p; @p or.b32 %1, %1, %3; }\" : \"+d\"(n), \"+r\"(word) : \"d\"(t), \"r\"(val));\n"
+         "  else asm (\"{ .reg .pred p; setp.lt.f64 p, %0, %2; selp.f64 %0, %2, %0, p; @p lop3.b32 %1, %1, %3, %4, 0xEA; }\" : \"+d\"(n), \"+r\"(word) : \"d\"(t), \"r\"(~field), \"r\"(val));\n"
+         "}\n#endif\n\n";
     gen_cell_row_vit (o, m, J.fwd, J);
     gen_cell_row_lin (o, m, J.fwd, true);
     gen_cell_row_lin (o, m, J.bwd, false);
@@ -933,7 +935,7 @@ int jit_host_tables (const mb_machine* m, int which, std::vector<double>& out) {
     out.insert (out.end(), f.silN.begin(), f.silN.begin() + nf);
     out.insert (out.end(), b.silN.begin(), b.silN.begin() + nb);
     out.push_back (f.originInv); out.push_back (b.originInv); out.push_back (f.resLog); out.push_back (b.resLog);
-  } else if (which == 5) { out.push_back (f.ok && b.ok && J.linearOK ? 1. : 0.); out.push_back (J.nonPositive ? 1. : 0.); }
+  } else if (which == 5) out.push_back (f.ok && b.ok && J.linearOK ? 1. : 0.);
   else { set_error ("mb_jit_host_tables: which must be 0..5"); return 1; }
   return 0;
 }
@@ -1063,10 +1065,8 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   if (J.modV && (which == 5 || which == 6) && !J.normOK) narrow = true;
   narrow = narrow && J.modV && scoreKernel;
   const bool rowTab = J.modV && scoreKernel && !narrow;      // score module: row-layout tables
-  const int icmp = (rowTab && (which == 2 || which == 9) && J.nonPositive) ? J.vitIcmp : 0;      // how many of four Viterbi compares go to the integer pipe
-  const int slot = icmp ? (which == 2 ? 10 : 11) + (icmp == 2 ? 2 : 0) : which;      // index into blocksPerSM / smemBytes
+  const int slot = which;
   CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : which == 6 ? J.kBackwardLinN : J.kViterbiScoreN)
-    : icmp == 4 ? (which == 2 ? J.kViterbiI : J.kViterbiScoreI) : icmp == 2 ? (which == 2 ? J.kViterbiI2 : J.kViterbiScoreI2)
     : which == 9 ? J.kViterbiScore : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
   const bool lin = which >= 5 && which <= 8;      // 9: the score-only Viterbi, log domain
   int64_t maxLo = 0;
@@ -1098,7 +1098,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, icmp ? " (integer compares)" : rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
+    fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
              J.smemBytes[which], J.blocksPerSM[slot], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { (rowTab && lin) ? (void*) J.silParamLinN.data() : lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;

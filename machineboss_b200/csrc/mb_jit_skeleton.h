@@ -122,7 +122,7 @@ template<int DIR> __device__ __forceinline__ constexpr bool mb_live (int s) { re
 // MODE 3: Backward fused with the posterior-count accumulation of BackwardMatrix::getCounts
 //         (backward.cpp:62-87): each transition group's term w + B(dest) is formed once and used
 //         both for the Backward log-sum-exp and for exp(F(src) - ll + term).
-template<int MODE, int DIR, int ICMP = 0>
+template<int MODE, int DIR>
 __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
@@ -267,6 +267,11 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
           for (int s = 0; s < MB_S; ++s) { Dc[s] = Lk[s]; Lk[s] = Lc[s]; }
           unsigned long long pack0 = 0, pack1 = 0;
           unsigned pack32 = 0;
+#ifdef MB_ROWTAB
+          unsigned pk[MB_PKW];      // the step's packed back-pointers, filled field by field inside the cells
+#pragma unroll
+          for (int q = 0; q < MB_PKW; ++q) pk[q] = 0u;
+#endif
 #pragma unroll
           for (int c = 0; c < MB_C; ++c) {
             double N[MB_S];
@@ -298,22 +303,27 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
               mb_cell_cnt (Dc, Lc, U[c], N, ta[c], tokb, origin, E, P, Fc, cs, acc, c);
             } else {
 #ifdef MB_ROWTAB
-              const mb_tbword word = mb_cell_vitr<ICMP> (Dc, Lc, U[c], N, ea[c], ea[c] + eb8, ebr, origin, !STEADY && r == Lo && col0 + c == Li, P);
+              mb_cell_vitr<MODE == 1> (Dc, Lc, U[c], N, ea[c], ea[c] + eb8, ebr, origin, !STEADY && r == Lo && col0 + c == Li, P, pk, 8 * MB_TBBYTES * c);
 #else
               const mb_tbword word = mb_cell_vit (Dc, Lc, U[c], N, ta[c], tokb, origin, !STEADY && r == Lo && col0 + c == Li, E, P);
-#endif
               if (MODE == 1) {
                 const int sh = 8 * MB_TBBYTES * c;
                 if (MB_C * MB_TBBYTES <= 4) pack32 |= (unsigned) word << (sh & 31);
                 else if (sh < 64) pack0 |= (unsigned long long) word << (sh & 63);
                 else pack1 |= (unsigned long long) word << ((sh - 64) & 63);
               }
+#endif
             }
 #pragma unroll
             for (int s = 0; s < MB_S; ++s) { Dc[s] = U[c][s]; U[c][s] = N[s]; Lc[s] = N[s]; }
           }
           if (MODE == 1) {
             uint8_t* p = tbRow;
+#ifdef MB_ROWTAB
+            pack32 = pk[0];
+            pack0 = MB_PKW > 1 ? (unsigned long long) pk[0] | ((unsigned long long) pk[MB_PKW > 1 ? 1 : 0] << 32) : pk[0];
+            pack1 = MB_PKW > 3 ? (unsigned long long) pk[MB_PKW > 3 ? 2 : 0] | ((unsigned long long) pk[MB_PKW > 3 ? 3 : 0] << 32) : 0ull;
+#endif
             if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack32;
             else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack32;
             else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = pack32;
@@ -359,14 +369,6 @@ extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS_CNT) mb_k_
 #endif
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0> (P, A); }
 extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0> (P, A); }
-#ifdef MB_ROWTAB
-// the same two with the compares done on the bit patterns (integer pipe): only launched when no log-weight is positive
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_i (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0, 4> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score_i (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0, 4> (P, A); }
-// ... and with two of every four compares there, the other two on the FP64 pipe
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_i2 (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<1, 0, 2> (P, A); }
-extern "C" __global__ void __launch_bounds__(MB_THREADS, MB_MINBLOCKS) mb_k_viterbi_score_i2 (const __grid_constant__ MBSil P, const __grid_constant__ MBArgs A) { mb_run<4, 0, 2> (P, A); }
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // Scaled linear-domain sweep (Forward for DIR 0, Backward for DIR 1).

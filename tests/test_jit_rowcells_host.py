@@ -6,8 +6,7 @@ scales), then compared with the oracle.  What it pins without a GPU:
   * the linear-domain normalisation (a state's first silent group becomes a plain copy; every other weight is
     scaled by sigma_src / sigma_self; the result carries log sigma of the end state): Forward and Backward values
     must be the exact sums;
-  * the Viterbi cell with 0, 2 and 4 of every four compares done on the bit patterns as unsigned integers:
-    bit-identical scores in all three.
+  * the Viterbi cell, score-only and with the pointer fields recorded: bit-identical scores.
 The skewed sweep around the cells is the job of the -m gpu tests."""
 import os
 import struct
@@ -32,9 +31,8 @@ static const char* hostE = nullptr;      // the table the cell reads: addresses 
 #define MB_LDS(addr, off) (*(const double*) (hostE + (addr) + (off)))
 static inline double __longlong_as_double (long long v) { double d; memcpy (&d, &v, 8); return d; }
 static inline long long __double_as_longlong (double d) { long long v; memcpy (&v, &d, 8); return v; }
-template<bool ICMP> static inline bool mb_lt (const double a, const double b) {
-  if (ICMP) return (unsigned long long) __double_as_longlong (a) > (unsigned long long) __double_as_longlong (b);
-  return a < b;
+template<bool PTR> static inline void mb_vmax (double& n, const double t, unsigned& word, const unsigned field, const unsigned val) {
+  if (n < t) { n = t; if (PTR) word = (word & ~field) | val; }
 }
 static inline double mb_neg_inf() { return -INFINITY; }
 %(cells)s
@@ -73,18 +71,18 @@ int main (int argc, char** argv) {
   MBSilN PN;
   memcpy (&PN, silN.data(), sizeof PN);
   double out[MB_S];
-  // Viterbi, three compare mixes
+  // Viterbi: score only, and with the pointer fields recorded at the first and at the last column's position of the packed words
   double vit[3];
   int q = 0;
   hostE = (const char*) rowLog.data();
   sweep (x, y, false, -INFINITY, MB_WA_F, MB_WB_F, 0, [&] (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], unsigned ea, unsigned em, unsigned ebr, bool origin, bool sink) {
-    mb_cell_vitr<0> (D, L, U, N, ea, em, ebr, origin, sink, P); }, out);
+    unsigned pk[MB_PKW] = { 0 }; mb_cell_vitr<false> (D, L, U, N, ea, em, ebr, origin, sink, P, pk, 0); }, out);
   vit[q++] = out[MB_S - 1];
   sweep (x, y, false, -INFINITY, MB_WA_F, MB_WB_F, 0, [&] (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], unsigned ea, unsigned em, unsigned ebr, bool origin, bool sink) {
-    mb_cell_vitr<2> (D, L, U, N, ea, em, ebr, origin, sink, P); }, out);
+    unsigned pk[MB_PKW] = { 0 }; mb_cell_vitr<true> (D, L, U, N, ea, em, ebr, origin, sink, P, pk, 0); }, out);
   vit[q++] = out[MB_S - 1];
   sweep (x, y, false, -INFINITY, MB_WA_F, MB_WB_F, 0, [&] (const double (&D)[MB_S], const double (&L)[MB_S], const double (&U)[MB_S], double (&N)[MB_S], unsigned ea, unsigned em, unsigned ebr, bool origin, bool sink) {
-    mb_cell_vitr<4> (D, L, U, N, ea, em, ebr, origin, sink, P); }, out);
+    unsigned pk[MB_PKW] = { 0 }; mb_cell_vitr<true> (D, L, U, N, ea, em, ebr, origin, sink, P, pk, 8 * MB_TBBYTES * (MB_C - 1)); }, out);
   vit[q++] = out[MB_S - 1];
   // Forward and Backward, normalised linear domain
   hostE = (const char*) rowF.data();
@@ -141,9 +139,7 @@ def test_generated_row_cells_on_the_host(name, shapes, monkeypatch, tmp_path):
         out = subprocess.run([exe, str(data)], check=True, capture_output=True, text=True).stdout.split()
         v0, v2, v4, fwd, bwd = [float(v) for v in out]
         want_v, _ = orc.viterbi(x, y)
-        assert v0 == want_v, (name, k, v0, want_v)                      # bit-exact
-        if flags[1] == 1.0:                                             # no positive log-weight: the integer compares are valid
-            assert v2 == want_v and v4 == want_v, (name, k, v2, v4, want_v)
+        assert v0 == want_v and v2 == want_v and v4 == want_v, (name, k, v0, v2, v4, want_v)                      # bit-exact
         want_f = orc.forward(x, y, mode=LSE_EXACT)
         for got in (fwd, bwd):
             if np.isinf(want_f):
@@ -164,6 +160,3 @@ def test_normalisation_is_refused_when_a_unit_weight_is_zero():
     assert capi.jit_host_tables(*args, fm.lw, which=5)[0] == 1.0
     flags = [capi.jit_host_tables(*args, np.where(np.arange(len(lw)) == t, -np.inf, fm.lw), which=5)[0] for t in silent]
     assert 0.0 in flags      # at least one of the silent groups is a unit group
-    lw_pos = fm.lw.copy()
-    lw_pos[0] = 0.25         # a weight above 1: Viterbi scores may be positive, the integer compares are off
-    assert capi.jit_host_tables(*args, lw_pos, which=5)[1] == 0.0
