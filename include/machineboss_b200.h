@@ -191,6 +191,15 @@ int mb_jit_host_tables (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_
                         const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
                         int32_t which, double* out, int64_t cap, int64_t* n);
 
+/* The lane engine's windowed program for a machine without input alphabet, built and EXECUTED ON THE HOST for one read
+ * (no device needed: the CPU tests check the program's construction -- window, ring, hubs, push-form sums -- against
+ * the oracle).  op: 0 scaled linear sums, 1 max-plus (Viterbi), 2 log-sum-exp.  info[8] = { usable, window states, ring
+ * slots, hub sources, hub destinations, live states, records, back-pointer bytes }; backPointers (may be NULL; op 1)
+ * receives (outLen + 1) * nStates words, [o][state], in the engine's (kind, index-in-list) format. */
+int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                     const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                     const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, uint32_t* backPointers);
+
 /* ---- measurement hooks (not part of the reference surface) ----
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
  * (CUDA events on the launching stream), and how many kernels that was. */

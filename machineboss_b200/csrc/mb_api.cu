@@ -26,7 +26,7 @@ static const char* const kOptionNames[] = {
   "jit_no_norm",                                              // 1: never use the normalised linear kernels (score module)
   "jit_unroll",                                               // unroll factor of the steady-state step loop (1 - 4)
   "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
-  "lane_r", "lane_warps", "no_lane", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
+  "lane_r", "lane_warps", "no_lane", "lane_old", "lane_bs", "lane_la", "lane_wn", "lane_host_only", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
 };
 
 Options thread_options() { return g_options; }
@@ -725,6 +725,28 @@ int mb_jit_host_tables (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_
   if (n) *n = (int64_t) v.size();
   if (out) for (int64_t q = 0; q < (int64_t) v.size() && q < cap; ++q) out[q] = v[q];
   return 0;
+}
+
+int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                     const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                     const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, uint32_t* backPointers) {
+  mb_machine m;
+  m.opt = g_options;
+  m.opt.set ("lane_host_only", 1);
+  m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
+  m.src.assign (src, src + nTrans); m.dst.assign (dst, dst + nTrans);
+  m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);
+  m.lw.assign (logWeight, logWeight + nTrans);
+  build_csr (&m, true, m.hInc);
+  int rc = lane_prepare (&m);
+  int32_t inf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  if (!rc) rc = lane2_info (&m, inf);
+  if (info) for (int q = 0; q < 8; ++q) info[q] = inf[q];
+  std::vector<uint32_t> bp;
+  if (!rc && inf[0] && result) rc = lane2_emulate (&m, outTokens, outLen, op, result, backPointers ? &bp : nullptr);
+  if (!rc && backPointers) for (size_t q = 0; q < bp.size(); ++q) backPointers[q] = bp[q];
+  lane_destroy (&m);
+  return rc;
 }
 
 int mb_last_kernel_ms (const mb_batch* b, double* ms, int64_t* nLaunches) {

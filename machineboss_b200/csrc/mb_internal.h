@@ -182,6 +182,9 @@ int lane_update_weights (mb_machine* m);
 bool lane_wanted (const mb_machine* m, const mb_batch* b);      // no input sequences, no envelopes
 int lane_forward (mb_machine* m, mb_batch* b, double* loglike);
 int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
+// the windowed program of the lane engine, executed for one read on the host (diagnostic; op 0 sum, 1 max, 2 log-sum-exp)
+int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut);
+int lane2_info (const mb_machine* m, int32_t* info);      // { usable, window states, ring slots, hub sources, hub destinations, live states, records, back-pointer bytes }
 
 // ---- big engine (mb_big.cu): machine-specialised Forward sweep for mid-size machines (a thread per cell, the cell as
 // straight-line code); full two-dimensional matrices only; flagged pairs go back to the wide engine's log-domain sweep ----

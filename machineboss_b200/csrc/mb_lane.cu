@@ -50,6 +50,52 @@ enum { L_SUM = 0, L_MAX = 1, L_LSE = 2 };
 
 struct LRec { double w; uint32_t src; uint32_t ctl; };      // src: source state * 32 (element offset in a lane-interleaved vector)
 
+// ---------------------------------------------------------------------------------------------
+// The windowed program (lane2): the same read-per-lane sweep with the cell's state vector kept ON CHIP.
+//
+// The first version of this engine kept two whole state vectors per read in global memory; every term of the
+// program loaded its source from there, and a profile's delete chain (D_k -> D_k+1 -> ...) became a chain of
+// dependent loads at L2 / HBM latency: 180 GCUPS, 2 % of the multiply-add roofline, 10.8 long-scoreboard stall
+// cycles per issued instruction (profiles/r01_ncu_summary.md).  What a cell really needs is little:
+//   * a silent transition's source is a state computed a few states earlier (dst - src < WN for all but a handful
+//     of hub states): the last WN states of the current cell live in a shared-memory WINDOW, win[state % WN][lane];
+//   * the few long-range silent edges go through HUBS: a hub SOURCE (the profile's begin state feeding every match
+//     state) keeps its value in a pinned shared-memory slot for the whole cell; a hub DESTINATION (the end state
+//     fed by every match state) is accumulated in PUSH form -- each source adds its term right after it has been
+//     finalised, in ascending source order, which is the reference's candidate order, so the Viterbi tie-break
+//     is unchanged;
+//   * emitting transitions read the PREVIOUS cell, and only LIVE states (sources of emitting transitions: 975 of
+//     PF00516's 2439) ever cross cells: they alone are written to global memory, compactly, and streamed back
+//     through a shared-memory RING with cp.async, LA blocks of BS states ahead of their use (sources sit within a
+//     few states of their destinations, so the ring is read almost in order).
+// Per cell and read the global traffic is the live vector once out and once in; everything else is shared memory
+// and registers.  The program is checked when it is built (every window, ring and hub access provably hits the
+// value it means to); a machine whose structure does not fit keeps the first version of the sweep.
+// ---------------------------------------------------------------------------------------------
+enum { K_EMIT = 0, K_WIN = 1, K_HUBS = 2, K_PUSH = 3, K_NONE = 4 };
+#define L2_SCALE 8u         // last emitting term of its destination: bring the sum into this cell's frame
+#define L2_END 16u          // finalise the destination after this record
+#define L2_LIVE 32u         // ... and store it to the live vector
+#define L2_HSTORE 64u       // ... and to hub-source slot L2_HS (ctl)
+#define L2_HINIT 128u       // first record of a hub destination: the accumulator starts from hub slot L2_HD (ctl)
+#define L2_PRESTORE 256u    // preamble: the accumulator (a hub destination's emitting terms) goes to hub slot (ctl >> 12) & 7
+#define L2_HS(ctl) (((ctl) >> 9) & 7u)       // hub-source slot of an L2_HSTORE record
+#define L2_HD(ctl) (((ctl) >> 12) & 7u)      // hub-destination slot of an L2_HINIT / L2_PRESTORE record
+#define L2_MAXHUB 8
+
+struct L2Prog {
+  bool ok = false;
+  std::string why;
+  int WN = 32, RN = 64, BS = 8, LA = 3;
+  int nHubS = 0, nHubD = 0, nLive = 0, nBlk = 0;      // blocks include block 0 = the preamble
+  std::vector<LRec> recLin, recLog;
+  std::vector<int64_t> recPerm;             // silent (window / hub / push) record -> hInc entry, -1 otherwise
+  std::vector<int32_t> recWant;             // (host only) what the record means to read: live index (emit), source state (window, hub source)
+  std::vector<int32_t> blkRec, blkLoad, loadIdx;
+  LRec* dRecLin = nullptr; LRec* dRecLog = nullptr;
+  int32_t* dBlk = nullptr;                  // blkRec | blkLoad | loadIdx on the device
+};
+
 struct LHost {
   std::vector<LRec> recLin, recLog;       // identical but for the weights
   std::vector<double> emLin, emLog;       // [row][nOut] token-indexed weights of the emitting terms
@@ -63,6 +109,9 @@ struct LHost {
   int S = 0, nOut = 0, bpBytes = 2;
   bool linearOk = false;
   int numSMs = 148;
+  // per destination state: its emitting rows (table row, source state) in candidate order -- what lane2_build starts from
+  std::vector<std::vector<std::pair<int, int>>> destRows;
+  L2Prog l2;
 };
 
 struct LParams {
@@ -226,6 +275,9 @@ __global__ void __launch_bounds__(128) lane_kernel (const __grid_constant__ LPar
 // host side
 // ---------------------------------------------------------------------------------------------
 static LHost* lh (const mb_machine* m) { return static_cast<LHost*> (m->lane); }
+static void lane2_build (const mb_machine* m, LHost* h);
+static void lane2_fill_weights (const mb_machine* m, LHost* h);
+static int lane2_upload (mb_machine* m, LHost* h, bool all);
 
 static void lane_fill_weights (const mb_machine* m, LHost* h) {
   bool ok = true;
@@ -251,7 +303,7 @@ static void lane_fill_weights (const mb_machine* m, LHost* h) {
 void lane_destroy (mb_machine* m) {
   LHost* h = lh (m);
   if (!h) return;
-  for (void* p: { (void*) h->dRecLin, (void*) h->dRecLog, (void*) h->dEmLin, (void*) h->dEmLog, (void*) h->dEmIdx }) if (p) cudaFree (p);
+  for (void* p: { (void*) h->dRecLin, (void*) h->dRecLog, (void*) h->dEmLin, (void*) h->dEmLog, (void*) h->dEmIdx, (void*) h->l2.dRecLin, (void*) h->l2.dRecLog, (void*) h->l2.dBlk }) if (p) cudaFree (p);
   delete h;
   m->lane = nullptr;
 }
@@ -278,7 +330,8 @@ int lane_update_weights (mb_machine* m) {
   LHost* h = lh (m);
   if (!h) return 0;
   lane_fill_weights (m, h);
-  return lane_upload (m, h, false);
+  if (h->l2.ok) lane2_fill_weights (m, h);
+  return lane_upload (m, h, false) || lane2_upload (m, h, false);
 }
 
 // The transition program: destinations in index order; per destination the emitting terms (union
@@ -306,9 +359,11 @@ int lane_prepare (mb_machine* m) {
       }
     }
     std::sort (keys.begin(), keys.end());
+    h->destRows.resize ((size_t) S);
     for (auto& kk: keys) {
       const int row = (int) (h->emPerm.size() / std::max (nOut, 1));
       rowOf[kk] = row;
+      h->destRows[d].push_back (std::make_pair (row, kk.first));
       h->emPerm.resize (h->emPerm.size() + nOut, -1);
       h->emIdx.resize (h->emIdx.size() + nOut, 0x3fff);
       LRec r = blank;
@@ -351,11 +406,500 @@ int lane_prepare (mb_machine* m) {
   h->emLin.assign (h->emPerm.size(), 0.);
   h->emLog.assign (h->emPerm.size(), -INFINITY);
   lane_fill_weights (m, h);
-  if (lane_upload (m, h, true)) return 1;
+  lane2_build (m, h);
+  if (h->l2.ok) lane2_fill_weights (m, h);
+  if (m->opt.get ("lane_host_only", 0)) return 0;      // (diagnostic: build the programs without touching a device)
+  if (lane_upload (m, h, true) || lane2_upload (m, h, true)) return 1;
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   if (m->opt.get ("verbose", 0))
     fprintf (stderr, "lane engine: S=%d records=%lld (emitting rows %zu x %d tokens), bp %d bytes\n", S, (long long) h->nRec, h->emPerm.size() / std::max (nOut, 1), nOut, h->bpBytes);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane2: building the windowed program
+// ---------------------------------------------------------------------------------------------
+static LRec l2_rec (uint32_t kind, uint32_t a, uint32_t flags) { LRec r; r.w = 0; r.src = a; r.ctl = kind | flags; return r; }
+
+static bool lane2_try (const mb_machine* m, LHost* h, int WN, int RN, int BS, int LA) {
+  L2Prog& P = h->l2;
+  const int S = m->S, nIn1 = m->nIn + 1, nOut1 = m->nOut + 1;
+  const HostCsr& inc = m->hInc;
+  auto fail = [&] (const std::string& w) { P.ok = false; P.why = w; return false; };
+  P = L2Prog();
+  P.WN = WN; P.RN = RN; P.BS = BS; P.LA = LA;
+  // ---- long-range silent edges and the hubs that carry them
+  struct Edge { int src, dst; };
+  std::vector<Edge> far;
+  for (int d = 1; d < S; ++d) {
+    const int64_t key = (int64_t) d * nIn1 * nOut1;
+    for (int64_t q = inc.off[key]; q < inc.off[key + 1]; ++q) if (d - inc.other[q] >= WN) far.push_back (Edge { inc.other[q], d });
+  }
+  std::vector<int> hubS ((size_t) S, -1), hubD ((size_t) S, -1);
+  for (;;) {      // greedy cover: the state with most uncovered long-range edges becomes a hub
+    std::vector<int> nOut ((size_t) S, 0), nIn ((size_t) S, 0);
+    int left = 0;
+    for (auto& e: far) if (hubS[e.src] < 0 && hubD[e.dst] < 0) { ++nOut[e.src]; ++nIn[e.dst]; ++left; }
+    if (!left) break;
+    int bestS = 0, bestD = 0;
+    for (int s = 0; s < S; ++s) { if (nOut[s] > nOut[bestS]) bestS = s; if (nIn[s] > nIn[bestD]) bestD = s; }
+    if (nOut[bestS] >= nIn[bestD]) { if (P.nHubS == L2_MAXHUB) return fail ("more than 8 hub sources"); hubS[bestS] = P.nHubS++; }
+    else { if (P.nHubD == L2_MAXHUB) return fail ("more than 8 hub destinations"); hubD[bestD] = P.nHubD++; }
+  }
+  // ---- live states: sources of emitting rows
+  std::vector<int> liveIdx ((size_t) S, -1);
+  { std::vector<char> isLive ((size_t) S, 0);
+    for (int d = 0; d < S; ++d) for (auto& rs: h->destRows[d]) isLive[rs.second] = 1;
+    for (int s = 0; s < S; ++s) if (isLive[s]) liveIdx[s] = P.nLive++; }
+  // ---- pushes: every silent term of a hub destination, attached to its source, in the destination's list order
+  struct Push { int hd; int64_t q; uint32_t cand; };
+  std::vector<std::vector<Push>> pushOf ((size_t) S);
+  for (int d = 1; d < S; ++d) {
+    if (hubD[d] < 0) continue;
+    const int64_t key = (int64_t) d * nIn1 * nOut1;
+    for (int64_t q = inc.off[key]; q < inc.off[key + 1]; ++q) pushOf[inc.other[q]].push_back (Push { hubD[d], q, (uint32_t) (q - inc.off[key]) });
+  }
+  // ---- records, block by block
+  std::vector<std::vector<int>> blkLive;      // live indices each block's emitting terms read, in order of use
+  auto emit_terms = [&] (int d, std::vector<int>& liveUse) {
+    const auto& rows = h->destRows[d];
+    for (size_t n = 0; n < rows.size(); ++n) {
+      LRec r = l2_rec (K_EMIT, (uint32_t) (liveIdx[rows[n].second] & (RN - 1)), n + 1 == rows.size() ? L2_SCALE : 0u);
+      const uint64_t rowBits = (uint64_t) rows[n].first;
+      memcpy (&r.w, &rowBits, 8);
+      P.recLin.push_back (r);
+      P.recPerm.push_back (-1);
+      P.recWant.push_back (liveIdx[rows[n].second]);
+      liveUse.push_back (liveIdx[rows[n].second]);
+    }
+  };
+  P.blkRec.push_back (0);
+  blkLive.emplace_back();
+  for (int d = 0; d < S; ++d) {      // block 0, the preamble: emitting terms of hub destinations go to their hub slot first
+    if (hubD[d] < 0 || h->destRows[d].empty()) continue;
+    emit_terms (d, blkLive.back());
+    P.recLin.push_back (l2_rec (K_NONE, 0, L2_PRESTORE | ((uint32_t) hubD[d] << 12)));
+    P.recPerm.push_back (-1);
+    P.recWant.push_back (-1);
+  }
+  P.blkRec.push_back ((int32_t) P.recLin.size());
+  for (int d0 = 0; d0 < S; d0 += BS) {
+    blkLive.emplace_back();
+    for (int d = d0; d < std::min (S, d0 + BS); ++d) {
+      const size_t first = P.recLin.size();
+      if (hubD[d] >= 0) { P.recLin.push_back (l2_rec (K_NONE, 0, L2_HINIT | ((uint32_t) hubD[d] << 12))); P.recPerm.push_back (-1); P.recWant.push_back (-1); }
+      else {
+        emit_terms (d, blkLive.back());
+        if (d > 0) {
+          const int64_t key = (int64_t) d * nIn1 * nOut1;
+          for (int64_t q = inc.off[key]; q < inc.off[key + 1]; ++q) {
+            const int src = inc.other[q];
+            const uint32_t cand = (uint32_t) (q - inc.off[key]) << 16;
+            if (hubS[src] >= 0) P.recLin.push_back (l2_rec (K_HUBS, (uint32_t) hubS[src], cand));
+            else if (d - src < WN) P.recLin.push_back (l2_rec (K_WIN, (uint32_t) (src & (WN - 1)), cand));
+            else return fail ("a long-range silent edge is not covered by a hub");
+            P.recPerm.push_back (q);
+            P.recWant.push_back (src);
+          }
+        }
+        if (P.recLin.size() == first) { P.recLin.push_back (l2_rec (K_NONE, 0, 0)); P.recPerm.push_back (-1); P.recWant.push_back (-1); }
+      }
+      P.recLin.back().ctl |= L2_END | (liveIdx[d] >= 0 ? L2_LIVE : 0u) | (hubS[d] >= 0 ? (L2_HSTORE | ((uint32_t) hubS[d] << 9)) : 0u);
+      for (auto& pu: pushOf[d]) { P.recLin.push_back (l2_rec (K_PUSH, (uint32_t) pu.hd, pu.cand << 16)); P.recPerm.push_back (pu.q); P.recWant.push_back (-1); }
+    }
+    P.blkRec.push_back ((int32_t) P.recLin.size());
+  }
+  P.nBlk = (int) P.blkRec.size() - 1;
+  // ---- ring schedule: block b's loads are issued LA blocks early; a slot may only be refilled once every block that
+  // still reads its old content has been processed
+  std::vector<int> lastUse ((size_t) std::max (P.nLive, 1), -1), tag ((size_t) RN, -1);
+  for (int b = 0; b < P.nBlk; ++b) for (int j: blkLive[b]) lastUse[j] = b;
+  P.blkLoad.push_back (0);
+  for (int b = 0; b < P.nBlk; ++b) {
+    for (int j: blkLive[b]) {
+      const int slot = j & (RN - 1);
+      if (tag[slot] == j) continue;
+      // the load is issued while block b - LA is being processed (blocks before that are done)
+      if (tag[slot] >= 0 && lastUse[tag[slot]] >= b - LA) return fail ("the ring of previous-cell values is too small for this machine");
+      tag[slot] = j;
+      P.loadIdx.push_back (j);
+    }
+    P.blkLoad.push_back ((int32_t) P.loadIdx.size());
+  }
+  { LRec r = l2_rec (K_NONE, 0, 0); P.recLin.push_back (r); P.recPerm.push_back (-1); P.recWant.push_back (-1); }      // spare record: the sweep keeps one in flight
+  P.recLog = P.recLin;
+  P.ok = true;
+  return true;
+}
+
+static void lane2_fill_weights (const mb_machine* m, LHost* h) {
+  L2Prog& P = h->l2;
+  for (size_t n = 0; n < P.recPerm.size(); ++n) {
+    if (P.recPerm[n] < 0) continue;
+    const double lw = m->hInc.lw[P.recPerm[n]];
+    P.recLog[n].w = lw;
+    P.recLin[n].w = exp (lw);
+  }
+}
+
+static int lane2_upload (mb_machine* m, LHost* h, bool all) {
+  L2Prog& P = h->l2;
+  if (!P.ok) return 0;
+  const size_t rb = P.recLin.size() * sizeof (LRec);
+  if (all) {
+    MB_CUDA (cudaMalloc (&P.dRecLin, rb)); MB_CUDA (cudaMalloc (&P.dRecLog, rb));
+    std::vector<int32_t> blk;
+    blk.insert (blk.end(), P.blkRec.begin(), P.blkRec.end());
+    blk.insert (blk.end(), P.blkLoad.begin(), P.blkLoad.end());
+    blk.insert (blk.end(), P.loadIdx.begin(), P.loadIdx.end());
+    blk.push_back (0);
+    MB_CUDA (cudaMalloc (&P.dBlk, blk.size() * 4));
+    MB_CUDA (cudaMemcpy (P.dBlk, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice));
+  }
+  MB_CUDA (cudaMemcpy (P.dRecLin, P.recLin.data(), rb, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (P.dRecLog, P.recLog.data(), rb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int lane2_info (const mb_machine* m, int32_t* info) {
+  LHost* h = lh (m);
+  if (!h) { set_error ("lane engine not prepared"); return 1; }
+  const L2Prog& P = h->l2;
+  const int32_t v[8] = { P.ok ? 1 : 0, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, (int32_t) P.recLin.size(), h->bpBytes };
+  for (int q = 0; q < 8; ++q) info[q] = v[q];
+  if (!P.ok) set_error ("lane2: " + P.why);
+  return 0;
+}
+
+static void lane2_build (const mb_machine* m, LHost* h) {
+  if (m->opt.get ("lane_old", 0)) { h->l2.ok = false; h->l2.why = "disabled (option lane_old)"; return; }
+  const int BS = std::max (1, std::min (64, m->opt.get ("lane_bs", 8))), LA = std::max (1, std::min (8, m->opt.get ("lane_la", 3)));
+  for (int WN: { 32, 64, 128 }) {
+    if (m->opt.has ("lane_wn") && WN != m->opt.get ("lane_wn", 32)) continue;
+    for (int RN: { 16, 32, 64, 128 }) if (lane2_try (m, h, WN, RN, BS, LA)) return;
+  }
+}
+
+// The program executed for ONE read on the host, slot for slot as the kernel does it (same window, ring and hub
+// arithmetic, with every slot tagged so that a stale read is an error): what the CPU test checks against the oracle.
+// op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
+int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut) {
+  LHost* h = lh (m);
+  if (!h || !h->l2.ok) { set_error (std::string ("lane2: no windowed program for this machine") + (h ? ": " + h->l2.why : std::string())); return 1; }
+  const L2Prog& P = h->l2;
+  const std::vector<LRec>& rec = op == L_SUM ? P.recLin : P.recLog;
+  const std::vector<double>& em = op == L_SUM ? h->emLin : h->emLog;
+  const int nOut = h->nOut, S = h->S;
+  const double ZERO = op == L_SUM ? 0. : -INFINITY, ONE = op == L_SUM ? 1. : 0.;
+  const unsigned kb = h->bpBytes == 1 ? 6 : 14;
+  auto lse = [] (double a, double b) { const double mx = std::max (a, b), mn = std::min (a, b); return mn == -INFINITY ? mx : mx + log1p (exp (mn - mx)); };
+  std::vector<double> win ((size_t) P.WN), ring ((size_t) P.RN), hubS (L2_MAXHUB), hubD (L2_MAXHUB), live[2];
+  std::vector<int> winTag ((size_t) P.WN, -1), ringTag ((size_t) P.RN, -1), hubSTag (L2_MAXHUB, -1);
+  std::vector<uint32_t> hubDB (L2_MAXHUB);
+  live[0].assign ((size_t) std::max (P.nLive, 1), ZERO); live[1] = live[0];
+  // which state sits in which slot is recomputed from the program: d counts END records, live index counts L2_LIVE
+  int Fprev = 0, Gprev = L_SENT;
+  double res = ZERO;
+  int Fres = 0;
+  if (bpOut) bpOut->assign ((size_t) (Lo + 1) * S, 0xffffu);
+  // static map live index -> state, for the ring tags
+  for (int64_t o = 0; o <= Lo; ++o) {
+    std::vector<double>& cur = live[o & 1];
+    const std::vector<double>& prev = live[(o & 1) ^ 1];
+    const int tok = o > 0 ? y[o - 1] - 1 : 0;
+    int F = 0; double f = 1.;
+    if (op == L_SUM && o > 0) { if (Gprev == L_SENT) f = 0.; else { F = Gprev; f = std::ldexp (1., Fprev - F); } }
+    std::fill (hubD.begin(), hubD.end(), ZERO);
+    std::fill (hubDB.begin(), hubDB.end(), 0xffffu);
+    std::fill (ringTag.begin(), ringTag.end(), -1);      // a new cell: nothing of the previous vector is in the ring yet
+    std::fill (winTag.begin(), winTag.end(), -1);
+    std::fill (hubSTag.begin(), hubSTag.end(), -1);
+    double acc = ZERO, vlast = ZERO;
+    uint32_t best = 0xffffu;
+    int mx = 0; unsigned mn = 0xffffffffu;
+    int d = 0, nl = 0;
+    auto issue = [&] (int b) { for (int j = P.blkLoad[b]; j < P.blkLoad[b + 1]; ++j) { const int li = P.loadIdx[j]; ring[li & (P.RN - 1)] = prev[li]; ringTag[li & (P.RN - 1)] = li; } };
+    for (int b = 0; b < std::min (P.LA, P.nBlk); ++b) issue (b);
+    for (int b = 0; b < P.nBlk; ++b) {
+      if (b + P.LA < P.nBlk) issue (b + P.LA);
+      if (b == 1) acc = o == 0 ? ONE : ZERO;      // the origin cell's start state (forward.defs.h:36), after the preamble
+      for (int n = P.blkRec[b]; n < P.blkRec[b + 1]; ++n) {
+        const LRec& r = rec[n];
+        const uint32_t ctl = r.ctl, kind = ctl & 7u;
+        if (ctl & L2_HINIT) { acc = hubD[L2_HD (ctl)]; best = hubDB[L2_HD (ctl)]; }
+        if (kind == K_EMIT) {
+          if (o > 0) {
+            uint64_t row; memcpy (&row, &r.w, 8);
+            const double x = ring[r.src], w = em[(size_t) row * nOut + tok];
+            if (ringTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a ring slot does not hold the previous-cell value the term means to read"); return 1; }
+            if (op == L_SUM) acc = fma (w, x, acc);
+            else if (op == L_LSE) acc = lse (acc, x + w);
+            else { const double c = x + w; if (acc < c) { acc = c; best = ((uint32_t) T_INSERT << kb) | h->emIdx[(size_t) row * nOut + tok]; } }
+          }
+          if (op == L_SUM && (ctl & L2_SCALE)) acc *= f;
+        } else if (kind == K_WIN || kind == K_HUBS) {
+          if (kind == K_WIN && winTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a window slot does not hold the state the term means to read"); return 1; }
+          if (kind == K_HUBS && hubSTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a hub source is read before it has been written"); return 1; }
+          const double x = kind == K_WIN ? win[r.src] : hubS[r.src];
+          if (op == L_SUM) acc = fma (r.w, x, acc);
+          else if (op == L_LSE) acc = lse (acc, x + r.w);
+          else { const double c = x + r.w; if (acc < c) { acc = c; best = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
+        } else if (kind == K_PUSH) {
+          double& a = hubD[r.src];
+          if (op == L_SUM) a = fma (r.w, vlast, a);
+          else if (op == L_LSE) a = lse (a, vlast + r.w);
+          else { const double c = vlast + r.w; if (a < c) { a = c; hubDB[r.src] = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
+        }
+        if (ctl & L2_PRESTORE) { hubD[L2_HD (ctl)] = acc; hubDB[L2_HD (ctl)] = best; acc = ZERO; best = 0xffffu; }
+        if (ctl & L2_END) {
+          win[d & (P.WN - 1)] = acc; winTag[d & (P.WN - 1)] = d;
+          vlast = acc;
+          if (ctl & L2_LIVE) cur[nl++] = acc;
+          if (ctl & L2_HSTORE) { hubS[L2_HS (ctl)] = acc; hubSTag[L2_HS (ctl)] = d; }
+          if (op == L_SUM) {
+            int64_t bits; memcpy (&bits, &acc, 8);
+            const int hi = (int) (bits >> 32);
+            mx = std::max (mx, hi); mn = std::min (mn, (unsigned) (hi - 0x00100000));
+          } else if (op == L_MAX && bpOut) (*bpOut)[(size_t) o * S + d] = best;
+          res = acc; Fres = F;
+          acc = ZERO; best = 0xffffu;
+          ++d;
+        }
+      }
+    }
+    if (d != S || nl != P.nLive) { set_error ("lane2 emulation: the program does not visit every state"); return 1; }
+    if (op == L_SUM) {
+      int Gc = L_SENT;
+      if (mx >= 0x00100000) Gc = F + (mx >> 20) - 1023;
+      Fprev = F; Gprev = Gc;
+    }
+  }
+  *result = op == L_SUM ? (res > 0. ? log (res) + Fres * 0.693147180559945309417232121458 : -INFINITY) : res;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lane2: the kernel.  One warp = 32 * R reads; shared memory per warp: the window, the ring, the hub slots
+// (rows of 32 * R doubles, a lane's R reads 32 apart: every access of the warp is one conflict-free 256-byte row).
+// ---------------------------------------------------------------------------------------------
+struct L2Params {
+  const LRec* rec;
+  const int32_t* blkRec; const int32_t* blkLoad; const int32_t* loadIdx;
+  int32_t nBlk, LA, WN, RN, nHubS, nHubD, nLive;
+  const double* em; const uint16_t* emIdx;
+  int32_t S, nOut, bpBytes;
+  DevBatch b;
+  const int64_t* order; int64_t nWork;
+  unsigned long long* counter;
+  double* result; int32_t* flag;
+  double* vec;                                // per resident warp: 2 live vectors of nLive * 32 * R doubles
+  unsigned char* bp; const int64_t* bpOff;
+};
+
+__device__ __forceinline__ void l2_cp_async8 (void* smem, const void* gmem) {
+  asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned) __cvta_generic_to_shared (smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void l2_commit() { asm volatile ("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void l2_wait (const int pending) {      // at most `pending` groups still in flight
+  if (pending <= 0) asm volatile ("cp.async.wait_group 0;" ::: "memory");
+  else if (pending == 1) asm volatile ("cp.async.wait_group 1;" ::: "memory");
+  else if (pending == 2) asm volatile ("cp.async.wait_group 2;" ::: "memory");
+  else if (pending == 3) asm volatile ("cp.async.wait_group 3;" ::: "memory");
+  else if (pending == 4) asm volatile ("cp.async.wait_group 4;" ::: "memory");
+  else if (pending == 5) asm volatile ("cp.async.wait_group 5;" ::: "memory");
+  else if (pending == 6) asm volatile ("cp.async.wait_group 6;" ::: "memory");
+  else if (pending == 7) asm volatile ("cp.async.wait_group 7;" ::: "memory");
+  else asm volatile ("cp.async.wait_group 8;" ::: "memory");
+}
+
+template<int OP, int R>
+__global__ void __launch_bounds__(128) lane2_kernel (const __grid_constant__ L2Params p) {
+  extern __shared__ double l2smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+  constexpr int LPT = 32 * R;
+  const int rows = p.WN + p.RN + p.nHubS + p.nHubD;
+  double* win = l2smem + (size_t) warp * rows * LPT + lane;
+  double* ring = win + p.WN * LPT;
+  double* hubS = ring + p.RN * LPT;
+  double* hubD = hubS + p.nHubS * LPT;
+  unsigned* hubDB = reinterpret_cast<unsigned*> (l2smem + (size_t) nWarps * rows * LPT) + (size_t) warp * p.nHubD * LPT + lane;      // L_MAX only
+  double* v0 = p.vec + ((size_t) blockIdx.x * nWarps + warp) * 2 * (size_t) p.nLive * LPT + lane;
+  double* v1 = v0 + (size_t) p.nLive * LPT;
+  const double ZERO = OP == L_SUM ? 0. : l_ninf(), ONE = OP == L_SUM ? 1. : 0.;
+  const unsigned kb = p.bpBytes == 1 ? 6 : 14;
+  const double LN2 = 0.693147180559945309417232121458;
+  const int winMask = p.WN - 1, ringMask = p.RN - 1;
+  for (;;) {
+    long long task = 0;
+    if (lane == 0) task = (long long) atomicAdd (p.counter, 1ULL);
+    task = __shfl_sync (0xffffffffu, task, 0);
+    if (task * LPT >= p.nWork) break;
+    int64_t k[R];
+    const uint8_t* y[R];
+    int Lo[R], maxLo = -1;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const long long rd = task * LPT + q * 32 + lane;
+      const bool have = rd < p.nWork;
+      k[q] = have ? p.order[rd] : 0;
+      y[q] = p.b.y + p.b.yOff[k[q]];
+      Lo[q] = have ? (int) (p.b.yOff[k[q] + 1] - p.b.yOff[k[q]]) : -1;
+      maxLo = max (maxLo, Lo[q]);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) maxLo = max (maxLo, __shfl_xor_sync (0xffffffffu, maxLo, off));
+    unsigned char* bp = OP == L_MAX && p.bp ? p.bp + p.bpOff[task] + (size_t) lane * p.bpBytes : nullptr;
+    bool bad[R];
+    int Fprev[R], Gprev[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { bad[q] = false; Fprev[q] = 0; Gprev[q] = L_SENT; }
+    for (int o = 0; o <= maxLo; ++o) {
+      double* cur = (o & 1) ? v1 : v0;
+      const double* prev = (o & 1) ? v0 : v1;
+      int tok[R], F[R], mx[R];
+      unsigned mn[R], best[R];
+      double f[R], acc[R], res[R], vlast[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        tok[q] = (o <= Lo[q] && o > 0) ? y[q][o - 1] - 1 : 0;
+        F[q] = 0; f[q] = 1.;
+        if (OP == L_SUM && o > 0) { if (Gprev[q] == L_SENT) f[q] = 0.; else { F[q] = Gprev[q]; f[q] = l_pow2 (Fprev[q] - F[q]); } }
+        mx[q] = 0; mn[q] = 0xffffffffu; best[q] = 0xffffu;
+        acc[q] = ZERO; res[q] = ZERO; vlast[q] = ZERO;
+      }
+      for (int hd = 0; hd < p.nHubD; ++hd) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) { hubD[hd * LPT + q * 32] = ZERO; if (OP == L_MAX) hubDB[hd * LPT + q * 32] = 0xffffu; }
+      }
+      const bool usePrev = o > 0;
+      // the previous cell's live values travel into the ring LA blocks ahead of the block that reads them
+      auto issue = [&] (const int blk) {
+        for (int j = __ldg (p.blkLoad + blk), je = __ldg (p.blkLoad + blk + 1); j < je; ++j) {
+          const int li = __ldg (p.loadIdx + j);
+#pragma unroll
+          for (int q = 0; q < R; ++q) l2_cp_async8 (ring + (li & ringMask) * LPT + q * 32, prev + (size_t) li * LPT + q * 32);
+        }
+        l2_commit();
+      };
+      if (usePrev) for (int blk = 0; blk < min (p.LA, p.nBlk); ++blk) issue (blk);
+      double* curOut = cur;
+      unsigned char* bpRow = bp ? bp + (size_t) o * p.S * LPT * p.bpBytes : nullptr;
+      int d = 0;
+      const LRec* r = p.rec;
+      uint4 nx = __ldg (reinterpret_cast<const uint4*> (r));
+      int n = 0;
+      for (int blk = 0; blk < p.nBlk; ++blk) {
+        if (usePrev) {
+          if (blk + p.LA < p.nBlk) issue (blk + p.LA); else l2_commit();      // (an empty group keeps the count uniform)
+          l2_wait (p.LA);      // the group of block blk has landed
+        }
+        if (blk == 1) {      // the origin cell's start state (forward.defs.h:36), after the preamble
+#pragma unroll
+          for (int q = 0; q < R; ++q) acc[q] = o == 0 ? ONE : ZERO;
+        }
+        for (const int ne = __ldg (p.blkRec + blk + 1); n < ne; ++n) {
+          const uint4 u = nx;
+          nx = __ldg (reinterpret_cast<const uint4*> (r + n + 1));      // the stream ends with a spare record
+          const unsigned ctl = u.w, kind = ctl & 7u;
+          if (ctl & L2_HINIT) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) { acc[q] = hubD[L2_HD (ctl) * LPT + q * 32]; if (OP == L_MAX) best[q] = hubDB[L2_HD (ctl) * LPT + q * 32]; }
+          }
+          if (kind == K_EMIT) {
+            if (usePrev) {
+              double x[R], w[R];
+              unsigned ix[R];
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                x[q] = ring[u.z * LPT + q * 32];
+                w[q] = __ldg (p.em + (size_t) u.x * p.nOut + tok[q]);
+                if (OP == L_MAX) ix[q] = __ldg (p.emIdx + (size_t) u.x * p.nOut + tok[q]);
+              }
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                if (OP == L_SUM) acc[q] = fma (w[q], x[q], acc[q]);
+                else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w[q]);
+                else { const double c = x[q] + w[q]; if (acc[q] < c) { acc[q] = c; best[q] = ((unsigned) T_INSERT << kb) | ix[q]; } }
+              }
+            }
+            if (OP == L_SUM && (ctl & L2_SCALE)) {
+#pragma unroll
+              for (int q = 0; q < R; ++q) acc[q] *= f[q];
+            }
+          } else if (kind == K_WIN || kind == K_HUBS) {
+            const double w = __hiloint2double ((int) u.y, (int) u.x);
+            const double* src = (kind == K_WIN ? win : hubS) + u.z * LPT;
+            double x[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) x[q] = src[q * 32];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              if (OP == L_SUM) acc[q] = fma (w, x[q], acc[q]);
+              else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w);
+              else { const double c = x[q] + w; if (acc[q] < c) { acc[q] = c; best[q] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
+            }
+          } else if (kind == K_PUSH) {
+            const double w = __hiloint2double ((int) u.y, (int) u.x);
+            double* a = hubD + u.z * LPT;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              if (OP == L_SUM) a[q * 32] = fma (w, vlast[q], a[q * 32]);
+              else if (OP == L_LSE) a[q * 32] = l_lse (a[q * 32], vlast[q] + w);
+              else { const double c = vlast[q] + w; if (a[q * 32] < c) { a[q * 32] = c; hubDB[u.z * LPT + q * 32] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
+            }
+          }
+          if (ctl & L2_PRESTORE) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              hubD[L2_HD (ctl) * LPT + q * 32] = acc[q];
+              if (OP == L_MAX) hubDB[L2_HD (ctl) * LPT + q * 32] = best[q];
+              acc[q] = ZERO; best[q] = 0xffffu;
+            }
+          }
+          if (ctl & L2_END) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              win[(d & winMask) * LPT + q * 32] = acc[q];
+              vlast[q] = acc[q];
+              if (ctl & L2_LIVE) curOut[q * 32] = acc[q];
+              if (ctl & L2_HSTORE) hubS[L2_HS (ctl) * LPT + q * 32] = acc[q];
+              if (OP == L_SUM) {
+                const int hi = __double2hiint (acc[q]);
+                mx[q] = max (mx[q], hi);
+                mn[q] = min (mn[q], (unsigned) (hi - 0x00100000));      // zeros and denormals wrap to the top and drop out
+              } else if (OP == L_MAX && bpRow) {
+                if (p.bpBytes == 1) bpRow[q * 32] = (unsigned char) best[q]; else reinterpret_cast<uint16_t*> (bpRow)[q * 32] = (uint16_t) best[q];
+              }
+              res[q] = acc[q];      // after the last record: the end state
+              acc[q] = ZERO;
+              best[q] = 0xffffu;
+            }
+            if (ctl & L2_LIVE) curOut += LPT;
+            if (OP == L_MAX && bpRow) bpRow += LPT * p.bpBytes;
+            ++d;
+          }
+        }
+      }
+      if (usePrev) l2_wait (0);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (OP == L_SUM) {
+          int Gc = L_SENT;
+          if (mx[q] >= 0x00100000) {
+            const int emx = mx[q] >> 20;
+            Gc = F[q] + emx - 1023;
+            if (o <= Lo[q] && (emx == 0x7ff || (mn[q] != 0xffffffffu && emx - (int) ((mn[q] >> 20) + 1) > L_SPREAD))) bad[q] = true;
+          }
+          Fprev[q] = F[q]; Gprev[q] = Gc;
+        }
+        if (o == Lo[q]) {
+          if (OP == L_SUM) { p.result[k[q]] = res[q] > 0. ? log (res[q]) + F[q] * LN2 : l_ninf(); p.flag[k[q]] = bad[q] || !(res[q] > 0.) || !(res[q] < 1e300); }
+          else p.result[k[q]] = res[q];
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 struct LBuf {
@@ -370,7 +914,8 @@ struct LBuf {
 // independent chain per thread makes up for the missing warps in the sums (65 536 reads: 40 -> 89 GCUPS),
 // while the max-plus sweep, which carries a pointer per chain, stays at one.
 static int lane_reads_per_lane (const mb_machine* m, const LHost* h, int64_t nWork, int op) {
-  if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
+  if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? (h->l2.ok ? 2 : 4) : r >= 2 ? 2 : 1; }
+  if (h->l2.ok) return 1;
   if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
@@ -411,9 +956,55 @@ static int lane_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>
   return 0;
 }
 
+// the windowed sweep (lane2): as many warps per SM as shared memory holds
+template<int OP, int R>
+static int lane2_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
+                           unsigned char* dBp, const int64_t* dBpOff) {
+  LHost* h = lh (m);
+  const L2Prog& P = h->l2;
+  constexpr int LPT = 32 * R;
+  const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + LPT - 1) / LPT;
+  const size_t perWarp = (size_t) (P.WN + P.RN + P.nHubS + P.nHubD) * LPT * 8 + (OP == L_MAX ? (size_t) P.nHubD * LPT * 4 : 0);
+  const size_t kSmem = 227 * 1024 - 1024;
+  int warpsPerSM = (int) std::min<size_t> (kSmem / perWarp, 32);
+  if (m->opt.has ("lane_warps")) warpsPerSM = std::max (1, std::min (warpsPerSM, m->opt.get ("lane_warps", 16)));
+  if (warpsPerSM < 1) { set_error ("lane engine: the window does not fit in shared memory"); return 1; }
+  // CTAs of 2 warps (of 1 when few tasks or little room): a fine grain for the task counter
+  const int wpc = (warpsPerSM >= 2 && nTasks >= (int64_t) h->numSMs * 2) ? 2 : 1;
+  const int ctasPerSM = std::max (1, warpsPerSM / wpc);
+  const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + wpc - 1) / wpc, (int64_t) ctasPerSM * h->numSMs));
+  const size_t smem = perWarp * wpc;
+  MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  b->wsOrderHoldsFull = false;
+  int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
+  unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * wpc * 2 * std::max (P.nLive, 1) * LPT * 8);
+  if (!dOrder || !dCounter || !dVec) return 1;
+  MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
+  MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
+  L2Params p {};
+  p.rec = OP == L_SUM ? P.dRecLin : P.dRecLog;
+  p.blkRec = P.dBlk; p.blkLoad = P.dBlk + P.blkRec.size(); p.loadIdx = P.dBlk + P.blkRec.size() + P.blkLoad.size();
+  p.nBlk = P.nBlk; p.LA = P.LA; p.WN = P.WN; p.RN = P.RN; p.nHubS = P.nHubS; p.nHubD = P.nHubD; p.nLive = P.nLive;
+  p.em = OP == L_SUM ? h->dEmLin : h->dEmLog; p.emIdx = h->dEmIdx;
+  p.S = h->S; p.nOut = h->nOut; p.bpBytes = h->bpBytes;
+  p.b = b->dev;
+  p.order = dOrder; p.nWork = nWork; p.counter = dCounter;
+  p.result = dResult; p.flag = dFlag; p.vec = dVec;
+  p.bp = dBp; p.bpOff = dBpOff;
+  if (m->opt.get ("verbose", 0))
+    fprintf (stderr, "lane engine (windowed): %lld reads, R=%d, grid %d x %d threads, %zu B smem per CTA (%d warps per SM), window %d, ring %d, hubs %d + %d, %d live of %d states, %lld records\n",
+             (long long) nWork, R, grid, 32 * wpc, smem, ctasPerSM * wpc, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, h->S, (long long) P.recLin.size());
+  lane2_kernel<OP, R><<<grid, 32 * wpc, smem, b->stream>>> (p);
+  MB_CUDA (cudaGetLastError());
+  return 0;
+}
+
 template<int OP>
 static int lane_launch (mb_machine* m, mb_batch* b, int R, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
                         unsigned char* dBp, const int64_t* dBpOff) {
+  if (lh (m)->l2.ok)
+    return R >= 2 ? lane2_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff) : lane2_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);
   return R == 4 ? lane_launch_r<OP, 4> (m, b, order, dResult, dFlag, dBp, dBpOff)
        : R == 2 ? lane_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff)
                 : lane_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);

@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+cd ${GRAFT_REPO_ROOT:-.}
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests -m gpu -q -x -k "lane or hmmer or unitindel or counter or group" ) > gpurun_out/pytest_gpu5.log 2>&1
+tail -8 gpurun_out/pytest_gpu5.log
+timeout 900 python tools/lane_variants.py > gpurun_out/lane_variants.jsonl 2> gpurun_out/lane_variants.err
+cat gpurun_out/lane_variants.jsonl; grep "lane engine" gpurun_out/lane_variants.err | sort | uniq -c | head; tail -2 gpurun_out/lane_variants.err
+MACHINE=PF00516_protpsw READS=16384 VARIANTS='[{}, {"lane_r": 2}, {"lane_old": 1}]' timeout 600 python tools/lane_variants.py > gpurun_out/lane_variants_c.jsonl 2>> gpurun_out/lane_variants.err
+cat gpurun_out/lane_variants_c.jsonl
