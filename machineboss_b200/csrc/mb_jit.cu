@@ -774,7 +774,6 @@ static void fill_weights (const mb_machine* m, JitEngine& J, std::vector<double>
 
 // score module: row-layout tables and the parameter block of the normalised linear kernels
 static int upload_row_tables (const mb_machine* m, JitEngine& J) {
-  if (!J.modV) return 0;
   RowTables f, b;
   row_tables (m, J.fwd, true, f);
   row_tables (m, J.bwd, false, b);
@@ -861,7 +860,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   const int passC = pass ? J.CV : J.C, passMinBlocks = pass ? J.minBlocksV : J.minBlocks;
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
-  if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n#define MB_ROWTAB 1\n";
+  if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n";
+  o << "#define MB_ROWTAB 1\n";      // the score kernels of both modules read row-layout tables; the E-step and log-domain kernels keep the indexed ones
   o << "#define MB_STEADY_UNROLL " << std::max (1, std::min (4, m->opt.get ("jit_unroll", pass ? 2 : 1))) << "\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
   o << "#define MB_S " << m->S << "\n#define MB_C " << passC << "\n#define MB_NIN " << m->nIn << "\n#define MB_NOUT " << m->nOut << "\n";
@@ -876,7 +876,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
   o << "__device__ __forceinline__ double mb_neg_inf();\n__device__ __forceinline__ double mb_lse (double, double);\n";
   o << "__device__ __forceinline__ float mb_post (double);\n__device__ __forceinline__ float mb_warp_sum (float);\n__device__ __forceinline__ double mb_warp_sum_d (double);\n\n";
-  if (pass) {
+  {
     // row-layout emission tables and the normalised linear parameter block (see Program::WA, Program::unitSlot)
     o << "// MB_ROWCELLS_BEGIN (the host harness of tests/test_jit_rowcells_host.py compiles from here to MB_ROWCELLS_END)\n";
     o << "#define MB_WA_F " << J.fwd.WA << "\n#define MB_WB_F " << J.fwd.WB << "\n#define MB_WA_B " << J.bwd.WA << "\n#define MB_WB_B " << J.bwd.WB << "\n";
@@ -884,7 +884,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
     o << "#ifndef MB_LDS\n"
          "template<int OFF> __device__ __forceinline__ double mb_lds (const unsigned addr) { double v; asm (\"ld.shared.f64 %0, [%1+%2];\" : \"=d\"(v) : \"r\"(addr), \"n\"(OFF)); return v; }\n"
          "#define MB_LDS(addr, off) mb_lds<off> (addr)\n#endif\n";
-    o << "#define MB_PKW " << (J.CV * J.tbBytes + 3) / 4 << "      // 32-bit words of packed back-pointers per lane and step\n";
+    o << "#define MB_PKW " << (passC * J.tbBytes + 3) / 4 << "      // 32-bit words of packed back-pointers per lane and step\n";
     o << "#ifndef MB_HOST_HARNESS\n"
          "// n = max (n, t) with the reference's tie-break (a later candidate wins only if strictly greater); with PTR the\n"
          "// winner's field value replaces the field in `word`: (word & ~field) | val, or a plain OR for a one-bit field\n"
@@ -1061,10 +1061,9 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
                    const CountArgs& ca = CountArgs(), bool narrow = false) {
   JitEngine& J = *(JitEngine*) m->jit;
   const bool scoreKernel = which == 2 || which == 5 || which == 6 || which == 9;
-  // the score module's linear sweeps are the normalised ones: without usable unit weights the first module's take over
-  if (J.modV && (which == 5 || which == 6) && !J.normOK) narrow = true;
+  if ((which == 5 || which == 6) && !J.normOK) { set_error ("jit engine: the normalised linear sweep was asked for a machine whose unit weights cannot be divided out"); return 1; }
   narrow = narrow && J.modV && scoreKernel;
-  const bool rowTab = J.modV && scoreKernel && !narrow;      // score module: row-layout tables
+  const bool rowTab = scoreKernel;      // the score kernels of both modules read the row-layout tables
   const int slot = which;
   CUfunction fn = narrow ? (which == 2 ? J.kViterbiN : which == 5 ? J.kForwardLinN : which == 6 ? J.kBackwardLinN : J.kViterbiScoreN)
     : which == 9 ? J.kViterbiScore : which == 0 ? J.kForward : which == 1 ? J.kBackward : which == 2 ? J.kViterbi : which == 3 ? J.kFStore : which == 4 ? J.kBCounts : which == 5 ? J.kForwardLin : which == 6 ? J.kBackwardLin : which == 7 ? J.kFStoreLin : J.kBCountsLin;
@@ -1113,9 +1112,10 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
   if (!dRes) return 1;
   if (timing_begin (b)) return 1;
   int64_t launches = 1;
-  if (J.linearOK) {
-    // scaled linear-domain sweep; pairs it flags (dangerous dynamic range) or scores -inf are
-    // re-run with the log-domain kernel, which has no range limit
+  if (J.linearOK && J.normOK) {
+    // scaled linear-domain sweep (normalised: see Program::unitSlot; a machine whose unit weights cannot be divided
+    // out -- a silent transition of weight 0 -- takes the log-domain kernel); pairs it flags (dangerous dynamic
+    // range) or scores -inf are re-run with the log-domain kernel, which has no range limit
     int32_t* dFlag = (int32_t*) ws_reserve (b, WS_FLAG, (size_t) b->nPairs * 4);
     if (!dFlag) return 1;
     CountArgs ca;

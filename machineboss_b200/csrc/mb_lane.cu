@@ -72,7 +72,12 @@ struct LRec { double w; uint32_t src; uint32_t ctl; };      // src: source state
 // and registers.  The program is checked when it is built (every window, ring and hub access provably hits the
 // value it means to); a machine whose structure does not fit keeps the first version of the sweep.
 // ---------------------------------------------------------------------------------------------
-enum { K_EMIT = 0, K_WIN = 1, K_HUBS = 2, K_PUSH = 3, K_NONE = 4 };
+enum { K_EMIT = 0, K_WIN = 1, K_HUBS = 2, K_PUSH = 3, K_NONE = 4, K_LOAD = 5, K_CTRL = 6 };
+#define L3_NREC 64          // records per chunk
+#define L3_EMAX 16          // emission rows per chunk
+#define L3_COMMIT 1u        // K_CTRL (in the record's `src` field): close the group of ring loads issued so far
+#define L3_WAIT 2u          // K_CTRL: wait until all but the last LA groups have landed (the next block's values are in the ring)
+#define L3_ORIGIN 4u        // K_CTRL: the accumulator takes the origin cell's start value
 #define L2_SCALE 8u         // last emitting term of its destination: bring the sum into this cell's frame
 #define L2_END 16u          // finalise the destination after this record
 #define L2_LIVE 32u         // ... and store it to the live vector
@@ -92,8 +97,18 @@ struct L2Prog {
   std::vector<int64_t> recPerm;             // silent (window / hub / push) record -> hInc entry, -1 otherwise
   std::vector<int32_t> recWant;             // (host only) what the record means to read: live index (emit), source state (window, hub source)
   std::vector<int32_t> blkRec, blkLoad, loadIdx;
-  LRec* dRecLin = nullptr; LRec* dRecLog = nullptr;
-  int32_t* dBlk = nullptr;                  // blkRec | blkLoad | loadIdx on the device
+  // The program as the kernel reads it: ONE flat stream per cell -- the ring loads of a block (K_LOAD) and the group
+  // commit / wait points (K_CTRL) are records like the others -- cut into CHUNKS of at most L3_NREC records that use at
+  // most L3_EMAX emission rows; a chunk is one contiguous blob (records | its emission rows, nOut doubles each |
+  // their candidate indices) that a CTA fetches with ONE bulk copy (TMA) into shared memory, double buffered, while
+  // its warps -- all walking the same program position on different reads -- work through the previous chunk.
+  std::vector<LRec> flat;                   // weights filled per blob
+  std::vector<int64_t> flatPerm;            // silent record -> hInc entry (-1 otherwise)
+  std::vector<int32_t> flatWant, flatRow;   // (host) what a record means to read; table row of an emitting record
+  std::vector<int32_t> chunkFirst;          // [nChunks + 1] first flat record of each chunk
+  int nChunks = 0, blobBytes = 0, emOff = 0, idxOff = 0;
+  std::vector<char> blobLin, blobLog;
+  char* dBlobLin = nullptr; char* dBlobLog = nullptr;
 };
 
 struct LHost {
@@ -303,7 +318,7 @@ static void lane_fill_weights (const mb_machine* m, LHost* h) {
 void lane_destroy (mb_machine* m) {
   LHost* h = lh (m);
   if (!h) return;
-  for (void* p: { (void*) h->dRecLin, (void*) h->dRecLog, (void*) h->dEmLin, (void*) h->dEmLog, (void*) h->dEmIdx, (void*) h->l2.dRecLin, (void*) h->l2.dRecLog, (void*) h->l2.dBlk }) if (p) cudaFree (p);
+  for (void* p: { (void*) h->dRecLin, (void*) h->dRecLog, (void*) h->dEmLin, (void*) h->dEmLog, (void*) h->dEmIdx, (void*) h->l2.dBlobLin, (void*) h->l2.dBlobLog }) if (p) cudaFree (p);
   delete h;
   m->lane = nullptr;
 }
@@ -532,32 +547,92 @@ static bool lane2_try (const mb_machine* m, LHost* h, int WN, int RN, int BS, in
   return true;
 }
 
+// the flat stream: per block its K_LOAD records travel LA blocks ahead of the block itself
+static void lane2_flatten (LHost* h) {
+  L2Prog& P = h->l2;
+  auto ctrl = [&] (uint32_t what) { P.flat.push_back (l2_rec (K_CTRL, what, 0)); P.flatPerm.push_back (-1); P.flatWant.push_back (-1); P.flatRow.push_back (-1); };
+  auto loads = [&] (int blk) {
+    if (blk < P.nBlk)
+      for (int j = P.blkLoad[blk]; j < P.blkLoad[blk + 1]; ++j) {
+        P.flat.push_back (l2_rec (K_LOAD, (uint32_t) P.loadIdx[j], 0));
+        P.flatPerm.push_back (-1); P.flatWant.push_back (P.loadIdx[j]); P.flatRow.push_back (-1);
+      }
+    ctrl (L3_COMMIT);      // (an empty group keeps the count uniform)
+  };
+  for (int blk = 0; blk < std::min (P.LA, P.nBlk); ++blk) loads (blk);
+  for (int blk = 0; blk < P.nBlk; ++blk) {
+    if (blk + P.LA < P.nBlk) loads (blk + P.LA); else ctrl (L3_COMMIT);
+    ctrl (L3_WAIT | (blk == 1 ? L3_ORIGIN : 0u));
+    for (int n = P.blkRec[blk]; n < P.blkRec[blk + 1]; ++n) {
+      P.flat.push_back (P.recLin[n]);
+      P.flatPerm.push_back (P.recPerm[n]);
+      P.flatWant.push_back (P.recWant[n]);
+      uint64_t row = 0;
+      if ((P.recLin[n].ctl & 7u) == K_EMIT) memcpy (&row, &P.recLin[n].w, 8);
+      P.flatRow.push_back ((P.recLin[n].ctl & 7u) == K_EMIT ? (int32_t) row : -1);
+    }
+  }
+  // chunks
+  P.chunkFirst.assign (1, 0);
+  int nRec = 0, nEm = 0;
+  for (size_t n = 0; n < P.flat.size(); ++n) {
+    const bool isEmit = (P.flat[n].ctl & 7u) == K_EMIT;
+    if (nRec == L3_NREC || (isEmit && nEm == L3_EMAX)) { P.chunkFirst.push_back ((int32_t) n); nRec = 0; nEm = 0; }
+    ++nRec;
+    if (isEmit) ++nEm;
+  }
+  P.chunkFirst.push_back ((int32_t) P.flat.size());
+  P.nChunks = (int) P.chunkFirst.size() - 1;
+  P.emOff = L3_NREC * (int) sizeof (LRec);
+  P.idxOff = P.emOff + L3_EMAX * std::max (h->nOut, 1) * 8;
+  P.blobBytes = (P.idxOff + L3_EMAX * std::max (h->nOut, 1) * 2 + 15) & ~15;
+}
+
+// blobs for the current weights: the records (silent weights inside), each chunk's emission rows and candidate indices
 static void lane2_fill_weights (const mb_machine* m, LHost* h) {
   L2Prog& P = h->l2;
-  for (size_t n = 0; n < P.recPerm.size(); ++n) {
-    if (P.recPerm[n] < 0) continue;
-    const double lw = m->hInc.lw[P.recPerm[n]];
-    P.recLog[n].w = lw;
-    P.recLin[n].w = exp (lw);
+  const int nOut = std::max (h->nOut, 1);
+  P.blobLin.assign ((size_t) P.nChunks * P.blobBytes, 0);
+  P.blobLog = P.blobLin;
+  for (int c = 0; c < P.nChunks; ++c) {
+    char* bl = P.blobLin.data() + (size_t) c * P.blobBytes;
+    char* bg = P.blobLog.data() + (size_t) c * P.blobBytes;
+    int nEm = 0;
+    for (int n = P.chunkFirst[c]; n < P.chunkFirst[c + 1]; ++n) {
+      LRec rl = P.flat[n], rg = P.flat[n];
+      const uint32_t kind = rl.ctl & 7u;
+      if (kind == K_EMIT) {
+        const uint64_t local = (uint64_t) nEm;      // the row's place in this chunk's emission area
+        memcpy (&rl.w, &local, 8); memcpy (&rg.w, &local, 8);
+        for (int t = 0; t < h->nOut; ++t) {
+          ((double*) (bl + P.emOff))[nEm * nOut + t] = h->emLin[(size_t) P.flatRow[n] * h->nOut + t];
+          ((double*) (bg + P.emOff))[nEm * nOut + t] = h->emLog[(size_t) P.flatRow[n] * h->nOut + t];
+          ((uint16_t*) (bl + P.idxOff))[nEm * nOut + t] = ((uint16_t*) (bg + P.idxOff))[nEm * nOut + t] = h->emIdx[(size_t) P.flatRow[n] * h->nOut + t];
+        }
+        ++nEm;
+      } else if (P.flatPerm[n] >= 0) {
+        const double lw = m->hInc.lw[P.flatPerm[n]];
+        rg.w = lw;
+        rl.w = exp (lw);
+      }
+      memcpy (bl + (size_t) (n - P.chunkFirst[c]) * sizeof (LRec), &rl, sizeof (LRec));
+      memcpy (bg + (size_t) (n - P.chunkFirst[c]) * sizeof (LRec), &rg, sizeof (LRec));
+    }
+    // the rest of the record area: records that do nothing
+    for (int n = P.chunkFirst[c + 1] - P.chunkFirst[c]; n < L3_NREC; ++n) {
+      const LRec r = l2_rec (K_NONE, 0, 0);
+      memcpy (bl + (size_t) n * sizeof (LRec), &r, sizeof (LRec));
+      memcpy (bg + (size_t) n * sizeof (LRec), &r, sizeof (LRec));
+    }
   }
 }
 
 static int lane2_upload (mb_machine* m, LHost* h, bool all) {
   L2Prog& P = h->l2;
   if (!P.ok) return 0;
-  const size_t rb = P.recLin.size() * sizeof (LRec);
-  if (all) {
-    MB_CUDA (cudaMalloc (&P.dRecLin, rb)); MB_CUDA (cudaMalloc (&P.dRecLog, rb));
-    std::vector<int32_t> blk;
-    blk.insert (blk.end(), P.blkRec.begin(), P.blkRec.end());
-    blk.insert (blk.end(), P.blkLoad.begin(), P.blkLoad.end());
-    blk.insert (blk.end(), P.loadIdx.begin(), P.loadIdx.end());
-    blk.push_back (0);
-    MB_CUDA (cudaMalloc (&P.dBlk, blk.size() * 4));
-    MB_CUDA (cudaMemcpy (P.dBlk, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice));
-  }
-  MB_CUDA (cudaMemcpy (P.dRecLin, P.recLin.data(), rb, cudaMemcpyHostToDevice));
-  MB_CUDA (cudaMemcpy (P.dRecLog, P.recLog.data(), rb, cudaMemcpyHostToDevice));
+  if (all) { MB_CUDA (cudaMalloc (&P.dBlobLin, P.blobLin.size())); MB_CUDA (cudaMalloc (&P.dBlobLog, P.blobLog.size())); }
+  MB_CUDA (cudaMemcpy (P.dBlobLin, P.blobLin.data(), P.blobLin.size(), cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (P.dBlobLog, P.blobLog.data(), P.blobLog.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -565,7 +640,7 @@ int lane2_info (const mb_machine* m, int32_t* info) {
   LHost* h = lh (m);
   if (!h) { set_error ("lane engine not prepared"); return 1; }
   const L2Prog& P = h->l2;
-  const int32_t v[8] = { P.ok ? 1 : 0, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, (int32_t) P.recLin.size(), h->bpBytes };
+  const int32_t v[8] = { P.ok ? 1 : 0, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, (int32_t) P.flat.size(), h->bpBytes };
   for (int q = 0; q < 8; ++q) info[q] = v[q];
   if (!P.ok) set_error ("lane2: " + P.why);
   return 0;
@@ -576,20 +651,19 @@ static void lane2_build (const mb_machine* m, LHost* h) {
   const int BS = std::max (1, std::min (64, m->opt.get ("lane_bs", 8))), LA = std::max (1, std::min (8, m->opt.get ("lane_la", 3)));
   for (int WN: { 32, 64, 128 }) {
     if (m->opt.has ("lane_wn") && WN != m->opt.get ("lane_wn", 32)) continue;
-    for (int RN: { 16, 32, 64, 128 }) if (lane2_try (m, h, WN, RN, BS, LA)) return;
+    for (int RN: { 16, 32, 64, 128 }) if (lane2_try (m, h, WN, RN, BS, LA)) { lane2_flatten (h); return; }
   }
 }
 
-// The program executed for ONE read on the host, slot for slot as the kernel does it (same window, ring and hub
-// arithmetic, with every slot tagged so that a stale read is an error): what the CPU test checks against the oracle.
-// op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
+// The program executed for ONE read on the host, chunk by chunk and slot by slot as the kernel does it (the same blobs,
+// the same window, ring and hub arithmetic, with every slot tagged so that a stale read is an error): what the CPU test
+// checks against the oracle.  op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
 int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut) {
   LHost* h = lh (m);
   if (!h || !h->l2.ok) { set_error (std::string ("lane2: no windowed program for this machine") + (h ? ": " + h->l2.why : std::string())); return 1; }
   const L2Prog& P = h->l2;
-  const std::vector<LRec>& rec = op == L_SUM ? P.recLin : P.recLog;
-  const std::vector<double>& em = op == L_SUM ? h->emLin : h->emLog;
-  const int nOut = h->nOut, S = h->S;
+  const std::vector<char>& blob = op == L_SUM ? P.blobLin : P.blobLog;
+  const int nOut = std::max (h->nOut, 1), S = h->S;
   const double ZERO = op == L_SUM ? 0. : -INFINITY, ONE = op == L_SUM ? 1. : 0.;
   const unsigned kb = h->bpBytes == 1 ? 6 : 14;
   auto lse = [] (double a, double b) { const double mx = std::max (a, b), mn = std::min (a, b); return mn == -INFINITY ? mx : mx + log1p (exp (mn - mx)); };
@@ -597,12 +671,10 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
   std::vector<int> winTag ((size_t) P.WN, -1), ringTag ((size_t) P.RN, -1), hubSTag (L2_MAXHUB, -1);
   std::vector<uint32_t> hubDB (L2_MAXHUB);
   live[0].assign ((size_t) std::max (P.nLive, 1), ZERO); live[1] = live[0];
-  // which state sits in which slot is recomputed from the program: d counts END records, live index counts L2_LIVE
   int Fprev = 0, Gprev = L_SENT;
   double res = ZERO;
   int Fres = 0;
   if (bpOut) bpOut->assign ((size_t) (Lo + 1) * S, 0xffffu);
-  // static map live index -> state, for the ring tags
   for (int64_t o = 0; o <= Lo; ++o) {
     std::vector<double>& cur = live[o & 1];
     const std::vector<double>& prev = live[(o & 1) ^ 1];
@@ -618,37 +690,52 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
     uint32_t best = 0xffffu;
     int mx = 0; unsigned mn = 0xffffffffu;
     int d = 0, nl = 0;
-    auto issue = [&] (int b) { for (int j = P.blkLoad[b]; j < P.blkLoad[b + 1]; ++j) { const int li = P.loadIdx[j]; ring[li & (P.RN - 1)] = prev[li]; ringTag[li & (P.RN - 1)] = li; } };
-    for (int b = 0; b < std::min (P.LA, P.nBlk); ++b) issue (b);
-    for (int b = 0; b < P.nBlk; ++b) {
-      if (b + P.LA < P.nBlk) issue (b + P.LA);
-      if (b == 1) acc = o == 0 ? ONE : ZERO;      // the origin cell's start state (forward.defs.h:36), after the preamble
-      for (int n = P.blkRec[b]; n < P.blkRec[b + 1]; ++n) {
-        const LRec& r = rec[n];
+    // ring loads land when their group is waited for: pending[g] = loads of group g; a WAIT completes all but the last LA groups
+    std::vector<std::vector<int>> pending (1);
+    size_t landed = 0;
+    for (int c = 0; c < P.nChunks; ++c) {
+      const char* bl = blob.data() + (size_t) c * P.blobBytes;
+      const double* em = (const double*) (bl + P.emOff);
+      const uint16_t* emIdx = (const uint16_t*) (bl + P.idxOff);
+      for (int q = 0; q < L3_NREC; ++q) {
+        LRec r;
+        memcpy (&r, bl + (size_t) q * sizeof (LRec), sizeof (LRec));
+        const int n = P.chunkFirst[c] + q;      // (flat index, for the tags; records past the chunk's end do nothing)
         const uint32_t ctl = r.ctl, kind = ctl & 7u;
+        if (kind == K_LOAD) { if (o > 0) pending.back().push_back ((int) r.src); continue; }
+        if (kind == K_CTRL) {
+          if (r.src & L3_COMMIT) pending.emplace_back();
+          if (r.src & L3_WAIT) {
+            const size_t done = pending.size() - 1 > (size_t) P.LA ? pending.size() - 1 - (size_t) P.LA : 0;      // closed groups: all but the open one
+            for (; landed < done; ++landed) for (int li: pending[landed]) { ring[li & (P.RN - 1)] = prev[li]; ringTag[li & (P.RN - 1)] = li; }
+          }
+          if (r.src & L3_ORIGIN) acc = o == 0 ? ONE : ZERO;      // the origin cell's start state (forward.defs.h:36), after the preamble
+          continue;
+        }
         if (ctl & L2_HINIT) { acc = hubD[L2_HD (ctl)]; best = hubDB[L2_HD (ctl)]; }
         if (kind == K_EMIT) {
           if (o > 0) {
             uint64_t row; memcpy (&row, &r.w, 8);
+            if (row >= L3_EMAX) { set_error ("lane2 emulation: an emission row outside the chunk's area"); return 1; }
             const double x = ring[r.src], w = em[(size_t) row * nOut + tok];
-            if (ringTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a ring slot does not hold the previous-cell value the term means to read"); return 1; }
+            if (ringTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a ring slot does not hold the previous-cell value the term means to read"); return 1; }
             if (op == L_SUM) acc = fma (w, x, acc);
             else if (op == L_LSE) acc = lse (acc, x + w);
-            else { const double c = x + w; if (acc < c) { acc = c; best = ((uint32_t) T_INSERT << kb) | h->emIdx[(size_t) row * nOut + tok]; } }
+            else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_INSERT << kb) | emIdx[(size_t) row * nOut + tok]; } }
           }
           if (op == L_SUM && (ctl & L2_SCALE)) acc *= f;
         } else if (kind == K_WIN || kind == K_HUBS) {
-          if (kind == K_WIN && winTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a window slot does not hold the state the term means to read"); return 1; }
-          if (kind == K_HUBS && hubSTag[r.src] != P.recWant[n]) { set_error ("lane2 emulation: a hub source is read before it has been written"); return 1; }
+          if (kind == K_WIN && winTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a window slot does not hold the state the term means to read"); return 1; }
+          if (kind == K_HUBS && hubSTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a hub source is read before it has been written"); return 1; }
           const double x = kind == K_WIN ? win[r.src] : hubS[r.src];
           if (op == L_SUM) acc = fma (r.w, x, acc);
           else if (op == L_LSE) acc = lse (acc, x + r.w);
-          else { const double c = x + r.w; if (acc < c) { acc = c; best = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
+          else { const double cnd = x + r.w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
         } else if (kind == K_PUSH) {
           double& a = hubD[r.src];
           if (op == L_SUM) a = fma (r.w, vlast, a);
           else if (op == L_LSE) a = lse (a, vlast + r.w);
-          else { const double c = vlast + r.w; if (a < c) { a = c; hubDB[r.src] = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
+          else { const double cnd = vlast + r.w; if (a < cnd) { a = cnd; hubDB[r.src] = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
         }
         if (ctl & L2_PRESTORE) { hubD[L2_HD (ctl)] = acc; hubDB[L2_HD (ctl)] = best; acc = ZERO; best = 0xffffu; }
         if (ctl & L2_END) {
@@ -679,21 +766,24 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// lane2: the kernel.  One warp = 32 * R reads; shared memory per warp: the window, the ring, the hub slots
-// (rows of 32 * R doubles, a lane's R reads 32 apart: every access of the warp is one conflict-free 256-byte row).
+// lane2: the kernel.  A CTA of W warps = 32 W reads; its warps walk the SAME program position, so the program is
+// fetched once per CTA: thread 0 issues one bulk copy (TMA, cp.async.bulk + mbarrier) per chunk into a double
+// buffer in shared memory while the warps work through the previous chunk, and every record, emission weight
+// and state value a term needs is then a shared-memory read.  Per warp: the window, the ring, the hub slots
+// (rows of 32 doubles: every access of the warp is one conflict-free 256-byte row).  Global memory sees the
+// tokens, the live vectors (out once, back in once through the ring, per cell) and the Viterbi back-pointers.
 // ---------------------------------------------------------------------------------------------
 struct L2Params {
-  const LRec* rec;
-  const int32_t* blkRec; const int32_t* blkLoad; const int32_t* loadIdx;
-  int32_t nBlk, LA, WN, RN, nHubS, nHubD, nLive;
-  const double* em; const uint16_t* emIdx;
+  const char* blob;
+  int32_t nChunks, blobBytes, emOff, idxOff;
+  int32_t LA, WN, RN, nHubS, nHubD, nLive;
   int32_t S, nOut, bpBytes;
   DevBatch b;
-  const int64_t* order; int64_t nWork;
+  const int64_t* order; int64_t nWork;       // reads, longest first; task n = reads [32n, 32n+32)
   unsigned long long* counter;
   double* result; int32_t* flag;
-  double* vec;                                // per resident warp: 2 live vectors of nLive * 32 * R doubles
-  unsigned char* bp; const int64_t* bpOff;
+  double* vec;                                // per resident warp: 2 live vectors of nLive * 32 doubles
+  unsigned char* bp; const int64_t* bpOff;   // back-pointers of task n at bpOff[n]: [o][state][lane]
 };
 
 __device__ __forceinline__ void l2_cp_async8 (void* smem, const void* gmem) {
@@ -711,193 +801,174 @@ __device__ __forceinline__ void l2_wait (const int pending) {      // at most `p
   else if (pending == 7) asm volatile ("cp.async.wait_group 7;" ::: "memory");
   else asm volatile ("cp.async.wait_group 8;" ::: "memory");
 }
+// one-dimensional bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void l2_mbar_init (const unsigned mbar, const unsigned count) { asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void l2_bulk_load (const unsigned dst, const void* src, const unsigned bytes, const unsigned mbar) {
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void l2_mbar_wait (const unsigned mbar, const unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  } while (!ok);
+}
 
-template<int OP, int R>
-__global__ void __launch_bounds__(128) lane2_kernel (const __grid_constant__ L2Params p) {
-  extern __shared__ double l2smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-  constexpr int LPT = 32 * R;
+template<int OP>
+__global__ void __launch_bounds__(256) lane2_kernel (const __grid_constant__ L2Params p) {
+  extern __shared__ __align__(16) char l2smemRaw[];
+  __shared__ long long sTask;
+  __shared__ int sMaxLo;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
+  // shared memory: two chunk buffers | two mbarriers | per warp: window, ring, hub sources, hub destinations | (L_MAX) hub-destination pointers
+  char* buf0 = l2smemRaw;
+  const unsigned bufAddr = (unsigned) __cvta_generic_to_shared (buf0);
+  const unsigned mbarAddr = bufAddr + 2u * (unsigned) p.blobBytes;
+  double* warpBase = reinterpret_cast<double*> (l2smemRaw + 2 * p.blobBytes + 16);
   const int rows = p.WN + p.RN + p.nHubS + p.nHubD;
-  double* win = l2smem + (size_t) warp * rows * LPT + lane;
-  double* ring = win + p.WN * LPT;
-  double* hubS = ring + p.RN * LPT;
-  double* hubD = hubS + p.nHubS * LPT;
-  unsigned* hubDB = reinterpret_cast<unsigned*> (l2smem + (size_t) nWarps * rows * LPT) + (size_t) warp * p.nHubD * LPT + lane;      // L_MAX only
-  double* v0 = p.vec + ((size_t) blockIdx.x * nWarps + warp) * 2 * (size_t) p.nLive * LPT + lane;
-  double* v1 = v0 + (size_t) p.nLive * LPT;
+  double* win = warpBase + (size_t) warp * rows * 32 + lane;
+  double* ring = win + p.WN * 32;
+  double* hubS = ring + p.RN * 32;
+  double* hubD = hubS + p.nHubS * 32;
+  unsigned* hubDB = reinterpret_cast<unsigned*> (warpBase + (size_t) nWarps * rows * 32) + (size_t) warp * p.nHubD * 32 + lane;      // L_MAX only
+  double* v0 = p.vec + ((size_t) blockIdx.x * nWarps + warp) * 2 * (size_t) p.nLive * 32 + lane;
+  double* v1 = v0 + (size_t) p.nLive * 32;
   const double ZERO = OP == L_SUM ? 0. : l_ninf(), ONE = OP == L_SUM ? 1. : 0.;
   const unsigned kb = p.bpBytes == 1 ? 6 : 14;
   const double LN2 = 0.693147180559945309417232121458;
   const int winMask = p.WN - 1, ringMask = p.RN - 1;
+  if (tid == 0) {
+    l2_mbar_init (mbarAddr, 1);
+    l2_mbar_init (mbarAddr + 8, 1);
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase0 = 0, phase1 = 0;      // parity of the next completion of each buffer's mbarrier
   for (;;) {
-    long long task = 0;
-    if (lane == 0) task = (long long) atomicAdd (p.counter, 1ULL);
-    task = __shfl_sync (0xffffffffu, task, 0);
-    if (task * LPT >= p.nWork) break;
-    int64_t k[R];
-    const uint8_t* y[R];
-    int Lo[R], maxLo = -1;
+    __syncthreads();      // (sTask, sMaxLo of the previous round have been read by everyone)
+    if (tid == 0) { sTask = (long long) atomicAdd (p.counter, (unsigned long long) nWarps); sMaxLo = -1; }
+    __syncthreads();
+    const long long task = sTask + warp;
+    if (sTask * 32 >= p.nWork) break;
+    const long long rd = task * 32 + lane;
+    const bool have = rd < p.nWork;
+    const int64_t k = have ? p.order[rd] : 0;
+    const uint8_t* y = p.b.y + p.b.yOff[k];
+    const int Lo = have ? (int) (p.b.yOff[k + 1] - p.b.yOff[k]) : -1;
+    int warpMaxLo = Lo;
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const long long rd = task * LPT + q * 32 + lane;
-      const bool have = rd < p.nWork;
-      k[q] = have ? p.order[rd] : 0;
-      y[q] = p.b.y + p.b.yOff[k[q]];
-      Lo[q] = have ? (int) (p.b.yOff[k[q] + 1] - p.b.yOff[k[q]]) : -1;
-      maxLo = max (maxLo, Lo[q]);
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) maxLo = max (maxLo, __shfl_xor_sync (0xffffffffu, maxLo, off));
-    unsigned char* bp = OP == L_MAX && p.bp ? p.bp + p.bpOff[task] + (size_t) lane * p.bpBytes : nullptr;
-    bool bad[R];
-    int Fprev[R], Gprev[R];
-#pragma unroll
-    for (int q = 0; q < R; ++q) { bad[q] = false; Fprev[q] = 0; Gprev[q] = L_SENT; }
-    for (int o = 0; o <= maxLo; ++o) {
+    for (int off = 16; off; off >>= 1) warpMaxLo = max (warpMaxLo, __shfl_xor_sync (0xffffffffu, warpMaxLo, off));
+    if (lane == 0) atomicMax (&sMaxLo, warpMaxLo);
+    __syncthreads();
+    const int ctaMaxLo = sMaxLo;
+    unsigned char* bp = OP == L_MAX && p.bp && task * 32 < p.nWork ? p.bp + p.bpOff[task] + (size_t) lane * p.bpBytes : nullptr;
+    bool bad = false;
+    int Fprev = 0, Gprev = L_SENT;
+    for (int o = 0; o <= ctaMaxLo; ++o) {
+      const bool active = o <= warpMaxLo;      // (a warp whose reads have ended keeps the CTA's barriers company)
       double* cur = (o & 1) ? v1 : v0;
       const double* prev = (o & 1) ? v0 : v1;
-      int tok[R], F[R], mx[R];
-      unsigned mn[R], best[R];
-      double f[R], acc[R], res[R], vlast[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        tok[q] = (o <= Lo[q] && o > 0) ? y[q][o - 1] - 1 : 0;
-        F[q] = 0; f[q] = 1.;
-        if (OP == L_SUM && o > 0) { if (Gprev[q] == L_SENT) f[q] = 0.; else { F[q] = Gprev[q]; f[q] = l_pow2 (Fprev[q] - F[q]); } }
-        mx[q] = 0; mn[q] = 0xffffffffu; best[q] = 0xffffu;
-        acc[q] = ZERO; res[q] = ZERO; vlast[q] = ZERO;
-      }
-      for (int hd = 0; hd < p.nHubD; ++hd) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) { hubD[hd * LPT + q * 32] = ZERO; if (OP == L_MAX) hubDB[hd * LPT + q * 32] = 0xffffu; }
-      }
+      const int tok = (o <= Lo && o > 0) ? y[o - 1] - 1 : 0;
+      int F = 0, mx = 0;
+      double f = 1.;
+      if (OP == L_SUM && o > 0) { if (Gprev == L_SENT) f = 0.; else { F = Gprev; f = l_pow2 (Fprev - F); } }
+      unsigned mn = 0xffffffffu, best = 0xffffu;
+      double acc = ZERO, res = ZERO, vlast = ZERO;
+      if (active)
+        for (int hd = 0; hd < p.nHubD; ++hd) { hubD[hd * 32] = ZERO; if (OP == L_MAX) hubDB[hd * 32] = 0xffffu; }
       const bool usePrev = o > 0;
-      // the previous cell's live values travel into the ring LA blocks ahead of the block that reads them
-      auto issue = [&] (const int blk) {
-        for (int j = __ldg (p.blkLoad + blk), je = __ldg (p.blkLoad + blk + 1); j < je; ++j) {
-          const int li = __ldg (p.loadIdx + j);
-#pragma unroll
-          for (int q = 0; q < R; ++q) l2_cp_async8 (ring + (li & ringMask) * LPT + q * 32, prev + (size_t) li * LPT + q * 32);
-        }
-        l2_commit();
-      };
-      if (usePrev) for (int blk = 0; blk < min (p.LA, p.nBlk); ++blk) issue (blk);
       double* curOut = cur;
-      unsigned char* bpRow = bp ? bp + (size_t) o * p.S * LPT * p.bpBytes : nullptr;
+      unsigned char* bpRow = bp ? bp + (size_t) o * p.S * 32 * p.bpBytes : nullptr;
       int d = 0;
-      const LRec* r = p.rec;
-      uint4 nx = __ldg (reinterpret_cast<const uint4*> (r));
-      int n = 0;
-      for (int blk = 0; blk < p.nBlk; ++blk) {
-        if (usePrev) {
-          if (blk + p.LA < p.nBlk) issue (blk + p.LA); else l2_commit();      // (an empty group keeps the count uniform)
-          l2_wait (p.LA);      // the group of block blk has landed
-        }
-        if (blk == 1) {      // the origin cell's start state (forward.defs.h:36), after the preamble
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[q] = o == 0 ? ONE : ZERO;
-        }
-        for (const int ne = __ldg (p.blkRec + blk + 1); n < ne; ++n) {
-          const uint4 u = nx;
-          nx = __ldg (reinterpret_cast<const uint4*> (r + n + 1));      // the stream ends with a spare record
+      __syncthreads();      // everyone has left the previous cell's last chunk: its buffer may be refilled
+      if (tid == 0) l2_bulk_load (bufAddr, p.blob, (unsigned) p.blobBytes, mbarAddr);
+      for (int c = 0; c < p.nChunks; ++c) {
+        if (c > 0) __syncthreads();      // chunk c - 1 is done with: its buffer takes chunk c + 1
+        if (tid == 0 && c + 1 < p.nChunks)
+          l2_bulk_load (bufAddr + (unsigned) (((c + 1) & 1) * p.blobBytes), p.blob + (size_t) (c + 1) * p.blobBytes, (unsigned) p.blobBytes, mbarAddr + 8u * ((c + 1) & 1));
+        if (c & 1) { l2_mbar_wait (mbarAddr + 8, phase1); phase1 ^= 1u; } else { l2_mbar_wait (mbarAddr, phase0); phase0 ^= 1u; }
+        if (!active) continue;
+        const char* bl = buf0 + (c & 1) * p.blobBytes;
+        const uint4* rec = reinterpret_cast<const uint4*> (bl);
+        const double* em = reinterpret_cast<const double*> (bl + p.emOff);
+        const uint16_t* emIdx = reinterpret_cast<const uint16_t*> (bl + p.idxOff);
+#pragma unroll 4
+        for (int n = 0; n < L3_NREC; ++n) {
+          const uint4 u = rec[n];
           const unsigned ctl = u.w, kind = ctl & 7u;
-          if (ctl & L2_HINIT) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) { acc[q] = hubD[L2_HD (ctl) * LPT + q * 32]; if (OP == L_MAX) best[q] = hubDB[L2_HD (ctl) * LPT + q * 32]; }
+          if (kind == K_LOAD) {
+            if (usePrev) l2_cp_async8 (ring + (u.z & ringMask) * 32, prev + (size_t) u.z * 32);
+            continue;
           }
+          if (kind == K_CTRL) {
+            if (usePrev && (u.z & L3_COMMIT)) l2_commit();
+            if (usePrev && (u.z & L3_WAIT)) l2_wait (p.LA);
+            if (u.z & L3_ORIGIN) acc = o == 0 ? ONE : ZERO;
+            continue;
+          }
+          if (ctl & L2_HINIT) { acc = hubD[L2_HD (ctl) * 32]; if (OP == L_MAX) best = hubDB[L2_HD (ctl) * 32]; }
           if (kind == K_EMIT) {
             if (usePrev) {
-              double x[R], w[R];
-              unsigned ix[R];
-#pragma unroll
-              for (int q = 0; q < R; ++q) {
-                x[q] = ring[u.z * LPT + q * 32];
-                w[q] = __ldg (p.em + (size_t) u.x * p.nOut + tok[q]);
-                if (OP == L_MAX) ix[q] = __ldg (p.emIdx + (size_t) u.x * p.nOut + tok[q]);
-              }
-#pragma unroll
-              for (int q = 0; q < R; ++q) {
-                if (OP == L_SUM) acc[q] = fma (w[q], x[q], acc[q]);
-                else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w[q]);
-                else { const double c = x[q] + w[q]; if (acc[q] < c) { acc[q] = c; best[q] = ((unsigned) T_INSERT << kb) | ix[q]; } }
-              }
+              const double x = ring[u.z * 32], w = em[u.x * p.nOut + tok];
+              if (OP == L_SUM) acc = fma (w, x, acc);
+              else if (OP == L_LSE) acc = l_lse (acc, x + w);
+              else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((unsigned) T_INSERT << kb) | emIdx[u.x * p.nOut + tok]; } }
             }
-            if (OP == L_SUM && (ctl & L2_SCALE)) {
-#pragma unroll
-              for (int q = 0; q < R; ++q) acc[q] *= f[q];
-            }
+            if (OP == L_SUM && (ctl & L2_SCALE)) acc *= f;
           } else if (kind == K_WIN || kind == K_HUBS) {
             const double w = __hiloint2double ((int) u.y, (int) u.x);
-            const double* src = (kind == K_WIN ? win : hubS) + u.z * LPT;
-            double x[R];
-#pragma unroll
-            for (int q = 0; q < R; ++q) x[q] = src[q * 32];
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              if (OP == L_SUM) acc[q] = fma (w, x[q], acc[q]);
-              else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w);
-              else { const double c = x[q] + w; if (acc[q] < c) { acc[q] = c; best[q] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
-            }
+            const double x = (kind == K_WIN ? win : hubS)[u.z * 32];
+            if (OP == L_SUM) acc = fma (w, x, acc);
+            else if (OP == L_LSE) acc = l_lse (acc, x + w);
+            else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
           } else if (kind == K_PUSH) {
             const double w = __hiloint2double ((int) u.y, (int) u.x);
-            double* a = hubD + u.z * LPT;
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              if (OP == L_SUM) a[q * 32] = fma (w, vlast[q], a[q * 32]);
-              else if (OP == L_LSE) a[q * 32] = l_lse (a[q * 32], vlast[q] + w);
-              else { const double c = vlast[q] + w; if (a[q * 32] < c) { a[q * 32] = c; hubDB[u.z * LPT + q * 32] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
-            }
+            double* a = hubD + u.z * 32;
+            if (OP == L_SUM) *a = fma (w, vlast, *a);
+            else if (OP == L_LSE) *a = l_lse (*a, vlast + w);
+            else { const double cnd = vlast + w; if (*a < cnd) { *a = cnd; hubDB[u.z * 32] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
           }
           if (ctl & L2_PRESTORE) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              hubD[L2_HD (ctl) * LPT + q * 32] = acc[q];
-              if (OP == L_MAX) hubDB[L2_HD (ctl) * LPT + q * 32] = best[q];
-              acc[q] = ZERO; best[q] = 0xffffu;
-            }
+            hubD[L2_HD (ctl) * 32] = acc;
+            if (OP == L_MAX) hubDB[L2_HD (ctl) * 32] = best;
+            acc = ZERO; best = 0xffffu;
           }
           if (ctl & L2_END) {
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-              win[(d & winMask) * LPT + q * 32] = acc[q];
-              vlast[q] = acc[q];
-              if (ctl & L2_LIVE) curOut[q * 32] = acc[q];
-              if (ctl & L2_HSTORE) hubS[L2_HS (ctl) * LPT + q * 32] = acc[q];
-              if (OP == L_SUM) {
-                const int hi = __double2hiint (acc[q]);
-                mx[q] = max (mx[q], hi);
-                mn[q] = min (mn[q], (unsigned) (hi - 0x00100000));      // zeros and denormals wrap to the top and drop out
-              } else if (OP == L_MAX && bpRow) {
-                if (p.bpBytes == 1) bpRow[q * 32] = (unsigned char) best[q]; else reinterpret_cast<uint16_t*> (bpRow)[q * 32] = (uint16_t) best[q];
-              }
-              res[q] = acc[q];      // after the last record: the end state
-              acc[q] = ZERO;
-              best[q] = 0xffffu;
+            win[(d & winMask) * 32] = acc;
+            vlast = acc;
+            if (ctl & L2_LIVE) { *curOut = acc; curOut += 32; }
+            if (ctl & L2_HSTORE) hubS[L2_HS (ctl) * 32] = acc;
+            if (OP == L_SUM) {
+              const int hi = __double2hiint (acc);
+              mx = max (mx, hi);
+              mn = min (mn, (unsigned) (hi - 0x00100000));      // zeros and denormals wrap to the top and drop out
+            } else if (OP == L_MAX && bpRow) {
+              if (p.bpBytes == 1) *bpRow = (unsigned char) best; else *reinterpret_cast<uint16_t*> (bpRow) = (uint16_t) best;
+              bpRow += 32 * p.bpBytes;
             }
-            if (ctl & L2_LIVE) curOut += LPT;
-            if (OP == L_MAX && bpRow) bpRow += LPT * p.bpBytes;
+            res = acc;      // after the last record: the end state
+            acc = ZERO;
+            best = 0xffffu;
             ++d;
           }
         }
       }
-      if (usePrev) l2_wait (0);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
+      if (usePrev && active) l2_wait (0);
+      if (active) {
         if (OP == L_SUM) {
           int Gc = L_SENT;
-          if (mx[q] >= 0x00100000) {
-            const int emx = mx[q] >> 20;
-            Gc = F[q] + emx - 1023;
-            if (o <= Lo[q] && (emx == 0x7ff || (mn[q] != 0xffffffffu && emx - (int) ((mn[q] >> 20) + 1) > L_SPREAD))) bad[q] = true;
+          if (mx >= 0x00100000) {
+            const int emx = mx >> 20;
+            Gc = F + emx - 1023;
+            if (o <= Lo && (emx == 0x7ff || (mn != 0xffffffffu && emx - (int) ((mn >> 20) + 1) > L_SPREAD))) bad = true;
           }
-          Fprev[q] = F[q]; Gprev[q] = Gc;
+          Fprev = F; Gprev = Gc;
         }
-        if (o == Lo[q]) {
-          if (OP == L_SUM) { p.result[k[q]] = res[q] > 0. ? log (res[q]) + F[q] * LN2 : l_ninf(); p.flag[k[q]] = bad[q] || !(res[q] > 0.) || !(res[q] < 1e300); }
-          else p.result[k[q]] = res[q];
+        if (o == Lo) {
+          if (OP == L_SUM) { p.result[k] = res > 0. ? log (res) + F * LN2 : l_ninf(); p.flag[k] = bad || !(res > 0.) || !(res < 1e300); }
+          else p.result[k] = res;
         }
       }
-      __syncwarp();
     }
   }
 }
@@ -914,8 +985,8 @@ struct LBuf {
 // independent chain per thread makes up for the missing warps in the sums (65 536 reads: 40 -> 89 GCUPS),
 // while the max-plus sweep, which carries a pointer per chain, stays at one.
 static int lane_reads_per_lane (const mb_machine* m, const LHost* h, int64_t nWork, int op) {
-  if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? (h->l2.ok ? 2 : 4) : r >= 2 ? 2 : 1; }
-  if (h->l2.ok) return 1;
+  if (h->l2.ok) return 1;      // the windowed sweep keeps one read per lane
+  if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
   if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
@@ -956,46 +1027,52 @@ static int lane_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>
   return 0;
 }
 
-// the windowed sweep (lane2): as many warps per SM as shared memory holds
-template<int OP, int R>
-static int lane2_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
-                           unsigned char* dBp, const int64_t* dBpOff) {
+// the windowed sweep (lane2): CTAs of W warps, as many per SM as shared memory holds
+template<int OP>
+static int lane2_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
+                         unsigned char* dBp, const int64_t* dBpOff) {
   LHost* h = lh (m);
   const L2Prog& P = h->l2;
-  constexpr int LPT = 32 * R;
-  const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + LPT - 1) / LPT;
-  const size_t perWarp = (size_t) (P.WN + P.RN + P.nHubS + P.nHubD) * LPT * 8 + (OP == L_MAX ? (size_t) P.nHubD * LPT * 4 : 0);
-  const size_t kSmem = 227 * 1024 - 1024;
-  int warpsPerSM = (int) std::min<size_t> (kSmem / perWarp, 32);
-  if (m->opt.has ("lane_warps")) warpsPerSM = std::max (1, std::min (warpsPerSM, m->opt.get ("lane_warps", 16)));
-  if (warpsPerSM < 1) { set_error ("lane engine: the window does not fit in shared memory"); return 1; }
-  // CTAs of 2 warps (of 1 when few tasks or little room): a fine grain for the task counter
-  const int wpc = (warpsPerSM >= 2 && nTasks >= (int64_t) h->numSMs * 2) ? 2 : 1;
-  const int ctasPerSM = std::max (1, warpsPerSM / wpc);
-  const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + wpc - 1) / wpc, (int64_t) ctasPerSM * h->numSMs));
-  const size_t smem = perWarp * wpc;
-  MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + 31) / 32;
+  const size_t perWarp = (size_t) (P.WN + P.RN + P.nHubS + P.nHubD) * 32 * 8 + (OP == L_MAX ? (size_t) P.nHubD * 32 * 4 : 0);
+  const size_t fixed = 2 * (size_t) P.blobBytes + 16 + 64;
+  const size_t kSmem = 227 * 1024 - 2048;      // (the kernel's two static words included)
+  // warps per CTA: the largest of 8, 6, 4, 2, 1 that gives the most warps per SM
+  int W = 1, ctasPerSM = 1, bestWarps = 0;
+  const int wantW = m->opt.get ("lane_warps_per_cta", 0);
+  for (int w: { 8, 6, 4, 2, 1 }) {
+    if (wantW && w != wantW) continue;
+    const size_t need = fixed + (size_t) w * perWarp;
+    if (need > kSmem) continue;
+    const int c = (int) std::min<size_t> (kSmem / need, 32 / w);
+    if (c * w > bestWarps) { bestWarps = c * w; W = w; ctasPerSM = c; }
+  }
+  if (!bestWarps) { set_error ("lane engine: the window does not fit in shared memory"); return 1; }
+  if (m->opt.has ("lane_warps")) ctasPerSM = std::max (1, std::min (ctasPerSM, m->opt.get ("lane_warps", 16) / W));
+  while (W > 1 && nTasks < (int64_t) h->numSMs * W) W /= 2;      // few reads: narrower CTAs spread them over the SMs
+  const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + W - 1) / W, (int64_t) ctasPerSM * h->numSMs));
+  const size_t smem = fixed + (size_t) W * perWarp;
+  MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   b->wsOrderHoldsFull = false;
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
   unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
-  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * wpc * 2 * std::max (P.nLive, 1) * LPT * 8);
+  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * W * 2 * std::max (P.nLive, 1) * 32 * 8);
   if (!dOrder || !dCounter || !dVec) return 1;
   MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
   MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
   L2Params p {};
-  p.rec = OP == L_SUM ? P.dRecLin : P.dRecLog;
-  p.blkRec = P.dBlk; p.blkLoad = P.dBlk + P.blkRec.size(); p.loadIdx = P.dBlk + P.blkRec.size() + P.blkLoad.size();
-  p.nBlk = P.nBlk; p.LA = P.LA; p.WN = P.WN; p.RN = P.RN; p.nHubS = P.nHubS; p.nHubD = P.nHubD; p.nLive = P.nLive;
-  p.em = OP == L_SUM ? h->dEmLin : h->dEmLog; p.emIdx = h->dEmIdx;
-  p.S = h->S; p.nOut = h->nOut; p.bpBytes = h->bpBytes;
+  p.blob = OP == L_SUM ? P.dBlobLin : P.dBlobLog;
+  p.nChunks = P.nChunks; p.blobBytes = P.blobBytes; p.emOff = P.emOff; p.idxOff = P.idxOff;
+  p.LA = P.LA; p.WN = P.WN; p.RN = P.RN; p.nHubS = P.nHubS; p.nHubD = P.nHubD; p.nLive = P.nLive;
+  p.S = h->S; p.nOut = std::max (h->nOut, 1); p.bpBytes = h->bpBytes;
   p.b = b->dev;
   p.order = dOrder; p.nWork = nWork; p.counter = dCounter;
   p.result = dResult; p.flag = dFlag; p.vec = dVec;
   p.bp = dBp; p.bpOff = dBpOff;
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "lane engine (windowed): %lld reads, R=%d, grid %d x %d threads, %zu B smem per CTA (%d warps per SM), window %d, ring %d, hubs %d + %d, %d live of %d states, %lld records\n",
-             (long long) nWork, R, grid, 32 * wpc, smem, ctasPerSM * wpc, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, h->S, (long long) P.recLin.size());
-  lane2_kernel<OP, R><<<grid, 32 * wpc, smem, b->stream>>> (p);
+    fprintf (stderr, "lane engine (windowed): %lld reads, grid %d x %d threads (%d CTAs per SM), %zu B smem per CTA, window %d, ring %d, hubs %d + %d, %d live of %d states, %zu records in %d chunks of %d B\n",
+             (long long) nWork, grid, 32 * W, ctasPerSM, smem, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, h->S, P.flat.size(), P.nChunks, P.blobBytes);
+  lane2_kernel<OP><<<grid, 32 * W, smem, b->stream>>> (p);
   MB_CUDA (cudaGetLastError());
   return 0;
 }
@@ -1003,8 +1080,7 @@ static int lane2_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t
 template<int OP>
 static int lane_launch (mb_machine* m, mb_batch* b, int R, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
                         unsigned char* dBp, const int64_t* dBpOff) {
-  if (lh (m)->l2.ok)
-    return R >= 2 ? lane2_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff) : lane2_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);
+  if (lh (m)->l2.ok) return lane2_launch<OP> (m, b, order, dResult, dFlag, dBp, dBpOff);      // (one read per lane)
   return R == 4 ? lane_launch_r<OP, 4> (m, b, order, dResult, dFlag, dBp, dBpOff)
        : R == 2 ? lane_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff)
                 : lane_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);
