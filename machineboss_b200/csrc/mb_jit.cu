@@ -1025,6 +1025,7 @@ struct MBArgsHost {   // must match struct MBArgs in the skeleton
   int32_t* flag;
   unsigned* F32; const int64_t* f32Off;
   int32_t* ef; const int64_t* efOff;
+  const int64_t* items; const int64_t* itemBnd; int* prog;
 };
 
 struct DevBuf {
@@ -1072,12 +1073,32 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
   int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[slot]);
-  grid = std::min<int64_t> (grid, ((int64_t) order.size() + warpsPerBlock - 1) / warpsPerBlock);
+  // SPLIT mode: with fewer pairs than resident warps the strips of a pair become work items of their own, and the warps
+  // that claim them run as a pipeline down the strips (see MBArgs::items in the skeleton)
+  const int W = 32 * (scoreKernel && !narrow && J.modV ? J.CV : J.C);
+  bool split = false;
+  std::vector<int64_t> items, itemBnd;
+  if (scoreKernel && m->opt.get ("jit_split", -1) != 0) {
+    int64_t nItems = 0;
+    for (int64_t k: order) nItems += (b->xOff[k + 1] - b->xOff[k] + W) / W;
+    split = nItems > (int64_t) order.size() && (m->opt.get ("jit_split", -1) > 0 || (double) order.size() < 0.75 * (double) (grid * warpsPerBlock));
+    if (split) {
+      int64_t at = 0;
+      for (int64_t k: order) {
+        const int64_t nStrips = (b->xOff[k + 1] - b->xOff[k] + W) / W, Lo = b->yOff[k + 1] - b->yOff[k];
+        if (nStrips > 0xffff) { split = false; break; }
+        for (int64_t st = 0; st < nStrips; ++st) { items.push_back ((k << 16) | st); itemBnd.push_back (at); at += (Lo + 1) * (m->S + 1); }
+      }
+      itemBnd.push_back (at);
+    }
+  }
+  const int64_t nWorkItems = split ? (int64_t) items.size() : (int64_t) order.size();
+  grid = std::min<int64_t> (grid, (nWorkItems + warpsPerBlock - 1) / warpsPerBlock);
   grid = std::max<int64_t> (grid, 1);
   const int64_t bndStride = 2 * (maxLo + 1) * (m->S + 1);   // the linear sweeps append the frame exponent to each row
   if (ws_bytes (b, WS_ORDER) < order.size() * 8) b->wsOrderHoldsFull = false;   // the slot is about to be re-allocated
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
-  double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (grid * warpsPerBlock * bndStride) * 8);
+  double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) (split ? itemBnd.back() + bndStride : grid * warpsPerBlock * bndStride) * 8);
   unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
   if (!dOrder || !dBnd || !dCounter) return 1;
   const bool isFull = &order == &b->fullOrder;
@@ -1087,7 +1108,19 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
   MBArgsHost A;
   A.x = b->dX; A.xOff = b->dXOff; A.y = b->dY; A.yOff = b->dYOff;
-  A.order = dOrder; A.nWork = (int64_t) order.size(); A.counter = dCounter;
+  A.order = dOrder; A.nWork = nWorkItems; A.counter = dCounter;
+  A.items = nullptr; A.itemBnd = nullptr; A.prog = nullptr;
+  if (split) {
+    int64_t* dItems = (int64_t*) ws_reserve (b, WS_ITEMS, items.size() * 8);
+    int64_t* dItemBnd = (int64_t*) ws_reserve (b, WS_ITEMBND, itemBnd.size() * 8);
+    int* dProg = (int*) ws_reserve (b, WS_PROG, items.size() * 4);
+    if (!dItems || !dItemBnd || !dProg) return 1;
+    MB_CUDA (cudaMemcpyAsync (dItems, items.data(), items.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dItemBnd, itemBnd.data(), itemBnd.size() * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemsetAsync (dProg, 0, items.size() * 4, b->stream));
+    if (ca.flag) MB_CUDA (cudaMemsetAsync (ca.flag, 0, (size_t) b->nPairs * 4, b->stream));      // strips OR their reasons into the pair's flag
+    A.items = dItems; A.itemBnd = dItemBnd; A.prog = dProg;
+  }
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dResult;
   A.emit = (which == 5 || which == 7) ? J.dEmitFLin : (which == 6 || which == 8) ? J.dEmitBLin : (which == 1 || which == 4) ? J.dEmitB : J.dEmitF;
@@ -1097,7 +1130,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.tb = dTb; A.tbOff = dTbOff;
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
+    fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, split ? " (split: strips as work items)" : rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
              J.smemBytes[which], J.blocksPerSM[slot], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { (rowTab && lin) ? (void*) J.silParamLinN.data() : lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;

@@ -38,7 +38,24 @@ struct MBArgs {
   int32_t* flag;                         // per pair: 1 = the scaled linear sweep saw a dangerous dynamic range
   unsigned* F32; const int64_t* f32Off;  // linear E-step: high words of the Forward values, [outPos][inPos][state]
   int32_t* ef; const int64_t* efOff;     // linear E-step: frame exponent per (strip, block of MB_RESCALE steps)
+  // SPLIT mode (few or long pairs: fewer pairs than resident warps).  A work item is ONE STRIP of a pair,
+  // items[w] = pair << 16 | strip, the strips of a pair consecutive in w; the warps that claim them run as a
+  // pipeline down the strips: strip s writes its last column to the item's own boundary buffer and publishes in
+  // prog[w] how many rows of it are complete, strip s + 1 (item w + 1, claimed later, hence never waited for by
+  // its predecessor) waits until the rows it is about to stage are there.  items == 0: a warp takes whole pairs.
+  const int64_t* items; const int64_t* itemBnd; int* prog;
 };
+
+// rows [0, need) of the previous strip's boundary are complete and visible (split mode)
+__device__ __forceinline__ void mb_wait_rows (const int* prog, const int need) {
+  while (*(volatile const int*) prog < need) { }
+  __threadfence();
+}
+// lane 31 has written rows [0, rows) of this strip's boundary: make them visible, then say so
+__device__ __forceinline__ void mb_publish_rows (int* prog, const int rows) {
+  __threadfence();
+  *(volatile int*) prog = rows;
+}
 
 __device__ __forceinline__ double mb_neg_inf() { return __longlong_as_double (0xfff0000000000000LL); }
 
@@ -151,7 +168,9 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     if (lane == 0) w = atomicAdd (A.counter, 1ULL);
     w = __shfl_sync (MB_FULL, w, 0);
     if ((int64_t) w >= A.nWork) break;
-    const int64_t k = A.order[w];
+    const bool split = A.items != 0;
+    const int64_t item = split ? A.items[w] : 0;
+    const int64_t k = split ? (item >> 16) : A.order[w];
     const int64_t x0 = A.xOff[k], y0 = A.yOff[k];
     const int Li = (int) (A.xOff[k + 1] - x0), Lo = (int) (A.yOff[k + 1] - y0);
     const uint8_t* x = A.x + x0;
@@ -163,7 +182,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     const double ll = MODE == 3 ? A.ll[k] : 0.0;
     if (MODE == 3 && !(ll > NI)) continue;     // impossible pair: no posterior (the reference would produce NaN)
 
-    for (int strip = 0; strip < nStrips; ++strip) {
+    const int stripFirst = split ? (int) (item & 0xffff) : 0, stripEnd = split ? stripFirst + 1 : nStrips;
+    for (int strip = stripFirst; strip < stripEnd; ++strip) {
       const int col0 = strip * MB_W + lane * MB_C;
       int ta[MB_C];
 #ifdef MB_ROWTAB
@@ -192,14 +212,16 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         for (int q = 0; q < (MB_NSIL_B > 0 ? MB_NSIL_B : 1); ++q) cs[q] = 0.f;
         for (int q = 0; q < MB_NCTX; ++q) acc[q * 32] = 0.f;
       }
-      const double* bin = (strip & 1) ? bndB : bndA;
-      double* bout = (strip & 1) ? bndA : bndB;
       const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      const double* bin = split ? (hasIn ? A.bnd + A.itemBnd[w - 1] : bndA) : ((strip & 1) ? bndB : bndA);
+      double* bout = split ? A.bnd + A.itemBnd[w] : ((strip & 1) ? bndA : bndB);
+      const bool waits = split && hasIn, publishes = split && hasOut && lane == 31;
       if (!hasIn) {      // the column left of the matrix: nothing comes from there
         __syncwarp();
         for (int q = lane; q < 32 * MB_ROW; q += 32) sIn[q] = NI;
         __syncwarp();
       }
+      if (waits) mb_wait_rows (A.prog + (w - 1), min (32, Lo + 1));
       double stageNext[MB_S];
 #pragma unroll
       for (int s = 0; s < MB_S; ++s)
@@ -222,6 +244,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       // ramp predicates (row in range, origin cell, result cell) fold away
       // every 32 steps (kept out of the step body so that the steady loop carries no block tests)
       auto blockStart = [&] (const int t) {
+        if (publishes && t >= 32) mb_publish_rows (A.prog + w, t - 31);      // (steps < t are done: lane 31 has written rows <= t - 32)
+        if (waits) mb_wait_rows (A.prog + (w - 1), min (t + 64, Lo + 1));
         if (hasIn) {                        // stage 32 rows of the previous strip's last column: lane q takes row t+q;
           __syncwarp();                     // the values were fetched a block ago, the next block's are fetched now
 #pragma unroll
@@ -355,6 +379,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
         }
         for (; t < nSteps; ++t) { if ((t & 31) == 0) blockStart (t); step (t, MBBool<false>()); }
       }
+      if (publishes) mb_publish_rows (A.prog + w, Lo + 1);
       if (MODE == 3) mb_flush_counts (cs, acc, ta, A.counts, A.idTabB, lane);
       __syncwarp();
     }
@@ -435,7 +460,9 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
     if (lane == 0) w = atomicAdd (A.counter, 1ULL);
     w = __shfl_sync (MB_FULL, w, 0);
     if ((int64_t) w >= A.nWork) break;
-    const int64_t k = A.order[w];
+    const bool split = A.items != 0;
+    const int64_t item = split ? A.items[w] : 0;
+    const int64_t k = split ? (item >> 16) : A.order[w];
     const int64_t x0 = A.xOff[k], y0 = A.yOff[k];
     const int Li = (int) (A.xOff[k + 1] - x0), Lo = (int) (A.yOff[k + 1] - y0);
     const uint8_t* x = A.x + x0;
@@ -457,7 +484,8 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
       zf = exp2 (fl - lz);
     }
 
-    for (int strip = 0; strip < nStrips; ++strip) {
+    const int stripFirst = split ? (int) (item & 0xffff) : 0, stripEnd = split ? stripFirst + 1 : nStrips;
+    for (int strip = stripFirst; strip < stripEnd; ++strip) {
       // MODE 3 pads the matrix on the LEFT of the reversed sweep (columns < 0: every value there stays
       // exactly 0, a sum of products of zeros), so that its strips and lanes mirror the Forward sweep's:
       // step t of this strip then needs exactly the block the Forward wrote at step Lo+31-t of strip
@@ -490,14 +518,16 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
         for (int q = 0; q < (MB_NSIL_B > 0 ? MB_NSIL_B : 1); ++q) csd[q] = 0.0;
         for (int q = 0; q < MB_NCTX; ++q) accd[q * 32] = 0.0;
       }
-      const double* bin = (strip & 1) ? bndB : bndA;
-      double* bout = (strip & 1) ? bndA : bndB;
       const bool hasIn = strip > 0, hasOut = strip + 1 < nStrips;
+      const double* bin = split ? (hasIn ? A.bnd + A.itemBnd[w - 1] : bndA) : ((strip & 1) ? bndB : bndA);
+      double* bout = split ? A.bnd + A.itemBnd[w] : ((strip & 1) ? bndA : bndB);
+      const bool waits = split && hasIn, publishes = split && hasOut && lane == 31;
       if (!hasIn) {
         __syncwarp();
         for (int q = lane; q < MB_RESCALE * MB_ROW; q += 32) sIn[q] = 0.0;
         __syncwarp();
       }
+      if (waits) mb_wait_rows (A.prog + (w - 1), min (MB_RESCALE, Lo + 1));
       // row tokens (0-based): rows 0..31 are published now, rows 32..63 at step 0, and so on one block ahead
       // (the raw 1-based byte is kept until it is published a block later: subtracting 1 at once would make
       // the warp wait for the global load)
@@ -532,6 +562,8 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
       // ramp predicates (row in range, origin cell, result cell) fold away
       // every MB_RESCALE steps (kept out of the step body so that the steady loop carries no block tests)
       auto blockStart = [&] (const int t) {
+        if (publishes && t >= 32) mb_publish_rows (A.prog + w, t - 31);      // (steps < t are done: lane 31 has written rows <= t - 32)
+        if (waits) mb_wait_rows (A.prog + (w - 1), min (t + 2 * MB_RESCALE, Lo + 1));
         {
           bool nz = false;      // LF: this lane holds something
           if (t > 0) {
@@ -750,11 +782,12 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
         }
         for (; t < nSteps; ++t) { if ((t & (MB_RESCALE - 1)) == 0) blockStart (t); step (t, MBBool<false>()); }
       }
+      if (publishes) mb_publish_rows (A.prog + w, Lo + 1);
       suspect = (int) __reduce_or_sync (MB_FULL, (unsigned) suspect);      // why: 1 spread, 2 neighbour frame, 4 boundary frame
       if (MODE == 3) mb_flush_counts_lin (csd, accd, ta, A.counts, A.idTabB, lane);
       __syncwarp();
     }
-    if (lane == 0) A.flag[k] = suspect;
+    if (lane == 0) { if (split) { if (suspect) atomicOr (A.flag + k, suspect); } else A.flag[k] = suspect; }
   }
 }
 

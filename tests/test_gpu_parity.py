@@ -592,3 +592,33 @@ def test_group_over_all_devices_equals_single_device():
         pytest.skip("needs at least two GPUs")
     g = _check_group_against_single(capi, None)
     assert g.n_devices == capi.device_count()
+
+
+@pytest.mark.parametrize("split", [1, 0])
+def test_split_mode_strips_as_work_items(split):
+    """With fewer pairs than resident warps the strips of a pair are work items of their own and the warps that claim them
+    run as a pipeline down the strips, each waiting for the rows of its left neighbour's boundary (option jit_split: 1
+    forces it, 0 forbids it; the default decides by the batch).  Pairs of 1 to 12 strips, ragged: every score pass and the
+    traceback against the oracle, and nothing handed to the log domain."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    shapes = [(3000, 2800), (600, 700), (257, 300), (100, 50), (1025, 900), (0, 7), (256, 31), (255, 1000), (511, 40)]
+    pairs = [(synth_tokens(83, k, 0, li, 4), synth_tokens(83, k, 1, lo, 4)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1, jit_split=split)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    assert b.last_redo() == 0
+    bl = capi.backward(m, b)
+    assert b.last_redo() == 0
+    sc, paths = capi.viterbi(m, b)
+    sc2 = capi.viterbi(m, b, paths=False)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(ll[k] - f) <= 1e-9 * max(1.0, abs(f)) and abs(bl[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, ll[k], bl[k], f)
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and sc2[k] == v, (k, sc[k], v)
+        assert paths[k].tolist() == p.tolist(), k
+    # the default picks the split for a batch this small: same numbers
+    m_auto = make_machine(capi, fm, 1)
+    assert np.array_equal(capi.forward(m_auto, b), ll) and np.array_equal(capi.viterbi(m_auto, b, paths=False), sc)
