@@ -73,6 +73,19 @@ struct LRec { double w; uint32_t src; uint32_t ctl; };      // src: source state
 // value it means to); a machine whose structure does not fit keeps the first version of the sweep.
 // ---------------------------------------------------------------------------------------------
 enum { K_EMIT = 0, K_WIN = 1, K_HUBS = 2, K_PUSH = 3, K_NONE = 4, K_LOAD = 5, K_CTRL = 6 };
+// The stream the kernel executes: single-purpose records { double w; uint32 a; uint32 op }, op & 15 = opcode.  Every
+// shared-memory operand is a ROW of the warp's region (window rows, then ring rows, then hub sources, then hub
+// destinations), so a term is: one address shift, one load per read, one multiply-add per read.
+enum { X_TERM = 0,       // acc = fma (w, region[a], acc)                 (window or hub-source row a; op >> 16 = candidate index)
+       X_EMIT = 1,       // acc = fma (emission[w-bits row][token], region[a], acc)  (ring row a); op & 16: then acc *= f
+       X_PUSH = 2,       // region[a] = fma (w, vlast, region[a])         (hub-destination row a; (op >> 4) & 7 = its slot)
+       X_END = 3,        // region[a] = vlast = res = acc; acc = 0        (window row a); op & 16: live (store to the live vector, track the
+                         //                                                range); op & 32: also to hub-source row (w-bits)
+       X_HINIT = 4,      // acc = region[a]                               (hub-destination row a; (op >> 4) & 7 = its slot)
+       X_PRESTORE = 5,   // region[a] = acc; acc = 0                      (likewise)
+       X_LOAD = 6,       // ring row a <- previous live vector, index (w-bits)   (cp.async)
+       X_CTRL = 7,       // a: L3_COMMIT | L3_WAIT | L3_ORIGIN
+       X_NOP = 8 };
 #define L3_NREC 64          // records per chunk
 #define L3_EMAX 16          // emission rows per chunk
 #define L3_COMMIT 1u        // K_CTRL (in the record's `src` field): close the group of ring loads issued so far
@@ -525,6 +538,8 @@ static bool lane2_try (const mb_machine* m, LHost* h, int WN, int RN, int BS, in
     P.blkRec.push_back ((int32_t) P.recLin.size());
   }
   P.nBlk = (int) P.blkRec.size() - 1;
+  LA = std::min (LA, P.nBlk);      // (a program of fewer blocks than the lookahead: everything is requested up front)
+  P.LA = LA;
   // ---- ring schedule: block b's loads are issued LA blocks early; a slot may only be refilled once every block that
   // still reads its old content has been processed
   std::vector<int> lastUse ((size_t) std::max (P.nLive, 1), -1), tag ((size_t) RN, -1);
@@ -547,43 +562,55 @@ static bool lane2_try (const mb_machine* m, LHost* h, int WN, int RN, int BS, in
   return true;
 }
 
-// the flat stream: per block its K_LOAD records travel LA blocks ahead of the block itself
+// the flat stream: single-purpose records; per block its ring loads travel LA blocks ahead of the block itself
 static void lane2_flatten (LHost* h) {
   L2Prog& P = h->l2;
-  auto ctrl = [&] (uint32_t what) { P.flat.push_back (l2_rec (K_CTRL, what, 0)); P.flatPerm.push_back (-1); P.flatWant.push_back (-1); P.flatRow.push_back (-1); };
+  const uint32_t rowWin = 0, rowRing = (uint32_t) P.WN, rowHubS = rowRing + (uint32_t) P.RN, rowHubD = rowHubS + (uint32_t) P.nHubS;
+  auto put = [&] (uint32_t opcode, uint32_t a, uint32_t aux, uint64_t wbits, int64_t perm, int32_t want, int32_t row) {
+    LRec r; r.src = a; r.ctl = opcode | aux;
+    memcpy (&r.w, &wbits, 8);
+    P.flat.push_back (r); P.flatPerm.push_back (perm); P.flatWant.push_back (want); P.flatRow.push_back (row);
+  };
   auto loads = [&] (int blk) {
     if (blk < P.nBlk)
-      for (int j = P.blkLoad[blk]; j < P.blkLoad[blk + 1]; ++j) {
-        P.flat.push_back (l2_rec (K_LOAD, (uint32_t) P.loadIdx[j], 0));
-        P.flatPerm.push_back (-1); P.flatWant.push_back (P.loadIdx[j]); P.flatRow.push_back (-1);
-      }
-    ctrl (L3_COMMIT);      // (an empty group keeps the count uniform)
+      for (int j = P.blkLoad[blk]; j < P.blkLoad[blk + 1]; ++j)
+        put (X_LOAD, rowRing + (uint32_t) (P.loadIdx[j] & (P.RN - 1)), 0, (uint64_t) P.loadIdx[j], -1, P.loadIdx[j], -1);
+    put (X_CTRL, L3_COMMIT, 0, 0, -1, -1, -1);      // (an empty group keeps the count uniform)
   };
+  int d = 0;      // destination state of the next END
   for (int blk = 0; blk < std::min (P.LA, P.nBlk); ++blk) loads (blk);
   for (int blk = 0; blk < P.nBlk; ++blk) {
-    if (blk + P.LA < P.nBlk) loads (blk + P.LA); else ctrl (L3_COMMIT);
-    ctrl (L3_WAIT | (blk == 1 ? L3_ORIGIN : 0u));
+    if (blk + P.LA < P.nBlk) loads (blk + P.LA); else put (X_CTRL, L3_COMMIT, 0, 0, -1, -1, -1);
+    put (X_CTRL, L3_WAIT | (blk == 1 ? L3_ORIGIN : 0u), 0, 0, -1, -1, -1);
     for (int n = P.blkRec[blk]; n < P.blkRec[blk + 1]; ++n) {
-      P.flat.push_back (P.recLin[n]);
-      P.flatPerm.push_back (P.recPerm[n]);
-      P.flatWant.push_back (P.recWant[n]);
-      uint64_t row = 0;
-      if ((P.recLin[n].ctl & 7u) == K_EMIT) memcpy (&row, &P.recLin[n].w, 8);
-      P.flatRow.push_back ((P.recLin[n].ctl & 7u) == K_EMIT ? (int32_t) row : -1);
+      const LRec& r = P.recLin[n];
+      const uint32_t ctl = r.ctl, kind = ctl & 7u, cand = ctl & 0xffff0000u;
+      if (ctl & L2_HINIT) put (X_HINIT, rowHubD + L2_HD (ctl), L2_HD (ctl) << 4, 0, -1, -1, -1);
+      if (kind == K_EMIT) {
+        uint64_t row; memcpy (&row, &r.w, 8);
+        put (X_EMIT, rowRing + r.src, (ctl & L2_SCALE) ? 16u : 0u, 0, -1, P.recWant[n], (int32_t) row);
+      } else if (kind == K_WIN) put (X_TERM, rowWin + r.src, cand, 0, P.recPerm[n], P.recWant[n], -1);
+      else if (kind == K_HUBS) put (X_TERM, rowHubS + r.src, cand, 0, P.recPerm[n], P.recWant[n], -1);
+      else if (kind == K_PUSH) put (X_PUSH, rowHubD + r.src, cand | (r.src << 4), 0, P.recPerm[n], -1, -1);
+      if (ctl & L2_PRESTORE) put (X_PRESTORE, rowHubD + L2_HD (ctl), L2_HD (ctl) << 4, 0, -1, -1, -1);
+      if (ctl & L2_END) {
+        put (X_END, rowWin + (uint32_t) (d & (P.WN - 1)), ((ctl & L2_LIVE) ? 16u : 0u) | ((ctl & L2_HSTORE) ? 32u : 0u), (uint64_t) (rowHubS + L2_HS (ctl)), -1, d, -1);
+        ++d;
+      }
     }
   }
   // chunks
   P.chunkFirst.assign (1, 0);
   int nRec = 0, nEm = 0;
   for (size_t n = 0; n < P.flat.size(); ++n) {
-    const bool isEmit = (P.flat[n].ctl & 7u) == K_EMIT;
+    const bool isEmit = (P.flat[n].ctl & 15u) == X_EMIT;
     if (nRec == L3_NREC || (isEmit && nEm == L3_EMAX)) { P.chunkFirst.push_back ((int32_t) n); nRec = 0; nEm = 0; }
     ++nRec;
     if (isEmit) ++nEm;
   }
   P.chunkFirst.push_back ((int32_t) P.flat.size());
   P.nChunks = (int) P.chunkFirst.size() - 1;
-  P.emOff = L3_NREC * (int) sizeof (LRec);
+  P.emOff = (L3_NREC + 1) * (int) sizeof (LRec);      // (one spare record: the sweep reads one ahead)
   P.idxOff = P.emOff + L3_EMAX * std::max (h->nOut, 1) * 8;
   P.blobBytes = (P.idxOff + L3_EMAX * std::max (h->nOut, 1) * 2 + 15) & ~15;
 }
@@ -594,14 +621,14 @@ static void lane2_fill_weights (const mb_machine* m, LHost* h) {
   const int nOut = std::max (h->nOut, 1);
   P.blobLin.assign ((size_t) P.nChunks * P.blobBytes, 0);
   P.blobLog = P.blobLin;
+  LRec nop; nop.w = 0; nop.src = 0; nop.ctl = X_NOP;
   for (int c = 0; c < P.nChunks; ++c) {
     char* bl = P.blobLin.data() + (size_t) c * P.blobBytes;
     char* bg = P.blobLog.data() + (size_t) c * P.blobBytes;
     int nEm = 0;
     for (int n = P.chunkFirst[c]; n < P.chunkFirst[c + 1]; ++n) {
       LRec rl = P.flat[n], rg = P.flat[n];
-      const uint32_t kind = rl.ctl & 7u;
-      if (kind == K_EMIT) {
+      if ((rl.ctl & 15u) == X_EMIT) {
         const uint64_t local = (uint64_t) nEm;      // the row's place in this chunk's emission area
         memcpy (&rl.w, &local, 8); memcpy (&rg.w, &local, 8);
         for (int t = 0; t < h->nOut; ++t) {
@@ -618,11 +645,9 @@ static void lane2_fill_weights (const mb_machine* m, LHost* h) {
       memcpy (bl + (size_t) (n - P.chunkFirst[c]) * sizeof (LRec), &rl, sizeof (LRec));
       memcpy (bg + (size_t) (n - P.chunkFirst[c]) * sizeof (LRec), &rg, sizeof (LRec));
     }
-    // the rest of the record area: records that do nothing
-    for (int n = P.chunkFirst[c + 1] - P.chunkFirst[c]; n < L3_NREC; ++n) {
-      const LRec r = l2_rec (K_NONE, 0, 0);
-      memcpy (bl + (size_t) n * sizeof (LRec), &r, sizeof (LRec));
-      memcpy (bg + (size_t) n * sizeof (LRec), &r, sizeof (LRec));
+    for (int n = P.chunkFirst[c + 1] - P.chunkFirst[c]; n <= L3_NREC; ++n) {      // the rest of the record area, spare record included
+      memcpy (bl + (size_t) n * sizeof (LRec), &nop, sizeof (LRec));
+      memcpy (bg + (size_t) n * sizeof (LRec), &nop, sizeof (LRec));
     }
   }
 }
@@ -655,9 +680,9 @@ static void lane2_build (const mb_machine* m, LHost* h) {
   }
 }
 
-// The program executed for ONE read on the host, chunk by chunk and slot by slot as the kernel does it (the same blobs,
-// the same window, ring and hub arithmetic, with every slot tagged so that a stale read is an error): what the CPU test
-// checks against the oracle.  op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
+// The program executed for ONE read on the host, chunk by chunk and row by row as the kernel does it (the same blobs,
+// the same region rows, every row tagged with what it holds so that a stale read is an error): what the CPU test checks
+// against the oracle.  op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
 int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut) {
   LHost* h = lh (m);
   if (!h || !h->l2.ok) { set_error (std::string ("lane2: no windowed program for this machine") + (h ? ": " + h->l2.why : std::string())); return 1; }
@@ -667,8 +692,9 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
   const double ZERO = op == L_SUM ? 0. : -INFINITY, ONE = op == L_SUM ? 1. : 0.;
   const unsigned kb = h->bpBytes == 1 ? 6 : 14;
   auto lse = [] (double a, double b) { const double mx = std::max (a, b), mn = std::min (a, b); return mn == -INFINITY ? mx : mx + log1p (exp (mn - mx)); };
-  std::vector<double> win ((size_t) P.WN), ring ((size_t) P.RN), hubS (L2_MAXHUB), hubD (L2_MAXHUB), live[2];
-  std::vector<int> winTag ((size_t) P.WN, -1), ringTag ((size_t) P.RN, -1), hubSTag (L2_MAXHUB, -1);
+  const int rows = P.WN + P.RN + P.nHubS + P.nHubD, rowHubD = P.WN + P.RN + P.nHubS;
+  std::vector<double> region ((size_t) rows, ZERO), live[2];
+  std::vector<int> tag ((size_t) rows, -1);
   std::vector<uint32_t> hubDB (L2_MAXHUB);
   live[0].assign ((size_t) std::max (P.nLive, 1), ZERO); live[1] = live[0];
   int Fprev = 0, Gprev = L_SENT;
@@ -681,17 +707,14 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
     const int tok = o > 0 ? y[o - 1] - 1 : 0;
     int F = 0; double f = 1.;
     if (op == L_SUM && o > 0) { if (Gprev == L_SENT) f = 0.; else { F = Gprev; f = std::ldexp (1., Fprev - F); } }
-    std::fill (hubD.begin(), hubD.end(), ZERO);
-    std::fill (hubDB.begin(), hubDB.end(), 0xffffu);
-    std::fill (ringTag.begin(), ringTag.end(), -1);      // a new cell: nothing of the previous vector is in the ring yet
-    std::fill (winTag.begin(), winTag.end(), -1);
-    std::fill (hubSTag.begin(), hubSTag.end(), -1);
+    std::fill (tag.begin(), tag.end(), -1);      // a new cell: nothing of it is in the window, nothing of the previous vector in the ring
+    for (int hd = 0; hd < P.nHubD; ++hd) { region[rowHubD + hd] = ZERO; hubDB[hd] = 0xffffu; }
     double acc = ZERO, vlast = ZERO;
     uint32_t best = 0xffffu;
     int mx = 0; unsigned mn = 0xffffffffu;
     int d = 0, nl = 0;
-    // ring loads land when their group is waited for: pending[g] = loads of group g; a WAIT completes all but the last LA groups
-    std::vector<std::vector<int>> pending (1);
+    // ring loads land when their group is waited for: pending[g] = (row, live index) of group g; a WAIT completes all but the last LA groups
+    std::vector<std::vector<std::pair<int, int>>> pending (1);
     size_t landed = 0;
     for (int c = 0; c < P.nChunks; ++c) {
       const char* bl = blob.data() + (size_t) c * P.blobBytes;
@@ -700,57 +723,66 @@ int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, do
       for (int q = 0; q < L3_NREC; ++q) {
         LRec r;
         memcpy (&r, bl + (size_t) q * sizeof (LRec), sizeof (LRec));
-        const int n = P.chunkFirst[c] + q;      // (flat index, for the tags; records past the chunk's end do nothing)
-        const uint32_t ctl = r.ctl, kind = ctl & 7u;
-        if (kind == K_LOAD) { if (o > 0) pending.back().push_back ((int) r.src); continue; }
-        if (kind == K_CTRL) {
-          if (r.src & L3_COMMIT) pending.emplace_back();
-          if (r.src & L3_WAIT) {
-            const size_t done = pending.size() - 1 > (size_t) P.LA ? pending.size() - 1 - (size_t) P.LA : 0;      // closed groups: all but the open one
-            for (; landed < done; ++landed) for (int li: pending[landed]) { ring[li & (P.RN - 1)] = prev[li]; ringTag[li & (P.RN - 1)] = li; }
+        const int n = P.chunkFirst[c] + q;      // (flat index, for the tags; records past the chunk's end are X_NOP)
+        const uint32_t opc = r.ctl & 15u;
+        uint64_t wbits; memcpy (&wbits, &r.w, 8);
+        if ((int) r.src >= rows && opc != X_CTRL && opc != X_NOP) { set_error ("lane2 emulation: a row outside the warp's region"); return 1; }
+        switch (opc) {
+          case X_LOAD: if (o > 0) pending.back().push_back (std::make_pair ((int) r.src, (int) wbits)); break;
+          case X_CTRL:
+            if (r.src & L3_COMMIT) pending.emplace_back();
+            if (r.src & L3_WAIT) {
+              const size_t done = pending.size() - 1 > (size_t) P.LA ? pending.size() - 1 - (size_t) P.LA : 0;
+              for (; landed < done; ++landed) for (auto& ld: pending[landed]) { region[ld.first] = prev[ld.second]; tag[ld.first] = ld.second; }
+            }
+            if (r.src & L3_ORIGIN) acc = o == 0 ? ONE : ZERO;      // the origin cell's start state (forward.defs.h:36), after the preamble
+            break;
+          case X_HINIT: acc = region[r.src]; best = hubDB[(r.ctl >> 4) & 7u]; break;
+          case X_EMIT:
+            if (o > 0) {
+              if (wbits >= L3_EMAX) { set_error ("lane2 emulation: an emission row outside the chunk's area"); return 1; }
+              if (tag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a ring row does not hold the previous-cell value the term means to read"); return 1; }
+              const double x = region[r.src], w = em[(size_t) wbits * nOut + tok];
+              if (op == L_SUM) acc = fma (w, x, acc);
+              else if (op == L_LSE) acc = lse (acc, x + w);
+              else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_INSERT << kb) | emIdx[(size_t) wbits * nOut + tok]; } }
+            }
+            if (op == L_SUM && (r.ctl & 16u)) acc *= f;
+            break;
+          case X_TERM: {
+            if (tag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a window or hub row does not hold the state the term means to read"); return 1; }
+            const double x = region[r.src];
+            if (op == L_SUM) acc = fma (r.w, x, acc);
+            else if (op == L_LSE) acc = lse (acc, x + r.w);
+            else { const double cnd = x + r.w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_SILENT << kb) | (r.ctl >> 16); } }
+            break;
           }
-          if (r.src & L3_ORIGIN) acc = o == 0 ? ONE : ZERO;      // the origin cell's start state (forward.defs.h:36), after the preamble
-          continue;
-        }
-        if (ctl & L2_HINIT) { acc = hubD[L2_HD (ctl)]; best = hubDB[L2_HD (ctl)]; }
-        if (kind == K_EMIT) {
-          if (o > 0) {
-            uint64_t row; memcpy (&row, &r.w, 8);
-            if (row >= L3_EMAX) { set_error ("lane2 emulation: an emission row outside the chunk's area"); return 1; }
-            const double x = ring[r.src], w = em[(size_t) row * nOut + tok];
-            if (ringTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a ring slot does not hold the previous-cell value the term means to read"); return 1; }
-            if (op == L_SUM) acc = fma (w, x, acc);
-            else if (op == L_LSE) acc = lse (acc, x + w);
-            else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_INSERT << kb) | emIdx[(size_t) row * nOut + tok]; } }
+          case X_PUSH: {
+            double& a = region[r.src];
+            if (op == L_SUM) a = fma (r.w, vlast, a);
+            else if (op == L_LSE) a = lse (a, vlast + r.w);
+            else { const double cnd = vlast + r.w; if (a < cnd) { a = cnd; hubDB[(r.ctl >> 4) & 7u] = ((uint32_t) T_SILENT << kb) | (r.ctl >> 16); } }
+            break;
           }
-          if (op == L_SUM && (ctl & L2_SCALE)) acc *= f;
-        } else if (kind == K_WIN || kind == K_HUBS) {
-          if (kind == K_WIN && winTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a window slot does not hold the state the term means to read"); return 1; }
-          if (kind == K_HUBS && hubSTag[r.src] != P.flatWant[n]) { set_error ("lane2 emulation: a hub source is read before it has been written"); return 1; }
-          const double x = kind == K_WIN ? win[r.src] : hubS[r.src];
-          if (op == L_SUM) acc = fma (r.w, x, acc);
-          else if (op == L_LSE) acc = lse (acc, x + r.w);
-          else { const double cnd = x + r.w; if (acc < cnd) { acc = cnd; best = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
-        } else if (kind == K_PUSH) {
-          double& a = hubD[r.src];
-          if (op == L_SUM) a = fma (r.w, vlast, a);
-          else if (op == L_LSE) a = lse (a, vlast + r.w);
-          else { const double cnd = vlast + r.w; if (a < cnd) { a = cnd; hubDB[r.src] = ((uint32_t) T_SILENT << kb) | (ctl >> 16); } }
-        }
-        if (ctl & L2_PRESTORE) { hubD[L2_HD (ctl)] = acc; hubDB[L2_HD (ctl)] = best; acc = ZERO; best = 0xffffu; }
-        if (ctl & L2_END) {
-          win[d & (P.WN - 1)] = acc; winTag[d & (P.WN - 1)] = d;
-          vlast = acc;
-          if (ctl & L2_LIVE) cur[nl++] = acc;
-          if (ctl & L2_HSTORE) { hubS[L2_HS (ctl)] = acc; hubSTag[L2_HS (ctl)] = d; }
-          if (op == L_SUM) {
-            int64_t bits; memcpy (&bits, &acc, 8);
-            const int hi = (int) (bits >> 32);
-            mx = std::max (mx, hi); mn = std::min (mn, (unsigned) (hi - 0x00100000));
-          } else if (op == L_MAX && bpOut) (*bpOut)[(size_t) o * S + d] = best;
-          res = acc; Fres = F;
-          acc = ZERO; best = 0xffffu;
-          ++d;
+          case X_PRESTORE: region[r.src] = acc; hubDB[(r.ctl >> 4) & 7u] = best; acc = ZERO; best = 0xffffu; break;
+          case X_END:
+            region[r.src] = acc; tag[r.src] = d;
+            vlast = acc;
+            if (r.ctl & 32u) { region[wbits] = acc; tag[wbits] = d; }
+            if (r.ctl & 16u) {
+              cur[nl++] = acc;
+              if (op == L_SUM) {      // only live values cross cells: they set the next frame
+                int64_t bits; memcpy (&bits, &acc, 8);
+                const int hi = (int) (bits >> 32);
+                mx = std::max (mx, hi); mn = std::min (mn, (unsigned) (hi - 0x00100000));
+              }
+            }
+            if (op == L_MAX && bpOut) (*bpOut)[(size_t) o * S + d] = best;
+            res = acc; Fres = F;
+            acc = ZERO; best = 0xffffu;
+            ++d;
+            break;
+          default: break;
         }
       }
     }
@@ -814,29 +846,27 @@ __device__ __forceinline__ void l2_mbar_wait (const unsigned mbar, const unsigne
   } while (!ok);
 }
 
-template<int OP>
+template<int OP, int R>
 __global__ void __launch_bounds__(256) lane2_kernel (const __grid_constant__ L2Params p) {
   extern __shared__ __align__(16) char l2smemRaw[];
   __shared__ long long sTask;
   __shared__ int sMaxLo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
-  // shared memory: two chunk buffers | two mbarriers | per warp: window, ring, hub sources, hub destinations | (L_MAX) hub-destination pointers
+  constexpr int LPT = 32 * R;      // reads per warp: read q of a lane is read q * 32 + lane of the warp's task
+  // shared memory: two chunk buffers | two mbarriers | per warp: its region (window, ring, hub sources, hub destinations: rows of
+  // LPT doubles, every access of the warp one conflict-free 256-byte line) | (L_MAX) hub-destination pointers
   char* buf0 = l2smemRaw;
   const unsigned bufAddr = (unsigned) __cvta_generic_to_shared (buf0);
   const unsigned mbarAddr = bufAddr + 2u * (unsigned) p.blobBytes;
   double* warpBase = reinterpret_cast<double*> (l2smemRaw + 2 * p.blobBytes + 16);
-  const int rows = p.WN + p.RN + p.nHubS + p.nHubD;
-  double* win = warpBase + (size_t) warp * rows * 32 + lane;
-  double* ring = win + p.WN * 32;
-  double* hubS = ring + p.RN * 32;
-  double* hubD = hubS + p.nHubS * 32;
-  unsigned* hubDB = reinterpret_cast<unsigned*> (warpBase + (size_t) nWarps * rows * 32) + (size_t) warp * p.nHubD * 32 + lane;      // L_MAX only
-  double* v0 = p.vec + ((size_t) blockIdx.x * nWarps + warp) * 2 * (size_t) p.nLive * 32 + lane;
-  double* v1 = v0 + (size_t) p.nLive * 32;
+  const int rows = p.WN + p.RN + p.nHubS + p.nHubD, rowHubD = p.WN + p.RN + p.nHubS;
+  double* region = warpBase + (size_t) warp * rows * LPT + lane;
+  unsigned* hubDB = reinterpret_cast<unsigned*> (warpBase + (size_t) nWarps * rows * LPT) + (size_t) warp * L2_MAXHUB * LPT + lane;      // L_MAX only
+  double* v0 = p.vec + ((size_t) blockIdx.x * nWarps + warp) * 2 * (size_t) p.nLive * LPT + lane;
+  double* v1 = v0 + (size_t) p.nLive * LPT;
   const double ZERO = OP == L_SUM ? 0. : l_ninf(), ONE = OP == L_SUM ? 1. : 0.;
   const unsigned kb = p.bpBytes == 1 ? 6 : 14;
   const double LN2 = 0.693147180559945309417232121458;
-  const int winMask = p.WN - 1, ringMask = p.RN - 1;
   if (tid == 0) {
     l2_mbar_init (mbarAddr, 1);
     l2_mbar_init (mbarAddr + 8, 1);
@@ -849,37 +879,52 @@ __global__ void __launch_bounds__(256) lane2_kernel (const __grid_constant__ L2P
     if (tid == 0) { sTask = (long long) atomicAdd (p.counter, (unsigned long long) nWarps); sMaxLo = -1; }
     __syncthreads();
     const long long task = sTask + warp;
-    if (sTask * 32 >= p.nWork) break;
-    const long long rd = task * 32 + lane;
-    const bool have = rd < p.nWork;
-    const int64_t k = have ? p.order[rd] : 0;
-    const uint8_t* y = p.b.y + p.b.yOff[k];
-    const int Lo = have ? (int) (p.b.yOff[k + 1] - p.b.yOff[k]) : -1;
-    int warpMaxLo = Lo;
+    if (sTask * LPT >= p.nWork) break;
+    int64_t k[R];
+    const uint8_t* y[R];
+    int Lo[R], warpMaxLo = -1;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const long long rd = task * LPT + q * 32 + lane;
+      const bool have = rd < p.nWork;
+      k[q] = have ? p.order[rd] : 0;
+      y[q] = p.b.y + p.b.yOff[k[q]];
+      Lo[q] = have ? (int) (p.b.yOff[k[q] + 1] - p.b.yOff[k[q]]) : -1;
+      warpMaxLo = max (warpMaxLo, Lo[q]);
+    }
 #pragma unroll
     for (int off = 16; off; off >>= 1) warpMaxLo = max (warpMaxLo, __shfl_xor_sync (0xffffffffu, warpMaxLo, off));
     if (lane == 0) atomicMax (&sMaxLo, warpMaxLo);
     __syncthreads();
     const int ctaMaxLo = sMaxLo;
-    unsigned char* bp = OP == L_MAX && p.bp && task * 32 < p.nWork ? p.bp + p.bpOff[task] + (size_t) lane * p.bpBytes : nullptr;
-    bool bad = false;
-    int Fprev = 0, Gprev = L_SENT;
+    unsigned char* bp = OP == L_MAX && p.bp && task * LPT < p.nWork ? p.bp + p.bpOff[task] + (size_t) lane * p.bpBytes : nullptr;
+    bool bad[R];
+    int Fprev[R], Gprev[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { bad[q] = false; Fprev[q] = 0; Gprev[q] = L_SENT; }
     for (int o = 0; o <= ctaMaxLo; ++o) {
       const bool active = o <= warpMaxLo;      // (a warp whose reads have ended keeps the CTA's barriers company)
       double* cur = (o & 1) ? v1 : v0;
       const double* prev = (o & 1) ? v0 : v1;
-      const int tok = (o <= Lo && o > 0) ? y[o - 1] - 1 : 0;
-      int F = 0, mx = 0;
-      double f = 1.;
-      if (OP == L_SUM && o > 0) { if (Gprev == L_SENT) f = 0.; else { F = Gprev; f = l_pow2 (Fprev - F); } }
-      unsigned mn = 0xffffffffu, best = 0xffffu;
-      double acc = ZERO, res = ZERO, vlast = ZERO;
+      int tok[R], F[R], mx[R];
+      unsigned mn[R], best[R];
+      double f[R], acc[R], res[R], vlast[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        tok[q] = (o <= Lo[q] && o > 0) ? y[q][o - 1] - 1 : 0;
+        F[q] = 0; f[q] = 1.;
+        if (OP == L_SUM && o > 0) { if (Gprev[q] == L_SENT) f[q] = 0.; else { F[q] = Gprev[q]; f[q] = l_pow2 (Fprev[q] - F[q]); } }
+        mx[q] = 0; mn[q] = 0xffffffffu; best[q] = 0xffffu;
+        acc[q] = ZERO; res[q] = ZERO; vlast[q] = ZERO;
+      }
       if (active)
-        for (int hd = 0; hd < p.nHubD; ++hd) { hubD[hd * 32] = ZERO; if (OP == L_MAX) hubDB[hd * 32] = 0xffffu; }
+        for (int hd = 0; hd < p.nHubD; ++hd) {
+#pragma unroll
+          for (int q = 0; q < R; ++q) { region[(rowHubD + hd) * LPT + q * 32] = ZERO; if (OP == L_MAX) hubDB[hd * LPT + q * 32] = 0xffffu; }
+        }
       const bool usePrev = o > 0;
       double* curOut = cur;
-      unsigned char* bpRow = bp ? bp + (size_t) o * p.S * 32 * p.bpBytes : nullptr;
-      int d = 0;
+      unsigned char* bpRow = bp ? bp + (size_t) o * p.S * LPT * p.bpBytes : nullptr;
       __syncthreads();      // everyone has left the previous cell's last chunk: its buffer may be refilled
       if (tid == 0) l2_bulk_load (bufAddr, p.blob, (unsigned) p.blobBytes, mbarAddr);
       for (int c = 0; c < p.nChunks; ++c) {
@@ -892,81 +937,139 @@ __global__ void __launch_bounds__(256) lane2_kernel (const __grid_constant__ L2P
         const uint4* rec = reinterpret_cast<const uint4*> (bl);
         const double* em = reinterpret_cast<const double*> (bl + p.emOff);
         const uint16_t* emIdx = reinterpret_cast<const uint16_t*> (bl + p.idxOff);
-#pragma unroll 4
+        uint4 nx = rec[0];
+#pragma unroll 2
         for (int n = 0; n < L3_NREC; ++n) {
-          const uint4 u = rec[n];
-          const unsigned ctl = u.w, kind = ctl & 7u;
-          if (kind == K_LOAD) {
-            if (usePrev) l2_cp_async8 (ring + (u.z & ringMask) * 32, prev + (size_t) u.z * 32);
-            continue;
-          }
-          if (kind == K_CTRL) {
-            if (usePrev && (u.z & L3_COMMIT)) l2_commit();
-            if (usePrev && (u.z & L3_WAIT)) l2_wait (p.LA);
-            if (u.z & L3_ORIGIN) acc = o == 0 ? ONE : ZERO;
-            continue;
-          }
-          if (ctl & L2_HINIT) { acc = hubD[L2_HD (ctl) * 32]; if (OP == L_MAX) best = hubDB[L2_HD (ctl) * 32]; }
-          if (kind == K_EMIT) {
-            if (usePrev) {
-              const double x = ring[u.z * 32], w = em[u.x * p.nOut + tok];
-              if (OP == L_SUM) acc = fma (w, x, acc);
-              else if (OP == L_LSE) acc = l_lse (acc, x + w);
-              else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((unsigned) T_INSERT << kb) | emIdx[u.x * p.nOut + tok]; } }
+          const uint4 u = nx;
+          nx = rec[n + 1];      // (the record area ends with a spare record)
+          double* row = region + u.z * LPT;
+          switch (u.w & 15u) {
+            case X_TERM: {
+              const double w = __hiloint2double ((int) u.y, (int) u.x);
+              double x[R];
+#pragma unroll
+              for (int q = 0; q < R; ++q) x[q] = row[q * 32];
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                if (OP == L_SUM) acc[q] = fma (w, x[q], acc[q]);
+                else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w);
+                else { const double cnd = x[q] + w; if (acc[q] < cnd) { acc[q] = cnd; best[q] = ((unsigned) T_SILENT << kb) | (u.w >> 16); } }
+              }
+              break;
             }
-            if (OP == L_SUM && (ctl & L2_SCALE)) acc *= f;
-          } else if (kind == K_WIN || kind == K_HUBS) {
-            const double w = __hiloint2double ((int) u.y, (int) u.x);
-            const double x = (kind == K_WIN ? win : hubS)[u.z * 32];
-            if (OP == L_SUM) acc = fma (w, x, acc);
-            else if (OP == L_LSE) acc = l_lse (acc, x + w);
-            else { const double cnd = x + w; if (acc < cnd) { acc = cnd; best = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
-          } else if (kind == K_PUSH) {
-            const double w = __hiloint2double ((int) u.y, (int) u.x);
-            double* a = hubD + u.z * 32;
-            if (OP == L_SUM) *a = fma (w, vlast, *a);
-            else if (OP == L_LSE) *a = l_lse (*a, vlast + w);
-            else { const double cnd = vlast + w; if (*a < cnd) { *a = cnd; hubDB[u.z * 32] = ((unsigned) T_SILENT << kb) | (ctl >> 16); } }
-          }
-          if (ctl & L2_PRESTORE) {
-            hubD[L2_HD (ctl) * 32] = acc;
-            if (OP == L_MAX) hubDB[L2_HD (ctl) * 32] = best;
-            acc = ZERO; best = 0xffffu;
-          }
-          if (ctl & L2_END) {
-            win[(d & winMask) * 32] = acc;
-            vlast = acc;
-            if (ctl & L2_LIVE) { *curOut = acc; curOut += 32; }
-            if (ctl & L2_HSTORE) hubS[L2_HS (ctl) * 32] = acc;
-            if (OP == L_SUM) {
-              const int hi = __double2hiint (acc);
-              mx = max (mx, hi);
-              mn = min (mn, (unsigned) (hi - 0x00100000));      // zeros and denormals wrap to the top and drop out
-            } else if (OP == L_MAX && bpRow) {
-              if (p.bpBytes == 1) *bpRow = (unsigned char) best; else *reinterpret_cast<uint16_t*> (bpRow) = (uint16_t) best;
-              bpRow += 32 * p.bpBytes;
+            case X_END: {
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                row[q * 32] = acc[q];
+                vlast[q] = acc[q];
+                res[q] = acc[q];      // after the last record: the end state
+              }
+              if (u.w & 32u) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) region[u.x * LPT + q * 32] = acc[q];
+              }
+              if (u.w & 16u) {      // a live state: it crosses to the next cell, and sets that cell's frame
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                  curOut[q * 32] = acc[q];
+                  if (OP == L_SUM) {
+                    const int hi = __double2hiint (acc[q]);
+                    mx[q] = max (mx[q], hi);
+                    mn[q] = min (mn[q], (unsigned) (hi - 0x00100000));      // zeros and denormals wrap to the top and drop out
+                  }
+                }
+                curOut += LPT;
+              }
+              if (OP == L_MAX && bpRow) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                  if (p.bpBytes == 1) bpRow[q * 32] = (unsigned char) best[q]; else reinterpret_cast<uint16_t*> (bpRow)[q * 32] = (uint16_t) best[q];
+                }
+                bpRow += LPT * p.bpBytes;
+              }
+#pragma unroll
+              for (int q = 0; q < R; ++q) { acc[q] = ZERO; best[q] = 0xffffu; }
+              break;
             }
-            res = acc;      // after the last record: the end state
-            acc = ZERO;
-            best = 0xffffu;
-            ++d;
+            case X_EMIT: {
+              if (usePrev) {
+                double x[R], w[R];
+#pragma unroll
+                for (int q = 0; q < R; ++q) { x[q] = row[q * 32]; w[q] = em[u.x * p.nOut + tok[q]]; }
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                  if (OP == L_SUM) acc[q] = fma (w[q], x[q], acc[q]);
+                  else if (OP == L_LSE) acc[q] = l_lse (acc[q], x[q] + w[q]);
+                  else { const double cnd = x[q] + w[q]; if (acc[q] < cnd) { acc[q] = cnd; best[q] = ((unsigned) T_INSERT << kb) | emIdx[u.x * p.nOut + tok[q]]; } }
+                }
+              }
+              if (OP == L_SUM && (u.w & 16u)) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) acc[q] *= f[q];
+              }
+              break;
+            }
+            case X_PUSH: {
+              const double w = __hiloint2double ((int) u.y, (int) u.x);
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                if (OP == L_SUM) row[q * 32] = fma (w, vlast[q], row[q * 32]);
+                else if (OP == L_LSE) row[q * 32] = l_lse (row[q * 32], vlast[q] + w);
+                else { const double cnd = vlast[q] + w; if (row[q * 32] < cnd) { row[q * 32] = cnd; hubDB[((u.w >> 4) & 7u) * LPT + q * 32] = ((unsigned) T_SILENT << kb) | (u.w >> 16); } }
+              }
+              break;
+            }
+            case X_LOAD: {
+              if (usePrev) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) l2_cp_async8 (row + q * 32, prev + (size_t) u.x * LPT + q * 32);
+              }
+              break;
+            }
+            case X_CTRL: {
+              if (usePrev && (u.z & L3_COMMIT)) l2_commit();
+              if (usePrev && (u.z & L3_WAIT)) l2_wait (p.LA);
+              if (u.z & L3_ORIGIN) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) acc[q] = o == 0 ? ONE : ZERO;
+              }
+              break;
+            }
+            case X_HINIT: {
+#pragma unroll
+              for (int q = 0; q < R; ++q) { acc[q] = row[q * 32]; if (OP == L_MAX) best[q] = hubDB[((u.w >> 4) & 7u) * LPT + q * 32]; }
+              break;
+            }
+            case X_PRESTORE: {
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                row[q * 32] = acc[q];
+                if (OP == L_MAX) hubDB[((u.w >> 4) & 7u) * LPT + q * 32] = best[q];
+                acc[q] = ZERO; best[q] = 0xffffu;
+              }
+              break;
+            }
+            default: break;
           }
         }
       }
       if (usePrev && active) l2_wait (0);
       if (active) {
-        if (OP == L_SUM) {
-          int Gc = L_SENT;
-          if (mx >= 0x00100000) {
-            const int emx = mx >> 20;
-            Gc = F + emx - 1023;
-            if (o <= Lo && (emx == 0x7ff || (mn != 0xffffffffu && emx - (int) ((mn >> 20) + 1) > L_SPREAD))) bad = true;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          if (OP == L_SUM) {
+            int Gc = L_SENT;
+            if (mx[q] >= 0x00100000) {
+              const int emx = mx[q] >> 20;
+              Gc = F[q] + emx - 1023;
+              if (o <= Lo[q] && (emx == 0x7ff || (mn[q] != 0xffffffffu && emx - (int) ((mn[q] >> 20) + 1) > L_SPREAD))) bad[q] = true;
+            }
+            Fprev[q] = F[q]; Gprev[q] = Gc;
           }
-          Fprev = F; Gprev = Gc;
-        }
-        if (o == Lo) {
-          if (OP == L_SUM) { p.result[k] = res > 0. ? log (res) + F * LN2 : l_ninf(); p.flag[k] = bad || !(res > 0.) || !(res < 1e300); }
-          else p.result[k] = res;
+          if (o == Lo[q]) {
+            if (OP == L_SUM) { p.result[k[q]] = res[q] > 0. ? log (res[q]) + F[q] * LN2 : l_ninf(); p.flag[k[q]] = bad[q] || !(res[q] > 0.) || !(res[q] < 1e300); }
+            else p.result[k[q]] = res[q];
+          }
         }
       }
     }
@@ -985,8 +1088,8 @@ struct LBuf {
 // independent chain per thread makes up for the missing warps in the sums (65 536 reads: 40 -> 89 GCUPS),
 // while the max-plus sweep, which carries a pointer per chain, stays at one.
 static int lane_reads_per_lane (const mb_machine* m, const LHost* h, int64_t nWork, int op) {
-  if (h->l2.ok) return 1;      // the windowed sweep keeps one read per lane
   if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
+  if (h->l2.ok) return nWork >= (int64_t) h->numSMs * 4 * 128 ? 4 : nWork >= (int64_t) h->numSMs * 4 * 64 ? 2 : 1;      // the interpreter's work per record is shared by a lane's reads
   if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
@@ -1027,20 +1130,21 @@ static int lane_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>
   return 0;
 }
 
-// the windowed sweep (lane2): CTAs of W warps, as many per SM as shared memory holds
-template<int OP>
-static int lane2_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
-                         unsigned char* dBp, const int64_t* dBpOff) {
+// the windowed sweep (lane2): CTAs of W warps of 32 * R reads, as many per SM as shared memory holds
+template<int OP, int R>
+static int lane2_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
+                           unsigned char* dBp, const int64_t* dBpOff) {
   LHost* h = lh (m);
   const L2Prog& P = h->l2;
-  const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + 31) / 32;
-  const size_t perWarp = (size_t) (P.WN + P.RN + P.nHubS + P.nHubD) * 32 * 8 + (OP == L_MAX ? (size_t) P.nHubD * 32 * 4 : 0);
+  constexpr int LPT = 32 * R;
+  const int64_t nWork = (int64_t) order.size(), nTasks = (nWork + LPT - 1) / LPT;
+  const size_t perWarp = (size_t) (P.WN + P.RN + P.nHubS + P.nHubD) * LPT * 8 + (OP == L_MAX ? (size_t) L2_MAXHUB * LPT * 4 : 0);
   const size_t fixed = 2 * (size_t) P.blobBytes + 16 + 64;
   const size_t kSmem = 227 * 1024 - 2048;      // (the kernel's two static words included)
-  // warps per CTA: the largest of 8, 6, 4, 2, 1 that gives the most warps per SM
+  // warps per CTA: the one of 8, 6, 4, 3, 2, 1 that gives the most warps per SM (the largest on a tie)
   int W = 1, ctasPerSM = 1, bestWarps = 0;
   const int wantW = m->opt.get ("lane_warps_per_cta", 0);
-  for (int w: { 8, 6, 4, 2, 1 }) {
+  for (int w: { 8, 6, 4, 3, 2, 1 }) {
     if (wantW && w != wantW) continue;
     const size_t need = fixed + (size_t) w * perWarp;
     if (need > kSmem) continue;
@@ -1049,14 +1153,14 @@ static int lane2_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>&
   }
   if (!bestWarps) { set_error ("lane engine: the window does not fit in shared memory"); return 1; }
   if (m->opt.has ("lane_warps")) ctasPerSM = std::max (1, std::min (ctasPerSM, m->opt.get ("lane_warps", 16) / W));
-  while (W > 1 && nTasks < (int64_t) h->numSMs * W) W /= 2;      // few reads: narrower CTAs spread them over the SMs
+  while (W > 1 && nTasks < (int64_t) h->numSMs * W * ctasPerSM) W = (W + 1) / 2;      // few reads: narrower CTAs spread them over the SMs
   const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + W - 1) / W, (int64_t) ctasPerSM * h->numSMs));
   const size_t smem = fixed + (size_t) W * perWarp;
-  MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   b->wsOrderHoldsFull = false;
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
   unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
-  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * W * 2 * std::max (P.nLive, 1) * 32 * 8);
+  double* dVec = (double*) ws_reserve (b, WS_BND, (size_t) grid * W * 2 * std::max (P.nLive, 1) * LPT * 8);
   if (!dOrder || !dCounter || !dVec) return 1;
   MB_CUDA (cudaMemcpyAsync (dOrder, order.data(), order.size() * 8, cudaMemcpyHostToDevice, b->stream));
   MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
@@ -1070,9 +1174,9 @@ static int lane2_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>&
   p.result = dResult; p.flag = dFlag; p.vec = dVec;
   p.bp = dBp; p.bpOff = dBpOff;
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "lane engine (windowed): %lld reads, grid %d x %d threads (%d CTAs per SM), %zu B smem per CTA, window %d, ring %d, hubs %d + %d, %d live of %d states, %zu records in %d chunks of %d B\n",
-             (long long) nWork, grid, 32 * W, ctasPerSM, smem, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, h->S, P.flat.size(), P.nChunks, P.blobBytes);
-  lane2_kernel<OP><<<grid, 32 * W, smem, b->stream>>> (p);
+    fprintf (stderr, "lane engine (windowed): %lld reads, %d per lane, grid %d x %d threads (%d CTAs per SM), %zu B smem per CTA, window %d, ring %d, hubs %d + %d, %d live of %d states, %zu records in %d chunks of %d B\n",
+             (long long) nWork, R, grid, 32 * W, ctasPerSM, smem, P.WN, P.RN, P.nHubS, P.nHubD, P.nLive, h->S, P.flat.size(), P.nChunks, P.blobBytes);
+  lane2_kernel<OP, R><<<grid, 32 * W, smem, b->stream>>> (p);
   MB_CUDA (cudaGetLastError());
   return 0;
 }
@@ -1080,7 +1184,9 @@ static int lane2_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>&
 template<int OP>
 static int lane_launch (mb_machine* m, mb_batch* b, int R, const std::vector<int64_t>& order, double* dResult, int32_t* dFlag,
                         unsigned char* dBp, const int64_t* dBpOff) {
-  if (lh (m)->l2.ok) return lane2_launch<OP> (m, b, order, dResult, dFlag, dBp, dBpOff);      // (one read per lane)
+  if (lh (m)->l2.ok)
+    return R >= 4 ? lane2_launch_r<OP, 4> (m, b, order, dResult, dFlag, dBp, dBpOff) : R == 2 ? lane2_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff)
+                  : lane2_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);
   return R == 4 ? lane_launch_r<OP, 4> (m, b, order, dResult, dFlag, dBp, dBpOff)
        : R == 2 ? lane_launch_r<OP, 2> (m, b, order, dResult, dFlag, dBp, dBpOff)
                 : lane_launch_r<OP, 1> (m, b, order, dResult, dFlag, dBp, dBpOff);

@@ -75,6 +75,7 @@ struct PairResult {
   vector<long long> path;  // global transition ids, start -> end
   vector<long long> sample;  // a path drawn by ForwardMatrix::samplePath
   string matrices;
+  string postTrans;          // top of BackwardMatrix::postTransQueue + the trace from its first entry
 };
 
 int main (int argc, char** argv) {
@@ -155,7 +156,8 @@ int main (int argc, char** argv) {
 
     auto wants = [&] (const char* w) { return (("," + doList + ",").find (string (",") + w + ",")) != string::npos; };
     const bool doForward = wants ("forward"), doRolling = wants ("rolling"), doViterbi = wants ("viterbi"), doPath = wants ("path"),
-      doBackward = wants ("backward"), doCounts = wants ("counts"), doMatrices = wants ("matrices"), doSample = wants ("sample");
+      doBackward = wants ("backward"), doCounts = wants ("counts"), doMatrices = wants ("matrices"), doSample = wants ("sample"),
+      doPostTrans = wants ("posttrans");
 
     vector<PairResult> res (pairs.size());
     vector<MachineCounts> threadCounts ((size_t) nThreads, MachineCounts (eval));
@@ -205,6 +207,37 @@ int main (int argc, char** argv) {
           r.backward = b.logLike();
           threadCounts[tid].loglike += r.forward;
         } else if (doBackward) { const BackwardMatrix b (eval, sp); r.backward = b.logLike(); }
+        if (doPostTrans) {
+          // BackwardMatrix::postTransQueue (backward.cpp:52-56): every (cell, transition) posterior, largest first; then
+          // BackwardMatrix::traceFrom with a TraceTerminator (backward.cpp:98-108) from the first entry's SOURCE cell
+          const ForwardMatrix f (eval, sp);
+          const BackwardMatrix b (eval, sp);
+          r.forward = f.logLike();
+          ostringstream m;
+          if (r.forward > -numeric_limits<double>::infinity()) {
+            BackwardMatrix::PostTransQueue q = b.postTransQueue (f);
+            m << ",\"postTransCount\":" << q.size() << ",\"postTrans\":[";
+            BackwardMatrix::PostTrans first = q.top();
+            for (int n = 0; n < 12 && !q.empty(); ++n) {
+              const BackwardMatrix::PostTrans pt = q.top();
+              q.pop();
+              m << (n ? "," : "") << "[" << pt.inPos << "," << pt.outPos << "," << (eval.state[pt.src].transOffset + pt.transIndex) << "," << dstr (pt.weight) << "]";
+            }
+            m << "]";
+            const MachineTransition& mt = machine.state[first.src].getTransition (first.transIndex);
+            const long srcIn = first.inPos - (mt.inputEmpty() ? 0 : 1), srcOut = first.outPos - (mt.outputEmpty() ? 0 : 1);
+            vector<long long> visited;
+            BackwardMatrix::TraceTerminator collect = [&] (Envelope::InputIndex, Envelope::OutputIndex, StateIndex src, EvaluatedMachineState::TransIndex ti) {
+              visited.push_back ((long long) (eval.state[src].transOffset + ti));
+              return false;
+            };
+            b.traceFrom (machine, f, srcIn, srcOut, first.src, first.transIndex, collect);
+            m << ",\"traceFrom\":[";
+            for (size_t n = 0; n < visited.size(); ++n) m << (n ? "," : "") << visited[n];
+            m << "]";
+          }
+          r.postTrans = m.str();
+        }
         if (doMatrices) {
           const ForwardMatrix f (eval, sp);
           const BackwardMatrix b (eval, sp);
@@ -249,7 +282,7 @@ int main (int argc, char** argv) {
         cout << (k ? ",\n  " : "\n  ") << "{\"tokenizable\":" << (r.tokenizable ? "true" : "false");
         const double ninf = -numeric_limits<double>::infinity();
         if (doRolling) cout << ",\"rolling\":" << dstr (r.tokenizable ? r.rolling : ninf);
-        if (doForward || doCounts || doMatrices || doSample) cout << ",\"forward\":" << dstr (r.tokenizable ? r.forward : ninf);
+        if (doForward || doCounts || doMatrices || doSample || doPostTrans) cout << ",\"forward\":" << dstr (r.tokenizable ? r.forward : ninf);
         if (doBackward || doCounts || doMatrices) cout << ",\"backward\":" << dstr (r.tokenizable ? r.backward : ninf);
         if (doViterbi || doPath || doMatrices) cout << ",\"viterbi\":" << dstr (r.tokenizable ? r.viterbi : ninf);
         if (doPath) {
@@ -267,7 +300,7 @@ int main (int argc, char** argv) {
           cout << ",\"env\":";
           env.writeJson (cout);
         }
-        cout << r.matrices << "}";
+        cout << r.matrices << r.postTrans << "}";
       }
       cout << "\n ]";
     }

@@ -16,7 +16,7 @@ if os.environ.get("LEN"):
 y, y_off = bench.synth_ragged(bench.SEED + 5, lens, mj["n_out"])
 batch = capi.Batch(x=np.zeros(0, np.uint8), x_off=np.zeros(n + 1, np.int64), y=y, y_off=y_off)
 cells = batch.cell_states(mj["n_states"])
-variants = [dict(), dict(lane_warps_per_cta=4), dict(lane_warps_per_cta=2), dict(lane_la=5), dict(lane_bs=16), dict(lane_warps=8), dict(lane_old=1)]
+variants = [dict(), dict(lane_r=1), dict(lane_r=2), dict(lane_r=4), dict(lane_r=4, lane_warps_per_cta=2), dict(lane_r=2, lane_bs=16), dict(lane_old=1)]
 if os.environ.get("VARIANTS"):
     variants = json.loads(os.environ["VARIANTS"])
 ref = None
