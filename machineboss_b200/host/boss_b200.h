@@ -24,8 +24,11 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <algorithm>
+#include <functional>
 #include <list>
 #include <map>
+#include <queue>
 #include <memory>
 #include <random>
 #include <cmath>
@@ -405,6 +408,15 @@ struct EvaluatedMachine {
     for (size_t t = 0; t < dst.size(); ++t) if ((StateIndex) dst[t] == s && in[t] == inTok && out[t] == outTok) ids.push_back ((int32_t) t);
     return ids;
   }
+  // the role of EvaluatedMachineState::outgoing: ids of the transitions out of `s` labelled (inTok, outTok), by destination
+  // state, then transition index
+  vector<int32_t> outgoingIds (StateIndex s, int inTok, int outTok) const {
+    vector<int32_t> ids;
+    for (size_t t = state[s].transOffset; t < state[s].transOffset + state[s].nTransitions; ++t) if (in[t] == inTok && out[t] == outTok) ids.push_back ((int32_t) t);
+    std::stable_sort (ids.begin(), ids.end(), [&] (int32_t a, int32_t b) { return dst[a] < dst[b]; });
+    return ids;
+  }
+  StateIndex transDest (int32_t id) const { return (StateIndex) dst[id]; }
   StateIndex transSource (int32_t id) const { return (StateIndex) src[id]; }
   double transLogWeight (int32_t id) const { return logWeight[id]; }
 
@@ -626,21 +638,29 @@ protected:
     DeviceBatch b (machine, vector<const SeqPair*> (1, &seqPair));
     mbCheck (mb_matrix (machine.handle(), b.handle(), 0, kind, cells.data()));
   }
-  // DPMatrix::traceBack with a TransSelector (dpmatrix.defs.h:82-110): candidates in the reference's order
-  // (match, delete, insert, silent sources; each list by source state, then transition index)
-  template<class Selector>
-  MachinePath traceBackWith (Selector select, int s) const {
-    long i = (long) seqPair.input.seq.size(), o = (long) seqPair.output.seq.size();
-    if (!(cell (i, o, s) > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceback: no finite-weight paths");
+public:
+  typedef long InputIndex;
+  typedef long OutputIndex;
+  // called with the cell and state a step starts from (traceBack: the step's source) and the transition's index in
+  // that state's list; returning true ends the trace (dpmatrix.h:71)
+  typedef std::function<bool (InputIndex, OutputIndex, StateIndex, size_t)> TraceTerminator;
+  typedef std::function<size_t (const vector<double>&)> TransSelector;
+  static size_t selectMaxTrans (const vector<double>& logWeights) {      // the FIRST maximum (dpmatrix.defs.h:171-174)
+    return (size_t) std::distance (logWeights.begin(), std::max_element (logWeights.begin(), logWeights.end()));
+  }
+  // DPMatrix::traceBack (..., TraceTerminator, TransSelector) (dpmatrix.defs.h:82-110): from (inPos, outPos, s) towards the
+  // origin.  Candidates in the reference's order: match, delete, insert, silent sources, each by source state then
+  // transition index.  (This is the overload that honours the position; see SURVEY 8a row 10 for the others' quirk.)
+  void traceBack (InputIndex i, OutputIndex o, StateIndex s, TraceTerminator stopTrace, TransSelector select = selectMaxTrans) const {
+    if (!(cell (i, o, (int) s) > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceback: no finite-weight paths");
     const vector<InputToken> inTok = machine.inputTokenizer.tokenize (seqPair.input.seq);
     const vector<OutputToken> outTok = machine.outputTokenizer.tokenize (seqPair.output.seq);
-    list<MachineTransition> rev;
     while (i > 0 || o > 0 || s != 0) {
       vector<double> ll;
       vector<int32_t> ids;
       const int a = i ? inTok[i - 1] : 0, c = o ? outTok[o - 1] : 0;
       auto visit = [&] (int wantIn, int wantOut, long pi, long po) {
-        for (int32_t id: machine.incomingIds (s, wantIn, wantOut)) { ids.push_back (id); ll.push_back (cell (pi, po, machine.transSource (id)) + machine.transLogWeight (id)); }
+        for (int32_t id: machine.incomingIds (s, wantIn, wantOut)) { ids.push_back (id); ll.push_back (cell (pi, po, (int) machine.transSource (id)) + machine.transLogWeight (id)); }
       };
       if (i && o) visit (a, c, i - 1, o - 1);
       if (i) visit (a, 0, i - 1, o);
@@ -648,13 +668,49 @@ protected:
       visit (0, 0, i, o);
       if (ids.empty()) throw runtime_error ("traceback: dead end");
       const size_t best = select (ll);
-      const int32_t id = ids[best < ids.size() ? best : ids.size() - 1];
-      const MachineTransition& t = machine.transition (id);
-      rev.push_front (t);
+      const MachineTransition t = machine.transition (ids[best < ids.size() ? best : ids.size() - 1]);
       if (!t.inputEmpty()) --i;
       if (!t.outputEmpty()) --o;
-      s = (int) machine.transSource (id);
+      s = t.src;
+      if (stopTrace (i, o, s, t.transIndex)) break;
     }
+  }
+  // DPMatrix::traceForward (dpmatrix.defs.h:128-158) over a Backward matrix: from (inPos, outPos, s) towards the end
+  void traceForward (InputIndex i, OutputIndex o, StateIndex s, TraceTerminator stopTrace, TransSelector select = selectMaxTrans) const {
+    if (!(cell (i, o, (int) s) > -std::numeric_limits<double>::infinity())) throw runtime_error ("Can't do traceforward: no finite-weight paths");
+    const vector<InputToken> inTok = machine.inputTokenizer.tokenize (seqPair.input.seq);
+    const vector<OutputToken> outTok = machine.outputTokenizer.tokenize (seqPair.output.seq);
+    const long Li = (long) inTok.size(), Lo = (long) outTok.size();
+    while (i < Li || o < Lo || s != machine.nStates() - 1) {
+      vector<double> ll;
+      vector<int32_t> ids;
+      const int a = i < Li ? inTok[i] : 0, c = o < Lo ? outTok[o] : 0;
+      auto visit = [&] (int wantIn, int wantOut, long ni, long no) {
+        for (int32_t id: machine.outgoingIds (s, wantIn, wantOut)) { ids.push_back (id); ll.push_back (cell (ni, no, (int) machine.transDest (id)) + machine.transLogWeight (id)); }
+      };
+      if (i < Li && o < Lo) visit (a, c, i + 1, o + 1);
+      if (i < Li) visit (a, 0, i + 1, o);
+      if (o < Lo) visit (0, c, i, o + 1);
+      visit (0, 0, i, o);
+      if (ids.empty()) throw runtime_error ("traceforward: dead end");
+      const size_t best = select (ll);
+      const MachineTransition t = machine.transition (ids[best < ids.size() ? best : ids.size() - 1]);
+      if (stopTrace (i, o, s, t.transIndex)) break;
+      if (!t.inputEmpty()) ++i;
+      if (!t.outputEmpty()) ++o;
+      s = t.dest;
+    }
+  }
+protected:
+  // the whole path from the end cell, as a MachinePath (ViterbiMatrix::path, ForwardMatrix::samplePath)
+  template<class Selector>
+  MachinePath traceBackWith (Selector select, int s) const {
+    list<MachineTransition> rev;
+    TraceTerminator collect = [&] (InputIndex, OutputIndex, StateIndex src, size_t ti) {
+      rev.push_front (machine.transition ((int32_t) (machine.state[src].transOffset + ti)));
+      return false;
+    };
+    traceBack ((long) seqPair.input.seq.size(), (long) seqPair.output.seq.size(), (StateIndex) s, collect, select);
     MachinePath p;
     p.trans.assign (rev.begin(), rev.end());
     return p;
@@ -701,6 +757,49 @@ public:
   BackwardMatrix (const EvaluatedMachine& m, const SeqPair& sp, const Envelope&) : StoredMatrix (m, sp, MB_MATRIX_BACKWARD) { fill(); }
   double logLike() const { return ll; }
   void getCounts (const ForwardMatrix&, MachineCounts&) const;   // backward.cpp:58-60
+  // ---- consumers of the stored matrices (backward.h:13-34, backward.cpp:52-56,62-108) ----
+  // called per (source state, transition index, DESTINATION cell of the transition, posterior probability)
+  typedef std::function<void (StateIndex, size_t, InputIndex, OutputIndex, double)> BackTransVisitor;
+  struct PostTrans {
+    InputIndex inPos;
+    OutputIndex outPos;
+    StateIndex src;
+    size_t transIndex;
+    double weight;
+    bool operator< (const PostTrans& p) const { return weight < p.weight; }
+  };
+  typedef std::priority_queue<PostTrans> PostTransQueue;
+  // BackwardMatrix::getCounts with a visitor (backward.cpp:62-87): every (cell, outgoing transition) posterior, cells from the
+  // end to the origin, states descending, each state's match / delete / insert / silent lists in turn.  Host loop over the two
+  // stored matrices (mb_matrix): the per-pair form; sums over a list belong in MachineCounts.
+  void getCounts (const ForwardMatrix& forward, const BackTransVisitor& visit) const {
+    const vector<InputToken> inTok = machine.inputTokenizer.tokenize (seqPair.input.seq);
+    const vector<OutputToken> outTok = machine.outputTokenizer.tokenize (seqPair.output.seq);
+    const long Li = (long) inTok.size(), Lo = (long) outTok.size();
+    const double total = logLike();
+    for (long o = Lo; o >= 0; --o)
+      for (long i = Li; i >= 0; --i)
+        for (long s = (long) machine.nStates() - 1; s >= 0; --s) {
+          const double logOdds = forward.cell (i, o, (int) s) - total;
+          auto group = [&] (int wantIn, int wantOut, long ni, long no) {
+            for (int32_t id: machine.outgoingIds ((StateIndex) s, wantIn, wantOut))
+              visit ((StateIndex) s, (size_t) id - machine.state[s].transOffset, ni, no, exp (logOdds + (cell (ni, no, (int) machine.transDest (id)) + machine.transLogWeight (id))));
+          };
+          const int a = i < Li ? inTok[i] : 0, c = o < Lo ? outTok[o] : 0;
+          if (i < Li && o < Lo) group (a, c, i + 1, o + 1);
+          if (i < Li) group (a, 0, i + 1, o);
+          if (o < Lo) group (0, c, i, o + 1);
+          group (0, 0, i, o);
+        }
+  }
+  PostTransQueue postTransQueue (const ForwardMatrix& forward) const {      // backward.cpp:52-56
+    PostTransQueue q;
+    getCounts (forward, [&] (StateIndex s, size_t ti, InputIndex ip, OutputIndex op, double w) { q.push (PostTrans { ip, op, s, ti, w }); });
+    return q;
+  }
+  // BackwardMatrix::traceFrom with a TraceTerminator (backward.cpp:98-108): back from (inPos, outPos, state) through the Forward
+  // matrix, then the transition itself, then on through this matrix to the end
+  void traceFrom (const ForwardMatrix& forward, InputIndex i, OutputIndex o, StateIndex s, size_t transIndex, TraceTerminator stopTrace) const;
 private:
   double ll = 0;
   void fill() {
@@ -777,6 +876,13 @@ struct MachineCounts {
     outs << "]" << std::endl;
   }
 };
+
+inline void BackwardMatrix::traceFrom (const ForwardMatrix& forward, InputIndex i, OutputIndex o, StateIndex s, size_t transIndex, TraceTerminator stopTrace) const {
+  if (stopTrace (i, o, s, transIndex)) return;
+  forward.traceBack (i, o, s, stopTrace);
+  const MachineTransition t = machine.transition ((int32_t) (machine.state[s].transOffset + transIndex));
+  traceForward (i + (t.inputEmpty() ? 0 : 1), o + (t.outputEmpty() ? 0 : 1), t.dest, stopTrace);
+}
 
 inline void BackwardMatrix::getCounts (const ForwardMatrix&, MachineCounts& counts) const {
   if (counts.count.empty()) counts.init (machine);

@@ -84,6 +84,7 @@ int main (int argc, char** argv) {
     bool doL = false, doV = false, doA = false, doC = false, doSample = false, useApi = false;
     string envMode;
     long long sampleSeed = 1;
+    int postTransTop = 0;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
       auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
@@ -106,6 +107,7 @@ int main (int argc, char** argv) {
       else if (f == "-C" || f == "--counts") doC = true;
       else if (f == "--envelope") envMode = next();      // full | path | <width>: print each pair's Envelope (t/src/testenv.cpp; no device needed)
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
+      else if (f == "--post-trans") postTransTop = atoi (next().c_str());      // the top of BackwardMatrix::postTransQueue and the trace from its first entry
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "--api") useApi = true;      // route the verbs through the api.h free functions (Machine, Params, SeqPair), pair by pair
       else if (f == "--gpus") hostGpuLimit() = atoi (next().c_str());      // lists of pairs use this many GPUs (default: every visible one)
@@ -169,7 +171,7 @@ int main (int argc, char** argv) {
     for (const auto& i: inSeqs) for (const auto& o: outSeqs) { SeqPair sp; sp.input = i; sp.output = o; data.seqPairs.push_back (sp); }
     if (data.seqPairs.empty() && inputEmpty && outputEmpty) data.seqPairs.push_back (SeqPair());   // boss.cpp:769-770
     if (data.seqPairs.empty()) throw runtime_error ("no sequence data given");
-    if (!(doL || doV || doA || doC || doT || doSample)) throw runtime_error ("nothing to do: give -L, -V, -A, -C or -T");
+    if (!(doL || doV || doA || doC || doT || doSample || postTransTop)) throw runtime_error ("nothing to do: give -L, -V, -A, -C or -T");
 
     if (doT) {   // boss.cpp:776-787
       if (constraints.empty() && machine.cons.empty()) throw runtime_error ("To fit parameters, please specify a constraints file and (for machines with input/output) a data file");
@@ -238,6 +240,37 @@ int main (int argc, char** argv) {
         cout << "}" << endl;
       } else
       counts.writeJson (cout);
+    }
+    if (postTransTop) {   // BackwardMatrix::postTransQueue (backward.cpp:52-56) and traceFrom (backward.cpp:98-108), per pair
+      cout << "[";
+      size_t k = 0;
+      cout.precision (17);
+      for (const auto& sp: data.seqPairs) {
+        cout << (k++ ? ",\n " : "") << "{";
+        if (eval.canTokenize (sp)) {
+          const ForwardMatrix f (eval, sp);
+          if (f.logLike() > ninf) {
+            const BackwardMatrix b (eval, sp);
+            BackwardMatrix::PostTransQueue q = b.postTransQueue (f);
+            cout << "\"postTransCount\":" << q.size() << ",\"postTrans\":[";
+            const BackwardMatrix::PostTrans first = q.top();
+            for (int n = 0; n < postTransTop && !q.empty(); ++n) {
+              const BackwardMatrix::PostTrans pt = q.top();
+              q.pop();
+              cout << (n ? "," : "") << "[" << pt.inPos << "," << pt.outPos << "," << (eval.state[pt.src].transOffset + pt.transIndex) << "," << pt.weight << "]";
+            }
+            const MachineTransition mt = eval.transition ((int32_t) (eval.state[first.src].transOffset + first.transIndex));
+            cout << "],\"traceFrom\":[";
+            size_t n = 0;
+            b.traceFrom (f, first.inPos - (mt.inputEmpty() ? 0 : 1), first.outPos - (mt.outputEmpty() ? 0 : 1), first.src, first.transIndex,
+                         [&] (long, long, StateIndex src, size_t ti) { cout << (n++ ? "," : "") << (eval.state[src].transOffset + ti); return false; });
+            cout << "]";
+          }
+        }
+        cout << "}";
+      }
+      cout << "]\n";
+      cout.precision (6);
     }
     if (doSample) {   // ForwardMatrix::samplePath (forward.cpp:17-19), pair k drawn with mt19937 (seed + k): [[transition ids], ...]
       cout << "[";

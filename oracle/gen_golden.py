@@ -304,8 +304,31 @@ def sample_case():
     print("aux_sample_paths             pairs=%d" % len(sym_pairs))
 
 
+def post_trans_case():
+    """BackwardMatrix::postTransQueue (backward.cpp:52-56) and traceFrom with a TraceTerminator (backward.cpp:98-108): the twelve
+    largest (cell, transition) posteriors of a pair and the transitions visited tracing from the first one's source cell."""
+    margs = machine_args(["preset:dnapsw"], peaked_dna())
+    mach = run(margs + ["--emit-machine"])
+    alpha = mach["inAlphabet"]
+    shapes = [(9, 11), (14, 12), (0, 3), (6, 6)]
+    sym_pairs = [([alpha[t - 1] for t in synth_tokens(112, k, 0, li, 4)], [alpha[t - 1] for t in synth_tokens(112, k, 1, lo, 4)])
+                 for k, (li, lo) in enumerate(shapes)]
+    sym_pairs[3] = (sym_pairs[3][0], sym_pairs[3][0])      # identical sequences: a sharply peaked posterior
+    f = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": a}, "output": {"name": "y%d" % k, "sequence": b}} for k, (a, b) in enumerate(sym_pairs)], f)
+    f.close()
+    res = run(margs + ["--pairs", f.name, "--do", "posttrans"])
+    os.unlink(f.name)
+    with open(os.path.join(OUT, "aux_post_trans.json"), "w") as fo:
+        json.dump({"note": "BackwardMatrix::postTransQueue / traceFrom of the reference: [destination inPos, outPos, global transition id, posterior]; traceFrom = ids in visit order",
+                   "machine": mach, "pairs": [dict(input=a, output=b, **r) for (a, b), r in zip(sym_pairs, res["pairs"])]}, fo, separators=(",", ":"))
+    print("aux_post_trans               pairs=%d" % len(sym_pairs))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sample":
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "posttrans":
+        post_trans_case()
+    elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sample":
         sample_case()
     elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "envelope":
         envelope_case()
@@ -314,3 +337,4 @@ if __name__ == "__main__":
     else:
         main()
         sample_case()
+        post_trans_case()

@@ -106,6 +106,37 @@ def test_cli_sample_paths_match_the_reference():
     assert got == [p["sample"] for p in g["pairs"]]
 
 
+@pytest.mark.gpu
+def test_cli_post_trans_queue_and_trace_from_match_the_reference():
+    """BackwardMatrix::postTransQueue (backward.cpp:52-56) and traceFrom with a TraceTerminator (backward.cpp:98-108) of the
+    host mirror, over the device's stored Forward and Backward matrices, against the reference's own output (refdrv): the
+    number of (cell, transition) posteriors, the largest ones, and -- where the first is not tied -- the transitions
+    visited tracing back and forward from it."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_post_trans.json")) as f:
+        g = json.load(f)
+    mf = _machine_file(g)
+    pf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+    json.dump([{"input": {"name": "x%d" % k, "sequence": p["input"]}, "output": {"name": "y%d" % k, "sequence": p["output"]}}
+               for k, p in enumerate(g["pairs"])], pf)
+    pf.close()
+    r = subprocess.run([_cli(), "--evaluated-machine", mf, "-D", pf.name, "--post-trans", "12"], capture_output=True, text=True, check=True)
+    got = json.loads(r.stdout)
+    assert len(got) == len(g["pairs"])
+    traced = 0
+    for mine, ref in zip(got, g["pairs"]):
+        assert mine["postTransCount"] == ref["postTransCount"]
+        want = {(e[0], e[1], e[2]): e[3] for e in ref["postTrans"]}
+        np.testing.assert_allclose([e[3] for e in mine["postTrans"]], [e[3] for e in ref["postTrans"]], rtol=1e-6)      # the weights, in order
+        floor = ref["postTrans"][-1][3] * (1 + 1e-6)
+        for e in mine["postTrans"]:
+            if e[3] > floor:      # (entries tied with the last one shown may be others of the same weight)
+                assert (e[0], e[1], e[2]) in want and abs(want[(e[0], e[1], e[2])] - e[3]) <= 1e-6 * e[3], e
+        if ref["postTrans"][0][3] > ref["postTrans"][1][3] * (1 + 1e-6):
+            assert mine["traceFrom"] == ref["traceFrom"]
+            traced += 1
+    assert traced >= 2
+
+
 def test_cli_envelopes_match_the_reference_goldens():
     """Makefile:450-462 test-env: Envelope::initFull / initPath / initPathArea of the host mirror against
     t/expect/*_env.json (CPU only: no device involved)."""
