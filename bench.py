@@ -280,8 +280,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the set-B, strong-scaling and configs 2-5 legs")
     ap.add_argument("--strong-pairs", type=int, default=10000, help="pairs IN TOTAL of the strong-scaling leg")
     ap.add_argument("--cfg3-pairs", type=int, default=100000)
-    ap.add_argument("--cfg4-pairs", type=int, default=148)
-    ap.add_argument("--cfg5-reads", type=int, default=65536)
+    ap.add_argument("--cfg4-pairs", type=int, default=1000)
+    ap.add_argument("--cfg5-reads", type=int, default=131072)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -456,6 +456,7 @@ def main():
             out["set_b"] = run_set_b(capi, P, args.len)
             if world == 1:
                 out["configs"] = run_configs(capi, args)
+                out["ingest"] = run_ingest()
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = max(8, threads)
@@ -608,6 +609,34 @@ def run_set_b(capi, P, L):
            "pairs_per_s": P / (ms / 1e3), "redo_pairs": f["redo"], "redo_frac": f["redo"] / P,
            "loglike_pair0": float(r["forward"][1][0]), "viterbi_pair0": float(r["viterbi"][1][0][0])}
     batch.close(); mach.close()
+    return out
+
+
+def run_ingest(n_pairs=100000, length=300):
+    """sequence files -> packed tokens on the host (boss_b200_ingest.h), timed by the host mirror's own
+    CLI on config 3's data (protein pairs as two FASTA files), to be read next to the GPU time of the same pairs."""
+    import tempfile
+    from machineboss_b200 import build
+    try:
+        cli = build.build_host()
+    except Exception as e:      # no host compiler on this box
+        return {"unavailable": str(e)[:200]}
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    x, _, y, _ = synth_batch(SEED + 3, 0, n_pairs, length, length, 20)
+    out = {"what": "%d protein pairs of %d aa: two FASTA files -> packed tokens, host only, one thread" % (n_pairs, length)}
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for toks, prefix in ((x, b"x"), (y, b"y")):
+            seqs = aa[toks - 1].reshape(n_pairs, length)
+            path = os.path.join(tmp, prefix.decode() + ".fa")
+            with open(path, "wb") as f:
+                for k in range(n_pairs):
+                    f.write(b">" + prefix + str(k).encode() + b"\n" + seqs[k].tobytes() + b"\n")
+            paths.append(path)
+        r = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", paths[0], paths[1], "--ingest-only"], capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"unavailable": r.stderr[-200:]}
+        out.update(json.loads(r.stdout))
     return out
 
 

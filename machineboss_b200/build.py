@@ -48,7 +48,7 @@ CLI = os.path.join(HERE, "boss_b200")
 def build_host(force: bool = False) -> str:
     """Compile the C++ host mirror's CLI (host/boss_b200_cli.cpp) against the shared library."""
     src = os.path.join(HERE, "host", "boss_b200_cli.cpp")
-    deps = [src, os.path.join(HERE, "host", "boss_b200.h"), os.path.join(HERE, "host", "boss_b200_fit.h"), os.path.join(HERE, "host", "mbjson.h"), LIB]
+    deps = [src, os.path.join(HERE, "host", "boss_b200.h"), os.path.join(HERE, "host", "boss_b200_fit.h"), os.path.join(HERE, "host", "boss_b200_ingest.h"), os.path.join(HERE, "host", "mbjson.h"), LIB]
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     build()

@@ -1028,7 +1028,7 @@ __global__ void __launch_bounds__(256) lane2_kernel (const __grid_constant__ L2P
             }
             case X_CTRL: {
               if (usePrev && (u.z & L3_COMMIT)) l2_commit();
-              if (usePrev && (u.z & L3_WAIT)) l2_wait (p.LA);
+              if (usePrev && (u.z & L3_WAIT)) { if (p.LA == 3) asm volatile ("cp.async.wait_group 3;" ::: "memory"); else l2_wait (p.LA); }
               if (u.z & L3_ORIGIN) {
 #pragma unroll
                 for (int q = 0; q < R; ++q) acc[q] = o == 0 ? ONE : ZERO;
@@ -1089,7 +1089,10 @@ struct LBuf {
 // while the max-plus sweep, which carries a pointer per chain, stays at one.
 static int lane_reads_per_lane (const mb_machine* m, const LHost* h, int64_t nWork, int op) {
   if (m->opt.has ("lane_r")) { const int r = m->opt.get ("lane_r", 1); return r >= 4 ? 4 : r >= 2 ? 2 : 1; }
-  if (h->l2.ok) return nWork >= (int64_t) h->numSMs * 4 * 128 ? 4 : nWork >= (int64_t) h->numSMs * 4 * 64 ? 2 : 1;      // the interpreter's work per record is shared by a lane's reads
+  // the windowed sweep: one read per lane.  More reads per lane share the interpreter's work per record but cost warps
+  // (shared memory), and the sweep lives on warps: measured on B200, PF00516, 65 536 ragged reads: 114 / 108 / 98 GCUPS
+  // at 1 / 2 / 4 reads per lane
+  if (h->l2.ok) return 1;
   if (op == L_MAX || nWork >= (int64_t) h->numSMs * 40 * 32) return 1;
   return nWork >= (int64_t) h->numSMs * 8 * 64 ? 2 : 1;
 }
@@ -1152,8 +1155,12 @@ static int lane2_launch_r (mb_machine* m, mb_batch* b, const std::vector<int64_t
     if (c * w > bestWarps) { bestWarps = c * w; W = w; ctasPerSM = c; }
   }
   if (!bestWarps) { set_error ("lane engine: the window does not fit in shared memory"); return 1; }
+  // few reads: narrower CTAs (and as many of them as fit) spread the tasks over the SMs
+  while (W > 1 && !wantW && nTasks < (int64_t) h->numSMs * W * ctasPerSM) {
+    W = (W + 1) / 2;
+    ctasPerSM = (int) std::min<size_t> (kSmem / (fixed + (size_t) W * perWarp), 32 / W);
+  }
   if (m->opt.has ("lane_warps")) ctasPerSM = std::max (1, std::min (ctasPerSM, m->opt.get ("lane_warps", 16) / W));
-  while (W > 1 && nTasks < (int64_t) h->numSMs * W * ctasPerSM) W = (W + 1) / 2;      // few reads: narrower CTAs spread them over the SMs
   const int grid = (int) std::max<int64_t> (1, std::min<int64_t> ((nTasks + W - 1) / W, (int64_t) ctasPerSM * h->numSMs));
   const size_t smem = fixed + (size_t) W * perWarp;
   MB_CUDA (cudaFuncSetAttribute (lane2_kernel<OP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

@@ -31,7 +31,10 @@
 #include <fstream>
 #include <iostream>
 
+#include <chrono>
+
 #include "boss_b200_fit.h"
+#include "boss_b200_ingest.h"
 
 using namespace MachineBoss;
 using namespace std;
@@ -85,6 +88,8 @@ int main (int argc, char** argv) {
     string envMode;
     long long sampleSeed = 1;
     int postTransTop = 0;
+    bool fastIngest = false, ingestOnly = false;
+    string pairedFastaIn, pairedFastaOut;
     for (int a = 1; a < argc; ++a) {
       const string f = argv[a];
       auto next = [&] () -> string { if (a + 1 >= argc) throw runtime_error ("missing value for " + f); return argv[++a]; };
@@ -109,6 +114,9 @@ int main (int argc, char** argv) {
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
       else if (f == "--post-trans") postTransTop = atoi (next().c_str());      // the top of BackwardMatrix::postTransQueue and the trace from its first entry
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
+      else if (f == "--fast-ingest") fastIngest = true;      // -D lists go straight to packed tokens (boss_b200_ingest.h); -L / -V only
+      else if (f == "--paired-fasta") { fastIngest = true; pairedFastaIn = next(); pairedFastaOut = next(); }      // record k of one file with record k of the other
+      else if (f == "--ingest-only") { fastIngest = true; ingestOnly = true; }      // time the ingest, touch no device
       else if (f == "--api") useApi = true;      // route the verbs through the api.h free functions (Machine, Params, SeqPair), pair by pair
       else if (f == "--gpus") hostGpuLimit() = atoi (next().c_str());      // lists of pairs use this many GPUs (default: every visible one)
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
@@ -163,6 +171,37 @@ int main (int argc, char** argv) {
       eval = evaluate (machine, any);
     }
 
+    if (fastIngest) {      // lists at scale: files -> packed tokens -> device, no SeqPair objects in between
+      const auto t0 = std::chrono::steady_clock::now();
+      PackedPairs pp;
+      size_t fileBytes = 0;
+      if (pairedFastaIn.size()) {
+        const string a = readTextFile (pairedFastaIn), b = readTextFile (pairedFastaOut);
+        fileBytes = a.size() + b.size();
+        pp = packedFromFasta (a, b, eval);
+      } else {
+        if (dataFiles.size() != 1) throw runtime_error ("--fast-ingest takes one -D file (or --paired-fasta)");
+        const string text = readTextFile (dataFiles[0]);
+        fileBytes = text.size();
+        pp = packedFromSeqPairListJson (text, eval);
+      }
+      const double secs = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
+      if (ingestOnly) {
+        cout << "{\"pairs\":" << pp.size() << ",\"residues\":" << pp.residues() << ",\"file_bytes\":" << fileBytes << ",\"seconds\":" << secs
+             << ",\"pairs_per_s\":" << (double) pp.size() / secs << ",\"MB_per_s\":" << (double) fileBytes / 1e6 / secs << "}" << endl;
+        return EXIT_SUCCESS;
+      }
+      if (!(doL || doV) || doA || doC || doT) throw runtime_error ("--fast-ingest serves -L and -V");
+      for (int pass = 0; pass < 2; ++pass) {
+        if (!(pass ? doV : doL)) continue;
+        const vector<double> sc = packedScores (eval, pp, pass == 1);
+        cout << "[";
+        for (size_t k = 0; k < pp.size(); ++k)
+          cout << (k ? ",\n " : "") << "[\"" << Json::escape (pp.xName[k]) << "\",\"" << Json::escape (pp.yName[k]) << "\"," << toInfinitySafeString (sc[k]) << "]";
+        cout << "]\n";
+      }
+      return EXIT_SUCCESS;
+    }
     SeqPairList data;
     for (const auto& df: dataFiles) { SeqPairList l = SeqPairList::fromFile (df); data.seqPairs.insert (data.seqPairs.end(), l.seqPairs.begin(), l.seqPairs.end()); }
     const bool inputEmpty = eval.inputTokenizer.tok2sym.size() == 1, outputEmpty = eval.outputTokenizer.tok2sym.size() == 1;

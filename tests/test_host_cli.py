@@ -173,3 +173,52 @@ def test_cli_pairs_with_alignments_get_the_path_envelope():
     got = np.array([v for row in json.loads(r.stdout) for v in row], dtype=np.float64)
     want = np.array([gnum(v) for v in case["counts"]])
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def _protein_files(n, length, tmp):
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    rng = np.random.default_rng(3)
+    xs = rng.integers(0, 20, size=(n, length))
+    ys = rng.integers(0, 20, size=(n, length - 3))
+    fa_in, fa_out, js = os.path.join(tmp, "in.fa"), os.path.join(tmp, "out.fa"), os.path.join(tmp, "list.json")
+    with open(fa_in, "w") as f:
+        for k in range(n):
+            f.write(">x%d some description\n%s\n" % (k, "".join(aa[c] for c in xs[k])))
+    with open(fa_out, "w") as f:
+        for k in range(n):
+            s = "".join(aa[c] for c in ys[k])
+            f.write(">y%d\n%s\n%s\n" % (k, s[:40], s[40:]))      # wrapped lines
+    with open(js, "w") as f:
+        json.dump([{"input": {"name": "x%d" % k, "sequence": [aa[c] for c in xs[k]]}, "meta": {"note": [1, {"a": 'b"c'}]},
+                    "output": {"sequence": [aa[c] for c in ys[k]], "name": "y%d" % k}} for k in range(n)], f)
+    return fa_in, fa_out, js
+
+
+def test_fast_ingest_reads_lists_and_fasta_without_a_device(tmp_path):
+    """boss_b200_ingest.h: a SeqPairList JSON and a pair of FASTA files go straight to packed tokens (no device needed for
+    --ingest-only): pair and residue counts, and the failures a Tokenizer would raise."""
+    cli = _cli()
+    fa_in, fa_out, js = _protein_files(50, 60, str(tmp_path))
+    for args in (["-D", js], ["--paired-fasta", fa_in, fa_out]):
+        r = subprocess.run([cli, "--preset", "protpsw"] + args + ["--ingest-only"], capture_output=True, text=True, check=True)
+        got = json.loads(r.stdout)
+        assert got["pairs"] == 50 and got["residues"] == 50 * (60 + 57), got
+    bad = os.path.join(str(tmp_path), "bad.fa")
+    open(bad, "w").write(">z\nACDZ\n")      # Z is not an amino acid of protpsw
+    r = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", bad, bad, "--ingest-only"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Can't tokenize symbol Z" in r.stderr
+    aligned = os.path.join(str(tmp_path), "aligned.json")
+    json.dump([{"input": {"name": "a"}, "output": {"name": "b"}, "alignment": [["A", "A"]]}], open(aligned, "w"))
+    r = subprocess.run([cli, "--preset", "protpsw", "-D", aligned, "--ingest-only"], capture_output=True, text=True)
+    assert r.returncode != 0 and "alignment" in r.stderr
+
+
+@pytest.mark.gpu
+def test_fast_ingest_scores_equal_the_general_reader(tmp_path):
+    """-L and -V through the packed path (--fast-ingest, --paired-fasta) print what the SeqPairList path prints."""
+    cli = _cli()
+    fa_in, fa_out, js = _protein_files(40, 50, str(tmp_path))
+    want = subprocess.run([cli, "--preset", "protpsw", "-D", js, "-L", "-V"], capture_output=True, text=True, check=True).stdout
+    fast = subprocess.run([cli, "--preset", "protpsw", "-D", js, "--fast-ingest", "-L", "-V"], capture_output=True, text=True, check=True).stdout
+    fasta = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", fa_in, fa_out, "-L", "-V"], capture_output=True, text=True, check=True).stdout
+    assert fast == want and fasta == want
