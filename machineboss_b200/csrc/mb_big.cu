@@ -37,6 +37,11 @@ struct BigGroup { int self, type, other, rank; int emitOff = -1, silIdx = -1, ta
 struct BigEngine {
   std::vector<BigGroup> groups;      // by (destination, kind, source, rank): the reference's candidate order
   std::vector<int> liveU, liveL;     // sources of insert groups; sources of delete / match groups
+  // Linear-domain normalisation, as in mb_jit.cu (Program::unitSlot): value'(d) = value(d) / sigma_d with sigma_d = w_u sigma_src(u)
+  // for the state's first silent group u makes that group a plain copy (prot2dna => dnapsw: 716 multiply-adds per cell become
+  // ~450); every other weight is scaled by sigma_src / sigma_self on the host, the result carries log sigma of the end state.
+  std::vector<int> unitGroup;        // per state: index into groups, or -1
+  double resLog = 0;
   int nEmit = 0, nSil = 0, threads = 128;
   std::string source;
   void* mod = nullptr;
@@ -88,6 +93,10 @@ static void big_plan (const mb_machine* m, BigEngine& B) {
   }
   B.liveU.clear(); B.liveL.clear();
   for (int s = 0; s < m->S; ++s) { if (isU[s]) B.liveU.push_back (s); if (isL[s]) B.liveL.push_back (s); }
+  B.unitGroup.assign ((size_t) m->S, -1);
+  if (!m->opt.get ("jit_no_norm", 0))
+    for (size_t gi = 0; gi < B.groups.size(); ++gi)
+      if (B.groups[gi].type == T_SILENT && B.unitGroup[B.groups[gi].self] < 0) B.unitGroup[B.groups[gi].self] = (int) gi;
   // pointer fields, packed greedily into 32-bit words (no field straddles a word)
   B.groupStart.assign ((size_t) m->S + 1, 0);
   for (auto& gr: B.groups) B.groupStart[gr.self + 1]++;
@@ -154,7 +163,9 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   size_t gi = 0;
   for (int d = 0; d < S; ++d) {
     bool first = true;
+    if (B.unitGroup[d] >= 0) { o << "  double n" << d << " = n" << B.groups[B.unitGroup[d]].other << ";\n"; first = false; }      // the unit group: a copy
     for (; gi < B.groups.size() && B.groups[gi].self == d; ++gi) {
+      if ((int) gi == B.unitGroup[d]) continue;
       const BigGroup& gr = B.groups[gi];
       std::ostringstream src, w;
       if (gr.type == T_INSERT) {
@@ -238,12 +249,24 @@ int big_update_weights (mb_machine* m) {
   std::vector<double> emitLog (emit.size(), -INFINITY), silLog (sil.size(), -INFINITY);
   bool ok = true;
   const double lim = 24.0 * 0.6931471805599453;
+  std::vector<double> ls ((size_t) m->S, 0.);      // log sigma per state; a silent group's source is an earlier state
+  for (int d = 0; d < m->S; ++d) {
+    if (B->unitGroup[d] < 0) continue;
+    const BigGroup& u = B->groups[B->unitGroup[d]];
+    const double w = m->lw[u.entries[0].second];
+    if (!std::isfinite (w)) { ok = false; continue; }      // a unit weight of 0 cannot be divided out: the wide engine's sweeps take the machine
+    ls[d] = w + ls[u.other];
+    if (std::fabs (ls[d]) > 100. * 0.6931471805599453) ok = false;
+  }
+  B->resLog = ls[m->S - 1];
   for (auto& gr: B->groups)
     for (auto& e: gr.entries) {
       const double lw = m->lw[e.second];
       if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
-      if (gr.type == T_SILENT) { sil[gr.silIdx] = std::exp (lw); silLog[gr.silIdx] = lw; }
-      else { emit[(size_t) gr.emitOff + e.first] = std::exp (lw); emitLog[(size_t) gr.emitOff + e.first] = lw; }
+      const double scaled = lw > -INFINITY ? lw + ls[gr.other] - ls[gr.self] : -INFINITY;      // the linear sweep's weight, in normalised units
+      if (std::isfinite (scaled) && std::fabs (scaled) > 2 * lim) ok = false;
+      if (gr.type == T_SILENT) { sil[gr.silIdx] = std::exp (scaled); silLog[gr.silIdx] = lw; }
+      else { emit[(size_t) gr.emitOff + e.first] = std::exp (scaled); emitLog[(size_t) gr.emitOff + e.first] = lw; }
     }
   B->linearOK = ok;
   MB_CUDA (cudaSetDevice (m->device));
@@ -306,6 +329,7 @@ struct MBBigArgsHost {      // must match struct MBBigArgs in the skeleton
   double* result; int32_t* flag;
   const double* emit;
   unsigned* bp; const int64_t* bpOff;
+  double resLog;
 };
 
 int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
@@ -337,6 +361,7 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dRes; A.flag = dFlag; A.emit = B.dEmit;
   A.bp = nullptr; A.bpOff = nullptr;
+  A.resLog = B.resLog;
   void* params[1] = { &A };
   if (timing_begin (b)) return 1;
   if (rt_launch (B.kForward, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params)) return 1;
@@ -447,6 +472,7 @@ int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   A.counter = dCounter; A.bnd = dBnd; A.bndStride = bndStride;
   A.result = dRes; A.flag = nullptr; A.emit = B.dEmitLog;
   A.bp = nullptr; A.bpOff = nullptr;
+  A.resLog = 0;
   void* params[1] = { &A };
   auto launch = [&] (const std::vector<int64_t>& work, const int64_t* dOrder) {
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> (maxGrid, ((int64_t) work.size() + warps - 1) / warps));

@@ -40,6 +40,7 @@ struct MBBigArgs {
   double* result; int32_t* flag;
   const double* emit;
   unsigned* bp; const int64_t* bpOff;      // MODE 1: back-pointer words of work item n at bp + bpOff[n]
+  double resLog;                           // linear sweep: log of the scale the end state carries (normalised weights)
 };
 
 __device__ __forceinline__ double mb_pow2 (int d) { return __hiloint2double ((1023 + d) << 20, 0); }
@@ -198,7 +199,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
             if (LIN) bout[(int64_t) r * MB_BROW + MB_NLL] = (double) ecur;
           }
           if (r == Lo && col == Li) {
-            if (LIN) A.result[k] = res > 0.0 ? log (res) + (double) ecur * 0.6931471805599453094 : __longlong_as_double (0xfff0000000000000LL);
+            if (LIN) A.result[k] = res > 0.0 ? log (res) + (double) ecur * 0.6931471805599453094 + A.resLog : __longlong_as_double (0xfff0000000000000LL);
             else A.result[k] = res;
           }
         }
