@@ -237,6 +237,12 @@ struct JitEngine {
   std::vector<char> silParamLinN;         // MBSilN { f[], b[], originF, originB, resLogF, resLogB }
   bool normOK = false;                    // every unit group's weight is usable: the normalised linear kernels may run
   std::string sourceV;
+  // split mode (strips as work items): the score module once more with MB_SPLIT 1, compiled when a call first needs it
+  std::string sourceS;
+  CUmodule modS = nullptr;
+  bool splitTried = false;
+  CUfunction kSplit[4] = { nullptr, nullptr, nullptr, nullptr };      // viterbi, forward_lin, backward_lin, viterbi_score
+  int blocksPerSMS[4] = { 1, 1, 1, 1 };
   // E-step: Forward states kept per cell (those with an emitting transition group coming in, plus the
   // start state); the others follow from them inside the cell through the silent groups
   std::vector<int> stored;
@@ -661,10 +667,32 @@ static int compile (mb_machine* m, JitEngine& J) {
   return 0;
 }
 
+// The split-mode module, on first use.
+static int ensure_split_module (mb_machine* m, JitEngine& J) {
+  if (J.modS) return 0;
+  if (J.splitTried) { set_error ("jit engine: the split-mode module could not be built"); return 1; }
+  J.splitTried = true;
+  std::vector<char> cubin;
+  if (nvrtc_compile (J.sourceS, ".split.cu", cubin, nullptr)) return 1;
+  if (!cu_ok (g_drv.ModuleLoadData (&J.modS, cubin.data()), "cuModuleLoadData")) return 1;
+  const char* names[4] = { "mb_k_viterbi", "mb_k_forward_lin", "mb_k_backward_lin", "mb_k_viterbi_score" };
+  const int qOf[4] = { 2, 5, 6, 9 };
+  for (int q = 0; q < 4; ++q) {
+    if (!cu_ok (g_drv.ModuleGetFunction (&J.kSplit[q], J.modS, names[q]), "cuModuleGetFunction")) return 1;
+    if (!cu_ok (g_drv.FuncSetAttribute (J.kSplit[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[qOf[q]]), "cuFuncSetAttribute")) return 1;
+    int nb = 0;
+    if (!cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, J.kSplit[q], J.threads, J.smemBytes[qOf[q]]), "occupancy")) return 1;
+    J.blocksPerSMS[q] = std::max (1, nb);
+  }
+  if (m->opt.get ("verbose", 0)) fprintf (stderr, "[mb_jit] split-mode module compiled\n");
+  return 0;
+}
+
 // Columns per lane for a score-only call over `pairs`: CV unless the narrower strips of C waste so much
 // less padding that they win.  Cost per cell relative to C (measured, 10 000 dnapsw pairs of 1 kb):
-// Viterbi 0.60, linear sweeps 0.87.
-static bool use_narrow (const mb_machine* m, const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, bool viterbi) {
+// Viterbi with back-pointers 0.60, linear sweeps 0.87; Viterbi scores only 0.85 (100 000 protpsw pairs of 300 aa: 17.0 ms in
+// 3 strips of 128 against 19.9 in 2 of 256, with back-pointers 27.9 against 24.0).
+static bool use_narrow (const mb_machine* m, const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, int kind /* 0 sums, 1 Viterbi + pointers, 2 Viterbi scores */) {
   if (!J.modV) return false;
   if (m->opt.has ("jit_narrow")) return m->opt.get ("jit_narrow", 0) != 0;
   double cellsN = 0, cellsW = 0;
@@ -673,7 +701,7 @@ static bool use_narrow (const mb_machine* m, const JitEngine& J, const mb_batch*
     cellsN += std::ceil ((Li + 1) / (32.0 * J.C)) * 32.0 * J.C * rows;
     cellsW += std::ceil ((Li + 1) / (32.0 * J.CV)) * 32.0 * J.CV * rows;
   }
-  return cellsN < (viterbi ? 0.60 : 0.87) * cellsW;
+  return cellsN < (kind == 1 ? 0.60 : kind == 2 ? 0.85 : 0.87) * cellsW;
 }
 
 // ---- the same run-time compilation plumbing for the other generated engine (mb_big.cu) ----
@@ -870,7 +898,8 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#define MB_MINBLOCKS_LIN " << (pass ? J.minBlocksLinV : J.minBlocksLin) << "\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
+  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#ifdef MB_SPLIT\n#define MB_MINBLOCKS_LIN " << std::min (2, pass ? J.minBlocksLinV : J.minBlocksLin) << "      // (the split-mode sums spill below 170 registers)\n#else\n#define MB_MINBLOCKS_LIN "
+    << (pass ? J.minBlocksLinV : J.minBlocksLin) << "\n#endif\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
@@ -909,6 +938,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   o << kJitSkeleton;
   (pass ? J.sourceV : J.source) = o.str();
   }
+  J.sourceS = "#define MB_SPLIT 1\n" + (J.sourceV.empty() ? J.source : J.sourceV);
 }
 
 // Diagnostic used by the CPU tests: the tables the score module's kernels read, as the host prepares them for
@@ -954,6 +984,11 @@ int jit_compile_check (const mb_machine* m, std::string* log) {
     if (nvrtc_compile (J.sourceV, ".viterbi.cu", cubin, &logV)) return 1;
     if (log) *log += "\n---- Viterbi module (MB_C = " + std::to_string (J.CV) + ") ----\n" + logV;
   }
+  if (m->opt.get ("jit_split", -1) > 0) {
+    std::string logS;
+    if (nvrtc_compile (J.sourceS, ".split.cu", cubin, &logS)) return 1;
+    if (log) *log += "\n---- split-mode module ----\n" + logS;
+  }
   return 0;
 }
 
@@ -993,6 +1028,7 @@ void jit_destroy (mb_machine* m) {
   JitEngine* J = (JitEngine*) m->jit;
   if (J->mod && g_drv.ModuleUnload) g_drv.ModuleUnload (J->mod);
   if (J->modV && g_drv.ModuleUnload) g_drv.ModuleUnload (J->modV);
+  if (J->modS && g_drv.ModuleUnload) g_drv.ModuleUnload (J->modS);
   if (J->dEmitF) cudaFree (J->dEmitF);
   if (J->dEmitB) cudaFree (J->dEmitB);
   if (J->dEmitFLin) cudaFree (J->dEmitFLin);
@@ -1075,7 +1111,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[slot]);
   // SPLIT mode: with fewer pairs than resident warps the strips of a pair become work items of their own, and the warps
   // that claim them run as a pipeline down the strips (see MBArgs::items in the skeleton)
-  const int W = 32 * (scoreKernel && !narrow && J.modV ? J.CV : J.C);
+  const int W = 32 * (scoreKernel && J.modV ? J.CV : J.C);      // (the split module has the score module's columns per lane)
   bool split = false;
   std::vector<int64_t> items, itemBnd;
   if (scoreKernel && m->opt.get ("jit_split", -1) != 0) {
@@ -1091,6 +1127,13 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
       }
       itemBnd.push_back (at);
     }
+  }
+  if (split) {
+    if (ensure_split_module (m, J)) return 1;
+    const int q = which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3;
+    narrow = false;
+    fn = J.kSplit[q];
+    grid = (int64_t) J.numSMs * J.blocksPerSMS[q];
   }
   const int64_t nWorkItems = split ? (int64_t) items.size() : (int64_t) order.size();
   grid = std::min<int64_t> (grid, (nWorkItems + warpsPerBlock - 1) / warpsPerBlock);
@@ -1153,7 +1196,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     if (!dFlag) return 1;
     CountArgs ca;
     ca.flag = dFlag;
-    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (m, J, b, order, false))) return 1;
+    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (m, J, b, order, 0))) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
     MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
     MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -1317,7 +1360,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
-  const bool narrow = use_narrow (m, J, b, full_order (b), true);
+  const bool narrow = use_narrow (m, J, b, full_order (b), trace ? 1 : 2);
   if (!trace) {      // scores only (boss -V): no back-pointers, no scratch beyond the strip boundaries
     double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
     if (!dRes) return 1;

@@ -46,6 +46,11 @@ struct MBArgs {
   const int64_t* items; const int64_t* itemBnd; int* prog;
 };
 
+// Split mode is compiled into a module of its own (MB_SPLIT 1, built the first time a call needs it): in the ordinary
+// modules `split` is a compile-time false and none of this costs registers or instructions.
+#ifndef MB_SPLIT
+#define MB_SPLIT 0
+#endif
 // rows [0, need) of the previous strip's boundary are complete and visible (split mode)
 __device__ __forceinline__ void mb_wait_rows (const int* prog, const int need) {
   while (*(volatile const int*) prog < need) { }
@@ -168,7 +173,7 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     if (lane == 0) w = atomicAdd (A.counter, 1ULL);
     w = __shfl_sync (MB_FULL, w, 0);
     if ((int64_t) w >= A.nWork) break;
-    const bool split = A.items != 0;
+    const bool split = MB_SPLIT && A.items != 0;
     const int64_t item = split ? A.items[w] : 0;
     const int64_t k = split ? (item >> 16) : A.order[w];
     const int64_t x0 = A.xOff[k], y0 = A.yOff[k];
@@ -460,7 +465,7 @@ __device__ __forceinline__ void mb_run_lin (const SIL& P, const MBArgs& A) {
     if (lane == 0) w = atomicAdd (A.counter, 1ULL);
     w = __shfl_sync (MB_FULL, w, 0);
     if ((int64_t) w >= A.nWork) break;
-    const bool split = A.items != 0;
+    const bool split = MB_SPLIT && A.items != 0;
     const int64_t item = split ? A.items[w] : 0;
     const int64_t k = split ? (item >> 16) : A.order[w];
     const int64_t x0 = A.xOff[k], y0 = A.yOff[k];

@@ -682,7 +682,7 @@ static void lane2_build (const mb_machine* m, LHost* h) {
 
 // The program executed for ONE read on the host, chunk by chunk and row by row as the kernel does it (the same blobs,
 // the same region rows, every row tagged with what it holds so that a stale read is an error): what the CPU test checks
-// against the oracle.  op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
+// against known answers.  op: L_SUM (scaled linear domain, frame per cell), L_MAX, L_LSE.  Returns 0, or 1 with the error set.
 int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut) {
   LHost* h = lh (m);
   if (!h || !h->l2.ok) { set_error (std::string ("lane2: no windowed program for this machine") + (h ? ": " + h->l2.why : std::string())); return 1; }

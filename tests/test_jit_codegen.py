@@ -16,3 +16,20 @@ def test_jit_kernels_compile(name):
         return
     assert "mb_k_forward" in log and "mb_k_viterbi" in log and "mb_k_backward" in log
     assert "0 bytes spill stores" in log
+
+
+def test_split_mode_module_compiles():
+    """The score module with MB_SPLIT 1 (strips of a pair as work items; built on the device only when a call with few,
+    long pairs first needs it) compiles without spills; the ordinary modules carry no trace of it."""
+    from machineboss_b200 import capi
+    fm = FlatMachine.from_json(load_golden("dnapsw_small")["machine"])
+    capi.set_option("jit_split", 1)
+    try:
+        log = capi.jit_compile_check(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
+    finally:
+        capi.set_option("jit_split", None)
+    assert "split-mode module" in log
+    tail = log[log.index("split-mode module"):]
+    assert "mb_k_viterbi" in tail and "mb_k_forward_lin" in tail
+    spills = [l for l in tail.splitlines() if "spill stores" in l]
+    assert len(spills) == 4 and all(" 0 bytes spill stores" in l for l in spills), spills
