@@ -200,6 +200,16 @@ int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t n
                      const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
                      const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, uint32_t* backPointers);
 
+/* The column engine's reading of a generator without input whose states repeat with a period (a profile HMM: column =
+ * period of the machine, row = read position), built and EXECUTED ON THE HOST for one read (no device needed: the CPU
+ * tests check the analysis, the per-column weight tables and the prefix / suffix programs against known answers).
+ * op: 0 log-sum-exp, 1 max-plus.  info[12] = { usable, period, first periodic state, columns, prefix states, suffix states,
+ * carried states, accumulators, transition groups per cell, weight slots per column, left-going states, states read
+ * from the row above }.  log (may be NULL): the NVRTC log of the generated strip kernel, compiled for sm_100a. */
+int mb_col_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                    const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap);
+
 /* ---- measurement hooks (not part of the reference surface) ----
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch
  * (CUDA events on the launching stream), and how many kernels that was. */

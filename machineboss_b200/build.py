@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmachineboss_b200.so")
-SOURCES = ["mb_api.cu", "mb_generic.cu", "mb_jit.cu", "mb_wide.cu", "mb_lane.cu", "mb_big.cu", "mb_group.cu"]
+SOURCES = ["mb_api.cu", "mb_generic.cu", "mb_jit.cu", "mb_wide.cu", "mb_lane.cu", "mb_big.cu", "mb_group.cu", "mb_col.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -21,7 +21,7 @@ _lib = None
 SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
-           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_viterbi_paths_start", "mb_batch_wait", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables", "mb_lane_emulate",
+           "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_viterbi_paths_start", "mb_batch_wait", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables", "mb_lane_emulate", "mb_col_emulate",
            "mb_shard_pairs", "mb_group_create", "mb_group_info", "mb_group_destroy", "mb_group_machine_create", "mb_group_machine_update_weights",
            "mb_group_machine_set_option", "mb_group_machine_info", "mb_group_machine_destroy", "mb_group_batch_create", "mb_group_batch_set_envelopes",
            "mb_group_batch_shard", "mb_group_batch_destroy", "mb_group_forward", "mb_group_backward", "mb_group_viterbi", "mb_group_viterbi_paths",
@@ -68,6 +68,7 @@ def lib():
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
         L.mb_jit_host_tables.argtypes = [I32, I32, I32, I64, P, P, P, P, P, I32, P, I64, ctypes.POINTER(I64)]
         L.mb_lane_emulate.argtypes = [I32, I32, I32, I64, P, P, P, P, P, P, I64, I32, ctypes.POINTER(D), P, P]
+        L.mb_col_emulate.argtypes = [I32, I32, I32, I64, P, P, P, P, P, P, I64, I32, ctypes.POINTER(D), P, ctypes.c_char_p, I64]
         L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         L.mb_shard_pairs.argtypes = [I64, P, P, I32, P]
@@ -156,6 +157,20 @@ def lane_emulate(n_states, n_in, n_out, src, dst, tin, tout, log_weight, y, op: 
     _check(lib().mb_lane_emulate(int(n_states), int(n_in), int(n_out), int(lw.shape[0]), *[_ptr(a) for a in arrs], _ptr(lw),
                                  _ptr(y), len(y), int(op), ctypes.byref(res), info.ctypes.data, bp.ctypes.data if back_pointers else None))
     return (res.value, info, bp) if back_pointers else (res.value, info)
+
+
+def col_emulate(n_states, n_in, n_out, src, dst, tin, tout, log_weight, y, op: int, compile_log: bool = False):
+    """The column engine's program for a periodic generator run for one read on the host; returns (result, info[12][, NVRTC log]).
+    info[0] == 0: the machine has no such structure (result is meaningless)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
+    lw = np.ascontiguousarray(log_weight, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    res = ctypes.c_double(0)
+    info = np.zeros(12, dtype=np.int32)
+    buf = ctypes.create_string_buffer(1 << 16) if compile_log else None
+    _check(lib().mb_col_emulate(int(n_states), int(n_in), int(n_out), int(lw.shape[0]), *[_ptr(a) for a in arrs], _ptr(lw),
+                                _ptr(y), len(y), int(op), ctypes.byref(res), info.ctypes.data, buf, len(buf) if compile_log else 0))
+    return (res.value, info, buf.value.decode()) if compile_log else (res.value, info)
 
 
 def _ptr(a):

@@ -27,6 +27,7 @@ static const char* const kOptionNames[] = {
   "jit_unroll",                                               // unroll factor of the steady-state step loop (1 - 4)
   "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
   "lane_r", "lane_warps", "no_lane", "lane_old", "lane_bs", "lane_la", "lane_wn", "lane_host_only", "lane_warps_per_cta", "wide_g", "wide_w", "no_big", "big_warps", "big_debug",
+  "no_col", "col_sil_regs", "col_threads", "col_minblocks", "col_r", "col_bnd_budget_mb",      // column engine (mb_col.cu)
 };
 
 Options thread_options() { return g_options; }
@@ -746,6 +747,29 @@ int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t n
   if (!rc && inf[0] && result) rc = lane2_emulate (&m, outTokens, outLen, op, result, backPointers ? &bp : nullptr);
   if (!rc && backPointers) for (size_t q = 0; q < bp.size(); ++q) backPointers[q] = bp[q];
   lane_destroy (&m);
+  return rc;
+}
+
+int mb_col_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
+                    const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
+                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap) {
+  mb_machine m;
+  m.opt = g_options;
+  m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
+  m.src.assign (src, src + nTrans); m.dst.assign (dst, dst + nTrans);
+  m.in.assign (inTok, inTok + nTrans); m.out.assign (outTok, outTok + nTrans);
+  m.lw.assign (logWeight, logWeight + nTrans);
+  int rc = col_prepare (&m, true);
+  int32_t inf[12];
+  col_info (&m, inf);
+  if (info) for (int q = 0; q < 12; ++q) info[q] = inf[q];
+  if (!rc && inf[0] && result) rc = col_emulate (&m, outTokens, outLen, op, result);
+  if (!rc && inf[0] && log && logCap > 0) {      // compile the generated strip kernel too (NVRTC, no device)
+    std::string l;
+    rc = col_compile_check (&m, &l);
+    strncpy (log, l.c_str(), (size_t) logCap - 1); log[logCap - 1] = 0;
+  }
+  col_destroy (&m);
   return rc;
 }
 

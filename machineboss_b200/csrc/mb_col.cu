@@ -1,0 +1,633 @@
+// mb_col.cu -- the column engine: generators without input whose states repeat with a period (profile HMMs and their
+// compositions with an error model: SURVEY.md section 8 config 5; the reference builds them in src/hmmer.cpp and
+// runs them through the same ForwardMatrix / ViterbiMatrix, forward.cpp:5-56, viterbi.cpp:5-47), swept as a
+// two-dimensional recurrence -- column = period of the machine, row = read position -- by a machine-specialised strip
+// kernel (mb_col_skeleton.h).  Reached through the lane engine (mb_lane.cu), which keeps the reads the linear sweep
+// flags, the traceback, and every machine this file declines.
+//
+// The analysis (col_analyse).  States [0, a0) are the PREFIX, [a0, a0 + K P) the K PERIODS of P states, the rest the
+// SUFFIX.  Accepted when every transition is one of
+//     period k -> period k (silent: to a later state of the period; or consuming a token)      SILENT / UP   group
+//     period k -> period k+1 (silent, or consuming a token)                                    LEFT / DIAG   group
+//     prefix -> prefix, suffix -> suffix                                                       the small programs below
+//     prefix -> period k  (any k: "hub" sources such as a profile's begin state)               the prefix state is CARRIED
+//     period k -> suffix  (any k: "hub" destinations such as a profile's end state)            an ACCUMULATOR collects it
+//     prefix -> suffix                                                                         carried all the way
+// A carried state is a state of the cell whose only group is a copy from the column to the left; an accumulator
+// is one with that copy plus what its column sends to the suffix state.  The period P is the smallest shift under
+// which the (number of transitions, number that consume a token) profile of the middle half of the states repeats;
+// the phase a0 is the one that classifies with the fewest groups.  The weights of a group differ from column to
+// column (-inf where a column lacks the transition): one table row per column, nSlots = silent groups + nOut per
+// token-consuming group.
+//
+// Three kernels per chunk of reads: col_prefix_kernel (a thread per read: the prefix states over the rows, written as
+// the first strip's left boundary), the strip kernel, col_suffix_kernel (a thread per read: the suffix states from
+// the last column's accumulators; the end state at the last row is the result).  The two small kernels are
+// table-driven and work in the log domain with an exact log-sum-exp (a few dozen states: no time to speak of).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "mb_internal.h"
+#include "mb_col_skeleton.h"
+
+namespace mb {
+
+enum { CG_SILENT = 0, CG_LEFT = 1, CG_UP = 2, CG_DIAG = 3 };
+enum { CE_SILENT = 0, CE_EMIT = 1, CE_EXT_CUR = 2, CE_EXT_PREV = 3 };
+
+struct ColGroup { int type, dst, src, slot; bool emit; };      // cell-state indices; slot < 0: a copy (weight one)
+struct ColEntry { int dst, src, tok, kind; int64_t trans; };   // trans < 0: weight one
+
+struct ColProg {
+  bool ok = false;
+  std::string why;
+  int P = 0, a0 = 0, K = 0, nPre = 0, nSuf = 0, nC = 0, nA = 0, nCell = 0;
+  int nSlots = 0, nSilSlots = 0, nLU = 0, nLL = 0, nLD = 0, nStrips = 0, nOut = 0;
+  std::vector<int> carried;                      // prefix state behind carried state c
+  std::vector<std::pair<int, int>> acc;          // (suffix-local state, consumes a token)
+  std::vector<ColGroup> groups;                  // in order of destination
+  std::vector<int> upIdx, leftIdx, diagIdx;      // per cell state: index in U[] / the left-going set / Lprev[], or -1
+  std::vector<int64_t> slotTrans;                // [K][nSlots] -> transition, or -1
+  std::vector<ColEntry> pre, suf;
+};
+
+struct ColEngine {
+  ColProg prog;
+  std::string source;
+  int threads = 256, minBlocks = 2, R = 1;
+  bool silInRegs = false;
+  bool linearOK = false;
+  void* mod = nullptr; void* kSum = nullptr; void* kMax = nullptr;
+  int blocksPerSMSum = 1, blocksPerSMMax = 1, numSMs = 148;
+  size_t smemBytes = 0;
+  std::vector<double> tabLin, tabLog, preW, sufW;
+  double* dTabLin = nullptr; double* dTabLog = nullptr;
+  int32_t* dPre = nullptr; double* dPreW = nullptr; int32_t* dSuf = nullptr; double* dSufW = nullptr;
+  int32_t* dCarriedSlot = nullptr;      // [nC] left-going slot of carried c | [nC] prefix state
+};
+
+static ColEngine* ce (const mb_machine* m) { return static_cast<ColEngine*> (m->col); }
+
+// ---------------------------------------------------------------------------------------------
+// analysis
+// ---------------------------------------------------------------------------------------------
+static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& out, bool build) {
+  const int S = m->S, end = a0 + K * P;
+  typedef std::tuple<int, int, int, int> Key;      // (source kind/state, relation, destination, emit)
+  std::map<Key, int> keyGroup;
+  std::set<int> carriedSet;
+  std::set<std::pair<int, int>> accSet;
+  struct Raw { int64_t t; int kind; int src, dst; int col; bool emit; };      // kind 0 per->per dk 0, 1 per->per dk 1, 2 pre->per, 3 per->suf
+  std::vector<Raw> raws;
+  for (int64_t t = 0; t < m->T; ++t) {
+    const int s = m->src[t], d = m->dst[t];
+    const bool emit = m->out[t] != 0;
+    if (m->in[t] != 0) return false;
+    if (s == 0 && d == 0 && !emit) continue;      // the start state's silent self-loop contributes nothing (machine.cpp:759)
+    const int ws = s < a0 ? 0 : s >= end ? 2 : 1, wd = d < a0 ? 0 : d >= end ? 2 : 1;
+    if (ws == 1 && wd == 1) {
+      const int ks = (s - a0) / P, kd = (d - a0) / P, js = (s - a0) % P, jd = (d - a0) % P;
+      if (kd - ks != 0 && kd - ks != 1) return false;
+      if (!emit && kd == ks && jd <= js) return false;
+      raws.push_back (Raw { t, kd - ks, js, jd, kd, emit });
+    } else if (ws == 0 && wd == 1) { carriedSet.insert (s); raws.push_back (Raw { t, 2, s, (d - a0) % P, (d - a0) / P, emit }); }
+    else if (ws == 1 && wd == 2) { accSet.insert (std::make_pair (d - end, emit ? 1 : 0)); raws.push_back (Raw { t, 3, (s - a0) % P, d - end, (s - a0) / P, emit }); }
+    else if (ws == 0 && wd == 0) { if (!emit && d <= s) return false; }
+    else if (ws == 2 && wd == 2) { if (!emit && d <= s) return false; }
+    else if (ws == 0 && wd == 2) carriedSet.insert (s);
+    else return false;
+  }
+  for (auto& r: raws) keyGroup[Key (r.kind == 2 ? -1 - r.src : r.src, r.kind, r.dst, r.emit ? 1 : 0)] = 0;
+  out.P = P; out.a0 = a0; out.K = K; out.nPre = a0; out.nSuf = S - end;
+  out.nC = (int) carriedSet.size(); out.nA = (int) accSet.size();
+  out.nCell = out.nC + P + out.nA;
+  if (!build) { out.groups.resize (keyGroup.size()); return true; }
+
+  out.nOut = m->nOut;
+  out.carried.assign (carriedSet.begin(), carriedSet.end());
+  out.acc.assign (accSet.begin(), accSet.end());
+  std::map<int, int> carriedIdx;
+  for (int c = 0; c < out.nC; ++c) carriedIdx[out.carried[c]] = c;
+  std::map<std::pair<int, int>, int> accIdx;
+  for (int a = 0; a < out.nA; ++a) accIdx[out.acc[a]] = a;
+  auto cellOfPeriod = [&] (int j) { return out.nC + j; };
+  // groups, with their cell-state indices
+  std::vector<ColGroup> gs;
+  for (auto& kv: keyGroup) {
+    const int srcKey = std::get<0> (kv.first), kind = std::get<1> (kv.first), dst = std::get<2> (kv.first);
+    const bool emit = std::get<3> (kv.first) != 0;
+    ColGroup g;
+    g.emit = emit; g.slot = 0;
+    if (kind == 0) { g.type = emit ? CG_UP : CG_SILENT; g.src = cellOfPeriod (srcKey); g.dst = cellOfPeriod (dst); }
+    else if (kind == 1) { g.type = emit ? CG_DIAG : CG_LEFT; g.src = cellOfPeriod (srcKey); g.dst = cellOfPeriod (dst); }
+    else if (kind == 2) { g.type = emit ? CG_UP : CG_SILENT; g.src = carriedIdx[-1 - srcKey]; g.dst = cellOfPeriod (dst); }
+    else { g.type = emit ? CG_UP : CG_SILENT; g.src = cellOfPeriod (srcKey); g.dst = out.nC + P + accIdx[std::make_pair (dst, emit ? 1 : 0)]; }
+    gs.push_back (g);
+  }
+  for (int c = 0; c < out.nC; ++c) gs.push_back (ColGroup { CG_LEFT, c, c, -1, false });
+  for (int a = 0; a < out.nA; ++a) gs.push_back (ColGroup { CG_LEFT, out.nC + P + a, out.nC + P + a, -1, false });
+  std::stable_sort (gs.begin(), gs.end(), [] (const ColGroup& p, const ColGroup& q) { return p.dst != q.dst ? p.dst < q.dst : (p.slot < 0) > (q.slot < 0); });
+  int slot = 0;
+  for (auto& g: gs) if (g.slot >= 0 && !g.emit) g.slot = slot++;
+  out.nSilSlots = slot;
+  for (auto& g: gs) if (g.slot >= 0 && g.emit) { g.slot = slot; slot += m->nOut; }
+  out.nSlots = std::max (slot, 1);
+  out.groups = gs;
+  out.upIdx.assign ((size_t) out.nCell, -1); out.leftIdx.assign ((size_t) out.nCell, -1); out.diagIdx.assign ((size_t) out.nCell, -1);
+  std::vector<char> isU ((size_t) out.nCell, 0), isL ((size_t) out.nCell, 0), isD ((size_t) out.nCell, 0);
+  for (auto& g: gs) { if (g.type == CG_UP) isU[g.src] = 1; if (g.type == CG_LEFT || g.type == CG_DIAG) isL[g.src] = 1; if (g.type == CG_DIAG) isD[g.src] = 1; }
+  for (int c = 0; c < out.nC; ++c) isL[c] = 1;      // carried all the way to the suffix kernel
+  out.nLU = out.nLL = out.nLD = 0;
+  for (int s = 0; s < out.nCell; ++s) { if (isU[s]) out.upIdx[s] = out.nLU++; if (isL[s]) out.leftIdx[s] = out.nLL++; if (isD[s]) out.diagIdx[s] = out.nLD++; }
+  out.nStrips = (K + 31) / 32;
+  // per column: which transition fills which slot
+  std::map<std::tuple<int, int, int, int>, int> groupOf;      // (type, src, dst, emit) -> index in gs
+  for (size_t n = 0; n < gs.size(); ++n) if (gs[n].slot >= 0) groupOf[std::make_tuple (gs[n].type, gs[n].src, gs[n].dst, gs[n].emit ? 1 : 0)] = (int) n;
+  out.slotTrans.assign ((size_t) K * out.nSlots, -1);
+  for (auto& r: raws) {
+    int type, src, dst;
+    if (r.kind == 0) { type = r.emit ? CG_UP : CG_SILENT; src = cellOfPeriod (r.src); dst = cellOfPeriod (r.dst); }
+    else if (r.kind == 1) { type = r.emit ? CG_DIAG : CG_LEFT; src = cellOfPeriod (r.src); dst = cellOfPeriod (r.dst); }
+    else if (r.kind == 2) { type = r.emit ? CG_UP : CG_SILENT; src = carriedIdx[r.src]; dst = cellOfPeriod (r.dst); }
+    else { type = r.emit ? CG_UP : CG_SILENT; src = cellOfPeriod (r.src); dst = out.nC + P + accIdx[std::make_pair (r.dst, r.emit ? 1 : 0)]; }
+    const ColGroup& g = gs[groupOf[std::make_tuple (type, src, dst, r.emit ? 1 : 0)]];
+    int64_t& cell = out.slotTrans[(size_t) r.col * out.nSlots + g.slot + (r.emit ? m->out[r.t] - 1 : 0)];
+    if (cell >= 0) { out.why = "parallel transitions with the same label"; return false; }
+    cell = r.t;
+  }
+  // the prefix and suffix programs, by destination (a silent source is an earlier state, so it is final when read)
+  for (int64_t t = 0; t < m->T; ++t) {
+    const int s = m->src[t], d = m->dst[t];
+    const bool emit = m->out[t] != 0;
+    if (s == 0 && d == 0 && !emit) continue;
+    if (s < a0 && d < a0) out.pre.push_back (ColEntry { d, s, m->out[t], emit ? CE_EMIT : CE_SILENT, t });
+    else if (s >= end && d >= end) out.suf.push_back (ColEntry { d - end, s - end, m->out[t], emit ? CE_EMIT : CE_SILENT, t });
+    else if (s < a0 && d >= end) out.suf.push_back (ColEntry { d - end, out.leftIdx[carriedIdx[s]], m->out[t], emit ? CE_EXT_PREV : CE_EXT_CUR, t });
+  }
+  for (int a = 0; a < out.nA; ++a) out.suf.push_back (ColEntry { out.acc[a].first, out.leftIdx[out.nC + P + a], 0, CE_EXT_CUR, -1 });
+  auto byDst = [] (const ColEntry& p, const ColEntry& q) { return p.dst < q.dst; };
+  std::stable_sort (out.pre.begin(), out.pre.end(), byDst);
+  std::stable_sort (out.suf.begin(), out.suf.end(), byDst);
+  return true;
+}
+
+static void col_analyse (const mb_machine* m, ColProg& best) {
+  best = ColProg();
+  const int S = m->S;
+  if (m->nIn != 0) { best.why = "the machine reads an input sequence"; return; }
+  if (S < 200) { best.why = "fewer than 200 states"; return; }
+  std::vector<std::pair<int, int>> sig ((size_t) S, std::make_pair (0, 0));
+  for (int64_t t = 0; t < m->T; ++t) { ++sig[m->src[t]].first; if (m->out[t]) ++sig[m->src[t]].second; }
+  const int lo = S / 4, hi = 3 * S / 4;
+  int P = 0;
+  for (int p = 1; p <= 128 && !P; ++p) {
+    bool same = true;
+    for (int s = lo; s < hi && same; ++s) same = sig[s] == sig[s + p];
+    if (same) P = p;
+  }
+  if (!P) { best.why = "no period of up to 128 states in the transition profile"; return; }
+  double bestScore = 1e300;
+  int bestA0 = -1, bestK = 0;
+  for (int phase = 0; phase < P; ++phase) {
+    int a0 = lo - (lo % P) + phase;
+    while (a0 - P >= 1) a0 -= P;
+    int K = (S - 1 - a0) / P;
+    ColProg trial;
+    bool ok = false;
+    for (int tries = 0; tries < 8 && K >= 32; ++tries) {      // irregular periods at either end go to the prefix / suffix
+      if (col_classify (m, a0, P, K, trial, false)) { ok = true; break; }
+      if (tries % 2 == 0) --K; else { a0 += P; --K; }
+    }
+    if (!ok) continue;
+    const double score = (double) trial.groups.size() + 4. * (trial.nC + trial.nA) + trial.nPre + trial.nSuf;
+    if (score < bestScore) { bestScore = score; bestA0 = a0; bestK = K; }
+  }
+  if (bestA0 < 0) { best.why = "period " + std::to_string (P) + ": no phase classifies (transitions that skip a period, or run backwards)"; return; }
+  if (!col_classify (m, bestA0, P, bestK, best, true)) { if (best.why.empty()) best.why = "classification failed"; return; }
+  if (best.nLL < 1 || best.nLL > 40) { best.why = "left-going states: " + std::to_string (best.nLL); return; }
+  if (best.nLU > 40) { best.why = "too many states consumed from the row above"; return; }
+  if (best.nPre > 64 || best.nSuf > 64) { best.why = "prefix / suffix of more than 64 states"; return; }
+  if ((size_t) best.nSlots * 32 * 8 > 160 * 1024) { best.why = "a strip's weight table exceeds 160 KB"; return; }
+  if (best.groups.size() > 600) { best.why = "more than 600 transition groups per cell"; return; }
+  if (m->nOut > 250) { best.why = "alphabet too large"; return; }
+  best.ok = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// code generation
+// ---------------------------------------------------------------------------------------------
+static void col_generate (const mb_machine* m, ColEngine& E) {
+  const ColProg& p = E.prog;
+  E.silInRegs = p.nSilSlots <= m->opt.get ("col_sil_regs", 40);
+  E.threads = std::max (32, std::min (1024, m->opt.get ("col_threads", 256) / 32 * 32));
+  E.minBlocks = std::max (1, std::min (8, m->opt.get ("col_minblocks", p.nCell <= 12 ? 2 : 1)));
+  E.R = std::max (1, std::min (16, m->opt.get ("col_r", 1)));
+  std::ostringstream o;
+  o << "// generated by machineboss_b200 (mb_col.cu): period " << p.P << ", " << p.K << " columns from state " << p.a0 << ", " << p.nC << " carried, " << p.nA << " accumulators\n";
+  o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
+  o << "#define MB_NLL " << p.nLL << "\n#define MB_NLU " << p.nLU << "\n#define MB_NLD " << p.nLD << "\n#define MB_NSLOTS " << p.nSlots << "\n";
+  o << "#define MB_COL_THREADS " << E.threads << "\n#define MB_COL_MINBLOCKS " << E.minBlocks << "\n";
+  o << "#define MB_COL_DECLW";
+  if (E.silInRegs) for (int q = 0; q < p.nSilSlots; ++q) o << " const double w" << q << " = W[" << q << " * 32];";
+  o << "\n";
+  auto weight = [&] (const ColGroup& g) {
+    std::ostringstream w;
+    if (g.emit) w << "W[(" << g.slot << " + tokb) * 32]";
+    else if (E.silInRegs) w << "w" << g.slot;
+    else w << "W[" << g.slot << " * 32]";
+    return w.str();
+  };
+  auto source = [&] (const ColGroup& g) {
+    std::ostringstream s;
+    if (g.type == CG_SILENT) s << "n" << g.src;
+    else if (g.type == CG_LEFT) s << "Lin[" << p.leftIdx[g.src] << "]";
+    else if (g.type == CG_UP) s << "U[" << p.upIdx[g.src] << "]";
+    else s << "Lprev[" << p.diagIdx[g.src] << "]";
+    return s.str();
+  };
+  for (int lin = 1; lin >= 0; --lin) {
+    o << "#define MB_COL_CELL_" << (lin ? "LIN" : "MAX") << " \\\n";
+    size_t gi = 0;
+    for (int d = 0; d < p.nCell; ++d) {
+      bool first = true;
+      o << "  double n" << d;
+      std::ostringstream rest;
+      for (; gi < p.groups.size() && p.groups[gi].dst == d; ++gi) {
+        const ColGroup& g = p.groups[gi];
+        if (g.slot < 0) { o << " = " << source (g) << ";"; first = false; continue; }      // the copy comes first
+        if (lin) {
+          if (first) rest << " n" << d << " = " << source (g) << " * " << weight (g) << ";";
+          else rest << " n" << d << " = fma (" << source (g) << ", " << weight (g) << ", n" << d << ");";
+        } else {
+          if (first) rest << " n" << d << " = " << source (g) << " + " << weight (g) << ";";
+          else rest << " { const double c = " << source (g) << " + " << weight (g) << "; if (n" << d << " < c) n" << d << " = c; }";
+        }
+        if (first) { o << ";"; first = false; }
+      }
+      if (first) o << " = ZERO;";
+      o << rest.str() << " \\\n";
+    }
+    for (int s = 0; s < p.nCell; ++s) if (p.upIdx[s] >= 0) o << "  U[" << p.upIdx[s] << "] = n" << s << "; \\\n";
+    for (int s = 0; s < p.nCell; ++s) if (p.leftIdx[s] >= 0) o << "  Lown[" << p.leftIdx[s] << "] = n" << s << "; \\\n";
+    o << "\n";
+  }
+  o << "#define MB_COL_KEEPDIAG";
+  for (int s = 0; s < p.nCell; ++s) if (p.diagIdx[s] >= 0) o << " Lprev[" << p.diagIdx[s] << "] = Lin[" << p.leftIdx[s] << "];";
+  o << "\n";
+  o << kColSkeleton;
+  E.source = o.str();
+}
+
+// ---------------------------------------------------------------------------------------------
+// the prefix and suffix programs on the device (a thread per read, log domain)
+// ---------------------------------------------------------------------------------------------
+#define COL_MAXSIDE 64
+#define COL_MAXLL 40
+struct ColSideArgs {
+  const uint8_t* y; const int64_t* yOff; const int64_t* order; int64_t nWork;
+  double* bnd; const int64_t* bndOff;
+  const int32_t* ent; const double* w; int32_t nEnt;      // entries: dst, src, tok, kind
+  int32_t nStates, nLL, nC;
+  const int32_t* carried;      // [nC] left-going slot | [nC] prefix state
+  double* result;
+};
+
+__device__ __forceinline__ double col_ninf() { return __longlong_as_double (0xfff0000000000000LL); }
+__device__ __forceinline__ double col_lse (double a, double b) {
+  const double mx = fmax (a, b), mn = fmin (a, b);
+  if (!(mn > col_ninf())) return mx;
+  return mx + log1p (exp (mn - mx));
+}
+
+template<bool SUM>
+__global__ void __launch_bounds__(128) col_prefix_kernel (ColSideArgs A) {
+  const int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.nWork) return;
+  const int64_t k = A.order[n];
+  const uint8_t* y = A.y + A.yOff[k];
+  const int Lo = (int) (A.yOff[k + 1] - A.yOff[k]);
+  double* bnd = A.bnd + A.bndOff[n];
+  double cur[COL_MAXSIDE], prev[COL_MAXSIDE];
+  for (int s = 0; s < A.nStates; ++s) prev[s] = col_ninf();
+  const int brow = A.nLL + 1;
+  for (int o = 0; o <= Lo; ++o) {
+    for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
+    if (o == 0) cur[0] = 0.;
+    const int tok = o ? y[o - 1] : -1;
+    for (int e = 0; e < A.nEnt; ++e) {
+      const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
+      double v;
+      if (kind == CE_SILENT) v = cur[src] + A.w[e];
+      else if (etok == tok) v = prev[src] + A.w[e];
+      else continue;
+      cur[dst] = SUM ? col_lse (cur[dst], v) : fmax (cur[dst], v);
+    }
+    double* row = bnd + (int64_t) o * brow;
+    if (SUM) {      // linear values under a power-of-two frame
+      double mx = col_ninf();
+      for (int c = 0; c < A.nC; ++c) mx = fmax (mx, cur[A.carried[A.nC + c]]);
+      const int fr = mx > col_ninf() ? (int) floor (mx * 1.4426950408889634) : 0;
+      for (int j = 0; j < A.nLL; ++j) row[j] = 0.;
+      for (int c = 0; c < A.nC; ++c) { const double v = cur[A.carried[A.nC + c]]; row[A.carried[c]] = v > col_ninf() ? exp (v - (double) fr * 0.6931471805599453094) : 0.; }
+      row[A.nLL] = (double) fr;
+    } else {
+      for (int j = 0; j < A.nLL; ++j) row[j] = col_ninf();
+      for (int c = 0; c < A.nC; ++c) row[A.carried[c]] = cur[A.carried[A.nC + c]];
+      row[A.nLL] = 0.;
+    }
+    for (int s = 0; s < A.nStates; ++s) prev[s] = cur[s];
+  }
+}
+
+template<bool SUM>
+__global__ void __launch_bounds__(128) col_suffix_kernel (ColSideArgs A) {
+  const int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.nWork) return;
+  const int64_t k = A.order[n];
+  const uint8_t* y = A.y + A.yOff[k];
+  const int Lo = (int) (A.yOff[k + 1] - A.yOff[k]);
+  const double* bnd = A.bnd + A.bndOff[n];
+  double cur[COL_MAXSIDE], prev[COL_MAXSIDE], X[COL_MAXLL], Xprev[COL_MAXLL];
+  for (int s = 0; s < A.nStates; ++s) prev[s] = col_ninf();
+  for (int j = 0; j < A.nLL; ++j) Xprev[j] = col_ninf();
+  const int brow = A.nLL + 1;
+  for (int o = 0; o <= Lo; ++o) {
+    const double* row = bnd + (int64_t) o * brow;
+    const double fr = SUM ? row[A.nLL] * 0.6931471805599453094 : 0.;
+    for (int j = 0; j < A.nLL; ++j) { const double v = row[j]; X[j] = SUM ? (v > 0. ? log (v) + fr : col_ninf()) : v; }
+    for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
+    const int tok = o ? y[o - 1] : -1;
+    for (int e = 0; e < A.nEnt; ++e) {
+      const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
+      double v;
+      if (kind == CE_SILENT) v = cur[src] + A.w[e];
+      else if (kind == CE_EXT_CUR) v = X[src] + A.w[e];
+      else if (etok != tok) continue;
+      else v = (kind == CE_EMIT ? prev[src] : Xprev[src]) + A.w[e];
+      cur[dst] = SUM ? col_lse (cur[dst], v) : fmax (cur[dst], v);
+    }
+    for (int s = 0; s < A.nStates; ++s) prev[s] = cur[s];
+    for (int j = 0; j < A.nLL; ++j) Xprev[j] = X[j];
+  }
+  A.result[k] = prev[A.nStates - 1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights, preparation
+// ---------------------------------------------------------------------------------------------
+static void col_fill_weights (const mb_machine* m, ColEngine& E) {
+  const ColProg& p = E.prog;
+  E.tabLin.assign ((size_t) p.nStrips * p.nSlots * 32, 0.);
+  E.tabLog.assign ((size_t) p.nStrips * p.nSlots * 32, -INFINITY);
+  bool ok = true;
+  const double lim = 40. * 0.6931471805599453;
+  for (int k = 0; k < p.K; ++k)
+    for (int q = 0; q < p.nSlots; ++q) {
+      const int64_t t = p.slotTrans[(size_t) k * p.nSlots + q];
+      if (t < 0) continue;
+      const double lw = m->lw[t];
+      if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
+      const size_t at = ((size_t) (k / 32) * p.nSlots + q) * 32 + (k & 31);
+      E.tabLog[at] = lw;
+      E.tabLin[at] = std::exp (lw);
+    }
+  E.preW.assign (std::max<size_t> (p.pre.size(), 1), 0.);
+  E.sufW.assign (std::max<size_t> (p.suf.size(), 1), 0.);
+  for (size_t e = 0; e < p.pre.size(); ++e) E.preW[e] = p.pre[e].trans >= 0 ? m->lw[p.pre[e].trans] : 0.;
+  for (size_t e = 0; e < p.suf.size(); ++e) E.sufW[e] = p.suf[e].trans >= 0 ? m->lw[p.suf[e].trans] : 0.;
+  for (double w: E.preW) if (std::isnan (w) || w == INFINITY) ok = false;
+  for (double w: E.sufW) if (std::isnan (w) || w == INFINITY) ok = false;
+  E.linearOK = ok;
+}
+
+int col_update_weights (mb_machine* m) {
+  ColEngine* E = ce (m);
+  if (!E) return 0;
+  col_fill_weights (m, *E);
+  if (!E->dTabLin) return 0;      // host only
+  MB_CUDA (cudaSetDevice (m->device));
+  MB_CUDA (cudaMemcpy (E->dTabLin, E->tabLin.data(), E->tabLin.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (E->dTabLog, E->tabLog.data(), E->tabLog.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (E->dPreW, E->preW.data(), E->preW.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (E->dSufW, E->sufW.data(), E->sufW.size() * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void col_destroy (mb_machine* m) {
+  ColEngine* E = ce (m);
+  if (!E) return;
+  if (E->mod) rt_unload (E->mod);
+  for (void* p: { (void*) E->dTabLin, (void*) E->dTabLog, (void*) E->dPre, (void*) E->dPreW, (void*) E->dSuf, (void*) E->dSufW, (void*) E->dCarriedSlot }) if (p) cudaFree (p);
+  delete E;
+  m->col = nullptr;
+}
+
+// Analysis, code generation and (unless hostOnly) compilation + upload.  A machine without the structure is not an
+// error: m->col stays null and the lane engine's own sweep runs.
+int col_prepare (mb_machine* m, bool hostOnly) {
+  if (m->opt.get ("no_col", 0)) return 0;
+  ColEngine* E = new ColEngine;
+  col_analyse (m, E->prog);
+  if (m->opt.get ("verbose", 0)) {
+    const ColProg& p = E->prog;
+    if (p.ok) fprintf (stderr, "column engine: period %d, %d columns from state %d (prefix %d, suffix %d states), %d carried, %d accumulators, %zu groups, %d weight slots (%d silent), %d up, %d left-going, %d diagonal\n",
+                       p.P, p.K, p.a0, p.nPre, p.nSuf, p.nC, p.nA, p.groups.size(), p.nSlots, p.nSilSlots, p.nLU, p.nLL, p.nLD);
+    else fprintf (stderr, "column engine: not for this machine (%s)\n", p.why.c_str());
+  }
+  if (!E->prog.ok) { delete E; return 0; }
+  m->col = E;
+  col_generate (m, *E);
+  col_fill_weights (m, *E);
+  if (hostOnly) return 0;
+  const ColProg& p = E->prog;
+  std::vector<char> cubin;
+  if (rt_compile (E->source, ".col.cu", cubin, nullptr)) return 1;
+  MB_CUDA (cudaSetDevice (m->device));
+  if (rt_load (cubin, &E->mod) || rt_function (E->mod, "mb_k_col_sum", &E->kSum) || rt_function (E->mod, "mb_k_col_max", &E->kMax)) return 1;
+  MB_CUDA (cudaDeviceGetAttribute (&E->numSMs, cudaDevAttrMultiProcessorCount, m->device));
+  E->smemBytes = (size_t) (p.nSlots * 32 + (E->threads / 32) * 16 * p.nLL) * 8;
+  if (rt_prepare (E->kSum, E->threads, E->smemBytes, &E->blocksPerSMSum) || rt_prepare (E->kMax, E->threads, E->smemBytes, &E->blocksPerSMMax)) return 1;
+  if (E->blocksPerSMSum < 1 || E->blocksPerSMMax < 1) { set_error ("column engine: a kernel does not fit on an SM"); return 1; }
+  MB_CUDA (cudaMalloc (&E->dTabLin, E->tabLin.size() * 8));
+  MB_CUDA (cudaMalloc (&E->dTabLog, E->tabLog.size() * 8));
+  std::vector<int32_t> pre, suf, car;
+  for (auto& e: p.pre) { pre.push_back (e.dst); pre.push_back (e.src); pre.push_back (e.tok); pre.push_back (e.kind); }
+  for (auto& e: p.suf) { suf.push_back (e.dst); suf.push_back (e.src); suf.push_back (e.tok); suf.push_back (e.kind); }
+  for (int c = 0; c < p.nC; ++c) car.push_back (p.leftIdx[c]);
+  for (int c = 0; c < p.nC; ++c) car.push_back (p.carried[c]);
+  MB_CUDA (cudaMalloc (&E->dPre, std::max<size_t> (pre.size(), 1) * 4));
+  MB_CUDA (cudaMalloc (&E->dSuf, std::max<size_t> (suf.size(), 1) * 4));
+  MB_CUDA (cudaMalloc (&E->dCarriedSlot, std::max<size_t> (car.size(), 1) * 4));
+  MB_CUDA (cudaMalloc (&E->dPreW, E->preW.size() * 8));
+  MB_CUDA (cudaMalloc (&E->dSufW, E->sufW.size() * 8));
+  if (!pre.empty()) MB_CUDA (cudaMemcpy (E->dPre, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice));
+  if (!suf.empty()) MB_CUDA (cudaMemcpy (E->dSuf, suf.data(), suf.size() * 4, cudaMemcpyHostToDevice));
+  if (!car.empty()) MB_CUDA (cudaMemcpy (E->dCarriedSlot, car.data(), car.size() * 4, cudaMemcpyHostToDevice));
+  if (m->opt.get ("verbose", 0))
+    fprintf (stderr, "column engine: %d threads per CTA, %zu B smem, %d / %d CTAs per SM (sums / max), silent weights in %s\n", E->threads, E->smemBytes, E->blocksPerSMSum, E->blocksPerSMMax, E->silInRegs ? "registers" : "shared memory");
+  return col_update_weights (m);
+}
+
+int col_compile_check (const mb_machine* m, std::string* log) {
+  ColEngine E;
+  col_analyse (m, E.prog);
+  if (!E.prog.ok) { set_error ("machine not eligible for the column engine: " + E.prog.why); return 1; }
+  col_generate (m, E);
+  std::vector<char> cubin;
+  return rt_compile (E.source, ".col.cu", cubin, log);
+}
+
+bool col_usable (const mb_machine* m, bool sums) {
+  const ColEngine* E = ce (m);
+  return E && E->mod && (!sums || E->linearOK) && !m->opt.get ("no_col", 0);
+}
+
+int col_info (const mb_machine* m, int32_t* info) {
+  const ColEngine* E = ce (m);
+  for (int q = 0; q < 12; ++q) info[q] = 0;
+  if (!E) return 0;
+  const ColProg& p = E->prog;
+  const int v[12] = { 1, p.P, p.a0, p.K, p.nPre, p.nSuf, p.nC, p.nA, (int) p.groups.size(), p.nSlots, p.nLL, p.nLU };
+  for (int q = 0; q < 12; ++q) info[q] = v[q];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch: chunks of reads whose boundary buffers fit the budget; three kernels per chunk
+// ---------------------------------------------------------------------------------------------
+struct MBColArgsHost {      // must match struct MBColArgs in the skeleton
+  const uint8_t* y; const int64_t* yOff;
+  const int64_t* order; int64_t nWork; unsigned long long* counter;
+  double* bnd; const int64_t* bndOff;
+  const double* tab;
+  int32_t* flag;
+  int nStrips, K, R, pad;
+};
+
+// order: reads, longest first.  sums: Forward (flags set for the reads whose result must not be trusted); else Viterbi scores.
+int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, bool sums, double* dResult, int32_t* dFlag, int64_t* launches) {
+  ColEngine& E = *ce (m);
+  const ColProg& p = E.prog;
+  const int brow = p.nLL + 1;
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
+  const double budget = std::min (0.5 * (double) freeB, (double) m->opt.get ("col_bnd_budget_mb", 4096) * 1048576.);
+  const int warps = E.threads / 32;
+  for (size_t c0 = 0; c0 < order.size();) {
+    std::vector<int64_t> off;
+    double doubles = 0;
+    size_t c1 = c0;
+    while (c1 < order.size()) {
+      const int64_t k = order[c1];
+      const double need = (double) (b->yOff[k + 1] - b->yOff[k] + 1) * brow;
+      if (c1 > c0 && (doubles + need) * 8 > budget) break;
+      off.push_back ((int64_t) doubles);
+      doubles += need;
+      ++c1;
+    }
+    const int64_t nWork = (int64_t) (c1 - c0);
+    int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, (size_t) nWork * 8);
+    int64_t* dOff = (int64_t*) ws_reserve (b, WS_ITEMBND, (size_t) nWork * 8);
+    double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) doubles * 8);
+    unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+    if (!dOrder || !dOff || !dBnd || !dCounter) return 1;
+    b->wsOrderHoldsFull = false;
+    MB_CUDA (cudaMemcpyAsync (dOrder, order.data() + c0, (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOff, off.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
+    ColSideArgs S;
+    S.y = b->dY; S.yOff = b->dYOff; S.order = dOrder; S.nWork = nWork; S.bnd = dBnd; S.bndOff = dOff;
+    S.ent = E.dPre; S.w = E.dPreW; S.nEnt = (int32_t) p.pre.size(); S.nStates = p.nPre; S.nLL = p.nLL; S.nC = p.nC; S.carried = E.dCarriedSlot; S.result = dResult;
+    const unsigned sideGrid = (unsigned) ((nWork + 127) / 128);
+    if (sums) col_prefix_kernel<true><<<sideGrid, 128, 0, b->stream>>> (S); else col_prefix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
+    MB_CUDA (cudaGetLastError());
+    MBColArgsHost A;
+    A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
+    A.bnd = dBnd; A.bndOff = dOff; A.tab = sums ? E.dTabLin : E.dTabLog; A.flag = dFlag;
+    A.nStrips = p.nStrips; A.K = p.K; A.R = E.R; A.pad = 0;
+    const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
+    const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * (sums ? E.blocksPerSMSum : E.blocksPerSMMax), groups));
+    void* params[1] = { &A };
+    if (rt_launch (sums ? E.kSum : E.kMax, (unsigned) grid, (unsigned) E.threads, E.smemBytes, b->stream, params)) return 1;
+    S.ent = E.dSuf; S.w = E.dSufW; S.nEnt = (int32_t) p.suf.size(); S.nStates = p.nSuf;
+    if (sums) col_suffix_kernel<true><<<sideGrid, 128, 0, b->stream>>> (S); else col_suffix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
+    MB_CUDA (cudaGetLastError());
+    if (launches) *launches += 3;
+    if (m->opt.get ("verbose", 0))
+      fprintf (stderr, "column engine: %lld reads, grid %lld x %d threads, %d read(s) per warp and strip, boundary rows %.1f MB\n", (long long) nWork, (long long) grid, E.threads, E.R, doubles * 8 / 1e6);
+    c0 = c1;
+    if (c0 < order.size()) MB_CUDA (cudaStreamSynchronize (b->stream));      // the next chunk reuses the workspace
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the column program executed on the host for one read (diagnostic: pins the analysis and the tables without a device)
+// op 0: log-sum-exp (exact), 1: max
+// ---------------------------------------------------------------------------------------------
+int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result) {
+  const ColEngine* E = ce (m);
+  if (!E) { set_error ("column engine: no program for this machine"); return 1; }
+  const ColProg& p = E->prog;
+  const double NINF = -INFINITY;
+  auto comb = [&] (double a, double v) {
+    if (op == 1) return std::max (a, v);
+    const double mx = std::max (a, v), mn = std::min (a, v);
+    return mn > NINF ? mx + std::log1p (std::exp (mn - mx)) : mx;
+  };
+  auto tabw = [&] (int k, int slot) { return E->tabLog[((size_t) (k / 32) * p.nSlots + slot) * 32 + (k & 31)]; };
+  std::vector<double> preCur ((size_t) std::max (p.nPre, 1), NINF), prePrev = preCur, sufCur ((size_t) std::max (p.nSuf, 1), NINF), sufPrev = sufCur;
+  std::vector<double> cur ((size_t) p.K * p.nCell, NINF), prev = cur;
+  std::vector<double> bCur ((size_t) p.nCell, NINF), bPrev = bCur, xPrev ((size_t) p.nCell, NINF);      // the boundary column (column -1) at this row and the row above
+  for (int64_t o = 0; o <= Lo; ++o) {
+    const int tok = o ? y[o - 1] : -1;
+    std::fill (preCur.begin(), preCur.end(), NINF);
+    if (o == 0) preCur[0] = 0.;
+    for (size_t e = 0; e < p.pre.size(); ++e) {
+      const ColEntry& en = p.pre[e];
+      if (en.kind == CE_SILENT) preCur[en.dst] = comb (preCur[en.dst], preCur[en.src] + E->preW[e]);
+      else if (en.tok == tok) preCur[en.dst] = comb (preCur[en.dst], prePrev[en.src] + E->preW[e]);
+    }
+    std::fill (bCur.begin(), bCur.end(), NINF);
+    for (int c = 0; c < p.nC; ++c) bCur[c] = preCur[p.carried[c]];
+    for (int k = 0; k < p.K; ++k) {
+      double* n = &cur[(size_t) k * p.nCell];
+      const double* left = k ? &cur[(size_t) (k - 1) * p.nCell] : bCur.data();
+      const double* diag = k ? &prev[(size_t) (k - 1) * p.nCell] : bPrev.data();
+      const double* up = &prev[(size_t) k * p.nCell];
+      for (int s = 0; s < p.nCell; ++s) n[s] = NINF;
+      for (auto& g: p.groups) {
+        const double src = g.type == CG_SILENT ? n[g.src] : g.type == CG_LEFT ? left[g.src] : g.type == CG_UP ? up[g.src] : diag[g.src];
+        double w = 0.;
+        if (g.slot >= 0) { if (g.emit) { if (tok < 1) continue; w = tabw (k, g.slot + tok - 1); } else w = tabw (k, g.slot); }
+        n[g.dst] = comb (n[g.dst], src + w);
+      }
+    }
+    const double* X = &cur[(size_t) (p.K - 1) * p.nCell];
+    std::fill (sufCur.begin(), sufCur.end(), NINF);
+    auto ext = [&] (const double* cell, int leftSlot) { for (int s = 0; s < p.nCell; ++s) if (p.leftIdx[s] == leftSlot) return cell[s]; return NINF; };
+    for (size_t e = 0; e < p.suf.size(); ++e) {
+      const ColEntry& en = p.suf[e];
+      double v;
+      if (en.kind == CE_SILENT) v = sufCur[en.src] + E->sufW[e];
+      else if (en.kind == CE_EXT_CUR) v = ext (X, en.src) + E->sufW[e];
+      else if (en.tok != tok) continue;
+      else v = (en.kind == CE_EMIT ? sufPrev[en.src] : ext (xPrev.data(), en.src)) + E->sufW[e];
+      sufCur[en.dst] = comb (sufCur[en.dst], v);
+    }
+    for (int s = 0; s < p.nCell; ++s) xPrev[s] = X[s];
+    prev.swap (cur); bPrev = bCur; prePrev = preCur; sufPrev = sufCur;
+  }
+  *result = sufPrev[p.nSuf - 1];
+  return 0;
+}
+
+}  // namespace mb

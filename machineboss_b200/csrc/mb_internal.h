@@ -109,6 +109,8 @@ struct mb_machine {
   // big engine (mb_big.cu): generated straight-line Forward sweep for mid-size machines, reached through the wide engine
   void* big = nullptr;
   bool bigTried = false;
+  // column engine (mb_col.cu): periodic generators swept as column = period, row = read position; reached through the lane engine
+  void* col = nullptr;
 };
 
 struct mb_batch {
@@ -185,6 +187,17 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 // the windowed program of the lane engine, executed for one read on the host (diagnostic; op 0 sum, 1 max, 2 log-sum-exp)
 int lane2_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<uint32_t>* bpOut);
 int lane2_info (const mb_machine* m, int32_t* info);      // { usable, window states, ring slots, hub sources, hub destinations, live states, records, back-pointer bytes }
+
+// ---- column engine (mb_col.cu): generators without input whose states repeat with a period (profile HMMs), swept as
+// a two-dimensional recurrence by a generated strip kernel; the lane engine calls it and keeps what it declines ----
+int col_prepare (mb_machine* m, bool hostOnly);      // 0 also when the machine has no such structure (m->col stays null)
+void col_destroy (mb_machine* m);
+int col_update_weights (mb_machine* m);
+bool col_usable (const mb_machine* m, bool sums);
+int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, bool sums, double* dResult, int32_t* dFlag, int64_t* launches);
+int col_compile_check (const mb_machine* m, std::string* log);
+int col_info (const mb_machine* m, int32_t* info);      // { usable, period, first state, columns, prefix, suffix, carried, accumulators, groups, weight slots, left-going, up }
+int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result);      // op 0 log-sum-exp, 1 max
 
 // ---- big engine (mb_big.cu): machine-specialised Forward sweep for mid-size machines (a thread per cell, the cell as
 // straight-line code); full two-dimensional matrices only; flagged pairs go back to the wide engine's log-domain sweep ----

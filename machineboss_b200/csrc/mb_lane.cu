@@ -330,6 +330,7 @@ static void lane_fill_weights (const mb_machine* m, LHost* h) {
 
 void lane_destroy (mb_machine* m) {
   LHost* h = lh (m);
+  col_destroy (m);
   if (!h) return;
   for (void* p: { (void*) h->dRecLin, (void*) h->dRecLog, (void*) h->dEmLin, (void*) h->dEmLog, (void*) h->dEmIdx, (void*) h->l2.dBlobLin, (void*) h->l2.dBlobLog }) if (p) cudaFree (p);
   delete h;
@@ -359,7 +360,7 @@ int lane_update_weights (mb_machine* m) {
   if (!h) return 0;
   lane_fill_weights (m, h);
   if (h->l2.ok) lane2_fill_weights (m, h);
-  return lane_upload (m, h, false) || lane2_upload (m, h, false);
+  return lane_upload (m, h, false) || lane2_upload (m, h, false) || col_update_weights (m);
 }
 
 // The transition program: destinations in index order; per destination the emitting terms (union
@@ -436,8 +437,9 @@ int lane_prepare (mb_machine* m) {
   lane_fill_weights (m, h);
   lane2_build (m, h);
   if (h->l2.ok) lane2_fill_weights (m, h);
-  if (m->opt.get ("lane_host_only", 0)) return 0;      // (diagnostic: build the programs without touching a device)
+  if (m->opt.get ("lane_host_only", 0)) return col_prepare (m, true);      // (diagnostic: build the programs without touching a device)
   if (lane_upload (m, h, true) || lane2_upload (m, h, true)) return 1;
+  if (col_prepare (m, false)) return 1;      // periodic machines (profile HMMs): the column engine takes the sweeps it can
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   if (m->opt.get ("verbose", 0))
     fprintf (stderr, "lane engine: S=%d records=%lld (emitting rows %zu x %d tokens), bp %d bytes\n", S, (long long) h->nRec, h->emPerm.size() / std::max (nOut, 1), nOut, h->bpBytes);
@@ -1224,7 +1226,23 @@ int lane_forward (mb_machine* m, mb_batch* b, double* loglike) {
   if (timing_begin (b)) return 1;
   int64_t launches = 1;
   const int R = lane_reads_per_lane (m, h, b->nPairs, L_SUM);
-  if (h->linearOk) {
+  if (col_usable (m, true)) {
+    // the column engine's linear sweep; reads it flags, or that come out without any path, are decided by the log-domain sweep here
+    launches = 0;
+    if (col_launch (m, b, order, true, dRes.as<double>(), dFlag.as<int32_t>(), &launches)) return 1;
+    std::vector<int32_t> flag ((size_t) b->nPairs);
+    std::vector<double> res ((size_t) b->nPairs);
+    MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag.p, flag.size() * 4, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaMemcpyAsync (res.data(), dRes.p, res.size() * 8, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    std::vector<int64_t> redo;
+    for (int64_t k = 0; k < b->nPairs; ++k) if (flag[k] || !(res[k] > -INFINITY)) redo.push_back (k);
+    if (!redo.empty()) {
+      if (lane_launch<L_LSE> (m, b, lane_reads_per_lane (m, h, (int64_t) redo.size(), L_LSE), lane_order (b, &redo), dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
+      ++launches;
+    }
+    b->lastRedo = (int64_t) redo.size();
+  } else if (h->linearOk) {
     if (lane_launch<L_SUM> (m, b, R, order, dRes.as<double>(), dFlag.as<int32_t>(), nullptr, nullptr)) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
     MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag.p, flag.size() * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -1257,8 +1275,10 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   if (dRes.alloc ((size_t) b->nPairs * 8)) return 1;
   if (!trace) {
     if (timing_begin (b)) return 1;
-    if (lane_launch<L_MAX> (m, b, lane_reads_per_lane (m, h, b->nPairs, L_MAX), order, dRes.as<double>(), nullptr, nullptr, nullptr)) return 1;
-    if (timing_end (b, 1)) return 1;
+    int64_t launches = 1;
+    if (col_usable (m, false)) { launches = 0; if (col_launch (m, b, order, false, dRes.as<double>(), nullptr, &launches)) return 1; }
+    else if (lane_launch<L_MAX> (m, b, lane_reads_per_lane (m, h, b->nPairs, L_MAX), order, dRes.as<double>(), nullptr, nullptr, nullptr)) return 1;
+    if (timing_end (b, launches)) return 1;
     MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
     return 0;
   }

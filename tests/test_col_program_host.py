@@ -1,0 +1,56 @@
+"""CPU test of the column engine (mb_col.cu): the period analysis of a generator without input, the per-column weight
+tables and the prefix / suffix programs are EXECUTED ON THE HOST for one read (column = period of the machine, row =
+read position, carried prefix states, accumulators for the suffix) and compared with the oracle -- Forward as the exact
+sum, Viterbi bit for bit -- and the generated strip kernel is compiled for sm_100a.  No device involved."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import LSE_EXACT, FlatMachine, Oracle, load_golden, synth_tokens
+
+
+def _generator(name):
+    fm = FlatMachine.from_json(load_golden(name)["machine"])
+    if fm.n_in != 0:
+        keep = fm.tin == 0
+        fm = FlatMachine(fm.n_states, 0, fm.n_out, fm.src[keep], fm.dst[keep], fm.tin[keep], fm.tout[keep], fm.lw[keep], [], fm.out_alphabet)
+    return fm
+
+
+@pytest.mark.parametrize("name,lens", [("hmmer_pf00516", [0, 1, 7, 60]), ("hmmer_pf00516_protpsw", [0, 12])])
+def test_column_program_on_the_host(name, lens):
+    from machineboss_b200 import capi
+    fm = _generator(name)
+    args = (fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw)
+    orc = Oracle(fm)
+    x = np.zeros(0, np.uint8)
+    for k, lo in enumerate(lens):
+        y = synth_tokens(31, k, 1, lo, fm.n_out)
+        f, info = capi.col_emulate(*args, y, 0)
+        assert info[0] == 1, "no column program for %s" % name
+        want = orc.forward(x, y, mode=LSE_EXACT)
+        assert (f == want) if math.isinf(want) else abs(f - want) <= 1e-10 * max(1.0, abs(want)), (name, lo, f, want)
+        v, _ = capi.col_emulate(*args, y, 1)
+        want_v, _ = orc.viterbi(x, y)
+        assert v == want_v, (name, lo, v, want_v)
+    # the structure found: 5 states per profile node (Mx, M, D, Ix, I), times the error model's states in the composition
+    assert info[1] == (5 if name == "hmmer_pf00516" else 25) and info[3] >= 480 and info[6] >= 1 and info[7] >= 1
+    assert info[1] * info[3] + info[4] + info[5] == fm.n_states
+
+
+def test_column_kernel_compiles():
+    from machineboss_b200 import capi
+    fm = _generator("hmmer_pf00516")
+    _, info, log = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0, compile_log=True)
+    assert info[0] == 1 and "mb_k_col_sum" in log and "mb_k_col_max" in log
+    spills = [l for l in log.splitlines() if "spill stores" in l]
+    assert len(spills) == 2 and all(" 0 bytes spill stores" in l for l in spills), log
+
+
+@pytest.mark.parametrize("name", ["unitindel", "counter_xxx", "dnapsw_small"])
+def test_machines_without_a_period_are_declined(name):
+    from machineboss_b200 import capi
+    fm = _generator(name)
+    _, info = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0)
+    assert info[0] == 0
