@@ -51,6 +51,7 @@ struct ColProg {
   std::string why;
   int P = 0, a0 = 0, K = 0, nPre = 0, nSuf = 0, nC = 0, nA = 0, nCell = 0;
   int nSlots = 0, nSilSlots = 0, nLU = 0, nLL = 0, nLD = 0, nStrips = 0, nOut = 0;
+  int C = 1, Kpad = 0;                           // columns per lane; K rounded up to a multiple of it (empty columns pass the carried states and accumulators on)
   std::vector<int> carried;                      // prefix state behind carried state c
   std::vector<std::pair<int, int>> acc;          // (suffix-local state, consumes a token)
   std::vector<ColGroup> groups;                  // in order of destination
@@ -147,7 +148,9 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
   for (int c = 0; c < out.nC; ++c) isL[c] = 1;      // carried all the way to the suffix kernel
   out.nLU = out.nLL = out.nLD = 0;
   for (int s = 0; s < out.nCell; ++s) { if (isU[s]) out.upIdx[s] = out.nLU++; if (isL[s]) out.leftIdx[s] = out.nLL++; if (isD[s]) out.diagIdx[s] = out.nLD++; }
-  out.nStrips = (K + 31) / 32;
+  out.C = std::max (1, std::min (4, m->opt.get ("col_c", out.nCell <= 12 ? 2 : 1)));
+  out.Kpad = (K + out.C - 1) / out.C * out.C;
+  out.nStrips = (out.Kpad + 32 * out.C - 1) / (32 * out.C);
   // per column: which transition fills which slot
   std::map<std::tuple<int, int, int, int>, int> groupOf;      // (type, src, dst, emit) -> index in gs
   for (size_t n = 0; n < gs.size(); ++n) if (gs[n].slot >= 0) groupOf[std::make_tuple (gs[n].type, gs[n].src, gs[n].dst, gs[n].emit ? 1 : 0)] = (int) n;
@@ -215,7 +218,7 @@ static void col_analyse (const mb_machine* m, ColProg& best) {
   if (best.nLL < 1 || best.nLL > 40) { best.why = "left-going states: " + std::to_string (best.nLL); return; }
   if (best.nLU > 40) { best.why = "too many states consumed from the row above"; return; }
   if (best.nPre > 64 || best.nSuf > 64) { best.why = "prefix / suffix of more than 64 states"; return; }
-  if ((size_t) best.nSlots * 32 * 8 > 160 * 1024) { best.why = "a strip's weight table exceeds 160 KB"; return; }
+  if ((size_t) best.nSlots * 32 * best.C * 8 > 160 * 1024) { best.why = "a strip's weight table exceeds 160 KB"; return; }
   if (best.groups.size() > 600) { best.why = "more than 600 transition groups per cell"; return; }
   if (m->nOut > 250) { best.why = "alphabet too large"; return; }
   best.ok = true;
@@ -226,57 +229,66 @@ static void col_analyse (const mb_machine* m, ColProg& best) {
 // ---------------------------------------------------------------------------------------------
 static void col_generate (const mb_machine* m, ColEngine& E) {
   const ColProg& p = E.prog;
-  E.silInRegs = p.nSilSlots <= m->opt.get ("col_sil_regs", 40);
+  E.silInRegs = p.nSilSlots * p.C <= m->opt.get ("col_sil_regs", 40);
   E.threads = std::max (32, std::min (1024, m->opt.get ("col_threads", 256) / 32 * 32));
   E.minBlocks = std::max (1, std::min (8, m->opt.get ("col_minblocks", p.nCell <= 12 ? 2 : 1)));
   E.R = std::max (1, std::min (16, m->opt.get ("col_r", 1)));
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_col.cu): period " << p.P << ", " << p.K << " columns from state " << p.a0 << ", " << p.nC << " carried, " << p.nA << " accumulators\n";
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\ntypedef unsigned long long uint64_t;\n";
-  o << "#define MB_NLL " << p.nLL << "\n#define MB_NLU " << p.nLU << "\n#define MB_NLD " << p.nLD << "\n#define MB_NSLOTS " << p.nSlots << "\n";
+  const int C = p.C;
+  o << "#define MB_COL_C " << C << "\n#define MB_NLL " << p.nLL << "\n#define MB_NUREG " << p.nLU * C << "\n#define MB_NDREG " << p.nLD * C << "\n#define MB_NSLOTS " << p.nSlots << "\n";
   o << "#define MB_COL_THREADS " << E.threads << "\n#define MB_COL_MINBLOCKS " << E.minBlocks << "\n";
   o << "#define MB_COL_DECLW";
-  if (E.silInRegs) for (int q = 0; q < p.nSilSlots; ++q) o << " const double w" << q << " = W[" << q << " * 32];";
+  if (E.silInRegs) for (int c = 0; c < C; ++c) for (int q = 0; q < p.nSilSlots; ++q) o << " const double w" << c << "_" << q << " = W[" << q * C + c << " * 32];";
   o << "\n";
-  auto weight = [&] (const ColGroup& g) {
+  // column c of the lane: its weights sit at W[(slot * C + c) * 32]; what it reads from the column to its left is the
+  // shuffled Lin / Lprev for c = 0 and the lane's own previous column otherwise
+  auto weight = [&] (const ColGroup& g, int c) {
     std::ostringstream w;
-    if (g.emit) w << "W[(" << g.slot << " + tokb) * 32]";
-    else if (E.silInRegs) w << "w" << g.slot;
-    else w << "W[" << g.slot << " * 32]";
+    if (g.emit) w << "W[((" << g.slot << " + tokb) * " << C << " + " << c << ") * 32]";
+    else if (E.silInRegs) w << "w" << c << "_" << g.slot;
+    else w << "W[" << g.slot * C + c << " * 32]";
     return w.str();
   };
-  auto source = [&] (const ColGroup& g) {
+  auto source = [&] (const ColGroup& g, int c) {
     std::ostringstream s;
-    if (g.type == CG_SILENT) s << "n" << g.src;
-    else if (g.type == CG_LEFT) s << "Lin[" << p.leftIdx[g.src] << "]";
-    else if (g.type == CG_UP) s << "U[" << p.upIdx[g.src] << "]";
-    else s << "Lprev[" << p.diagIdx[g.src] << "]";
+    if (g.type == CG_SILENT) s << "n" << c << "_" << g.src;
+    else if (g.type == CG_LEFT) { if (c) s << "n" << c - 1 << "_" << g.src; else s << "Lin[" << p.leftIdx[g.src] << "]"; }
+    else if (g.type == CG_UP) s << "U[" << c * p.nLU + p.upIdx[g.src] << "]";
+    else s << "Lprev[" << c * p.nLD + p.diagIdx[g.src] << "]";
     return s.str();
   };
   for (int lin = 1; lin >= 0; --lin) {
     o << "#define MB_COL_CELL_" << (lin ? "LIN" : "MAX") << " \\\n";
-    size_t gi = 0;
-    for (int d = 0; d < p.nCell; ++d) {
-      bool first = true;
-      o << "  double n" << d;
-      std::ostringstream rest;
-      for (; gi < p.groups.size() && p.groups[gi].dst == d; ++gi) {
-        const ColGroup& g = p.groups[gi];
-        if (g.slot < 0) { o << " = " << source (g) << ";"; first = false; continue; }      // the copy comes first
-        if (lin) {
-          if (first) rest << " n" << d << " = " << source (g) << " * " << weight (g) << ";";
-          else rest << " n" << d << " = fma (" << source (g) << ", " << weight (g) << ", n" << d << ");";
-        } else {
-          if (first) rest << " n" << d << " = " << source (g) << " + " << weight (g) << ";";
-          else rest << " { const double c = " << source (g) << " + " << weight (g) << "; if (n" << d << " < c) n" << d << " = c; }";
+    for (int c = 0; c < C; ++c) {
+      size_t gi = 0;
+      for (int d = 0; d < p.nCell; ++d) {
+        bool first = true;
+        std::ostringstream nm;
+        nm << "n" << c << "_" << d;
+        const std::string n = nm.str();
+        o << "  double " << n;
+        std::ostringstream rest;
+        for (; gi < p.groups.size() && p.groups[gi].dst == d; ++gi) {
+          const ColGroup& g = p.groups[gi];
+          if (g.slot < 0) { o << " = " << source (g, c) << ";"; first = false; continue; }      // the copy comes first
+          if (lin) {
+            if (first) rest << " " << n << " = " << source (g, c) << " * " << weight (g, c) << ";";
+            else rest << " " << n << " = fma (" << source (g, c) << ", " << weight (g, c) << ", " << n << ");";
+          } else {
+            if (first) rest << " " << n << " = " << source (g, c) << " + " << weight (g, c) << ";";
+            else rest << " { const double cand = " << source (g, c) << " + " << weight (g, c) << "; if (" << n << " < cand) " << n << " = cand; }";
+          }
+          if (first) { o << ";"; first = false; }
         }
-        if (first) { o << ";"; first = false; }
+        if (first) o << " = ZERO;";
+        o << rest.str() << " \\\n";
       }
-      if (first) o << " = ZERO;";
-      o << rest.str() << " \\\n";
     }
-    for (int s = 0; s < p.nCell; ++s) if (p.upIdx[s] >= 0) o << "  U[" << p.upIdx[s] << "] = n" << s << "; \\\n";
-    for (int s = 0; s < p.nCell; ++s) if (p.leftIdx[s] >= 0) o << "  Lown[" << p.leftIdx[s] << "] = n" << s << "; \\\n";
+    for (int c = 0; c < C; ++c) for (int s = 0; s < p.nCell; ++s) if (p.upIdx[s] >= 0) o << "  U[" << c * p.nLU + p.upIdx[s] << "] = n" << c << "_" << s << "; \\\n";
+    for (int c = 0; c + 1 < C; ++c) for (int s = 0; s < p.nCell; ++s) if (p.diagIdx[s] >= 0) o << "  Lprev[" << (c + 1) * p.nLD + p.diagIdx[s] << "] = n" << c << "_" << s << "; \\\n";
+    for (int s = 0; s < p.nCell; ++s) if (p.leftIdx[s] >= 0) o << "  Lown[" << p.leftIdx[s] << "] = n" << C - 1 << "_" << s << "; \\\n";
     o << "\n";
   }
   o << "#define MB_COL_KEEPDIAG";
@@ -383,10 +395,16 @@ __global__ void __launch_bounds__(128) col_suffix_kernel (ColSideArgs A) {
 // ---------------------------------------------------------------------------------------------
 // weights, preparation
 // ---------------------------------------------------------------------------------------------
+// column k = (strip * 32 + lane) * C + c; its weight of slot q sits at [strip][q][c][lane]
+static size_t col_tab_index (const ColProg& p, int k, int q) {
+  const int strip = k / (32 * p.C), lane = (k / p.C) % 32, c = k % p.C;
+  return (((size_t) strip * p.nSlots + q) * p.C + c) * 32 + lane;
+}
+
 static void col_fill_weights (const mb_machine* m, ColEngine& E) {
   const ColProg& p = E.prog;
-  E.tabLin.assign ((size_t) p.nStrips * p.nSlots * 32, 0.);
-  E.tabLog.assign ((size_t) p.nStrips * p.nSlots * 32, -INFINITY);
+  E.tabLin.assign ((size_t) p.nStrips * p.nSlots * 32 * p.C, 0.);
+  E.tabLog.assign ((size_t) p.nStrips * p.nSlots * 32 * p.C, -INFINITY);
   bool ok = true;
   const double lim = 40. * 0.6931471805599453;
   for (int k = 0; k < p.K; ++k)
@@ -395,7 +413,7 @@ static void col_fill_weights (const mb_machine* m, ColEngine& E) {
       if (t < 0) continue;
       const double lw = m->lw[t];
       if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
-      const size_t at = ((size_t) (k / 32) * p.nSlots + q) * 32 + (k & 31);
+      const size_t at = col_tab_index (p, k, q);
       E.tabLog[at] = lw;
       E.tabLin[at] = std::exp (lw);
     }
@@ -453,7 +471,7 @@ int col_prepare (mb_machine* m, bool hostOnly) {
   MB_CUDA (cudaSetDevice (m->device));
   if (rt_load (cubin, &E->mod) || rt_function (E->mod, "mb_k_col_sum", &E->kSum) || rt_function (E->mod, "mb_k_col_max", &E->kMax)) return 1;
   MB_CUDA (cudaDeviceGetAttribute (&E->numSMs, cudaDevAttrMultiProcessorCount, m->device));
-  E->smemBytes = (size_t) (p.nSlots * 32 + (E->threads / 32) * 16 * p.nLL) * 8;
+  E->smemBytes = (size_t) (p.nSlots * 32 * p.C + (E->threads / 32) * 16 * p.nLL) * 8;
   if (rt_prepare (E->kSum, E->threads, E->smemBytes, &E->blocksPerSMSum) || rt_prepare (E->kMax, E->threads, E->smemBytes, &E->blocksPerSMMax)) return 1;
   if (E->blocksPerSMSum < 1 || E->blocksPerSMMax < 1) { set_error ("column engine: a kernel does not fit on an SM"); return 1; }
   MB_CUDA (cudaMalloc (&E->dTabLin, E->tabLin.size() * 8));
@@ -472,7 +490,7 @@ int col_prepare (mb_machine* m, bool hostOnly) {
   if (!suf.empty()) MB_CUDA (cudaMemcpy (E->dSuf, suf.data(), suf.size() * 4, cudaMemcpyHostToDevice));
   if (!car.empty()) MB_CUDA (cudaMemcpy (E->dCarriedSlot, car.data(), car.size() * 4, cudaMemcpyHostToDevice));
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "column engine: %d threads per CTA, %zu B smem, %d / %d CTAs per SM (sums / max), silent weights in %s\n", E->threads, E->smemBytes, E->blocksPerSMSum, E->blocksPerSMMax, E->silInRegs ? "registers" : "shared memory");
+    fprintf (stderr, "column engine: %d column(s) per lane, %d threads per CTA, %zu B smem, %d / %d CTAs per SM (sums / max), silent weights in %s\n", p.C, E->threads, E->smemBytes, E->blocksPerSMSum, E->blocksPerSMMax, E->silInRegs ? "registers" : "shared memory");
   return col_update_weights (m);
 }
 
@@ -552,7 +570,7 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
     MBColArgsHost A;
     A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
     A.bnd = dBnd; A.bndOff = dOff; A.tab = sums ? E.dTabLin : E.dTabLog; A.flag = dFlag;
-    A.nStrips = p.nStrips; A.K = p.K; A.R = E.R; A.pad = 0;
+    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.pad = 0;
     const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * (sums ? E.blocksPerSMSum : E.blocksPerSMMax), groups));
     void* params[1] = { &A };
@@ -583,7 +601,7 @@ int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, doub
     const double mx = std::max (a, v), mn = std::min (a, v);
     return mn > NINF ? mx + std::log1p (std::exp (mn - mx)) : mx;
   };
-  auto tabw = [&] (int k, int slot) { return E->tabLog[((size_t) (k / 32) * p.nSlots + slot) * 32 + (k & 31)]; };
+  auto tabw = [&] (int k, int slot) { return E->tabLog[col_tab_index (p, k, slot)]; };
   std::vector<double> preCur ((size_t) std::max (p.nPre, 1), NINF), prePrev = preCur, sufCur ((size_t) std::max (p.nSuf, 1), NINF), sufPrev = sufCur;
   std::vector<double> cur ((size_t) p.K * p.nCell, NINF), prev = cur;
   std::vector<double> bCur ((size_t) p.nCell, NINF), bPrev = bCur, xPrev ((size_t) p.nCell, NINF);      // the boundary column (column -1) at this row and the row above

@@ -8,10 +8,12 @@
 // recurrence: COLUMN k = period k of the machine, ROW o = read position, a cell of P + (a few) states with the
 // transition weights depending on the column.  That is the shape the strip engines sweep at full speed.
 //
-// Mapping.  Strips of 32 columns, lane j owns column j of the strip, rows swept in a skew (at step t lane j is at row
-// t - j), exactly as the big engine (mb_big_skeleton.h), with three differences:
-//   * the weights belong to the column: one table per strip, [slot][lane], staged in shared memory for the whole CTA;
-//     the silent slots of a lane's column live in registers for the strip (MB_COL_DECLW) when there are few enough;
+// Mapping.  Strips of 32 * MB_COL_C columns, lane j owns MB_COL_C adjacent columns of the strip (their cells at one row
+// are computed one after the other in the same step: the second reads the first's fresh values from registers), rows
+// swept in a skew (at step t lane j is at row t - j), as the big engine (mb_big_skeleton.h), with three differences:
+//   * the weights belong to the column: one table per strip, [slot][column of the lane][lane], staged in shared memory
+//     for the whole CTA; the silent slots of a lane's columns live in registers for the strip (MB_COL_DECLW) when there
+//     are few enough;
 //   * all warps of a CTA work on the SAME strip (of different reads) so that they share that table: a CTA claims
 //     nWarps * R reads at a time and takes them through the strips together;
 //   * the first strip's left boundary is not empty: it holds, per row, the values of the machine's prefix states
@@ -36,12 +38,15 @@ struct MBColArgs {
   const uint8_t* y; const int64_t* yOff;
   const int64_t* order; int64_t nWork; unsigned long long* counter;
   double* bnd; const int64_t* bndOff;      // work item n: (Lo + 1) rows of MB_BROW doubles at bnd + bndOff[n]
-  const double* tab;                       // [strip][slot][lane] weights
+  const double* tab;                       // [strip][slot][column of the lane][lane] weights
   int32_t* flag;
   int nStrips, K, R, pad;
 };
 
 __device__ __forceinline__ double mb_pow2 (int d) { return __hiloint2double ((1023 + d) << 20, 0); }
+__device__ __forceinline__ void mb_lds_lane0 (double& v, const int lane, const unsigned addr) {
+  asm volatile ("{ .reg .pred p; setp.eq.s32 p, %1, 0; @p ld.shared.f64 %0, [%2]; }" : "+d"(v) : "r"(lane), "r"(addr));
+}
 
 template<int MODE>
 __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
@@ -51,8 +56,9 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
   __shared__ unsigned long long sBase;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
   double* sTab = mb_smem;
-  double* sIn = mb_smem + MB_NSLOTS * 32 + warp * (MB_COL_RESCALE * MB_NLL);
+  double* sIn = mb_smem + MB_NSLOTS * 32 * MB_COL_C + warp * (MB_COL_RESCALE * MB_NLL);
   const double* W = sTab + lane;
+  const unsigned sInAddr = (unsigned) __cvta_generic_to_shared (sIn);
 
   for (;;) {
     __syncthreads();
@@ -64,14 +70,14 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
     for (int strip = 0; strip < A.nStrips; ++strip) {
       __syncthreads();
       {
-        const double* src = A.tab + (int64_t) strip * (MB_NSLOTS * 32);
-        for (int q = threadIdx.x; q < MB_NSLOTS * 32; q += blockDim.x) sTab[q] = __ldg (src + q);
+        const double* src = A.tab + (int64_t) strip * (MB_NSLOTS * 32 * MB_COL_C);
+        for (int q = threadIdx.x; q < MB_NSLOTS * 32 * MB_COL_C; q += blockDim.x) sTab[q] = __ldg (src + q);
       }
       __syncthreads();
       MB_COL_DECLW      // the silent weights of my column, in registers for the strip
-      const int col = strip * 32 + lane;
+      const int col = (strip * 32 + lane) * MB_COL_C;      // my first column; A.K is a multiple of MB_COL_C (padded with empty columns)
       const bool inCol = col < A.K;
-      const int outLane = (strip + 1 < A.nStrips) ? 31 : ((A.K - 1) & 31);
+      const int outLane = (strip + 1 < A.nStrips) ? 31 : ((A.K / MB_COL_C - 1) & 31);
 
       for (int rr = 0; rr < A.R; ++rr) {
         const int64_t w = base + (int64_t) rr * nWarps + warp;
@@ -83,14 +89,15 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
         double* bnd = A.bnd + A.bndOff[w];
         int suspect = 0;
 
-        double U[MB_NLU > 0 ? MB_NLU : 1];      // my column's last cell: the sources of the groups that consume a token and stay in the column
-        double Lown[MB_NLL], Lprev[MB_NLD > 0 ? MB_NLD : 1];      // my last cell's left-going states; what the diagonal cell sent (sources of diagonal groups only)
+        double U[MB_NUREG > 0 ? MB_NUREG : 1];      // my columns' last cells: the sources of the groups that consume a token and stay in the column
+        double Lown[MB_NLL];                        // my last column's left-going states
+        double Lprev[MB_NDREG > 0 ? MB_NDREG : 1];  // sources of diagonal groups, a row ago: [0, MB_NLD) what the left lane sent, then my own columns but the last
 #pragma unroll
-        for (int q = 0; q < (MB_NLU > 0 ? MB_NLU : 1); ++q) U[q] = ZERO;
+        for (int q = 0; q < (MB_NUREG > 0 ? MB_NUREG : 1); ++q) U[q] = ZERO;
 #pragma unroll
         for (int j = 0; j < MB_NLL; ++j) Lown[j] = ZERO;
 #pragma unroll
-        for (int j = 0; j < (MB_NLD > 0 ? MB_NLD : 1); ++j) Lprev[j] = ZERO;
+        for (int j = 0; j < (MB_NDREG > 0 ? MB_NDREG : 1); ++j) Lprev[j] = ZERO;
         int ecur = LIN ? (int) __ldcg (bnd + MB_NLL) : 0;      // frame: true value = stored value * 2^ecur
         double gl = 1.0;                                        // 2^(left neighbour's frame - mine)
         double stageNext[MB_NLL], stageNextE = (double) ecur;   // boundary row t + lane of the next block (lanes < MB_COL_RESCALE)
@@ -108,11 +115,11 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
               int mh = 0;
               unsigned ml = 0xffffffffu;
 #pragma unroll
-              for (int q = 0; q < MB_NLU; ++q) { const int h = __double2hiint (U[q]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
+              for (int q = 0; q < MB_NUREG; ++q) { const int h = __double2hiint (U[q]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
 #pragma unroll
               for (int j = 0; j < MB_NLL; ++j) { const int h = __double2hiint (Lown[j]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
 #pragma unroll
-              for (int j = 0; j < MB_NLD; ++j) { const int h = __double2hiint (Lprev[j]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
+              for (int j = 0; j < MB_NDREG; ++j) { const int h = __double2hiint (Lprev[j]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
               nz = mh >= 0x00100000;
               if (nz) {
                 const int ex = mh >> 20;
@@ -120,11 +127,11 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
                 if (shift != 0) {
                   const double f = mb_pow2 (-shift);
 #pragma unroll
-                  for (int q = 0; q < MB_NLU; ++q) U[q] *= f;
+                  for (int q = 0; q < MB_NUREG; ++q) U[q] *= f;
 #pragma unroll
                   for (int j = 0; j < MB_NLL; ++j) Lown[j] *= f;
 #pragma unroll
-                  for (int j = 0; j < MB_NLD; ++j) Lprev[j] *= f;
+                  for (int j = 0; j < MB_NDREG; ++j) Lprev[j] *= f;
                   ecur += shift;
                 }
                 if (ml != 0xffffffffu && ex - (int) ((ml + 1u) >> 20) > 700) suspect |= 1;
@@ -178,9 +185,10 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
           double Lin[MB_NLL];
 #pragma unroll
           for (int j = 0; j < MB_NLL; ++j) {
-            const double fromUp = __shfl_up_sync (MB_FULL, Lown[j], 1);
-            const double fromLane = LIN ? fromUp * gl : fromUp;
-            Lin[j] = lane ? fromLane : sIn[(t & (MB_COL_RESCALE - 1)) * MB_NLL + j];
+            double v = __shfl_up_sync (MB_FULL, Lown[j], 1);
+            if (LIN) v *= gl;
+            mb_lds_lane0 (v, lane, sInAddr + (unsigned) (((t & (MB_COL_RESCALE - 1)) * MB_NLL + j) * 8));      // lane 0 takes the staged boundary row: a predicated load, no select
+            Lin[j] = v;
           }
           if (r >= 0 && r <= Lo && inCol) {
             if (LIN) { MB_COL_CELL_LIN }
