@@ -148,7 +148,9 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
   for (int c = 0; c < out.nC; ++c) isL[c] = 1;      // carried all the way to the suffix kernel
   out.nLU = out.nLL = out.nLD = 0;
   for (int s = 0; s < out.nCell; ++s) { if (isU[s]) out.upIdx[s] = out.nLU++; if (isL[s]) out.leftIdx[s] = out.nLL++; if (isD[s]) out.diagIdx[s] = out.nLD++; }
-  out.C = std::max (1, std::min (4, m->opt.get ("col_c", out.nCell <= 12 ? 2 : 1)));
+  // two columns per lane halve the per-cell share of the shuffles, the boundary traffic and the loop (measured on B200:
+  // PF00516 812 -> 1332 GCUPS, PF00516 => protpsw 564 -> 685; three and four lose to register pressure)
+  out.C = std::max (1, std::min (4, m->opt.get ("col_c", (size_t) out.nSlots * 64 * 8 <= 112 * 1024 ? 2 : 1)));
   out.Kpad = (K + out.C - 1) / out.C * out.C;
   out.nStrips = (out.Kpad + 32 * out.C - 1) / (32 * out.C);
   // per column: which transition fills which slot
