@@ -1114,7 +1114,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   const int W = 32 * (scoreKernel && J.modV ? J.CV : J.C);      // (the split module has the score module's columns per lane)
   bool split = false;
   std::vector<int64_t> items, itemBnd;
-  if (scoreKernel && m->opt.get ("jit_split", -1) != 0) {
+  if (scoreKernel && !narrow && m->opt.get ("jit_split", -1) != 0) {      // (the caller laid out its back-pointers for the strips it chose: narrow strips are never split)
     int64_t nItems = 0;
     for (int64_t k: order) nItems += (b->xOff[k + 1] - b->xOff[k] + W) / W;
     split = nItems > (int64_t) order.size() && (m->opt.get ("jit_split", -1) > 0 || (double) order.size() < 0.75 * (double) (grid * warpsPerBlock));
@@ -1131,7 +1131,6 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   if (split) {
     if (ensure_split_module (m, J)) return 1;
     const int q = which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3;
-    narrow = false;
     fn = J.kSplit[q];
     grid = (int64_t) J.numSMs * J.blocksPerSMS[q];
   }

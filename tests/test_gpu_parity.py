@@ -254,7 +254,7 @@ def test_lane_engine_reads_per_lane(reads_per_lane):
         lens = [(7 * k + 3) % (max_len + 1) for k in range(n_reads)]
         pairs = [(np.zeros(0, np.uint8), synth_tokens(21, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
         orc = Oracle(fm)
-        m = make_machine(capi, fm, 2, lane_r=reads_per_lane)
+        m = make_machine(capi, fm, 2, lane_r=reads_per_lane, no_col=1)      # (the column engine would take the profile's sweeps)
         b = capi.Batch(pairs)
         ll = capi.forward(m, b)
         sc, paths = capi.viterbi(m, b)
@@ -440,7 +440,7 @@ def test_lane_engine_config5_read_lengths(reads_per_lane):
         lens[0], lens[1], lens[2] = 500, 50, 275
         pairs = [(np.zeros(0, np.uint8), synth_tokens(23, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
         orc = Oracle(fm)
-        m = make_machine(capi, fm, 2, lane_r=reads_per_lane)
+        m = make_machine(capi, fm, 2, lane_r=reads_per_lane, no_col=1)      # (the column engine would take the profile's sweeps)
         b = capi.Batch(pairs)
         ll = capi.forward(m, b)
         assert b.last_redo() == 0, (name, b.last_redo())
@@ -454,6 +454,78 @@ def test_lane_engine_config5_read_lengths(reads_per_lane):
             v, p = orc.viterbi(x, y)
             assert sc[k] == v and sc2[k] == v, (name, k, sc[k], v)
             assert paths[k].tolist() == p.tolist(), (name, k)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(col_c=1), dict(col_c=3, col_minblocks=1), dict(col_r=2, col_bnd_budget_mb=1), dict(col_threads=64, col_sil_regs=0)])
+def test_column_engine_profile_reads(opts):
+    """Periodic generators (PF00516 and PF00516 => protpsw) through the column engine (mb_col.cu: column = profile node,
+    row = read position): read lengths around the strip-staging block (0, 1, 15 - 17, 31 - 33) and config 5's own 50 - 500,
+    one to three columns per lane, several reads per warp, boundary buffers forced into several chunks -- Forward against the
+    oracle, Viterbi scores bit for bit, and the same numbers as the lane engine's own sweep."""
+    capi = _capi()
+    for name, n_reads in (("hmmer_pf00516", 150), ("hmmer_pf00516_protpsw", 40)):
+        fm = FlatMachine.from_json(load_golden(name)["machine"])
+        lens = [50 + (k * 37) % 451 for k in range(n_reads)]
+        lens[:12] = [0, 1, 15, 16, 17, 31, 32, 33, 500, 50, 275, 2]
+        pairs = [(np.zeros(0, np.uint8), synth_tokens(27, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
+        orc = Oracle(fm)
+        m = make_machine(capi, fm, 2, **opts)
+        b = capi.Batch(pairs)
+        ll = capi.forward(m, b)
+        launches = b.last_kernel_ms()[1]
+        assert launches >= 3 and launches % 3 == 0, launches      # prefix, strips, suffix per chunk: the column engine ran
+        if "col_bnd_budget_mb" in opts:
+            assert launches >= 6
+        assert b.last_redo() == 0
+        sc = capi.viterbi(m, b, paths=False)
+        lane = make_machine(capi, fm, 2, no_col=1)
+        ll_lane = capi.forward(lane, b)
+        sc_lane = capi.viterbi(lane, b, paths=False)
+        assert np.array_equal(sc, sc_lane)
+        np.testing.assert_allclose(ll, ll_lane, rtol=1e-10)
+        for k in sorted(set(list(range(12)) + [n_reads - 1] + list(range(14, n_reads, 31)))):
+            x, y = pairs[k]
+            f = orc.forward(x, y)
+            assert forward_agrees(fm, x, y, ll[k], f), (name, k, ll[k], f)
+            v, _ = orc.viterbi(x, y)
+            assert sc[k] == v, (name, k, sc[k], v)
+        sc2, paths = capi.viterbi(m, b)      # with paths: the lane engine's sweep and traceback
+        assert np.array_equal(sc2, sc)
+        v, p = orc.viterbi(*pairs[10])
+        assert paths[10].tolist() == p.tolist()
+
+
+def test_column_engine_hands_impossible_reads_to_the_log_domain():
+    """A profile that cannot emit residue 1: reads containing it have no path.  The column engine's linear sweep returns
+    nothing for them; they are counted as re-run and come back -inf from the lane engine's log-domain sweep, the others are
+    untouched."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("hmmer_pf00516")["machine"])
+    lw = np.where(fm.tout == 1, -np.inf, fm.lw)
+    fm2 = FlatMachine(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, lw, fm.in_alphabet, fm.out_alphabet)
+    pairs = []
+    for k in range(40):
+        y = synth_tokens(33, k, 1, 20 + k, fm.n_out)
+        if k % 2:
+            y = np.where(y == 1, 2, y).astype(np.uint8)
+        pairs.append((np.zeros(0, np.uint8), y))
+    m = make_machine(capi, fm2, 2)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    sc = capi.viterbi(m, b, paths=False)
+    orc = Oracle(fm2)
+    n_inf = 0
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        if np.isinf(f):
+            n_inf += 1
+            assert ll[k] == f and sc[k] == f, (k, ll[k], sc[k])
+        else:
+            assert abs(ll[k] - f) <= 1e-9 * abs(f), (k, ll[k], f)
+            assert sc[k] == orc.viterbi(x, y)[0]
+    assert n_inf >= 10 and b.last_redo() == 0      # (last call was Viterbi; the Forward call's count is checked below)
+    capi.forward(m, b)
+    assert b.last_redo() == n_inf
 
 
 def test_chunked_traceback_and_counts():
