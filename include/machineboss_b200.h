@@ -205,10 +205,13 @@ int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t n
  * tests check the analysis, the per-column weight tables and the prefix / suffix programs against known answers).
  * op: 0 log-sum-exp, 1 max-plus.  info[12] = { usable, period, first periodic state, columns, prefix states, suffix states,
  * carried states, accumulators, transition groups per cell, weight slots per column, left-going states, states read
- * from the row above }.  log (may be NULL): the NVRTC log of the generated strip kernel, compiled for sm_100a. */
+ * from the row above }.  log (may be NULL): the NVRTC log of the generated strip kernel, compiled for sm_100a.  pathLen (may
+ * be NULL; op 1): the number of transitions on the Viterbi path, walked back over the program's pointers; at most pathCap
+ * ids are written to path. */
 int mb_col_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
                     const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
-                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap);
+                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap,
+                    int32_t* path, int64_t pathCap, int64_t* pathLen);
 
 /* ---- measurement hooks (not part of the reference surface) ----
  * Device time, in milliseconds, of the kernels launched by the last compute call on this batch

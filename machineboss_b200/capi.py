@@ -68,7 +68,7 @@ def lib():
         L.mb_jit_compile_check.argtypes = [I32, I32, I32, I64, P, P, P, P, ctypes.c_char_p, I64]
         L.mb_jit_host_tables.argtypes = [I32, I32, I32, I64, P, P, P, P, P, I32, P, I64, ctypes.POINTER(I64)]
         L.mb_lane_emulate.argtypes = [I32, I32, I32, I64, P, P, P, P, P, P, I64, I32, ctypes.POINTER(D), P, P]
-        L.mb_col_emulate.argtypes = [I32, I32, I32, I64, P, P, P, P, P, P, I64, I32, ctypes.POINTER(D), P, ctypes.c_char_p, I64]
+        L.mb_col_emulate.argtypes = [I32, I32, I32, I64, P, P, P, P, P, P, I64, I32, ctypes.POINTER(D), P, ctypes.c_char_p, I64, P, I64, ctypes.POINTER(I64)]
         L.mb_last_redo.argtypes = [P, ctypes.POINTER(I64)]
         L.mb_last_kernel_ms.argtypes = [P, ctypes.POINTER(D), ctypes.POINTER(I64)]
         L.mb_shard_pairs.argtypes = [I64, P, P, I32, P]
@@ -159,18 +159,27 @@ def lane_emulate(n_states, n_in, n_out, src, dst, tin, tout, log_weight, y, op: 
     return (res.value, info, bp) if back_pointers else (res.value, info)
 
 
-def col_emulate(n_states, n_in, n_out, src, dst, tin, tout, log_weight, y, op: int, compile_log: bool = False):
-    """The column engine's program for a periodic generator run for one read on the host; returns (result, info[12][, NVRTC log]).
-    info[0] == 0: the machine has no such structure (result is meaningless)."""
+def col_emulate(n_states, n_in, n_out, src, dst, tin, tout, log_weight, y, op: int, compile_log: bool = False, path: bool = False):
+    """The column engine's program for a periodic generator run for one read on the host; returns (result, info[12][, NVRTC log]
+    [, Viterbi path]).  info[0] == 0: the machine has no such structure (result is meaningless)."""
     arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (src, dst, tin, tout)]
     lw = np.ascontiguousarray(log_weight, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.uint8)
     res = ctypes.c_double(0)
     info = np.zeros(12, dtype=np.int32)
     buf = ctypes.create_string_buffer(1 << 16) if compile_log else None
+    ids = np.zeros(4 * (len(y) + 1) + 4 * int(n_states), dtype=np.int32) if path else None
+    n_ids = ctypes.c_int64(0)
     _check(lib().mb_col_emulate(int(n_states), int(n_in), int(n_out), int(lw.shape[0]), *[_ptr(a) for a in arrs], _ptr(lw),
-                                _ptr(y), len(y), int(op), ctypes.byref(res), info.ctypes.data, buf, len(buf) if compile_log else 0))
-    return (res.value, info, buf.value.decode()) if compile_log else (res.value, info)
+                                _ptr(y), len(y), int(op), ctypes.byref(res), info.ctypes.data, buf, len(buf) if compile_log else 0,
+                                ids.ctypes.data if path else None, len(ids) if path else 0, ctypes.byref(n_ids) if path else None))
+    out = (res.value, info)
+    if compile_log:
+        out += (buf.value.decode(),)
+    if path:
+        assert n_ids.value <= len(ids)
+        out += (ids[: n_ids.value].copy(),)
+    return out
 
 
 def _ptr(a):

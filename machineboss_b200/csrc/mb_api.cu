@@ -752,7 +752,8 @@ int mb_lane_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t n
 
 int mb_col_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
                     const int32_t* src, const int32_t* dst, const int32_t* inTok, const int32_t* outTok, const double* logWeight,
-                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap) {
+                    const uint8_t* outTokens, int64_t outLen, int32_t op, double* result, int32_t* info, char* log, int64_t logCap,
+                    int32_t* path, int64_t pathCap, int64_t* pathLen) {
   mb_machine m;
   m.opt = g_options;
   m.S = nStates; m.nIn = nInTok; m.nOut = nOutTok; m.T = nTrans;
@@ -763,7 +764,9 @@ int mb_col_emulate (int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nT
   int32_t inf[12];
   col_info (&m, inf);
   if (info) for (int q = 0; q < 12; ++q) info[q] = inf[q];
-  if (!rc && inf[0] && result) rc = col_emulate (&m, outTokens, outLen, op, result);
+  std::vector<int64_t> walked;
+  if (!rc && inf[0] && result) rc = col_emulate (&m, outTokens, outLen, op, result, pathLen ? &walked : nullptr);
+  if (!rc && pathLen) { *pathLen = (int64_t) walked.size(); for (int64_t q = 0; q < (int64_t) walked.size() && q < pathCap; ++q) path[q] = (int32_t) walked[q]; }
   if (!rc && inf[0] && log && logCap > 0) {      // compile the generated strip kernel too (NVRTC, no device)
     std::string l;
     rc = col_compile_check (&m, &l);

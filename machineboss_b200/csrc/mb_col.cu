@@ -44,7 +44,7 @@ enum { CG_SILENT = 0, CG_LEFT = 1, CG_UP = 2, CG_DIAG = 3 };
 enum { CE_SILENT = 0, CE_EMIT = 1, CE_EXT_CUR = 2, CE_EXT_PREV = 3 };
 
 struct ColGroup { int type, dst, src, slot; bool emit; };      // cell-state indices; slot < 0: a copy (weight one)
-struct ColEntry { int dst, src, tok, kind; int64_t trans; };   // trans < 0: weight one
+struct ColEntry { int dst, src, tok, kind; int64_t trans; int ord; };   // trans < 0: weight one; ord: rank among the destination's candidates
 
 struct ColProg {
   bool ok = false;
@@ -135,7 +135,15 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
   }
   for (int c = 0; c < out.nC; ++c) gs.push_back (ColGroup { CG_LEFT, c, c, -1, false });
   for (int a = 0; a < out.nA; ++a) gs.push_back (ColGroup { CG_LEFT, out.nC + P + a, out.nC + P + a, -1, false });
-  std::stable_sort (gs.begin(), gs.end(), [] (const ColGroup& p, const ColGroup& q) { return p.dst != q.dst ? p.dst < q.dst : (p.slot < 0) > (q.slot < 0); });
+  // Candidates of a state in the reference's order (viterbi.cpp:30-39: token-consuming sources before silent ones, each by
+  // source state): the copy from the left stands for sources in earlier columns, carried states are prefix states (lowest
+  // index), then the column to the left, then this column.  Strict '<' in the max-plus cell then keeps the same first maximum.
+  auto rank = [&] (const ColGroup& g) {
+    if (g.slot < 0) return -1;
+    const int cls = g.src < out.nC ? 0 : (g.type == CG_LEFT || g.type == CG_DIAG) ? 1 : 2;
+    return ((g.emit ? 0 : 1) * 3 + cls) * 4096 + g.src;
+  };
+  std::stable_sort (gs.begin(), gs.end(), [&] (const ColGroup& p, const ColGroup& q) { return p.dst != q.dst ? p.dst < q.dst : rank (p) < rank (q); });
   int slot = 0;
   for (auto& g: gs) if (g.slot >= 0 && !g.emit) g.slot = slot++;
   out.nSilSlots = slot;
@@ -173,12 +181,14 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
     const int s = m->src[t], d = m->dst[t];
     const bool emit = m->out[t] != 0;
     if (s == 0 && d == 0 && !emit) continue;
-    if (s < a0 && d < a0) out.pre.push_back (ColEntry { d, s, m->out[t], emit ? CE_EMIT : CE_SILENT, t });
-    else if (s >= end && d >= end) out.suf.push_back (ColEntry { d - end, s - end, m->out[t], emit ? CE_EMIT : CE_SILENT, t });
-    else if (s < a0 && d >= end) out.suf.push_back (ColEntry { d - end, out.leftIdx[carriedIdx[s]], m->out[t], emit ? CE_EXT_PREV : CE_EXT_CUR, t });
+    const int ord = (emit ? 0 : 1) * (S + 1) + s;      // token-consuming candidates first, each class by source state
+    if (s < a0 && d < a0) out.pre.push_back (ColEntry { d, s, m->out[t], emit ? CE_EMIT : CE_SILENT, t, ord });
+    else if (s >= end && d >= end) out.suf.push_back (ColEntry { d - end, s - end, m->out[t], emit ? CE_EMIT : CE_SILENT, t, ord });
+    else if (s < a0 && d >= end) out.suf.push_back (ColEntry { d - end, out.leftIdx[carriedIdx[s]], m->out[t], emit ? CE_EXT_PREV : CE_EXT_CUR, t, ord });
   }
-  for (int a = 0; a < out.nA; ++a) out.suf.push_back (ColEntry { out.acc[a].first, out.leftIdx[out.nC + P + a], 0, CE_EXT_CUR, -1 });
-  auto byDst = [] (const ColEntry& p, const ColEntry& q) { return p.dst < q.dst; };
+  for (int a = 0; a < out.nA; ++a)      // an accumulator stands for the period states that send to the suffix state: between the prefix and the suffix
+    out.suf.push_back (ColEntry { out.acc[a].first, out.leftIdx[out.nC + P + a], 0, CE_EXT_CUR, -1, (out.acc[a].second ? 0 : 1) * (S + 1) + a0 });
+  auto byDst = [] (const ColEntry& p, const ColEntry& q) { return p.dst != q.dst ? p.dst < q.dst : p.ord < q.ord; };
   std::stable_sort (out.pre.begin(), out.pre.end(), byDst);
   std::stable_sort (out.suf.begin(), out.suf.end(), byDst);
   return true;
@@ -593,15 +603,77 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
 // the column program executed on the host for one read (diagnostic: pins the analysis and the tables without a device)
 // op 0: log-sum-exp (exact), 1: max
 // ---------------------------------------------------------------------------------------------
-int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result) {
+// The walk back over the pointers of the max-plus sweep (DPMatrix::traceBack, dpmatrix.defs.h:82-110, in the column
+// program's coordinates), shared by the host emulation and -- through the same tables -- the device kernel.  A position is
+// (where, k, o, s): where 2 = suffix state s, 1 = cell state s of column k, 0 = prefix state s, at row o.
+//   suffix entry won: silent / token-consuming inside the suffix, or an external one -- an accumulator or a carried state
+//     of the last column (row o, or o - 1 when the entry consumes the token);
+//   cell group won: a copy from the left moves one column left without a transition (from column 0 into the prefix: a
+//     carried state IS its prefix state); SILENT stays, LEFT moves a column, UP a row, DIAG both;
+//   prefix entry won: as in the suffix; the walk ends at (row 0, state 0).
+struct ColPtrs {      // what col_emulate records for the walk
+  std::vector<int32_t> pre, cell, suf;      // [o][state] entry index; [o][k][cell state] group index; -1: nothing won
+};
+
+static int col_walk (const ColProg& p, const uint8_t* y, int64_t Lo, const ColPtrs& P, std::vector<int64_t>& path) {
+  path.clear();
+  int where = 2, k = p.K - 1, s = p.nSuf - 1;
+  int64_t o = Lo;
+  auto cellOfLeft = [&] (int leftSlot) { for (int c = 0; c < p.nCell; ++c) if (p.leftIdx[c] == leftSlot) return c; return -1; };
+  for (int64_t guard = 0; guard < (Lo + 2) * ((int64_t) p.K * p.nCell + p.nPre + p.nSuf + 2); ++guard) {
+    if (where == 0 && o == 0 && s == 0) { std::reverse (path.begin(), path.end()); return 0; }
+    if (where == 2) {
+      const int e = P.suf[(size_t) o * p.nSuf + s];
+      if (e < 0) break;
+      const ColEntry& en = p.suf[e];
+      if (en.trans >= 0) path.push_back (en.trans);
+      if (en.kind == CE_SILENT) s = en.src;
+      else if (en.kind == CE_EMIT) { s = en.src; --o; }
+      else { where = 1; k = p.K - 1; s = cellOfLeft (en.src); if (en.kind == CE_EXT_PREV) --o; }
+    } else if (where == 1) {
+      const int gi = P.cell[((size_t) o * p.K + k) * p.nCell + s];
+      if (gi < 0) break;
+      const ColGroup& g = p.groups[gi];
+      if (g.slot < 0) {      // the copy from the left
+        if (k == 0) { if (s >= p.nC) break; where = 0; s = p.carried[s]; } else --k;
+        continue;
+      }
+      const int64_t t = p.slotTrans[(size_t) k * p.nSlots + g.slot + (g.emit ? y[o - 1] - 1 : 0)];
+      if (t < 0) break;
+      path.push_back (t);
+      s = g.src;
+      if (g.type == CG_LEFT || g.type == CG_DIAG) { if (k == 0) break; --k; }
+      if (g.type == CG_UP || g.type == CG_DIAG) --o;
+    } else {
+      const int e = P.pre[(size_t) o * p.nPre + s];
+      if (e < 0) break;
+      const ColEntry& en = p.pre[e];
+      path.push_back (en.trans);
+      s = en.src;
+      if (en.kind == CE_EMIT) --o;
+    }
+  }
+  set_error ("column engine: the walk back over the pointers did not reach the start state");
+  return 1;
+}
+
+int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<int64_t>* path) {
   const ColEngine* E = ce (m);
   if (!E) { set_error ("column engine: no program for this machine"); return 1; }
   const ColProg& p = E->prog;
   const double NINF = -INFINITY;
-  auto comb = [&] (double a, double v) {
-    if (op == 1) return std::max (a, v);
+  const bool ptrs = op == 1 && path;
+  ColPtrs P;
+  if (ptrs) {
+    P.pre.assign ((size_t) (Lo + 1) * p.nPre, -1);
+    P.cell.assign ((size_t) (Lo + 1) * p.K * p.nCell, -1);
+    P.suf.assign ((size_t) (Lo + 1) * p.nSuf, -1);
+  }
+  // a <- a (+) v; max-plus keeps the FIRST maximum (strict '<', dpmatrix.defs.h:171-174) and notes who won
+  auto comb = [&] (double& a, double v, int32_t* ptr, int who) {
+    if (op == 1) { if (a < v) { a = v; if (ptr) *ptr = who; } return; }
     const double mx = std::max (a, v), mn = std::min (a, v);
-    return mn > NINF ? mx + std::log1p (std::exp (mn - mx)) : mx;
+    a = mn > NINF ? mx + std::log1p (std::exp (mn - mx)) : mx;
   };
   auto tabw = [&] (int k, int slot) { return E->tabLog[col_tab_index (p, k, slot)]; };
   std::vector<double> preCur ((size_t) std::max (p.nPre, 1), NINF), prePrev = preCur, sufCur ((size_t) std::max (p.nSuf, 1), NINF), sufPrev = sufCur;
@@ -613,8 +685,9 @@ int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, doub
     if (o == 0) preCur[0] = 0.;
     for (size_t e = 0; e < p.pre.size(); ++e) {
       const ColEntry& en = p.pre[e];
-      if (en.kind == CE_SILENT) preCur[en.dst] = comb (preCur[en.dst], preCur[en.src] + E->preW[e]);
-      else if (en.tok == tok) preCur[en.dst] = comb (preCur[en.dst], prePrev[en.src] + E->preW[e]);
+      int32_t* ptr = ptrs ? &P.pre[(size_t) o * p.nPre + en.dst] : nullptr;
+      if (en.kind == CE_SILENT) comb (preCur[en.dst], preCur[en.src] + E->preW[e], ptr, (int) e);
+      else if (en.tok == tok) comb (preCur[en.dst], prePrev[en.src] + E->preW[e], ptr, (int) e);
     }
     std::fill (bCur.begin(), bCur.end(), NINF);
     for (int c = 0; c < p.nC; ++c) bCur[c] = preCur[p.carried[c]];
@@ -624,11 +697,12 @@ int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, doub
       const double* diag = k ? &prev[(size_t) (k - 1) * p.nCell] : bPrev.data();
       const double* up = &prev[(size_t) k * p.nCell];
       for (int s = 0; s < p.nCell; ++s) n[s] = NINF;
-      for (auto& g: p.groups) {
+      for (size_t gi = 0; gi < p.groups.size(); ++gi) {
+        const ColGroup& g = p.groups[gi];
         const double src = g.type == CG_SILENT ? n[g.src] : g.type == CG_LEFT ? left[g.src] : g.type == CG_UP ? up[g.src] : diag[g.src];
         double w = 0.;
         if (g.slot >= 0) { if (g.emit) { if (tok < 1) continue; w = tabw (k, g.slot + tok - 1); } else w = tabw (k, g.slot); }
-        n[g.dst] = comb (n[g.dst], src + w);
+        comb (n[g.dst], src + w, ptrs ? &P.cell[((size_t) o * p.K + k) * p.nCell + g.dst] : nullptr, (int) gi);
       }
     }
     const double* X = &cur[(size_t) (p.K - 1) * p.nCell];
@@ -641,12 +715,13 @@ int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, doub
       else if (en.kind == CE_EXT_CUR) v = ext (X, en.src) + E->sufW[e];
       else if (en.tok != tok) continue;
       else v = (en.kind == CE_EMIT ? sufPrev[en.src] : ext (xPrev.data(), en.src)) + E->sufW[e];
-      sufCur[en.dst] = comb (sufCur[en.dst], v);
+      comb (sufCur[en.dst], v, ptrs ? &P.suf[(size_t) o * p.nSuf + en.dst] : nullptr, (int) e);
     }
     for (int s = 0; s < p.nCell; ++s) xPrev[s] = X[s];
     prev.swap (cur); bPrev = bCur; prePrev = preCur; sufPrev = sufCur;
   }
   *result = sufPrev[p.nSuf - 1];
+  if (ptrs) { path->clear(); if (*result > NINF) return col_walk (p, y, Lo, P, *path); }
   return 0;
 }
 

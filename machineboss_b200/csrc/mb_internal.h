@@ -197,7 +197,7 @@ bool col_usable (const mb_machine* m, bool sums);
 int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, bool sums, double* dResult, int32_t* dFlag, int64_t* launches);
 int col_compile_check (const mb_machine* m, std::string* log);
 int col_info (const mb_machine* m, int32_t* info);      // { usable, period, first state, columns, prefix, suffix, carried, accumulators, groups, weight slots, left-going, up }
-int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result);      // op 0 log-sum-exp, 1 max
+int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<int64_t>* path);      // op 0 log-sum-exp, 1 max (path: the traceback, may be null)
 
 // ---- big engine (mb_big.cu): machine-specialised Forward sweep for mid-size machines (a thread per cell, the cell as
 // straight-line code); full two-dimensional matrices only; flagged pairs go back to the wide engine's log-domain sweep ----

@@ -31,9 +31,10 @@ def test_column_program_on_the_host(name, lens):
         assert info[0] == 1, "no column program for %s" % name
         want = orc.forward(x, y, mode=LSE_EXACT)
         assert (f == want) if math.isinf(want) else abs(f - want) <= 1e-10 * max(1.0, abs(want)), (name, lo, f, want)
-        v, _ = capi.col_emulate(*args, y, 1)
-        want_v, _ = orc.viterbi(x, y)
+        v, _, walked = capi.col_emulate(*args, y, 1, path=True)
+        want_v, want_p = orc.viterbi(x, y)
         assert v == want_v, (name, lo, v, want_v)
+        assert walked.tolist() == want_p.tolist(), (name, lo)      # the walk back over the program's pointers is the reference's path
     # the structure found: 5 states per profile node (Mx, M, D, Ix, I), times the error model's states in the composition
     assert info[1] == (5 if name == "hmmer_pf00516" else 25) and info[3] >= 480 and info[6] >= 1 and info[7] >= 1
     assert info[1] * info[3] + info[4] + info[5] == fm.n_states

