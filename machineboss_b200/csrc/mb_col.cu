@@ -57,6 +57,10 @@ struct ColProg {
   std::vector<ColGroup> groups;                  // in order of destination
   std::vector<int> upIdx, leftIdx, diagIdx;      // per cell state: index in U[] / the left-going set / Lprev[], or -1
   std::vector<int64_t> slotTrans;                // [K][nSlots] -> transition, or -1
+  // Viterbi pointers: cell state d's field is ptrBits[d] wide at (ptrWord[d], ptrShift[d]) of the cell's nPtrWords 32-bit words and
+  // holds the index of the winning candidate among the state's groups [groupStart[d], groupStart[d+1]); bpBytes bytes per cell
+  std::vector<int> ptrWord, ptrShift, ptrBits, groupStart;
+  int nPtrWords = 1, bpBytes = 4;
   std::vector<ColEntry> pre, suf;
 };
 
@@ -73,6 +77,10 @@ struct ColEngine {
   double* dTabLin = nullptr; double* dTabLog = nullptr;
   int32_t* dPre = nullptr; double* dPreW = nullptr; int32_t* dSuf = nullptr; double* dSufW = nullptr;
   int32_t* dCarriedSlot = nullptr;      // [nC] left-going slot of carried c | [nC] prefix state
+  void* kMaxP = nullptr;                // max-plus with pointers
+  int blocksPerSMMaxP = 1;
+  int32_t* dTbPlan = nullptr;           // the traceback's tables, one array (see ColTbPlan)
+  size_t tbOff[12] = { 0 };
 };
 
 static ColEngine* ce (const mb_machine* m) { return static_cast<ColEngine*> (m->col); }
@@ -158,6 +166,23 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
   for (int s = 0; s < out.nCell; ++s) { if (isU[s]) out.upIdx[s] = out.nLU++; if (isL[s]) out.leftIdx[s] = out.nLL++; if (isD[s]) out.diagIdx[s] = out.nLD++; }
   // two columns per lane halve the per-cell share of the shuffles, the boundary traffic and the loop (measured on B200:
   // PF00516 812 -> 1332 GCUPS, PF00516 => protpsw 564 -> 685; three and four lose to register pressure)
+  out.groupStart.assign ((size_t) out.nCell + 1, 0);
+  for (auto& g: gs) out.groupStart[g.dst + 1]++;
+  for (int d = 0; d < out.nCell; ++d) out.groupStart[d + 1] += out.groupStart[d];
+  out.ptrWord.assign ((size_t) out.nCell, 0); out.ptrShift.assign ((size_t) out.nCell, 0); out.ptrBits.assign ((size_t) out.nCell, 0);
+  {
+    int word = 0, used = 0;
+    for (int d = 0; d < out.nCell; ++d) {
+      const int n = out.groupStart[d + 1] - out.groupStart[d];
+      int bt = 0; while ((1 << bt) < n) ++bt;
+      if (bt == 0) continue;
+      if (used + bt > 32) { ++word; used = 0; }
+      out.ptrWord[d] = word; out.ptrShift[d] = used; out.ptrBits[d] = bt;
+      used += bt;
+    }
+    out.nPtrWords = word + 1;
+    out.bpBytes = word == 0 ? (used <= 8 ? 1 : used <= 16 ? 2 : 4) : 4 * out.nPtrWords;
+  }
   out.C = std::max (1, std::min (4, m->opt.get ("col_c", (size_t) out.nSlots * 64 * 8 <= 112 * 1024 ? 2 : 1)));
   out.Kpad = (K + out.C - 1) / out.C * out.C;
   out.nStrips = (out.Kpad + 32 * out.C - 1) / (32 * out.C);
@@ -251,6 +276,7 @@ static void col_generate (const mb_machine* m, ColEngine& E) {
   const int C = p.C;
   o << "#define MB_COL_C " << C << "\n#define MB_NLL " << p.nLL << "\n#define MB_NUREG " << p.nLU * C << "\n#define MB_NDREG " << p.nLD * C << "\n#define MB_NSLOTS " << p.nSlots << "\n";
   o << "#define MB_COL_THREADS " << E.threads << "\n#define MB_COL_MINBLOCKS " << E.minBlocks << "\n";
+  o << "#define MB_NPW " << p.nPtrWords << "\n#define MB_BPBYTES " << p.bpBytes << "\n";
   o << "#define MB_COL_DECLW";
   if (E.silInRegs) for (int c = 0; c < C; ++c) for (int q = 0; q < p.nSilSlots; ++q) o << " const double w" << c << "_" << q << " = W[" << q * C + c << " * 32];";
   o << "\n";
@@ -271,8 +297,10 @@ static void col_generate (const mb_machine* m, ColEngine& E) {
     else s << "Lprev[" << c * p.nLD + p.diagIdx[g.src] << "]";
     return s.str();
   };
-  for (int lin = 1; lin >= 0; --lin) {
-    o << "#define MB_COL_CELL_" << (lin ? "LIN" : "MAX") << " \\\n";
+  for (int pass = 0; pass < 3; ++pass) {      // sums; max-plus; max-plus with the winners' indices
+    const int lin = pass == 0;
+    const bool wp = pass == 2;
+    o << "#define MB_COL_CELL_" << (lin ? "LIN" : wp ? "MAXP" : "MAX") << " \\\n";
     for (int c = 0; c < C; ++c) {
       size_t gi = 0;
       for (int d = 0; d < p.nCell; ++d) {
@@ -282,6 +310,8 @@ static void col_generate (const mb_machine* m, ColEngine& E) {
         const std::string n = nm.str();
         o << "  double " << n;
         std::ostringstream rest;
+        const size_t g0 = gi;
+        if (wp && p.ptrBits[d]) rest << " unsigned p" << c << "_" << d << " = 0u;";
         for (; gi < p.groups.size() && p.groups[gi].dst == d; ++gi) {
           const ColGroup& g = p.groups[gi];
           if (g.slot < 0) { o << " = " << source (g, c) << ";"; first = false; continue; }      // the copy comes first
@@ -290,6 +320,7 @@ static void col_generate (const mb_machine* m, ColEngine& E) {
             else rest << " " << n << " = fma (" << source (g, c) << ", " << weight (g, c) << ", " << n << ");";
           } else {
             if (first) rest << " " << n << " = " << source (g, c) << " + " << weight (g, c) << ";";
+            else if (wp) rest << " { const double cand = " << source (g, c) << " + " << weight (g, c) << "; if (" << n << " < cand) { " << n << " = cand; p" << c << "_" << d << " = " << gi - g0 << "u; } }";
             else rest << " { const double cand = " << source (g, c) << " + " << weight (g, c) << "; if (" << n << " < cand) " << n << " = cand; }";
           }
           if (first) { o << ";"; first = false; }
@@ -301,6 +332,13 @@ static void col_generate (const mb_machine* m, ColEngine& E) {
     for (int c = 0; c < C; ++c) for (int s = 0; s < p.nCell; ++s) if (p.upIdx[s] >= 0) o << "  U[" << c * p.nLU + p.upIdx[s] << "] = n" << c << "_" << s << "; \\\n";
     for (int c = 0; c + 1 < C; ++c) for (int s = 0; s < p.nCell; ++s) if (p.diagIdx[s] >= 0) o << "  Lprev[" << (c + 1) * p.nLD + p.diagIdx[s] << "] = n" << c << "_" << s << "; \\\n";
     for (int s = 0; s < p.nCell; ++s) if (p.leftIdx[s] >= 0) o << "  Lown[" << p.leftIdx[s] << "] = n" << C - 1 << "_" << s << "; \\\n";
+    if (wp)
+      for (int c = 0; c < C; ++c)
+        for (int wd = 0; wd < p.nPtrWords; ++wd) {
+          o << "  pk[" << c * p.nPtrWords + wd << "] = 0u";
+          for (int d = 0; d < p.nCell; ++d) if (p.ptrBits[d] && p.ptrWord[d] == wd) o << " | (p" << c << "_" << d << " << " << p.ptrShift[d] << ")";
+          o << "; \\\n";
+        }
     o << "\n";
   }
   o << "#define MB_COL_KEEPDIAG";
@@ -322,6 +360,7 @@ struct ColSideArgs {
   int32_t nStates, nLL, nC;
   const int32_t* carried;      // [nC] left-going slot | [nC] prefix state
   double* result;
+  unsigned short* ptr; const int64_t* ptrOff;      // max-plus with traceback: the winning entry per (row, state) of work item n at ptr + ptrOff[n]; 0xffff: none
 };
 
 __device__ __forceinline__ double col_ninf() { return __longlong_as_double (0xfff0000000000000LL); }
@@ -346,13 +385,16 @@ __global__ void __launch_bounds__(128) col_prefix_kernel (ColSideArgs A) {
     for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
     if (o == 0) cur[0] = 0.;
     const int tok = o ? y[o - 1] : -1;
+    unsigned short* won = (!SUM && A.ptr) ? A.ptr + A.ptrOff[n] + (int64_t) o * A.nStates : (unsigned short*) 0;
+    if (won) for (int s = 0; s < A.nStates; ++s) won[s] = 0xffff;
     for (int e = 0; e < A.nEnt; ++e) {
       const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
       double v;
       if (kind == CE_SILENT) v = cur[src] + A.w[e];
       else if (etok == tok) v = prev[src] + A.w[e];
       else continue;
-      cur[dst] = SUM ? col_lse (cur[dst], v) : fmax (cur[dst], v);
+      if (SUM) cur[dst] = col_lse (cur[dst], v);
+      else if (cur[dst] < v) { cur[dst] = v; if (won) won[dst] = (unsigned short) e; }      // strict '<': the first maximum stays (dpmatrix.defs.h:171-174)
     }
     double* row = bnd + (int64_t) o * brow;
     if (SUM) {      // linear values under a power-of-two frame
@@ -389,6 +431,8 @@ __global__ void __launch_bounds__(128) col_suffix_kernel (ColSideArgs A) {
     for (int j = 0; j < A.nLL; ++j) { const double v = row[j]; X[j] = SUM ? (v > 0. ? log (v) + fr : col_ninf()) : v; }
     for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
     const int tok = o ? y[o - 1] : -1;
+    unsigned short* won = (!SUM && A.ptr) ? A.ptr + A.ptrOff[n] + (int64_t) o * A.nStates : (unsigned short*) 0;
+    if (won) for (int s = 0; s < A.nStates; ++s) won[s] = 0xffff;
     for (int e = 0; e < A.nEnt; ++e) {
       const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
       double v;
@@ -396,7 +440,8 @@ __global__ void __launch_bounds__(128) col_suffix_kernel (ColSideArgs A) {
       else if (kind == CE_EXT_CUR) v = X[src] + A.w[e];
       else if (etok != tok) continue;
       else v = (kind == CE_EMIT ? prev[src] : Xprev[src]) + A.w[e];
-      cur[dst] = SUM ? col_lse (cur[dst], v) : fmax (cur[dst], v);
+      if (SUM) cur[dst] = col_lse (cur[dst], v);
+      else if (cur[dst] < v) { cur[dst] = v; if (won) won[dst] = (unsigned short) e; }
     }
     for (int s = 0; s < A.nStates; ++s) prev[s] = cur[s];
     for (int j = 0; j < A.nLL; ++j) Xprev[j] = X[j];
@@ -455,7 +500,7 @@ void col_destroy (mb_machine* m) {
   ColEngine* E = ce (m);
   if (!E) return;
   if (E->mod) rt_unload (E->mod);
-  for (void* p: { (void*) E->dTabLin, (void*) E->dTabLog, (void*) E->dPre, (void*) E->dPreW, (void*) E->dSuf, (void*) E->dSufW, (void*) E->dCarriedSlot }) if (p) cudaFree (p);
+  for (void* p: { (void*) E->dTabLin, (void*) E->dTabLog, (void*) E->dPre, (void*) E->dPreW, (void*) E->dSuf, (void*) E->dSufW, (void*) E->dCarriedSlot, (void*) E->dTbPlan }) if (p) cudaFree (p);
   delete E;
   m->col = nullptr;
 }
@@ -481,11 +526,32 @@ int col_prepare (mb_machine* m, bool hostOnly) {
   std::vector<char> cubin;
   if (rt_compile (E->source, ".col.cu", cubin, nullptr)) return 1;
   MB_CUDA (cudaSetDevice (m->device));
-  if (rt_load (cubin, &E->mod) || rt_function (E->mod, "mb_k_col_sum", &E->kSum) || rt_function (E->mod, "mb_k_col_max", &E->kMax)) return 1;
+  if (rt_load (cubin, &E->mod) || rt_function (E->mod, "mb_k_col_sum", &E->kSum) || rt_function (E->mod, "mb_k_col_max", &E->kMax)
+      || rt_function (E->mod, "mb_k_col_maxp", &E->kMaxP)) return 1;
   MB_CUDA (cudaDeviceGetAttribute (&E->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   E->smemBytes = (size_t) (p.nSlots * 32 * p.C + (E->threads / 32) * 16 * p.nLL) * 8;
-  if (rt_prepare (E->kSum, E->threads, E->smemBytes, &E->blocksPerSMSum) || rt_prepare (E->kMax, E->threads, E->smemBytes, &E->blocksPerSMMax)) return 1;
-  if (E->blocksPerSMSum < 1 || E->blocksPerSMMax < 1) { set_error ("column engine: a kernel does not fit on an SM"); return 1; }
+  if (rt_prepare (E->kSum, E->threads, E->smemBytes, &E->blocksPerSMSum) || rt_prepare (E->kMax, E->threads, E->smemBytes, &E->blocksPerSMMax)
+      || rt_prepare (E->kMaxP, E->threads, E->smemBytes, &E->blocksPerSMMaxP)) return 1;
+  if (E->blocksPerSMSum < 1 || E->blocksPerSMMax < 1 || E->blocksPerSMMaxP < 1) { set_error ("column engine: a kernel does not fit on an SM"); return 1; }
+  {      // the traceback's tables: groupStart | ptrWord | ptrShift | ptrBits | group type | source | slot | left slot -> cell state | carried -> prefix state | slotTrans | prefix entries | suffix entries
+    std::vector<int32_t> plan;
+    auto section = [&] (int q, const std::vector<int32_t>& v) { E->tbOff[q] = plan.size(); plan.insert (plan.end(), v.begin(), v.end()); };
+    std::vector<int32_t> gt, gsrc, gslot, leftCell ((size_t) p.nLL, -1), st ((size_t) p.K * p.nSlots), pe, se;
+    for (auto& g: p.groups) { gt.push_back (g.type); gsrc.push_back (g.src); gslot.push_back (g.slot); }
+    for (int c = 0; c < p.nCell; ++c) if (p.leftIdx[c] >= 0) leftCell[p.leftIdx[c]] = c;
+    for (size_t q = 0; q < st.size(); ++q) st[q] = (int32_t) p.slotTrans[q];
+    for (auto& e: p.pre) { pe.push_back (e.src); pe.push_back (e.kind); pe.push_back ((int32_t) e.trans); }
+    for (auto& e: p.suf) { se.push_back (e.src); se.push_back (e.kind); se.push_back ((int32_t) e.trans); }
+    section (0, std::vector<int32_t> (p.groupStart.begin(), p.groupStart.end()));
+    section (1, std::vector<int32_t> (p.ptrWord.begin(), p.ptrWord.end()));
+    section (2, std::vector<int32_t> (p.ptrShift.begin(), p.ptrShift.end()));
+    section (3, std::vector<int32_t> (p.ptrBits.begin(), p.ptrBits.end()));
+    section (4, gt); section (5, gsrc); section (6, gslot); section (7, leftCell);
+    section (8, std::vector<int32_t> (p.carried.begin(), p.carried.end()));
+    section (9, st); section (10, pe); section (11, se);
+    MB_CUDA (cudaMalloc (&E->dTbPlan, std::max<size_t> (plan.size(), 1) * 4));
+    MB_CUDA (cudaMemcpy (E->dTbPlan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice));
+  }
   MB_CUDA (cudaMalloc (&E->dTabLin, E->tabLin.size() * 8));
   MB_CUDA (cudaMalloc (&E->dTabLog, E->tabLog.size() * 8));
   std::vector<int32_t> pre, suf, car;
@@ -539,7 +605,8 @@ struct MBColArgsHost {      // must match struct MBColArgs in the skeleton
   double* bnd; const int64_t* bndOff;
   const double* tab;
   int32_t* flag;
-  int nStrips, K, R, pad;
+  int nStrips, K, R, bpPitch;
+  unsigned char* bp; const int64_t* bpOff;
 };
 
 // order: reads, longest first.  sums: Forward (flags set for the reads whose result must not be trusted); else Viterbi scores.
@@ -576,13 +643,14 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
     ColSideArgs S;
     S.y = b->dY; S.yOff = b->dYOff; S.order = dOrder; S.nWork = nWork; S.bnd = dBnd; S.bndOff = dOff;
     S.ent = E.dPre; S.w = E.dPreW; S.nEnt = (int32_t) p.pre.size(); S.nStates = p.nPre; S.nLL = p.nLL; S.nC = p.nC; S.carried = E.dCarriedSlot; S.result = dResult;
+    S.ptr = nullptr; S.ptrOff = nullptr;
     const unsigned sideGrid = (unsigned) ((nWork + 127) / 128);
     if (sums) col_prefix_kernel<true><<<sideGrid, 128, 0, b->stream>>> (S); else col_prefix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
     MB_CUDA (cudaGetLastError());
     MBColArgsHost A;
     A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
     A.bnd = dBnd; A.bndOff = dOff; A.tab = sums ? E.dTabLin : E.dTabLog; A.flag = dFlag;
-    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.pad = 0;
+    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.bpPitch = 0; A.bp = nullptr; A.bpOff = nullptr;
     const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * (sums ? E.blocksPerSMSum : E.blocksPerSMMax), groups));
     void* params[1] = { &A };
@@ -596,6 +664,179 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
     c0 = c1;
     if (c0 < order.size()) MB_CUDA (cudaStreamSynchronize (b->stream));      // the next chunk reuses the workspace
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Viterbi with traceback: the max-plus sweep storing every cell's pointers, then a thread per read walking them back
+// (col_walk below is the same walk on the host).  Chunks of reads whose pointers fit in memory.
+// ---------------------------------------------------------------------------------------------
+struct ColTbPlan {
+  const int32_t *groupStart, *ptrWord, *ptrShift, *ptrBits, *gType, *gSrc, *gSlot, *leftCell, *carried, *slotTrans, *preEnt, *sufEnt;
+  int32_t nCell, nC, K, nPre, nSuf, nSlots, bpBytes, bpPitch;
+};
+
+// out == nullptr: lengths only; otherwise the path is written start -> end at out[outOff[n] ..) (lenOut[n] from the first pass)
+__global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const uint8_t* __restrict__ yAll, const int64_t* __restrict__ yOff, const int64_t* __restrict__ order, int64_t nWork,
+                                      const unsigned char* __restrict__ bp, const int64_t* __restrict__ bpOff,
+                                      const unsigned short* __restrict__ sidePtr, const int64_t* __restrict__ preOff, const int64_t* __restrict__ sufOff,
+                                      const double* __restrict__ score, int64_t* __restrict__ lenOut, int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
+  const int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nWork) return;
+  const int64_t kr = order[n];
+  const uint8_t* y = yAll + yOff[kr];
+  const int64_t Lo = yOff[kr + 1] - yOff[kr];
+  const unsigned char* cells = bp + bpOff[n];
+  const unsigned short* preP = sidePtr + preOff[n];
+  const unsigned short* sufP = sidePtr + sufOff[n];
+  int64_t len = 0;
+  if (score[kr] > -INFINITY) {      // boss.cpp:831
+    const int64_t total = out ? lenOut[n] : 0;
+    int32_t* dst = out ? out + outOff[n] : nullptr;
+    int where = 2, k = p.K - 1, s = p.nSuf - 1;
+    int64_t o = Lo;
+    const int64_t limit = (Lo + 2) * ((int64_t) p.K * 4 + p.nPre + p.nSuf + p.nCell + 4);
+    for (int64_t guard = 0; guard < limit; ++guard) {
+      if (where == 0 && o == 0 && s == 0) break;
+      int32_t tr = -1;
+      if (where == 2) {
+        const int e = sufP[o * p.nSuf + s];
+        if (e == 0xffff) break;
+        const int src = p.sufEnt[3 * e], kind = p.sufEnt[3 * e + 1];
+        tr = p.sufEnt[3 * e + 2];
+        if (kind == CE_SILENT) s = src;
+        else if (kind == CE_EMIT) { s = src; --o; }
+        else { where = 1; k = p.K - 1; s = p.leftCell[src]; if (kind == CE_EXT_PREV) --o; }
+      } else if (where == 1) {
+        const int bits = p.ptrBits[s];
+        int idx = 0;
+        if (bits) {
+          const unsigned char* c = cells + o * p.bpPitch + (int64_t) k * p.bpBytes;
+          const unsigned v = p.bpBytes == 1 ? (unsigned) c[0] : p.bpBytes == 2 ? (unsigned) *(const unsigned short*) c : ((const unsigned*) c)[p.ptrWord[s]];
+          idx = (int) ((v >> p.ptrShift[s]) & ((1u << bits) - 1u));
+        }
+        const int g = p.groupStart[s] + idx;
+        if (g >= p.groupStart[s + 1]) break;
+        const int slot = p.gSlot[g], type = p.gType[g];
+        if (slot < 0) {      // the copy from the left: no transition
+          if (k == 0) { if (s >= p.nC) break; where = 0; s = p.carried[s]; }
+          else if (!bits) k = 0;      // nothing else ever enters this state (a carried state): straight to the first column
+          else --k;
+          continue;
+        }
+        const bool emit = type == CG_UP || type == CG_DIAG;
+        tr = p.slotTrans[(int64_t) k * p.nSlots + slot + (emit ? y[o - 1] - 1 : 0)];
+        if (tr < 0) break;
+        s = p.gSrc[g];
+        if (type == CG_LEFT || type == CG_DIAG) { if (k == 0) break; --k; }
+        if (emit) --o;
+      } else {
+        const int e = preP[o * p.nPre + s];
+        if (e == 0xffff) break;
+        tr = p.preEnt[3 * e + 2];
+        s = p.preEnt[3 * e];
+        if (p.preEnt[3 * e + 1] == CE_EMIT) --o;
+      }
+      if (tr >= 0) { if (dst && len < total) dst[total - 1 - len] = tr; ++len; }
+    }
+  }
+  if (!out) lenOut[n] = len;
+}
+
+// scores (dResult, by read) and paths (b->dPaths, b->pathStart / pathLen) of every read in `order`; *ms receives the device time
+int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int64_t* launches, double* msOut) {
+  ColEngine& E = *ce (m);
+  const ColProg& p = E.prog;
+  const int brow = p.nLL + 1;
+  const int64_t bpPitch = ((int64_t) p.Kpad * p.bpBytes + 7) / 8 * 8;
+  size_t freeB = 0, totalB = 0;
+  MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
+  const double budget = std::min (0.6 * (double) freeB, (double) m->opt.get ("col_bp_budget_mb", 1 << 20) * 1048576.);
+  const int warps = E.threads / 32;
+  int64_t packed = 0;
+  double ms = 0;
+  ColTbPlan T;
+  const int32_t* base = E.dTbPlan;
+  T.groupStart = base + E.tbOff[0]; T.ptrWord = base + E.tbOff[1]; T.ptrShift = base + E.tbOff[2]; T.ptrBits = base + E.tbOff[3];
+  T.gType = base + E.tbOff[4]; T.gSrc = base + E.tbOff[5]; T.gSlot = base + E.tbOff[6]; T.leftCell = base + E.tbOff[7]; T.carried = base + E.tbOff[8];
+  T.slotTrans = base + E.tbOff[9]; T.preEnt = base + E.tbOff[10]; T.sufEnt = base + E.tbOff[11];
+  T.nCell = p.nCell; T.nC = p.nC; T.K = p.K; T.nPre = p.nPre; T.nSuf = p.nSuf; T.nSlots = p.nSlots; T.bpBytes = p.bpBytes; T.bpPitch = (int32_t) bpPitch;
+  for (size_t c0 = 0; c0 < order.size();) {
+    std::vector<int64_t> off, bpOff, preOff, sufOff;
+    double doubles = 0, bpBytes = 0, sideShorts = 0;
+    size_t c1 = c0;
+    while (c1 < order.size()) {
+      const int64_t k = order[c1];
+      const double rows = (double) (b->yOff[k + 1] - b->yOff[k] + 1);
+      const double need = rows * (brow * 8 + bpPitch + (p.nPre + p.nSuf) * 2 + 16);
+      if (need > budget) { set_error ("column engine: one read's Viterbi pointers need more device memory than is free"); return 1; }
+      if (c1 > c0 && doubles * 8 + bpBytes + sideShorts * 2 + need > budget) break;
+      off.push_back ((int64_t) doubles); bpOff.push_back ((int64_t) bpBytes);
+      preOff.push_back ((int64_t) sideShorts); sufOff.push_back ((int64_t) (sideShorts + rows * p.nPre));
+      doubles += rows * brow; bpBytes += rows * (double) bpPitch; sideShorts += rows * (p.nPre + p.nSuf);
+      ++c1;
+    }
+    const int64_t nWork = (int64_t) (c1 - c0);
+    b->wsOrderHoldsFull = false;
+    int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, (size_t) nWork * 8);
+    int64_t* dOffs = (int64_t*) ws_reserve (b, WS_ITEMBND, (size_t) nWork * 8 * 4);      // bnd | bp | prefix | suffix offsets
+    double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) doubles * 8);
+    unsigned char* dBp = (unsigned char*) ws_reserve (b, WS_TB, (size_t) bpBytes + 8);
+    unsigned short* dSide = (unsigned short*) ws_reserve (b, WS_PATHTMP, (size_t) sideShorts * 2 + 8);
+    unsigned long long* dCounter = (unsigned long long*) ws_reserve (b, WS_COUNTER, 8);
+    int64_t* dLen = (int64_t*) ws_reserve (b, WS_LEN, (size_t) nWork * 8);
+    int64_t* dOutOff = (int64_t*) ws_reserve (b, WS_OUTOFF, (size_t) nWork * 8);
+    if (!dOrder || !dOffs || !dBnd || !dBp || !dSide || !dCounter || !dLen || !dOutOff) return 1;
+    MB_CUDA (cudaMemcpyAsync (dOrder, order.data() + c0, (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOffs, off.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOffs + nWork, bpOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOffs + 2 * nWork, preOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemcpyAsync (dOffs + 3 * nWork, sufOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
+    if (timing_begin (b)) return 1;
+    ColSideArgs S;
+    S.y = b->dY; S.yOff = b->dYOff; S.order = dOrder; S.nWork = nWork; S.bnd = dBnd; S.bndOff = dOffs;
+    S.ent = E.dPre; S.w = E.dPreW; S.nEnt = (int32_t) p.pre.size(); S.nStates = p.nPre; S.nLL = p.nLL; S.nC = p.nC; S.carried = E.dCarriedSlot; S.result = dResult;
+    S.ptr = dSide; S.ptrOff = dOffs + 2 * nWork;
+    const unsigned sideGrid = (unsigned) ((nWork + 127) / 128);
+    col_prefix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
+    MB_CUDA (cudaGetLastError());
+    MBColArgsHost A;
+    A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
+    A.bnd = dBnd; A.bndOff = dOffs; A.tab = E.dTabLog; A.flag = nullptr;
+    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.bpPitch = (int) bpPitch; A.bp = dBp; A.bpOff = dOffs + nWork;
+    const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
+    const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * E.blocksPerSMMaxP, groups));
+    void* params[1] = { &A };
+    if (rt_launch (E.kMaxP, (unsigned) grid, (unsigned) E.threads, E.smemBytes, b->stream, params)) return 1;
+    S.ent = E.dSuf; S.w = E.dSufW; S.nEnt = (int32_t) p.suf.size(); S.nStates = p.nSuf; S.ptrOff = dOffs + 3 * nWork;
+    col_suffix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
+    MB_CUDA (cudaGetLastError());
+    const unsigned tbGrid = (unsigned) ((nWork + 63) / 64);
+    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dSide, dOffs + 2 * nWork, dOffs + 3 * nWork, dResult, dLen, nullptr, nullptr);
+    MB_CUDA (cudaGetLastError());
+    std::vector<int64_t> len ((size_t) nWork), outOff ((size_t) nWork);
+    MB_CUDA (cudaMemcpyAsync (len.data(), dLen, (size_t) nWork * 8, cudaMemcpyDeviceToHost, b->stream));
+    MB_CUDA (cudaStreamSynchronize (b->stream));
+    for (int64_t q = 0; q < nWork; ++q) {
+      const int64_t k = order[c0 + q];
+      outOff[q] = packed;
+      b->pathStart[k] = packed;
+      b->pathLen[k] = len[q];
+      packed += len[q];
+    }
+    if (paths_reserve (b, packed)) return 1;
+    MB_CUDA (cudaMemcpyAsync (dOutOff, outOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dSide, dOffs + 2 * nWork, dOffs + 3 * nWork, dResult, dLen, b->dPaths, dOutOff);
+    MB_CUDA (cudaGetLastError());
+    if (launches) *launches += 5;
+    if (timing_end (b, 5)) return 1;
+    ms += b->lastMs;
+    if (m->opt.get ("verbose", 0))
+      fprintf (stderr, "column engine: Viterbi with traceback, %lld reads, %d B of pointers per cell, %.1f MB of pointers, %.1f MB of boundary rows\n", (long long) nWork, p.bpBytes, bpBytes / 1e6, doubles * 8 / 1e6);
+    c0 = c1;
+  }
+  if (msOut) *msOut = ms;
   return 0;
 }
 

@@ -26,6 +26,8 @@
 // steps (as MB_LANE_FRAMES of mb_jit_skeleton.h: the left neighbour's values enter through 2^(its frame - mine),
 // boundary rows carry their frame; a spread above 2^700 or a frame more than 2^900 away flags the read for the
 // lane engine's log-domain sweep).  MODE 2: max-plus in the log domain (Viterbi scores; FP64 add + compare, exact).
+// MODE 1: the same with every cell's pointers stored -- per cell state the index of the winning candidate among the
+// state's groups, packed into MB_BPBYTES bytes -- for col_traceback_kernel (mb_col.cu).
 #ifndef MB_COL_SKELETON_H
 #define MB_COL_SKELETON_H
 
@@ -40,7 +42,8 @@ struct MBColArgs {
   double* bnd; const int64_t* bndOff;      // work item n: (Lo + 1) rows of MB_BROW doubles at bnd + bndOff[n]
   const double* tab;                       // [strip][slot][column of the lane][lane] weights
   int32_t* flag;
-  int nStrips, K, R, pad;
+  int nStrips, K, R, bpPitch;              // bpPitch: bytes per row of a read's pointers (MODE 1)
+  unsigned char* bp; const int64_t* bpOff; // MODE 1: the pointers of work item n's cell (row, column) at bp + bpOff[n] + row * bpPitch + column * MB_BPBYTES
 };
 
 __device__ __forceinline__ double mb_pow2 (int d) { return __hiloint2double ((1023 + d) << 20, 0); }
@@ -87,6 +90,7 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
         const int Lo = (int) (A.yOff[k + 1] - y0);
         const uint8_t* y = A.y + y0;
         double* bnd = A.bnd + A.bndOff[w];
+        unsigned char* bp = MODE == 1 ? A.bp + A.bpOff[w] + (int64_t) col * MB_BPBYTES : (unsigned char*) 0;
         int suspect = 0;
 
         double U[MB_NUREG > 0 ? MB_NUREG : 1];      // my columns' last cells: the sources of the groups that consume a token and stay in the column
@@ -192,7 +196,21 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
           }
           if (r >= 0 && r <= Lo && inCol) {
             if (LIN) { MB_COL_CELL_LIN }
-            else { MB_COL_CELL_MAX }
+            else if (MODE == 2) { MB_COL_CELL_MAX }
+            else {
+              unsigned pk[MB_COL_C * MB_NPW];
+              MB_COL_CELL_MAXP
+              unsigned char* dstp = bp + (int64_t) r * A.bpPitch;
+#pragma unroll
+              for (int c = 0; c < MB_COL_C; ++c) {
+                if (MB_BPBYTES == 1) dstp[c] = (unsigned char) pk[c];
+                else if (MB_BPBYTES == 2) ((unsigned short*) dstp)[c] = (unsigned short) pk[c];
+                else {
+#pragma unroll
+                  for (int q = 0; q < MB_NPW; ++q) ((unsigned*) dstp)[c * MB_NPW + q] = pk[c * MB_NPW + q];
+                }
+              }
+            }
             if (lane == outLane) {
               double* dst = bnd + (int64_t) r * MB_BROW;
 #pragma unroll
@@ -212,6 +230,7 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
 
 extern "C" __global__ void __launch_bounds__(MB_COL_THREADS, MB_COL_MINBLOCKS) mb_k_col_sum (const __grid_constant__ MBColArgs A) { mb_col_run<0> (A); }
 extern "C" __global__ void __launch_bounds__(MB_COL_THREADS, MB_COL_MINBLOCKS) mb_k_col_max (const __grid_constant__ MBColArgs A) { mb_col_run<2> (A); }
+extern "C" __global__ void __launch_bounds__(MB_COL_THREADS, MB_COL_MINBLOCKS) mb_k_col_maxp (const __grid_constant__ MBColArgs A) { mb_col_run<1> (A); }
 )MBSRC";
 
 #endif

@@ -195,6 +195,7 @@ void col_destroy (mb_machine* m);
 int col_update_weights (mb_machine* m);
 bool col_usable (const mb_machine* m, bool sums);
 int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, bool sums, double* dResult, int32_t* dFlag, int64_t* launches);
+int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, double* dResult, int64_t* launches, double* ms);      // scores + paths into the batch
 int col_compile_check (const mb_machine* m, std::string* log);
 int col_info (const mb_machine* m, int32_t* info);      // { usable, period, first state, columns, prefix, suffix, carried, accumulators, groups, weight slots, left-going, up }
 int col_emulate (const mb_machine* m, const uint8_t* y, int64_t Lo, int op, double* result, std::vector<int64_t>* path);      // op 0 log-sum-exp, 1 max (path: the traceback, may be null)

@@ -1282,6 +1282,18 @@ int lane_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
     return 0;
   }
+  if (col_usable (m, false) && !m->opt.get ("col_no_traceback", 0)) {      // periodic generators: the column engine's sweep with pointers and its own walk back
+    b->pathStart.assign ((size_t) b->nPairs, 0);
+    b->pathLen.assign ((size_t) b->nPairs, 0);
+    int64_t launches = 0;
+    double ms = 0;
+    if (col_viterbi_paths (m, b, order, dRes.as<double>(), &launches, &ms)) return 1;
+    b->lastMs = ms;
+    b->lastLaunches = launches;
+    MB_CUDA (cudaMemcpy (score, dRes.p, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < b->nPairs; ++k) pathLen[k] = b->pathLen[k];
+    return 0;
+  }
   // chunks of whole tasks (LPT reads) whose back-pointers, (maxLo+1) * S * LPT bytes or half-words per task, fit in free memory
   const int R = lane_reads_per_lane (m, h, b->nPairs, L_MAX), LPT = 32 * R;
   size_t freeB = 0, totalB = 0;

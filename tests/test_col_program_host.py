@@ -44,9 +44,9 @@ def test_column_kernel_compiles():
     from machineboss_b200 import capi
     fm = _generator("hmmer_pf00516")
     _, info, log = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0, compile_log=True)
-    assert info[0] == 1 and "mb_k_col_sum" in log and "mb_k_col_max" in log
+    assert info[0] == 1 and "mb_k_col_sum" in log and "mb_k_col_max" in log and "mb_k_col_maxp" in log
     spills = [l for l in log.splitlines() if "spill stores" in l]
-    assert len(spills) == 2 and all(" 0 bytes spill stores" in l for l in spills), log
+    assert len(spills) == 3 and all(" 0 bytes spill stores" in l for l in spills), log
 
 
 @pytest.mark.parametrize("name", ["unitindel", "counter_xxx", "dnapsw_small"])

@@ -456,7 +456,7 @@ def test_lane_engine_config5_read_lengths(reads_per_lane):
             assert paths[k].tolist() == p.tolist(), (name, k)
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(col_c=1), dict(col_c=3, col_minblocks=1), dict(col_r=2, col_bnd_budget_mb=1), dict(col_threads=64, col_sil_regs=0)])
+@pytest.mark.parametrize("opts", [dict(), dict(col_c=1), dict(col_c=3, col_minblocks=1), dict(col_r=2, col_bnd_budget_mb=1, col_bp_budget_mb=4), dict(col_threads=64, col_sil_regs=0)])
 def test_column_engine_profile_reads(opts):
     """Periodic generators (PF00516 and PF00516 => protpsw) through the column engine (mb_col.cu: column = profile node,
     row = read position): read lengths around the strip-staging block (0, 1, 15 - 17, 31 - 33) and config 5's own 50 - 500,
@@ -483,16 +483,21 @@ def test_column_engine_profile_reads(opts):
         sc_lane = capi.viterbi(lane, b, paths=False)
         assert np.array_equal(sc, sc_lane)
         np.testing.assert_allclose(ll, ll_lane, rtol=1e-10)
+        sc2, paths = capi.viterbi(m, b)      # with paths: the sweep that stores pointers, and the walk back over them
+        assert np.array_equal(sc2, sc)
+        launches = b.last_kernel_ms()[1]
+        assert launches >= 5 and launches % 5 == 0, launches      # prefix, strips, suffix, two traceback passes per chunk
+        if "col_bp_budget_mb" in opts:
+            assert launches >= 10
         for k in sorted(set(list(range(12)) + [n_reads - 1] + list(range(14, n_reads, 31)))):
             x, y = pairs[k]
             f = orc.forward(x, y)
             assert forward_agrees(fm, x, y, ll[k], f), (name, k, ll[k], f)
-            v, _ = orc.viterbi(x, y)
+            v, p = orc.viterbi(x, y)
             assert sc[k] == v, (name, k, sc[k], v)
-        sc2, paths = capi.viterbi(m, b)      # with paths: the lane engine's sweep and traceback
-        assert np.array_equal(sc2, sc)
-        v, p = orc.viterbi(*pairs[10])
-        assert paths[10].tolist() == p.tolist()
+            assert paths[k].tolist() == p.tolist(), (name, k)
+        _, paths_lane = capi.viterbi(lane, b)
+        assert all(np.array_equal(a, c) for a, c in zip(paths, paths_lane))
 
 
 def test_column_engine_hands_impossible_reads_to_the_log_domain():
@@ -513,6 +518,9 @@ def test_column_engine_hands_impossible_reads_to_the_log_domain():
     b = capi.Batch(pairs)
     ll = capi.forward(m, b)
     sc = capi.viterbi(m, b, paths=False)
+    sc_p, paths = capi.viterbi(m, b)
+    assert np.array_equal(sc, sc_p)
+    assert all((len(paths[k]) == 0) == bool(np.isinf(sc[k])) for k in range(len(pairs)))
     orc = Oracle(fm2)
     n_inf = 0
     for k, (x, y) in enumerate(pairs):
