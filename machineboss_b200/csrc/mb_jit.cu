@@ -867,7 +867,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   while (J.C * J.tbBytes > 16) J.C /= 2;
   J.CV = J.C; J.minBlocksV = J.minBlocks;
   if (m->S <= 8 && J.C == 4 && 8 * J.tbBytes <= 16) { J.CV = 8; J.minBlocksV = 3; }
-  if (m->opt.has ("jit_cv")) J.CV = std::max (1, std::min (8, m->opt.get ("jit_cv", 8)));
+  if (m->opt.has ("jit_cv")) J.CV = std::max (1, std::min (16, m->opt.get ("jit_cv", 8)));
   while (J.CV * J.tbBytes > 16) J.CV /= 2;
   if (m->opt.has ("jit_minblocks_v")) J.minBlocksV = std::max (1, std::min (16, m->opt.get ("jit_minblocks_v", 3)));
   J.minBlocksLinV = std::max (J.minBlocksV, 4);
