@@ -237,6 +237,13 @@ struct JitEngine {
   std::vector<char> silParamLinN;         // MBSilN { f[], b[], originF, originB, resLogF, resLogB }
   bool normOK = false;                    // every unit group's weight is usable: the normalised linear kernels may run
   std::string sourceV;
+  // FITTED strip widths: when every pair of a batch fits one strip of 32 * Cf columns for a Cf between the two built-in widths
+  // (or just above the wider one), a score module with MB_C = Cf sweeps a third fewer cells than the built-in ones
+  // (300 aa proteins: 1 strip of 320 columns against 3 of 128 or 2 of 256).  Compiled the first time a batch asks for it,
+  // at most kMaxFitModules per machine.
+  struct FitModule { int C = 0; CUmodule mod = nullptr; CUfunction k[4] = { nullptr, nullptr, nullptr, nullptr }; int blocksPerSM[4] = { 1, 1, 1, 1 }; };      // viterbi, forward_lin, backward_lin, viterbi_score
+  std::vector<FitModule> fit;
+  std::vector<int> fitFailed;
   // split mode (strips as work items): the score module once more with MB_SPLIT 1, compiled when a call first needs it
   std::string sourceS;
   CUmodule modS = nullptr;
@@ -688,20 +695,69 @@ static int ensure_split_module (mb_machine* m, JitEngine& J) {
   return 0;
 }
 
-// Columns per lane for a score-only call over `pairs`: CV unless the narrower strips of C waste so much
-// less padding that they win.  Cost per cell relative to C (measured, 10 000 dnapsw pairs of 1 kb):
-// Viterbi with back-pointers 0.60, linear sweeps 0.87; Viterbi scores only 0.85 (100 000 protpsw pairs of 300 aa: 17.0 ms in
-// 3 strips of 128 against 19.9 in 2 of 256, with back-pointers 27.9 against 24.0).
-static bool use_narrow (const mb_machine* m, const JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, int kind /* 0 sums, 1 Viterbi + pointers, 2 Viterbi scores */) {
-  if (!J.modV) return false;
-  if (m->opt.has ("jit_narrow")) return m->opt.get ("jit_narrow", 0) != 0;
-  double cellsN = 0, cellsW = 0;
-  for (int64_t k: pairs) {
-    const double Li = (double) (b->xOff[k + 1] - b->xOff[k]), rows = (double) (b->yOff[k + 1] - b->yOff[k]) + 32;
-    cellsN += std::ceil ((Li + 1) / (32.0 * J.C)) * 32.0 * J.C * rows;
-    cellsW += std::ceil ((Li + 1) / (32.0 * J.CV)) * 32.0 * J.CV * rows;
+static std::string module_source (const mb_machine* m, JitEngine& J, int passC, int pass, int passMinBlocks, int passMinBlocksLin);
+
+// A fitted score module (MB_C = C), on first use.  Returns its index in J.fit, or -1 when it cannot be built (the caller
+// falls back to a built-in width).
+static const int kMaxFitModules = 3;
+static int ensure_fit_module (mb_machine* m, JitEngine& J, int C) {
+  for (size_t q = 0; q < J.fit.size(); ++q) if (J.fit[q].C == C) return (int) q;
+  for (int c: J.fitFailed) if (c == C) return -1;
+  if ((int) J.fit.size() >= kMaxFitModules) return -1;
+  JitEngine::FitModule F;
+  F.C = C;
+  std::vector<char> cubin;
+  // wider lanes need more registers: the sums at 3 CTAs per SM (168 registers) as the Viterbi kernels
+  const std::string src = module_source (m, J, C, 1, J.minBlocksV, C > 8 ? std::min (J.minBlocksLinV, 3) : J.minBlocksLinV);
+  bool ok = !nvrtc_compile (src, ".fit.cu", cubin, nullptr) && cu_ok (g_drv.ModuleLoadData (&F.mod, cubin.data()), "cuModuleLoadData");
+  const char* names[4] = { "mb_k_viterbi", "mb_k_forward_lin", "mb_k_backward_lin", "mb_k_viterbi_score" };
+  const int qOf[4] = { 2, 5, 6, 9 };
+  for (int q = 0; q < 4 && ok; ++q) {
+    ok = cu_ok (g_drv.ModuleGetFunction (&F.k[q], F.mod, names[q]), "cuModuleGetFunction")
+      && cu_ok (g_drv.FuncSetAttribute (F.k[q], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int) J.smemBytes[qOf[q]]), "cuFuncSetAttribute");
+    int nb = 0;
+    ok = ok && cu_ok (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor (&nb, F.k[q], J.threads, J.smemBytes[qOf[q]]), "occupancy");
+    F.blocksPerSM[q] = std::max (1, nb);
   }
-  return cellsN < (kind == 1 ? 0.60 : kind == 2 ? 0.85 : 0.87) * cellsW;
+  if (!ok) { if (F.mod && g_drv.ModuleUnload) g_drv.ModuleUnload (F.mod); J.fitFailed.push_back (C); return -1; }
+  J.fit.push_back (F);
+  if (m->opt.get ("verbose", 0)) fprintf (stderr, "[mb_jit] score module fitted to the batch compiled: %d columns per lane (strips of %d)\n", C, 32 * C);
+  return (int) J.fit.size() - 1;
+}
+
+// Columns per lane for a score-only call over `pairs`: the built-in C (narrow) or CV (wide), or a width FITTED to the batch.
+// Modelled cost = lane-cells swept (strips * 32 C * (Lo + 32) per pair) * cost per lane-cell, the latter measured on B200
+// (100 000 protpsw pairs of 300 aa; ps per lane-cell at C = 4 / 8 / 10): sums 1.16 / 0.92 / 0.97, Viterbi scores 1.33 / 1.17 /
+// 1.19, Viterbi with pointers 2.19 / 1.41 / 1.5.  A fitted module costs a compilation (about a second), so it must promise
+// 12 % on a batch of at least 256 pairs.  kind: 0 sums, 1 Viterbi + pointers, 2 Viterbi scores.
+static int choose_width (mb_machine* m, JitEngine& J, const mb_batch* b, const std::vector<int64_t>& pairs, int kind) {
+  if (!J.modV) return J.C;
+  if (m->opt.has ("jit_narrow")) return m->opt.get ("jit_narrow", 0) ? J.C : J.CV;
+  static const double c4[3] = { 1.16, 2.19, 1.33 }, c8[3] = { 0.92, 1.41, 1.17 };
+  auto perCell = [&] (int C) {      // interpolated in 1 / C between the built-in widths, 5 % above the wide one beyond it
+    if (C >= J.CV) return C == J.CV ? c8[kind] : 1.05 * c8[kind];
+    if (C <= J.C) return c4[kind];
+    const double t = (1. / C - 1. / J.CV) / (1. / J.C - 1. / J.CV);
+    return c8[kind] + t * (c4[kind] - c8[kind]);
+  };
+  int64_t maxLi = 0;
+  for (int64_t k: pairs) maxLi = std::max (maxLi, b->xOff[k + 1] - b->xOff[k]);
+  auto cost = [&] (int C) {
+    double cells = 0;
+    for (int64_t k: pairs) {
+      const double Li = (double) (b->xOff[k + 1] - b->xOff[k]), rows = (double) (b->yOff[k + 1] - b->yOff[k]) + 32;
+      cells += std::ceil ((Li + 1) / (32.0 * C)) * 32.0 * C * rows;
+    }
+    return cells * perCell (C);
+  };
+  const double costN = cost (J.C), costW = cost (J.CV);
+  int best = costN < costW ? J.C : J.CV;
+  const double bestBuiltin = std::min (costN, costW);
+  const int forced = m->opt.get ("jit_fit_c", -1);      // > 0: this fitted width whenever it holds the batch in one strip; 0: never fit
+  const int Cf = forced > 0 ? forced : (int) ((maxLi + 1 + 31) / 32);
+  if (forced != 0 && Cf >= 2 && Cf <= 12 && Cf != J.C && Cf != J.CV && Cf * J.tbBytes <= 16 && (int64_t) 32 * Cf >= maxLi + 1
+      && (forced > 0 || (pairs.size() >= 256 && cost (Cf) < 0.88 * bestBuiltin)) && ensure_fit_module (m, J, Cf) >= 0) best = Cf;
+  return best;
 }
 
 // ---- the same run-time compilation plumbing for the other generated engine (mb_big.cu) ----
@@ -847,7 +903,10 @@ struct TbPlan {
   const int32_t* bits;
   const int32_t* idTab;
   int32_t S, nOut, tbBytes, W;
+  int32_t padC, padSlots;      // fitted strip widths: column i's pointers sit at slot (i / padC) * padSlots + i % padC of the row (padC == 0: at slot i)
 };
+
+static std::string module_source (const mb_machine* m, JitEngine& J, int passC, int pass, int passMinBlocks, int passMinBlocksLin);
 
 static void generate (const mb_machine* m, JitEngine& J) {
   build_program (m, true, J.fwd);
@@ -884,8 +943,14 @@ static void generate (const mb_machine* m, JitEngine& J) {
     if (n) { J.ctxBase[k] = J.nCtx; J.nCtx += n; }
   }
 
-  for (int pass = 0; pass < (J.CV != J.C ? 2 : 1); ++pass) {
-  const int passC = pass ? J.CV : J.C, passMinBlocks = pass ? J.minBlocksV : J.minBlocks;
+  J.source = module_source (m, J, J.C, 0, J.minBlocks, J.minBlocksLin);
+  J.sourceV = J.CV != J.C ? module_source (m, J, J.CV, 1, J.minBlocksV, J.minBlocksLinV) : std::string();
+  J.sourceS = "#define MB_SPLIT 1\n" + (J.sourceV.empty() ? J.source : J.sourceV);
+}
+
+// One module's source: every kernel at passC columns per lane.  pass 0: the first module (E-step and log-domain kernels, and
+// the narrow score kernels); pass 1: the score module (frame per lane, steady loop unrolled).
+static std::string module_source (const mb_machine* m, JitEngine& J, int passC, int pass, int passMinBlocks, int passMinBlocksLin) {
   std::ostringstream o;
   o << "// generated by machineboss_b200 (mb_jit.cu) for a machine with " << m->S << " states, " << m->T << " transitions\n";
   if (pass) o << "#define MB_SCORE_MODULE 1\n#define MB_LANE_FRAMES 1\n";
@@ -898,8 +963,9 @@ static void generate (const mb_machine* m, JitEngine& J) {
   for (auto& sl: J.fwd.slots) if (sl.type != T_SILENT) liveF |= 1ull << sl.other;
   for (auto& sl: J.bwd.slots) if (sl.type != T_SILENT) liveB |= 1ull << sl.other;
   o << "#define MB_LIVE_F " << liveF << "ull\n#define MB_LIVE_B " << liveB << "ull\n";
-  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#ifdef MB_SPLIT\n#define MB_MINBLOCKS_LIN " << std::min (2, pass ? J.minBlocksLinV : J.minBlocksLin) << "      // (the split-mode sums spill below 170 registers)\n#else\n#define MB_MINBLOCKS_LIN "
-    << (pass ? J.minBlocksLinV : J.minBlocksLin) << "\n#endif\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
+  { const int cb = passC * J.tbBytes; if (cb != 1 && cb != 2 && cb != 4 && cb != 8 && cb != 16) o << "#define MB_TBPAD " << 16 / J.tbBytes << "\n"; }
+  o << "#define MB_MINBLOCKS " << passMinBlocks << "\n#ifdef MB_SPLIT\n#define MB_MINBLOCKS_LIN " << std::min (2, passMinBlocksLin) << "      // (the split-mode sums spill below 170 registers)\n#else\n#define MB_MINBLOCKS_LIN "
+    << passMinBlocksLin << "\n#endif\n#define MB_MINBLOCKS_CNT " << J.minBlocksCnt << "\n";
   o << "#define MB_NSIL_B " << J.bwd.nSil << "\n#define MB_NCTX " << std::max (J.nCtx, 1) << "\n";
   o << "typedef " << (J.tbBytes <= 4 ? "unsigned" : "unsigned long long") << " mb_tbword;\n";
   o << "struct MBSil { double f[" << std::max (J.fwd.nSil, 1) << "]; double b[" << std::max (J.bwd.nSil, 1) << "]; };\n";
@@ -936,9 +1002,7 @@ static void generate (const mb_machine* m, JitEngine& J) {
   gen_cell_counts_lin (o, m, J);
   gen_fstore_lin (o, m, J);
   o << kJitSkeleton;
-  (pass ? J.sourceV : J.source) = o.str();
-  }
-  J.sourceS = "#define MB_SPLIT 1\n" + (J.sourceV.empty() ? J.source : J.sourceV);
+  return o.str();
 }
 
 // Diagnostic used by the CPU tests: the tables the score module's kernels read, as the host prepares them for
@@ -1029,6 +1093,7 @@ void jit_destroy (mb_machine* m) {
   if (J->mod && g_drv.ModuleUnload) g_drv.ModuleUnload (J->mod);
   if (J->modV && g_drv.ModuleUnload) g_drv.ModuleUnload (J->modV);
   if (J->modS && g_drv.ModuleUnload) g_drv.ModuleUnload (J->modS);
+  for (auto& f: J->fit) if (f.mod && g_drv.ModuleUnload) g_drv.ModuleUnload (f.mod);
   if (J->dEmitF) cudaFree (J->dEmitF);
   if (J->dEmitB) cudaFree (J->dEmitB);
   if (J->dEmitFLin) cudaFree (J->dEmitFLin);
@@ -1095,9 +1160,16 @@ struct CountArgs { double* F = nullptr; const int64_t* fOff = nullptr; const dou
                    unsigned* F32 = nullptr; const int64_t* f32Off = nullptr; int32_t* ef = nullptr; const int64_t* efOff = nullptr; };
 
 static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int64_t>& order, double* dResult, uint8_t* dTb, const int64_t* dTbOff,
-                   const CountArgs& ca = CountArgs(), bool narrow = false) {
+                   const CountArgs& ca = CountArgs(), int useC = 0) {      // useC: columns per lane of a score kernel (0: the default module's)
   JitEngine& J = *(JitEngine*) m->jit;
   const bool scoreKernel = which == 2 || which == 5 || which == 6 || which == 9;
+  bool narrow = useC == J.C && useC != J.CV;
+  const int scoreIdx = which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3;
+  const JitEngine::FitModule* fitM = nullptr;
+  if (scoreKernel && useC && useC != J.C && useC != J.CV) {
+    for (auto& f: J.fit) if (f.C == useC) fitM = &f;
+    if (!fitM) { set_error ("jit engine: no module fitted to " + std::to_string (useC) + " columns per lane"); return 1; }
+  }
   if ((which == 5 || which == 6) && !J.normOK) { set_error ("jit engine: the normalised linear sweep was asked for a machine whose unit weights cannot be divided out"); return 1; }
   narrow = narrow && J.modV && scoreKernel;
   const bool rowTab = scoreKernel;      // the score kernels of both modules read the row-layout tables
@@ -1108,13 +1180,14 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   int64_t maxLo = 0;
   for (int64_t k: order) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warpsPerBlock = J.threads / 32;
-  int64_t grid = (int64_t) J.numSMs * (narrow ? J.blocksPerSMN[which == 2 ? 0 : which == 5 ? 1 : which == 6 ? 2 : 3] : J.blocksPerSM[slot]);
+  int64_t grid = (int64_t) J.numSMs * (fitM ? fitM->blocksPerSM[scoreIdx] : narrow ? J.blocksPerSMN[scoreIdx] : J.blocksPerSM[slot]);
+  if (fitM) fn = fitM->k[scoreIdx];
   // SPLIT mode: with fewer pairs than resident warps the strips of a pair become work items of their own, and the warps
   // that claim them run as a pipeline down the strips (see MBArgs::items in the skeleton)
   const int W = 32 * (scoreKernel && J.modV ? J.CV : J.C);      // (the split module has the score module's columns per lane)
   bool split = false;
   std::vector<int64_t> items, itemBnd;
-  if (scoreKernel && !narrow && m->opt.get ("jit_split", -1) != 0) {      // (the caller laid out its back-pointers for the strips it chose: narrow strips are never split)
+  if (scoreKernel && !narrow && !fitM && m->opt.get ("jit_split", -1) != 0) {      // (the caller laid out its back-pointers for the strips it chose: narrow strips are never split)
     int64_t nItems = 0;
     for (int64_t k: order) nItems += (b->xOff[k + 1] - b->xOff[k] + W) / W;
     split = nItems > (int64_t) order.size() && (m->opt.get ("jit_split", -1) > 0 || (double) order.size() < 0.75 * (double) (grid * warpsPerBlock));
@@ -1173,7 +1246,7 @@ static int launch (mb_machine* m, mb_batch* b, int which, const std::vector<int6
   A.F = ca.F; A.fOff = ca.fOff; A.ll = ca.ll; A.counts = ca.counts; A.idTabB = J.dIdTabB;
   if (m->opt.get ("verbose", 0))
     fprintf (stderr, "[mb_jit] kernel %d%s grid %lld x %d threads, %zu B smem, %d CTAs/SM, C=%d, %zu pairs, bnd %.1f MB\n", which, split ? " (split: strips as work items)" : rowTab && lin ? " (normalised)" : "", (long long) grid, J.threads,
-             J.smemBytes[which], J.blocksPerSM[slot], ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
+             J.smemBytes[which], J.blocksPerSM[slot], fitM ? fitM->C : ((which == 2 || which == 5 || which == 6 || which == 9) && !narrow) ? J.CV : J.C, order.size(), (double) (grid * warpsPerBlock * bndStride) * 8 / 1e6);
   void* params[2] = { (rowTab && lin) ? (void*) J.silParamLinN.data() : lin ? (void*) J.silParamLin.data() : (void*) J.silParam.data(), (void*) &A };
   if (!cu_ok (g_drv.LaunchKernel (fn, (unsigned) grid, 1, 1, (unsigned) J.threads, 1, 1, (unsigned) J.smemBytes[which], (CUstream) b->stream, params, nullptr), "cuLaunchKernel")) return 1;
   return 0;
@@ -1195,7 +1268,7 @@ int jit_forward (mb_machine* m, mb_batch* b, double* loglike, bool backward) {
     if (!dFlag) return 1;
     CountArgs ca;
     ca.flag = dFlag;
-    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, use_narrow (m, J, b, order, 0))) return 1;
+    if (launch (m, b, backward ? 6 : 5, order, dRes, nullptr, nullptr, ca, choose_width (m, J, b, order, 0))) return 1;
     std::vector<int32_t> flag ((size_t) b->nPairs);
     MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
     MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, (size_t) b->nPairs * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -1251,7 +1324,7 @@ __global__ void __launch_bounds__(64) jit_traceback_kernel (TbPlan p, int nSlots
   if (slot >= nPairsHere) return;
   const int64_t k = pairs[slot];
   const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
-  const int64_t pitch = ((Li + p.W) / p.W) * p.W;
+  const int64_t pitch = p.padC ? ((Li + p.W) / p.W) * 32 * p.padSlots : ((Li + p.W) / p.W) * p.W;
   const uint8_t* base = tb + tbOff[k];
   uint8_t* out = tmp + tmpOff[slot + 1];     // one past the end of this pair's slot
   int64_t n = 0;
@@ -1259,7 +1332,8 @@ __global__ void __launch_bounds__(64) jit_traceback_kernel (TbPlan p, int nSlots
     int64_t i = Li, o = Lo;
     int s = p.S - 1;
     auto fetch = [&] (int64_t ii, int64_t oo) {
-      const uint8_t* wp = base + (oo * pitch + ii) * p.tbBytes;
+      const int64_t at = p.padC ? (ii / p.padC) * p.padSlots + ii % p.padC : ii;
+      const uint8_t* wp = base + (oo * pitch + at) * p.tbBytes;
       if (ii >= 8 && oo >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - (8 * pitch + 8) * p.tbBytes));
       unsigned long long w = 0;
       for (int q = 0; q < p.tbBytes; ++q) w |= (unsigned long long) wp[q] << (8 * q);
@@ -1359,28 +1433,32 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   b->pathLen.clear();
   if (b->nPairs == 0) return 0;
   const bool trace = pathLen != nullptr;
-  const bool narrow = use_narrow (m, J, b, full_order (b), trace ? 1 : 2);
+  const int useC = choose_width (m, J, b, full_order (b), trace ? 1 : 2);
   if (!trace) {      // scores only (boss -V): no back-pointers, no scratch beyond the strip boundaries
     double* dRes = (double*) ws_reserve (b, WS_RESULT2, (size_t) b->nPairs * 8);
     if (!dRes) return 1;
     if (timing_begin (b)) return 1;
-    if (launch (m, b, 9, full_order (b), dRes, nullptr, nullptr, CountArgs(), narrow)) return 1;
+    if (launch (m, b, 9, full_order (b), dRes, nullptr, nullptr, CountArgs(), useC)) return 1;
     if (timing_end (b, 1)) return 1;
     MB_CUDA (cudaMemcpy (score, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost));
     return 0;
   }
-  const int W = 32 * (narrow ? J.C : J.CV);
-  // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words; chunk the batch if it does not fit
+  const int W = 32 * useC;
+  // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words (a fitted width whose lane bytes are not a power of two:
+  // 16 bytes per lane, MB_TBPAD); chunk the batch if it does not fit
+  const int laneBytes = useC * J.tbBytes;
+  const bool padded = laneBytes != 1 && laneBytes != 2 && laneBytes != 4 && laneBytes != 8 && laneBytes != 16;
+  const int64_t rowCols = padded ? 32 * (16 / J.tbBytes) : W;      // column slots per strip in a row of pointers
   double wanted = 0;
   for (int64_t k = 0; k < b->nPairs; ++k)
-    wanted += (double) ((((b->yOff[k + 1] - b->yOff[k]) + 1) * ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * W) * J.tbBytes + 255) & ~(int64_t) 255);
+    wanted += (double) ((((b->yOff[k + 1] - b->yOff[k]) + 1) * ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * rowCols) * J.tbBytes + 255) & ~(int64_t) 255);
   const double budget = memory_budget (m, b, WS_TB, wanted, "jit_tb_budget_mb");
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
   std::vector<int64_t> chunkBytes (1, 0);
   for (int64_t k = 0; k < b->nPairs; ++k) {
     const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
-    int64_t need = (Lo + 1) * (((Li + W) / W) * W) * J.tbBytes;
+    int64_t need = (Lo + 1) * (((Li + W) / W) * rowCols) * J.tbBytes;
     need = (need + 255) & ~(int64_t) 255;
     if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": Viterbi back-pointers do not fit in device memory"); return 1; }
     if (!chunks.back().empty() && (double) (chunkBytes.back() + need) > budget) { chunks.emplace_back(); chunkBytes.push_back (0); }
@@ -1410,6 +1488,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   tp.bits = tp.shift + m->S;
   tp.idTab = tp.bits + m->S;
   tp.S = m->S; tp.nOut = m->nOut; tp.tbBytes = J.tbBytes; tp.W = W;
+  tp.padC = padded ? useC : 0; tp.padSlots = padded ? 16 / J.tbBytes : 0;
   int64_t packed = 0, launches = 0;
   double ms = 0;
   for (size_t c = 0; c < chunks.size(); ++c) {
@@ -1417,7 +1496,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     if (chunks.size() > 1) chunkOrder = cost_order (b, chunks[c]);
     const std::vector<int64_t>& order = chunks.size() > 1 ? chunkOrder : full_order (b);
     if (timing_begin (b)) return 1;
-    if (launch (m, b, 2, order, dRes, dTb, dTbOff, CountArgs(), narrow)) return 1;
+    if (launch (m, b, 2, order, dRes, dTb, dTbOff, CountArgs(), useC)) return 1;
     ++launches;
     if (trace) {
       const size_t n = chunks[c].size();

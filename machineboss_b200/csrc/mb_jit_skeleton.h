@@ -181,7 +181,11 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     const uint8_t* x = A.x + x0;
     const uint8_t* y = A.y + y0;
     const int nStrips = (Li + MB_W) / MB_W;
+#ifdef MB_TBPAD      // a strip width fitted to the batch (MB_C * MB_TBBYTES not a power of two): the lane's pointers sit at the start of a 16-byte group of MB_TBPAD column slots
+    const int64_t pitch = (int64_t) nStrips * 32 * MB_TBPAD;
+#else
     const int64_t pitch = (int64_t) nStrips * MB_W;
+#endif
     uint8_t* tb = MODE == 1 ? A.tb + A.tbOff[k] : (uint8_t*) 0;
     double* Fm = (MODE == 2 || MODE == 3) ? A.F + A.fOff[k] : (double*) 0;
     const double ll = MODE == 3 ? A.ll[k] : 0.0;
@@ -242,7 +246,11 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       const int nSteps = Lo + 32;
       // where this lane's row r = t - lane goes: pointers advanced by one row per step instead of recomputed
+#ifdef MB_TBPAD
+      uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) (0 - lane) * pitch + (strip * 32 + lane) * MB_TBPAD) * MB_TBBYTES : (uint8_t*) 0;
+#else
       uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) (0 - lane) * pitch + col0) * MB_TBBYTES : (uint8_t*) 0;
+#endif
       const int64_t tbStep = pitch * MB_TBBYTES;
       double* boutRow = bout + (int64_t) (0 - lane) * MB_ROW;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
@@ -351,13 +359,13 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
 #ifdef MB_ROWTAB
             pack32 = pk[0];
             pack0 = MB_PKW > 1 ? (unsigned long long) pk[0] | ((unsigned long long) pk[MB_PKW > 1 ? 1 : 0] << 32) : pk[0];
-            pack1 = MB_PKW > 3 ? (unsigned long long) pk[MB_PKW > 3 ? 2 : 0] | ((unsigned long long) pk[MB_PKW > 3 ? 3 : 0] << 32) : 0ull;
+            pack1 = MB_PKW > 2 ? (unsigned long long) pk[MB_PKW > 2 ? 2 : 0] | (MB_PKW > 3 ? (unsigned long long) pk[MB_PKW > 3 ? 3 : 0] << 32 : 0ull) : 0ull;
 #endif
             if (MB_C * MB_TBBYTES == 1) *p = (uint8_t) pack32;
             else if (MB_C * MB_TBBYTES == 2) *(unsigned short*) p = (unsigned short) pack32;
             else if (MB_C * MB_TBBYTES == 4) *(unsigned int*) p = pack32;
             else if (MB_C * MB_TBBYTES == 8) *(unsigned long long*) p = pack0;
-            else *(ulonglong2*) p = make_ulonglong2 (pack0, pack1);
+            else *(ulonglong2*) p = make_ulonglong2 (pack0, pack1);      // 16 bytes, or a fitted width's padded group (MB_TBPAD)
           }
           if (hasOut && lane == 31) {
 #pragma unroll

@@ -244,6 +244,52 @@ def test_jit_strip_widths(narrow):
         assert paths[k].tolist() == p.tolist(), k
 
 
+@pytest.mark.parametrize("name,fit_c,max_li", [("dnapsw_peaked", 10, 319), ("dnapsw_peaked", 5, 150), ("dnapsw_peaked", 12, 383), ("protpsw_synth", 10, 300), ("protpsw_synth", 3, 95)])
+def test_jit_strips_fitted_to_the_batch(name, fit_c, max_li):
+    """A score module compiled for the batch (mb_jit.cu choose_width / ensure_fit_module): every pair in ONE strip of 32 * C
+    columns, C not a power of two, so the Viterbi pointers of a lane sit in a padded 16-byte group (MB_TBPAD).  Forced with
+    jit_fit_c on ragged pairs up to the strip's last column; Forward, Backward, Viterbi scores bit for bit and the paths."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden(name)["machine"])
+    shapes = [(max_li, 120), (max_li - 1, 33), (0, 7), (1, 0), (max_li // 2, 200), (31, 64), (32, 31), (33, 400)]
+    pairs = [(synth_tokens(93, k, 0, li, fm.n_in), synth_tokens(93, k, 1, lo, fm.n_out)) for k, (li, lo) in enumerate(shapes)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 1, jit_fit_c=fit_c, verbose=1)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    bl = capi.backward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    sc2 = capi.viterbi(m, b, paths=False)
+    ref = make_machine(capi, fm, 1, jit_fit_c=0)
+    assert np.array_equal(capi.viterbi(ref, b, paths=False), sc)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(ll[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, ll[k], f)
+        assert abs(bl[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, bl[k], f)
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v and sc2[k] == v, (k, sc[k], v)
+        assert paths[k].tolist() == p.tolist(), k
+
+
+def test_jit_fitted_strips_are_chosen_for_uniform_short_pairs(capfd):
+    """300 x 300 pairs in a batch of 512: the cost model prefers one strip of 320 columns to 3 of 128 or 2 of 256, compiles
+    the module once, and the numbers do not change."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    pairs = [(synth_tokens(95, k, 0, 300 - (k % 7), 4), synth_tokens(95, k, 1, 290 + (k % 11), 4)) for k in range(512)]
+    b = capi.Batch(pairs)
+    m = make_machine(capi, fm, 1, verbose=1)
+    ll = capi.forward(m, b)
+    sc, paths = capi.viterbi(m, b)
+    err = capfd.readouterr().err
+    assert "fitted to the batch compiled: 10 columns per lane" in err and err.count("fitted to the batch compiled") == 1
+    ref = make_machine(capi, fm, 1, jit_fit_c=0)
+    ll0 = capi.forward(ref, b)
+    sc0, paths0 = capi.viterbi(ref, b)
+    np.testing.assert_allclose(ll, ll0, rtol=1e-12)
+    assert np.array_equal(sc, sc0) and all(np.array_equal(p, q) for p, q in zip(paths, paths0))
+
+
 @pytest.mark.parametrize("reads_per_lane", [1, 2, 4])
 def test_lane_engine_reads_per_lane(reads_per_lane):
     """Batches without input sequences go through the lane engine (a read per lane, mb_lane.cu): every
