@@ -67,6 +67,46 @@ class FlatMachine:
                            np.ascontiguousarray(lw, dtype=np.float64), self.in_alphabet, self.out_alphabet)
 
 
+def synthetic_profile(n_nodes: int = 80, n_out: int = 4, seed: int = 7, skip: bool = False) -> FlatMachine:
+    """A generator with a period of 3 states per node (M, I, D) whose transitions consume the token when they LEAVE a state --
+    unlike the reference's HMMER import (Mx / M, Ix / I), so that the column engine meets diagonal groups (node k -> k+1
+    consuming a token), token-consuming self-loops, a begin hub entered with a token, and flanking states with their own
+    dynamics (N before, C after the nodes).  skip: add node k -> k+2 transitions, which no column sweep can take."""
+    rng = np.random.default_rng(seed)
+    S0, N, B = 0, 1, 2
+    M = lambda k: 3 + 3 * (k - 1)
+    I = lambda k: M(k) + 1
+    D = lambda k: M(k) + 2
+    E = 3 + 3 * n_nodes
+    C, T = E + 1, E + 2
+    rows = []
+
+    def silent(a, b):
+        rows.append((a, b, 0, 0, float(np.log(rng.uniform(0.05, 0.6)))))
+
+    def emit(a, b):
+        for c in range(1, n_out + 1):
+            rows.append((a, b, 0, c, float(np.log(rng.uniform(0.02, 0.5)))))
+
+    silent(S0, N); silent(S0, B); emit(N, N); silent(N, B)
+    for k in range(1, n_nodes + 1):
+        emit(B, M(k))
+    for k in range(1, n_nodes + 1):
+        emit(M(k), I(k)); emit(I(k), I(k)); silent(M(k), E)
+        if k < n_nodes:
+            emit(M(k), M(k + 1)); emit(I(k), M(k + 1)); silent(M(k), D(k + 1)); silent(D(k), D(k + 1)); emit(D(k), M(k + 1))
+        else:
+            silent(D(k), E); silent(I(k), E)
+        if skip and k + 2 <= n_nodes:
+            silent(M(k), D(k + 2))
+    silent(E, C); emit(C, C); silent(C, T); silent(E, T)
+    rows.sort(key=lambda r: r[0])      # the reference enumerates transitions state by state (eval.cpp:49-69)
+    a = np.array(rows, dtype=object)
+    return FlatMachine(T + 1, 0, n_out, np.array([r[0] for r in rows], np.int32), np.array([r[1] for r in rows], np.int32),
+                       np.zeros(len(rows), np.int32), np.array([r[3] for r in rows], np.int32), np.array([r[4] for r in rows], np.float64),
+                       [], [chr(65 + c) for c in range(n_out)])
+
+
 def load_golden(name: str) -> dict:
     path = os.path.join(GOLDEN, name + ".json")
     if os.path.exists(path):

@@ -7,7 +7,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import LSE_EXACT, FlatMachine, Oracle, load_golden, synth_tokens
+from helpers import LSE_EXACT, FlatMachine, Oracle, load_golden, synth_tokens, synthetic_profile
 
 
 def _generator(name):
@@ -53,5 +53,35 @@ def test_column_kernel_compiles():
 def test_machines_without_a_period_are_declined(name):
     from machineboss_b200 import capi
     fm = _generator(name)
+    _, info = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0)
+    assert info[0] == 0
+
+
+def test_synthetic_profile_with_diagonal_groups_and_flanking_states():
+    """A hand-made periodic generator the HMMER import never produces: transitions that consume a token while moving to the next
+    node (diagonal groups), token-consuming self-loops, a begin hub entered with a token, and N / C flanking states with
+    self-loops (prefix and suffix programs with their own dynamics).  Forward, Viterbi and the walk back, against the oracle."""
+    from machineboss_b200 import capi
+    fm = synthetic_profile()
+    args = (fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw)
+    orc = Oracle(fm)
+    x = np.zeros(0, np.uint8)
+    for k, lo in enumerate([0, 1, 2, 5, 17, 40, 95]):
+        y = synth_tokens(37, k, 1, lo, fm.n_out)
+        f, info = capi.col_emulate(*args, y, 0)
+        assert info[0] == 1 and info[1] == 3, info
+        want = orc.forward(x, y, mode=LSE_EXACT)
+        assert (f == want) if math.isinf(want) else abs(f - want) <= 1e-10 * max(1.0, abs(want)), (lo, f, want)
+        v, _, walked = capi.col_emulate(*args, y, 1, path=True)
+        want_v, want_p = orc.viterbi(x, y)
+        assert v == want_v, (lo, v, want_v)
+        assert walked.tolist() == want_p.tolist(), lo
+    _, info, log = capi.col_emulate(*args, np.zeros(0, np.uint8), 0, compile_log=True)
+    assert "mb_k_col_maxp" in log
+
+
+def test_transitions_that_skip_a_node_are_declined():
+    from machineboss_b200 import capi
+    fm = synthetic_profile(skip=True)
     _, info = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0)
     assert info[0] == 0

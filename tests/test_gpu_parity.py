@@ -11,7 +11,7 @@ import math
 import numpy as np
 import pytest
 
-from helpers import (LSE_EXACT, FlatMachine, Oracle, gnum, golden_names, load_golden, pairs_from_golden,
+from helpers import (LSE_EXACT, FlatMachine, Oracle, gnum, golden_names, load_golden, pairs_from_golden, synthetic_profile,
                      synth_tokens)
 
 pytestmark = pytest.mark.gpu
@@ -544,6 +544,32 @@ def test_column_engine_profile_reads(opts):
             assert paths[k].tolist() == p.tolist(), (name, k)
         _, paths_lane = capi.viterbi(lane, b)
         assert all(np.array_equal(a, c) for a, c in zip(paths, paths_lane))
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(col_c=1), dict(col_c=3, col_minblocks=1), dict(col_sil_regs=0, col_r=2)])
+def test_column_engine_synthetic_profile(opts):
+    """A periodic generator unlike the HMMER import (helpers.synthetic_profile): diagonal groups (a token consumed on the way
+    to the next node), token-consuming self-loops, a begin hub entered with a token, N / C flanking states with their own
+    dynamics in the prefix and suffix programs -- the kernel paths the PF00516 machines do not reach."""
+    capi = _capi()
+    fm = synthetic_profile(n_nodes=90)
+    lens = [0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 64, 150, 301] + [5 + (k * 13) % 120 for k in range(60)]
+    pairs = [(np.zeros(0, np.uint8), synth_tokens(39, k, 1, lo, fm.n_out)) for k, lo in enumerate(lens)]
+    orc = Oracle(fm)
+    m = make_machine(capi, fm, 2, **opts)
+    b = capi.Batch(pairs)
+    ll = capi.forward(m, b)
+    launches = b.last_kernel_ms()[1]
+    assert launches >= 3 and launches % 3 == 0, launches      # the column engine ran
+    sc = capi.viterbi(m, b, paths=False)
+    sc2, paths = capi.viterbi(m, b)
+    assert np.array_equal(sc, sc2)
+    for k, (x, y) in enumerate(pairs):
+        f = orc.forward(x, y, mode=LSE_EXACT)
+        assert (ll[k] == f) if np.isinf(f) else abs(ll[k] - f) <= 1e-9 * max(1.0, abs(f)), (k, ll[k], f)
+        v, p = orc.viterbi(x, y)
+        assert sc[k] == v, (k, sc[k], v)
+        assert paths[k].tolist() == p.tolist(), k
 
 
 def test_column_engine_hands_impossible_reads_to_the_log_domain():
