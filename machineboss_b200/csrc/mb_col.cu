@@ -605,7 +605,7 @@ struct MBColArgsHost {      // must match struct MBColArgs in the skeleton
   double* bnd; const int64_t* bndOff;
   const double* tab;
   int32_t* flag;
-  int nStrips, K, R, bpPitch;
+  int nStrips, K, R, pad;
   unsigned char* bp; const int64_t* bpOff;
 };
 
@@ -650,7 +650,7 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
     MBColArgsHost A;
     A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
     A.bnd = dBnd; A.bndOff = dOff; A.tab = sums ? E.dTabLin : E.dTabLog; A.flag = dFlag;
-    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.bpPitch = 0; A.bp = nullptr; A.bpOff = nullptr;
+    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.pad = 0; A.bp = nullptr; A.bpOff = nullptr;
     const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * (sums ? E.blocksPerSMSum : E.blocksPerSMMax), groups));
     void* params[1] = { &A };
@@ -673,7 +673,7 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
 // ---------------------------------------------------------------------------------------------
 struct ColTbPlan {
   const int32_t *groupStart, *ptrWord, *ptrShift, *ptrBits, *gType, *gSrc, *gSlot, *leftCell, *carried, *slotTrans, *preEnt, *sufEnt;
-  int32_t nCell, nC, K, nPre, nSuf, nSlots, bpBytes, bpPitch;
+  int32_t nCell, nC, K, nPre, nSuf, nSlots, bpBytes, C;      // C: columns per lane of the sweep that stored the pointers
 };
 
 // out == nullptr: lengths only; otherwise the path is written start -> end at out[outOff[n] ..) (lenOut[n] from the first pass)
@@ -711,7 +711,9 @@ __global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const u
         const int bits = p.ptrBits[s];
         int idx = 0;
         if (bits) {
-          const unsigned char* c = cells + o * p.bpPitch + (int64_t) k * p.bpBytes;
+          // sweep order (see MBColArgs::bp): column k is column k % C of lane (k / C) % 32 in strip k / (32 C), stored at step o + lane
+          const int strip = k / (32 * p.C), lane = (k / p.C) & 31;
+          const unsigned char* c = cells + ((((int64_t) strip * (Lo + 32) + o + lane) * 32 + lane) * p.C + k % p.C) * p.bpBytes;
           const unsigned v = p.bpBytes == 1 ? (unsigned) c[0] : p.bpBytes == 2 ? (unsigned) *(const unsigned short*) c : ((const unsigned*) c)[p.ptrWord[s]];
           idx = (int) ((v >> p.ptrShift[s]) & ((1u << bits) - 1u));
         }
@@ -748,7 +750,7 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
   ColEngine& E = *ce (m);
   const ColProg& p = E.prog;
   const int brow = p.nLL + 1;
-  const int64_t bpPitch = ((int64_t) p.Kpad * p.bpBytes + 7) / 8 * 8;
+  const int64_t stepBytes = (int64_t) 32 * p.C * p.bpBytes;      // one (strip, step) block of pointers
   size_t freeB = 0, totalB = 0;
   MB_CUDA (cudaMemGetInfo (&freeB, &totalB));
   const double budget = std::min (0.6 * (double) freeB, (double) m->opt.get ("col_bp_budget_mb", 1 << 20) * 1048576.);
@@ -760,7 +762,7 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
   T.groupStart = base + E.tbOff[0]; T.ptrWord = base + E.tbOff[1]; T.ptrShift = base + E.tbOff[2]; T.ptrBits = base + E.tbOff[3];
   T.gType = base + E.tbOff[4]; T.gSrc = base + E.tbOff[5]; T.gSlot = base + E.tbOff[6]; T.leftCell = base + E.tbOff[7]; T.carried = base + E.tbOff[8];
   T.slotTrans = base + E.tbOff[9]; T.preEnt = base + E.tbOff[10]; T.sufEnt = base + E.tbOff[11];
-  T.nCell = p.nCell; T.nC = p.nC; T.K = p.K; T.nPre = p.nPre; T.nSuf = p.nSuf; T.nSlots = p.nSlots; T.bpBytes = p.bpBytes; T.bpPitch = (int32_t) bpPitch;
+  T.nCell = p.nCell; T.nC = p.nC; T.K = p.K; T.nPre = p.nPre; T.nSuf = p.nSuf; T.nSlots = p.nSlots; T.bpBytes = p.bpBytes; T.C = p.C;
   for (size_t c0 = 0; c0 < order.size();) {
     std::vector<int64_t> off, bpOff, preOff, sufOff;
     double doubles = 0, bpBytes = 0, sideShorts = 0;
@@ -768,12 +770,13 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
     while (c1 < order.size()) {
       const int64_t k = order[c1];
       const double rows = (double) (b->yOff[k + 1] - b->yOff[k] + 1);
-      const double need = rows * (brow * 8 + bpPitch + (p.nPre + p.nSuf) * 2 + 16);
+      const double bpNeed = (double) (((int64_t) p.nStrips * (int64_t) (rows + 31) * stepBytes + 15) / 16 * 16);
+      const double need = rows * (brow * 8 + (p.nPre + p.nSuf) * 2 + 16) + bpNeed;
       if (need > budget) { set_error ("column engine: one read's Viterbi pointers need more device memory than is free"); return 1; }
       if (c1 > c0 && doubles * 8 + bpBytes + sideShorts * 2 + need > budget) break;
       off.push_back ((int64_t) doubles); bpOff.push_back ((int64_t) bpBytes);
       preOff.push_back ((int64_t) sideShorts); sufOff.push_back ((int64_t) (sideShorts + rows * p.nPre));
-      doubles += rows * brow; bpBytes += rows * (double) bpPitch; sideShorts += rows * (p.nPre + p.nSuf);
+      doubles += rows * brow; bpBytes += bpNeed; sideShorts += rows * (p.nPre + p.nSuf);
       ++c1;
     }
     const int64_t nWork = (int64_t) (c1 - c0);
@@ -804,7 +807,7 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
     MBColArgsHost A;
     A.y = b->dY; A.yOff = b->dYOff; A.order = dOrder; A.nWork = nWork; A.counter = dCounter;
     A.bnd = dBnd; A.bndOff = dOffs; A.tab = E.dTabLog; A.flag = nullptr;
-    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.bpPitch = (int) bpPitch; A.bp = dBp; A.bpOff = dOffs + nWork;
+    A.nStrips = p.nStrips; A.K = p.Kpad; A.R = E.R; A.pad = 0; A.bp = dBp; A.bpOff = dOffs + nWork;
     const int64_t groups = (nWork + (int64_t) warps * E.R - 1) / ((int64_t) warps * E.R);
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * E.blocksPerSMMaxP, groups));
     void* params[1] = { &A };

@@ -42,8 +42,11 @@ struct MBColArgs {
   double* bnd; const int64_t* bndOff;      // work item n: (Lo + 1) rows of MB_BROW doubles at bnd + bndOff[n]
   const double* tab;                       // [strip][slot][column of the lane][lane] weights
   int32_t* flag;
-  int nStrips, K, R, bpPitch;              // bpPitch: bytes per row of a read's pointers (MODE 1)
-  unsigned char* bp; const int64_t* bpOff; // MODE 1: the pointers of work item n's cell (row, column) at bp + bpOff[n] + row * bpPitch + column * MB_BPBYTES
+  int nStrips, K, R, pad;
+  // MODE 1: work item n's pointers at bp + bpOff[n], in SWEEP ORDER: one block per (strip, step) holding what the warp's lanes
+  // produced in that step -- [(strip * (Lo + 32) + step) * 32 + lane] groups of MB_COL_C * MB_BPBYTES bytes -- so that a step's
+  // store is one contiguous run (row-major rows would scatter the skewed lanes over 32 sectors: measured 2 x the kernel time)
+  unsigned char* bp; const int64_t* bpOff;
 };
 
 __device__ __forceinline__ double mb_pow2 (int d) { return __hiloint2double ((1023 + d) << 20, 0); }
@@ -90,7 +93,7 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
         const int Lo = (int) (A.yOff[k + 1] - y0);
         const uint8_t* y = A.y + y0;
         double* bnd = A.bnd + A.bndOff[w];
-        unsigned char* bp = MODE == 1 ? A.bp + A.bpOff[w] + (int64_t) col * MB_BPBYTES : (unsigned char*) 0;
+        unsigned char* bp = MODE == 1 ? A.bp + A.bpOff[w] + ((int64_t) strip * (Lo + 32) * 32 + lane) * (MB_COL_C * MB_BPBYTES) : (unsigned char*) 0;
         int suspect = 0;
 
         double U[MB_NUREG > 0 ? MB_NUREG : 1];      // my columns' last cells: the sources of the groups that consume a token and stay in the column
@@ -200,7 +203,13 @@ __device__ __forceinline__ void mb_col_run (const MBColArgs& A) {
             else {
               unsigned pk[MB_COL_C * MB_NPW];
               MB_COL_CELL_MAXP
-              unsigned char* dstp = bp + (int64_t) r * A.bpPitch;
+              unsigned char* dstp = bp + (int64_t) t * (32 * MB_COL_C * MB_BPBYTES);
+              if (MB_COL_C * MB_BPBYTES == 4 && MB_BPBYTES < 4) {      // the lane's columns in one 32-bit store
+                unsigned word = 0u;
+#pragma unroll
+                for (int c = 0; c < MB_COL_C; ++c) word |= pk[c] << (8 * MB_BPBYTES * c);
+                *(unsigned*) dstp = word;
+              } else
 #pragma unroll
               for (int c = 0; c < MB_COL_C; ++c) {
                 if (MB_BPBYTES == 1) dstp[c] = (unsigned char) pk[c];

@@ -2,7 +2,7 @@
 set -u
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -m gpu -q -x -k "synthetic or column" ) > gpurun_out/pytest_gpu17.log 2>&1
+( time timeout 900 python -m pytest tests -m gpu -q -x -k "synthetic or column or hmmer" ) > gpurun_out/pytest_gpu17.log 2>&1
 tail -12 gpurun_out/pytest_gpu17.log
 python - > gpurun_out/col_tb_launches.txt 2>&1 <<'PY'
 import sys, numpy as np
