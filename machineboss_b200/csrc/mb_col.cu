@@ -360,7 +360,7 @@ struct ColSideArgs {
   int32_t nStates, nLL, nC;
   const int32_t* carried;      // [nC] left-going slot | [nC] prefix state
   double* result;
-  unsigned short* ptr; const int64_t* ptrOff;      // max-plus with traceback: the winning entry per (row, state) of work item n at ptr + ptrOff[n]; 0xffff: none
+  unsigned short* ptr;      // max-plus with traceback: the winning entry of (row o, work item n, state s) at ptr[(o * nWork + n) * nStates + s] (threads of a warp write neighbours); 0xffff: none
 };
 
 __device__ __forceinline__ double col_ninf() { return __longlong_as_double (0xfff0000000000000LL); }
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128) col_prefix_kernel (ColSideArgs A) {
     for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
     if (o == 0) cur[0] = 0.;
     const int tok = o ? y[o - 1] : -1;
-    unsigned short* won = (!SUM && A.ptr) ? A.ptr + A.ptrOff[n] + (int64_t) o * A.nStates : (unsigned short*) 0;
+    unsigned short* won = (!SUM && A.ptr) ? A.ptr + ((int64_t) o * A.nWork + n) * A.nStates : (unsigned short*) 0;
     if (won) for (int s = 0; s < A.nStates; ++s) won[s] = 0xffff;
     for (int e = 0; e < A.nEnt; ++e) {
       const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128) col_suffix_kernel (ColSideArgs A) {
     for (int j = 0; j < A.nLL; ++j) { const double v = row[j]; X[j] = SUM ? (v > 0. ? log (v) + fr : col_ninf()) : v; }
     for (int s = 0; s < A.nStates; ++s) cur[s] = col_ninf();
     const int tok = o ? y[o - 1] : -1;
-    unsigned short* won = (!SUM && A.ptr) ? A.ptr + A.ptrOff[n] + (int64_t) o * A.nStates : (unsigned short*) 0;
+    unsigned short* won = (!SUM && A.ptr) ? A.ptr + ((int64_t) o * A.nWork + n) * A.nStates : (unsigned short*) 0;
     if (won) for (int s = 0; s < A.nStates; ++s) won[s] = 0xffff;
     for (int e = 0; e < A.nEnt; ++e) {
       const int dst = A.ent[4 * e], src = A.ent[4 * e + 1], etok = A.ent[4 * e + 2], kind = A.ent[4 * e + 3];
@@ -643,7 +643,7 @@ int col_launch (mb_machine* m, mb_batch* b, const std::vector<int64_t>& order, b
     ColSideArgs S;
     S.y = b->dY; S.yOff = b->dYOff; S.order = dOrder; S.nWork = nWork; S.bnd = dBnd; S.bndOff = dOff;
     S.ent = E.dPre; S.w = E.dPreW; S.nEnt = (int32_t) p.pre.size(); S.nStates = p.nPre; S.nLL = p.nLL; S.nC = p.nC; S.carried = E.dCarriedSlot; S.result = dResult;
-    S.ptr = nullptr; S.ptrOff = nullptr;
+    S.ptr = nullptr;
     const unsigned sideGrid = (unsigned) ((nWork + 127) / 128);
     if (sums) col_prefix_kernel<true><<<sideGrid, 128, 0, b->stream>>> (S); else col_prefix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
     MB_CUDA (cudaGetLastError());
@@ -679,7 +679,7 @@ struct ColTbPlan {
 // out == nullptr: lengths only; otherwise the path is written start -> end at out[outOff[n] ..) (lenOut[n] from the first pass)
 __global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const uint8_t* __restrict__ yAll, const int64_t* __restrict__ yOff, const int64_t* __restrict__ order, int64_t nWork,
                                       const unsigned char* __restrict__ bp, const int64_t* __restrict__ bpOff,
-                                      const unsigned short* __restrict__ sidePtr, const int64_t* __restrict__ preOff, const int64_t* __restrict__ sufOff,
+                                      const unsigned short* __restrict__ prePtr, const unsigned short* __restrict__ sufPtr,
                                       const double* __restrict__ score, int64_t* __restrict__ lenOut, int32_t* __restrict__ out, const int64_t* __restrict__ outOff) {
   const int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nWork) return;
@@ -687,8 +687,8 @@ __global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const u
   const uint8_t* y = yAll + yOff[kr];
   const int64_t Lo = yOff[kr + 1] - yOff[kr];
   const unsigned char* cells = bp + bpOff[n];
-  const unsigned short* preP = sidePtr + preOff[n];
-  const unsigned short* sufP = sidePtr + sufOff[n];
+  const unsigned short* preP = prePtr + n * p.nPre;      // row o: + o * nWork * nPre
+  const unsigned short* sufP = sufPtr + n * p.nSuf;
   int64_t len = 0;
   if (score[kr] > -INFINITY) {      // boss.cpp:831
     const int64_t total = out ? lenOut[n] : 0;
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const u
       if (where == 0 && o == 0 && s == 0) break;
       int32_t tr = -1;
       if (where == 2) {
-        const int e = sufP[o * p.nSuf + s];
+        const int e = sufP[o * nWork * p.nSuf + s];
         if (e == 0xffff) break;
         const int src = p.sufEnt[3 * e], kind = p.sufEnt[3 * e + 1];
         tr = p.sufEnt[3 * e + 2];
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(64) col_traceback_kernel (ColTbPlan p, const u
         if (type == CG_LEFT || type == CG_DIAG) { if (k == 0) break; --k; }
         if (emit) --o;
       } else {
-        const int e = preP[o * p.nPre + s];
+        const int e = preP[o * nWork * p.nPre + s];
         if (e == 0xffff) break;
         tr = p.preEnt[3 * e + 2];
         s = p.preEnt[3 * e];
@@ -764,25 +764,25 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
   T.slotTrans = base + E.tbOff[9]; T.preEnt = base + E.tbOff[10]; T.sufEnt = base + E.tbOff[11];
   T.nCell = p.nCell; T.nC = p.nC; T.K = p.K; T.nPre = p.nPre; T.nSuf = p.nSuf; T.nSlots = p.nSlots; T.bpBytes = p.bpBytes; T.C = p.C;
   for (size_t c0 = 0; c0 < order.size();) {
-    std::vector<int64_t> off, bpOff, preOff, sufOff;
+    std::vector<int64_t> off, bpOff;
     double doubles = 0, bpBytes = 0, sideShorts = 0;
     size_t c1 = c0;
+    const double rowsMax = (double) (b->yOff[order[c0] + 1] - b->yOff[order[c0]] + 1);      // the chunk's longest read comes first
     while (c1 < order.size()) {
       const int64_t k = order[c1];
       const double rows = (double) (b->yOff[k + 1] - b->yOff[k] + 1);
       const double bpNeed = (double) (((int64_t) p.nStrips * (int64_t) (rows + 31) * stepBytes + 15) / 16 * 16);
-      const double need = rows * (brow * 8 + (p.nPre + p.nSuf) * 2 + 16) + bpNeed;
+      const double need = rows * (brow * 8 + 16) + rowsMax * (p.nPre + p.nSuf) * 2 + bpNeed;      // (the prefix / suffix pointers are [row][read][state]: every read pays for the longest one's rows)
       if (need > budget) { set_error ("column engine: one read's Viterbi pointers need more device memory than is free"); return 1; }
       if (c1 > c0 && doubles * 8 + bpBytes + sideShorts * 2 + need > budget) break;
       off.push_back ((int64_t) doubles); bpOff.push_back ((int64_t) bpBytes);
-      preOff.push_back ((int64_t) sideShorts); sufOff.push_back ((int64_t) (sideShorts + rows * p.nPre));
-      doubles += rows * brow; bpBytes += bpNeed; sideShorts += rows * (p.nPre + p.nSuf);
+      doubles += rows * brow; bpBytes += bpNeed; sideShorts += rowsMax * (p.nPre + p.nSuf);
       ++c1;
     }
     const int64_t nWork = (int64_t) (c1 - c0);
     b->wsOrderHoldsFull = false;
     int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, (size_t) nWork * 8);
-    int64_t* dOffs = (int64_t*) ws_reserve (b, WS_ITEMBND, (size_t) nWork * 8 * 4);      // bnd | bp | prefix | suffix offsets
+    int64_t* dOffs = (int64_t*) ws_reserve (b, WS_ITEMBND, (size_t) nWork * 8 * 2);      // bnd | bp offsets
     double* dBnd = (double*) ws_reserve (b, WS_BND, (size_t) doubles * 8);
     unsigned char* dBp = (unsigned char*) ws_reserve (b, WS_TB, (size_t) bpBytes + 8);
     unsigned short* dSide = (unsigned short*) ws_reserve (b, WS_PATHTMP, (size_t) sideShorts * 2 + 8);
@@ -793,14 +793,14 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
     MB_CUDA (cudaMemcpyAsync (dOrder, order.data() + c0, (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
     MB_CUDA (cudaMemcpyAsync (dOffs, off.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
     MB_CUDA (cudaMemcpyAsync (dOffs + nWork, bpOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
-    MB_CUDA (cudaMemcpyAsync (dOffs + 2 * nWork, preOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
-    MB_CUDA (cudaMemcpyAsync (dOffs + 3 * nWork, sufOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
+    unsigned short* dPreP = dSide;
+    unsigned short* dSufP = dSide + (int64_t) rowsMax * nWork * p.nPre;
     MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
     if (timing_begin (b)) return 1;
     ColSideArgs S;
     S.y = b->dY; S.yOff = b->dYOff; S.order = dOrder; S.nWork = nWork; S.bnd = dBnd; S.bndOff = dOffs;
     S.ent = E.dPre; S.w = E.dPreW; S.nEnt = (int32_t) p.pre.size(); S.nStates = p.nPre; S.nLL = p.nLL; S.nC = p.nC; S.carried = E.dCarriedSlot; S.result = dResult;
-    S.ptr = dSide; S.ptrOff = dOffs + 2 * nWork;
+    S.ptr = dPreP;
     const unsigned sideGrid = (unsigned) ((nWork + 127) / 128);
     col_prefix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
     MB_CUDA (cudaGetLastError());
@@ -812,11 +812,11 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
     const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) E.numSMs * E.blocksPerSMMaxP, groups));
     void* params[1] = { &A };
     if (rt_launch (E.kMaxP, (unsigned) grid, (unsigned) E.threads, E.smemBytes, b->stream, params)) return 1;
-    S.ent = E.dSuf; S.w = E.dSufW; S.nEnt = (int32_t) p.suf.size(); S.nStates = p.nSuf; S.ptrOff = dOffs + 3 * nWork;
+    S.ent = E.dSuf; S.w = E.dSufW; S.nEnt = (int32_t) p.suf.size(); S.nStates = p.nSuf; S.ptr = dSufP;
     col_suffix_kernel<false><<<sideGrid, 128, 0, b->stream>>> (S);
     MB_CUDA (cudaGetLastError());
     const unsigned tbGrid = (unsigned) ((nWork + 63) / 64);
-    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dSide, dOffs + 2 * nWork, dOffs + 3 * nWork, dResult, dLen, nullptr, nullptr);
+    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dPreP, dSufP, dResult, dLen, nullptr, nullptr);
     MB_CUDA (cudaGetLastError());
     std::vector<int64_t> len ((size_t) nWork), outOff ((size_t) nWork);
     MB_CUDA (cudaMemcpyAsync (len.data(), dLen, (size_t) nWork * 8, cudaMemcpyDeviceToHost, b->stream));
@@ -830,7 +830,7 @@ int col_viterbi_paths (mb_machine* m, mb_batch* b, const std::vector<int64_t>& o
     }
     if (paths_reserve (b, packed)) return 1;
     MB_CUDA (cudaMemcpyAsync (dOutOff, outOff.data(), (size_t) nWork * 8, cudaMemcpyHostToDevice, b->stream));
-    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dSide, dOffs + 2 * nWork, dOffs + 3 * nWork, dResult, dLen, b->dPaths, dOutOff);
+    col_traceback_kernel<<<tbGrid, 64, 0, b->stream>>> (T, b->dY, b->dYOff, dOrder, nWork, dBp, dOffs + nWork, dPreP, dSufP, dResult, dLen, b->dPaths, dOutOff);
     MB_CUDA (cudaGetLastError());
     if (launches) *launches += 5;
     if (timing_end (b, 5)) return 1;

@@ -903,7 +903,7 @@ struct TbPlan {
   const int32_t* bits;
   const int32_t* idTab;
   int32_t S, nOut, tbBytes, W;
-  int32_t padC, padSlots;      // fitted strip widths: column i's pointers sit at slot (i / padC) * padSlots + i % padC of the row (padC == 0: at slot i)
+  int32_t C, laneBytes;        // sweep order: cell (i, o) at ((strip * (Lo + 32) + o + lane) * 32 + lane) * laneBytes + (i % C) * tbBytes, strip = i / W, lane = (i % W) / C
 };
 
 static std::string module_source (const mb_machine* m, JitEngine& J, int passC, int pass, int passMinBlocks, int passMinBlocksLin);
@@ -1324,7 +1324,6 @@ __global__ void __launch_bounds__(64) jit_traceback_kernel (TbPlan p, int nSlots
   if (slot >= nPairsHere) return;
   const int64_t k = pairs[slot];
   const int64_t Li = b.xOff[k + 1] - b.xOff[k], Lo = b.yOff[k + 1] - b.yOff[k];
-  const int64_t pitch = p.padC ? ((Li + p.W) / p.W) * 32 * p.padSlots : ((Li + p.W) / p.W) * p.W;
   const uint8_t* base = tb + tbOff[k];
   uint8_t* out = tmp + tmpOff[slot + 1];     // one past the end of this pair's slot
   int64_t n = 0;
@@ -1332,9 +1331,10 @@ __global__ void __launch_bounds__(64) jit_traceback_kernel (TbPlan p, int nSlots
     int64_t i = Li, o = Lo;
     int s = p.S - 1;
     auto fetch = [&] (int64_t ii, int64_t oo) {
-      const int64_t at = p.padC ? (ii / p.padC) * p.padSlots + ii % p.padC : ii;
-      const uint8_t* wp = base + (oo * pitch + at) * p.tbBytes;
-      if (ii >= 8 && oo >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - (8 * pitch + 8) * p.tbBytes));
+      const int64_t strip = ii / p.W, within = ii % p.W, lane = within / p.C;
+      const uint8_t* wp = base + (((strip * (Lo + 32) + oo + lane) * 32 + lane) * p.laneBytes + (within % p.C) * p.tbBytes);
+      // where the path most likely goes: eight cells up the diagonal (the same strip's block sixteen steps back, one lane to the left for 8 columns per lane)
+      if (within >= 8 && oo >= 8) asm volatile ("prefetch.global.L2 [%0];" :: "l"(wp - ((int64_t) (8 + 8 / p.C) * 32 + 8 / p.C) * p.laneBytes));
       unsigned long long w = 0;
       for (int q = 0; q < p.tbBytes; ++q) w |= (unsigned long long) wp[q] << (8 * q);
       return w;
@@ -1444,21 +1444,21 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     return 0;
   }
   const int W = 32 * useC;
-  // back-pointer storage: (Lo+1) rows of pitch = ceil((Li+1)/W)*W words (a fitted width whose lane bytes are not a power of two:
-  // 16 bytes per lane, MB_TBPAD); chunk the batch if it does not fit
+  // back-pointer storage in sweep order: per strip (Lo + 32) steps of 32 lanes' groups (a fitted width whose lane bytes are not
+  // a power of two: 16 bytes per lane, MB_TBPAD); chunk the batch if it does not fit
   const int laneBytes = useC * J.tbBytes;
   const bool padded = laneBytes != 1 && laneBytes != 2 && laneBytes != 4 && laneBytes != 8 && laneBytes != 16;
-  const int64_t rowCols = padded ? 32 * (16 / J.tbBytes) : W;      // column slots per strip in a row of pointers
+  const int64_t stepBytes = 32 * (padded ? 16 : laneBytes);      // one (strip, step) block of pointers
   double wanted = 0;
   for (int64_t k = 0; k < b->nPairs; ++k)
-    wanted += (double) ((((b->yOff[k + 1] - b->yOff[k]) + 1) * ((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * rowCols) * J.tbBytes + 255) & ~(int64_t) 255);
+    wanted += (double) (((((b->xOff[k + 1] - b->xOff[k]) + W) / W) * ((b->yOff[k + 1] - b->yOff[k]) + 32) * stepBytes + 255) & ~(int64_t) 255);
   const double budget = memory_budget (m, b, WS_TB, wanted, "jit_tb_budget_mb");
   std::vector<std::vector<int64_t>> chunks (1);
   std::vector<int64_t> tbOffHost ((size_t) b->nPairs, 0);
   std::vector<int64_t> chunkBytes (1, 0);
   for (int64_t k = 0; k < b->nPairs; ++k) {
     const int64_t Li = b->xOff[k + 1] - b->xOff[k], Lo = b->yOff[k + 1] - b->yOff[k];
-    int64_t need = (Lo + 1) * (((Li + W) / W) * rowCols) * J.tbBytes;
+    int64_t need = ((Li + W) / W) * (Lo + 32) * stepBytes;
     need = (need + 255) & ~(int64_t) 255;
     if ((double) need > budget) { set_error ("pair " + std::to_string (k) + ": Viterbi back-pointers do not fit in device memory"); return 1; }
     if (!chunks.back().empty() && (double) (chunkBytes.back() + need) > budget) { chunks.emplace_back(); chunkBytes.push_back (0); }
@@ -1488,7 +1488,7 @@ int jit_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   tp.bits = tp.shift + m->S;
   tp.idTab = tp.bits + m->S;
   tp.S = m->S; tp.nOut = m->nOut; tp.tbBytes = J.tbBytes; tp.W = W;
-  tp.padC = padded ? useC : 0; tp.padSlots = padded ? 16 / J.tbBytes : 0;
+  tp.C = useC; tp.laneBytes = padded ? 16 : laneBytes;
   int64_t packed = 0, launches = 0;
   double ms = 0;
   for (size_t c = 0; c < chunks.size(); ++c) {

@@ -181,10 +181,14 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
     const uint8_t* x = A.x + x0;
     const uint8_t* y = A.y + y0;
     const int nStrips = (Li + MB_W) / MB_W;
-#ifdef MB_TBPAD      // a strip width fitted to the batch (MB_C * MB_TBBYTES not a power of two): the lane's pointers sit at the start of a 16-byte group of MB_TBPAD column slots
-    const int64_t pitch = (int64_t) nStrips * 32 * MB_TBPAD;
+    // Back-pointers in SWEEP ORDER: one block per (strip, step) holding the 32 lanes' groups of MB_TBLANE bytes (the lane's
+    // MB_C cells of that step; a fitted strip width whose MB_C * MB_TBBYTES is not a power of two pads the group to 16 bytes),
+    // so that a step's store is one contiguous run of 32 * MB_TBLANE bytes.  (Row-major rows scattered the skewed lanes over
+    // 32 sectors per store.)  Cell (i, o): strip i / MB_W, lane (i % MB_W) / MB_C, step o + lane.
+#ifdef MB_TBPAD
+#define MB_TBLANE 16
 #else
-    const int64_t pitch = (int64_t) nStrips * MB_W;
+#define MB_TBLANE (MB_C * MB_TBBYTES)
 #endif
     uint8_t* tb = MODE == 1 ? A.tb + A.tbOff[k] : (uint8_t*) 0;
     double* Fm = (MODE == 2 || MODE == 3) ? A.F + A.fOff[k] : (double*) 0;
@@ -246,12 +250,8 @@ __device__ __forceinline__ void mb_run (const MBSil& P, const MBArgs& A) {
       int tokNext = ring[(0 - lane) & 127];          // token of this lane's row at step 0 (only lane 0's is real)
       const int nSteps = Lo + 32;
       // where this lane's row r = t - lane goes: pointers advanced by one row per step instead of recomputed
-#ifdef MB_TBPAD
-      uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) (0 - lane) * pitch + (strip * 32 + lane) * MB_TBPAD) * MB_TBBYTES : (uint8_t*) 0;
-#else
-      uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) (0 - lane) * pitch + col0) * MB_TBBYTES : (uint8_t*) 0;
-#endif
-      const int64_t tbStep = pitch * MB_TBBYTES;
+      uint8_t* tbRow = MODE == 1 ? tb + ((int64_t) strip * (Lo + 32) * 32 + lane) * MB_TBLANE : (uint8_t*) 0;      // this lane's group at step 0
+      const int64_t tbStep = 32 * MB_TBLANE;
       double* boutRow = bout + (int64_t) (0 - lane) * MB_ROW;
       // one step of the skewed sweep; STEADY = every lane is inside the matrix (31 <= t < Lo), so the
       // ramp predicates (row in range, origin cell, result cell) fold away
