@@ -421,7 +421,7 @@ __global__ void big_traceback_kernel (BigTbPlan p, DevBatch b, const int64_t* __
       if (ng == 0) break;      // cannot happen on a finite path
       int ptr = 0;
       if (p.bits[s]) {
-        const unsigned w = base[((o * nStrips + (i >> 5)) * p.nWords + p.word[s]) * 32 + (i & 31)];
+        const unsigned w = base[(((o + (i & 31)) * nStrips + (i >> 5)) * p.nWords + p.word[s]) * 32 + (i & 31)];      // sweep order: the cell was stored at step o + lane
         ptr = (int) ((w >> p.shift[s]) & ((1u << p.bits[s]) - 1u));
       }
       if (ptr >= ng) break;
@@ -512,7 +512,7 @@ int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
     size_t c1 = c0;
     for (; c1 < order.size(); ++c1) {
       const int64_t k = order[c1];
-      const double need = (double) (b->yOff[k + 1] - b->yOff[k] + 1) * (double) ((b->xOff[k + 1] - b->xOff[k] + 32) / 32) * B.nPtrWords * 32;
+      const double need = (double) (b->yOff[k + 1] - b->yOff[k] + 32) * (double) ((b->xOff[k + 1] - b->xOff[k] + 32) / 32) * B.nPtrWords * 32;      // (Lo + 32) steps per strip
       if (need * 4 > budget) { set_error ("pair " + std::to_string (k) + " needs more device memory for its back-pointers than is free (" + std::to_string (need * 4) + " bytes)"); return 1; }
       if (!chunk.empty() && (words + need) * 4 > budget) break;
       chunk.push_back (k);

@@ -22,8 +22,8 @@
 // MODE 0: that Forward sweep.  MODE 1 / 2: Viterbi (viterbi.cpp:18-47) with / without back-pointers: the same
 // sweep in the log domain, FP64 add + strict '<' over each state's groups in the reference's candidate order
 // (bit-exact scores, first maximum wins); no frames.  A cell's pointers (ceil(log2(#groups)) bits per state,
-// MB_NPW 32-bit words) are stored as bp[((row * nStrips + strip) * MB_NPW + word) * 32 + lane]: every store of the
-// warp is one 128-byte line.
+// MB_NPW 32-bit words) are stored in sweep order, bp[((step * nStrips + strip) * MB_NPW + word) * 32 + lane] with step = row +
+// lane: every store of the warp is one 128-byte line (indexed by row the skewed lanes would scatter over 32 lines).
 #ifndef MB_BIG_SKELETON_H
 #define MB_BIG_SKELETON_H
 
@@ -188,7 +188,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
             unsigned pw[MB_NPW];
             mb_big_cell_vit (up, Lin, Lprev, Lown, a, tokb, r == 0 && col == 0, E, res, pw);
             if (MODE == 1) {
-              unsigned* dst = bp + ((int64_t) r * nStrips + strip) * (MB_NPW * 32);
+              unsigned* dst = bp + ((int64_t) t * nStrips + strip) * (MB_NPW * 32);      // by STEP, not by row: the lanes of a step are at different rows
 #pragma unroll
               for (int q = 0; q < MB_NPW; ++q) dst[q * 32] = pw[q];
             }
