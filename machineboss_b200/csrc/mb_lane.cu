@@ -439,7 +439,10 @@ int lane_prepare (mb_machine* m) {
   if (h->l2.ok) lane2_fill_weights (m, h);
   if (m->opt.get ("lane_host_only", 0)) return col_prepare (m, true);      // (diagnostic: build the programs without touching a device)
   if (lane_upload (m, h, true) || lane2_upload (m, h, true)) return 1;
-  if (col_prepare (m, false)) return 1;      // periodic machines (profile HMMs): the column engine takes the sweeps it can
+  if (col_prepare (m, false)) {      // periodic machines (profile HMMs): the column engine takes the sweeps it can; if it cannot be built, the sweeps here serve
+    if (m->opt.get ("verbose", 0)) fprintf (stderr, "lane engine: the column engine could not be prepared (%s); using the lane sweeps\n", mb_last_error());
+    col_destroy (m);
+  }
   MB_CUDA (cudaDeviceGetAttribute (&h->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   if (m->opt.get ("verbose", 0))
     fprintf (stderr, "lane engine: S=%d records=%lld (emitting rows %zu x %d tokens), bp %d bytes\n", S, (long long) h->nRec, h->emPerm.size() / std::max (nOut, 1), nOut, h->bpBytes);
