@@ -33,3 +33,19 @@ def test_split_mode_module_compiles():
     assert "mb_k_viterbi" in tail and "mb_k_forward_lin" in tail
     spills = [l for l in tail.splitlines() if "spill stores" in l]
     assert len(spills) == 4 and all(" 0 bytes spill stores" in l for l in spills), spills
+
+
+@pytest.mark.parametrize("name,cols", [("dnapsw_small", 10), ("protpsw_synth", 10), ("dnapsw_small", 5), ("protpsw_synth", 12)])
+def test_score_module_at_a_fitted_width_compiles(name, cols):
+    """The score module at a strip width fitted to a batch (mb_jit.cu ensure_fit_module: MB_C not a power of two, the lane's
+    Viterbi pointers in a padded 16-byte group, MB_TBPAD) is the same source as the wide module at that width: compile it."""
+    from machineboss_b200 import capi
+    fm = FlatMachine.from_json(load_golden(name)["machine"])
+    capi.set_option("jit_cv", cols)
+    try:
+        log = capi.jit_compile_check(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
+    finally:
+        capi.set_option("jit_cv", None)
+    assert "MB_C = %d" % cols in log
+    tail = log[log.index("Viterbi module"):]
+    assert "mb_k_viterbi" in tail and "mb_k_forward_lin" in tail
