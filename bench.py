@@ -702,7 +702,7 @@ def run_configs(capi, args):
         b = capi.Batch(x=np.zeros(0, np.uint8), x_off=np.zeros(n + 1, np.int64), y=y, y_off=y_off)
         entry("cfg5" if preset == "PF00516_protpsw" else "cfg5-core",
               "HMMER profile %s (%d states), Forward + Viterbi on 1 000 000 reads of 50 - 500 residues" % (preset.replace("_", " => "), mj["n_states"]),
-              "%d reads, lengths 50 - 500 (uniform, ragged)" % n, mj, b, n, timed_passes(capi, mach, b, ["forward", "viterbi_score", "viterbi"], reps=1))
+              "%d reads, lengths 50 - 500 (uniform, ragged)" % n, mj, b, n, timed_passes(capi, mach, b, ["forward", "viterbi_score", "viterbi"], reps=3))
         b.close(); mach.close()
     return out
 
