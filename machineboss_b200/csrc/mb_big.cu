@@ -42,6 +42,21 @@ struct BigEngine {
   // ~450); every other weight is scaled by sigma_src / sigma_self on the host, the result carries log sigma of the end state.
   std::vector<int> unitGroup;        // per state: index into groups, or -1
   double resLog = 0;
+  // FOLDED live-up values (linear sweep only).  The insert groups u -> d of one destination are usually PROPORTIONAL:
+  // w(u -> d, b) = c_u e(b) for every token b -- in a composed machine the emission belongs to the destination, the factor to
+  // the transition (prot2dna => dnapsw: 144 insert groups into 74 destinations, every destination's groups proportional).
+  // Then sum_u u(row above) w(u -> d, b) = e(b) F with F = sum_u c_u u, and what has to cross rows is F, one value per
+  // CLASS (destination, direction of e), not one per source state: 74 values per lane in shared memory instead of 139, two
+  // loads less per group, and twice the warps per SM.  The classes depend on the weights' ratios, so they are found
+  // numerically when the engine is prepared and checked again when the weights change (big_update_weights asks for the
+  // engine to be rebuilt if the partition moved).  The max-plus sweeps do not fold: (u + c) + e and u + (c + e) round differently.
+  struct FoldClass { int dst, emitOffLin; std::vector<std::pair<int, int>> members; };      // (group index, fold-factor slot; -1: factor one, the representative)
+  std::vector<FoldClass> classes;
+  std::vector<int> groupClass;       // per group: its class (insert groups), or -1
+  std::vector<int> emitOffLin;       // per group: offset in the linear emission table (match / delete groups), or -1
+  int nEmitLin = 0, nFold = 0, threadsLin = 128;
+  void* dFold = nullptr;             // __constant__ mb_big_fold in the module
+  size_t smemBytesLin = 0;
   int nEmit = 0, nSil = 0, threads = 128;
   std::string source;
   void* mod = nullptr;
@@ -97,6 +112,46 @@ static void big_plan (const mb_machine* m, BigEngine& B) {
   if (!m->opt.get ("jit_no_norm", 0))
     for (size_t gi = 0; gi < B.groups.size(); ++gi)
       if (B.groups[gi].type == T_SILENT && B.unitGroup[B.groups[gi].self] < 0) B.unitGroup[B.groups[gi].self] = (int) gi;
+  // fold classes of the insert groups, by destination: a group joins the first class of its destination whose representative's
+  // token vector it is a multiple of (same tokens present, constant log-ratio), else it opens a class
+  {
+    B.classes.clear();
+    B.groupClass.assign (B.groups.size(), -1);
+    B.emitOffLin.assign (B.groups.size(), -1);
+    B.nEmitLin = 0; B.nFold = 0;
+    const bool fold = !m->opt.get ("big_no_fold", 0);
+    auto vec = [&] (const BigGroup& gr) { std::vector<double> v ((size_t) gr.tableSize, -INFINITY); for (auto& e: gr.entries) v[e.first] = m->lw[e.second]; return v; };
+    for (size_t gi = 0; gi < B.groups.size(); ++gi) {
+      const BigGroup& gr = B.groups[gi];
+      if (gr.type == T_SILENT) continue;
+      if (gr.type != T_INSERT) { B.emitOffLin[gi] = B.nEmitLin; B.nEmitLin += gr.tableSize; continue; }
+      const std::vector<double> v = vec (gr);
+      int found = -1;
+      for (size_t c = 0; c < B.classes.size() && found < 0 && fold; ++c) {
+        if (B.classes[c].dst != gr.self) continue;
+        const std::vector<double> r = vec (B.groups[B.classes[c].members[0].first]);
+        bool same = true, any = false;
+        double ratio = 0;
+        for (size_t q = 0; q < v.size() && same; ++q) {
+          if ((v[q] > -INFINITY) != (r[q] > -INFINITY)) same = false;
+          else if (v[q] > -INFINITY) {
+            if (!std::isfinite (v[q]) || !std::isfinite (r[q])) same = false;
+            else if (!any) { ratio = v[q] - r[q]; any = true; }
+            else if (std::fabs ((v[q] - r[q]) - ratio) > 1e-12 * std::max (1.0, std::fabs (ratio))) same = false;
+          }
+        }
+        if (same && any) found = (int) c;
+      }
+      if (found < 0) {
+        BigEngine::FoldClass fc;
+        fc.dst = gr.self; fc.emitOffLin = B.nEmitLin; B.nEmitLin += gr.tableSize;
+        fc.members.push_back (std::make_pair ((int) gi, -1));
+        B.classes.push_back (fc);
+        found = (int) B.classes.size() - 1;
+      } else B.classes[found].members.push_back (std::make_pair ((int) gi, B.nFold++));
+      B.groupClass[gi] = found;
+    }
+  }
   // pointer fields, packed greedily into 32-bit words (no field straddles a word)
   B.groupStart.assign ((size_t) m->S + 1, 0);
   for (auto& gr: B.groups) B.groupStart[gr.self + 1]++;
@@ -138,8 +193,11 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
     int warps = 8;      // 255 registers per thread: at most 8 warps per SM
     if (m->opt.has ("big_warps")) warps = std::max (1, std::min (8, m->opt.get ("big_warps", 8)));
     // (192 KB, not all 227: what is left is the L1 that holds the spilled registers -- prot2dna => dnapsw ran 3 % faster with 4 warps than with 5)
+    int warpsLin = warps;
     while (warps > 1 && (size_t) (((std::max (B.nEmit, 1) + 1) & ~1) + warps * ((int) B.liveU.size() * 32 + 16 * nLL)) * 8 > 192 * 1024) --warps;
+    while (warpsLin > 1 && (size_t) (((std::max (B.nEmitLin, 1) + 1) & ~1) + warpsLin * ((int) B.classes.size() * 32 + 16 * nLL)) * 8 > 192 * 1024) --warpsLin;
     B.threads = 32 * warps;
+    B.threadsLin = 32 * warpsLin;
   }
   std::vector<int> uIdx ((size_t) S, -1), lIdx ((size_t) S, -1);
   for (size_t q = 0; q < B.liveU.size(); ++q) uIdx[B.liveU[q]] = (int) q;
@@ -149,18 +207,28 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   o << "typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
   o << "#define MB_S " << S << "\n#define MB_NLU " << B.liveU.size() << "\n#define MB_NLL " << nLL << "\n#define MB_NEMIT " << std::max (B.nEmit, 1)
     << "\n#define MB_BIG_THREADS " << B.threads << "\n";
+  o << "#define MB_NLU_LIN " << B.classes.size() << "\n#define MB_NEMIT_LIN " << std::max (B.nEmitLin, 1) << "\n#define MB_BIG_THREADS_LIN " << B.threadsLin << "\n";
   {      // which emission-table entries carry a transition (the others stay 0 / -inf): lets a host-side harness fill the tables
     std::string present ((size_t) std::max (B.nEmit, 1), '0');
     for (auto& gr: B.groups) if (gr.type != T_SILENT) for (auto& e: gr.entries) present[(size_t) gr.emitOff + e.first] = '1';
     o << "// MB_EMIT_PRESENT " << present << "\n// MB_NSIL " << B.nSil << "\n";
+    std::string presentLin ((size_t) std::max (B.nEmitLin, 1), '0');      // the sums' table: match / delete groups, and one vector per fold class (its representative's)
+    for (size_t g = 0; g < B.groups.size(); ++g) if (B.emitOffLin[g] >= 0) for (auto& e: B.groups[g].entries) presentLin[(size_t) B.emitOffLin[g] + e.first] = '1';
+    for (auto& fc: B.classes) for (auto& e: B.groups[fc.members[0].first].entries) presentLin[(size_t) fc.emitOffLin + e.first] = '1';
+    o << "// MB_EMIT_PRESENT_LIN " << presentLin << "\n// MB_NFOLD " << B.nFold << "\n";
   }
   o << "#define MB_NPW " << B.nPtrWords << "\n";
-  o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n__constant__ double mb_big_sil_log[" << std::max (B.nSil, 1) << "];\n\n";
+  o << "__constant__ double mb_big_sil[" << std::max (B.nSil, 1) << "];\n__constant__ double mb_big_sil_log[" << std::max (B.nSil, 1) << "];\n";
+  o << "__constant__ double mb_big_fold[" << std::max (B.nFold, 1) << "];      // factors of the folded live-up sums (BigEngine::classes)\n\n";
   // the cell: live-up states read from (and written back to) the lane's column of `up`, left / diagonal cells' states in L / D
   o << "__device__ __forceinline__ void mb_big_cell (double* __restrict__ up, const double (&L)[MB_NLL], const double (&D)[MB_NLL], double (&Lo)[MB_NLL], "
        "const int a, const int b, const bool origin, const double* __restrict__ E, double& res) {\n";
   std::vector<char> loaded ((size_t) S, 0);
   size_t gi = 0;
+  // what each state contributes to the folded sums: (class, factor slot)
+  std::vector<std::vector<std::pair<int, int>>> foldsOf ((size_t) S);
+  for (size_t c = 0; c < B.classes.size(); ++c) for (auto& mem: B.classes[c].members) foldsOf[B.groups[mem.first].other].push_back (std::make_pair ((int) c, mem.second));
+  std::vector<char> classUsed (B.classes.size(), 0), classStarted (B.classes.size(), 0);
   for (int d = 0; d < S; ++d) {
     bool first = true;
     if (B.unitGroup[d] >= 0) { o << "  double n" << d << " = n" << B.groups[B.unitGroup[d]].other << ";\n"; first = false; }      // the unit group: a copy
@@ -168,19 +236,29 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
       if ((int) gi == B.unitGroup[d]) continue;
       const BigGroup& gr = B.groups[gi];
       std::ostringstream src, w;
-      if (gr.type == T_INSERT) {
-        if (!loaded[gr.other]) { o << "  const double u" << gr.other << " = up[" << uIdx[gr.other] << " * 32];\n"; loaded[gr.other] = 1; }
-        src << "u" << gr.other; w << "E[" << gr.emitOff << " + b]";
-      } else if (gr.type == T_DELETE) { src << "L[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a]"; }
-      else if (gr.type == T_MATCH) { src << "D[" << lIdx[gr.other] << "]"; w << "E[" << gr.emitOff << " + a * " << m->nOut << " + b]"; }
+      if (gr.type == T_INSERT) {      // once per class: the folded sum of the row above times the class's token vector
+        const int c = B.groupClass[gi];
+        if (classUsed[c]) continue;
+        classUsed[c] = 1;
+        o << "  const double F" << c << " = up[" << c << " * 32];\n";
+        src << "F" << c; w << "E[" << B.classes[c].emitOffLin << " + b]";
+      } else if (gr.type == T_DELETE) { src << "L[" << lIdx[gr.other] << "]"; w << "E[" << B.emitOffLin[gi] << " + a]"; }
+      else if (gr.type == T_MATCH) { src << "D[" << lIdx[gr.other] << "]"; w << "E[" << B.emitOffLin[gi] << " + a * " << m->nOut << " + b]"; }
       else { src << "n" << gr.other; w << "mb_big_sil[" << gr.silIdx << "]"; }
       if (first) { o << "  double n" << d << " = " << src.str() << " * " << w.str() << ";\n"; first = false; }
       else o << "  n" << d << " = fma (" << src.str() << ", " << w.str() << ", n" << d << ");\n";
     }
     if (first) o << "  double n" << d << " = 0.0;\n";
     if (d == 0) o << "  if (origin) n0 = 1.0;\n";
+    for (auto& fo: foldsOf[d]) {      // n_d is final: add it to the sums it belongs to (its register can be released)
+      std::ostringstream term;
+      if (fo.second < 0) term << "n" << d; else term << "n" << d << " * mb_big_fold[" << fo.second << "]";
+      if (!classStarted[fo.first]) { o << "  double f" << fo.first << " = " << term.str() << ";\n"; classStarted[fo.first] = 1; }
+      else if (fo.second < 0) o << "  f" << fo.first << " += n" << d << ";\n";
+      else o << "  f" << fo.first << " = fma (n" << d << ", mb_big_fold[" << fo.second << "], f" << fo.first << ");\n";
+    }
   }
-  for (size_t q = 0; q < B.liveU.size(); ++q) o << "  up[" << q << " * 32] = n" << B.liveU[q] << ";\n";
+  for (size_t c = 0; c < B.classes.size(); ++c) o << "  up[" << c << " * 32] = f" << c << ";\n";
   for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
   if (B.liveL.empty()) o << "  Lo[0] = 0.0;\n";
   o << "  res = n" << S - 1 << ";\n}\n\n";
@@ -245,8 +323,9 @@ void big_destroy (mb_machine* m) {
 int big_update_weights (mb_machine* m) {
   BigEngine* B = be (m);
   if (!B) return 0;
-  std::vector<double> emit ((size_t) std::max (B->nEmit, 1), 0.), sil ((size_t) std::max (B->nSil, 1), 0.);
-  std::vector<double> emitLog (emit.size(), -INFINITY), silLog (sil.size(), -INFINITY);
+  std::vector<double> emit ((size_t) std::max (B->nEmitLin, 1), 0.), sil ((size_t) std::max (B->nSil, 1), 0.), foldF ((size_t) std::max (B->nFold, 1), 0.);
+  std::vector<double> emitLog ((size_t) std::max (B->nEmit, 1), -INFINITY), silLog (sil.size(), -INFINITY);
+  bool moved = false;      // the fold classes no longer fit the weights: the engine has to be generated again
   bool ok = true;
   const double lim = 24.0 * 0.6931471805599453;
   std::vector<double> ls ((size_t) m->S, 0.);      // log sigma per state; a silent group's source is an earlier state
@@ -259,21 +338,52 @@ int big_update_weights (mb_machine* m) {
     if (std::fabs (ls[d]) > 100. * 0.6931471805599453) ok = false;
   }
   B->resLog = ls[m->S - 1];
-  for (auto& gr: B->groups)
+  auto scaledOf = [&] (const BigGroup& gr, double lw) { return lw > -INFINITY ? lw + ls[gr.other] - ls[gr.self] : -INFINITY; };      // the linear sweep's weight, in normalised units
+  for (size_t gi = 0; gi < B->groups.size(); ++gi) {
+    const BigGroup& gr = B->groups[gi];
     for (auto& e: gr.entries) {
       const double lw = m->lw[e.second];
       if (std::isnan (lw) || lw == INFINITY || (std::isfinite (lw) && std::fabs (lw) > lim)) ok = false;
-      const double scaled = lw > -INFINITY ? lw + ls[gr.other] - ls[gr.self] : -INFINITY;      // the linear sweep's weight, in normalised units
+      const double scaled = scaledOf (gr, lw);
       if (std::isfinite (scaled) && std::fabs (scaled) > 2 * lim) ok = false;
       if (gr.type == T_SILENT) { sil[gr.silIdx] = std::exp (scaled); silLog[gr.silIdx] = lw; }
-      else { emit[(size_t) gr.emitOff + e.first] = std::exp (scaled); emitLog[(size_t) gr.emitOff + e.first] = lw; }
+      else {
+        emitLog[(size_t) gr.emitOff + e.first] = lw;
+        if (B->emitOffLin[gi] >= 0) emit[(size_t) B->emitOffLin[gi] + e.first] = std::exp (scaled);
+      }
     }
+  }
+  // fold classes: the representative's vector is the class's token table; every other member is a constant multiple of it
+  for (auto& fc: B->classes) {
+    const BigGroup& rep = B->groups[fc.members[0].first];
+    std::vector<double> r ((size_t) rep.tableSize, -INFINITY);
+    for (auto& e: rep.entries) { r[e.first] = scaledOf (rep, m->lw[e.second]); emit[(size_t) fc.emitOffLin + e.first] = std::exp (r[e.first]); }
+    for (size_t q = 1; q < fc.members.size(); ++q) {
+      const BigGroup& gr = B->groups[fc.members[q].first];
+      std::vector<double> v ((size_t) gr.tableSize, -INFINITY);
+      for (auto& e: gr.entries) v[e.first] = scaledOf (gr, m->lw[e.second]);
+      bool any = false;
+      double ratio = 0;
+      for (size_t t = 0; t < v.size(); ++t) {
+        if ((v[t] > -INFINITY) != (r[t] > -INFINITY)) moved = true;
+        else if (v[t] > -INFINITY) {
+          if (!any) { ratio = v[t] - r[t]; any = true; }
+          else if (!(std::fabs ((v[t] - r[t]) - ratio) <= 1e-9 * std::max (1.0, std::fabs (ratio)))) moved = true;
+        }
+      }
+      if (!any) moved = true;
+      if (std::fabs (ratio) > 2 * lim) ok = false;
+      foldF[fc.members[q].second] = std::exp (ratio);
+    }
+  }
   B->linearOK = ok;
+  if (moved) return 2;
   MB_CUDA (cudaSetDevice (m->device));
   MB_CUDA (cudaMemcpy (B->dEmit, emit.data(), emit.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (B->dSil, sil.data(), sil.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (B->dEmitLog, emitLog.data(), emitLog.size() * 8, cudaMemcpyHostToDevice));
   MB_CUDA (cudaMemcpy (B->dSilLog, silLog.data(), silLog.size() * 8, cudaMemcpyHostToDevice));
+  MB_CUDA (cudaMemcpy (B->dFold, foldF.data(), foldF.size() * 8, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -287,8 +397,8 @@ int big_prepare (mb_machine* m) {
   if (rt_load (cubin, &B->mod) || rt_function (B->mod, "mb_k_big_forward", &B->kForward)
       || rt_function (B->mod, "mb_k_big_viterbi", &B->kViterbi) || rt_function (B->mod, "mb_k_big_viterbi_score", &B->kViterbiScore)) return 1;
   size_t bytes = 0;
-  if (rt_global (B->mod, "mb_big_sil", &B->dSil, &bytes) || rt_global (B->mod, "mb_big_sil_log", &B->dSilLog, &bytes)) return 1;
-  MB_CUDA (cudaMalloc (&B->dEmit, (size_t) std::max (B->nEmit, 1) * 8));
+  if (rt_global (B->mod, "mb_big_sil", &B->dSil, &bytes) || rt_global (B->mod, "mb_big_sil_log", &B->dSilLog, &bytes) || rt_global (B->mod, "mb_big_fold", &B->dFold, &bytes)) return 1;
+  MB_CUDA (cudaMalloc (&B->dEmit, (size_t) std::max (B->nEmitLin, 1) * 8));
   MB_CUDA (cudaMalloc (&B->dEmitLog, (size_t) std::max (B->nEmit, 1) * 8));
   {      // traceback tables, one int32 array: [S+1] groupStart | [S] word | [S] shift | [S] bits | [G] type | [G] source | [G] idOff | ids
     std::vector<int32_t> plan;
@@ -307,13 +417,16 @@ int big_prepare (mb_machine* m) {
   MB_CUDA (cudaDeviceGetAttribute (&B->numSMs, cudaDevAttrMultiProcessorCount, m->device));
   const int warps = B->threads / 32, nLL = std::max<int> ((int) B->liveL.size(), 1);
   B->smemBytes = (size_t) (((std::max (B->nEmit, 1) + 1) & ~1) + warps * ((int) B->liveU.size() * 32 + 16 * nLL)) * 8;
-  if (rt_prepare (B->kForward, B->threads, B->smemBytes, &B->blocksPerSM) || rt_prepare (B->kViterbi, B->threads, B->smemBytes, &B->blocksPerSMV)
+  B->smemBytesLin = (size_t) (((std::max (B->nEmitLin, 1) + 1) & ~1) + (B->threadsLin / 32) * ((int) B->classes.size() * 32 + 16 * nLL)) * 8;
+  if (rt_prepare (B->kForward, B->threadsLin, B->smemBytesLin, &B->blocksPerSM) || rt_prepare (B->kViterbi, B->threads, B->smemBytes, &B->blocksPerSMV)
       || rt_prepare (B->kViterbiScore, B->threads, B->smemBytes, &B->blocksPerSMVS)) return 1;
   if (B->blocksPerSM < 1 || B->blocksPerSMV < 1 || B->blocksPerSMVS < 1) { set_error ("big engine: a kernel does not fit on an SM"); return 1; }
   if (m->opt.get ("verbose", 0))
-    fprintf (stderr, "big engine: S=%d groups=%zu (silent %d), live-up %zu, left-going %zu, emission table %d doubles, %zu B smem, %d CTA(s)/SM\n",
-             m->S, B->groups.size(), B->nSil, B->liveU.size(), B->liveL.size(), B->nEmit, B->smemBytes, B->blocksPerSM);
-  return big_update_weights (m);
+    fprintf (stderr, "big engine: S=%d groups=%zu (silent %d), live-up %zu (sums: %zu folded classes, %d warps per CTA; max-plus: %d), left-going %zu, emission table %d doubles, %zu / %zu B smem, %d CTA(s)/SM\n",
+             m->S, B->groups.size(), B->nSil, B->liveU.size(), B->classes.size(), B->threadsLin / 32, B->threads / 32, B->liveL.size(), B->nEmit, B->smemBytesLin, B->smemBytes, B->blocksPerSM);
+  const int rc = big_update_weights (m);
+  if (rc == 2) { set_error ("big engine: the fold classes do not fit the weights they were built from"); return 1; }
+  return rc;
 }
 
 bool big_wanted (const mb_machine* m, const mb_batch* b) {
@@ -342,7 +455,7 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   std::stable_sort (order.begin(), order.end(), [&] (int64_t p, int64_t q) { return cost (p) > cost (q); });
   int64_t maxLo = 0;
   for (int64_t k = 0; k < b->nPairs; ++k) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
-  const int warps = B.threads / 32, nLL = std::max<int> ((int) B.liveL.size(), 1);
+  const int warps = B.threadsLin / 32, nLL = std::max<int> ((int) B.liveL.size(), 1);
   const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) B.numSMs * B.blocksPerSM, (b->nPairs + warps - 1) / warps));
   const int64_t bndStride = 2 * (maxLo + 1) * (nLL + 1);
   b->wsOrderHoldsFull = false;
@@ -364,7 +477,7 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   A.resLog = B.resLog;
   void* params[1] = { &A };
   if (timing_begin (b)) return 1;
-  if (rt_launch (B.kForward, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params)) return 1;
+  if (rt_launch (B.kForward, (unsigned) grid, (unsigned) B.threadsLin, B.smemBytesLin, b->stream, params)) return 1;
   std::vector<int32_t> flag ((size_t) b->nPairs);
   MB_CUDA (cudaMemcpyAsync (loglike, dRes, (size_t) b->nPairs * 8, cudaMemcpyDeviceToHost, b->stream));
   MB_CUDA (cudaMemcpyAsync (flag.data(), dFlag, flag.size() * 4, cudaMemcpyDeviceToHost, b->stream));

@@ -49,14 +49,19 @@ template<int MODE>
 __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
   constexpr bool LIN = MODE == 0;
   const double ZERO = LIN ? 0.0 : __longlong_as_double (0xfff0000000000000LL);
+  // The sums keep FOLDED live-up values (mb_big.cu: one per class of proportional insert groups instead of one per source
+  // state) and their own emission table; the max-plus sweeps keep the sources themselves (folding would re-associate the
+  // additions and lose the bit-exact scores).
+  constexpr int NLU = LIN ? MB_NLU_LIN : MB_NLU;
+  constexpr int NEMIT = LIN ? MB_NEMIT_LIN : MB_NEMIT;
   extern __shared__ double mb_smem[];
   double* E = mb_smem;
-  for (int q = threadIdx.x; q < MB_NEMIT; q += blockDim.x) E[q] = A.emit[q];
+  for (int q = threadIdx.x; q < NEMIT; q += blockDim.x) E[q] = A.emit[q];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
   // shared memory: emission tables | per warp: live-up states v[q][lane] | per warp: MB_BIG_RESCALE staged boundary rows
-  double* up = mb_smem + ((MB_NEMIT + 1) & ~1) + warp * (MB_NLU * 32) + lane;
-  double* sIn = mb_smem + ((MB_NEMIT + 1) & ~1) + nWarps * (MB_NLU * 32) + warp * (MB_BIG_RESCALE * MB_NLL);
+  double* up = mb_smem + ((NEMIT + 1) & ~1) + warp * (NLU * 32) + lane;
+  double* sIn = mb_smem + ((NEMIT + 1) & ~1) + nWarps * (NLU * 32) + warp * (MB_BIG_RESCALE * MB_NLL);
   const int64_t wslot = (int64_t) blockIdx.x * nWarps + warp;
   double* bndA = A.bnd + wslot * A.bndStride;
   double* bndB = bndA + (A.bndStride >> 1);
@@ -79,7 +84,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
       const int col = strip * 32 + lane;
       const bool inCol = col <= Li;
       const int a = (col >= 1 && inCol) ? x[col - 1] - 1 : 0;
-      for (int q = 0; q < MB_NLU; ++q) up[q * 32] = ZERO;
+      for (int q = 0; q < NLU; ++q) up[q * 32] = ZERO;
       double Lown[MB_NLL], Lprev[MB_NLL];      // my last cell's left-going states; what I received a step ago (the diagonal cell)
 #pragma unroll
       for (int j = 0; j < MB_NLL; ++j) { Lown[j] = ZERO; Lprev[j] = ZERO; }
@@ -108,7 +113,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
           if (LIN && t > 0) {      // renormalise my values to [1, 2)
             int mh = 0;
             unsigned ml = 0xffffffffu;
-            for (int q = 0; q < MB_NLU; ++q) { const int h = __double2hiint (up[q * 32]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
+            for (int q = 0; q < NLU; ++q) { const int h = __double2hiint (up[q * 32]); mh = max (mh, h); ml = min (ml, (unsigned) (h - 1)); }
 #pragma unroll
             for (int j = 0; j < MB_NLL; ++j) {
               const int h = __double2hiint (Lown[j]), g = __double2hiint (Lprev[j]);
@@ -120,7 +125,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
               const int shift = min (ex - 1023, 1000);
               if (shift != 0) {
                 const double f = mb_pow2 (-shift);
-                for (int q = 0; q < MB_NLU; ++q) up[q * 32] *= f;
+                for (int q = 0; q < NLU; ++q) up[q * 32] *= f;
 #pragma unroll
                 for (int j = 0; j < MB_NLL; ++j) { Lown[j] *= f; Lprev[j] *= f; }
                 ecur += shift;
@@ -213,7 +218,7 @@ __device__ __forceinline__ void mb_big_run (const MBBigArgs& A) {
   }
 }
 
-extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_forward (const __grid_constant__ MBBigArgs A) { mb_big_run<0> (A); }
+extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS_LIN, 1) mb_k_big_forward (const __grid_constant__ MBBigArgs A) { mb_big_run<0> (A); }
 extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_viterbi (const __grid_constant__ MBBigArgs A) { mb_big_run<1> (A); }
 extern "C" __global__ void __launch_bounds__(MB_BIG_THREADS, 1) mb_k_big_viterbi_score (const __grid_constant__ MBBigArgs A) { mb_big_run<2> (A); }
 )MBSRC";

@@ -640,7 +640,13 @@ void wide_destroy (mb_machine* m) {
 
 int wide_update_weights (mb_machine* m) {
   if (lane_update_weights (m)) return 1;
-  if (big_update_weights (m)) return 1;
+  {
+    const int rc = big_update_weights (m);
+    if (rc == 2) {      // the new weights' ratios changed which insert groups are proportional: generate the big engine again
+      big_destroy (m);
+      if (big_supported (m, nullptr) && big_prepare (m)) big_destroy (m);      // (without it the table-driven sweeps here serve)
+    } else if (rc) return 1;
+  }
   WHost* h = wh (m);
   if (!h) return 0;
   wide_fill_weights (m, h);

@@ -33,13 +33,15 @@ int main (int argc, char** argv) {
   std::vector<int> x, y;
   for (int i = 0; i < Li; ++i) x.push_back (atoi (argv[3 + i]));
   for (int o = 0; o < Lo; ++o) y.push_back (atoi (argv[3 + Li + o]));
-  static const char present[] = "%(present)s";
-  std::vector<double> Elin (MB_NEMIT), Elog (MB_NEMIT);
-  for (int q = 0; q < MB_NEMIT; ++q) { Elin[q] = present[q] == '1' ? 1.0 : 0.0; Elog[q] = present[q] == '1' ? 0.0 : -INFINITY; }
+  static const char present[] = "%(present)s", presentLin[] = "%(present_lin)s";
+  std::vector<double> Elin (MB_NEMIT_LIN), Elog (MB_NEMIT);      // the sums read their own table: one token vector per fold class
+  for (int q = 0; q < MB_NEMIT; ++q) Elog[q] = present[q] == '1' ? 0.0 : -INFINITY;
+  for (int q = 0; q < MB_NEMIT_LIN; ++q) Elin[q] = presentLin[q] == '1' ? 1.0 : 0.0;
   for (int q = 0; q < %(nsil)d; ++q) { mb_big_sil[q] = 1.0; mb_big_sil_log[q] = 0.0; }
+  for (int q = 0; q < %(nfold)d; ++q) mb_big_fold[q] = 1.0;
   for (int mode = 0; mode < 2; ++mode) {
     const double ZERO = mode ? -INFINITY : 0.0;
-    std::vector<std::vector<double> > up (Li + 1, std::vector<double> ((MB_NLU ? MB_NLU : 1) * 32, ZERO));
+    std::vector<std::vector<double> > up (Li + 1, std::vector<double> (((MB_NLU > MB_NLU_LIN ? MB_NLU : MB_NLU_LIN) + 1) * 32, ZERO));
     std::vector<std::vector<double> > loPrev (Li + 1, std::vector<double> (MB_NLL, ZERO)), loCur = loPrev;
     double res = ZERO;
     for (int o = 0; o <= Lo; ++o) {
@@ -73,8 +75,12 @@ def test_generated_cells_on_the_host(name, shapes, monkeypatch, tmp_path):
     cells = "\n".join(l for l in cells.splitlines() if not l.startswith("typedef "))
     present = re.search(r"// MB_EMIT_PRESENT ([01]+)", src).group(1)
     nsil = int(re.search(r"// MB_NSIL (\d+)", src).group(1))
+    present_lin = re.search(r"// MB_EMIT_PRESENT_LIN ([01]+)", src).group(1)
+    nfold = int(re.search(r"// MB_NFOLD (\d+)", src).group(1))
+    if name == "prot2dna_dnapsw":      # with equal weights every destination's insert groups are proportional: one folded value each
+        assert nfold > 0 and int(re.search(r"#define MB_NLU_LIN (\d+)", src).group(1)) < int(re.search(r"#define MB_NLU (\d+)", src).group(1))
     cpp = tmp_path / "harness.cpp"
-    cpp.write_text(HARNESS % {"cells": cells, "present": present, "nsil": nsil})
+    cpp.write_text(HARNESS % {"cells": cells, "present": present, "nsil": nsil, "present_lin": present_lin, "nfold": nfold})
     exe = str(tmp_path / "harness")
     subprocess.run(["g++", "-O1", "-std=c++14", "-o", exe, str(cpp)], check=True, capture_output=True, text=True)
     ones = fm.with_weights(np.zeros_like(fm.lw))      # every transition weight 1

@@ -368,6 +368,36 @@ def test_big_engine_against_wide_engine():
     assert sc[1] == v and paths[1].tolist() == p.tolist()
 
 
+def test_big_engine_folded_sums_follow_the_weights():
+    """The big engine's Forward keeps one folded value per class of proportional insert groups (mb_big.cu); the classes depend on the
+    weights' ratios.  New weights that keep the ratios are uploaded; weights that break them (every transition perturbed on its own)
+    make the engine generate itself again -- and with folding switched off (big_no_fold) the same numbers come out."""
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("prot2dna_dnapsw")["machine"])
+    shapes = [(40, 260), (12, 90), (33, 140), (0, 5)]
+    pairs = [(synth_tokens(41, k, 0, li, fm.n_in), synth_tokens(41, k, 1, lo, fm.n_out)) for k, (li, lo) in enumerate(shapes)]
+    b = capi.Batch(pairs)
+    m = make_machine(capi, fm, 2, verbose=1)
+    plain = make_machine(capi, fm, 2, big_no_fold=1)
+    ll = capi.forward(m, b)
+    np.testing.assert_allclose(ll, capi.forward(plain, b), rtol=1e-12)
+    orc = Oracle(fm)
+    for k, (x, y) in enumerate(pairs):
+        assert close(ll[k], orc.forward(x, y, mode=LSE_EXACT), rel=1e-9), k
+    rng = np.random.default_rng(5)
+    for trial, lw in enumerate([fm.lw + 0.25, np.where(np.isfinite(fm.lw), fm.lw + rng.uniform(-0.3, 0.3, fm.lw.shape), fm.lw)]):
+        m.update_weights(lw)      # trial 0: every ratio kept; trial 1: none
+        fm2 = fm.with_weights(lw)
+        orc2 = Oracle(fm2)
+        ll2 = capi.forward(m, b)
+        assert b.last_redo() == 0
+        for k, (x, y) in enumerate(pairs):
+            assert close(ll2[k], orc2.forward(x, y, mode=LSE_EXACT), rel=1e-9), (trial, k)
+        sc, paths = capi.viterbi(m, b)
+        v, p = orc2.viterbi(*pairs[1])
+        assert sc[1] == v and paths[1].tolist() == p.tolist()
+
+
 def test_wide_engine_log_domain_rerun():
     """The trap machine through the wide engine: the scaled sweep flags the long pairs and the log-domain sweep redoes them."""
     capi = _capi()
