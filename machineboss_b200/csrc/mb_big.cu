@@ -229,6 +229,14 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   std::vector<std::vector<std::pair<int, int>>> foldsOf ((size_t) S);
   for (size_t c = 0; c < B.classes.size(); ++c) for (auto& mem: B.classes[c].members) foldsOf[B.groups[mem.first].other].push_back (std::make_pair ((int) c, mem.second));
   std::vector<char> classUsed (B.classes.size(), 0), classStarted (B.classes.size(), 0);
+  // a class's sum is complete after its last member's source state; it is stored then (the OLD sum read into a register first
+  // if the class's destination comes later in the state order), so that it does not occupy a register to the end of the cell
+  // (measured on B200, config 4: storing early costs the sums 12 % -- 234 registers become 255 -- while it gains the max-plus
+  // sweeps 3 - 49 %; option big_early_store turns it on for the sums too)
+  const bool earlyStore = m->opt.get ("big_early_store", 0) != 0;
+  std::vector<char> classStored (B.classes.size(), 0);
+  std::vector<int> classLast (B.classes.size(), -1);
+  for (size_t c = 0; c < B.classes.size(); ++c) for (auto& mem: B.classes[c].members) classLast[c] = std::max (classLast[c], B.groups[mem.first].other);
   for (int d = 0; d < S; ++d) {
     bool first = true;
     if (B.unitGroup[d] >= 0) { o << "  double n" << d << " = n" << B.groups[B.unitGroup[d]].other << ";\n"; first = false; }      // the unit group: a copy
@@ -238,9 +246,9 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
       std::ostringstream src, w;
       if (gr.type == T_INSERT) {      // once per class: the folded sum of the row above times the class's token vector
         const int c = B.groupClass[gi];
-        if (classUsed[c]) continue;
-        classUsed[c] = 1;
-        o << "  const double F" << c << " = up[" << c << " * 32];\n";
+        if (classUsed[c] == 2) continue;
+        if (!classUsed[c]) o << "  const double F" << c << " = up[" << c << " * 32];\n";
+        classUsed[c] = 2;
         src << "F" << c; w << "E[" << B.classes[c].emitOffLin << " + b]";
       } else if (gr.type == T_DELETE) { src << "L[" << lIdx[gr.other] << "]"; w << "E[" << B.emitOffLin[gi] << " + a]"; }
       else if (gr.type == T_MATCH) { src << "D[" << lIdx[gr.other] << "]"; w << "E[" << B.emitOffLin[gi] << " + a * " << m->nOut << " + b]"; }
@@ -256,9 +264,18 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
       if (!classStarted[fo.first]) { o << "  double f" << fo.first << " = " << term.str() << ";\n"; classStarted[fo.first] = 1; }
       else if (fo.second < 0) o << "  f" << fo.first << " += n" << d << ";\n";
       else o << "  f" << fo.first << " = fma (n" << d << ", mb_big_fold[" << fo.second << "], f" << fo.first << ");\n";
+      const int c = fo.first;
+      if (earlyStore && classLast[c] == d) {      // complete: store (a class may list the same source twice only through different groups; the last one closes it)
+        bool lastOfState = true;
+        for (auto& later: foldsOf[d]) if (&later > &fo && later.first == c) lastOfState = false;
+        if (lastOfState) {
+          if (!classUsed[c] && B.classes[c].dst > d) { o << "  const double F" << c << " = up[" << c << " * 32];\n"; classUsed[c] = 1; }
+          if (classUsed[c] || B.classes[c].dst <= d) { o << "  up[" << c << " * 32] = f" << c << ";\n"; classStored[c] = 1; }
+        }
+      }
     }
   }
-  for (size_t c = 0; c < B.classes.size(); ++c) o << "  up[" << c << " * 32] = f" << c << ";\n";
+  for (size_t c = 0; c < B.classes.size(); ++c) if (!classStored[c]) o << "  up[" << c << " * 32] = f" << c << ";\n";
   for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
   if (B.liveL.empty()) o << "  Lo[0] = 0.0;\n";
   o << "  res = n" << S - 1 << ";\n}\n\n";
@@ -268,7 +285,13 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
   o << "__device__ __forceinline__ void mb_big_cell_vit (double* __restrict__ up, const double (&L)[MB_NLL], const double (&D)[MB_NLL], double (&Lo)[MB_NLL], "
        "const int a, const int b, const bool origin, const double* __restrict__ E, double& res, unsigned (&pw)[MB_NPW]) {\n";
   o << "  const double NI = __longlong_as_double (0xfff0000000000000LL);\n";
+  for (int wd = 0; wd < B.nPtrWords; ++wd) o << "  unsigned pw" << wd << " = 0u;\n";
   std::fill (loaded.begin(), loaded.end(), 0);
+  // A live-up state's new value goes to shared memory as soon as it is final -- and its pointer into the packed word -- so that
+  // neither stays in a register to the end of the cell (139 doubles did: 584 - 856 bytes of spills per thread).  A consumer
+  // further down the state order still needs the OLD value: it is read into a register just before the store.
+  std::vector<int> lastConsumer ((size_t) S, -1);
+  for (auto& gr: B.groups) if (gr.type == T_INSERT) lastConsumer[gr.other] = std::max (lastConsumer[gr.other], gr.self);
   gi = 0;
   for (int d = 0; d < S; ++d) {
     int k = 0;
@@ -286,15 +309,15 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
     }
     if (k == 0) o << "  double n" << d << " = NI;\n";
     if (d == 0) o << "  if (origin) n0 = 0.0;\n";
+    if (k > 0 && B.ptrBits[d]) o << "  pw" << B.ptrWord[d] << " |= p" << d << " << " << B.ptrShift[d] << ";\n";
+    if (uIdx[d] >= 0) {
+      if (lastConsumer[d] > d && !loaded[d]) { o << "  const double u" << d << " = up[" << uIdx[d] << " * 32];\n"; loaded[d] = 1; }
+      o << "  up[" << uIdx[d] << " * 32] = n" << d << ";\n";
+    }
   }
-  for (size_t q = 0; q < B.liveU.size(); ++q) o << "  up[" << q << " * 32] = n" << B.liveU[q] << ";\n";
   for (size_t q = 0; q < B.liveL.size(); ++q) o << "  Lo[" << q << "] = n" << B.liveL[q] << ";\n";
   if (B.liveL.empty()) o << "  Lo[0] = NI;\n";
-  for (int wd = 0; wd < B.nPtrWords; ++wd) {
-    o << "  pw[" << wd << "] = 0u";
-    for (int d = 0; d < S; ++d) if (B.ptrBits[d] && B.ptrWord[d] == wd) o << " | (p" << d << " << " << B.ptrShift[d] << ")";
-    o << ";\n";
-  }
+  for (int wd = 0; wd < B.nPtrWords; ++wd) o << "  pw[" << wd << "] = pw" << wd << ";\n";
   o << "  res = n" << S - 1 << ";\n}\n";
   o << kBigSkeleton;
   B.source = o.str();
@@ -456,7 +479,9 @@ int big_forward (mb_machine* m, mb_batch* b, double* loglike) {
   int64_t maxLo = 0;
   for (int64_t k = 0; k < b->nPairs; ++k) maxLo = std::max (maxLo, b->yOff[k + 1] - b->yOff[k]);
   const int warps = B.threadsLin / 32, nLL = std::max<int> ((int) B.liveL.size(), 1);
-  const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) B.numSMs * B.blocksPerSM, (b->nPairs + warps - 1) / warps));
+  // one CTA per SM as soon as there are that many pairs (warps pull pairs from a counter; with fewer pairs than warps the pairs
+  // spread over all SMs instead of filling half of them: 592 pairs on 8-warp CTAs would otherwise occupy 74 SMs)
+  const int64_t grid = std::max<int64_t> (1, std::min<int64_t> ((int64_t) B.numSMs * B.blocksPerSM, b->nPairs));
   const int64_t bndStride = 2 * (maxLo + 1) * (nLL + 1);
   b->wsOrderHoldsFull = false;
   int64_t* dOrder = (int64_t*) ws_reserve (b, WS_ORDER, order.size() * 8);
@@ -588,7 +613,7 @@ int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
   A.resLog = 0;
   void* params[1] = { &A };
   auto launch = [&] (const std::vector<int64_t>& work, const int64_t* dOrder) {
-    const int64_t grid = std::max<int64_t> (1, std::min<int64_t> (maxGrid, ((int64_t) work.size() + warps - 1) / warps));
+    const int64_t grid = std::max<int64_t> (1, std::min<int64_t> (maxGrid, (int64_t) work.size()));
     A.order = dOrder; A.nWork = (int64_t) work.size();
     MB_CUDA (cudaMemsetAsync (dCounter, 0, 8, b->stream));
     return rt_launch (trace ? B.kViterbi : B.kViterbiScore, (unsigned) grid, (unsigned) B.threads, B.smemBytes, b->stream, params);
