@@ -27,7 +27,7 @@ static const char* const kOptionNames[] = {
   "jit_unroll",                                               // unroll factor of the steady-state step loop (1 - 4)
   "jit_fit_c",                                                // > 0: sweep with a score module of this many columns per lane whenever the batch fits one strip; 0: never fit a module to a batch
   "jit_split",                                                // 0: never split a pair over the warps of a CTA, 1: always (when it has more than one strip)
-  "lane_r", "lane_warps", "no_lane", "lane_old", "lane_bs", "lane_la", "lane_wn", "lane_host_only", "lane_warps_per_cta", "wide_g", "wide_w", "no_big", "big_warps", "big_debug", "big_no_fold", "big_early_store",
+  "lane_r", "lane_warps", "no_lane", "lane_old", "lane_bs", "lane_la", "lane_wn", "lane_host_only", "lane_warps_per_cta", "wide_g", "wide_w", "no_big", "big_warps", "big_debug", "big_no_fold", "big_early_store", "big_smem_kb",
   "no_col", "col_no_traceback", "col_bp_budget_mb", "col_c", "col_sil_regs", "col_threads", "col_minblocks", "col_r", "col_bnd_budget_mb",      // column engine (mb_col.cu)
 };
 

@@ -194,8 +194,9 @@ static void big_generate (const mb_machine* m, BigEngine& B) {
     if (m->opt.has ("big_warps")) warps = std::max (1, std::min (8, m->opt.get ("big_warps", 8)));
     // (192 KB, not all 227: what is left is the L1 that holds the spilled registers -- prot2dna => dnapsw ran 3 % faster with 4 warps than with 5)
     int warpsLin = warps;
-    while (warps > 1 && (size_t) (((std::max (B.nEmit, 1) + 1) & ~1) + warps * ((int) B.liveU.size() * 32 + 16 * nLL)) * 8 > 192 * 1024) --warps;
-    while (warpsLin > 1 && (size_t) (((std::max (B.nEmitLin, 1) + 1) & ~1) + warpsLin * ((int) B.classes.size() * 32 + 16 * nLL)) * 8 > 192 * 1024) --warpsLin;
+    const size_t cap = (size_t) std::max (48, std::min (227, m->opt.get ("big_smem_kb", 192))) * 1024;
+    while (warps > 1 && (size_t) (((std::max (B.nEmit, 1) + 1) & ~1) + warps * ((int) B.liveU.size() * 32 + 16 * nLL)) * 8 > cap) --warps;
+    while (warpsLin > 1 && (size_t) (((std::max (B.nEmitLin, 1) + 1) & ~1) + warpsLin * ((int) B.classes.size() * 32 + 16 * nLL)) * 8 > cap) --warpsLin;
     B.threads = 32 * warps;
     B.threadsLin = 32 * warpsLin;
   }
@@ -656,6 +657,18 @@ int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen) {
       chunk.push_back (k);
       bpOff.push_back ((int64_t) words);
       words += need;
+    }
+    // A pair is one warp's work from start to end, so a chunk costs as many "waves" as its pairs fill the resident warps:
+    // when pairs remain for another chunk, cut this one back to whole waves (1000 pairs of which 840 fit: 592 + 408 are two
+    // waves, 840 + 160 would be three)
+    {
+      const size_t resident = (size_t) maxGrid * warps;
+      if (c1 < order.size() && chunk.size() > resident) {
+        const size_t keep = chunk.size() / resident * resident;
+        c1 = c0 + keep;
+        words = (double) bpOff[keep];
+        chunk.resize (keep); bpOff.resize (keep);
+      }
     }
     c0 = c1;
     BigBuf dBp, dBpOff, dOrder, dLen, dOutOff;
