@@ -24,7 +24,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:jit_
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-configs --em-pairs 256 > gpurun_out/ncu_tb_run.log 2>&1
 # the engines of the other configs: the generated thread-per-cell sweep (config 4 machine) ...
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mb_k_big_forward -c 1 -o gpurun_out/prof_mb_k_big_forward \
-    python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 592 --li 300 --lo 1000 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_big_run.log 2>&1
+    python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 1184 --li 300 --lo 1000 --engines 2 --no-trace --reps 1 > gpurun_out/ncu_big_run.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:mb_k_big_viterbi$' -c 1 -o gpurun_out/prof_mb_k_big_viterbi \
+    python tools/bench_wide.py --machine prot2dna_dnapsw --pairs 592 --li 300 --lo 1000 --engines 2 --reps 1 > gpurun_out/ncu_bigv_run.log 2>&1
 # ... and the profile sweeps (config 5 machine): the column engine's strip kernel, and the lane engine's windowed sweep it replaced
 READS=32768 VARIANTS='[{}]' timeout 600 ncu --set full --clock-control none --import-source on -k regex:mb_k_col_sum -c 1 -o gpurun_out/prof_mb_k_col_sum \
     python tools/lane_variants.py > gpurun_out/ncu_col_run.log 2>&1
