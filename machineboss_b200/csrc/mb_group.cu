@@ -142,6 +142,10 @@ struct mb_group {
   std::vector<int> devices;
   std::vector<std::unique_ptr<Worker>> workers;
   std::vector<nccl_comm> comms;      // empty: counts are added on the host
+  // machines and batches of the group keep it alive: mb_group_destroy with children still around only marks it, and the last
+  // child's destruction frees it (a caller that tears its handles down in any order -- an interpreter at exit -- stays safe)
+  int children = 0;
+  bool released = false;
   // job(d) on every device's thread at once; the first failure's message becomes this thread's last error
   int run (const std::function<int (int)>& job) {
     for (size_t d = 0; d < workers.size(); ++d) workers[d]->start ([=] { return job ((int) d); });
@@ -211,10 +215,19 @@ int mb_group_info (const mb_group* g, int32_t* nDevices, int32_t* devices, int32
   return 0;
 }
 
-void mb_group_destroy (mb_group* g) {
-  if (!g) return;
+static void group_free (mb_group* g) {
   for (nccl_comm c: g->comms) if (c) g_nccl.CommDestroy (c);
   delete g;
+}
+
+static void group_child_gone (mb_group* g) {
+  if (--g->children == 0 && g->released) group_free (g);
+}
+
+void mb_group_destroy (mb_group* g) {
+  if (!g) return;
+  if (g->children > 0) { g->released = true; return; }
+  group_free (g);
 }
 
 int mb_group_machine_create (mb_group* g, mb_gmachine** out, int32_t nStates, int32_t nInTok, int32_t nOutTok, int64_t nTrans,
@@ -223,6 +236,7 @@ int mb_group_machine_create (mb_group* g, mb_gmachine** out, int32_t nStates, in
   *out = nullptr;
   mb_gmachine* gm = new mb_gmachine;
   gm->g = g; gm->S = nStates; gm->T = nTrans;
+  ++g->children;
   gm->m.assign (g->devices.size(), nullptr);
   gm->dReduce.assign (g->devices.size(), nullptr);
   const Options opts = thread_options();      // the caller's defaults apply to every replica
@@ -262,7 +276,9 @@ void mb_group_machine_destroy (mb_gmachine* gm) {
     if (gm->dReduce[d]) cudaFree (gm->dReduce[d]);
     return 0;
   });
+  mb_group* g = gm->g;
   delete gm;
+  group_child_gone (g);
 }
 
 int mb_group_batch_create (mb_group* g, mb_gbatch** out, int64_t nPairs, const uint8_t* inTokens, const int64_t* inOff,
@@ -275,6 +291,7 @@ int mb_group_batch_create (mb_group* g, mb_gbatch** out, int64_t nPairs, const u
   const int nDev = (int) g->devices.size();
   mb_gbatch* gb = new mb_gbatch;
   gb->g = g; gb->nPairs = nPairs;
+  ++g->children;
   gb->shardOf.assign ((size_t) nPairs, 0);
   gb->load.assign ((size_t) nDev, 0.);
   gb->pairsOf.assign ((size_t) nDev, std::vector<int64_t>());
@@ -324,7 +341,9 @@ int mb_group_batch_shard (const mb_gbatch* gb, int32_t* deviceOfPair, double* ce
 void mb_group_batch_destroy (mb_gbatch* gb) {
   if (!gb) return;
   gb->g->run ([&] (int d) { if (gb->b[d]) mb_batch_destroy (gb->b[d]); return 0; });
+  mb_group* g = gb->g;
   delete gb;
+  group_child_gone (g);
 }
 
 }  // extern "C"
