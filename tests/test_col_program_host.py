@@ -85,3 +85,23 @@ def test_transitions_that_skip_a_node_are_declined():
     fm = synthetic_profile(skip=True)
     _, info = capi.col_emulate(fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw, np.zeros(0, np.uint8), 0)
     assert info[0] == 0
+
+
+@pytest.mark.parametrize("n_nodes,n_out,seed", [(70, 2, 1), (101, 20, 2), (66, 3, 3), (200, 4, 4)])
+def test_synthetic_profiles_of_other_shapes(n_nodes, n_out, seed):
+    """The same hand-made generator at other sizes, alphabets and weights: the analysis must find the period of 3 whatever the
+    number of nodes (also when it is not a multiple of the columns per lane), and the program must reproduce the oracle."""
+    from machineboss_b200 import capi
+    fm = synthetic_profile(n_nodes=n_nodes, n_out=n_out, seed=seed)
+    args = (fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout, fm.lw)
+    orc = Oracle(fm)
+    x = np.zeros(0, np.uint8)
+    for k, lo in enumerate([1, 9, 33]):
+        y = synth_tokens(43 + seed, k, 1, lo, fm.n_out)
+        f, info = capi.col_emulate(*args, y, 0)
+        assert info[0] == 1 and info[1] == 3 and info[1] * info[3] + info[4] + info[5] == fm.n_states, info
+        want = orc.forward(x, y, mode=LSE_EXACT)
+        assert abs(f - want) <= 1e-10 * max(1.0, abs(want)), (lo, f, want)
+        v, _, walked = capi.col_emulate(*args, y, 1, path=True)
+        want_v, want_p = orc.viterbi(x, y)
+        assert v == want_v and walked.tolist() == want_p.tolist(), lo
