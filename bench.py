@@ -637,12 +637,6 @@ def run_ingest(n_pairs=100000, length=300):
         if r.returncode != 0:
             return {"unavailable": r.stderr[-200:]}
         out.update(json.loads(r.stdout))
-        # the same files cut at record starts and parsed on 8 host threads (--ingest-threads; not the default: on a host with
-        # rationed cores the pieces only add a copy)
-        r = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", paths[0], paths[1], "--ingest-only", "--ingest-threads", "8"], capture_output=True, text=True)
-        if r.returncode == 0:
-            par = json.loads(r.stdout)
-            out["threads8"] = {"seconds": par["seconds"], "pairs_per_s": par["pairs_per_s"], "same_checksum": par["checksum"] == out.get("checksum")}
     return out
 
 

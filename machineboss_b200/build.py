@@ -52,7 +52,7 @@ def build_host(force: bool = False) -> str:
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     build()
-    cmd = ["g++", "-std=c++14", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-lz", "-pthread", "-Wl,-rpath," + HERE]
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", src, "-o", CLI, "-L" + HERE, "-lmachineboss_b200", "-lz", "-Wl,-rpath," + HERE]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)

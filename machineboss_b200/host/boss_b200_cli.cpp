@@ -117,7 +117,6 @@ int main (int argc, char** argv) {
       else if (f == "--fast-ingest") fastIngest = true;      // -D lists go straight to packed tokens (boss_b200_ingest.h); -L / -V only
       else if (f == "--paired-fasta") { fastIngest = true; pairedFastaIn = next(); pairedFastaOut = next(); }      // record k of one file with record k of the other
       else if (f == "--ingest-only") { fastIngest = true; ingestOnly = true; }      // time the ingest, touch no device
-      else if (f == "--ingest-threads") ingest::ingestThreads() = atoi (next().c_str());      // host threads of the FASTA ingest (default 1; 0: one per hardware thread, at most 16)
       else if (f == "--api") useApi = true;      // route the verbs through the api.h free functions (Machine, Params, SeqPair), pair by pair
       else if (f == "--gpus") hostGpuLimit() = atoi (next().c_str());      // lists of pairs use this many GPUs (default: every visible one)
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
@@ -189,7 +188,7 @@ int main (int argc, char** argv) {
       const double secs = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
       if (ingestOnly) {
         cout << "{\"pairs\":" << pp.size() << ",\"residues\":" << pp.residues() << ",\"file_bytes\":" << fileBytes << ",\"seconds\":" << secs
-             << ",\"pairs_per_s\":" << (double) pp.size() / secs << ",\"MB_per_s\":" << (double) fileBytes / 1e6 / secs << ",\"checksum\":\"" << packedChecksum (pp) << "\"}" << endl;
+             << ",\"pairs_per_s\":" << (double) pp.size() / secs << ",\"MB_per_s\":" << (double) fileBytes / 1e6 / secs << "}" << endl;
         return EXIT_SUCCESS;
       }
       if (!(doL || doV) || doA || doC || doT) throw runtime_error ("--fast-ingest serves -L and -V");

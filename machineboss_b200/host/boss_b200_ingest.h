@@ -15,9 +15,6 @@
 
 #include <cstring>
 
-#include <exception>
-#include <thread>
-
 #include "boss_b200.h"
 
 namespace MachineBoss {
@@ -149,8 +146,9 @@ inline PackedPairs packedFromSeqPairListJson (const string& text, const Evaluate
 
 namespace ingest {
   template<class Tok>
-  inline void fasta (const char* p, const char* end, const FastTokens<Tok>& tok, vector<uint8_t>& seq, vector<int64_t>& off, vector<string>& names) {
-    seq.resize ((size_t) (end - p));      // at most one token per byte of the file: written through a pointer, trimmed at the end
+  inline void fasta (const string& text, const FastTokens<Tok>& tok, vector<uint8_t>& seq, vector<int64_t>& off, vector<string>& names) {
+    const char* p = text.data(); const char* end = p + text.size();
+    seq.resize (text.size());      // at most one token per byte of the file: written through a pointer, trimmed at the end
     uint8_t* out = seq.data();
     bool open = false;
     while (p < end) {
@@ -178,71 +176,12 @@ namespace ingest {
   }
 }
 
-namespace ingest {
-  template<class Tok>
-  inline void fasta (const string& text, const FastTokens<Tok>& tok, vector<uint8_t>& seq, vector<int64_t>& off, vector<string>& names) {
-    fasta (text.data(), text.data() + text.size(), tok, seq, off, names);
-  }
-
-  // The same over `threads` host threads: the file is cut at record starts ("\n>") into pieces of about equal size, every piece
-  // parsed on its own (tokens, record ends relative to the piece, names), the pieces concatenated in order.  Files below
-  // `minBytes` and threads <= 1 take the serial path.  An unknown symbol throws from the calling thread as the serial path does.
-  inline int& ingestThreads() { static int n = 1; return n; }      // 1: the serial pass (the default: on a host whose cores are rationed the pieces only add a copy); 0: one per hardware thread, at most 16
-  template<class Tok>
-  inline void fastaParallel (const string& text, const FastTokens<Tok>& tok, vector<uint8_t>& seq, vector<int64_t>& off, vector<string>& names, size_t minBytes = 4u << 20) {
-    int threads = ingestThreads() > 0 ? ingestThreads() : (int) std::min (16u, std::max (1u, std::thread::hardware_concurrency()));
-    if (threads <= 1 || text.size() < minBytes) { fasta (text, tok, seq, off, names); return; }
-    vector<size_t> cut (1, 0);      // piece p is [cut[p], cut[p + 1])
-    for (int p = 1; p < threads; ++p) {
-      size_t at = text.size() / (size_t) threads * (size_t) p;
-      at = text.find ("\n>", at);
-      if (at == string::npos) break;
-      if (at + 1 > cut.back()) cut.push_back (at + 1);
-    }
-    cut.push_back (text.size());
-    const size_t nPieces = cut.size() - 1;
-    struct Piece { vector<uint8_t> seq; vector<int64_t> off; vector<string> names; std::exception_ptr err; };
-    vector<Piece> piece (nPieces);
-    vector<std::thread> pool;
-    for (size_t p = 0; p < nPieces; ++p)
-      pool.emplace_back ([&, p] {
-        try { fasta (text.data() + cut[p], text.data() + cut[p + 1], tok, piece[p].seq, piece[p].off, piece[p].names); }
-        catch (...) { piece[p].err = std::current_exception(); }
-      });
-    for (auto& t: pool) t.join();
-    for (auto& pc: piece) if (pc.err) std::rethrow_exception (pc.err);
-    size_t total = 0, records = 0;
-    for (auto& pc: piece) { total += pc.seq.size(); records += pc.off.size(); }
-    seq.resize (total);
-    off.reserve (off.size() + records);
-    names.reserve (names.size() + records);
-    size_t base = 0;
-    for (auto& pc: piece) {
-      if (!pc.seq.empty()) memcpy (seq.data() + base, pc.seq.data(), pc.seq.size());
-      for (int64_t e: pc.off) off.push_back ((int64_t) base + e);
-      for (auto& n: pc.names) names.push_back (std::move (n));
-      base += pc.seq.size();
-    }
-  }
-}
-
 inline PackedPairs packedFromFasta (const string& inputText, const string& outputText, const EvaluatedMachine& m) {
   PackedPairs pp;
-  ingest::fastaParallel (inputText, ingest::FastTokens<InputTokenizer> (m.inputTokenizer), pp.x, pp.xOff, pp.xName);
-  ingest::fastaParallel (outputText, ingest::FastTokens<OutputTokenizer> (m.outputTokenizer), pp.y, pp.yOff, pp.yName);
+  ingest::fasta (inputText, ingest::FastTokens<InputTokenizer> (m.inputTokenizer), pp.x, pp.xOff, pp.xName);
+  ingest::fasta (outputText, ingest::FastTokens<OutputTokenizer> (m.outputTokenizer), pp.y, pp.yOff, pp.yName);
   if (pp.xOff.size() != pp.yOff.size()) throw runtime_error ("paired FASTA files hold different numbers of sequences");
   return pp;
-}
-
-// a checksum of the packed list (FNV-1a over tokens and offsets): lets two ingest paths be compared without a device
-inline uint64_t packedChecksum (const PackedPairs& pp) {
-  uint64_t h = 1469598103934665603ull;
-  auto mix = [&] (const void* p, size_t n) { const unsigned char* c = (const unsigned char*) p; for (size_t q = 0; q < n; ++q) { h ^= c[q]; h *= 1099511628211ull; } };
-  mix (pp.x.data(), pp.x.size()); mix (pp.y.data(), pp.y.size());
-  mix (pp.xOff.data(), pp.xOff.size() * 8); mix (pp.yOff.data(), pp.yOff.size() * 8);
-  for (auto& n: pp.xName) mix (n.data(), n.size());
-  for (auto& n: pp.yName) mix (n.data(), n.size());
-  return h;
 }
 
 // the packed list on every GPU of the box (as ListBatch, without SeqPair objects): Forward log-likelihoods / Viterbi scores

@@ -216,26 +216,6 @@ def test_fast_ingest_reads_lists_and_fasta_without_a_device(tmp_path):
     assert r.returncode != 0 and "alignment" in r.stderr
 
 
-def test_parallel_fasta_ingest_equals_the_serial_one(tmp_path):
-    """Files above 4 MB are cut at record starts and parsed on several host threads (boss_b200_ingest.h fastaParallel): the packed
-    tokens, offsets and names -- their checksum -- must be those of the serial pass, whatever the number of threads; an unknown
-    symbol in a later piece still fails the call."""
-    cli = _cli()
-    fa_in, fa_out, _ = _protein_files(40000, 110, str(tmp_path))      # 4.9 MB and 4.7 MB
-    sums = []
-    for threads in (1, 2, 5, 16):
-        r = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", fa_in, fa_out, "--ingest-only", "--ingest-threads", str(threads)],
-                           capture_output=True, text=True, check=True)
-        got = json.loads(r.stdout)
-        assert got["pairs"] == 40000 and got["residues"] == 40000 * (110 + 107), got
-        sums.append(got["checksum"])
-    assert len(set(sums)) == 1, sums
-    with open(fa_in, "a") as f:
-        f.write(">late\nACDEFZ\n")
-    r = subprocess.run([cli, "--preset", "protpsw", "--paired-fasta", fa_in, fa_in, "--ingest-only", "--ingest-threads", "4"], capture_output=True, text=True)
-    assert r.returncode != 0 and "Can't tokenize symbol Z" in r.stderr
-
-
 @pytest.mark.gpu
 def test_fast_ingest_scores_equal_the_general_reader(tmp_path):
     """-L and -V through the packed path (--fast-ingest, --paired-fasta) print what the SeqPairList path prints."""
