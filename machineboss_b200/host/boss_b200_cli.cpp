@@ -88,6 +88,8 @@ int main (int argc, char** argv) {
     string envMode;
     long long sampleSeed = 1;
     int postTransTop = 0;
+    bool doDownsample = false;
+    double downsampleSize = 1., downsampleProb = 0.;
     bool fastIngest = false, ingestOnly = false;
     string pairedFastaIn, pairedFastaOut;
     for (int a = 1; a < argc; ++a) {
@@ -112,6 +114,8 @@ int main (int argc, char** argv) {
       else if (f == "-C" || f == "--counts") doC = true;
       else if (f == "--envelope") envMode = next();      // full | path | <width>: print each pair's Envelope (t/src/testenv.cpp; no device needed)
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
+      else if (f == "--downsample-size") { doDownsample = true; downsampleSize = atof (next().c_str()); }      // boss.cpp:487-490: which transitions Machine::downsample keeps
+      else if (f == "--downsample-prob") { doDownsample = true; downsampleProb = atof (next().c_str()); }
       else if (f == "--post-trans") postTransTop = atoi (next().c_str());      // the top of BackwardMatrix::postTransQueue and the trace from its first entry
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "--fast-ingest") fastIngest = true;      // -D lists go straight to packed tokens (boss_b200_ingest.h); -L / -V only
@@ -160,6 +164,23 @@ int main (int argc, char** argv) {
       const MachineObjective objective (machine, counts, constraints, machine.funcs);
       objective.optimize (start).writeJson (cout);
       cout << endl;
+      return EXIT_SUCCESS;
+    }
+
+    if (doDownsample) {   // Machine::downsample's selection (machine.cpp:2036-2082) on a symbolic, toposorted, acyclic machine
+      if (!symbolic) throw runtime_error ("--downsample-size / --downsample-prob need a symbolic --machine");
+      Machine withParams = machine;
+      withParams.funcs = machine.funcs.combine (seed, true);
+      const vector<vector<bool>> allowed = downsampleTransitions (withParams, downsampleSize, downsampleProb);
+      size_t kept = 0, total = 0;
+      for (const auto& row: allowed) for (bool v: row) { ++total; if (v) ++kept; }
+      cout << "{\"nTransitions\":" << total << ",\"kept\":" << kept << ",\"allowed\":[";
+      for (size_t s = 0; s < allowed.size(); ++s) {
+        cout << (s ? "," : "") << "[";
+        for (size_t t = 0; t < allowed[s].size(); ++t) cout << (t ? "," : "") << (allowed[s][t] ? 1 : 0);
+        cout << "]";
+      }
+      cout << "]}" << endl;
       return EXIT_SUCCESS;
     }
 

@@ -567,6 +567,44 @@ struct MachineFitter {
 // Like api.cpp:31-75 each call evaluates the machine anew; the forms taking an EvaluatedMachine (boss_b200.h) skip
 // that.  A call on ONE pair pays a device round trip for a single matrix: lists belong in forwardBackwardCounts
 // (Machine, Params, SeqPairList), forwardLogLikes / viterbiLogLikes, or MachineFitter.
+// The selection of Machine::downsample (machine.cpp:2036-2082): which transitions of an acyclic, topologically sorted machine
+// stay when only the most probable ones are kept.  All labels are dropped (the "null" machine), Forward and Backward are filled
+// for the empty sequence pair -- one cell, every transition silent -- and the (cell, transition) posteriors are taken from the
+// top of BackwardMatrix::postTransQueue: each is traced back to the start and on to the end through the best transitions, every
+// transition on the way is kept, a trace stops where it meets one already kept; until maxProportion of the transitions are kept
+// or the next posterior falls below minPostProb.  Returns allowed[state][transIndex].  (What the reference does with the mask
+// afterwards -- subgraph, ergodicMachine, eliminateRedundantStates -- is machine algebra, outside this path.)
+inline vector<vector<bool>> downsampleTransitions (const Machine& machine, double maxProportionOfTransitionsToKeep, double minPostProbOfSelectedTransitions = 0.) {
+  Machine null (machine);
+  vector<vector<bool>> transAllowed;
+  size_t nTransNull = 0;
+  for (auto& ms: null.state) {
+    for (auto& mt: ms.trans) { mt.in = mt.out = string(); if (mt.dest <= (StateIndex) (&ms - &null.state[0])) throw runtime_error ("Machine must be acyclic & topologically sorted before downsampling can take place"); }
+    transAllowed.push_back (vector<bool> (ms.trans.size(), false));
+    nTransNull += ms.trans.size();
+  }
+  const SeqPair emptySeqPair;
+  const EvaluatedMachine eval = evaluate (null, machine.getParamDefs (true));
+  const ForwardMatrix fwd (eval, emptySeqPair);
+  const BackwardMatrix back (eval, emptySeqPair);
+  size_t nTrans = 0;
+  StoredMatrix::TraceTerminator stopTrace = [&] (long, long, StateIndex s, size_t ti) {
+    if (transAllowed[s][ti]) return true;
+    transAllowed[s][ti] = true;
+    ++nTrans;
+    return false;
+  };
+  BackwardMatrix::PostTransQueue queue = back.postTransQueue (fwd);
+  const size_t nTransTarget = (size_t) ((double) nTransNull * maxProportionOfTransitionsToKeep);
+  while (!queue.empty() && (nTrans == 0 || nTrans < nTransTarget)) {
+    const BackwardMatrix::PostTrans pt = queue.top();
+    if (pt.weight < minPostProbOfSelectedTransitions && nTrans > 0) break;
+    queue.pop();
+    back.traceFrom (fwd, pt.inPos, pt.outPos, pt.src, pt.transIndex, stopTrace);
+  }
+  return transAllowed;
+}
+
 inline Machine loadMachine (const string& filename) { return Machine::fromFile (filename); }                              // api.h:15
 inline Machine loadMachineJson (const string& jsonString) { Machine m; m.readJson (Json::parse (jsonString)); return m; }  // api.h:16
 inline double forwardLogLike (const Machine& machine, const Params& params, const SeqPair& seqPair) {                      // api.h:21

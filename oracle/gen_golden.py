@@ -325,8 +325,34 @@ def post_trans_case():
     print("aux_post_trans               pairs=%d" % len(sym_pairs))
 
 
+def downsample_case():
+    """Machine::downsample (machine.cpp:2036-2082) on alignment lattices -- a generator and a recognizer of fixed sequences composed
+    around a transducer, toposorted, as `boss ... --downsample-size` sees them (boss.cpp:487-490): which transitions the selection
+    loop keeps (refdrv replays the loop with the reference's own primitives, the function only returns the pruned machine)."""
+    cases = []
+    for specs, params, size, prob in (
+            (["generate:10110", "file:" + os.path.join(REF, "t/machine/bitstutter-noise.json"), "recognize:1001110"], os.path.join(REF, "t/io/params.json"), 0.3, 0.0),
+            (["generate:10110", "file:" + os.path.join(REF, "t/machine/bitstutter-noise.json"), "recognize:1001110"], os.path.join(REF, "t/io/params.json"), 1.0, 0.02),
+            (["generate:ACGTTGCA", "preset:dnapsw", "recognize:ACTTGGCA"], None, 0.3, 0.0),
+            (["generate:GATTACAT", "preset:dnapsw", "recognize:GCTACATT"], None, 1.0, 1e-3)):
+        a = []
+        for sp in specs:
+            a += ["--machine", sp]
+        if params:
+            a += ["--params", params]
+        res = run(a + ["--downsample", "%g,%g" % (size, prob)])
+        cases.append({"what": " => ".join(sp.split("/")[-1] for sp in specs), "size": size, "prob": prob, "machine": res["machine"],
+                      "nTransitions": res["nTransitions"], "kept": res["kept"], "allowed": res["allowed"]})
+        print("aux_downsample               %-60s %d of %d transitions kept" % (cases[-1]["what"][:60], res["kept"], res["nTransitions"]))
+    with open(os.path.join(OUT, "aux_downsample.json"), "w") as fo:
+        json.dump({"note": "Machine::downsample of the reference: allowed[state][transIndex] after the selection loop, on the toposorted machine given here", "cases": cases},
+                  fo, separators=(",", ":"))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "posttrans":
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "downsample":
+        downsample_case()
+    elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "posttrans":
         post_trans_case()
     elif len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sample":
         sample_case()
@@ -338,3 +364,4 @@ if __name__ == "__main__":
         main()
         sample_case()
         post_trans_case()
+        downsample_case()

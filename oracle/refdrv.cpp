@@ -15,6 +15,8 @@
 // Usage:
 //   refdrv --machine SPEC [--machine SPEC ...] [--params FILE] [--no-defaults]
 //          ( --emit-machine
+//          | --downsample SIZE,PROB   (the machine is toposorted first, as boss --downsample-size does, boss.cpp:487-490: prints
+//                                      the toposorted symbolic machine and which transitions Machine::downsample keeps)
 //          | [--pairs FILE | --synth N,LI,LO,SEED] --do forward,rolling,viterbi,path,backward,counts,matrices
 //            [--threads T] [--quiet-results] )
 //   SPEC = preset:NAME | file:PATH | hmmer:PATH | hmmer-global:PATH ; several SPECs are composed
@@ -58,6 +60,8 @@ static Machine loadSpec (const string& spec) {
   const string arg = c == string::npos ? spec : spec.substr (c + 1);
   if (kind == "preset") return MachinePresets::makePreset (arg);
   if (kind == "file") return MachineLoader::fromFile (arg);
+  if (kind == "generate") return Machine::generator (splitToChars (arg), arg);      // boss.cpp:362-364
+  if (kind == "recognize") return Machine::recognizer (splitToChars (arg), arg);    // boss.cpp:384-386
   if (kind == "hmmer" || kind == "hmmer-global") {
     HmmerModel hmm;
     ifstream in (arg);
@@ -82,6 +86,7 @@ int main (int argc, char** argv) {
   vector<string> specs;
   string paramsFile, pairsFile, doList;
   bool useDefaults = true, emitMachine = false, quiet = false;
+  string downsampleSpec;
   long long synthN = 0, synthLi = 0, synthLo = 0, synthSeed = 0;
   int nThreads = 1;
   long long sampleSeed = 1;
@@ -92,6 +97,7 @@ int main (int argc, char** argv) {
     else if (f == "--params") paramsFile = next();
     else if (f == "--no-defaults") useDefaults = false;
     else if (f == "--emit-machine") emitMachine = true;
+    else if (f == "--downsample") downsampleSpec = next();
     else if (f == "--pairs") pairsFile = next();
     else if (f == "--synth") { if (sscanf (next().c_str(), "%lld,%lld,%lld,%lld", &synthN, &synthLi, &synthLo, &synthSeed) != 4) { cerr << "bad --synth" << endl; exit (1); } }
     else if (f == "--do") doList = next();
@@ -111,6 +117,52 @@ int main (int argc, char** argv) {
     Params seed;
     if (paramsFile.size())
       seed = JsonLoader<ParamAssign>::fromFile (paramsFile);
+
+    if (downsampleSpec.size()) {
+      // The selection loop of Machine::downsample (machine.cpp:2036-2082) through the reference's own primitives (the null machine,
+      // ForwardMatrix / BackwardMatrix of the empty pair, postTransQueue, traceFrom with the stop terminator), so that the mask it
+      // builds can be seen: the function itself only returns the machine after subgraph / ergodicMachine / eliminateRedundantStates.
+      double maxProportion = 1, minPostProb = 0;
+      if (sscanf (downsampleSpec.c_str(), "%lf,%lf", &maxProportion, &minPostProb) != 2) { cerr << "bad --downsample" << endl; exit (1); }
+      Machine sorted = machine.toposort();
+      sorted.funcs = sorted.funcs.combine (seed, true);      // the parameter values travel with the machine ("defs")
+      Machine null (sorted);
+      vguard<vguard<bool> > transAllowed;
+      for (auto& ms: null.state) {
+        for (auto& mt: ms.trans) mt.in = mt.out = string();
+        transAllowed.push_back (vguard<bool> (ms.trans.size()));
+      }
+      const SeqPair emptySeqPair;
+      const EvaluatedMachine nullEval (null, sorted.getParamDefs (true));
+      const ForwardMatrix fwd (nullEval, emptySeqPair);
+      const BackwardMatrix back (nullEval, emptySeqPair);
+      size_t nTrans = 0;
+      DPMatrix<IdentityIndexMapper>::TraceTerminator stopTrace = [&] (Envelope::InputIndex, Envelope::OutputIndex, StateIndex st, EvaluatedMachineState::TransIndex ti) {
+        if (transAllowed[st][ti]) return true;
+        transAllowed[st][ti] = true;
+        ++nTrans;
+        return false;
+      };
+      BackwardMatrix::PostTransQueue queue = back.postTransQueue (fwd);
+      const size_t nTransTarget = null.nTransitions() * maxProportion;
+      while (!queue.empty() && (nTrans == 0 || nTrans < nTransTarget)) {
+        const BackwardMatrix::PostTrans pt = queue.top();
+        if (pt.weight < minPostProb && nTrans > 0) break;
+        queue.pop();
+        back.traceFrom (null, fwd, pt.inPos, pt.outPos, pt.src, pt.transIndex, stopTrace);
+      }
+      const Machine kept = sorted.downsample (maxProportion, minPostProb);      // the reference's own call, for its transition count
+      cout << "{\"machine\":";
+      sorted.writeJson (cout, false, true);
+      cout << ",\n \"nTransitions\":" << null.nTransitions() << ",\"kept\":" << nTrans << ",\"downsampledMachineTransitions\":" << kept.nTransitions() << ",\n \"allowed\":[";
+      for (size_t st = 0; st < transAllowed.size(); ++st) {
+        cout << (st ? "," : "") << "[";
+        for (size_t ti = 0; ti < transAllowed[st].size(); ++ti) cout << (ti ? "," : "") << (transAllowed[st][ti] ? 1 : 0);
+        cout << "]";
+      }
+      cout << "]}" << endl;
+      return 0;
+    }
     const Params params = machine.getParamDefs (useDefaults).combine (seed, true);   // --params overrides the -U defaults
     const EvaluatedMachine eval (machine, params);
 

@@ -140,6 +140,25 @@ def test_cli_post_trans_queue_and_trace_from_match_the_reference():
     assert traced >= 2
 
 
+@pytest.mark.gpu
+def test_cli_downsample_keeps_the_transitions_the_reference_keeps():
+    """Machine::downsample's selection (machine.cpp:2036-2082) in the host mirror (downsampleTransitions: the null machine's Forward and
+    Backward for the empty pair on the device, postTransQueue, traceFrom with the stop terminator) on four alignment lattices the
+    reference built and toposorted: the same transitions kept, by proportion and by posterior threshold."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_downsample.json")) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        mf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
+        json.dump(c["machine"], mf)
+        mf.close()
+        r = subprocess.run([_cli(), "--machine", mf.name, "-U", "--downsample-size", repr(c["size"]), "--downsample-prob", repr(c["prob"])],
+                           capture_output=True, text=True, check=True)
+        os.unlink(mf.name)
+        got = json.loads(r.stdout)
+        assert got["nTransitions"] == c["nTransitions"], c["what"]
+        assert got["kept"] == c["kept"] and got["allowed"] == c["allowed"], (c["what"], got["kept"], c["kept"])
+
+
 def test_cli_envelopes_match_the_reference_goldens():
     """Makefile:450-462 test-env: Envelope::initFull / initPath / initPathArea of the host mirror against
     t/expect/*_env.json (CPU only: no device involved)."""
