@@ -726,8 +726,9 @@ public:
   // ForwardMatrix::samplePath (forward.cpp:17-23): stochastic traceback, candidate weights exp(cell + logWeight),
   // random_index over them with the caller's mt19937 (dpmatrix.defs.h:176-186, util.h:151-165)
   template<class AnyMachine> MachinePath samplePath (const AnyMachine&, std::mt19937& rng) const { return samplePath (rng); }
-  MachinePath samplePath (std::mt19937& rng) const {
-    auto select = [&] (const vector<double>& logWeights) -> size_t {
+  // DPMatrix::randomTransSelector (dpmatrix.defs.h:176-186): draws a candidate in proportion to exp (log-weight)
+  static TransSelector randomTransSelector (std::mt19937& rng) {
+    return [&rng] (const vector<double>& logWeights) -> size_t {
       vector<double> w;
       double norm = 0;
       for (double lw: logWeights) { w.push_back (exp (lw)); norm += w.back(); }
@@ -737,8 +738,8 @@ public:
       for (size_t n = 0; n < w.size(); ++n) if ((variate -= w[n]) <= 0) return n;
       return w.size();
     };
-    return traceBackWith (select, (int) machine.nStates() - 1);
   }
+  MachinePath samplePath (std::mt19937& rng) const { return traceBackWith (randomTransSelector (rng), (int) machine.nStates() - 1); }
 private:
   double ll = 0;
   void fill() {

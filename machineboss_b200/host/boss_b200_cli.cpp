@@ -90,6 +90,8 @@ int main (int argc, char** argv) {
     int postTransTop = 0;
     bool doDownsample = false;
     double downsampleSize = 1., downsampleProb = 0.;
+    int downsamplePaths = 0;      // > 0: stochastic, that many paths; -1: stochastic, up to nStates paths until the fraction is covered
+    unsigned rngSeed = 5489u;     // mt19937's default seed
     bool fastIngest = false, ingestOnly = false;
     string pairedFastaIn, pairedFastaOut;
     for (int a = 1; a < argc; ++a) {
@@ -116,6 +118,9 @@ int main (int argc, char** argv) {
       else if (f == "--sample-paths") { doSample = true; sampleSeed = atoll (next().c_str()); }
       else if (f == "--downsample-size") { doDownsample = true; downsampleSize = atof (next().c_str()); }      // boss.cpp:487-490: which transitions Machine::downsample keeps
       else if (f == "--downsample-prob") { doDownsample = true; downsampleProb = atof (next().c_str()); }
+      else if (f == "--downsample-path") { doDownsample = true; downsamplePaths = atoi (next().c_str()); }      // boss.cpp:491-493: sample this many paths (seed: --seed)
+      else if (f == "--downsample-frac") { doDownsample = true; downsamplePaths = -1; downsampleSize = atof (next().c_str()); }      // boss.cpp:494-497: sample until this fraction is covered
+      else if (f == "--seed") rngSeed = (unsigned) atoll (next().c_str());
       else if (f == "--post-trans") postTransTop = atoi (next().c_str());      // the top of BackwardMatrix::postTransQueue and the trace from its first entry
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "--fast-ingest") fastIngest = true;      // -D lists go straight to packed tokens (boss_b200_ingest.h); -L / -V only
@@ -171,7 +176,9 @@ int main (int argc, char** argv) {
       if (!symbolic) throw runtime_error ("--downsample-size / --downsample-prob need a symbolic --machine");
       Machine withParams = machine;
       withParams.funcs = machine.funcs.combine (seed, true);
-      const vector<vector<bool>> allowed = downsampleTransitions (withParams, downsampleSize, downsampleProb);
+      std::mt19937 rng (rngSeed);
+      const vector<vector<bool>> allowed = downsamplePaths ? stochasticDownsampleTransitions (withParams, rng, downsampleSize, downsamplePaths > 0 ? downsamplePaths : (int) machine.nStates())
+                                                           : downsampleTransitions (withParams, downsampleSize, downsampleProb);
       size_t kept = 0, total = 0;
       for (const auto& row: allowed) for (bool v: row) { ++total; if (v) ++kept; }
       cout << "{\"nTransitions\":" << total << ",\"kept\":" << kept << ",\"allowed\":[";

@@ -605,6 +605,32 @@ inline vector<vector<bool>> downsampleTransitions (const Machine& machine, doubl
   return transAllowed;
 }
 
+// The selection of Machine::stochasticDownsample (machine.cpp:2084-2128): paths are drawn through the null machine's Forward matrix
+// (randomTransSelector, the caller's mt19937) until maxProportion of the transitions lie on a sampled path or maxPaths are drawn.
+inline vector<vector<bool>> stochasticDownsampleTransitions (const Machine& machine, std::mt19937& rng, double maxProportionOfTransitionsToKeep, int maxNumberOfPathsToSample) {
+  Machine null (machine);
+  vector<vector<bool>> transAllowed;
+  size_t nTransNull = 0;
+  for (auto& ms: null.state) {
+    for (auto& mt: ms.trans) { mt.in = mt.out = string(); if (mt.dest <= (StateIndex) (&ms - &null.state[0])) throw runtime_error ("Machine must be acyclic & topologically sorted before stochastic downsampling can take place"); }
+    transAllowed.push_back (vector<bool> (ms.trans.size(), false));
+    nTransNull += ms.trans.size();
+  }
+  const size_t nTransTarget = (size_t) ((double) nTransNull * maxProportionOfTransitionsToKeep);
+  const SeqPair emptySeqPair;
+  const EvaluatedMachine eval = evaluate (null, machine.getParamDefs (true));
+  const ForwardMatrix fwd (eval, emptySeqPair);
+  size_t nTrans = 0;
+  StoredMatrix::TraceTerminator neverStopTrace = [&] (long, long, StateIndex s, size_t ti) {
+    if (!transAllowed[s][ti]) { transAllowed[s][ti] = true; ++nTrans; }
+    return false;
+  };
+  const StoredMatrix::TransSelector selectRandomTrans = ForwardMatrix::randomTransSelector (rng);
+  for (int nPath = 0; nPath < maxNumberOfPathsToSample && nTrans < nTransTarget; ++nPath)
+    fwd.traceBack (0, 0, (StateIndex) null.nStates() - 1, neverStopTrace, selectRandomTrans);
+  return transAllowed;
+}
+
 inline Machine loadMachine (const string& filename) { return Machine::fromFile (filename); }                              // api.h:15
 inline Machine loadMachineJson (const string& jsonString) { Machine m; m.readJson (Json::parse (jsonString)); return m; }  // api.h:16
 inline double forwardLogLike (const Machine& machine, const Params& params, const SeqPair& seqPair) {                      // api.h:21

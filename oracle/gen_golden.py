@@ -344,6 +344,21 @@ def downsample_case():
         cases.append({"what": " => ".join(sp.split("/")[-1] for sp in specs), "size": size, "prob": prob, "machine": res["machine"],
                       "nTransitions": res["nTransitions"], "kept": res["kept"], "allowed": res["allowed"]})
         print("aux_downsample               %-60s %d of %d transitions kept" % (cases[-1]["what"][:60], res["kept"], res["nTransitions"]))
+    # Machine::stochasticDownsample (machine.cpp:2084-2128): paths sampled with mt19937 (seed) -- by number of paths (boss
+    # --downsample-path) and until a fraction of the transitions is covered, at most nStates paths (--downsample-frac)
+    for specs, params, frac, paths, seed in (
+            (["generate:ACGTTGCA", "preset:dnapsw", "recognize:ACTTGGCA"], None, 1.0, 5, 7),
+            (["generate:10110", "file:" + os.path.join(REF, "t/machine/bitstutter-noise.json"), "recognize:1001110"], os.path.join(REF, "t/io/params.json"), 0.5, -1, 3)):
+        a = []
+        for sp in specs:
+            a += ["--machine", sp]
+        if params:
+            a += ["--params", params]
+        n_states = len(run(a + ["--downsample", "1,0"])["machine"]["state"])
+        res = run(a + ["--downsample-path", "%g,%d,%d" % (frac, paths if paths > 0 else n_states, seed)])
+        cases.append({"what": " => ".join(sp.split("/")[-1] for sp in specs), "stochastic": True, "size": frac, "paths": paths, "seed": seed, "machine": res["machine"],
+                      "nTransitions": res["nTransitions"], "kept": res["kept"], "allowed": res["allowed"]})
+        print("aux_downsample (sampled)     %-60s %d of %d transitions on %d paths" % (cases[-1]["what"][:60], res["kept"], res["nTransitions"], res["paths"]))
     with open(os.path.join(OUT, "aux_downsample.json"), "w") as fo:
         json.dump({"note": "Machine::downsample of the reference: allowed[state][transIndex] after the selection loop, on the toposorted machine given here", "cases": cases},
                   fo, separators=(",", ":"))

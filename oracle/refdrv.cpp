@@ -86,7 +86,7 @@ int main (int argc, char** argv) {
   vector<string> specs;
   string paramsFile, pairsFile, doList;
   bool useDefaults = true, emitMachine = false, quiet = false;
-  string downsampleSpec;
+  string downsampleSpec, downsamplePathSpec;
   long long synthN = 0, synthLi = 0, synthLo = 0, synthSeed = 0;
   int nThreads = 1;
   long long sampleSeed = 1;
@@ -98,6 +98,7 @@ int main (int argc, char** argv) {
     else if (f == "--no-defaults") useDefaults = false;
     else if (f == "--emit-machine") emitMachine = true;
     else if (f == "--downsample") downsampleSpec = next();
+    else if (f == "--downsample-path") downsamplePathSpec = next();      // FRACTION,PATHS,SEED: Machine::stochasticDownsample's selection
     else if (f == "--pairs") pairsFile = next();
     else if (f == "--synth") { if (sscanf (next().c_str(), "%lld,%lld,%lld,%lld", &synthN, &synthLi, &synthLo, &synthSeed) != 4) { cerr << "bad --synth" << endl; exit (1); } }
     else if (f == "--do") doList = next();
@@ -117,6 +118,46 @@ int main (int argc, char** argv) {
     Params seed;
     if (paramsFile.size())
       seed = JsonLoader<ParamAssign>::fromFile (paramsFile);
+
+    if (downsamplePathSpec.size()) {
+      // The selection loop of Machine::stochasticDownsample (machine.cpp:2084-2128): paths sampled through the null machine's
+      // Forward matrix with randomTransSelector (mt19937 (SEED)) until the fraction of transitions is covered or PATHS are drawn.
+      double maxProportion = 1;
+      int maxPaths = 1;
+      long long seedValue = 1;
+      if (sscanf (downsamplePathSpec.c_str(), "%lf,%d,%lld", &maxProportion, &maxPaths, &seedValue) != 3) { cerr << "bad --downsample-path" << endl; exit (1); }
+      Machine sorted = machine.toposort();
+      sorted.funcs = sorted.funcs.combine (seed, true);
+      Machine null (sorted);
+      vguard<vguard<bool> > transAllowed;
+      for (auto& ms: null.state) {
+        for (auto& mt: ms.trans) mt.in = mt.out = string();
+        transAllowed.push_back (vguard<bool> (ms.trans.size()));
+      }
+      const size_t nTransTarget = null.nTransitions() * maxProportion;
+      const SeqPair emptySeqPair;
+      const EvaluatedMachine nullEval (null, sorted.getParamDefs (true));
+      const ForwardMatrix fwd (nullEval, emptySeqPair);
+      size_t nTrans = 0, nPath = 0;
+      DPMatrix<IdentityIndexMapper>::TraceTerminator neverStopTrace = [&] (Envelope::InputIndex, Envelope::OutputIndex, StateIndex st, EvaluatedMachineState::TransIndex ti) {
+        if (!transAllowed[st][ti]) { transAllowed[st][ti] = true; ++nTrans; }
+        return false;
+      };
+      mt19937 rng ((unsigned) seedValue);
+      ForwardMatrix::TransSelector selectRandomTrans = fwd.randomTransSelector (rng);
+      for (; nPath < (size_t) maxPaths && nTrans < nTransTarget; ++nPath)
+        fwd.traceBack (null, fwd.inLen, fwd.outLen, null.endState(), neverStopTrace, selectRandomTrans);
+      cout << "{\"machine\":";
+      sorted.writeJson (cout, false, true);
+      cout << ",\n \"nTransitions\":" << null.nTransitions() << ",\"kept\":" << nTrans << ",\"paths\":" << nPath << ",\n \"allowed\":[";
+      for (size_t st = 0; st < transAllowed.size(); ++st) {
+        cout << (st ? "," : "") << "[";
+        for (size_t ti = 0; ti < transAllowed[st].size(); ++ti) cout << (ti ? "," : "") << (transAllowed[st][ti] ? 1 : 0);
+        cout << "]";
+      }
+      cout << "]}" << endl;
+      return 0;
+    }
 
     if (downsampleSpec.size()) {
       // The selection loop of Machine::downsample (machine.cpp:2036-2082) through the reference's own primitives (the null machine,

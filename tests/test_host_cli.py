@@ -144,15 +144,20 @@ def test_cli_post_trans_queue_and_trace_from_match_the_reference():
 def test_cli_downsample_keeps_the_transitions_the_reference_keeps():
     """Machine::downsample's selection (machine.cpp:2036-2082) in the host mirror (downsampleTransitions: the null machine's Forward and
     Backward for the empty pair on the device, postTransQueue, traceFrom with the stop terminator) on four alignment lattices the
-    reference built and toposorted: the same transitions kept, by proportion and by posterior threshold."""
+    reference built and toposorted: the same transitions kept, by proportion and by posterior threshold -- and, for the stochastic
+    form (paths sampled through the Forward matrix), the same transitions visited for the same mt19937 seed."""
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_downsample.json")) as f:
         g = json.load(f)
     for c in g["cases"]:
         mf = tempfile.NamedTemporaryFile("w", suffix=".json", delete=False)
         json.dump(c["machine"], mf)
         mf.close()
-        r = subprocess.run([_cli(), "--machine", mf.name, "-U", "--downsample-size", repr(c["size"]), "--downsample-prob", repr(c["prob"])],
-                           capture_output=True, text=True, check=True)
+        if c.get("stochastic"):      # Machine::stochasticDownsample: paths drawn with the reference's mt19937 sequence
+            how = ["--downsample-path", str(c["paths"])] if c["paths"] > 0 else ["--downsample-frac", repr(c["size"])]
+            r = subprocess.run([_cli(), "--machine", mf.name, "-U", "--seed", str(c["seed"])] + how, capture_output=True, text=True, check=True)
+        else:
+            r = subprocess.run([_cli(), "--machine", mf.name, "-U", "--downsample-size", repr(c["size"]), "--downsample-prob", repr(c["prob"])],
+                               capture_output=True, text=True, check=True)
         os.unlink(mf.name)
         got = json.loads(r.stdout)
         assert got["nTransitions"] == c["nTransitions"], c["what"]
