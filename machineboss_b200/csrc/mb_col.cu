@@ -114,7 +114,10 @@ static bool col_classify (const mb_machine* m, int a0, int P, int K, ColProg& ou
     else if (ws == 0 && wd == 2) carriedSet.insert (s);
     else return false;
   }
-  for (auto& r: raws) keyGroup[Key (r.kind == 2 ? -1 - r.src : r.src, r.kind, r.dst, r.emit ? 1 : 0)] = 0;
+  for (auto& r: raws) {
+    keyGroup[Key (r.kind == 2 ? -1 - r.src : r.src, r.kind, r.dst, r.emit ? 1 : 0)] = 0;
+    if (keyGroup.size() > 640) return false;      // (a phase that needs this many groups is no periodic reading of the machine: give up on it early)
+  }
   out.P = P; out.a0 = a0; out.K = K; out.nPre = a0; out.nSuf = S - end;
   out.nC = (int) carriedSet.size(); out.nA = (int) accSet.size();
   out.nCell = out.nC + P + out.nA;
@@ -224,6 +227,7 @@ static void col_analyse (const mb_machine* m, ColProg& best) {
   const int S = m->S;
   if (m->nIn != 0) { best.why = "the machine reads an input sequence"; return; }
   if (S < 200) { best.why = "fewer than 200 states"; return; }
+  if (m->T > 2000000) { best.why = "more than 2 000 000 transitions"; return; }
   std::vector<std::pair<int, int>> sig ((size_t) S, std::make_pair (0, 0));
   for (int64_t t = 0; t < m->T; ++t) { ++sig[m->src[t]].first; if (m->out[t]) ++sig[m->src[t]].second; }
   const int lo = S / 4, hi = 3 * S / 4;
