@@ -34,6 +34,11 @@ typedef struct mb_batch mb_batch;
  * device without locking (the reference has no threads; its only global state is its logger and caches) ---- */
 const char* mb_last_error (void);                 /* message of the last failing call on this thread */
 int mb_version (void);
+
+/* A directory where the library keeps the modules it compiles at run time for a machine's structure (NVRTC, sm_100a), keyed by a
+ * hash of the generated source: a later process that creates a machine of the same structure loads the module instead of
+ * compiling it (seconds per machine).  NULL or "": no cache (the default).  Process-wide; the directory must exist. */
+int mb_set_kernel_cache_dir (const char* dir);
 int mb_device_count (int* count);                  /* cudaGetDeviceCount */
 int mb_set_device (int device);                    /* device used by handles this thread creates afterwards (default 0) */
 /* Tuning / diagnostic knobs (integers; MB_OPTION_UNSET restores the built-in choice).  mb_set_option sets the

@@ -18,7 +18,7 @@ ENGINE_GENERIC, ENGINE_JIT, ENGINE_WIDE = 0, 1, 2
 _lib = None
 
 # every symbol include/machineboss_b200.h declares
-SYMBOLS = ["mb_last_error", "mb_version", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
+SYMBOLS = ["mb_last_error", "mb_version", "mb_set_kernel_cache_dir", "mb_device_count", "mb_set_device", "mb_set_engine", "mb_set_option", "mb_machine_set_option",
            "mb_machine_create", "mb_machine_update_weights", "mb_machine_info", "mb_machine_destroy",
            "mb_batch_create", "mb_batch_destroy", "mb_batch_trim", "mb_batch_set_envelopes", "mb_forward", "mb_backward", "mb_viterbi",
            "mb_viterbi_paths", "mb_viterbi_paths_narrow", "mb_viterbi_paths_start", "mb_batch_wait", "mb_counts", "mb_matrix", "mb_last_kernel_ms", "mb_last_redo", "mb_jit_compile_check", "mb_jit_host_tables", "mb_lane_emulate", "mb_col_emulate",
@@ -41,6 +41,7 @@ def lib():
         L.mb_last_error.restype = ctypes.c_char_p
         L.mb_last_error.argtypes = []
         L.mb_version.restype = ctypes.c_int
+        L.mb_set_kernel_cache_dir.argtypes = [ctypes.c_char_p]
         L.mb_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
         L.mb_set_device.argtypes = [ctypes.c_int]
         L.mb_set_engine.argtypes = [ctypes.c_int]
@@ -119,6 +120,11 @@ def set_engine(e: int) -> None:
 
 
 OPTION_UNSET = -2147483648
+
+
+def set_kernel_cache_dir(path) -> None:
+    """Keep / look up the run-time compiled modules in this directory (None: no cache)."""
+    _check(lib().mb_set_kernel_cache_dir(path.encode() if path else None))
 
 
 def set_option(name: str, value) -> None:

@@ -315,6 +315,8 @@ extern "C" {
 const char* mb_last_error (void) { return g_error.c_str(); }
 int mb_version (void) { return 100; }
 
+int mb_set_kernel_cache_dir (const char* dir) { rt_set_cache_dir (dir); return 0; }
+
 int mb_device_count (int* count) {
   MB_CUDA (cudaGetDeviceCount (count));
   return 0;

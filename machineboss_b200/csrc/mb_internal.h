@@ -214,6 +214,7 @@ int big_viterbi (mb_machine* m, mb_batch* b, double* score, int64_t* pathLen);
 int wide_forward_log_subset (mb_machine* m, mb_batch* b, const std::vector<int64_t>& pairs, double* dResult);      // mb_wide.cu
 
 // run-time compilation plumbing shared by the generated engines (mb_jit.cu)
+void rt_set_cache_dir (const char* dir);      // compiled modules are kept in / taken from this directory (null or empty: no cache)
 int rt_compile (const std::string& source, const char* dumpSuffix, std::vector<char>& cubin, std::string* log);
 int rt_load (const std::vector<char>& cubin, void** module);
 void rt_unload (void* module);

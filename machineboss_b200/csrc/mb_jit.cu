@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -598,7 +599,42 @@ bool jit_supported (const mb_machine* m, std::string* why) {
   return true;
 }
 
+// A directory of compiled modules (mb_set_kernel_cache_dir): <FNV-1a 64 of the compiler options, the CUDA version this library was
+// built with and the generated source>.cubin.  A process that meets a machine structure it -- or an earlier process -- has
+// compiled before loads the module instead of running NVRTC (dnapsw: 4 s of compilation per process otherwise, which is most of
+// what a command-line call of one batch takes).  Off unless a directory is set.
+static std::mutex g_cacheMutex;
+static std::string g_cacheDir;
+void rt_set_cache_dir (const char* dir) { std::lock_guard<std::mutex> lock (g_cacheMutex); g_cacheDir = dir ? dir : ""; }
+static std::string cache_path (const std::string& source, const char* const* opts, int nOpts) {
+  std::string dir;
+  { std::lock_guard<std::mutex> lock (g_cacheMutex); dir = g_cacheDir; }
+  if (dir.empty()) return dir;
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&] (const char* p, size_t n) { for (size_t q = 0; q < n; ++q) { h ^= (unsigned char) p[q]; h *= 1099511628211ull; } };
+  for (int q = 0; q < nOpts; ++q) mix (opts[q], strlen (opts[q]) + 1);
+  const int version = CUDART_VERSION;
+  mix ((const char*) &version, sizeof version);
+  mix (source.data(), source.size());
+  char name[40];
+  snprintf (name, sizeof name, "/%016llx.cubin", h);
+  return dir + name;
+}
+
 static int nvrtc_compile (const std::string& source, const char* dumpSuffix, std::vector<char>& cubin, std::string* logOut) {
+  const char* cacheOpts[] = { "--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "--ptxas-options=-v", "-default-device" };
+  const std::string cached = cache_path (source, cacheOpts, 5);
+  if (!cached.empty()) {
+    if (FILE* f = fopen (cached.c_str(), "rb")) {
+      fseek (f, 0, SEEK_END);
+      const long n = ftell (f);
+      fseek (f, 0, SEEK_SET);
+      cubin.resize (n > 0 ? (size_t) n : 0);
+      const bool ok = n > 0 && fread (cubin.data(), 1, (size_t) n, f) == (size_t) n;
+      fclose (f);
+      if (ok) { if (logOut) *logOut = "(module taken from the kernel cache: " + cached + ")"; return 0; }
+    }
+  }
   if (!load_nvrtc()) return 1;
   nvrtcProgram prog;
   if (g_nvrtc.CreateProgram (&prog, source.c_str(), "mb_jit_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { set_error ("nvrtcCreateProgram failed"); return 1; }
@@ -621,6 +657,14 @@ static int nvrtc_compile (const std::string& source, const char* dumpSuffix, std
   cubin.resize (n);
   g_nvrtc.GetCUBIN (prog, cubin.data());
   g_nvrtc.DestroyProgram (&prog);
+  if (!cached.empty()) {      // written under another name first: a reader never sees half a file
+    const std::string tmp = cached + ".tmp" + std::to_string ((long long) getpid());
+    if (FILE* f = fopen (tmp.c_str(), "wb")) {
+      const bool ok = fwrite (cubin.data(), 1, n, f) == n;
+      fclose (f);
+      if (!ok || rename (tmp.c_str(), cached.c_str())) remove (tmp.c_str());
+    }
+  }
   if (const char* d = getenv ("MB_JIT_DUMP")) { FILE* f = fopen ((std::string (d) + dumpSuffix + ".cubin").c_str(), "wb"); if (f) { fwrite (cubin.data(), 1, n, f); fclose (f); } }
   return 0;
 }

@@ -33,6 +33,7 @@
 
 #include <chrono>
 
+#include <sys/stat.h>
 #include "boss_b200_fit.h"
 #include "boss_b200_ingest.h"
 
@@ -92,6 +93,7 @@ int main (int argc, char** argv) {
     double downsampleSize = 1., downsampleProb = 0.;
     int downsamplePaths = 0;      // > 0: stochastic, that many paths; -1: stochastic, up to nStates paths until the fraction is covered
     unsigned rngSeed = 5489u;     // mt19937's default seed
+    string kernelCache;           // empty: none
     bool fastIngest = false, ingestOnly = false;
     string pairedFastaIn, pairedFastaOut;
     for (int a = 1; a < argc; ++a) {
@@ -121,6 +123,7 @@ int main (int argc, char** argv) {
       else if (f == "--downsample-path") { doDownsample = true; downsamplePaths = atoi (next().c_str()); }      // boss.cpp:491-493: sample this many paths (seed: --seed)
       else if (f == "--downsample-frac") { doDownsample = true; downsamplePaths = -1; downsampleSize = atof (next().c_str()); }      // boss.cpp:494-497: sample until this fraction is covered
       else if (f == "--seed") rngSeed = (unsigned) atoll (next().c_str());
+      else if (f == "--kernel-cache") kernelCache = next();      // keep the compiled kernels in this directory between runs (e.g. ~/.cache/machineboss_b200)
       else if (f == "--post-trans") postTransTop = atoi (next().c_str());      // the top of BackwardMatrix::postTransQueue and the trace from its first entry
       else if (f == "--device") mbCheck (mb_set_device (atoi (next().c_str())));
       else if (f == "--fast-ingest") fastIngest = true;      // -D lists go straight to packed tokens (boss_b200_ingest.h); -L / -V only
@@ -130,6 +133,14 @@ int main (int argc, char** argv) {
       else if (f == "--gpus") hostGpuLimit() = atoi (next().c_str());      // lists of pairs use this many GPUs (default: every visible one)
       else if (f == "-h" || f == "--help") { cout << "usage: boss_b200 --evaluated-machine M.json [-D pairs.json | --input-fasta X --output-fasta Y | --input-chars S --output-chars S] -L|-V|-A|-C" << endl; return 0; }
       else throw runtime_error ("unknown option " + f);
+    }
+    // The kernels a machine's structure is compiled into (NVRTC, seconds) are kept between runs of this program, as a command-line
+    // call is one process per batch -- when --kernel-cache names a directory (the library caches nothing unless told to).
+    if (!kernelCache.empty()) {
+      string made;
+      for (size_t q = 1; q <= kernelCache.size(); ++q)
+        if (q == kernelCache.size() || kernelCache[q] == '/') { made = kernelCache.substr (0, q); mkdir (made.c_str(), 0755); }      // (errors show up as cache misses)
+      mb_set_kernel_cache_dir (kernelCache.c_str());
     }
     if (envMode.size()) {
       SeqPairList data;

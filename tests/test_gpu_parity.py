@@ -724,6 +724,41 @@ def test_silent_self_loop_on_the_start_state(engine):
     assert cnt[ins] == 0
 
 
+def test_machines_from_the_kernel_cache_give_the_same_results(tmp_path):
+    """mb_set_kernel_cache_dir: the second machine of a structure is loaded from the cubin the first one left in the directory -- and
+    sweeps, traces back and counts like a freshly compiled one (JIT engine, its fitted module, and the column engine)."""
+    import os
+    import time
+    capi = _capi()
+    fm = FlatMachine.from_json(load_golden("dnapsw_peaked")["machine"])
+    pairs = [(synth_tokens(97, k, 0, 300 - (k % 5), 4), synth_tokens(97, k, 1, 280 + (k % 9), 4)) for k in range(300)]
+    b = capi.Batch(pairs)
+    prof = synthetic_profile(n_nodes=70)
+    reads = capi.Batch([(np.zeros(0, np.uint8), synth_tokens(98, k, 1, 20 + k, prof.n_out)) for k in range(40)])
+    capi.set_kernel_cache_dir(str(tmp_path))
+    try:
+        out = []
+        for trial in range(2):
+            t0 = time.time()
+            m = make_machine(capi, fm, 1)
+            p = make_machine(capi, prof, 2)
+            made = time.time() - t0
+            ll = capi.forward(m, b)      # (300 uniform pairs: the fitted module is compiled -- or found -- here)
+            sc, paths = capi.viterbi(m, b)
+            cnt, _ = capi.counts(m, b)
+            out.append((ll, sc, paths, cnt, capi.forward(p, reads), capi.viterbi(p, reads, paths=False), made))
+            m.close(); p.close()
+        n_files = len([f for f in os.listdir(str(tmp_path)) if f.endswith(".cubin")])
+    finally:
+        capi.set_kernel_cache_dir(None)
+    assert n_files >= 4      # the JIT engine's two modules, the fitted one, the column engine's
+    a, c = out
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]) and np.array_equal(a[4], c[4]) and np.array_equal(a[5], c[5])
+    np.testing.assert_allclose(a[3], c[3], rtol=1e-12)      # (counts are summed with atomics: equal to rounding, run to run)
+    assert all(np.array_equal(x, y) for x, y in zip(a[2], c[2]))
+    assert c[6] < 0.5 * a[6], (a[6], c[6])      # creating the machines again took less than half as long
+
+
 def test_group_handles_may_be_destroyed_in_any_order():
     """An interpreter at exit (or a caller's error path) may destroy the group before its machines and batches: the group is
     kept alive until its last child is gone."""

@@ -49,3 +49,27 @@ def test_score_module_at_a_fitted_width_compiles(name, cols):
     assert "MB_C = %d" % cols in log
     tail = log[log.index("Viterbi module"):]
     assert "mb_k_viterbi" in tail and "mb_k_forward_lin" in tail
+
+
+def test_kernel_cache_directory(tmp_path):
+    """mb_set_kernel_cache_dir: the modules compiled for a machine structure are kept as <hash of the source>.cubin, and the next
+    compilation of the same structure -- in this or a later process -- takes them from there instead of running NVRTC."""
+    import os
+    import time
+    from machineboss_b200 import capi
+    fm = FlatMachine.from_json(load_golden("unitindel")["machine"])
+    args = (fm.n_states, fm.n_in, fm.n_out, fm.src, fm.dst, fm.tin, fm.tout)
+    capi.set_kernel_cache_dir(str(tmp_path))
+    try:
+        t0 = time.time()
+        first = capi.jit_compile_check(*args)
+        t1 = time.time()
+        again = capi.jit_compile_check(*args)
+        t2 = time.time()
+    finally:
+        capi.set_kernel_cache_dir(None)
+    files = sorted(os.listdir(str(tmp_path)))
+    assert len(files) >= 1 and all(f.endswith(".cubin") and len(f) == 22 for f in files), files
+    assert "kernel cache" not in first and "kernel cache" in again
+    assert (t2 - t1) < 0.5 * (t1 - t0)
+    assert "kernel cache" not in capi.jit_compile_check(*args)      # switched off again: compiled
