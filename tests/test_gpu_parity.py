@@ -793,7 +793,8 @@ def _check_group_against_single(capi, devices):
     dev, cells = gb.shard()
     assert len(dev) == len(pairs) and set(dev.tolist()) <= set(range(64))
     if g.n_devices > 1:
-        assert len(set(dev.tolist())) == g.n_devices and cells.max() / cells.mean() < 1.2      # every device has work, evenly
+        biggest = max((len(x) + 1.0) * (len(y) + 1.0) for x, y in pairs)      # (one pair cannot be split: on 8 devices it outweighs a device's share)
+        assert len(set(dev.tolist())) == g.n_devices and cells.max() <= max(1.2 * cells.mean(), 1.0001 * biggest)      # every device has work, evenly
     ll = capi.group_forward(gm, gb)
     sc, paths = capi.group_viterbi(gm, gb)
     cnt, cll = capi.group_counts(gm, gb)
