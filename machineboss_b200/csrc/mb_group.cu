@@ -13,6 +13,7 @@
 // memory, over NVLink.  NCCL is resolved at run time (libnccl.so.2); a group of one device, or a box without
 // the library, adds the per-device vectors on the host instead (mb_group_info reports which).
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstring>
@@ -200,7 +201,14 @@ int mb_group_create (mb_group** out, const int32_t* devices, int32_t nDevices) {
   for (int d: devs) g->workers.emplace_back (new Worker (d));
   if (devs.size() > 1 && load_nccl()) {
     g->comms.assign (devs.size(), nullptr);
+    // NCCL announces itself on STANDARD OUTPUT when NCCL_DEBUG is set in the environment ("NCCL version ..."): a program whose
+    // standard output is its result (boss_b200 prints JSON) must not have that mixed in, so file descriptor 1 points at
+    // standard error while the communicators are made
+    fflush (stdout);
+    const int savedOut = dup (1);
+    if (savedOut >= 0) dup2 (2, 1);
     const int r = g_nccl.CommInitAll (g->comms.data(), (int) devs.size(), devs.data());
+    if (savedOut >= 0) { fflush (stdout); dup2 (savedOut, 1); close (savedOut); }
     if (r != 0) g->comms.clear();      // no peer path between these devices: add on the host
   }
   *out = g;
